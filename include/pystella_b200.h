@@ -1,0 +1,182 @@
+/*
+ * pystella_b200 -- C ABI of the B200-native lattice-PDE hot path.
+ *
+ * This is the drop-in boundary underneath the Python classes that mirror
+ * zachjweiner/pystella (Stepper / FiniteDifferencer / DomainDecomposition /
+ * Reduction).  pystella itself has no FFI layer (every kernel is generated at
+ * run time by loopy -> OpenCL), so each entry point cites the reference
+ * *Python* call site whose device work it replaces (paths relative to the
+ * reference checkout).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless stated otherwise;
+ *   - arrays are C-ordered with z fastest; "padded" arrays have shape
+ *     (Nx+2h, Ny+2h, Nz+2h), "unpadded" arrays (Nx, Ny, Nz)
+ *     (pystella/field/__init__.py:579-606);
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
+ *   - functions return 0 on success; on failure a non-zero code is returned
+ *     and psb_last_error() describes it (thread-local string);
+ *   - nothing here allocates device memory: workspaces are passed in.
+ */
+#ifndef PYSTELLA_B200_H
+#define PYSTELLA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PSB_ABI_VERSION 1
+
+#define PSB_F64 0
+#define PSB_F32 1
+
+#define PSB_MAX_SCALARS 4      /* fields per ScalarSector handled by one launch   */
+#define PSB_MAX_TERMS 16       /* monomials of dV/df_n per field                  */
+#define PSB_MAX_RED_ARRAYS 8   /* distinct input arrays of one reduction launch   */
+#define PSB_MAX_RED_TERMS 32   /* monomials over all outputs of one reduction     */
+#define PSB_MAX_RED_OUTPUTS 16 /* reductions per launch                           */
+
+const char* psb_last_error(void);
+int psb_abi_version(void);
+/* Compiled with FMA contraction disabled (bit-comparable with the oracle)? */
+int psb_strict_fp(void);
+
+/* ------------------------------------------------------------------------
+ * Scalar-sector Runge-Kutta stage.
+ *
+ * One launch performs, for every field n < nscalars and every site of the
+ * x-range [x_begin, x_end) x [0,Ny) x [0,Nz):
+ *
+ *     rhs_f    = dfdt_n
+ *     rhs_dfdt = lap(f_n) - 2*hubble*dfdt_n - a^2 * dV/df_n(f_0..f_{n-1})
+ *     kf_n    <- A*kf_n    + dt*rhs_f    ;  f_n    <- f_n    + B*kf_n
+ *     kdfdt_n <- A*kdfdt_n + dt*rhs_dfdt ;  dfdt_n <- dfdt_n + B*kdfdt_n
+ *
+ * i.e. pystella.ScalarSector.rhs_dict (pystella/sectors.py:117-131) advanced by
+ * one stage of pystella.LowStorageRKStepper (pystella/step.py:473-491, coefficients
+ * step.py:543-557); the wave equation of examples/wave_equation.py:49-53 is the
+ * case nscalars=1, a=1, hubble=0, no potential.  dV/df_n is a polynomial
+ * sum_t coef[n][t] * prod_m f_m^power[n][t][m].
+ *
+ * psb_scalar_stage_fused evaluates lap(f_n) in-kernel from `f_in` (which must
+ * hold valid halos on the faces) with the centred stencil of radius h
+ * (pystella/derivs.py:160-165, 291-296), writes the new f to `f_out` (a second
+ * padded buffer: the stencil of neighbouring sites still needs the old f) and,
+ * where wrap_* is set, also stores the periodic image of each boundary site
+ * into the opposite face halo of f_out (replaces the P==1 branches of
+ * DomainDecomposition.share_halos, pystella/decomp.py:387-395, 422-424, for
+ * star stencils).  It replaces the reference's per-stage pair
+ * FiniteDifferencer.__call__ (pystella/derivs.py:339-429) + Stepper.__call__
+ * (pystella/step.py:158-170, 524-528).
+ *
+ * psb_scalar_stage_unfused reads lap(f_n) from `lap_f` (unpadded) and updates
+ * f in place (f_out must equal f_in), exactly like the reference's
+ * element-wise stage kernel.
+ * ---------------------------------------------------------------------- */
+typedef struct psb_scalar_stage_args {
+  int32_t dtype;                 /* PSB_F64 | PSB_F32                                */
+  int32_t nscalars;              /* 1..PSB_MAX_SCALARS                               */
+  int32_t h;                     /* halo padding of f/dfdt/k == stencil radius, 1..4 */
+  int32_t wrap_x, wrap_y, wrap_z;/* fused: write periodic images into f_out halos    */
+  int64_t Nx, Ny, Nz;            /* rank (un-padded) shape                           */
+  int64_t x_begin, x_end;        /* sites updated by this launch                     */
+  int64_t field_stride;          /* elements between fields in padded arrays         */
+  int64_t lap_stride;            /* elements between fields in lap_f (unfused)       */
+  const void* f_in;              /* padded, field 0                                  */
+  void* f_out;                   /* padded, field 0 (fused: != f_in)                 */
+  void* dfdt;                    /* padded, in place                                 */
+  void* kf;                      /* padded, in place (the "_f_tmp" twin)             */
+  void* kdfdt;                   /* padded, in place (the "_dfdt_tmp" twin)          */
+  const void* lap_f;             /* unfused only: unpadded Laplacian                 */
+  double dx[3];                  /* grid spacing (fused)                             */
+  double dt, A, B;               /* stage coefficients                               */
+  double a, hubble;              /* used when a_dev/hubble_dev are NULL              */
+  const double* a_dev;           /* optional device scalars (stay on device)         */
+  const double* hubble_dev;
+  int32_t nterms[PSB_MAX_SCALARS];
+  double coef[PSB_MAX_SCALARS][PSB_MAX_TERMS];
+  int8_t power[PSB_MAX_SCALARS][PSB_MAX_TERMS][PSB_MAX_SCALARS];
+  /* optional fused energy partial sums of the INPUT state (may be NULL):
+   * per launch-block partials, see psb_scalar_stage_energy_slots() */
+  double* energy_partials;
+  int32_t tune_xchunk;           /* 0 = default; planes marched per CTA              */
+  int32_t tune_variant;          /* 0 = auto; see DESIGN.md (kernel variants)        */
+} psb_scalar_stage_args;
+
+int psb_scalar_stage_fused(const psb_scalar_stage_args* args, void* stream);
+int psb_scalar_stage_unfused(const psb_scalar_stage_args* args, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Finite differences: FiniteDifferencer.__call__ kernels lap_knl / grad_knl /
+ * grad_lap_knl / pd{x,y,z}_knl / pd*_incr_knl (pystella/derivs.py:291-337).
+ * `fx` is padded by `halo` >= h with valid halos; any of lap/pdx/pdy/pdz may be
+ * NULL.  With accumulate != 0 the first derivatives are added to the output
+ * (the `div += pd_i` kernels of FiniteDifferencer.divergence, derivs.py:462-468).
+ * ---------------------------------------------------------------------- */
+int psb_finite_difference(const void* fx, void* lap, void* pdx, void* pdy, void* pdz,
+                          int dtype, int64_t Nx, int64_t Ny, int64_t Nz,
+                          int h, int halo, const double dx[3], int accumulate,
+                          void* stream);
+
+/* ------------------------------------------------------------------------
+ * Periodic halo fill of one rank-local padded array, order z -> x -> y, each
+ * pass spanning the padded extent of the other axes (edges/corners included):
+ * the pack_unpack_{z,x,y}_knl kernels (pystella/decomp.py:181-182, 208-209,
+ * 232-233) called by DomainDecomposition.share_halos (decomp.py:387-395, 422-424).
+ * axes_mask: bit0 = x, bit1 = y, bit2 = z.
+ * ---------------------------------------------------------------------- */
+int psb_halo_wrap(void* arr, int dtype, int64_t Nx, int64_t Ny, int64_t Nz,
+                  int hx, int hy, int hz, int axes_mask, void* stream);
+
+/* Face pack/unpack for decomposed axes (pack_{x,y}_knl / unpack_{x,y}_knl,
+ * pystella/decomp.py:177-180, 204-207).  buf has shape (2, hx, Ny+2hy, Nz+2hz)
+ * for axis 0 and (2, Nx+2hx, hy, Nz+2hz) for axis 1; slot 0 = low face /
+ * high halo, slot 1 = high face / low halo, as in the reference. */
+int psb_halo_pack(const void* arr, void* buf, int dtype, int64_t Nx, int64_t Ny,
+                  int64_t Nz, int hx, int hy, int hz, int axis, void* stream);
+int psb_halo_unpack(void* arr, const void* buf, int dtype, int64_t Nx, int64_t Ny,
+                    int64_t Nz, int hx, int hy, int hz, int axis, void* stream);
+
+/* gather_knl / scatter_knl (pystella/decomp.py:253-254): strip / add padding. */
+int psb_remove_halos(const void* padded, void* unpadded, int dtype, int64_t Nx,
+                     int64_t Ny, int64_t Nz, int hx, int hy, int hz, void* stream);
+int psb_restore_halos(const void* unpadded, void* padded, int dtype, int64_t Nx,
+                      int64_t Ny, int64_t Nz, int hx, int hy, int hz, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Polynomial reductions: Reduction.__call__ (pystella/reduction.py:165-204,
+ * 237-255).  Output r is  op_r over sites of  sum_{t in terms(r)} coef[t] *
+ * prod_j arr_j^power[t][j]  (abs value taken first if flags bit0 is set), with
+ * op in {0: sum, 1: max, 2: min}.  Array j has halo padding halo[j] (0 for
+ * unpadded arrays).  Two launches: per-block partials, then a fixed-order
+ * finalize into out[r] (double).
+ * ---------------------------------------------------------------------- */
+typedef struct psb_reduce_args {
+  int32_t dtype;
+  int32_t narrays, nterms, noutputs;
+  int64_t Nx, Ny, Nz;
+  const void* arrays[PSB_MAX_RED_ARRAYS];
+  int32_t halo[PSB_MAX_RED_ARRAYS];
+  double coef[PSB_MAX_RED_TERMS];
+  int8_t power[PSB_MAX_RED_TERMS][PSB_MAX_RED_ARRAYS];
+  int32_t term_output[PSB_MAX_RED_TERMS]; /* which output each term feeds */
+  int32_t op[PSB_MAX_RED_OUTPUTS];
+  int32_t flags[PSB_MAX_RED_OUTPUTS];
+  double* partials;              /* workspace: psb_reduce_workspace_doubles() */
+  double* out;                   /* noutputs doubles (device)                 */
+} psb_reduce_args;
+
+int64_t psb_reduce_workspace_doubles(int noutputs);
+int psb_reduce(const psb_reduce_args* args, void* stream);
+
+/* Sum per-block energy partials written by psb_scalar_stage_fused into
+ * out[0..2*nscalars] = {kinetic_n..., potential, gradient_n...} (already
+ * divided by grid_size; ScalarSector.reducers, pystella/sectors.py:133-144). */
+int64_t psb_scalar_stage_energy_slots(const psb_scalar_stage_args* args);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYSTELLA_B200_H */

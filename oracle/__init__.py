@@ -1,0 +1,20 @@
+"""
+TEST INFRASTRUCTURE ONLY.
+
+CPU restatement of the zachjweiner/pystella hot path (finite-difference
+stencils, low-storage RK stages, periodic halo fill, reductions, FLRW
+expansion).  Nothing under ``pystella_b200/`` may import this package: it is
+the checker used by ``tests/``, ``__graft_entry__.smoke()`` and the
+``cpu_baseline`` / ``--impl reference`` legs of ``bench.py``.
+
+Parity status: the reference itself (pyopencl + loopy + pymbolic) cannot be
+imported or run in this image, so the oracle is pinned by (i) the coefficient
+tables extracted from the reference sources by ``tests/golden/make_golden.py``
+(committed as ``tests/golden/reference_tables.json``) and (ii) the reference's
+own known-answer tests re-expressed in ``tests/test_oracle_kat.py``
+(plane-wave eigenvalues, ``y' = y**n`` convergence, bit-exact periodic halos,
+FLRW expansion).  Per-stage array parity against the pyopencl path itself is
+unpinned by the reference (it stores no array fixtures).
+"""
+
+from oracle.numpy_oracle import *  # noqa: F401,F403

@@ -1,0 +1,209 @@
+"""
+Thin Python wrappers around the C ABI: they only marshal tensors / scalars into
+the argument structs of ``include/pystella_b200.h`` and raise on error.
+"""
+
+import ctypes as C
+
+import torch
+
+from pystella_b200 import _lib
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def fill_potential(args, dV_terms, nscalars):
+    """
+    ``dV_terms[n]`` = list of ``(coef, powers)`` for dV/df_n (polynomial in the
+    fields).  Writes nterms/coef/power of a ScalarStageArgs.
+    """
+    for n in range(nscalars):
+        terms = dV_terms[n] if dV_terms is not None else []
+        if len(terms) > _lib.MAX_TERMS:
+            raise ValueError(f"dV/df_{n} has {len(terms)} monomials; at most "
+                             f"{_lib.MAX_TERMS} are supported per field")
+        args.nterms[n] = len(terms)
+        for t, (c, powers) in enumerate(terms):
+            args.coef[n][t] = float(c)
+            for m in range(nscalars):
+                p = int(powers[m])
+                if p < 0 or p > 127:
+                    raise ValueError("monomial powers must be in 0..127")
+                args.power[n][t][m] = p
+
+
+def scalar_stage(*, fused, f_in, f_out, dfdt, kf, kdfdt, lap_f=None, h, dx=(1., 1., 1.),
+                 dt, A, B, a=1., hubble=0., a_dev=None, hubble_dev=None,
+                 dV_terms=None, wrap=(True, True, True), x_range=None,
+                 queue=None, strict=False, xchunk=0, variant=0):
+    """
+    One scalar-sector LSRK stage on padded arrays of shape ``(n, Nx+2h, Ny+2h, Nz+2h)``
+    (or without the leading axis for a single field).
+    """
+    lib = _lib.load(strict)
+    for name, t in (("f_in", f_in), ("f_out", f_out), ("dfdt", dfdt), ("kf", kf),
+                    ("kdfdt", kdfdt)):
+        _lib.require_cuda_tensor(t, name)
+        if t.dtype != f_in.dtype or t.shape != f_in.shape:
+            raise ValueError(f"{name} must match f in dtype and shape")
+    if f_in.dim() == 3:
+        nscalars = 1
+    elif f_in.dim() == 4:
+        nscalars = f_in.shape[0]
+    else:
+        raise ValueError("scalar fields must have shape (n, Nx+2h, Ny+2h, Nz+2h)")
+    if not 1 <= nscalars <= _lib.MAX_SCALARS:
+        raise NotImplementedError(
+            f"{nscalars} scalar fields per launch (max {_lib.MAX_SCALARS})")
+    Px, Py, Pz = f_in.shape[-3:]
+    Nx, Ny, Nz = Px - 2 * h, Py - 2 * h, Pz - 2 * h
+
+    args = _lib.ScalarStageArgs()
+    args.dtype = _lib.torch_dtype_code(f_in)
+    args.nscalars = nscalars
+    args.h = h
+    args.wrap_x, args.wrap_y, args.wrap_z = (int(bool(w)) for w in wrap)
+    args.Nx, args.Ny, args.Nz = Nx, Ny, Nz
+    if x_range is None:
+        x_range = (0, Nx)
+    args.x_begin, args.x_end = x_range
+    args.field_stride = Px * Py * Pz
+    args.f_in = _ptr(f_in)
+    args.f_out = _ptr(f_out)
+    args.dfdt = _ptr(dfdt)
+    args.kf = _ptr(kf)
+    args.kdfdt = _ptr(kdfdt)
+    if lap_f is not None:
+        _lib.require_cuda_tensor(lap_f, "lap_f")
+        if lap_f.shape[-3:] != (Nx, Ny, Nz) or lap_f.dtype != f_in.dtype:
+            raise ValueError("lap_f must have the un-padded shape and dtype of f")
+        args.lap_f = _ptr(lap_f)
+        args.lap_stride = Nx * Ny * Nz
+    for d in range(3):
+        args.dx[d] = float(dx[d])
+    args.dt, args.A, args.B = float(dt), float(A), float(B)
+    args.a, args.hubble = float(a), float(hubble)
+    args.a_dev = _ptr(a_dev)
+    args.hubble_dev = _ptr(hubble_dev)
+    fill_potential(args, dV_terms, nscalars)
+    args.tune_xchunk = xchunk
+    args.tune_variant = variant
+    fn = lib.psb_scalar_stage_fused if fused else lib.psb_scalar_stage_unfused
+    rc = fn(C.byref(args), _lib.stream_ptr(queue))
+    _lib.check(lib, rc, fn.__name__)
+
+
+def finite_difference(fx, *, lap=None, pdx=None, pdy=None, pdz=None, h, halo=None,
+                      dx, accumulate=False, queue=None, strict=False):
+    lib = _lib.load(strict)
+    _lib.require_cuda_tensor(fx, "fx")
+    halo = h if halo is None else halo
+    Nx, Ny, Nz = (n - 2 * halo for n in fx.shape[-3:])
+    for name, t in (("lap", lap), ("pdx", pdx), ("pdy", pdy), ("pdz", pdz)):
+        if t is None:
+            continue
+        _lib.require_cuda_tensor(t, name)
+        if tuple(t.shape) != (Nx, Ny, Nz) or t.dtype != fx.dtype:
+            raise ValueError(
+                f"{name} has shape {tuple(t.shape)}/{t.dtype}; expected {(Nx, Ny, Nz)}/"
+                f"{fx.dtype}")
+    dxa = (C.c_double * 3)(*[float(d) for d in dx])
+    rc = lib.psb_finite_difference(_ptr(fx), _ptr(lap), _ptr(pdx), _ptr(pdy), _ptr(pdz),
+                                   _lib.torch_dtype_code(fx), Nx, Ny, Nz, h, halo,
+                                   C.byref(dxa), int(accumulate),
+                                   _lib.stream_ptr(queue))
+    _lib.check(lib, rc, "psb_finite_difference")
+
+
+def halo_wrap(arr, halo_shape, axes_mask=7, queue=None, strict=False):
+    lib = _lib.load(strict)
+    _lib.require_cuda_tensor(arr, "fx")
+    hx, hy, hz = halo_shape
+    Nx, Ny, Nz = (n - 2 * h for n, h in zip(arr.shape[-3:], halo_shape))
+    rc = lib.psb_halo_wrap(_ptr(arr), _lib.torch_dtype_code(arr), Nx, Ny, Nz,
+                           hx, hy, hz, axes_mask, _lib.stream_ptr(queue))
+    _lib.check(lib, rc, "psb_halo_wrap")
+
+
+def halo_pack(arr, buf, halo_shape, axis, queue=None, unpack=False, strict=False):
+    lib = _lib.load(strict)
+    _lib.require_cuda_tensor(arr, "fx")
+    _lib.require_cuda_tensor(buf, "buf")
+    hx, hy, hz = halo_shape
+    Nx, Ny, Nz = (n - 2 * h for n, h in zip(arr.shape[-3:], halo_shape))
+    if unpack:
+        rc = lib.psb_halo_unpack(_ptr(arr), _ptr(buf), _lib.torch_dtype_code(arr),
+                                 Nx, Ny, Nz, hx, hy, hz, axis, _lib.stream_ptr(queue))
+    else:
+        rc = lib.psb_halo_pack(_ptr(arr), _ptr(buf), _lib.torch_dtype_code(arr),
+                               Nx, Ny, Nz, hx, hy, hz, axis, _lib.stream_ptr(queue))
+    _lib.check(lib, rc, "psb_halo_unpack" if unpack else "psb_halo_pack")
+
+
+def remove_halos(padded, unpadded, halo_shape, queue=None, restore=False, strict=False):
+    lib = _lib.load(strict)
+    _lib.require_cuda_tensor(padded, "padded")
+    _lib.require_cuda_tensor(unpadded, "unpadded")
+    hx, hy, hz = halo_shape
+    Nx, Ny, Nz = unpadded.shape[-3:]
+    if tuple(padded.shape[-3:]) != (Nx + 2 * hx, Ny + 2 * hy, Nz + 2 * hz):
+        raise ValueError("padded/unpadded shapes do not differ by 2*halo_shape")
+    if padded.dtype != unpadded.dtype:
+        raise ValueError("in_array and out_array have different dtypes")
+    code = _lib.torch_dtype_code(padded)
+    if restore:
+        rc = lib.psb_restore_halos(_ptr(unpadded), _ptr(padded), code, Nx, Ny, Nz,
+                                   hx, hy, hz, _lib.stream_ptr(queue))
+    else:
+        rc = lib.psb_remove_halos(_ptr(padded), _ptr(unpadded), code, Nx, Ny, Nz,
+                                  hx, hy, hz, _lib.stream_ptr(queue))
+    _lib.check(lib, rc, "psb_restore_halos" if restore else "psb_remove_halos")
+
+
+_reduce_ws = {}
+
+
+def reduce_poly(arrays, halos, terms, ops, flags, shape, queue=None, strict=False):
+    """
+    ``arrays``: list of tensors; ``halos``: their padding; ``terms``: list of
+    ``(output, coef, powers)``; ``ops``: per-output op code (0 sum, 1 max, 2 min).
+    Returns a float64 device tensor with one value per output.
+    """
+    lib = _lib.load(strict)
+    if len(arrays) > _lib.MAX_RED_ARRAYS:
+        raise NotImplementedError("too many distinct arrays in one reduction")
+    if len(terms) > _lib.MAX_RED_TERMS or len(ops) > _lib.MAX_RED_OUTPUTS:
+        raise NotImplementedError("too many terms/outputs in one reduction")
+    dev = arrays[0].device
+    args = _lib.ReduceArgs()
+    args.dtype = _lib.torch_dtype_code(arrays[0])
+    args.narrays, args.nterms, args.noutputs = len(arrays), len(terms), len(ops)
+    args.Nx, args.Ny, args.Nz = shape
+    for m, (t, h) in enumerate(zip(arrays, halos)):
+        _lib.require_cuda_tensor(t, f"array {m}")
+        if t.dtype != arrays[0].dtype:
+            raise ValueError("all arrays of a reduction must share one dtype")
+        if tuple(t.shape[-3:]) != tuple(n + 2 * h for n in shape):
+            raise ValueError(f"array {m} has shape {tuple(t.shape)}, expected padding {h}")
+        args.arrays[m] = t.data_ptr()
+        args.halo[m] = h
+    for t, (out, coef, powers) in enumerate(terms):
+        args.term_output[t] = out
+        args.coef[t] = float(coef)
+        for m, p in enumerate(powers):
+            args.power[t][m] = int(p)
+    for r, (op, fl) in enumerate(zip(ops, flags)):
+        args.op[r] = op
+        args.flags[r] = fl
+    key = (dev.index, torch.cuda.current_stream().cuda_stream)
+    if key not in _reduce_ws:
+        n = lib.psb_reduce_workspace_doubles(_lib.MAX_RED_OUTPUTS)
+        _reduce_ws[key] = torch.empty(n, dtype=torch.float64, device=dev)
+    out = torch.empty(len(ops), dtype=torch.float64, device=dev)
+    args.partials = _reduce_ws[key].data_ptr()
+    args.out = out.data_ptr()
+    rc = lib.psb_reduce(C.byref(args), _lib.stream_ptr(queue))
+    _lib.check(lib, rc, "psb_reduce")
+    return out

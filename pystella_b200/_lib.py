@@ -1,0 +1,161 @@
+"""
+ctypes binding of ``libpystella_b200.so`` (the C ABI declared in
+``include/pystella_b200.h``).  There is deliberately no fallback: if the shared
+object is missing or a call fails, an exception is raised.
+"""
+
+import ctypes as C
+import os
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+PSB_F64, PSB_F32 = 0, 1
+MAX_SCALARS = 4
+MAX_TERMS = 16
+MAX_RED_ARRAYS = 8
+MAX_RED_TERMS = 32
+MAX_RED_OUTPUTS = 16
+
+c_void_p, c_int, c_int32, c_int64, c_double = (
+    C.c_void_p, C.c_int, C.c_int32, C.c_int64, C.c_double)
+
+
+class ScalarStageArgs(C.Structure):
+    _fields_ = [
+        ("dtype", c_int32), ("nscalars", c_int32), ("h", c_int32),
+        ("wrap_x", c_int32), ("wrap_y", c_int32), ("wrap_z", c_int32),
+        ("Nx", c_int64), ("Ny", c_int64), ("Nz", c_int64),
+        ("x_begin", c_int64), ("x_end", c_int64),
+        ("field_stride", c_int64), ("lap_stride", c_int64),
+        ("f_in", c_void_p), ("f_out", c_void_p), ("dfdt", c_void_p),
+        ("kf", c_void_p), ("kdfdt", c_void_p), ("lap_f", c_void_p),
+        ("dx", c_double * 3),
+        ("dt", c_double), ("A", c_double), ("B", c_double),
+        ("a", c_double), ("hubble", c_double),
+        ("a_dev", c_void_p), ("hubble_dev", c_void_p),
+        ("nterms", c_int32 * MAX_SCALARS),
+        ("coef", (c_double * MAX_TERMS) * MAX_SCALARS),
+        ("power", ((C.c_int8 * MAX_SCALARS) * MAX_TERMS) * MAX_SCALARS),
+        ("energy_partials", c_void_p),
+        ("tune_xchunk", c_int32), ("tune_variant", c_int32),
+    ]
+
+
+class ReduceArgs(C.Structure):
+    _fields_ = [
+        ("dtype", c_int32), ("narrays", c_int32), ("nterms", c_int32),
+        ("noutputs", c_int32),
+        ("Nx", c_int64), ("Ny", c_int64), ("Nz", c_int64),
+        ("arrays", c_void_p * MAX_RED_ARRAYS),
+        ("halo", c_int32 * MAX_RED_ARRAYS),
+        ("coef", c_double * MAX_RED_TERMS),
+        ("power", (C.c_int8 * MAX_RED_ARRAYS) * MAX_RED_TERMS),
+        ("term_output", c_int32 * MAX_RED_TERMS),
+        ("op", c_int32 * MAX_RED_OUTPUTS),
+        ("flags", c_int32 * MAX_RED_OUTPUTS),
+        ("partials", c_void_p), ("out", c_void_p),
+    ]
+
+
+#: every symbol include/pystella_b200.h declares: (restype, argtypes)
+SYMBOLS = {
+    "psb_last_error": (C.c_char_p, []),
+    "psb_abi_version": (c_int, []),
+    "psb_strict_fp": (c_int, []),
+    "psb_scalar_stage_fused": (c_int, [C.POINTER(ScalarStageArgs), c_void_p]),
+    "psb_scalar_stage_unfused": (c_int, [C.POINTER(ScalarStageArgs), c_void_p]),
+    "psb_finite_difference": (c_int, [c_void_p] * 5 + [c_int, c_int64, c_int64, c_int64,
+                                                        c_int, c_int,
+                                                        C.POINTER(c_double * 3), c_int,
+                                                        c_void_p]),
+    "psb_halo_wrap": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64,
+                              c_int, c_int, c_int, c_int, c_void_p]),
+    "psb_halo_pack": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_int64,
+                              c_int, c_int, c_int, c_int, c_void_p]),
+    "psb_halo_unpack": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_int64,
+                                c_int, c_int, c_int, c_int, c_void_p]),
+    "psb_remove_halos": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_int64,
+                                 c_int, c_int, c_int, c_void_p]),
+    "psb_restore_halos": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_int64,
+                                  c_int, c_int, c_int, c_void_p]),
+    "psb_reduce_workspace_doubles": (c_int64, [c_int]),
+    "psb_reduce": (c_int, [C.POINTER(ReduceArgs), c_void_p]),
+    "psb_scalar_stage_energy_slots": (c_int64, [C.POINTER(ScalarStageArgs)]),
+}
+
+
+class PsbError(RuntimeError):
+    pass
+
+
+_libs = {}
+
+
+def lib_path(strict=False):
+    name = "libpystella_b200_strict.so" if strict else "libpystella_b200.so"
+    return os.path.join(HERE, "_C", name)
+
+
+def load(strict=False):
+    """Load (once) and return the shared library; raises if it is not built."""
+    strict = bool(strict) or os.environ.get("PSB_STRICT_FP", "0") == "1"
+    if strict not in _libs:
+        path = lib_path(strict)
+        if not os.path.exists(path):
+            raise PsbError(
+                f"{path} not found: build the CUDA extension first "
+                "(python -m pystella_b200.build); there is no CPU fallback")
+        lib = C.CDLL(path)
+        for name, (restype, argtypes) in SYMBOLS.items():
+            fn = getattr(lib, name)  # AttributeError if the symbol is missing
+            fn.restype = restype
+            fn.argtypes = argtypes
+        if lib.psb_abi_version() != 1:
+            raise PsbError("ABI version mismatch")
+        _libs[strict] = lib
+    return _libs[strict]
+
+
+def check(lib, rc, what):
+    if rc != 0:
+        msg = lib.psb_last_error().decode(errors="replace")
+        raise PsbError(f"{what} failed (code {rc}): {msg}")
+
+
+def dtype_code(dtype):
+    if dtype in (torch.float64, np.float64) or np.dtype(dtype) == np.float64:
+        return PSB_F64
+    if dtype in (torch.float32, np.float32) or np.dtype(dtype) == np.float32:
+        return PSB_F32
+    raise TypeError(f"unsupported dtype {dtype}")
+
+
+def torch_dtype_code(t):
+    if t.dtype == torch.float64:
+        return PSB_F64
+    if t.dtype == torch.float32:
+        return PSB_F32
+    raise TypeError(f"unsupported dtype {t.dtype} (float64/float32 only)")
+
+
+def stream_ptr(queue=None):
+    """``queue`` is a torch.cuda.Stream (the analogue of a cl.CommandQueue) or None."""
+    if queue is None:
+        return torch.cuda.current_stream().cuda_stream
+    if isinstance(queue, torch.cuda.Stream):
+        return queue.cuda_stream
+    raise TypeError("queue must be a torch.cuda.Stream or None")
+
+
+def require_cuda_tensor(t, name):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor on a CUDA device, got {type(t)}")
+    if not t.is_cuda:
+        raise PsbError(f"{name} lives on {t.device}: the hot path runs on the GPU only "
+                       "(no CPU fallback)")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+    return t
