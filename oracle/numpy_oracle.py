@@ -235,6 +235,28 @@ LSRK_TABLES = {
 }
 
 
+def _long_tables():
+    """
+    The 12/13/14-stage schemes (step.py:568-754) are long literal tables; the
+    oracle reads them from the committed extraction of the reference sources
+    (tests/golden/reference_tables.json, see tests/golden/make_golden.py).
+    """
+    import json
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                        "tests", "golden", "reference_tables.json")
+    if not os.path.exists(path):
+        return
+    with open(path) as fh:
+        tabs = json.load(fh)["lsrk"]
+    for name in ("LowStorageRK144", "LowStorageRK134", "LowStorageRK124"):
+        LSRK_TABLES[name] = (tabs[name]["A"], tabs[name]["B"],
+                             tabs[name]["expected_order"])
+
+
+_long_tables()
+
+
 def lsrk_stage(A_s, B_s, dt, unknowns, tmps, rhs):
     """
     One 2N-storage stage (step.py:476-485; statement order elementwise.py:173-203):
@@ -337,14 +359,17 @@ def poly_eval(terms, fields):
     """
     Evaluate a polynomial given as ``[(coef, (p_0, ..., p_{n-1})), ...]`` on a
     list of field arrays.  (The potentials of examples/scalar_preheating.py:98-105
-    and test/test_energy.py:49-51 are of this form.)
+    and test/test_energy.py:49-51 are of this form.)  Integer powers are expanded
+    into repeated products, ``coef * f_0 * f_0 * ... * f_1 * ...``, summed left to
+    right -- what a code generator emits for small integer exponents, and the
+    association order the CUDA kernels use.
     """
     out = 0.
     for c, powers in terms:
         t = c
         for fld, p in zip(fields, powers):
-            if p:
-                t = t * fld**p
+            for _ in range(int(p)):
+                t = t * fld
         out = out + t
     return out
 

@@ -1,0 +1,135 @@
+"""
+Orchestration of the fused stencil + RK stage (``psb_scalar_stage_fused``).
+
+Per stage and scalar system:
+
+* single rank: one launch over the whole slab; the kernel's store epilogue also
+  writes the periodic images onto the face halos of the new ``f``;
+* ``proc_shape = (P, 1, 1)``, P > 1: the two boundary slabs (the ``h`` outermost
+  x-planes on either side) are updated first; their new faces are then sent to
+  the x-neighbours on a side stream (NCCL over NVLink, straight out of / into the
+  field tensor -- x faces are contiguous) while the interior slab is updated on
+  the compute stream; the streams join before the next stage.  This replaces the
+  reference's synchronous pack -> D2H -> MPI.Sendrecv -> H2D -> unpack
+  (``pystella/decomp.py:402-419``) called from ``FiniteDifferencer.__call__``
+  (``pystella/derivs.py:412``).
+
+The new ``f`` is written to a stepper-owned twin buffer (neighbouring sites still
+need the old values); afterwards the *storage* of the user's tensor and of the twin
+are swapped (no copy), so the user-visible contract "``f`` is updated in place"
+(``examples/wave_equation.py:64``) holds for the tensor object passed in.  Views
+of ``f`` taken before the call keep pointing at the old storage.
+"""
+
+import torch
+import torch.distributed as dist
+
+from pystella_b200 import _kernels
+
+__all__ = ["fused_scalar_stage"]
+
+
+def _swap_storage(a, b):
+    a_data, b_data = a.data, b.data
+    a.data, b.data = b_data, a_data
+
+
+def _ensure_streams(stepper):
+    if stepper._streams is None:
+        stepper._streams = {
+            "comm": torch.cuda.Stream(),
+            "boundary_done": torch.cuda.Event(),
+            "comm_done": torch.cuda.Event(),
+        }
+    return stepper._streams
+
+
+def exchange_x_faces(decomp, f, h, fields_axis):
+    """
+    Post the x-face exchange of padded ``f`` (shape ``([n,] Px, Py, Pz)``): my low
+    interior planes go to rank ``rx-1``'s high halo and my high interior planes to
+    rank ``rx+1``'s low halo (``pystella/decomp.py:405-415``).  One batched group
+    of sends/receives for all fields.
+    """
+    lo = decomp.rankID(decomp.rx - 1, decomp.ry, decomp.rz)
+    hi = decomp.rankID(decomp.rx + 1, decomp.ry, decomp.rz)
+    ops = []
+    views = [f[n] for n in range(f.shape[0])] if fields_axis else [f]
+    for v in views:
+        Nx = v.shape[0] - 2 * h
+        ops += [
+            dist.P2POp(dist.isend, v[h:2 * h], lo, group=decomp.comm),
+            dist.P2POp(dist.irecv, v[Nx + h:], hi, group=decomp.comm),
+            dist.P2POp(dist.isend, v[Nx:Nx + h], hi, group=decomp.comm),
+            dist.P2POp(dist.irecv, v[:h], lo, group=decomp.comm),
+        ]
+    return dist.batch_isend_irecv(ops)
+
+
+def fused_scalar_stage(stepper, system, f, common, queue):
+    h = common["h"]
+    decomp = stepper.decomp
+    multi = decomp is not None and decomp.nranks > 1
+    if multi and (decomp.proc_shape[1] != 1):
+        raise NotImplementedError(
+            "the fused stage supports slab decompositions proc_shape=(P, 1, 1); use the "
+            "element-wise stepper with FiniteDifferencer for (Px, Py, 1)")
+    if decomp is not None and tuple(decomp.halo_shape) != (h, h, h):
+        raise ValueError("decomp.halo_shape differs from the stepper's halo_shape")
+
+    key = system.f_name
+    twin = stepper._twins.get(key)
+    if twin is None or twin.shape != f.shape or twin.dtype != f.dtype \
+            or twin.device != f.device:
+        twin = torch.empty_like(f)
+        # halo edges/corners of the twin are never written by the kernel; give them
+        # defined values once
+        twin.copy_(f)
+        stepper._twins[key] = twin
+        stepper._halos_fresh = False
+
+    if not stepper._halos_fresh:
+        # halos of the user's array are of unknown age: fill them once
+        views = [f[n] for n in range(f.shape[0])] if f.dim() == 4 else [f]
+        if decomp is not None:
+            for v in views:
+                decomp.share_halos(queue, v)
+        else:
+            for v in views:
+                _kernels.halo_wrap(v, (h, h, h), 7, queue)
+        stepper._halos_fresh = True
+
+    Nx = f.shape[-3] - 2 * h
+    args = dict(common)
+    args.update(fused=True, f_in=f, f_out=twin, dx=stepper.dx)
+    tune = getattr(stepper, "tune", None) or {}
+    args.update(xchunk=tune.get("xchunk", 0), variant=tune.get("variant", 0))
+
+    if not multi:
+        _kernels.scalar_stage(wrap=(True, True, True), **args)
+    else:
+        st = _ensure_streams(stepper)
+        cur = queue if queue is not None else torch.cuda.current_stream()
+        hb = min(h, Nx)
+        with torch.cuda.stream(cur):
+            # boundary slabs first
+            _kernels.scalar_stage(wrap=(False, True, True), x_range=(0, hb), **args)
+            if Nx - hb > hb:
+                _kernels.scalar_stage(wrap=(False, True, True), x_range=(Nx - hb, Nx),
+                                      **args)
+                interior = (hb, Nx - hb)
+            else:
+                _kernels.scalar_stage(wrap=(False, True, True), x_range=(hb, Nx), **args)
+                interior = None
+            st["boundary_done"].record(cur)
+        with torch.cuda.stream(st["comm"]):
+            st["comm"].wait_event(st["boundary_done"])
+            for req in exchange_x_faces(decomp, twin, h, f.dim() == 4):
+                req.wait()
+            st["comm_done"].record(st["comm"])
+        if interior is not None:
+            with torch.cuda.stream(cur):
+                _kernels.scalar_stage(wrap=(False, True, True), x_range=interior, **args)
+        cur.wait_event(st["comm_done"])
+
+    _swap_storage(f, twin)

@@ -1,0 +1,799 @@
+"""
+Time steppers.  Same classes, constructor arguments, ``__call__(stage, ...)``
+contract, ``num_stages`` / ``expected_order`` / ``num_unknowns`` / ``tmp_arrays``
+attributes as ``pystella/step.py:67-853``.
+
+What differs is *what a stage is*: the reference generates one OpenCL kernel per
+stage from the symbolic ``rhs_dict``; here ``rhs_dict`` is *recognised*
+(:func:`recognise_scalar_system`) and each stage dispatches a hand-written sm_100a
+kernel through the C ABI:
+
+* ``MapKernel=ElementWiseMap`` (default): the element-wise stage that reads a
+  precomputed Laplacian, as in the reference (``psb_scalar_stage_unfused``);
+* ``MapKernel=FusedStencilStage`` (+ ``dx=``, optionally ``decomp=``): the fused
+  stencil + RHS + update kernel (``psb_scalar_stage_fused``) -- the reference's
+  documented ``MapKernel`` hook (``pystella/step.py:94-103``) is where it plugs in.
+
+Scalar ODEs on host NumPy arrays (``rank_shape=(0, 0, 0)``; the reference runs
+these through loopy's C target, e.g. for :class:`~pystella_b200.Expansion`) are
+evaluated on the host.
+"""
+
+import numpy as np
+import torch
+
+from pystella_b200 import _kernels
+from pystella_b200._lib import PsbError
+from pystella_b200.field import (DynamicField, Field, Subscript, Variable, evaluate,
+                                 is_constant, to_polynomial)
+
+__all__ = [
+    "ElementWiseMap", "FusedStencilStage", "Stepper", "RungeKuttaStepper",
+    "LowStorageRKStepper", "RungeKutta4", "RungeKutta3Heun", "RungeKutta3Nystrom",
+    "RungeKutta3Ralston", "RungeKutta3SSP", "RungeKutta2Midpoint", "RungeKutta2Heun",
+    "RungeKutta2Ralston", "LowStorageRK54", "LowStorageRK144", "LowStorageRK134",
+    "LowStorageRK124", "LowStorageRK3Williamson", "LowStorageRK3Inhomogeneous",
+    "LowStorageRK3Symmetric", "LowStorageRK3PredictorCorrector", "LowStorageRK3SSP",
+    "all_steppers", "recognise_scalar_system",
+]
+
+
+class ElementWiseMap:
+    """
+    Marker for "one element-wise kernel per stage" (``pystella/elementwise.py:81-361``).
+    On device arrays the stage is the hand-written scalar-sector kernel; there is
+    no run-time code generator in this build, so systems outside the kernel menu
+    raise :class:`NotImplementedError` with the reason.
+    """
+
+
+class FusedStencilStage(ElementWiseMap):
+    """
+    ``MapKernel`` that evaluates ``lap_f`` in-kernel from ``f`` (TMA-staged tile,
+    finite-difference stencil of radius ``halo_shape``) instead of reading a
+    precomputed ``lap_f`` array, and maintains the face halos of ``f`` itself.
+    Requires ``dx=`` (and ``decomp=`` for more than one rank).
+    """
+
+
+# ---------------------------------------------------------------------------
+# system recognition
+# ---------------------------------------------------------------------------
+
+class ScalarSystem:
+    """A set of (f_n, dfdt_n) pairs obeying the scalar-sector equations."""
+
+    def __init__(self, field, nscalars, hubble, a, dV, has_outer_axis):
+        self.field = field              # the DynamicField
+        self.f_name = field.name
+        self.dot_name = field.dot.name
+        self.lap_name = field.lap.name
+        self.nscalars = nscalars
+        self.hubble = hubble            # scalar expression
+        self.a = a                      # scalar expression
+        self.dV = dV                    # [n] -> list of (coef_expr, powers)
+        self.has_outer_axis = has_outer_axis
+
+    def scalar_names(self):
+        names = set()
+        from pystella_b200.field import _walk
+        exprs = [self.hubble, self.a] + [c for terms in self.dV for c, _ in terms]
+        for e in exprs:
+            for node in _walk(e):
+                if isinstance(node, (Variable, Field)):
+                    names.add(node.name)
+        return names
+
+
+def _unknown_parts(key):
+    """-> (Field, outer subscript tuple) of an rhs_dict key."""
+    if isinstance(key, Field):
+        return key, ()
+    if isinstance(key, Subscript) and isinstance(key.aggregate, Field):
+        return key.aggregate, tuple(int(i) for i in key.index)
+    raise ValueError("rhs_dict keys must be Field instances")
+
+
+def recognise_scalar_system(rhs_dict):
+    """
+    Match ``rhs_dict`` against::
+
+        f[n]'    = dfdt[n]
+        dfdt[n]' = lap_f[n] + c_d * dfdt[n] + sum_t c_t * prod_m f[m]**p_tm
+
+    with scalar-expression coefficients (ScalarSector.rhs_dict,
+    ``pystella/sectors.py:117-131``; the wave equation of
+    ``examples/wave_equation.py:49-53`` is the case c_d = 0, no polynomial).
+    Returns a :class:`ScalarSystem` or raises ``NotImplementedError`` saying what
+    did not match.
+    """
+    keys = list(rhs_dict.keys())
+    dyn = None
+    for k in keys:
+        fld, _ = _unknown_parts(k)
+        if isinstance(fld, DynamicField):
+            if dyn is not None and fld.name != dyn.name:
+                raise NotImplementedError(
+                    "more than one DynamicField in one system: pass sectors "
+                    "separately (each gets its own stage kernel)")
+            dyn = fld
+    if dyn is None:
+        raise NotImplementedError(
+            "no DynamicField among the unknowns: device steppers implement the "
+            "scalar-sector / wave-equation system (f' = dfdt, dfdt' = lap_f + ...)")
+    if len(dyn.shape) > 1:
+        raise NotImplementedError("DynamicField with more than one outer axis")
+    nscalars = dyn.shape[0] if dyn.shape else 1
+    has_outer = bool(dyn.shape)
+
+    def sub(n):
+        return (n,) if has_outer else ()
+
+    if len(keys) != 2 * nscalars:
+        raise NotImplementedError(
+            f"expected {2 * nscalars} unknowns (f and dfdt per field), got {len(keys)}")
+
+    hubble = None
+    dV = []
+    for n in range(nscalars):
+        kf = dyn[sub(n)] if has_outer else dyn
+        kd = dyn.dot[sub(n)] if has_outer else dyn.dot
+        if kf not in rhs_dict or kd not in rhs_dict:
+            raise NotImplementedError(f"missing equation for field {n}")
+        # f' = dfdt
+        pf = to_polynomial(rhs_dict[kf])
+        ok = (len(pf) == 1)
+        if ok:
+            (mono, c), = pf.items()
+            ok = (len(mono) == 1 and mono[0][1] == 1 and mono[0][0].name == dyn.dot.name
+                  and mono[0][0].subscript == sub(n) and is_constant(c) and c == 1)
+        if not ok:
+            raise NotImplementedError(
+                f"equation for {kf} is not `{kd}` (got {rhs_dict[kf]})")
+        # dfdt' = lap + c_d dfdt + poly(f)
+        pd = to_polynomial(rhs_dict[kd])
+        c_d = 0
+        terms = []
+        saw_lap = False
+        for mono, c in pd.items():
+            names = {ref.name for ref, _ in mono}
+            if any(any(ref.shift) for ref, _ in mono):
+                raise NotImplementedError("shifted (stencil) operand in a stepper RHS")
+            if names == {dyn.lap.name}:
+                ref, pw = mono[0]
+                if not (len(mono) == 1 and pw == 1 and ref.subscript == sub(n)
+                        and is_constant(c) and c == 1):
+                    raise NotImplementedError(
+                        f"Laplacian term of field {n} must be exactly lap_f[{n}]")
+                saw_lap = True
+            elif names == {dyn.dot.name}:
+                ref, pw = mono[0]
+                if not (len(mono) == 1 and pw == 1 and ref.subscript == sub(n)):
+                    raise NotImplementedError(
+                        "only a linear friction term c*dfdt[n] is supported")
+                c_d = c
+            elif names <= {dyn.name}:
+                powers = [0] * nscalars
+                for ref, pw in mono:
+                    m = ref.subscript[0] if has_outer else 0
+                    powers[m] = pw
+                terms.append((-1 * c, tuple(powers)))
+            else:
+                raise NotImplementedError(
+                    f"term {mono} of d({kd})/dt is outside the scalar-sector menu")
+        if not saw_lap:
+            raise NotImplementedError(f"d({kd})/dt has no Laplacian term")
+        h_n = -1 * c_d / 2 if not (is_constant(c_d) and c_d == 0) else 0
+        if hubble is None:
+            hubble = h_n
+        elif not _same_scalar(hubble, h_n):
+            raise NotImplementedError("fields with different friction coefficients")
+        dV.append(terms)
+    return ScalarSystem(dyn, nscalars, hubble, 1, dV, has_outer)
+
+
+def _same_scalar(a, b):
+    if is_constant(a) and is_constant(b):
+        return a == b
+    from pystella_b200.field import _walk
+    names = sorted({n.name for e in (a, b) for n in _walk(e)
+                    if isinstance(n, (Variable, Field))})
+    for seed in (0.731, 1.377):
+        ctx = {n: seed * (k + 1.41) for k, n in enumerate(names)}
+        if abs(evaluate(a, ctx) - evaluate(b, ctx)) > 1e-13:
+            return False
+    return True
+
+
+def scalar_system_from_sector(sector):
+    """
+    Exact structure of a :class:`~pystella_b200.ScalarSector`: keeps ``a`` and
+    ``hubble`` as separate kernel scalars and ``dV/df_n`` as its own polynomial,
+    so the kernel evaluates ``(lap - 2*hubble*dfdt) - a**2 * dV`` in the
+    reference's association order.
+    """
+    from pystella_b200.field import diff
+    f = sector.f
+    n = sector.nscalars
+    V = sector.potential(f)
+    dV = []
+    for fld in range(n):
+        poly = to_polynomial(diff(V, f[fld]))
+        terms = []
+        for mono, c in poly.items():
+            powers = [0] * n
+            for ref, pw in mono:
+                if ref.name != f.name or any(ref.shift):
+                    raise NotImplementedError(
+                        "potential must be a polynomial in the scalar fields")
+                powers[ref.subscript[0] if f.shape else 0] = pw
+            terms.append((c, tuple(powers)))
+        dV.append(terms)
+    return ScalarSystem(f, n, Field("hubble", indices=[]), Field("a", indices=[]),
+                        dV, bool(f.shape))
+
+
+# ---------------------------------------------------------------------------
+# helpers
+# ---------------------------------------------------------------------------
+
+def get_name(expr):
+    if isinstance(expr, Field):
+        return expr.name
+    if isinstance(expr, Subscript):
+        return get_name(expr.aggregate)
+    if isinstance(expr, Variable):
+        return expr.name
+    if isinstance(expr, str):
+        return expr
+    raise ValueError(f"cannot name {expr}")
+
+
+def gen_tmp_name(expr, prefix="_", suffix="_tmp"):
+    return prefix + get_name(expr) + suffix
+
+
+def _scalar_value(x):
+    """Host scalar from float / 0-d or 1-element ndarray; None for device tensors."""
+    if isinstance(x, torch.Tensor):
+        return None
+    arr = np.asarray(x, dtype=np.float64)
+    if arr.size != 1:
+        raise ValueError("scalar arguments must have exactly one element")
+    return float(arr.reshape(-1)[0])
+
+
+def _is_device(x):
+    return isinstance(x, torch.Tensor) and x.is_cuda
+
+
+class Stepper:
+    """
+    Base class of time steppers (``pystella/step.py:67-170``).
+
+    :arg input: a ``dict`` ``{y: dy/dt}``, a :class:`~pystella_b200.Sector` or a
+        list of Sectors.
+
+    Keyword arguments: ``MapKernel`` (:class:`ElementWiseMap` or
+    :class:`FusedStencilStage`), ``dt`` (fixes the time step), ``halo_shape``,
+    ``rank_shape``, ``dtype``, and for the fused kernel ``dx`` / ``decomp``.
+    Unknown keyword arguments of the reference's code generator (``target``,
+    ``lsize``, ``args`` ...) are accepted and ignored.
+    """
+
+    num_stages = None
+    expected_order = None
+    num_copies = None
+
+    def __init__(self, input, MapKernel=ElementWiseMap, **kwargs):
+        from pystella_b200.sectors import ScalarSector, Sector, TensorPerturbationSector
+        self._sectors = None
+        if isinstance(input, (Sector, TensorPerturbationSector)):
+            self._sectors = [input]
+            self.rhs_dict = input.rhs_dict
+        elif isinstance(input, list):
+            self._sectors = list(input)
+            self.rhs_dict = dict(i for s in input for i in s.rhs_dict.items())
+        elif isinstance(input, dict):
+            self.rhs_dict = input
+        else:
+            raise TypeError("input must be a dict, a Sector or a list of Sectors")
+
+        for key in self.rhs_dict:
+            _unknown_parts(key)  # raises ValueError for non-Field keys
+
+        if not (isinstance(MapKernel, type) and issubclass(MapKernel, ElementWiseMap)):
+            raise TypeError("MapKernel must be ElementWiseMap or a subclass")
+        self.MapKernel = MapKernel
+        self.fused = issubclass(MapKernel, FusedStencilStage)
+
+        self.dt = kwargs.pop("dt", None)
+        fixed = kwargs.pop("fixed_parameters", None) or {}
+        if self.dt is None and "dt" in fixed:
+            self.dt = fixed["dt"]
+        self.halo_shape = kwargs.pop("halo_shape", None)
+        self.rank_shape = kwargs.pop("rank_shape", None)
+        self.dtype = kwargs.pop("dtype", None)
+        self.dx = kwargs.pop("dx", None)
+        self.decomp = kwargs.pop("decomp", None)
+        self.strict_fp = kwargs.pop("strict_fp", False)
+        self._ignored_kwargs = kwargs  # target=, lsize=, args=, options= ...
+
+        if self.fused and self.dx is None:
+            raise ValueError("FusedStencilStage needs the grid spacing: pass dx=(...)")
+        if isinstance(self.halo_shape, (tuple, list)):
+            if len(set(self.halo_shape)) != 1:
+                raise NotImplementedError("steppers need an isotropic halo_shape")
+            self.halo_shape = self.halo_shape[0]
+
+        self.num_unknowns = len(self.rhs_dict)
+        self.dof_names = {get_name(key) for key in self.rhs_dict}
+        self._systems = None
+        self._ScalarSector = ScalarSector
+        self._TensorSector = TensorPerturbationSector
+
+    # -- device systems -------------------------------------------------------
+    def _build_systems(self):
+        systems = []
+        if self._sectors is not None:
+            for s in self._sectors:
+                if isinstance(s, self._ScalarSector):
+                    systems.append(scalar_system_from_sector(s))
+                elif isinstance(s, self._TensorSector):
+                    from pystella_b200.gw import tensor_system_from_sector
+                    systems.append(tensor_system_from_sector(s))
+                else:
+                    systems.append(recognise_scalar_system(s.rhs_dict))
+        else:
+            systems.append(recognise_scalar_system(self.rhs_dict))
+        return systems
+
+    @property
+    def systems(self):
+        if self._systems is None:
+            self._systems = self._build_systems()
+        return self._systems
+
+    def _resolve_dt(self, kwargs):
+        dt = self.dt if self.dt is not None else kwargs.get("dt")
+        if dt is None:
+            raise ValueError("dt was not fixed at construction; pass dt=...")
+        return float(np.asarray(dt).reshape(-1)[0])
+
+    def _on_device(self, kwargs):
+        arrays = [kwargs[n] for n in self.dof_names if n in kwargs]
+        if not arrays:
+            missing = sorted(self.dof_names)
+            raise TypeError(f"missing array arguments {missing}")
+        if all(isinstance(x, np.ndarray) for x in arrays):
+            return False
+        if all(isinstance(x, torch.Tensor) for x in arrays):
+            for n in self.dof_names:
+                if not kwargs[n].is_cuda:
+                    raise PsbError(
+                        f"'{n}' lives on {kwargs[n].device}: the stepper kernels run on "
+                        "the GPU only (no CPU fallback)")
+            return True
+        raise TypeError("unknown arrays must be all torch.Tensor (device) or all "
+                        "numpy.ndarray (host scalar ODEs)")
+
+    def __call__(self, stage, queue=None, **kwargs):
+        raise NotImplementedError
+
+
+# ---------------------------------------------------------------------------
+# low-storage RK (pystella/step.py:441-528)
+# ---------------------------------------------------------------------------
+
+class LowStorageRKStepper(Stepper):
+    """
+    2N-storage Runge-Kutta: per unknown ``u`` with twin ``k``
+    ``k <- A[s]*k + dt*rhs ; u <- u + B[s]*k`` with all right-hand sides evaluated
+    from the old state (``pystella/step.py:473-491``).  Twins (``_<name>_tmp``) are
+    allocated zero-filled on the first call and kept in :attr:`tmp_arrays`
+    (``step.py:493-528``).
+    """
+
+    _A = []
+    _B = []
+    _C = []
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.tmp_arrays = {}
+        self._twins = {}        # fused: second padded buffer per stencilled unknown
+        self._halos_fresh = False
+        self._streams = None
+
+    def get_tmp_arrays_like(self, **kwargs):
+        """Zero-filled twins matching the unknown arrays passed by keyword."""
+        tmp_arrays = {}
+        for name in self.dof_names:
+            f = kwargs[name]
+            tmp_name = gen_tmp_name(name)
+            if isinstance(f, torch.Tensor):
+                tmp_arrays[tmp_name] = torch.zeros_like(f)
+            elif isinstance(f, np.ndarray):
+                tmp_arrays[tmp_name] = np.zeros_like(f)
+            else:
+                raise ValueError(f"Could not generate tmp array for {f}"
+                                 f"of type {type(f)}")
+        return tmp_arrays
+
+    def reset(self):
+        """Forget halo freshness (call after writing to ``f`` outside the stepper)."""
+        self._halos_fresh = False
+
+    def __call__(self, stage, *, queue=None, **kwargs):
+        if not 0 <= stage < self.num_stages:
+            raise IndexError(f"stage {stage} out of range for {type(self).__name__}")
+        kwargs.pop("filter_args", None)
+        kwargs.pop("allocator", None)
+        if len(self.tmp_arrays) == 0:
+            self.tmp_arrays = self.get_tmp_arrays_like(**kwargs)
+        if self._on_device(kwargs):
+            return self._device_stage(stage, queue, kwargs)
+        return self._host_stage(stage, kwargs)
+
+    # -- host scalar ODEs -------------------------------------------------------
+    def _host_stage(self, stage, kwargs):
+        ctx = dict(kwargs)
+        ctx.update(self.tmp_arrays)
+        if self.dt is not None:
+            ctx["dt"] = self.dt
+        dt = ctx["dt"]
+        A, B = self._A[stage], self._B[stage]
+        rhs = [np.array(evaluate(v, ctx), copy=True) for v in self.rhs_dict.values()]
+        for key, r in zip(self.rhs_dict.keys(), rhs):
+            fld, sub = _unknown_parts(key)
+            if isinstance(fld.child, Subscript):
+                sub = tuple(int(i) for i in fld.child.index) + sub
+            u = kwargs[fld.name]
+            k = self.tmp_arrays[gen_tmp_name(fld.name)]
+            idx = sub if sub else Ellipsis
+            k[idx] = A * k[idx] + dt * r
+            u[idx] = u[idx] + B * k[idx]
+        return None
+
+    # -- device ---------------------------------------------------------------
+    def _device_stage(self, stage, queue, kwargs):
+        dt = self._resolve_dt(kwargs)
+        A, B = self._A[stage], self._B[stage]
+        for system in self.systems:
+            system_stage = getattr(system, "run_stage", None)
+            if system_stage is not None:       # tensor sector etc.
+                system_stage(self, stage, queue, kwargs, dt, A, B)
+            else:
+                self._scalar_stage(system, stage, queue, kwargs, dt, A, B)
+        return None
+
+    def _scalars(self, system, kwargs):
+        out = {}
+        for which, expr in (("a", system.a), ("hubble", system.hubble)):
+            dev = None
+            if isinstance(expr, Field) and expr.name in kwargs \
+                    and isinstance(kwargs[expr.name], torch.Tensor):
+                dev = kwargs[expr.name]
+                if not (dev.is_cuda and dev.dtype == torch.float64 and dev.numel() == 1):
+                    raise ValueError(f"device scalar '{expr.name}' must be one float64")
+                out[which] = (1.0, dev)
+                continue
+            ctx = {n: _scalar_value(kwargs[n]) for n in system.scalar_names()
+                   if n in kwargs and not isinstance(kwargs[n], torch.Tensor)}
+            val = expr if is_constant(expr) else evaluate(expr, ctx)
+            out[which] = (float(val), None)
+        ctx = {n: _scalar_value(kwargs[n]) for n in system.scalar_names()
+               if n in kwargs and not isinstance(kwargs[n], torch.Tensor)}
+        dV = [[(c if is_constant(c) else float(evaluate(c, ctx)), p) for c, p in terms]
+              for terms in system.dV]
+        return out, dV
+
+    def _scalar_stage(self, system, stage, queue, kwargs, dt, A, B):
+        try:
+            f = kwargs[system.f_name]
+            dfdt = kwargs[system.dot_name]
+        except KeyError as e:
+            raise TypeError(f"missing array argument {e}") from None
+        kf = self.tmp_arrays[gen_tmp_name(system.f_name)]
+        kd = self.tmp_arrays[gen_tmp_name(system.dot_name)]
+        h = self.halo_shape
+        if h is None:
+            raise ValueError("pass halo_shape= when constructing a device stepper")
+        scal, dV = self._scalars(system, kwargs)
+        common = dict(dfdt=dfdt, kf=kf, kdfdt=kd, h=h, dt=dt, A=A, B=B,
+                      a=scal["a"][0], hubble=scal["hubble"][0],
+                      a_dev=scal["a"][1], hubble_dev=scal["hubble"][1],
+                      dV_terms=dV, queue=queue, strict=self.strict_fp)
+        if not self.fused:
+            lap = kwargs.get(system.lap_name)
+            if lap is None:
+                raise TypeError(
+                    f"missing array argument '{system.lap_name}' (the element-wise "
+                    "stage reads a precomputed Laplacian; use "
+                    "MapKernel=FusedStencilStage to compute it in-kernel)")
+            _kernels.scalar_stage(fused=False, f_in=f, f_out=f, lap_f=lap, **common)
+            return
+        from pystella_b200.fused import fused_scalar_stage
+        fused_scalar_stage(self, system, f, common, queue)
+
+
+class LowStorageRK54(LowStorageRKStepper):
+    """
+    Five-stage, fourth-order 2N-storage scheme of Carpenter & Kennedy (NASA TM
+    109112, 1994); coefficients as in ``pystella/step.py:543-557``.
+    """
+
+    num_stages = 5
+    expected_order = 4
+
+    _A = [
+        0,
+        -567301805773 / 1357537059087,
+        -2404267990393 / 2016746695238,
+        -3550918686646 / 2091501179385,
+        -1275806237668 / 842570457699,
+    ]
+
+    _B = [
+        1432997174477 / 9575080441755,
+        5161836677717 / 13612068292357,
+        1720146321549 / 2090206949498,
+        3134564353537 / 4481467310338,
+        2277821191437 / 14882151754819,
+    ]
+
+    _C = [
+        0,
+        1432997174477 / 9575080441755,
+        2526269341429 / 6820363962896,
+        2006345519317 / 3224310063776,
+        2802321613138 / 2924317926251,
+    ]
+
+
+def _load_long_tables():
+    """
+    The 12/13/14-stage schemes (``pystella/step.py:568-754``) are pure coefficient
+    tables; they are kept as data in ``lsrk_tables.json`` next to this module.
+    """
+    import json
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lsrk_tables.json")
+    with open(path) as fh:
+        return json.load(fh)
+
+
+_LONG = _load_long_tables()
+
+
+def _make_lsrk(name, doc):
+    tab = _LONG[name]
+    return type(name, (LowStorageRKStepper,), {
+        "__doc__": doc, "num_stages": tab["num_stages"],
+        "expected_order": tab["expected_order"],
+        "_A": tab["A"], "_B": tab["B"], "_C": tab["C"]})
+
+
+LowStorageRK144 = _make_lsrk(
+    "LowStorageRK144", "14-stage, fourth-order low-storage scheme optimised for "
+    "elliptic stability regions (Niegemann, Diehl & Busch 2012); step.py:568-628.")
+LowStorageRK134 = _make_lsrk(
+    "LowStorageRK134", "13-stage, fourth-order low-storage scheme optimised for "
+    "circular stability regions (Niegemann et al. 2012); step.py:631-690.")
+LowStorageRK124 = _make_lsrk(
+    "LowStorageRK124", "12-stage, fourth-order low-storage scheme optimised for "
+    "inviscid problems (Niegemann et al. 2012); step.py:693-754.")
+
+
+class LowStorageRK3Williamson(LowStorageRKStepper):
+    """Williamson (1980) three-stage third-order scheme; step.py:757-773."""
+    num_stages = 3
+    expected_order = 3
+    _A = [0, -5/9, -153/128]
+    _B = [1/3, 15/16, 8/15]
+    _C = [0, 4/9, 15/32]
+
+
+class LowStorageRK3Inhomogeneous(LowStorageRKStepper):
+    """Three-stage third-order scheme; step.py:776-788."""
+    num_stages = 3
+    expected_order = 3
+    _A = [0, -17/32, -32/27]
+    _B = [1/4, 8/9, 3/4]
+    _C = [0, 15/32, 4/9]
+
+
+class LowStorageRK3Symmetric(LowStorageRKStepper):
+    """step.py:791-800 (possible order reduction)."""
+    num_stages = 3
+    expected_order = 3
+    _A = [0, -2/3, -1]
+    _B = [1/3, 1, 1/2]
+    _C = [0, 1/3, 2/3]
+
+
+class LowStorageRK3PredictorCorrector(LowStorageRKStepper):
+    """step.py:803-812 (possible order reduction)."""
+    num_stages = 3
+    expected_order = 3
+    _A = [0, -1/4, -4/3]
+    _B = [1/2, 2/3, 1/2]
+    _C = [0, 1/2, 1]
+
+
+def _ssp3_coefficients():
+    # closed forms of step.py:815-833 in terms of the free parameter c2
+    c2 = .924574
+    z1 = np.sqrt(36 * c2**4 + 36 * c2**3 - 135 * c2**2 + 84 * c2 - 12)
+    z2 = 2 * c2**2 + c2 - 2
+    z3 = 12 * c2**4 - 18 * c2**3 + 18 * c2**2 - 11 * c2 + 2
+    z4 = 36 * c2**4 - 36 * c2**3 + 13 * c2**2 - 8 * c2 + 4
+    z5 = 69 * c2**3 - 62 * c2**2 + 28 * c2 - 8
+    z6 = 34 * c2**4 - 46 * c2**3 + 34 * c2**2 - 13 * c2 + 2
+    w = 3 * z2 - z1
+    B1 = c2
+    B2 = (12 * c2 * (c2 - 1) * w - w**2) / (144 * c2 * (3 * c2 - 2) * (c2 - 1)**2)
+    B3 = - 24 * (3 * c2 - 2) * (c2 - 1)**2 / (w**2 - 12 * c2 * (c2 - 1) * w)
+    A2 = ((- z1 * (6 * c2**2 - 4 * c2 + 1) + 3 * z3)
+          / ((2 * c2 + 1) * z1 - 3 * (c2 + 2) * (2 * c2 - 1)**2))
+    A3 = ((- z4 * z1 + 108 * (2 * c2 - 1) * c2**5 - 3 * (2 * c2 - 1) * z5)
+          / (24 * z1 * c2 * (c2 - 1)**4 + 72 * c2 * z6 + 72 * c2**6 * (2 * c2 - 13)))
+    return [0, A2, A3], [B1, B2, B3], [0, B1, B1 + B2 * (A2 + 1)]
+
+
+class LowStorageRK3SSP(LowStorageRKStepper):
+    """Strong-stability-preserving three-stage third-order scheme; step.py:836-846."""
+    num_stages = 3
+    expected_order = 3
+    _A, _B, _C = _ssp3_coefficients()
+
+
+# ---------------------------------------------------------------------------
+# classical RK with storage copies (pystella/step.py:173-411)
+# ---------------------------------------------------------------------------
+
+class RungeKuttaStepper(Stepper):
+    """
+    Classical explicit RK operating on ``num_copies`` copies of each unknown,
+    stored along a leading axis (``pystella/step.py:173-239``).  The right-hand
+    side reads copy 0 at stage 0 and copy 1 afterwards (``step.py:231``).
+    Subclasses provide :meth:`step_statements`: ``{copy: [(coef, src_copy), ...],
+    rhs_coef}`` per stage.
+
+    Host NumPy arrays only in this build (the reference exercises these on its C
+    target, ``test/test_step.py:42-99``); device runs use the low-storage family.
+    """
+
+    def step_statements(self, stage):
+        """-> list of ``(dst_copy, [(coef, src_copy), ...], dt_coef)`` in order."""
+        raise NotImplementedError
+
+    def __call__(self, stage, queue=None, **kwargs):
+        if not 0 <= stage < self.num_stages:
+            raise IndexError(f"stage {stage} out of range for {type(self).__name__}")
+        kwargs.pop("filter_args", None)
+        if self._on_device(kwargs):
+            raise NotImplementedError(
+                f"{type(self).__name__} on device arrays: classical RK with storage "
+                "copies is host-only in this build; use a LowStorageRK* stepper")
+        ctx = dict(kwargs)
+        if self.dt is not None:
+            ctx["dt"] = self.dt
+        dt = ctx["dt"]
+        q = 0 if stage == 0 else 1
+        names = self.dof_names
+        rctx = dict(ctx)
+        for n in names:
+            rctx[n] = kwargs[n][q]
+        rhs = [np.array(evaluate(v, rctx), copy=True) for v in self.rhs_dict.values()]
+        for key, r in zip(self.rhs_dict.keys(), rhs):
+            fld, sub = _unknown_parts(key)
+            arr = kwargs[fld.name]
+            new = {}
+            for dst, combo, c_dt in self.step_statements(stage):
+                val = sum(c * arr[(src,) + sub] for c, src in combo) + c_dt * dt * r
+                new[dst] = val
+            for dst, val in new.items():
+                arr[(dst,) + sub] = val
+        return None
+
+
+class RungeKutta4(RungeKuttaStepper):
+    """Classical four-stage fourth-order method, three copies; step.py:242-265."""
+    num_stages, expected_order, num_copies = 4, 4, 3
+
+    def step_statements(self, stage):
+        return [
+            [(1, [(1, 0)], 1/2), (2, [(1, 0)], 1/6)],
+            [(1, [(1, 0)], 1/2), (2, [(1, 2)], 1/3)],
+            [(1, [(1, 0)], 1), (2, [(1, 2)], 1/3)],
+            [(0, [(1, 2)], 1/6)],
+        ][stage]
+
+
+class RungeKutta3Heun(RungeKuttaStepper):
+    """Heun's third-order method; step.py:268-285."""
+    num_stages, expected_order, num_copies = 3, 3, 3
+
+    def step_statements(self, stage):
+        return [
+            [(1, [(1, 0)], 1/3), (2, [(1, 0)], 1/4)],
+            [(1, [(1, 0)], 2/3)],
+            [(0, [(1, 2)], 3/4)],
+        ][stage]
+
+
+class RungeKutta3Nystrom(RungeKuttaStepper):
+    """Nystrom's third-order method; step.py:288-307."""
+    num_stages, expected_order, num_copies = 3, 3, 3
+
+    def step_statements(self, stage):
+        return [
+            [(1, [(1, 0)], 2/3), (2, [(1, 0)], 2/8)],
+            [(1, [(1, 0)], 2/3), (2, [(1, 2)], 3/8)],
+            [(0, [(1, 2)], 3/8)],
+        ][stage]
+
+
+class RungeKutta3Ralston(RungeKuttaStepper):
+    """Ralston's third-order method; step.py:310-329."""
+    num_stages, expected_order, num_copies = 3, 3, 3
+
+    def step_statements(self, stage):
+        return [
+            [(1, [(1, 0)], 1/2), (2, [(1, 0)], 2/9)],
+            [(1, [(1, 0)], 3/4), (2, [(1, 2)], 1/3)],
+            [(0, [(1, 2)], 4/9)],
+        ][stage]
+
+
+class RungeKutta3SSP(RungeKuttaStepper):
+    """Three-stage third-order SSP method, two copies; step.py:332-350."""
+    num_stages, expected_order, num_copies = 3, 3, 2
+
+    def step_statements(self, stage):
+        return [
+            [(1, [(1, 0)], 1)],
+            [(1, [(3/4, 0), (1/4, 1)], 1/4)],
+            [(0, [(1/3, 0), (2/3, 1)], 2/3)],
+        ][stage]
+
+
+class RungeKutta2Midpoint(RungeKuttaStepper):
+    """Midpoint method; step.py:353-370."""
+    num_stages, expected_order, num_copies = 2, 2, 2
+
+    def step_statements(self, stage):
+        return [
+            [(1, [(1, 0)], 1/2)],
+            [(0, [(1, 0)], 1)],
+        ][stage]
+
+
+class RungeKutta2Heun(RungeKuttaStepper):
+    """Heun's second-order method (possible order reduction); step.py:374-387."""
+    num_stages, expected_order, num_copies = 2, 2, 2
+
+    def step_statements(self, stage):
+        return [
+            [(1, [(1, 0)], 1), (0, [(1, 0)], 1/2)],
+            [(0, [(1, 0)], 1/2)],
+        ][stage]
+
+
+class RungeKutta2Ralston(RungeKuttaStepper):
+    """Ralston's second-order method; step.py:390-408."""
+    num_stages, expected_order, num_copies = 2, 2, 2
+
+    def step_statements(self, stage):
+        return [
+            [(1, [(1, 0)], 2/3), (0, [(1, 0)], 1/4)],
+            [(0, [(1, 0)], 3/4)],
+        ][stage]
+
+
+all_steppers = [RungeKutta4, RungeKutta3SSP, RungeKutta3Heun, RungeKutta3Nystrom,
+                RungeKutta3Ralston, RungeKutta2Midpoint,
+                RungeKutta2Ralston, LowStorageRK54, LowStorageRK144,
+                LowStorageRK3Williamson, LowStorageRK3Inhomogeneous,
+                LowStorageRK3SSP]
