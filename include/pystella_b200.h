@@ -34,6 +34,7 @@ extern "C" {
 
 #define PSB_MAX_SCALARS 4      /* fields per ScalarSector handled by one launch   */
 #define PSB_MAX_TERMS 16       /* monomials of dV/df_n per field                  */
+#define PSB_ENERGY_STRIDE 16    /* doubles per energy-partials row (>= 2*MAX_SCALARS+1) */
 #define PSB_MAX_RED_ARRAYS 8   /* distinct input arrays of one reduction launch   */
 #define PSB_MAX_RED_TERMS 32   /* monomials over all outputs of one reduction     */
 #define PSB_MAX_RED_OUTPUTS 16 /* reductions per launch                           */
@@ -98,9 +99,17 @@ typedef struct psb_scalar_stage_args {
   int32_t nterms[PSB_MAX_SCALARS];
   double coef[PSB_MAX_SCALARS][PSB_MAX_TERMS];
   int8_t power[PSB_MAX_SCALARS][PSB_MAX_TERMS][PSB_MAX_SCALARS];
-  /* optional fused energy partial sums of the INPUT state (may be NULL):
-   * per launch-block partials, see psb_scalar_stage_energy_slots() */
+  /* Optional fused energy sums of the INPUT (pre-stage) state, fused kernel only
+   * (ScalarSector.reducers, pystella/sectors.py:133-144, without the a-dependent
+   * prefactors): per CTA  {sum dfdt_n^2 | n}, sum V(f), {sum -f_n*lap(f_n) | n}.
+   * energy_partials (may be NULL) holds psb_scalar_stage_energy_slots() rows of
+   * PSB_ENERGY_STRIDE doubles starting at row energy_slot_offset.  V is the
+   * polynomial sum_t vcoef[t] * prod_m f_m^vpower[t][m]. */
   double* energy_partials;
+  int64_t energy_slot_offset;
+  int32_t nvterms;
+  double vcoef[PSB_MAX_TERMS];
+  int8_t vpower[PSB_MAX_TERMS][PSB_MAX_SCALARS];
   int32_t tune_xchunk;           /* 0 = default; planes marched per CTA              */
   int32_t tune_variant;          /* 0 = auto; see DESIGN.md (kernel variants)        */
 } psb_scalar_stage_args;
@@ -171,10 +180,39 @@ typedef struct psb_reduce_args {
 int64_t psb_reduce_workspace_doubles(int noutputs);
 int psb_reduce(const psb_reduce_args* args, void* stream);
 
-/* Sum per-block energy partials written by psb_scalar_stage_fused into
- * out[0..2*nscalars] = {kinetic_n..., potential, gradient_n...} (already
- * divided by grid_size; ScalarSector.reducers, pystella/sectors.py:133-144). */
+/* Number of energy-partial rows one psb_scalar_stage_fused launch with these
+ * args writes (one per CTA). */
 int64_t psb_scalar_stage_energy_slots(const psb_scalar_stage_args* args);
+
+/* ------------------------------------------------------------------------
+ * Device-resident FLRW background (replaces, per RK stage, the host round trip
+ * Reduction.__call__ -> Expansion.step of examples/scalar_preheating.py:263-264:
+ * pystella/reduction.py:237-255, pystella/sectors.py:211-229,
+ * pystella/expansion.py:101-157).
+ *
+ * psb_energy_sums folds `nslots` partial rows into sums[0..nvals) in a fixed
+ * order (single CTA).  psb_expansion_stage (single thread) then forms, with the
+ * CURRENT scale factor a = state[0]:
+ *     kinetic_n  = sums[n]        / (2 a^2) / grid_size
+ *     potential  = sums[ns]                 / grid_size
+ *     gradient_n = sums[ns+1+n]   / (2 a^2) / grid_size
+ *     total = sum of all ; pressure = sum kinetic - sum gradient / 3 - potential
+ * writes energies[0..2ns+3) = {kinetic.., potential, gradient.., total, pressure}
+ * and advances (a, adot) by one low-storage RK stage of
+ *     a' = adot ; adot' = 4 pi a^2 / (3 mpl^2) (total - 3 pressure) a
+ * with twins (ka, kadot), then hubble = adot / a.
+ * state = {a, adot, hubble, ka, kadot} (5 doubles on the device).
+ * Between the two calls a multi-rank job all-reduces sums[0..nvals).
+ * ---------------------------------------------------------------------- */
+int psb_energy_sums(const double* partials, int64_t nslots, int nvals, double* sums,
+                    void* stream);
+int psb_expansion_stage(const double* sums, int nscalars, double grid_size, double mpl,
+                        double dt, double A, double B, double* state, double* energies,
+                        void* stream);
+/* adot = sqrt(8 pi a^2 rho / (3 mpl^2)) a from energies (first Friedmann equation,
+ * pystella/expansion.py:101-117): initialises state = {a, adot, hubble, 0, 0}. */
+int psb_expansion_init(const double* sums, int nscalars, double grid_size, double mpl,
+                       double a0, double* state, double* energies, void* stream);
 
 #ifdef __cplusplus
 }

@@ -24,7 +24,7 @@ from pystella_b200.derivs import (FiniteDifferencer, FirstCenteredDifference,
                                   centered_diff)
 from pystella_b200.decomp import DomainDecomposition
 from pystella_b200.reduction import Reduction, FieldStatistics
-from pystella_b200.expansion import Expansion
+from pystella_b200.expansion import Expansion, DeviceExpansion
 from pystella_b200._lib import PsbError
 
 __version__ = "0.1.0"
@@ -59,5 +59,6 @@ __all__ = [
     "FiniteDifferencer", "FirstCenteredDifference", "SecondCenteredDifference",
     "expand_stencil", "centered_diff",
     "DomainDecomposition", "Reduction", "FieldStatistics", "Expansion",
+    "DeviceExpansion",
     "PsbError", "choose_device",
 ]

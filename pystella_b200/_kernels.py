@@ -37,7 +37,9 @@ def fill_potential(args, dV_terms, nscalars):
 def scalar_stage(*, fused, f_in, f_out, dfdt, kf, kdfdt, lap_f=None, h, dx=(1., 1., 1.),
                  dt, A, B, a=1., hubble=0., a_dev=None, hubble_dev=None,
                  dV_terms=None, wrap=(True, True, True), x_range=None,
-                 queue=None, strict=False, xchunk=0, variant=0):
+                 queue=None, strict=False, xchunk=0, variant=0,
+                 energy_partials=None, energy_slot_offset=0, V_terms=None,
+                 count_slots_only=False):
     """
     One scalar-sector LSRK stage on padded arrays of shape ``(n, Nx+2h, Ny+2h, Nz+2h)``
     (or without the leading axis for a single field).
@@ -90,6 +92,24 @@ def scalar_stage(*, fused, f_in, f_out, dfdt, kf, kdfdt, lap_f=None, h, dx=(1., 
     fill_potential(args, dV_terms, nscalars)
     args.tune_xchunk = xchunk
     args.tune_variant = variant
+    if V_terms is not None:
+        if len(V_terms) > _lib.MAX_TERMS:
+            raise ValueError(f"V has {len(V_terms)} monomials; at most {_lib.MAX_TERMS}")
+        args.nvterms = len(V_terms)
+        for t, (c, powers) in enumerate(V_terms):
+            args.vcoef[t] = float(c)
+            for m in range(nscalars):
+                args.vpower[t][m] = int(powers[m])
+    if count_slots_only:
+        n = lib.psb_scalar_stage_energy_slots(C.byref(args))
+        if n < 0:
+            _lib.check(lib, 1, "psb_scalar_stage_energy_slots")
+        return n
+    if energy_partials is not None:
+        if not fused:
+            raise ValueError("energy partials come from the fused stage only")
+        args.energy_partials = _ptr(energy_partials)
+        args.energy_slot_offset = energy_slot_offset
     fn = lib.psb_scalar_stage_fused if fused else lib.psb_scalar_stage_unfused
     rc = fn(C.byref(args), _lib.stream_ptr(queue))
     _lib.check(lib, rc, fn.__name__)
@@ -207,3 +227,28 @@ def reduce_poly(arrays, halos, terms, ops, flags, shape, queue=None, strict=Fals
     rc = lib.psb_reduce(C.byref(args), _lib.stream_ptr(queue))
     _lib.check(lib, rc, "psb_reduce")
     return out
+
+
+def energy_sums(partials, nslots, nvals, sums, queue=None, strict=False):
+    lib = _lib.load(strict)
+    rc = lib.psb_energy_sums(_ptr(partials), nslots, nvals, _ptr(sums),
+                             _lib.stream_ptr(queue))
+    _lib.check(lib, rc, "psb_energy_sums")
+
+
+def expansion_stage(sums, nscalars, grid_size, mpl, dt, A, B, state, energies, queue=None,
+                    strict=False):
+    lib = _lib.load(strict)
+    rc = lib.psb_expansion_stage(_ptr(sums), nscalars, float(grid_size), float(mpl),
+                                 float(dt), float(A), float(B), _ptr(state),
+                                 _ptr(energies), _lib.stream_ptr(queue))
+    _lib.check(lib, rc, "psb_expansion_stage")
+
+
+def expansion_init(sums, nscalars, grid_size, mpl, a0, state, energies, queue=None,
+                   strict=False):
+    lib = _lib.load(strict)
+    rc = lib.psb_expansion_init(_ptr(sums), nscalars, float(grid_size), float(mpl),
+                                float(a0), _ptr(state), _ptr(energies),
+                                _lib.stream_ptr(queue))
+    _lib.check(lib, rc, "psb_expansion_init")

@@ -18,6 +18,7 @@ MAX_TERMS = 16
 MAX_RED_ARRAYS = 8
 MAX_RED_TERMS = 32
 MAX_RED_OUTPUTS = 16
+ENERGY_STRIDE = 16
 
 c_void_p, c_int, c_int32, c_int64, c_double = (
     C.c_void_p, C.c_int, C.c_int32, C.c_int64, C.c_double)
@@ -40,6 +41,10 @@ class ScalarStageArgs(C.Structure):
         ("coef", (c_double * MAX_TERMS) * MAX_SCALARS),
         ("power", ((C.c_int8 * MAX_SCALARS) * MAX_TERMS) * MAX_SCALARS),
         ("energy_partials", c_void_p),
+        ("energy_slot_offset", c_int64),
+        ("nvterms", c_int32),
+        ("vcoef", c_double * MAX_TERMS),
+        ("vpower", (C.c_int8 * MAX_SCALARS) * MAX_TERMS),
         ("tune_xchunk", c_int32), ("tune_variant", c_int32),
     ]
 
@@ -84,6 +89,11 @@ SYMBOLS = {
     "psb_reduce_workspace_doubles": (c_int64, [c_int]),
     "psb_reduce": (c_int, [C.POINTER(ReduceArgs), c_void_p]),
     "psb_scalar_stage_energy_slots": (c_int64, [C.POINTER(ScalarStageArgs)]),
+    "psb_energy_sums": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p]),
+    "psb_expansion_stage": (c_int, [c_void_p, c_int, c_double, c_double, c_double,
+                                    c_double, c_double, c_void_p, c_void_p, c_void_p]),
+    "psb_expansion_init": (c_int, [c_void_p, c_int, c_double, c_double, c_double,
+                                   c_void_p, c_void_p, c_void_p]),
 }
 
 

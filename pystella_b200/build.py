@@ -26,8 +26,8 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
           "-I" + os.path.join(ROOT, "include"), "-I" + CSRC]
 
-SOURCES = ["common.cu", "fused_stage.cu", "stage_unfused.cu", "fd.cu", "halo.cu",
-           "reduce.cu"]
+SOURCES = ["common.cu", "fused_stage.cu", "fused_stage_f64.cu", "fused_stage_f32.cu",
+           "stage_unfused.cu", "fd.cu", "halo.cu", "reduce.cu", "expansion.cu"]
 
 
 def _digest(paths, extra):

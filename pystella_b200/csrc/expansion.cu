@@ -1,0 +1,137 @@
+// Device-resident FLRW background: folds the fused stage's energy partials and
+// advances (a, adot) by one low-storage RK stage without leaving the GPU.
+// Replaces, per stage, Reduction.__call__ -> get_rho_and_p -> Expansion.step
+// (pystella/reduction.py:237-255, pystella/sectors.py:211-229,
+// pystella/expansion.py:101-157) and the blocking device-to-host reads between.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace psb {
+
+__global__ void __launch_bounds__(256)
+    energy_sums_kernel(const double* __restrict__ partials, int64_t nslots, int nvals,
+                       double* __restrict__ sums) {
+  __shared__ double sh[8];
+  for (int r = 0; r < nvals; ++r) {
+    double x = 0.0;
+    for (int64_t b = threadIdx.x; b < nslots; b += blockDim.x)
+      x += partials[b * PSB_ENERGY_STRIDE + r];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = x;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double y = sh[0];
+      for (int w = 1; w < 8; ++w) y += sh[w];
+      sums[r] = y;
+    }
+    __syncthreads();
+  }
+}
+
+struct Energies {
+  double total, pressure;
+};
+
+__device__ inline Energies form_energies(const double* sums, int ns, double grid_size,
+                                         double a, double* energies) {
+  // kinetic_n = <dfdt_n^2> / 2 / a^2 ; potential = <V> ; gradient_n = <-f lap f> / 2 / a^2
+  const double a2 = a * a;
+  double kin = 0.0, grad = 0.0;
+  for (int n = 0; n < ns; ++n) {
+    const double k = sums[n] / 2.0 / a2 / grid_size;
+    const double g = sums[ns + 1 + n] / 2.0 / a2 / grid_size;
+    energies[n] = k;
+    energies[ns + 1 + n] = g;
+    kin += k;
+    grad += g;
+  }
+  const double pot = sums[ns] / grid_size;
+  energies[ns] = pot;
+  Energies e;
+  e.total = kin + pot + grad;
+  e.pressure = kin - grad / 3.0 - pot;
+  energies[2 * ns + 1] = e.total;
+  energies[2 * ns + 2] = e.pressure;
+  return e;
+}
+
+__global__ void expansion_stage_kernel(const double* sums, int ns, double grid_size,
+                                       double mpl, double dt, double A, double B,
+                                       double* state, double* energies) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double a = state[0], adot = state[1], ka = state[3], kadot = state[4];
+  const Energies e = form_energies(sums, ns, grid_size, a, energies);
+  const double pi = 3.141592653589793;
+  // a' = adot ; adot' = 4 pi a^2 / 3 / mpl^2 (rho - 3 P) a   (expansion.py:119-138)
+  const double rhs_a = adot;
+  const double rhs_adot = 4.0 * pi * (a * a) / 3.0 / (mpl * mpl) *
+                          (e.total - 3.0 * e.pressure) * a;
+  ka = A * ka + dt * rhs_a;
+  a = a + B * ka;
+  kadot = A * kadot + dt * rhs_adot;
+  adot = adot + B * kadot;
+  state[0] = a;
+  state[1] = adot;
+  state[2] = adot / a;
+  state[3] = ka;
+  state[4] = kadot;
+}
+
+__global__ void expansion_init_kernel(const double* sums, int ns, double grid_size,
+                                      double mpl, double a0, double* state,
+                                      double* energies) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const Energies e = form_energies(sums, ns, grid_size, a0, energies);
+  const double pi = 3.141592653589793;
+  // adot = sqrt(8 pi a^2 / 3 / mpl^2 * rho) * a   (expansion.py:101-117)
+  const double adot = sqrt(8.0 * pi * (a0 * a0) / 3.0 / (mpl * mpl) * e.total) * a0;
+  state[0] = a0;
+  state[1] = adot;
+  state[2] = adot / a0;
+  state[3] = 0.0;
+  state[4] = 0.0;
+}
+
+}  // namespace psb
+
+extern "C" int psb_energy_sums(const double* partials, int64_t nslots, int nvals,
+                               double* sums, void* stream) {
+  using namespace psb;
+  PSB_REQUIRE(partials && sums, "psb_energy_sums: null pointer");
+  PSB_REQUIRE(nslots > 0 && nvals > 0 && nvals <= PSB_ENERGY_STRIDE,
+              "psb_energy_sums: bad sizes (nslots=%lld, nvals=%d)", (long long)nslots, nvals);
+  energy_sums_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(partials, nslots,
+                                                                      nvals, sums);
+  PSB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int psb_expansion_stage(const double* sums, int nscalars, double grid_size,
+                                   double mpl, double dt, double A, double B, double* state,
+                                   double* energies, void* stream) {
+  using namespace psb;
+  PSB_REQUIRE(sums && state && energies, "psb_expansion_stage: null pointer");
+  PSB_REQUIRE(nscalars >= 1 && nscalars <= PSB_MAX_SCALARS,
+              "psb_expansion_stage: nscalars=%d out of range", nscalars);
+  PSB_REQUIRE(grid_size > 0 && mpl > 0, "psb_expansion_stage: bad grid_size/mpl");
+  expansion_stage_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(
+      sums, nscalars, grid_size, mpl, dt, A, B, state, energies);
+  PSB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int psb_expansion_init(const double* sums, int nscalars, double grid_size,
+                                  double mpl, double a0, double* state, double* energies,
+                                  void* stream) {
+  using namespace psb;
+  PSB_REQUIRE(sums && state && energies, "psb_expansion_init: null pointer");
+  PSB_REQUIRE(nscalars >= 1 && nscalars <= PSB_MAX_SCALARS,
+              "psb_expansion_init: nscalars=%d out of range", nscalars);
+  PSB_REQUIRE(grid_size > 0 && mpl > 0 && a0 > 0, "psb_expansion_init: bad scalars");
+  expansion_init_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(
+      sums, nscalars, grid_size, mpl, a0, state, energies);
+  PSB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

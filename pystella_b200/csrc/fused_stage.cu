@@ -1,472 +1,12 @@
-// Fused finite-difference Laplacian + scalar-sector RHS + low-storage RK stage.
-//
-// One kernel per RK stage (replaces the reference's per-stage pair
-// FiniteDifferencer.__call__ -> Stepper.__call__, pystella/derivs.py:339-429 and
-// pystella/step.py:473-491, 524-528).  Each CTA owns a (BY x BZ) column of the
-// rank-local grid and marches along x:
-//
-//   * the padded f planes (with y/z halos) stream through a ring of shared-memory
-//     slots, filled by TMA (cp.async.bulk.tensor, one elected thread, mbarrier
-//     completion) P planes ahead of the compute front;
-//   * x-neighbours live in a per-thread register queue (2H+1 planes deep), y/z
-//     neighbours are read from the centre plane in shared memory;
-//   * dfdt / kf / kdfdt never need neighbours: they are read straight from HBM
-//     into registers as 16-byte vectors one plane ahead, and written back in place;
-//   * the new f goes to a second padded buffer (f_out) together with its periodic
-//     images on the face halos ("write-through halos").
-//
-// HBM traffic per site and stage: read f, dfdt, kf, kdfdt; write f, dfdt, kf,
-// kdfdt = 8*sizeof(T) (6*sizeof(T) when A == 0: the twins are not read).
-#include <math.h>
-#include <string.h>
-
+// C-ABI entry points of the fused stage; the kernels live in fused_stage_impl.cuh
+// and are instantiated per dtype in fused_stage_f64.cu / fused_stage_f32.cu.
 #include "common.cuh"
 
 namespace psb {
+int fused_dispatch_f64(const psb_scalar_stage_args* a, cudaStream_t s, int64_t* count);
+int fused_dispatch_f32(const psb_scalar_stage_args* a, cudaStream_t s, int64_t* count);
 
-template <typename T, int NF> struct FusedParams {
-  const T* f_in;
-  T* f_out;
-  T* dfdt;
-  T* kf;
-  T* kdfdt;
-  int64_t field_stride;
-  int Nx, Ny, Nz;
-  int x_begin, x_end, xchunk;
-  int wrap_x, wrap_y, wrap_z;
-  T inv_dx2[3];
-  T dt, A, B, a, hubble;
-  const double* a_dev;
-  const double* hubble_dev;
-  int nterms[NF];
-  T coef[NF][PSB_MAX_TERMS];
-  int8_t power[NF][PSB_MAX_TERMS][NF];
-  double* energy_partials;
-};
-
-template <typename T, int VEC>
-__device__ __forceinline__ Vec<T, VEC> ld_stream(const T* p) {
-  Vec<T, VEC> r;
-  if constexpr (sizeof(T) * VEC == 16) {
-    float4 x = __ldcs(reinterpret_cast<const float4*>(p));
-    r = *reinterpret_cast<Vec<T, VEC>*>(&x);
-  } else if constexpr (sizeof(T) * VEC == 8) {
-    float2 x = __ldcs(reinterpret_cast<const float2*>(p));
-    r = *reinterpret_cast<Vec<T, VEC>*>(&x);
-  } else {
-    float x = __ldcs(reinterpret_cast<const float*>(p));
-    r = *reinterpret_cast<Vec<T, VEC>*>(&x);
-  }
-  return r;
-}
-
-template <typename T, int VEC>
-__device__ __forceinline__ void st_stream(T* p, const Vec<T, VEC>& v) {
-  if constexpr (sizeof(T) * VEC == 16) {
-    __stcs(reinterpret_cast<float4*>(p), *reinterpret_cast<const float4*>(&v));
-  } else if constexpr (sizeof(T) * VEC == 8) {
-    __stcs(reinterpret_cast<float2*>(p), *reinterpret_cast<const float2*>(&v));
-  } else {
-    __stcs(reinterpret_cast<float*>(p), *reinterpret_cast<const float*>(&v));
-  }
-}
-
-// plain (L2-allocating) store: f_out is re-read by the next stage
-template <typename T, int VEC>
-__device__ __forceinline__ void st_plain(T* p, const Vec<T, VEC>& v) {
-  *reinterpret_cast<Vec<T, VEC>*>(p) = v;
-}
-
-template <typename T, int H, int NF, int VEC, int BY, int TZ, int P>
-struct FusedCfg {
-  static constexpr int BZ = TZ * VEC;
-  static constexpr int HL = ((H + VEC - 1) / VEC) * VEC;  // aligned left pad
-  static constexpr int WQ = 16 / (int)sizeof(T);          // TMA rows: multiple of 16 B
-  static constexpr int W = ((BZ + 2 * HL + WQ - 1) / WQ) * WQ;  // smem row length
-  static constexpr int ROWS = BY + 2 * H;
-  static constexpr int R = H + 1 + P;                     // ring slots
-  static constexpr int PLANE_BYTES_RAW = ROWS * W * (int)sizeof(T);
-  static constexpr int PLANE_BYTES = ((PLANE_BYTES_RAW + 127) / 128) * 128;
-  static constexpr int PLANE = PLANE_BYTES / (int)sizeof(T);
-  static constexpr int THREADS = BY * TZ;
-  static constexpr int SMEM_BYTES = R * NF * PLANE_BYTES + R * 8 + 128;
-  static_assert((W * sizeof(T)) % 16 == 0, "TMA box row must be a multiple of 16 B");
-};
-
-template <typename T, int H, int NF, int VEC, int BY, int TZ, int P, bool USE_TMA,
-          int MINB>
-__global__ void __launch_bounds__(BY* TZ, MINB)
-    fused_stage_kernel(const __grid_constant__ FusedParams<T, NF> p,
-                       const __grid_constant__ CUtensorMap tmap) {
-  using C = FusedCfg<T, H, NF, VEC, BY, TZ, P>;
-  using V = Vec<T, VEC>;
-  constexpr int R = C::R, W = C::W, HL = C::HL;
-
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  // align dynamic smem base to 128 B for TMA destinations
-  unsigned char* base = smem_raw + ((128 - (smem_u32(smem_raw) & 127)) & 127);
-  T* ring = reinterpret_cast<T*>(base);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(base + R * NF * C::PLANE_BYTES);
-
-  const int tz = threadIdx.x, ty = threadIdx.y;
-  const int tid = ty * TZ + tz;
-  const int z0 = blockIdx.x * C::BZ, y0 = blockIdx.y * BY;
-  const int xs = p.x_begin + blockIdx.z * p.xchunk;
-  const int xe = min(xs + p.xchunk, p.x_end);
-  const int nsteps = (xe - xs) + 2 * H;
-
-  const int j = y0 + ty, k = z0 + tz * VEC;
-  const bool active = (j < p.Ny) && (k < p.Nz);
-  const int64_t Pz = p.Nz + 2 * H, Py = p.Ny + 2 * H;
-  const int64_t plane_stride = Py * Pz;
-  // offset of site (i=0, j, k) in a padded array
-  const int64_t site0 = ((int64_t)H * Py + (j + H)) * Pz + (k + H);
-
-  T a = p.a, hubble = p.hubble;
-  if (p.a_dev) a = (T)(*p.a_dev);
-  if (p.hubble_dev) hubble = (T)(*p.hubble_dev);
-  const T two_h = (T)2 * hubble;
-  const T a_sq = a * a;
-  const bool read_k = (p.A != (T)0);
-
-  auto issue_plane = [&](int n) {
-    // plane arriving at step n: interior x index xs - H + n -> padded index xs + n
-    const int slot = n % R;
-    if constexpr (USE_TMA) {
-      mbar_expect_tx(&bars[slot], NF * C::PLANE_BYTES_RAW);
-#pragma unroll
-      for (int f = 0; f < NF; ++f)
-        tma_load_4d(ring + (slot * NF + f) * C::PLANE, &tmap, &bars[slot],
-                    z0 + H - HL, y0, xs + n, f);
-    }
-  };
-
-  auto coop_load_plane = [&](int n) {
-    // generic loader (layouts TMA cannot describe): all threads, zero fill OOB
-    const int slot = n % R;
-    const int px = xs + n;
-    for (int f = 0; f < NF; ++f) {
-      T* dst = ring + (slot * NF + f) * C::PLANE;
-      const T* src = p.f_in + f * p.field_stride + (int64_t)px * plane_stride;
-      for (int e = tid; e < C::ROWS * W; e += C::THREADS) {
-        const int r = e / W, c = e % W;
-        const int gy = y0 + r, gz = z0 + H - HL + c;
-        T val = (T)0;
-        if (gy < Py && gz >= 0 && gz < Pz) val = src[(int64_t)gy * Pz + gz];
-        dst[e] = val;
-      }
-    }
-  };
-
-  if constexpr (USE_TMA) {
-    if (tid == 0) {
-      tma_prefetch_desc(&tmap);
-      for (int s = 0; s < R; ++s) mbar_init(&bars[s], 1);
-      fence_barrier_init();
-    }
-    __syncthreads();
-    if (tid == 0) {
-      for (int n = 0; n <= P && n < nsteps; ++n) issue_plane(n);
-    }
-  } else {
-    for (int n = 0; n <= P && n < nsteps; ++n) coop_load_plane(n);
-    __syncthreads();
-  }
-
-  V q[NF][2 * H + 1];
-  V cur_d[NF], cur_kf[NF], cur_kd[NF];
-  V nxt_d[NF], nxt_kf[NF], nxt_kd[NF];
-#pragma unroll
-  for (int f = 0; f < NF; ++f) {
-#pragma unroll
-    for (int s = 0; s < 2 * H + 1; ++s)
-#pragma unroll
-      for (int v = 0; v < VEC; ++v) q[f][s].v[v] = (T)0;
-#pragma unroll
-    for (int v = 0; v < VEC; ++v) {
-      cur_d[f].v[v] = cur_kf[f].v[v] = cur_kd[f].v[v] = (T)0;
-      nxt_d[f].v[v] = nxt_kf[f].v[v] = nxt_kd[f].v[v] = (T)0;
-    }
-  }
-
-  const int own_off = (ty + H) * W + HL + tz * VEC;
-
-  for (int n = 0; n < nsteps; ++n) {
-    const int i = xs - 2 * H + n;  // site plane computed at this step (if n >= 2H)
-
-    // (1) prefetch next plane's pointwise arrays
-    if (active && (n + 1 >= 2 * H) && (i + 1 < xe)) {
-      const int64_t off = site0 + (int64_t)(i + 1) * plane_stride;
-#pragma unroll
-      for (int f = 0; f < NF; ++f) {
-        const int64_t o = off + f * p.field_stride;
-        nxt_d[f] = ld_stream<T, VEC>(p.dfdt + o);
-        if (read_k) {
-          nxt_kf[f] = ld_stream<T, VEC>(p.kf + o);
-          nxt_kd[f] = ld_stream<T, VEC>(p.kdfdt + o);
-        }
-      }
-    }
-
-    // (2) wait for the f plane of this step, push own values into the x queue
-    const int slot = n % R;
-    if constexpr (USE_TMA) mbar_wait(&bars[slot], (n / R) & 1);
-#pragma unroll
-    for (int f = 0; f < NF; ++f) {
-#pragma unroll
-      for (int s = 0; s < 2 * H; ++s) q[f][s] = q[f][s + 1];
-      q[f][2 * H] = ld_vec<T, VEC>(ring + (slot * NF + f) * C::PLANE + own_off);
-    }
-
-    // (3) compute
-    if (n >= 2 * H && active) {
-      const int cslot = (n - H) % R;
-      V lap[NF];
-#pragma unroll
-      for (int f = 0; f < NF; ++f) {
-        const T* pl = ring + (cslot * NF + f) * C::PLANE;
-        constexpr int NV = 1 + 2 * (HL / VEC);  // vectors covering the z neighbourhood
-        T zrow[NV * VEC];
-#pragma unroll
-        for (int w = 0; w < NV; ++w) {
-          V t = ld_vec<T, VEC>(pl + own_off - HL + w * VEC);
-#pragma unroll
-          for (int v = 0; v < VEC; ++v) zrow[w * VEC + v] = t.v[v];
-        }
-        V yn[2 * H + 1];
-#pragma unroll
-        for (int s = 1; s <= H; ++s) {
-          yn[H + s] = ld_vec<T, VEC>(pl + own_off + s * W);
-          yn[H - s] = ld_vec<T, VEC>(pl + own_off - s * W);
-        }
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) {
-          const T c = q[f][H].v[v];
-          // term order of the reference: c0*f0, c1*f[+1], c1*f[-1], c2*f[+2], ...
-          T sx = (T)lap_coef<H>(0) * c;
-          T sy = (T)lap_coef<H>(0) * c;
-          T sz = (T)lap_coef<H>(0) * c;
-#pragma unroll
-          for (int s = 1; s <= H; ++s) {
-            const T cs = (T)lap_coef<H>(s);
-            sx = sx + cs * q[f][H + s].v[v];
-            sx = sx + cs * q[f][H - s].v[v];
-            sy = sy + cs * yn[H + s].v[v];
-            sy = sy + cs * yn[H - s].v[v];
-            sz = sz + cs * zrow[HL + v + s];
-            sz = sz + cs * zrow[HL + v - s];
-          }
-          lap[f].v[v] = sx * p.inv_dx2[0] + sy * p.inv_dx2[1] + sz * p.inv_dx2[2];
-        }
-      }
-
-      const int64_t off = site0 + (int64_t)i * plane_stride;
-#pragma unroll
-      for (int f = 0; f < NF; ++f) {
-        V fo, dn, kfn, kdn;
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) {
-          // dV/df_f = sum_t coef * prod_m f_m^power
-          T dV = (T)0;
-          for (int t = 0; t < p.nterms[f]; ++t) {
-            T term = p.coef[f][t];
-#pragma unroll
-            for (int m = 0; m < NF; ++m) {
-              const T fm = q[m][H].v[v];
-              for (int e = 0; e < p.power[f][t][m]; ++e) term = term * fm;
-            }
-            dV = dV + term;
-          }
-          const T d_old = cur_d[f].v[v];
-          const T rhs_f = d_old;
-          const T rhs_d = (lap[f].v[v] - two_h * d_old) - a_sq * dV;
-          T kfv, kdv;
-          if (read_k) {
-            kfv = p.A * cur_kf[f].v[v] + p.dt * rhs_f;
-            kdv = p.A * cur_kd[f].v[v] + p.dt * rhs_d;
-          } else {
-            kfv = p.dt * rhs_f;
-            kdv = p.dt * rhs_d;
-          }
-          kfn.v[v] = kfv;
-          kdn.v[v] = kdv;
-          fo.v[v] = q[f][H].v[v] + p.B * kfv;
-          dn.v[v] = d_old + p.B * kdv;
-        }
-        const int64_t o = off + f * p.field_stride;
-        st_stream<T, VEC>(p.kf + o, kfn);
-        st_stream<T, VEC>(p.kdfdt + o, kdn);
-        st_stream<T, VEC>(p.dfdt + o, dn);
-        T* fout = p.f_out + o;
-        st_plain<T, VEC>(fout, fo);
-        // periodic images on the face halos (faces only: star stencils)
-        if (p.wrap_x) {
-          if (i < H) st_plain<T, VEC>(fout + (int64_t)p.Nx * plane_stride, fo);
-          if (i >= p.Nx - H) st_plain<T, VEC>(fout - (int64_t)p.Nx * plane_stride, fo);
-        }
-        if (p.wrap_y) {
-          if (j < H) st_plain<T, VEC>(fout + (int64_t)p.Ny * Pz, fo);
-          if (j >= p.Ny - H) st_plain<T, VEC>(fout - (int64_t)p.Ny * Pz, fo);
-        }
-        if (p.wrap_z) {
-#pragma unroll
-          for (int v = 0; v < VEC; ++v) {
-            if (k + v < H) fout[v + p.Nz] = fo.v[v];
-            if (k + v >= p.Nz - H) fout[v - p.Nz] = fo.v[v];
-          }
-        }
-      }
-    }
-
-    // (4) rotate prefetch registers
-#pragma unroll
-    for (int f = 0; f < NF; ++f) {
-      cur_d[f] = nxt_d[f];
-      cur_kf[f] = nxt_kf[f];
-      cur_kd[f] = nxt_kd[f];
-    }
-
-    // (5) everyone is done with the centre plane of this step: refill its slot
-    __syncthreads();
-    const int nn = n + P + 1;
-    if (nn < nsteps) {
-      if constexpr (USE_TMA) {
-        if (tid == 0) issue_plane(nn);
-      } else {
-        coop_load_plane(nn);
-        __syncthreads();
-      }
-    }
-  }
-}
-
-// ---------------------------------------------------------------------------
-// host side
-// ---------------------------------------------------------------------------
-
-template <typename T, int H, int NF, int VEC, int BY, int TZ, int P, int MINB>
-static int launch_fused(const psb_scalar_stage_args* a, cudaStream_t stream) {
-  using C = FusedCfg<T, H, NF, VEC, BY, TZ, P>;
-  FusedParams<T, NF> p;
-  p.f_in = static_cast<const T*>(a->f_in);
-  p.f_out = static_cast<T*>(a->f_out);
-  p.dfdt = static_cast<T*>(a->dfdt);
-  p.kf = static_cast<T*>(a->kf);
-  p.kdfdt = static_cast<T*>(a->kdfdt);
-  p.field_stride = a->field_stride;
-  p.Nx = (int)a->Nx;
-  p.Ny = (int)a->Ny;
-  p.Nz = (int)a->Nz;
-  p.x_begin = (int)a->x_begin;
-  p.x_end = (int)a->x_end;
-  p.wrap_x = a->wrap_x;
-  p.wrap_y = a->wrap_y;
-  p.wrap_z = a->wrap_z;
-  for (int d = 0; d < 3; ++d) {
-    // dx**-2 as the reference evaluates it in Python (derivs.py:295-296)
-    p.inv_dx2[d] = (T)pow(a->dx[d], -2.0);
-  }
-  p.dt = (T)a->dt;
-  p.A = (T)a->A;
-  p.B = (T)a->B;
-  p.a = (T)a->a;
-  p.hubble = (T)a->hubble;
-  p.a_dev = a->a_dev;
-  p.hubble_dev = a->hubble_dev;
-  for (int f = 0; f < NF; ++f) {
-    p.nterms[f] = a->nterms[f];
-    for (int t = 0; t < PSB_MAX_TERMS; ++t) {
-      p.coef[f][t] = (T)a->coef[f][t];
-      for (int m = 0; m < NF; ++m) p.power[f][t][m] = a->power[f][t][m];
-    }
-  }
-  p.energy_partials = a->energy_partials;
-
-  const int64_t nx = a->x_end - a->x_begin;
-  int xchunk = a->tune_xchunk > 0 ? a->tune_xchunk : 64;
-  if (xchunk > nx) xchunk = (int)nx;
-  p.xchunk = xchunk;
-  dim3 grid((unsigned)((a->Nz + C::BZ - 1) / C::BZ), (unsigned)((a->Ny + BY - 1) / BY),
-            (unsigned)((nx + xchunk - 1) / xchunk));
-  dim3 block(TZ, BY, 1);
-
-  const int64_t Px = a->Nx + 2 * H, Py = a->Ny + 2 * H, Pz = a->Nz + 2 * H;
-  CUtensorMap tmap;
-  memset(&tmap, 0, sizeof(tmap));
-  bool use_tma = (a->tune_variant != 2);
-  if (use_tma) {
-    int rc = encode_field_tensor_map(&tmap, a->dtype, a->f_in, NF, a->field_stride, Px,
-                                     Py, Pz, 1, C::ROWS, C::W);
-    if (rc != 0) use_tma = false;
-  }
-
-  if (use_tma) {
-    auto kern = fused_stage_kernel<T, H, NF, VEC, BY, TZ, P, true, MINB>;
-    PSB_CHECK_CUDA(cudaFuncSetAttribute(
-        kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    kern<<<grid, block, C::SMEM_BYTES, stream>>>(p, tmap);
-  } else {
-    auto kern = fused_stage_kernel<T, H, NF, VEC, BY, TZ, P, false, MINB>;
-    PSB_CHECK_CUDA(cudaFuncSetAttribute(
-        kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    kern<<<grid, block, C::SMEM_BYTES, stream>>>(p, tmap);
-  }
-  PSB_CHECK_CUDA(cudaGetLastError());
-  return 0;
-}
-
-template <typename T, int H, int NF>
-static int dispatch_vec(const psb_scalar_stage_args* a, cudaStream_t stream) {
-  // 16-byte (fp64) / 8-byte (fp32) vector path needs even alignment everywhere
-  const int64_t Pz = a->Nz + 2 * H;
-  const int64_t Py = a->Ny + 2 * H;
-  auto aligned = [&](const void* ptr) {
-    return reinterpret_cast<uintptr_t>(ptr) % (2 * sizeof(T)) == 0;
-  };
-  const bool vec2 = (H % 2 == 0) && (Pz % 2 == 0) && (a->Nz % 2 == 0) &&
-                    ((Py * Pz) % 2 == 0) && (a->field_stride % 2 == 0) &&
-                    aligned(a->f_in) && aligned(a->f_out) && aligned(a->dfdt) &&
-                    aligned(a->kf) && aligned(a->kdfdt) && a->tune_variant != 3;
-  if (vec2) {
-    if constexpr (NF == 1)
-      return launch_fused<T, H, NF, 2, 8, 64, 2, 2>(a, stream);
-    else
-      return launch_fused<T, H, NF, 2, 4, 64, 2, 1>(a, stream);
-  }
-  if constexpr (NF == 1)
-    return launch_fused<T, H, NF, 1, 8, 64, 2, 2>(a, stream);
-  else
-    return launch_fused<T, H, NF, 1, 4, 64, 2, 1>(a, stream);
-}
-
-template <typename T, int H>
-static int dispatch_nf(const psb_scalar_stage_args* a, cudaStream_t stream) {
-  switch (a->nscalars) {
-    case 1: return dispatch_vec<T, H, 1>(a, stream);
-    case 2: return dispatch_vec<T, H, 2>(a, stream);
-    case 3: return dispatch_vec<T, H, 3>(a, stream);
-    case 4: return dispatch_vec<T, H, 4>(a, stream);
-  }
-  set_error("psb_scalar_stage_fused: nscalars=%d out of range", a->nscalars);
-  return 1;
-}
-
-template <typename T>
-static int dispatch_h(const psb_scalar_stage_args* a, cudaStream_t stream) {
-  switch (a->h) {
-    case 1: return dispatch_nf<T, 1>(a, stream);
-    case 2: return dispatch_nf<T, 2>(a, stream);
-    case 3: return dispatch_nf<T, 3>(a, stream);
-    case 4: return dispatch_nf<T, 4>(a, stream);
-  }
-  set_error("psb_scalar_stage_fused: h=%d out of range 1..4", a->h);
-  return 1;
-}
-
-}  // namespace psb
-
-extern "C" int psb_scalar_stage_fused(const psb_scalar_stage_args* a, void* stream) {
-  using namespace psb;
+static int validate(const psb_scalar_stage_args* a) {
   PSB_REQUIRE(a != nullptr, "psb_scalar_stage_fused: null args");
   PSB_REQUIRE(a->f_in && a->f_out && a->dfdt && a->kf && a->kdfdt,
               "psb_scalar_stage_fused: null array pointer");
@@ -478,13 +18,33 @@ extern "C" int psb_scalar_stage_fused(const psb_scalar_stage_args* a, void* stre
   PSB_REQUIRE(a->x_begin >= 0 && a->x_end <= a->Nx && a->x_begin <= a->x_end,
               "psb_scalar_stage_fused: bad x range [%lld, %lld)", (long long)a->x_begin,
               (long long)a->x_end);
-  for (int f = 0; f < a->nscalars && f < PSB_MAX_SCALARS; ++f)
+  PSB_REQUIRE(a->nscalars >= 1 && a->nscalars <= PSB_MAX_SCALARS,
+              "psb_scalar_stage_fused: nscalars=%d out of range", a->nscalars);
+  for (int f = 0; f < a->nscalars; ++f)
     PSB_REQUIRE(a->nterms[f] >= 0 && a->nterms[f] <= PSB_MAX_TERMS,
                 "psb_scalar_stage_fused: too many potential terms");
+  PSB_REQUIRE(a->nvterms >= 0 && a->nvterms <= PSB_MAX_TERMS,
+              "psb_scalar_stage_fused: too many terms in V");
+  PSB_REQUIRE(a->dtype == PSB_F64 || a->dtype == PSB_F32,
+              "psb_scalar_stage_fused: unknown dtype %d", a->dtype);
+  return 0;
+}
+}  // namespace psb
+
+extern "C" int psb_scalar_stage_fused(const psb_scalar_stage_args* a, void* stream) {
+  using namespace psb;
+  if (int rc = validate(a)) return rc;
   if (a->x_begin == a->x_end) return 0;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (a->dtype == PSB_F64) return dispatch_h<double>(a, s);
-  if (a->dtype == PSB_F32) return dispatch_h<float>(a, s);
-  set_error("psb_scalar_stage_fused: unknown dtype %d", a->dtype);
-  return 1;
+  return a->dtype == PSB_F64 ? fused_dispatch_f64(a, s, nullptr)
+                             : fused_dispatch_f32(a, s, nullptr);
+}
+
+extern "C" int64_t psb_scalar_stage_energy_slots(const psb_scalar_stage_args* a) {
+  using namespace psb;
+  if (validate(a) != 0) return -1;
+  int64_t count = 0;
+  int rc = a->dtype == PSB_F64 ? fused_dispatch_f64(a, nullptr, &count)
+                               : fused_dispatch_f32(a, nullptr, &count);
+  return rc == 0 ? count : -1;
 }

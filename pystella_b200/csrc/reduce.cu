@@ -216,8 +216,3 @@ extern "C" int psb_reduce(const psb_reduce_args* a, void* stream) {
   set_error("psb_reduce: unknown dtype %d", a->dtype);
   return 1;
 }
-
-extern "C" int64_t psb_scalar_stage_energy_slots(const psb_scalar_stage_args* a) {
-  (void)a;
-  return 0;
-}

@@ -10,7 +10,7 @@ import numpy as np
 
 from pystella_b200.field import Field, var
 
-__all__ = ["Expansion"]
+__all__ = ["Expansion", "DeviceExpansion"]
 
 
 class Expansion:
@@ -63,3 +63,83 @@ class Expansion:
 def _scalar(x):
     arr = np.asarray(x)
     return arr.reshape(-1)[0] if arr.size == 1 else arr
+
+
+class DeviceExpansion:
+    """
+    The same background ODE with its state resident on the GPU, fed by the energy
+    sums the fused stage kernel accumulates (``energy=True`` steppers), so that a
+    time step needs no device-to-host synchronisation::
+
+        expand = ps.DeviceExpansion(energy0, ps.LowStorageRK54, grid_size=N**3)
+        for s in range(stepper.num_stages):
+            stepper(s, f=f, dfdt=dfdt, a=expand.a, hubble=expand.hubble)
+            expand.step(s, stepper, dt)
+
+    Stage ``s`` of the stepper reads ``(a, hubble)`` and accumulates the energy sums
+    of its *input* state; :meth:`step` turns them into energy density and pressure
+    with the current ``a`` and advances ``(a, adot)`` -- the same values, in the same
+    order, as the reference loop ``stepper -> expand.step -> compute_energy``
+    (``examples/scalar_preheating.py:258-264``), which recomputes the Laplacian
+    and synchronises with the host three times per stage to get them.
+
+    Attributes ``a``, ``adot``, ``hubble`` are 1-element float64 device tensors
+    (views of :attr:`state`); ``energies`` holds, after each :meth:`step`,
+    ``{kinetic_n.., potential, gradient_n.., total, pressure}`` of the state that
+    entered the stage.
+    """
+
+    def __init__(self, energy, Stepper, mpl=1., grid_size=None, decomp=None,
+                 nscalars=1, a0=1., device=None, strict_fp=False):
+        import torch
+        from pystella_b200.step import LowStorageRKStepper
+        if not issubclass(Stepper, LowStorageRKStepper):
+            raise NotImplementedError("DeviceExpansion needs a low-storage stepper")
+        if grid_size is None:
+            raise ValueError("pass grid_size= (global number of lattice sites)")
+        self.mpl = float(mpl)
+        self.grid_size = float(grid_size)
+        self.decomp = decomp
+        self.nscalars = nscalars
+        self.strict_fp = strict_fp
+        self._A, self._B = Stepper._A, Stepper._B
+        self.num_stages = Stepper.num_stages
+        dev = device or torch.device("cuda", torch.cuda.current_device())
+        adot0 = float(np.sqrt(8 * np.pi * a0**2 / 3 / self.mpl**2 * float(energy)) * a0)
+        self.state = torch.tensor([a0, adot0, adot0 / a0, 0., 0.], dtype=torch.float64,
+                                  device=dev)
+        self.a, self.adot, self.hubble = self.state[0:1], self.state[1:2], self.state[2:3]
+        self.sums = torch.zeros(16, dtype=torch.float64, device=dev)
+        self.energies = torch.zeros(2 * nscalars + 3, dtype=torch.float64, device=dev)
+
+    def step(self, stage, stepper, dt, queue=None):
+        """Fold the stepper's energy partials and advance one stage (no host sync)."""
+        from pystella_b200 import _kernels
+        if stepper.energy_partials is None or stepper.energy_nslots == 0:
+            raise ValueError("the stepper has produced no energy sums: construct it with "
+                             "MapKernel=FusedStencilStage, energy=True and call it first")
+        nvals = stepper.energy_nvals
+        _kernels.energy_sums(stepper.energy_partials, stepper.energy_nslots, nvals,
+                             self.sums, queue, self.strict_fp)
+        if self.decomp is not None and self.decomp.nranks > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.sums, group=self.decomp.comm)
+        _kernels.expansion_stage(self.sums, self.nscalars, self.grid_size, self.mpl, dt,
+                                 self._A[stage], self._B[stage], self.state, self.energies,
+                                 queue, self.strict_fp)
+
+    def get(self):
+        """Host copy ``dict(a, adot, hubble, energies)`` (synchronises)."""
+        st = self.state.cpu().numpy()
+        en = self.energies.cpu().numpy()
+        n = self.nscalars
+        return dict(a=st[0], adot=st[1], hubble=st[2],
+                    kinetic=en[:n].copy(), potential=en[n:n + 1].copy(),
+                    gradient=en[n + 1:2 * n + 1].copy(), total=en[2 * n + 1],
+                    pressure=en[2 * n + 2])
+
+    def constraint(self):
+        """Friedmann-constraint violation with the last stage's energy (host)."""
+        g = self.get()
+        return abs(np.sqrt(8 * np.pi * g["a"]**2 / 3 / self.mpl**2 * g["total"]) * g["a"]
+                   / g["adot"] - 1)

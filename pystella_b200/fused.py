@@ -66,6 +66,17 @@ def exchange_x_faces(decomp, f, h, fields_axis):
     return dist.batch_isend_irecv(ops)
 
 
+def _launch_ranges(Nx, h, multi):
+    """x-ranges of the launches of one stage: whole slab, or lo / hi boundary slabs
+    followed by the interior."""
+    if not multi:
+        return [(0, Nx)]
+    hb = min(h, Nx)
+    if Nx - hb > hb:
+        return [(0, hb), (Nx - hb, Nx), (hb, Nx - hb)]
+    return [(0, hb), (hb, Nx)]
+
+
 def fused_scalar_stage(stepper, system, f, common, queue):
     h = common["h"]
     decomp = stepper.decomp
@@ -102,25 +113,48 @@ def fused_scalar_stage(stepper, system, f, common, queue):
     Nx = f.shape[-3] - 2 * h
     args = dict(common)
     args.update(fused=True, f_in=f, f_out=twin, dx=stepper.dx)
-    tune = getattr(stepper, "tune", None) or {}
+    tune = stepper.tune or {}
     args.update(xchunk=tune.get("xchunk", 0), variant=tune.get("variant", 0))
 
+    if stepper.fused_energy:
+        if stepper._V_values is None:
+            raise NotImplementedError(
+                "fused energy sums need the potential V: construct the stepper from a "
+                "ScalarSector")
+        args.update(V_terms=stepper._V_values)
+        ranges = _launch_ranges(Nx, h, multi)
+        lkey = (tuple(f.shape), f.dtype, multi, args["xchunk"], args["variant"])
+        cache = stepper.__dict__.setdefault("_energy_layout", {})
+        if lkey not in cache:
+            cache[lkey] = [_kernels.scalar_stage(x_range=r, count_slots_only=True, **args)
+                           for r in ranges]
+        counts = cache[lkey]
+        total = sum(counts)
+        if stepper.energy_partials is None or stepper.energy_partials.shape[0] < total:
+            from pystella_b200._lib import ENERGY_STRIDE
+            stepper.energy_partials = torch.zeros(
+                (total, ENERGY_STRIDE), dtype=torch.float64, device=f.device)
+        stepper.energy_nslots = total
+        stepper.energy_nvals = 2 * system.nscalars + 1
+        offsets = [sum(counts[:i]) for i in range(len(counts))]
+        energy_kw = [dict(energy_partials=stepper.energy_partials, energy_slot_offset=o)
+                     for o in offsets]
+    else:
+        energy_kw = [{}, {}, {}]
+
     if not multi:
-        _kernels.scalar_stage(wrap=(True, True, True), **args)
+        _kernels.scalar_stage(wrap=(True, True, True), **args, **energy_kw[0])
     else:
         st = _ensure_streams(stepper)
         cur = queue if queue is not None else torch.cuda.current_stream()
-        hb = min(h, Nx)
         with torch.cuda.stream(cur):
             # boundary slabs first
-            _kernels.scalar_stage(wrap=(False, True, True), x_range=(0, hb), **args)
-            if Nx - hb > hb:
-                _kernels.scalar_stage(wrap=(False, True, True), x_range=(Nx - hb, Nx),
-                                      **args)
-                interior = (hb, Nx - hb)
-            else:
-                _kernels.scalar_stage(wrap=(False, True, True), x_range=(hb, Nx), **args)
-                interior = None
+            ranges = _launch_ranges(Nx, h, True)
+            _kernels.scalar_stage(wrap=(False, True, True), x_range=ranges[0], **args,
+                                  **energy_kw[0])
+            _kernels.scalar_stage(wrap=(False, True, True), x_range=ranges[1], **args,
+                                  **energy_kw[1])
+            interior = ranges[2] if len(ranges) > 2 else None
             st["boundary_done"].record(cur)
         with torch.cuda.stream(st["comm"]):
             st["comm"].wait_event(st["boundary_done"])
@@ -129,7 +163,8 @@ def fused_scalar_stage(stepper, system, f, common, queue):
             st["comm_done"].record(st["comm"])
         if interior is not None:
             with torch.cuda.stream(cur):
-                _kernels.scalar_stage(wrap=(False, True, True), x_range=interior, **args)
+                _kernels.scalar_stage(wrap=(False, True, True), x_range=interior, **args,
+                                      **energy_kw[2])
         cur.wait_event(st["comm_done"])
 
     _swap_storage(f, twin)

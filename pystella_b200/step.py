@@ -63,7 +63,8 @@ class FusedStencilStage(ElementWiseMap):
 class ScalarSystem:
     """A set of (f_n, dfdt_n) pairs obeying the scalar-sector equations."""
 
-    def __init__(self, field, nscalars, hubble, a, dV, has_outer_axis):
+    def __init__(self, field, nscalars, hubble, a, dV, has_outer_axis, V=None):
+        self.V = V                      # list of (coef_expr, powers) or None
         self.field = field              # the DynamicField
         self.f_name = field.name
         self.dot_name = field.dot.name
@@ -78,6 +79,7 @@ class ScalarSystem:
         names = set()
         from pystella_b200.field import _walk
         exprs = [self.hubble, self.a] + [c for terms in self.dV for c, _ in terms]
+        exprs += [c for c, _ in (self.V or [])]
         for e in exprs:
             for node in _walk(e):
                 if isinstance(node, (Variable, Field)):
@@ -229,8 +231,17 @@ def scalar_system_from_sector(sector):
                 powers[ref.subscript[0] if f.shape else 0] = pw
             terms.append((c, tuple(powers)))
         dV.append(terms)
+    Vterms = []
+    for mono, c in to_polynomial(V).items():
+        powers = [0] * n
+        for ref, pw in mono:
+            if ref.name != f.name or any(ref.shift):
+                raise NotImplementedError(
+                    "potential must be a polynomial in the scalar fields")
+            powers[ref.subscript[0] if f.shape else 0] = pw
+        Vterms.append((c, tuple(powers)))
     return ScalarSystem(f, n, Field("hubble", indices=[]), Field("a", indices=[]),
-                        dV, bool(f.shape))
+                        dV, bool(f.shape), V=Vterms)
 
 
 # ---------------------------------------------------------------------------
@@ -317,6 +328,11 @@ class Stepper:
         self.dx = kwargs.pop("dx", None)
         self.decomp = kwargs.pop("decomp", None)
         self.strict_fp = kwargs.pop("strict_fp", False)
+        #: fused stage also accumulates the energy sums of its input state
+        self.fused_energy = kwargs.pop("energy", False)
+        self.energy_partials = None
+        self.energy_nslots = 0
+        self.tune = kwargs.pop("tune", None)
         self._ignored_kwargs = kwargs  # target=, lsize=, args=, options= ...
 
         if self.fused and self.dx is None:
@@ -486,6 +502,10 @@ class LowStorageRKStepper(Stepper):
                if n in kwargs and not isinstance(kwargs[n], torch.Tensor)}
         dV = [[(c if is_constant(c) else float(evaluate(c, ctx)), p) for c, p in terms]
               for terms in system.dV]
+        self._V_values = None
+        if system.V is not None:
+            self._V_values = [(c if is_constant(c) else float(evaluate(c, ctx)), p)
+                              for c, p in system.V]
         return out, dV
 
     def _scalar_stage(self, system, stage, queue, kwargs, dt, A, B):

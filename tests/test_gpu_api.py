@@ -355,3 +355,83 @@ def test_fused_stepper_on_side_stream_and_device_scalars():
             q.synchronize()
         res.append((f.clone(), d.clone()))
     assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+
+
+def _oracle_energy(f, dfdt, h, dx, a, terms):
+    n = f.shape[0]
+    fi, di, laps = [], [], []
+    for i in range(n):
+        g = f[i].copy()
+        O.share_halos(g, h)
+        laps.append(O.laplacian(g, h, dx))
+        fi.append(O.interior(f[i], h))
+        di.append(O.interior(dfdt[i], h))
+    return O.get_rho_and_p(O.scalar_energy(fi, di, laps, a, terms))
+
+
+@pytest.mark.parametrize("nscalars", [1, 2])
+def test_device_resident_preheating_loop(nscalars):
+    """
+    Fused stage with in-kernel energy sums + DeviceExpansion (no host sync) against
+    the reference's loop order stepper -> expand.step -> compute_energy
+    (examples/scalar_preheating.py:258-264) run with the oracle.
+    """
+    rng = np.random.default_rng(49279)
+    N, h = (16, 24, 32), 2
+    pad = tuple(n + 2 * h for n in N)
+    dx = tuple(5 / n for n in N)
+    dt = 0.1 * min(dx)
+    mpl = 1.0
+    if nscalars == 1:
+        def potential(f):
+            return f[0]**2 / 2
+        terms = [(0.5, (2,))]
+        f0 = (.193 + 1e-3 * rng.standard_normal((1,) + pad))
+        d0 = (-.142231 + 1e-3 * rng.standard_normal((1,) + pad))
+    else:
+        potential, terms = _example_potential()
+        f0 = np.array([.193, 0.])[:, None, None, None] + 1e-3 * rng.standard_normal((2,) + pad)
+        d0 = np.array([-.142231, 0.])[:, None, None, None] + 1e-3 * rng.standard_normal((2,) + pad)
+    gs = float(np.prod(N))
+
+    # --- oracle, reference order
+    fr, dr = f0.copy(), d0.copy()
+    kfr, kdr = np.zeros_like(fr), np.zeros_like(fr)
+    lap = np.zeros((nscalars,) + N)
+    energy = _oracle_energy(fr, dr, h, dx, 1., terms)
+    e0 = float(energy["total"])
+    expand = O.Expansion(energy["total"], "LowStorageRK54", mpl=mpl)
+    stage_energies = []
+    nsteps = 2
+    for _ in range(nsteps):
+        for s in range(5):
+            stage_energies.append((float(energy["total"]), float(energy["pressure"])))
+            O.reference_schedule_stage(s, fr, dr, kfr, kdr, lap, h, dx, dt,
+                                       a=expand.a[0], hubble=expand.hubble[0],
+                                       potential_terms=terms)
+            expand.step(s, energy["total"], energy["pressure"], dt)
+            energy = _oracle_energy(fr, dr, h, dx, expand.a[0], terms)
+
+    # --- device-resident
+    sector = ps.ScalarSector(nscalars, potential=potential)
+    stepper = ps.LowStorageRK54(sector, halo_shape=h, dt=dt, dx=dx,
+                                MapKernel=ps.FusedStencilStage, energy=True)
+    dexp = ps.DeviceExpansion(e0, ps.LowStorageRK54, mpl=mpl, grid_size=gs,
+                              nscalars=nscalars)
+    f, dfdt = to_dev(f0), to_dev(d0)
+    got_energies = []
+    for _ in range(nsteps):
+        for s in range(5):
+            stepper(s, f=f, dfdt=dfdt, a=dexp.a, hubble=dexp.hubble)
+            dexp.step(s, stepper, dt)
+            g = dexp.get()
+            got_energies.append((g["total"], g["pressure"]))
+    for (t0, p0), (t1, p1) in zip(stage_energies, got_energies):
+        assert np.isclose(t1, t0, rtol=1e-12) and np.isclose(p1, p0, rtol=1e-11, atol=1e-16)
+    g = dexp.get()
+    assert np.isclose(g["a"], expand.a[0], rtol=1e-13)
+    assert np.isclose(g["adot"], expand.adot[0], rtol=1e-12)
+    assert np.isclose(g["hubble"], expand.hubble[0], rtol=1e-12)
+    for i in range(nscalars):
+        assert scale_err(O.interior(f[i].cpu().numpy(), h), O.interior(fr[i], h)) < 1e-12
+        assert scale_err(O.interior(dfdt[i].cpu().numpy(), h), O.interior(dr[i], h)) < 1e-12
