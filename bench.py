@@ -88,55 +88,65 @@ def background_energy(w):
 # ---------------------------------------------------------------------------
 
 class ClockSampler:
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-              "clocks_event_reasons.hw_thermal_slowdown,"
-              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """Samples SM clock / throttle reasons through NVML while the timed region runs."""
 
     def __init__(self, index=0):
-        self.lines = []
-        self.proc = None
         self.index = index
+        self.samples = []
+        self.stop_flag = False
+        self.thread = None
+        self.err = None
+
+    def _loop(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.index
+            if vis:
+                try:
+                    idx = int(vis.split(",")[self.index])
+                except ValueError:
+                    pass
+            hnd = nv.nvmlDeviceGetHandleByIndex(idx)
+            smax = nv.nvmlDeviceGetMaxClockInfo(hnd, nv.NVML_CLOCK_SM)
+            while not self.stop_flag:
+                sm = nv.nvmlDeviceGetClockInfo(hnd, nv.NVML_CLOCK_SM)
+                try:
+                    reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(hnd)
+                except Exception:
+                    reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(hnd)
+                try:
+                    power = nv.nvmlDeviceGetPowerUsage(hnd) / 1000.0
+                except Exception:
+                    power = None
+                self.samples.append((sm, smax, reasons, power))
+                time.sleep(0.02)
+        except Exception as exc:  # noqa: BLE001
+            self.err = repr(exc)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                 "-i", str(self.index), "-lms", "100"],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+        self.thread = threading.Thread(target=self._loop, daemon=True)
+        self.thread.start()
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, smax, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            parts = [x.strip() for x in ln.split(",")]
-            if len(parts) < 7:
-                continue
-            try:
-                sm.append(float(parts[0]))
-                smax.append(float(parts[1]))
-            except ValueError:
-                continue
-            for n, v in zip(names, parts[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        return {"sm_mhz": float(np.median(sm)) if sm else None,
-                "sm_max_mhz": float(np.max(smax)) if smax else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        self.stop_flag = True
+        if self.thread is not None:
+            self.thread.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0,
+                    "reasons": [f"nvml unavailable: {self.err}"]}
+        bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20,
+                "hw_thermal_slowdown": 0x40, "hw_power_brake": 0x80}
+        reasons = set()
+        for _, _, r, _ in self.samples:
+            for name, bit in bits.items():
+                if r & bit:
+                    reasons.add(name)
+        powers = [p for _, _, _, p in self.samples if p is not None]
+        return {"sm_mhz": float(np.median([s[0] for s in self.samples])),
+                "sm_max_mhz": float(self.samples[0][1]), "samples": len(self.samples),
+                "power_w_max": max(powers) if powers else None, "reasons": sorted(reasons)}
 
 
 # ---------------------------------------------------------------------------
@@ -176,7 +186,21 @@ def cpu_reference_steps(w, nsteps, warmup, budget_s=200.0):
         return time.perf_counter() - t0
 
     st = setup(ww)
-    t1 = run(ww, st, 1)  # first warm-up step, also used to bound the run
+    # OpenMP thread count: all hardware threads is not always fastest for this
+    # bandwidth-bound loop (SMT / NUMA); try all, half and a quarter, keep the best
+    try:
+        lib = CO.load(native)
+        nmax = os.cpu_count() or CO.num_threads(native)
+        best = None
+        for nt in sorted({nmax, max(1, nmax // 2), max(1, nmax // 4)}, reverse=True):
+            lib.omp_set_num_threads(nt)
+            tt = run(ww, st, 1)
+            if best is None or tt < best[0]:
+                best = (tt, nt)
+        lib.omp_set_num_threads(best[1])
+    except Exception:  # noqa: BLE001
+        pass
+    t1 = run(ww, st, 1)  # warm-up step at the chosen thread count; bounds the run
     sample = f"{N[0]}x{N[1]}x{N[2]} lattice, full LSRK54 steps"
     if t1 * (nsteps + warmup) > budget_s and N[1] > 256:
         ww = workload(256, "f64", 1, 0, "strong")

@@ -21,6 +21,8 @@
 #include <math.h>
 #include <string.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace psb {
@@ -407,10 +409,8 @@ __global__ void __launch_bounds__(BY* TZ, MINB)
 // host side
 // ---------------------------------------------------------------------------
 
-template <typename T, int H, int NF, int VEC, int BY, int TZ, int P, int MINB>
-static int launch_fused(const psb_scalar_stage_args* a, cudaStream_t stream) {
-  using C = FusedCfg<T, H, NF, VEC, BY, TZ, P>;
-  FusedParams<T, NF> p;
+template <typename T, int NF>
+static void fill_params(FusedParams<T, NF>& p, const psb_scalar_stage_args* a) {
   p.f_in = static_cast<const T*>(a->f_in);
   p.f_out = static_cast<T*>(a->f_out);
   p.dfdt = static_cast<T*>(a->dfdt);
@@ -451,6 +451,13 @@ static int launch_fused(const psb_scalar_stage_args* a, cudaStream_t stream) {
     for (int m = 0; m < NF; ++m) p.vpower[t][m] = a->vpower[t][m];
   }
 
+}
+
+template <typename T, int H, int NF, int VEC, int BY, int TZ, int P, int MINB>
+static int launch_fused(const psb_scalar_stage_args* a, cudaStream_t stream) {
+  using C = FusedCfg<T, H, NF, VEC, BY, TZ, P>;
+  FusedParams<T, NF> p;
+  fill_params<T, NF>(p, a);
   const int64_t nx = a->x_end - a->x_begin;
   int xchunk = a->tune_xchunk > 0 ? a->tune_xchunk : 64;
   if (xchunk > nx) xchunk = (int)nx;
@@ -499,6 +506,26 @@ static int64_t fused_grid_blocks(const psb_scalar_stage_args* a) {
          ((nx + xchunk - 1) / xchunk);
 }
 
+}  // namespace psb
+#include "fused_stage_ws.cuh"
+namespace psb {
+
+constexpr int v1_smem_bytes(int es, int H, int NF, int VEC, int BY, int TZ, int P) {
+  const int BZ = TZ * VEC;
+  const int HL = ((H + VEC - 1) / VEC) * VEC;
+  const int WQ = 16 / es;
+  const int W = ((BZ + 2 * HL + WQ - 1) / WQ) * WQ;
+  const int plane = (((BY + 2 * H) * W * es + 127) / 128) * 128;
+  return (H + 1 + P) * NF * plane + (H + 1 + P) * 8 + 128;
+}
+constexpr int v1_pick_tz(int es, int H, int NF, int VEC, int BY, int P) {
+  for (int tz = 64; tz >= 16; tz /= 2)
+    if (v1_smem_bytes(es, H, NF, VEC, BY, tz, P) <= 100 * 1024) return tz;
+  for (int tz = 64; tz >= 16; tz /= 2)
+    if (v1_smem_bytes(es, H, NF, VEC, BY, tz, P) <= SMEM_LIMIT) return tz;
+  return 16;
+}
+
 template <typename T, int H, int NF, int VEC, int BY, int TZ, int P, int MINB>
 static int fused_op(const psb_scalar_stage_args* a, cudaStream_t stream, int64_t* count) {
   if (count) {
@@ -506,6 +533,27 @@ static int fused_op(const psb_scalar_stage_args* a, cudaStream_t stream, int64_t
     return 0;
   }
   return launch_fused<T, H, NF, VEC, BY, TZ, P, MINB>(a, stream);
+}
+
+template <typename T, int H, int NF, int BY, int TZ, int P, int MINB>
+static int ws_op(const psb_scalar_stage_args* a, cudaStream_t stream, int64_t* count) {
+  if (count) {
+    *count = ws_grid_blocks<T, H, NF, BY, TZ, P>(a);
+    return 0;
+  }
+  return launch_ws<T, H, NF, BY, TZ, P, MINB>(a, stream);
+}
+
+// can TMA describe all four arrays?  (mirrors encode_field_tensor_map's checks)
+template <typename T>
+static bool tma_layout_ok(const psb_scalar_stage_args* a, int H) {
+  const int64_t es = sizeof(T);
+  const int64_t Pz = a->Nz + 2 * H, Py = a->Ny + 2 * H;
+  if ((Pz * es) % 16 || (Py * Pz * es) % 16 || (a->field_stride * es) % 16) return false;
+  const void* ptrs[5] = {a->f_in, a->f_out, a->dfdt, a->kf, a->kdfdt};
+  for (const void* q : ptrs)
+    if (reinterpret_cast<uintptr_t>(q) % 16) return false;
+  return true;
 }
 
 template <typename T, int H, int NF>
@@ -521,16 +569,34 @@ static int dispatch_vec(const psb_scalar_stage_args* a, cudaStream_t stream,
                     ((Py * Pz) % 2 == 0) && (a->field_stride % 2 == 0) &&
                     aligned(a->f_in) && aligned(a->f_out) && aligned(a->dfdt) &&
                     aligned(a->kf) && aligned(a->kdfdt) && a->tune_variant != 3;
+  constexpr int ES = (int)sizeof(T);
   if (vec2) {
+    // warp-specialised TMA pipeline (default)
+    const int var = a->tune_variant;
+    if ((var == 0 || var >= 10) && tma_layout_ok<T>(a, H)) {
+      if constexpr (std::is_same<T, double>::value && H == 2 && NF == 1) {
+        // tuned configurations of the headline case
+        if (var == 11) return ws_op<T, H, NF, 8, 64, 3, 1>(a, stream, count);
+        if (var == 12) return ws_op<T, H, NF, 8, 64, 2, 1>(a, stream, count);
+        if (var == 13) return ws_op<T, H, NF, 4, 64, 2, 2>(a, stream, count);
+        if (var == 14) return ws_op<T, H, NF, 2, 64, 3, 3>(a, stream, count);
+        return ws_op<T, H, NF, 4, 64, 3, 2>(a, stream, count);
+      } else {
+        constexpr int TZW = ws_pick_tz(ES, H, NF, 4, 2);
+        if constexpr (TZW > 0) return ws_op<T, H, NF, 4, TZW, 2, 1>(a, stream, count);
+      }
+    }
+    constexpr int TZ2 = v1_pick_tz(ES, H, NF, 2, (NF == 1 ? 8 : 4), 2);
     if constexpr (NF == 1)
-      return fused_op<T, H, NF, 2, 8, 64, 2, 2>(a, stream, count);
+      return fused_op<T, H, NF, 2, 8, TZ2, 2, (TZ2 == 64 ? 2 : 1)>(a, stream, count);
     else
-      return fused_op<T, H, NF, 2, 4, 64, 2, 1>(a, stream, count);
+      return fused_op<T, H, NF, 2, 4, TZ2, 2, 1>(a, stream, count);
   }
+  constexpr int TZ1 = v1_pick_tz(ES, H, NF, 1, (NF == 1 ? 8 : 4), 2);
   if constexpr (NF == 1)
-    return fused_op<T, H, NF, 1, 8, 64, 2, 2>(a, stream, count);
+    return fused_op<T, H, NF, 1, 8, TZ1, 2, (TZ1 == 64 ? 2 : 1)>(a, stream, count);
   else
-    return fused_op<T, H, NF, 1, 4, 64, 2, 1>(a, stream, count);
+    return fused_op<T, H, NF, 1, 4, TZ1, 2, 1>(a, stream, count);
 }
 
 template <typename T, int H>

@@ -1,0 +1,442 @@
+// Warp-specialised fused stage (the default path when the layout is TMA-able).
+//
+// One producer warp streams *all four* input arrays of the stage through shared
+// memory with TMA; the consumer warps never touch global memory for loads and
+// never meet at a CTA-wide barrier:
+//
+//   f ring   : R_f = H+1+P slots, each a padded (BY+2H) x W plane per field
+//              (own values -> x register queue; centre plane -> y/z neighbours)
+//   pw ring  : R_p = P+1 slots, each {dfdt, kf, kdfdt} x (BY x BZ) per field
+//   full_*   : mbarriers completed by TMA transaction bytes
+//   empty_*  : mbarriers on which every consumer warp arrives when it is done
+//              with a slot; the producer waits on them before refilling
+//
+// so P+1 planes (f + pointwise) are always in flight per CTA regardless of how
+// many warps are resident: memory-level parallelism comes from the TMA queue, not
+// from occupancy.  Results are stored straight from registers (16-byte vectors),
+// f_out additionally onto the periodic face halos.
+#pragma once
+#include "fused_stage_impl.cuh"
+
+namespace psb {
+
+template <typename T, int H, int NF, int BY, int TZ, int P> struct WsCfg {
+  static constexpr int VEC = 2;
+  static constexpr int BZ = TZ * VEC;
+  static constexpr int HL = ((H + VEC - 1) / VEC) * VEC;
+  static constexpr int WQ = 16 / (int)sizeof(T);
+  static constexpr int W = ((BZ + 2 * HL + WQ - 1) / WQ) * WQ;
+  static constexpr int ROWS = BY + 2 * H;
+  static constexpr int RF = H + 1 + P;
+  static constexpr int RP = P + 1;
+  static constexpr int FPLANE_RAW = ROWS * W * (int)sizeof(T);
+  static constexpr int FPLANE = ((FPLANE_RAW + 127) / 128) * 128;   // bytes, per field
+  // TMA needs a 16-byte aligned start along z: pointwise tiles begin PWL elements
+  // left of the first interior site of the tile (fp32, h = 2: two floats)
+  static constexpr int PWL = H % WQ;
+  static constexpr int PWW = ((BZ + PWL + WQ - 1) / WQ) * WQ;
+  static constexpr int PWTILE_RAW = BY * PWW * (int)sizeof(T);
+  static constexpr int PWTILE = ((PWTILE_RAW + 127) / 128) * 128;   // bytes, per array
+  static constexpr int PWSLOT = 3 * NF * PWTILE;
+  static constexpr int NCW = BY * TZ / 32;                           // consumer warps
+  static constexpr int THREADS = BY * TZ + 32;                       // + producer warp
+  static constexpr int NBAR = 2 * RF + 2 * RP;
+  static constexpr int SMEM_BYTES = RF * NF * FPLANE + RP * PWSLOT + NBAR * 8 + 128;
+};
+
+constexpr int SMEM_LIMIT = 200 * 1024;
+// x-planes marched per CTA: short chunks balance the 148 SMs better than they cost
+// in re-read prologue planes (measured at 512^3: 16 > 32 > 64 > 128)
+constexpr int WS_DEFAULT_XCHUNK = 16;
+
+constexpr int ws_smem_bytes(int es, int H, int NF, int BY, int TZ, int P) {
+  const int BZ = TZ * 2;
+  const int HL = ((H + 1) / 2) * 2;
+  const int WQ = 16 / es;
+  const int W = ((BZ + 2 * HL + WQ - 1) / WQ) * WQ;
+  const int fplane = (((BY + 2 * H) * W * es + 127) / 128) * 128;
+  const int pww = ((BZ + H % WQ + WQ - 1) / WQ) * WQ;
+  const int pwtile = ((BY * pww * es + 127) / 128) * 128;
+  return (H + 1 + P) * NF * fplane + (P + 1) * 3 * NF * pwtile + (2 * (H + 1 + P) + 2 * (P + 1)) * 8 +
+         128;
+}
+// widest z tile (64, 32 or 16 threads of 2 sites) whose rings fit; 0 = none
+constexpr int ws_pick_tz(int es, int H, int NF, int BY, int P) {
+  for (int tz = 64; tz >= 16; tz /= 2)
+    if (ws_smem_bytes(es, H, NF, BY, tz, P) <= SMEM_LIMIT) return tz;
+  return 0;
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <typename T, int H, int NF, int BY, int TZ, int P, bool ENERGY, int MINB>
+__global__ void __launch_bounds__(BY* TZ + 32, MINB)
+    fused_stage_ws_kernel(const __grid_constant__ FusedParams<T, NF> p,
+                          const __grid_constant__ CUtensorMap map_f,
+                          const __grid_constant__ CUtensorMap map_d,
+                          const __grid_constant__ CUtensorMap map_kf,
+                          const __grid_constant__ CUtensorMap map_kd) {
+  using C = WsCfg<T, H, NF, BY, TZ, P>;
+  constexpr int VEC = C::VEC, W = C::W, HL = C::HL, RF = C::RF, RP = C::RP;
+  using V = Vec<T, VEC>;
+
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned char* base = smem_raw + ((128 - (smem_u32(smem_raw) & 127)) & 127);
+  unsigned char* fring = base;
+  unsigned char* pring = base + RF * NF * C::FPLANE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(pring + RP * C::PWSLOT);
+  uint64_t* full_f = bars;
+  uint64_t* empty_f = bars + RF;
+  uint64_t* full_p = bars + 2 * RF;
+  uint64_t* empty_p = bars + 2 * RF + RP;
+
+  const int tid = threadIdx.x;
+  const int z0 = blockIdx.x * C::BZ, y0 = blockIdx.y * BY;
+  const int xs = p.x_begin + blockIdx.z * p.xchunk;
+  const int xe = min(xs + p.xchunk, p.x_end);
+  const int nsteps = (xe - xs) + 2 * H;   // f planes streamed
+  const int ncomp = xe - xs;              // site planes computed
+  const bool read_k = (p.A != (T)0);
+
+  if (tid == 0) {
+    for (int s = 0; s < RF; ++s) {
+      mbar_init(&full_f[s], 1);
+      mbar_init(&empty_f[s], C::NCW);
+    }
+    for (int s = 0; s < RP; ++s) {
+      mbar_init(&full_p[s], 1);
+      mbar_init(&empty_p[s], C::NCW);
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();
+
+  if (tid >= BY * TZ) {
+    // ======================= producer warp (one elected lane) ===================
+    if (tid == BY * TZ) {
+      tma_prefetch_desc(&map_f);
+      tma_prefetch_desc(&map_d);
+      tma_prefetch_desc(&map_kf);
+      tma_prefetch_desc(&map_kd);
+      const uint32_t pw_bytes = (read_k ? 3u : 1u) * NF * C::PWTILE_RAW;
+      for (int m = 0; m < nsteps; ++m) {
+        {  // f plane m: interior x index xs - H + m -> padded index xs + m
+          const int slot = m % RF;
+          if (m >= RF) mbar_wait(&empty_f[slot], ((m / RF) - 1) & 1);
+          mbar_expect_tx(&full_f[slot], NF * C::FPLANE_RAW);
+#pragma unroll
+          for (int f = 0; f < NF; ++f)
+            tma_load_4d(fring + (slot * NF + f) * C::FPLANE, &map_f, &full_f[slot],
+                        z0 + H - HL, y0, xs + m, f);
+        }
+        // consumer step m needs f plane m and the pointwise planes of compute index
+        // m - 2H: issue both in the same iteration so that both rings run P+1 ahead
+        const int c = m - 2 * H;
+        if (c >= 0 && c < ncomp) {
+          const int slot = c % RP;
+          if (c >= RP) mbar_wait(&empty_p[slot], ((c / RP) - 1) & 1);
+          mbar_expect_tx(&full_p[slot], pw_bytes);
+          unsigned char* dst = pring + slot * C::PWSLOT;
+          const int px = xs + c + H;  // padded x index of site plane xs + c
+#pragma unroll
+          for (int f = 0; f < NF; ++f) {
+            tma_load_4d(dst + (0 * NF + f) * C::PWTILE, &map_d, &full_p[slot],
+                        z0 + H - C::PWL, y0 + H, px, f);
+            if (read_k) {
+              tma_load_4d(dst + (1 * NF + f) * C::PWTILE, &map_kf, &full_p[slot],
+                          z0 + H - C::PWL, y0 + H, px, f);
+              tma_load_4d(dst + (2 * NF + f) * C::PWTILE, &map_kd, &full_p[slot],
+                          z0 + H - C::PWL, y0 + H, px, f);
+            }
+          }
+        }
+      }
+    }
+    return;
+  }
+
+  // ============================ consumer warps ==================================
+  const int tz = tid % TZ, ty = tid / TZ;
+  const int lane = tid & 31;
+  const int j = y0 + ty, k = z0 + tz * VEC;
+  const bool active = (j < p.Ny) && (k < p.Nz);
+  const int64_t Pz = p.Nz + 2 * H, Py = p.Ny + 2 * H;
+  const int64_t plane_stride = Py * Pz;
+  const int64_t site0 = ((int64_t)H * Py + (j + H)) * Pz + (k + H);
+
+  T a = p.a, hubble = p.hubble;
+  if (p.a_dev) a = (T)(*p.a_dev);
+  if (p.hubble_dev) hubble = (T)(*p.hubble_dev);
+  const T two_h = (T)2 * hubble;
+  const T a_sq = a * a;
+
+  const int own_off = (ty + H) * W + HL + tz * VEC;   // elements, within an f plane
+  const int pw_off = ty * C::PWW + C::PWL + tz * VEC;  // elements, within a pw tile
+
+  V q[NF][2 * H + 1];
+#pragma unroll
+  for (int f = 0; f < NF; ++f)
+#pragma unroll
+    for (int s = 0; s < 2 * H + 1; ++s)
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) q[f][s].v[v] = (T)0;
+
+  double e_kin[NF], e_grad[NF], e_pot = 0.0;
+#pragma unroll
+  for (int f = 0; f < NF; ++f) e_kin[f] = e_grad[f] = 0.0;
+
+  // running output pointers of site plane i (advance by one plane per compute step)
+  T* o_f = p.f_out + site0 + (int64_t)xs * plane_stride;
+  T* o_d = p.dfdt + site0 + (int64_t)xs * plane_stride;
+  T* o_kf = p.kf + site0 + (int64_t)xs * plane_stride;
+  T* o_kd = p.kdfdt + site0 + (int64_t)xs * plane_stride;
+
+  for (int n = 0; n < nsteps; ++n) {
+    const int slot = n % RF;
+    mbar_wait(&full_f[slot], (n / RF) & 1);
+#pragma unroll
+    for (int f = 0; f < NF; ++f) {
+#pragma unroll
+      for (int s = 0; s < 2 * H; ++s) q[f][s] = q[f][s + 1];
+      q[f][2 * H] = ld_vec<T, VEC>(
+          reinterpret_cast<const T*>(fring + (slot * NF + f) * C::FPLANE) + own_off);
+    }
+
+    if (n >= 2 * H) {
+      const int c = n - 2 * H;       // compute index; site plane i = xs + c
+      const int i = xs + c;
+      const int cslot = (n - H) % RF;
+      const int pslot = c % RP;
+      mbar_wait(&full_p[pslot], (c / RP) & 1);
+      if (active) {
+        const unsigned char* pw = pring + pslot * C::PWSLOT;
+        V lap[NF], dold[NF], kfo[NF], kdo[NF];
+#pragma unroll
+        for (int f = 0; f < NF; ++f) {
+          dold[f] = ld_vec<T, VEC>(
+              reinterpret_cast<const T*>(pw + (0 * NF + f) * C::PWTILE) + pw_off);
+          if (read_k) {
+            kfo[f] = ld_vec<T, VEC>(
+                reinterpret_cast<const T*>(pw + (1 * NF + f) * C::PWTILE) + pw_off);
+            kdo[f] = ld_vec<T, VEC>(
+                reinterpret_cast<const T*>(pw + (2 * NF + f) * C::PWTILE) + pw_off);
+          } else {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) kfo[f].v[v] = kdo[f].v[v] = (T)0;
+          }
+          const T* pl = reinterpret_cast<const T*>(fring + (cslot * NF + f) * C::FPLANE);
+          constexpr int NVZ = 1 + 2 * (HL / VEC);
+          T zrow[NVZ * VEC];
+#pragma unroll
+          for (int w = 0; w < NVZ; ++w) {
+            V t = ld_vec<T, VEC>(pl + own_off - HL + w * VEC);
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) zrow[w * VEC + v] = t.v[v];
+          }
+          V yn[2 * H + 1];
+#pragma unroll
+          for (int s = 1; s <= H; ++s) {
+            yn[H + s] = ld_vec<T, VEC>(pl + own_off + s * W);
+            yn[H - s] = ld_vec<T, VEC>(pl + own_off - s * W);
+          }
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) {
+            const T cc = q[f][H].v[v];
+            T sx = (T)lap_coef<H>(0) * cc;
+            T sy = (T)lap_coef<H>(0) * cc;
+            T sz = (T)lap_coef<H>(0) * cc;
+#pragma unroll
+            for (int s = 1; s <= H; ++s) {
+              const T cs = (T)lap_coef<H>(s);
+              sx = sx + cs * q[f][H + s].v[v];
+              sx = sx + cs * q[f][H - s].v[v];
+              sy = sy + cs * yn[H + s].v[v];
+              sy = sy + cs * yn[H - s].v[v];
+              sz = sz + cs * zrow[HL + v + s];
+              sz = sz + cs * zrow[HL + v - s];
+            }
+            lap[f].v[v] = sx * p.inv_dx2[0] + sy * p.inv_dx2[1] + sz * p.inv_dx2[2];
+          }
+        }
+
+        if constexpr (ENERGY) {
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) {
+#pragma unroll
+            for (int f = 0; f < NF; ++f) {
+              const T dv = dold[f].v[v];
+              e_kin[f] += (double)(dv * dv);
+              e_grad[f] += (double)(-(q[f][H].v[v] * lap[f].v[v]));
+            }
+            T Vv = (T)0;
+            for (int t = 0; t < p.nvterms; ++t) {
+              T term = p.vcoef[t];
+#pragma unroll
+              for (int m = 0; m < NF; ++m) {
+                const T fm = q[m][H].v[v];
+                for (int e = 0; e < p.vpower[t][m]; ++e) term = term * fm;
+              }
+              Vv = Vv + term;
+            }
+            e_pot += (double)Vv;
+          }
+        }
+
+#pragma unroll
+        for (int f = 0; f < NF; ++f) {
+          V fo, dn, kfn, kdn;
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) {
+            T dV = (T)0;
+            for (int t = 0; t < p.nterms[f]; ++t) {
+              T term = p.coef[f][t];
+#pragma unroll
+              for (int m = 0; m < NF; ++m) {
+                const T fm = q[m][H].v[v];
+                for (int e = 0; e < p.power[f][t][m]; ++e) term = term * fm;
+              }
+              dV = dV + term;
+            }
+            const T d_old = dold[f].v[v];
+            const T rhs_d = (lap[f].v[v] - two_h * d_old) - a_sq * dV;
+            T kfv, kdv;
+            if (read_k) {
+              kfv = p.A * kfo[f].v[v] + p.dt * d_old;
+              kdv = p.A * kdo[f].v[v] + p.dt * rhs_d;
+            } else {
+              kfv = p.dt * d_old;
+              kdv = p.dt * rhs_d;
+            }
+            kfn.v[v] = kfv;
+            kdn.v[v] = kdv;
+            fo.v[v] = q[f][H].v[v] + p.B * kfv;
+            dn.v[v] = d_old + p.B * kdv;
+          }
+          const int64_t fo_off = f * p.field_stride;
+          st_stream<T, VEC>(o_kf + fo_off, kfn);
+          st_stream<T, VEC>(o_kd + fo_off, kdn);
+          st_stream<T, VEC>(o_d + fo_off, dn);
+          T* fout = o_f + fo_off;
+          st_plain<T, VEC>(fout, fo);
+          if (p.wrap_x) {
+            if (i < H) st_plain<T, VEC>(fout + (int64_t)p.Nx * plane_stride, fo);
+            if (i >= p.Nx - H) st_plain<T, VEC>(fout - (int64_t)p.Nx * plane_stride, fo);
+          }
+          if (p.wrap_y) {
+            if (j < H) st_plain<T, VEC>(fout + (int64_t)p.Ny * Pz, fo);
+            if (j >= p.Ny - H) st_plain<T, VEC>(fout - (int64_t)p.Ny * Pz, fo);
+          }
+          if (p.wrap_z) {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+              if (k + v < H) fout[v + p.Nz] = fo.v[v];
+              if (k + v >= p.Nz - H) fout[v - p.Nz] = fo.v[v];
+            }
+          }
+        }
+      }
+      o_f += plane_stride;
+      o_d += plane_stride;
+      o_kf += plane_stride;
+      o_kd += plane_stride;
+      // this warp is done with the pointwise slot
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_p[pslot]);
+    }
+    // ... and with the f plane that just served as centre plane
+    if (n >= H) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_f[(n - H) % RF]);
+    }
+  }
+
+  if constexpr (ENERGY) {
+    // consumer-only reduction (the producer warp has exited): named barrier 1
+    constexpr int NV = 2 * NF + 1;
+    constexpr int NT = BY * TZ;
+    double vals[NV];
+#pragma unroll
+    for (int f = 0; f < NF; ++f) {
+      vals[f] = e_kin[f];
+      vals[NF + 1 + f] = e_grad[f];
+    }
+    vals[NF] = e_pot;
+    double* red = reinterpret_cast<double*>(pring);  // all pw slots are drained by now
+    asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
+#pragma unroll
+    for (int r = 0; r < NV; ++r) {
+      double x = vals[r];
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
+      if (lane == 0) red[(tid >> 5) * NV + r] = x;
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
+    if (tid < NV) {
+      double x = 0.0;
+      for (int w = 0; w < C::NCW; ++w) x += red[w * NV + tid];
+      const int64_t blk = ((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x +
+                          blockIdx.x;
+      p.energy_partials[(p.energy_slot_offset + blk) * PSB_ENERGY_STRIDE + tid] = x;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+
+template <typename T, int H, int NF, int BY, int TZ, int P>
+static int64_t ws_grid_blocks(const psb_scalar_stage_args* a) {
+  using C = WsCfg<T, H, NF, BY, TZ, P>;
+  const int64_t nx = a->x_end - a->x_begin;
+  if (nx <= 0) return 0;
+  int64_t xchunk = a->tune_xchunk > 0 ? a->tune_xchunk : WS_DEFAULT_XCHUNK;
+  if (xchunk > nx) xchunk = nx;
+  return ((a->Nz + C::BZ - 1) / C::BZ) * ((a->Ny + BY - 1) / BY) *
+         ((nx + xchunk - 1) / xchunk);
+}
+
+// returns 0 ok, >0 error, -1 = layout not TMA-able (caller falls back)
+template <typename T, int H, int NF, int BY, int TZ, int P, int MINB>
+static int launch_ws(const psb_scalar_stage_args* a, cudaStream_t stream) {
+  using C = WsCfg<T, H, NF, BY, TZ, P>;
+  const int64_t Px = a->Nx + 2 * H, Py = a->Ny + 2 * H, Pz = a->Nz + 2 * H;
+  CUtensorMap mf, md, mkf, mkd;
+  if (encode_field_tensor_map(&mf, a->dtype, a->f_in, NF, a->field_stride, Px, Py, Pz, 1,
+                              C::ROWS, C::W) != 0)
+    return -1;
+  if (encode_field_tensor_map(&md, a->dtype, a->dfdt, NF, a->field_stride, Px, Py, Pz, 1,
+                              BY, C::PWW) != 0 ||
+      encode_field_tensor_map(&mkf, a->dtype, a->kf, NF, a->field_stride, Px, Py, Pz, 1, BY,
+                              C::PWW) != 0 ||
+      encode_field_tensor_map(&mkd, a->dtype, a->kdfdt, NF, a->field_stride, Px, Py, Pz, 1,
+                              BY, C::PWW) != 0)
+    return -1;
+
+  FusedParams<T, NF> p;
+  fill_params<T, NF>(p, a);
+  const int64_t nx = a->x_end - a->x_begin;
+  int xchunk = a->tune_xchunk > 0 ? a->tune_xchunk : WS_DEFAULT_XCHUNK;
+  if (xchunk > nx) xchunk = (int)nx;
+  p.xchunk = xchunk;
+  dim3 grid((unsigned)((a->Nz + C::BZ - 1) / C::BZ), (unsigned)((a->Ny + BY - 1) / BY),
+            (unsigned)((nx + xchunk - 1) / xchunk));
+  dim3 block(C::THREADS, 1, 1);
+  if (a->energy_partials != nullptr) {
+    auto kern = fused_stage_ws_kernel<T, H, NF, BY, TZ, P, true, MINB>;
+    PSB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        C::SMEM_BYTES));
+    kern<<<grid, block, C::SMEM_BYTES, stream>>>(p, mf, md, mkf, mkd);
+  } else {
+    auto kern = fused_stage_ws_kernel<T, H, NF, BY, TZ, P, false, MINB>;
+    PSB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        C::SMEM_BYTES));
+    kern<<<grid, block, C::SMEM_BYTES, stream>>>(p, mf, md, mkf, mkd);
+  }
+  PSB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace psb
