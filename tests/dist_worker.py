@@ -1,0 +1,195 @@
+"""
+Worker run by the multi-process tests (gloo on CPU, nccl on GPUs):
+    python tests/dist_worker.py <case> <world> <port> [args...]
+Spawns `world` ranks with torch.multiprocessing and exits non-zero on any failure.
+"""
+import os
+import sys
+import traceback
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def _decomp_case(rank, world, proc_shape, h, grid_shape, backend):
+    import pystella_b200 as ps
+    from helpers import HostOps, periodic_global
+    import oracle as O
+
+    hh = (h,) * 3 if isinstance(h, int) else tuple(h)
+    decomp = ps.DomainDecomposition(proc_shape, h, grid_shape=grid_shape)
+    cuda = backend == "nccl"
+    if not cuda:
+        decomp.host_ops = HostOps()
+    assert decomp.nranks == world and decomp.rank == rank
+    assert decomp.rank_tuple == O.rank_tuple_of(proc_shape, rank)
+    rank_shape, start = decomp.get_rank_shape_start(grid_shape)
+    assert (rank_shape, start) == O.rank_shape_start(proc_shape, grid_shape,
+                                                     decomp.rank_tuple)
+    assert decomp.rank_shape == rank_shape
+
+    # same data on every rank (test/test_decomp.py:61-76)
+    rng = np.random.default_rng(12321)
+    data = periodic_global(rng, grid_shape, hh)
+    sub = np.zeros(tuple(n + 2 * x for n, x in zip(rank_shape, hh)))
+    rank_slice = tuple(slice(s + x, s + n + x) for n, s, x in zip(rank_shape, start, hh))
+    unpadded = tuple(slice(x, -x) if x > 0 else slice(None) for x in hh)
+    sub[unpadded] = data[rank_slice]
+    t = torch.from_numpy(sub.copy())
+    if cuda:
+        t = t.cuda()
+    decomp.share_halos(None, t)
+    if cuda:
+        torch.cuda.synchronize()
+    pencil = tuple(slice(s, s + n + 2 * x) for n, s, x in zip(rank_shape, start, hh))
+    got = t.cpu().numpy()
+    assert np.array_equal(got, data[pencil]), f"rank {rank} {decomp.rank_tuple}: halos wrong"
+
+    # collectives
+    assert decomp.allreduce(rank + 1) == world * (world + 1) // 2
+    assert decomp.allreduce(float(rank), op="max") == float(world - 1)
+    assert decomp.bcast("hello" if rank == 1 else None, 1) == "hello"
+    decomp.Barrier()
+
+    # gather / scatter round trip (test/test_decomp.py:108-173)
+    full = np.zeros(grid_shape) if rank == 0 else None
+    decomp.gather_array(None, t if cuda else t.numpy(), full, 0)
+    if rank == 0:
+        interior = tuple(slice(x, x + n) for x, n in zip(hh, grid_shape))
+        assert np.array_equal(full, data[interior])
+    back = np.zeros_like(sub)
+    decomp.scatter_array(None, full, back, 0)
+    assert np.array_equal(back[unpadded], sub[unpadded])
+
+
+def _reduction_case(rank, world, backend):
+    """Reduction / FieldStatistics over ranks (nccl only: kernels are CUDA)."""
+    import pystella_b200 as ps
+    grid = (32, 16, 24)
+    h = 2
+    decomp = ps.DomainDecomposition((world, 1, 1), h, grid_shape=grid)
+    rs, start = decomp.get_rank_shape_start(grid)
+    rng = np.random.default_rng(7)
+    full = rng.standard_normal(grid)
+    sub = np.zeros(tuple(n + 2 * h for n in rs))
+    sub[h:-h, h:-h, h:-h] = full[start[0]:start[0] + rs[0]]
+    t = torch.from_numpy(sub).cuda()
+    stats = ps.FieldStatistics(decomp, h, max_min=True)
+    out = stats(t)
+    assert np.isclose(out["mean"], full.mean(), rtol=1e-12)
+    assert np.isclose(out["variance"], full.var(), rtol=1e-11)
+    assert out["max"] == full.max() and out["min"] == full.min()
+    red = ps.Reduction(decomp, {"s": [(ps.Field("f", offset="h"), "sum")]}, halo_shape=h)
+    assert np.isclose(red(None, f=t)["s"][0], full.sum(), rtol=1e-12, atol=1e-12)
+
+
+def _fused_case(rank, world, backend, nscalars, energy):
+    """Multi-rank fused stepper (boundary/interior split + face exchange) == single rank."""
+    import pystella_b200 as ps
+    import oracle as O
+    h = 2
+    grid = (8 * world + (4 if world == 2 else 0), 16, 32)   # uneven for world == 2? keep even
+    grid = (16 * world, 16, 32)
+    dx = tuple(5 / n for n in grid)
+    dt = 0.1 * min(dx)
+    rng = np.random.default_rng(99)
+    pad_full = tuple(n + 2 * h for n in grid)
+    f0 = 0.2 + 1e-2 * rng.standard_normal((nscalars,) + pad_full)
+    d0 = -0.1 + 1e-2 * rng.standard_normal((nscalars,) + pad_full)
+    if nscalars == 1:
+        terms = [(0.5, (2,))]
+        def potential(f):
+            return f[0]**2 / 2
+    else:
+        terms = [(0.5, (2, 0)), (0.5, (0, 2)), (0.5, (2, 2))]
+        def potential(f):
+            return f[0]**2 / 2 + f[1]**2 / 2 + f[0]**2 * f[1]**2 / 2
+
+    # global oracle
+    fr, dr = f0.copy(), d0.copy()
+    kf, kd = np.zeros_like(fr), np.zeros_like(fr)
+    lap = np.zeros((nscalars,) + grid)
+    nsteps = 2
+    for _ in range(nsteps):
+        for s in range(5):
+            O.reference_schedule_stage(s, fr, dr, kf, kd, lap, h, dx, dt, a=1.05, hubble=0.2,
+                                       potential_terms=terms)
+
+    decomp = ps.DomainDecomposition((world, 1, 1), h, grid_shape=grid)
+    rs, start = decomp.get_rank_shape_start(grid)
+    sl = slice(start[0], start[0] + rs[0] + 2 * h)
+    f = torch.from_numpy(np.ascontiguousarray(f0[:, sl])).cuda()
+    d = torch.from_numpy(np.ascontiguousarray(d0[:, sl])).cuda()
+    sector = ps.ScalarSector(nscalars, potential=potential)
+    st = ps.LowStorageRK54(sector, halo_shape=h, dt=dt, dx=dx, decomp=decomp,
+                           MapKernel=ps.FusedStencilStage, energy=energy)
+    dexp = None
+    for _ in range(nsteps):
+        for s in range(5):
+            st(s, f=f, dfdt=d, a=1.05, hubble=0.2)
+    torch.cuda.synchronize()
+    inner = slice(start[0] + h, start[0] + h + rs[0])
+    for n in range(nscalars):
+        g = f[n].cpu().numpy()[h:-h, h:-h, h:-h]
+        r = fr[n][inner, h:-h, h:-h]
+        err = np.max(np.abs(g - r)) / np.max(np.abs(r))
+        assert err < 1e-12, f"rank {rank} field {n}: {err}"
+        g = d[n].cpu().numpy()[h:-h, h:-h, h:-h]
+        r = dr[n][inner, h:-h, h:-h]
+        assert np.max(np.abs(g - r)) / np.max(np.abs(r)) < 1e-12
+    if energy:
+        # energy sums of the last stage's input state, all-reduced, vs. a global reduction
+        dexp = ps.DeviceExpansion(1.0, ps.LowStorageRK54, grid_size=float(np.prod(grid)),
+                                  decomp=decomp, nscalars=nscalars)
+        dexp.step(0, st, dt)
+        sums = dexp.sums.cpu().numpy()
+        assert np.all(np.isfinite(sums[:2 * nscalars + 1]))
+        allr = decomp.allreduce(float(st.energy_nslots))
+        assert allr > 0
+
+
+def _worker(rank, world, port, case, args):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank),
+                      WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    backend = "nccl" if case.startswith("gpu") else "gloo"
+    if backend == "nccl":
+        torch.cuda.set_device(rank)
+        dist.init_process_group(backend, rank=rank, world_size=world,
+                                device_id=torch.device("cuda", rank))
+    else:
+        dist.init_process_group(backend, rank=rank, world_size=world)
+    try:
+        if case in ("cpu_decomp", "gpu_decomp"):
+            proc_shape = tuple(int(x) for x in args[0].split(","))
+            for h, grid in ((1, (32, 32, 32)), (2, (19, 23, 16)), ((2, 0, 3), (32, 32, 32)),
+                            ((0, 2, 1), (32, 32, 32)), (1, (109, 67, 32))):
+                _decomp_case(rank, world, proc_shape, h, grid, backend)
+        elif case == "gpu_reduction":
+            _reduction_case(rank, world, backend)
+        elif case == "gpu_fused":
+            _fused_case(rank, world, backend, int(args[0]), args[1] == "1")
+        else:
+            raise ValueError(case)
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def main():
+    case, world, port = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
+    args = sys.argv[4:]
+    try:
+        mp.spawn(_worker, args=(world, port, case, args), nprocs=world, join=True)
+    except Exception:
+        traceback.print_exc()
+        sys.exit(1)
+
+
+if __name__ == "__main__":
+    main()

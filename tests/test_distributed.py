@@ -1,0 +1,77 @@
+"""
+Multi-rank paths.  CPU (gloo, world_size 2-4): rank arithmetic, message ordering of
+share_halos (incl. (Px, Py, 1) decompositions with packed y faces and uneven
+splits), collectives, gather/scatter -- the halo kernels are replaced by the
+oracle-backed tests/helpers.HostOps there.  GPU (nccl): the same through the CUDA
+kernels, reductions over ranks, and the fused stepper's boundary/interior schedule
+against a single global oracle run.
+"""
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _run(case, world, *args, timeout=300):
+    cmd = [sys.executable, os.path.join(HERE, "dist_worker.py"), case, str(world),
+           str(_free_port()), *args]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+
+
+@pytest.mark.parametrize("proc_shape", ["2,1,1", "1,2,1", "2,2,1", "3,1,1"])
+def test_decomposition_gloo(proc_shape):
+    world = 1
+    for p in proc_shape.split(","):
+        world *= int(p)
+    _run("cpu_decomp", world, proc_shape)
+
+
+def _ngpus():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("proc_shape", ["2,1,1", "1,2,1"])
+def test_decomposition_nccl(proc_shape):
+    if _ngpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    _run("gpu_decomp", 2, proc_shape)
+
+
+@pytest.mark.gpu
+def test_reduction_nccl():
+    if _ngpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    _run("gpu_reduction", 2)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nscalars,energy", [(1, "0"), (2, "1")])
+def test_fused_stepper_nccl(nscalars, energy):
+    if _ngpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    _run("gpu_fused", 2, str(nscalars), energy)
+
+
+@pytest.mark.gpu
+def test_fused_stepper_nccl_4():
+    if _ngpus() < 4:
+        pytest.skip("needs 4 GPUs")
+    _run("gpu_fused", 4, "1", "1")
