@@ -298,7 +298,7 @@ def run_b200_arm(args):
         for s in range(NUM_STAGES):
             stepper(s, f=f, dfdt=dfdt, a=expand.a, hubble=expand.hubble)
             expand.step(s, stepper, dt)
-    n_stage_launches = 1 if world == 1 else 3
+    n_stage_launches = 1 if world == 1 else 2
     launches_per_step[0] = NUM_STAGES * (n_stage_launches + 2)
 
     def barrier():
@@ -447,8 +447,15 @@ def run_b200_arm(args):
             "background": {"a": bg["a"], "hubble": bg["hubble"]},
         }
         print(json.dumps(line), flush=True)
+    # leave without tearing NCCL down collectively (captured graphs keep the
+    # communicator busy; a hang here would only waste the lease)
+    sys.stdout.flush()
     if world > 1:
-        dist.destroy_process_group()
+        try:
+            dist.barrier()
+        except Exception:  # noqa: BLE001
+            pass
+        os._exit(0)
 
 
 def run_e2e(args, ps, torch, dist, w, decomp, sector, pin, dev, world, rank,
@@ -460,7 +467,7 @@ def run_e2e(args, ps, torch, dist, w, decomp, sector, pin, dev, world, rank,
     Expansion, whose scalars go back into the next stage; final fields downloaded.
     """
     h, dx, dt = w["h"], w["dx"], w["dt"]
-    steps = max(1, min(args.steps, 10))
+    steps = max(1, args.steps if world == 1 else min(args.steps, 10))
     stepper = ps.LowStorageRK54(sector, halo_shape=h, dt=dt, dx=dx, decomp=decomp,
                                 MapKernel=ps.FusedStencilStage, tune=tune)
     derivs = ps.FiniteDifferencer(decomp, h, dx, rank_shape=w["rank_shape"])

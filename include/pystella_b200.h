@@ -83,6 +83,8 @@ typedef struct psb_scalar_stage_args {
   int32_t wrap_x, wrap_y, wrap_z;/* fused: write periodic images into f_out halos    */
   int64_t Nx, Ny, Nz;            /* rank (un-padded) shape                           */
   int64_t x_begin, x_end;        /* sites updated by this launch                     */
+  int64_t x2_begin, x2_end;      /* fused: optional second x range of the same launch */
+                                 /* (both boundary slabs of a rank in one grid)       */
   int64_t field_stride;          /* elements between fields in padded arrays         */
   int64_t lap_stride;            /* elements between fields in lap_f (unfused)       */
   const void* f_in;              /* padded, field 0                                  */

@@ -70,7 +70,10 @@ def scalar_stage(*, fused, f_in, f_out, dfdt, kf, kdfdt, lap_f=None, h, dx=(1., 
     args.Nx, args.Ny, args.Nz = Nx, Ny, Nz
     if x_range is None:
         x_range = (0, Nx)
-    args.x_begin, args.x_end = x_range
+    if len(x_range) == 2 and isinstance(x_range[0], (tuple, list)):
+        (args.x_begin, args.x_end), (args.x2_begin, args.x2_end) = x_range
+    else:
+        args.x_begin, args.x_end = x_range
     args.field_stride = Px * Py * Pz
     args.f_in = _ptr(f_in)
     args.f_out = _ptr(f_out)

@@ -30,6 +30,7 @@ class ScalarStageArgs(C.Structure):
         ("wrap_x", c_int32), ("wrap_y", c_int32), ("wrap_z", c_int32),
         ("Nx", c_int64), ("Ny", c_int64), ("Nz", c_int64),
         ("x_begin", c_int64), ("x_end", c_int64),
+        ("x2_begin", c_int64), ("x2_end", c_int64),
         ("field_stride", c_int64), ("lap_stride", c_int64),
         ("f_in", c_void_p), ("f_out", c_void_p), ("dfdt", c_void_p),
         ("kf", c_void_p), ("kdfdt", c_void_p), ("lap_f", c_void_p),

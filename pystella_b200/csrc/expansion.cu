@@ -9,25 +9,30 @@
 
 namespace psb {
 
-__global__ void __launch_bounds__(256)
+// 1024 threads: thread t owns column (t % 16) of rows t/16, t/16 + 64, ... so that
+// consecutive threads read consecutive doubles; fixed-order tree over the 64 row
+// groups afterwards (deterministic for a given number of slots).
+__global__ void __launch_bounds__(1024)
     energy_sums_kernel(const double* __restrict__ partials, int64_t nslots, int nvals,
                        double* __restrict__ sums) {
-  __shared__ double sh[8];
-  for (int r = 0; r < nvals; ++r) {
-    double x = 0.0;
-    for (int64_t b = threadIdx.x; b < nslots; b += blockDim.x)
-      x += partials[b * PSB_ENERGY_STRIDE + r];
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
-    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = x;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      double y = sh[0];
-      for (int w = 1; w < 8; ++w) y += sh[w];
-      sums[r] = y;
-    }
+  __shared__ double sh[64][PSB_ENERGY_STRIDE];
+  const int col = threadIdx.x % PSB_ENERGY_STRIDE, grp = threadIdx.x / PSB_ENERGY_STRIDE;
+  double x0 = 0.0, x1 = 0.0, x2 = 0.0, x3 = 0.0;
+  int64_t row = grp;
+  for (; row + 192 < nslots; row += 256) {
+    x0 += partials[row * PSB_ENERGY_STRIDE + col];
+    x1 += partials[(row + 64) * PSB_ENERGY_STRIDE + col];
+    x2 += partials[(row + 128) * PSB_ENERGY_STRIDE + col];
+    x3 += partials[(row + 192) * PSB_ENERGY_STRIDE + col];
+  }
+  for (; row < nslots; row += 64) x0 += partials[row * PSB_ENERGY_STRIDE + col];
+  sh[grp][col] = (x0 + x1) + (x2 + x3);
+  __syncthreads();
+  for (int half = 32; half > 0; half >>= 1) {
+    if (grp < half) sh[grp][col] += sh[grp + half][col];
     __syncthreads();
   }
+  if (threadIdx.x < nvals) sums[threadIdx.x] = sh[0][threadIdx.x];
 }
 
 struct Energies {
@@ -102,7 +107,7 @@ extern "C" int psb_energy_sums(const double* partials, int64_t nslots, int nvals
   PSB_REQUIRE(partials && sums, "psb_energy_sums: null pointer");
   PSB_REQUIRE(nslots > 0 && nvals > 0 && nvals <= PSB_ENERGY_STRIDE,
               "psb_energy_sums: bad sizes (nslots=%lld, nvals=%d)", (long long)nslots, nvals);
-  energy_sums_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(partials, nslots,
+  energy_sums_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(partials, nslots,
                                                                       nvals, sums);
   PSB_CHECK_CUDA(cudaGetLastError());
   return 0;

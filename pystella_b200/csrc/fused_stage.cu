@@ -18,6 +18,10 @@ static int validate(const psb_scalar_stage_args* a) {
   PSB_REQUIRE(a->x_begin >= 0 && a->x_end <= a->Nx && a->x_begin <= a->x_end,
               "psb_scalar_stage_fused: bad x range [%lld, %lld)", (long long)a->x_begin,
               (long long)a->x_end);
+  PSB_REQUIRE(a->x2_begin >= 0 && a->x2_end <= a->Nx && a->x2_begin <= a->x2_end,
+              "psb_scalar_stage_fused: bad second x range");
+  PSB_REQUIRE(a->x2_end == a->x2_begin || a->x2_begin >= a->x_end || a->x2_end <= a->x_begin,
+              "psb_scalar_stage_fused: the two x ranges overlap");
   PSB_REQUIRE(a->nscalars >= 1 && a->nscalars <= PSB_MAX_SCALARS,
               "psb_scalar_stage_fused: nscalars=%d out of range", a->nscalars);
   for (int f = 0; f < a->nscalars; ++f)
@@ -34,7 +38,7 @@ static int validate(const psb_scalar_stage_args* a) {
 extern "C" int psb_scalar_stage_fused(const psb_scalar_stage_args* a, void* stream) {
   using namespace psb;
   if (int rc = validate(a)) return rc;
-  if (a->x_begin == a->x_end) return 0;
+  if (a->x_begin == a->x_end && a->x2_begin == a->x2_end) return 0;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   return a->dtype == PSB_F64 ? fused_dispatch_f64(a, s, nullptr)
                              : fused_dispatch_f32(a, s, nullptr);

@@ -36,6 +36,7 @@ template <typename T, int NF> struct FusedParams {
   int64_t field_stride;
   int Nx, Ny, Nz;
   int x_begin, x_end, xchunk;
+  int x2_begin, x2_end, nchunks1;
   int wrap_x, wrap_y, wrap_z;
   T inv_dx2[3];
   T dt, A, B, a, hubble;
@@ -118,8 +119,14 @@ __global__ void __launch_bounds__(BY* TZ, MINB)
   const int tz = threadIdx.x, ty = threadIdx.y;
   const int tid = ty * TZ + tz;
   const int z0 = blockIdx.x * C::BZ, y0 = blockIdx.y * BY;
-  const int xs = p.x_begin + blockIdx.z * p.xchunk;
-  const int xe = min(xs + p.xchunk, p.x_end);
+  int zc = blockIdx.z, xb = p.x_begin, xlim = p.x_end;
+  if (zc >= p.nchunks1) {  // second x range of the launch
+    zc -= p.nchunks1;
+    xb = p.x2_begin;
+    xlim = p.x2_end;
+  }
+  const int xs = xb + zc * p.xchunk;
+  const int xe = min(xs + p.xchunk, xlim);
   const int nsteps = (xe - xs) + 2 * H;
 
   const int j = y0 + ty, k = z0 + tz * VEC;
@@ -409,6 +416,24 @@ __global__ void __launch_bounds__(BY* TZ, MINB)
 // host side
 // ---------------------------------------------------------------------------
 
+// chunking of the (up to two) x ranges of one launch along gridDim.z
+struct XLayout {
+  int xchunk, n1, n2;
+};
+static inline XLayout x_layout(const psb_scalar_stage_args* a, int default_chunk) {
+  const int64_t nx1 = a->x_end - a->x_begin;
+  const int64_t nx2 = a->x2_end > a->x2_begin ? a->x2_end - a->x2_begin : 0;
+  int64_t xc = a->tune_xchunk > 0 ? a->tune_xchunk : default_chunk;
+  const int64_t nmax = nx1 > nx2 ? nx1 : nx2;
+  if (xc > nmax) xc = nmax;
+  if (xc < 1) xc = 1;
+  XLayout L;
+  L.xchunk = (int)xc;
+  L.n1 = (int)((nx1 + xc - 1) / xc);
+  L.n2 = (int)((nx2 + xc - 1) / xc);
+  return L;
+}
+
 template <typename T, int NF>
 static void fill_params(FusedParams<T, NF>& p, const psb_scalar_stage_args* a) {
   p.f_in = static_cast<const T*>(a->f_in);
@@ -422,6 +447,8 @@ static void fill_params(FusedParams<T, NF>& p, const psb_scalar_stage_args* a) {
   p.Nz = (int)a->Nz;
   p.x_begin = (int)a->x_begin;
   p.x_end = (int)a->x_end;
+  p.x2_begin = (int)a->x2_begin;
+  p.x2_end = (int)a->x2_end;
   p.wrap_x = a->wrap_x;
   p.wrap_y = a->wrap_y;
   p.wrap_z = a->wrap_z;
@@ -458,12 +485,11 @@ static int launch_fused(const psb_scalar_stage_args* a, cudaStream_t stream) {
   using C = FusedCfg<T, H, NF, VEC, BY, TZ, P>;
   FusedParams<T, NF> p;
   fill_params<T, NF>(p, a);
-  const int64_t nx = a->x_end - a->x_begin;
-  int xchunk = a->tune_xchunk > 0 ? a->tune_xchunk : 64;
-  if (xchunk > nx) xchunk = (int)nx;
-  p.xchunk = xchunk;
+  const XLayout L = x_layout(a, 64);
+  p.xchunk = L.xchunk;
+  p.nchunks1 = L.n1;
   dim3 grid((unsigned)((a->Nz + C::BZ - 1) / C::BZ), (unsigned)((a->Ny + BY - 1) / BY),
-            (unsigned)((nx + xchunk - 1) / xchunk));
+            (unsigned)(L.n1 + L.n2));
   dim3 block(TZ, BY, 1);
 
   const int64_t Px = a->Nx + 2 * H, Py = a->Ny + 2 * H, Pz = a->Nz + 2 * H;
@@ -498,12 +524,8 @@ static int launch_fused(const psb_scalar_stage_args* a, cudaStream_t stream) {
 template <typename T, int H, int NF, int VEC, int BY, int TZ, int P>
 static int64_t fused_grid_blocks(const psb_scalar_stage_args* a) {
   using C = FusedCfg<T, H, NF, VEC, BY, TZ, P>;
-  const int64_t nx = a->x_end - a->x_begin;
-  if (nx <= 0) return 0;
-  int64_t xchunk = a->tune_xchunk > 0 ? a->tune_xchunk : 64;
-  if (xchunk > nx) xchunk = nx;
-  return ((a->Nz + C::BZ - 1) / C::BZ) * ((a->Ny + BY - 1) / BY) *
-         ((nx + xchunk - 1) / xchunk);
+  const XLayout L = x_layout(a, 64);
+  return ((a->Nz + C::BZ - 1) / C::BZ) * ((a->Ny + BY - 1) / BY) * (int64_t)(L.n1 + L.n2);
 }
 
 }  // namespace psb

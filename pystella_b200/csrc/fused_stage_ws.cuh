@@ -94,8 +94,14 @@ __global__ void __launch_bounds__(BY* TZ + 32, MINB)
 
   const int tid = threadIdx.x;
   const int z0 = blockIdx.x * C::BZ, y0 = blockIdx.y * BY;
-  const int xs = p.x_begin + blockIdx.z * p.xchunk;
-  const int xe = min(xs + p.xchunk, p.x_end);
+  int zc = blockIdx.z, xb = p.x_begin, xlim = p.x_end;
+  if (zc >= p.nchunks1) {  // second x range of the launch
+    zc -= p.nchunks1;
+    xb = p.x2_begin;
+    xlim = p.x2_end;
+  }
+  const int xs = xb + zc * p.xchunk;
+  const int xe = min(xs + p.xchunk, xlim);
   const int nsteps = (xe - xs) + 2 * H;   // f planes streamed
   const int ncomp = xe - xs;              // site planes computed
   const bool read_k = (p.A != (T)0);
@@ -390,12 +396,8 @@ __global__ void __launch_bounds__(BY* TZ + 32, MINB)
 template <typename T, int H, int NF, int BY, int TZ, int P>
 static int64_t ws_grid_blocks(const psb_scalar_stage_args* a) {
   using C = WsCfg<T, H, NF, BY, TZ, P>;
-  const int64_t nx = a->x_end - a->x_begin;
-  if (nx <= 0) return 0;
-  int64_t xchunk = a->tune_xchunk > 0 ? a->tune_xchunk : WS_DEFAULT_XCHUNK;
-  if (xchunk > nx) xchunk = nx;
-  return ((a->Nz + C::BZ - 1) / C::BZ) * ((a->Ny + BY - 1) / BY) *
-         ((nx + xchunk - 1) / xchunk);
+  const XLayout L = x_layout(a, WS_DEFAULT_XCHUNK);
+  return ((a->Nz + C::BZ - 1) / C::BZ) * ((a->Ny + BY - 1) / BY) * (int64_t)(L.n1 + L.n2);
 }
 
 // returns 0 ok, >0 error, -1 = layout not TMA-able (caller falls back)
@@ -417,12 +419,11 @@ static int launch_ws(const psb_scalar_stage_args* a, cudaStream_t stream) {
 
   FusedParams<T, NF> p;
   fill_params<T, NF>(p, a);
-  const int64_t nx = a->x_end - a->x_begin;
-  int xchunk = a->tune_xchunk > 0 ? a->tune_xchunk : WS_DEFAULT_XCHUNK;
-  if (xchunk > nx) xchunk = (int)nx;
-  p.xchunk = xchunk;
+  const XLayout L = x_layout(a, WS_DEFAULT_XCHUNK);
+  p.xchunk = L.xchunk;
+  p.nchunks1 = L.n1;
   dim3 grid((unsigned)((a->Nz + C::BZ - 1) / C::BZ), (unsigned)((a->Ny + BY - 1) / BY),
-            (unsigned)((nx + xchunk - 1) / xchunk));
+            (unsigned)(L.n1 + L.n2));
   dim3 block(C::THREADS, 1, 1);
   if (a->energy_partials != nullptr) {
     auto kern = fused_stage_ws_kernel<T, H, NF, BY, TZ, P, true, MINB>;

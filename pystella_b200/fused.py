@@ -73,8 +73,9 @@ def _launch_ranges(Nx, h, multi):
         return [(0, Nx)]
     hb = min(h, Nx)
     if Nx - hb > hb:
-        return [(0, hb), (Nx - hb, Nx), (hb, Nx - hb)]
-    return [(0, hb), (hb, Nx)]
+        # both boundary slabs in ONE launch (two x ranges), then the interior
+        return [((0, hb), (Nx - hb, Nx)), (hb, Nx - hb)]
+    return [(0, Nx)]   # slab so thin that everything is boundary
 
 
 def fused_scalar_stage(stepper, system, f, common, queue):
@@ -140,7 +141,7 @@ def fused_scalar_stage(stepper, system, f, common, queue):
         energy_kw = [dict(energy_partials=stepper.energy_partials, energy_slot_offset=o)
                      for o in offsets]
     else:
-        energy_kw = [{}, {}, {}]
+        energy_kw = [{}, {}]
 
     if not multi:
         _kernels.scalar_stage(wrap=(True, True, True), **args, **energy_kw[0])
@@ -152,9 +153,7 @@ def fused_scalar_stage(stepper, system, f, common, queue):
             ranges = _launch_ranges(Nx, h, True)
             _kernels.scalar_stage(wrap=(False, True, True), x_range=ranges[0], **args,
                                   **energy_kw[0])
-            _kernels.scalar_stage(wrap=(False, True, True), x_range=ranges[1], **args,
-                                  **energy_kw[1])
-            interior = ranges[2] if len(ranges) > 2 else None
+            interior = ranges[1] if len(ranges) > 1 else None
             st["boundary_done"].record(cur)
         with torch.cuda.stream(st["comm"]):
             st["comm"].wait_event(st["boundary_done"])
@@ -164,7 +163,7 @@ def fused_scalar_stage(stepper, system, f, common, queue):
         if interior is not None:
             with torch.cuda.stream(cur):
                 _kernels.scalar_stage(wrap=(False, True, True), x_range=interior, **args,
-                                      **energy_kw[2])
+                                      **energy_kw[1])
         cur.wait_event(st["comm_done"])
 
     _swap_storage(f, twin)
