@@ -35,6 +35,7 @@ extern "C" {
 #define PSB_MAX_SCALARS 4      /* fields per ScalarSector handled by one launch   */
 #define PSB_MAX_TERMS 16       /* monomials of dV/df_n per field                  */
 #define PSB_ENERGY_STRIDE 16    /* doubles per energy-partials row (>= 2*MAX_SCALARS+1) */
+#define PSB_ENERGY_SUMS_DOUBLES (16 + 64 * 16 + 2)
 #define PSB_MAX_RED_ARRAYS 8   /* distinct input arrays of one reduction launch   */
 #define PSB_MAX_RED_TERMS 32   /* monomials over all outputs of one reduction     */
 #define PSB_MAX_RED_OUTPUTS 16 /* reductions per launch                           */
@@ -193,7 +194,8 @@ int64_t psb_scalar_stage_energy_slots(const psb_scalar_stage_args* args);
  * pystella/expansion.py:101-157).
  *
  * psb_energy_sums folds `nslots` partial rows into sums[0..nvals) in a fixed
- * order (single CTA).  psb_expansion_stage (single thread) then forms, with the
+ * order (two-level, one launch).  `sums` must hold PSB_ENERGY_SUMS_DOUBLES doubles,
+ * zero-initialised once by the caller (result + scratch rows + a ticket counter).  psb_expansion_stage (single thread) then forms, with the
  * CURRENT scale factor a = state[0]:
  *     kinetic_n  = sums[n]        / (2 a^2) / grid_size
  *     potential  = sums[ns]                 / grid_size

@@ -9,30 +9,52 @@
 
 namespace psb {
 
-// 1024 threads: thread t owns column (t % 16) of rows t/16, t/16 + 64, ... so that
-// consecutive threads read consecutive doubles; fixed-order tree over the 64 row
-// groups afterwards (deterministic for a given number of slots).
-__global__ void __launch_bounds__(1024)
+// Two-level fold in ONE launch: FOLD_BLOCKS blocks each fold a contiguous share of
+// the rows (thread t owns column t % 16 of rows t/16, t/16 + 16, ... of its share, so
+// consecutive threads read consecutive doubles); the last block to finish (atomic
+// ticket) folds the FOLD_BLOCKS block rows in index order -> deterministic result.
+constexpr int FOLD_BLOCKS = 64;
+constexpr int FOLD_THREADS = 256;
+
+__global__ void __launch_bounds__(FOLD_THREADS)
     energy_sums_kernel(const double* __restrict__ partials, int64_t nslots, int nvals,
-                       double* __restrict__ sums) {
-  __shared__ double sh[64][PSB_ENERGY_STRIDE];
+                       double* __restrict__ sums, double* __restrict__ scratch,
+                       unsigned int* __restrict__ ticket) {
+  constexpr int GROUPS = FOLD_THREADS / PSB_ENERGY_STRIDE;  // 16 rows in parallel
+  __shared__ double sh[GROUPS][PSB_ENERGY_STRIDE];
+  __shared__ bool last;
   const int col = threadIdx.x % PSB_ENERGY_STRIDE, grp = threadIdx.x / PSB_ENERGY_STRIDE;
-  double x0 = 0.0, x1 = 0.0, x2 = 0.0, x3 = 0.0;
-  int64_t row = grp;
-  for (; row + 192 < nslots; row += 256) {
+  const int64_t per = (nslots + gridDim.x - 1) / gridDim.x;
+  const int64_t r0 = per * blockIdx.x;
+  const int64_t r1 = r0 + per < nslots ? r0 + per : nslots;
+  double x0 = 0.0, x1 = 0.0;
+  int64_t row = r0 + grp;
+  for (; row + GROUPS < r1; row += 2 * GROUPS) {
     x0 += partials[row * PSB_ENERGY_STRIDE + col];
-    x1 += partials[(row + 64) * PSB_ENERGY_STRIDE + col];
-    x2 += partials[(row + 128) * PSB_ENERGY_STRIDE + col];
-    x3 += partials[(row + 192) * PSB_ENERGY_STRIDE + col];
+    x1 += partials[(row + GROUPS) * PSB_ENERGY_STRIDE + col];
   }
-  for (; row < nslots; row += 64) x0 += partials[row * PSB_ENERGY_STRIDE + col];
-  sh[grp][col] = (x0 + x1) + (x2 + x3);
+  if (row < r1) x0 += partials[row * PSB_ENERGY_STRIDE + col];
+  sh[grp][col] = x0 + x1;
   __syncthreads();
-  for (int half = 32; half > 0; half >>= 1) {
+  for (int half = GROUPS / 2; half > 0; half >>= 1) {
     if (grp < half) sh[grp][col] += sh[grp + half][col];
     __syncthreads();
   }
-  if (threadIdx.x < nvals) sums[threadIdx.x] = sh[0][threadIdx.x];
+  if (threadIdx.x < PSB_ENERGY_STRIDE)
+    scratch[blockIdx.x * PSB_ENERGY_STRIDE + threadIdx.x] = sh[0][threadIdx.x];
+  __threadfence();
+  if (threadIdx.x == 0) last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (last) {
+    __threadfence();
+    if (threadIdx.x < nvals) {
+      double y = 0.0;
+      for (unsigned b = 0; b < gridDim.x; ++b)
+        y += scratch[b * PSB_ENERGY_STRIDE + threadIdx.x];
+      sums[threadIdx.x] = y;
+    }
+    if (threadIdx.x == 0) *ticket = 0u;  // re-arm for the next launch
+  }
 }
 
 struct Energies {
@@ -107,8 +129,14 @@ extern "C" int psb_energy_sums(const double* partials, int64_t nslots, int nvals
   PSB_REQUIRE(partials && sums, "psb_energy_sums: null pointer");
   PSB_REQUIRE(nslots > 0 && nvals > 0 && nvals <= PSB_ENERGY_STRIDE,
               "psb_energy_sums: bad sizes (nslots=%lld, nvals=%d)", (long long)nslots, nvals);
-  energy_sums_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(partials, nslots,
-                                                                      nvals, sums);
+  // sums[16 .. 16 + 64*16 + 1): scratch rows and the ticket (zeroed by the caller once)
+  double* scratch = sums + PSB_ENERGY_STRIDE;
+  unsigned int* ticket =
+      reinterpret_cast<unsigned int*>(scratch + FOLD_BLOCKS * PSB_ENERGY_STRIDE);
+  int blocks = FOLD_BLOCKS;
+  if (nslots < 4 * FOLD_BLOCKS) blocks = 1;
+  energy_sums_kernel<<<blocks, FOLD_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+      partials, nslots, nvals, sums, scratch, ticket);
   PSB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

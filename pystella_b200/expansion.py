@@ -109,7 +109,8 @@ class DeviceExpansion:
         self.state = torch.tensor([a0, adot0, adot0 / a0, 0., 0.], dtype=torch.float64,
                                   device=dev)
         self.a, self.adot, self.hubble = self.state[0:1], self.state[1:2], self.state[2:3]
-        self.sums = torch.zeros(16, dtype=torch.float64, device=dev)
+        self._sums_buf = torch.zeros(16 + 64 * 16 + 2, dtype=torch.float64, device=dev)
+        self.sums = self._sums_buf[:16]
         self.energies = torch.zeros(2 * nscalars + 3, dtype=torch.float64, device=dev)
 
     def step(self, stage, stepper, dt, queue=None):
@@ -120,7 +121,7 @@ class DeviceExpansion:
                              "MapKernel=FusedStencilStage, energy=True and call it first")
         nvals = stepper.energy_nvals
         _kernels.energy_sums(stepper.energy_partials, stepper.energy_nslots, nvals,
-                             self.sums, queue, self.strict_fp)
+                             self._sums_buf, queue, self.strict_fp)
         if self.decomp is not None and self.decomp.nranks > 1:
             import torch.distributed as dist
             dist.all_reduce(self.sums, group=self.decomp.comm)

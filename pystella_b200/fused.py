@@ -66,12 +66,14 @@ def exchange_x_faces(decomp, f, h, fields_axis):
     return dist.batch_isend_irecv(ops)
 
 
-def _launch_ranges(Nx, h, multi):
+def _launch_ranges(Nx, h, multi, chunk=16):
     """x-ranges of the launches of one stage: whole slab, or lo / hi boundary slabs
     followed by the interior."""
     if not multi:
         return [(0, Nx)]
-    hb = min(h, Nx)
+    # the boundary launch takes whole x-chunks (no extra prologue planes compared
+    # with being part of the interior launch); the faces are their outermost h planes
+    hb = min(max(h, chunk), Nx)
     if Nx - hb > hb:
         # both boundary slabs in ONE launch (two x ranges), then the interior
         return [((0, hb), (Nx - hb, Nx)), (hb, Nx - hb)]
@@ -123,7 +125,7 @@ def fused_scalar_stage(stepper, system, f, common, queue):
                 "fused energy sums need the potential V: construct the stepper from a "
                 "ScalarSector")
         args.update(V_terms=stepper._V_values)
-        ranges = _launch_ranges(Nx, h, multi)
+        ranges = _launch_ranges(Nx, h, multi, args["xchunk"] or 16)
         lkey = (tuple(f.shape), f.dtype, multi, args["xchunk"], args["variant"])
         cache = stepper.__dict__.setdefault("_energy_layout", {})
         if lkey not in cache:
@@ -150,7 +152,7 @@ def fused_scalar_stage(stepper, system, f, common, queue):
         cur = queue if queue is not None else torch.cuda.current_stream()
         with torch.cuda.stream(cur):
             # boundary slabs first
-            ranges = _launch_ranges(Nx, h, True)
+            ranges = _launch_ranges(Nx, h, True, args["xchunk"] or 16)
             _kernels.scalar_stage(wrap=(False, True, True), x_range=ranges[0], **args,
                                   **energy_kw[0])
             interior = ranges[1] if len(ranges) > 1 else None
