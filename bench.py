@@ -46,6 +46,7 @@ def parse():
     p.add_argument("--no-cpu", action="store_true")
     p.add_argument("--xchunk", type=int, default=0)
     p.add_argument("--variant", type=int, default=0)
+    p.add_argument("--nx", type=int, default=0, help="override the global x extent")
     return p.parse_args()
 
 
@@ -53,12 +54,14 @@ def parse():
 # workload
 # ---------------------------------------------------------------------------
 
-def workload(grid, dtype, world, rank, scaling):
+def workload(grid, dtype, world, rank, scaling, nx=0):
     h = 2
     if scaling == "weak":
         grid_shape = (grid * world, grid, grid)
     else:
         grid_shape = (grid, grid, grid)
+    if nx:
+        grid_shape = (nx, grid, grid)
     box = (5.0 * grid_shape[0] / grid, 5.0, 5.0)
     dx = tuple(L / N for L, N in zip(box, grid_shape))
     dt = 0.1 * min(dx)
@@ -266,7 +269,7 @@ def run_b200_arm(args):
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node N"
 
-    w = workload(args.grid, args.dtype, world, rank, args.scaling)
+    w = workload(args.grid, args.dtype, world, rank, args.scaling, args.nx)
     h, dx, dt = w["h"], w["dx"], w["dt"]
     tdtype = torch.float64 if args.dtype == "f64" else torch.float32
     S = 8 if args.dtype == "f64" else 4
@@ -377,6 +380,9 @@ def run_b200_arm(args):
             expand.step(s, stepper, dt)
             stage_ms.append((s, a_ev, b_ev))
     torch.cuda.synchronize()
+    if os.environ.get("PSB_TIMELINE", "0") == "1" and rank == 0:
+        from pystella_b200.fused import timeline_report
+        print("[timeline ms since stage begin]", timeline_report(), file=sys.stderr)
     per_stage = {}
     for s, a_ev, b_ev in stage_ms:
         per_stage.setdefault(s, []).append(a_ev.elapsed_time(b_ev))

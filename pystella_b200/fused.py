@@ -21,6 +21,8 @@ are swapped (no copy), so the user-visible contract "``f`` is updated in place"
 of ``f`` taken before the call keep pointing at the old storage.
 """
 
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -34,10 +36,36 @@ def _swap_storage(a, b):
     a.data, b.data = b_data, a_data
 
 
+TIMELINE = os.environ.get("PSB_TIMELINE", "0") == "1"
+_timeline = []   # (label, event) tuples appended in issue order when PSB_TIMELINE=1
+
+
+def _mark(label, stream):
+    if TIMELINE:
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record(stream)
+        _timeline.append((label, ev))
+
+
+def timeline_report():
+    """Average gaps between consecutive marks (ms) since the last report."""
+    torch.cuda.synchronize()
+    out = {}
+    base = None
+    for label, ev in _timeline:
+        if label == "stage_begin":
+            base = ev
+            continue
+        if base is not None:
+            out.setdefault(label, []).append(base.elapsed_time(ev))
+    _timeline.clear()
+    return {k: sum(v) / len(v) for k, v in out.items()}
+
+
 def _ensure_streams(stepper):
     if stepper._streams is None:
         stepper._streams = {
-            "comm": torch.cuda.Stream(),
+            "comm": torch.cuda.Stream(priority=-1),
             "boundary_done": torch.cuda.Event(),
             "comm_done": torch.cuda.Event(),
         }
@@ -150,6 +178,7 @@ def fused_scalar_stage(stepper, system, f, common, queue):
     else:
         st = _ensure_streams(stepper)
         cur = queue if queue is not None else torch.cuda.current_stream()
+        _mark("stage_begin", cur)
         with torch.cuda.stream(cur):
             # boundary slabs first
             ranges = _launch_ranges(Nx, h, True, args["xchunk"] or 16)
@@ -157,15 +186,19 @@ def fused_scalar_stage(stepper, system, f, common, queue):
                                   **energy_kw[0])
             interior = ranges[1] if len(ranges) > 1 else None
             st["boundary_done"].record(cur)
+            _mark("boundary_done", cur)
         with torch.cuda.stream(st["comm"]):
             st["comm"].wait_event(st["boundary_done"])
             for req in exchange_x_faces(decomp, twin, h, f.dim() == 4):
                 req.wait()
             st["comm_done"].record(st["comm"])
+            _mark("comm_done", st["comm"])
         if interior is not None:
             with torch.cuda.stream(cur):
                 _kernels.scalar_stage(wrap=(False, True, True), x_range=interior, **args,
                                       **energy_kw[1])
+            _mark("interior_done", cur)
         cur.wait_event(st["comm_done"])
+        _mark("joined", cur)
 
     _swap_storage(f, twin)
