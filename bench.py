@@ -368,6 +368,9 @@ def run_b200_arm(args):
     assert np.isfinite(bg["a"]) and bg["a"] > 1.0, "background did not evolve"
 
     # ---------------- roofline of the dominant kernel (eager, per-launch events) ----
+    if os.environ.get("PSB_TIMELINE", "0") == "1":
+        from pystella_b200 import fused as _fused
+        _fused._timeline.clear()
     stage_ms = []
     reps = max(2, min(steps, 6))
     for _ in range(reps):

@@ -99,6 +99,16 @@ typedef struct psb_scalar_stage_args {
   double a, hubble;              /* used when a_dev/hubble_dev are NULL              */
   const double* a_dev;           /* optional device scalars (stay on device)         */
   const double* hubble_dev;
+  /* Fused compute + halo exchange over peer memory (x-slab decomposition, NVLink):
+   * when non-NULL, the new f of the h lowest / highest site planes is ALSO stored
+   * straight into the high / low x-halo of the neighbouring rank's f_out buffer
+   * (peer-mapped device pointers to field 0 of that buffer).  Replaces the
+   * pack -> D2H -> MPI.Sendrecv -> H2D -> unpack of pystella/decomp.py:402-419. */
+  void* peer_lo_f_out;           /* rank rx-1 (its HIGH halo receives my low planes)  */
+  void* peer_hi_f_out;           /* rank rx+1 (its LOW halo receives my high planes)  */
+  int64_t peer_lo_Nx;            /* x extent of rank rx-1 (locates its high halo)     */
+  int64_t peer_lo_stride;        /* field strides (elements) of the peers' buffers    */
+  int64_t peer_hi_stride;
   int32_t nterms[PSB_MAX_SCALARS];
   double coef[PSB_MAX_SCALARS][PSB_MAX_TERMS];
   int8_t power[PSB_MAX_SCALARS][PSB_MAX_TERMS][PSB_MAX_SCALARS];
@@ -213,6 +223,25 @@ int psb_energy_sums(const double* partials, int64_t nslots, int nvals, double* s
 int psb_expansion_stage(const double* sums, int nscalars, double grid_size, double mpl,
                         double dt, double A, double B, double* state, double* energies,
                         void* stream);
+/* Multi-rank variant without NCCL: every rank stores its sums into slot `rank` of
+ * each peer's symmetric slot array (peer_slots[q] -> rank q's array of
+ * [2][nranks][PSB_ENERGY_STRIDE] doubles), raises its flag there
+ * (peer_flags[q] -> rank q's uint64[2][nranks]), waits for all flags, adds the
+ * slots in rank order (bit-identical on all ranks) and then performs
+ * psb_expansion_stage.  The kernel doubles as the inter-GPU barrier that orders
+ * the peer-memory halo stores of psb_scalar_stage_fused before the next stage.
+ * `epoch` is a device counter the kernel increments (CUDA-graph friendly).
+ * With nscalars == 0 only the barrier is performed (no energies / expansion). */
+typedef struct psb_peer_args {
+  int32_t nranks, rank;
+  void* const* peer_slots;       /* device array of nranks pointers                  */
+  void* const* peer_flags;       /* device array of nranks pointers                  */
+  uint64_t* epoch;               /* device counter (this rank)                       */
+} psb_peer_args;
+int psb_expansion_stage_peer(const psb_peer_args* peers, const double* sums, int nscalars,
+                             double grid_size, double mpl, double dt, double A, double B,
+                             double* state, double* energies, void* stream);
+
 /* adot = sqrt(8 pi a^2 rho / (3 mpl^2)) a from energies (first Friedmann equation,
  * pystella/expansion.py:101-117): initialises state = {a, adot, hubble, 0, 0}. */
 int psb_expansion_init(const double* sums, int nscalars, double grid_size, double mpl,

@@ -39,7 +39,7 @@ def scalar_stage(*, fused, f_in, f_out, dfdt, kf, kdfdt, lap_f=None, h, dx=(1., 
                  dV_terms=None, wrap=(True, True, True), x_range=None,
                  queue=None, strict=False, xchunk=0, variant=0,
                  energy_partials=None, energy_slot_offset=0, V_terms=None,
-                 count_slots_only=False):
+                 count_slots_only=False, peer=None):
     """
     One scalar-sector LSRK stage on padded arrays of shape ``(n, Nx+2h, Ny+2h, Nz+2h)``
     (or without the leading axis for a single field).
@@ -92,6 +92,13 @@ def scalar_stage(*, fused, f_in, f_out, dfdt, kf, kdfdt, lap_f=None, h, dx=(1., 
     args.a, args.hubble = float(a), float(hubble)
     args.a_dev = _ptr(a_dev)
     args.hubble_dev = _ptr(hubble_dev)
+    if peer is not None:
+        # dict(lo=ptr, hi=ptr, lo_Nx=.., lo_stride=.., hi_stride=..): peer-mapped f_out
+        args.peer_lo_f_out = C.c_void_p(peer["lo"])
+        args.peer_hi_f_out = C.c_void_p(peer["hi"])
+        args.peer_lo_Nx = peer["lo_Nx"]
+        args.peer_lo_stride = peer["lo_stride"]
+        args.peer_hi_stride = peer["hi_stride"]
     fill_potential(args, dV_terms, nscalars)
     args.tune_xchunk = xchunk
     args.tune_variant = variant
@@ -255,3 +262,15 @@ def expansion_init(sums, nscalars, grid_size, mpl, a0, state, energies, queue=No
                                 float(a0), _ptr(state), _ptr(energies),
                                 _lib.stream_ptr(queue))
     _lib.check(lib, rc, "psb_expansion_init")
+
+
+def expansion_stage_peer(peer_args, sums, nscalars, grid_size, mpl, dt, A, B, state,
+                         energies, queue=None, strict=False):
+    """All-gather of the sums over peer memory + barrier + expansion stage (one kernel);
+    ``nscalars == 0``: barrier only."""
+    lib = _lib.load(strict)
+    rc = lib.psb_expansion_stage_peer(C.byref(peer_args), _ptr(sums), nscalars,
+                                      float(grid_size), float(mpl), float(dt), float(A),
+                                      float(B), _ptr(state), _ptr(energies),
+                                      _lib.stream_ptr(queue))
+    _lib.check(lib, rc, "psb_expansion_stage_peer")

@@ -38,6 +38,8 @@ class ScalarStageArgs(C.Structure):
         ("dt", c_double), ("A", c_double), ("B", c_double),
         ("a", c_double), ("hubble", c_double),
         ("a_dev", c_void_p), ("hubble_dev", c_void_p),
+        ("peer_lo_f_out", c_void_p), ("peer_hi_f_out", c_void_p),
+        ("peer_lo_Nx", c_int64), ("peer_lo_stride", c_int64), ("peer_hi_stride", c_int64),
         ("nterms", c_int32 * MAX_SCALARS),
         ("coef", (c_double * MAX_TERMS) * MAX_SCALARS),
         ("power", ((C.c_int8 * MAX_SCALARS) * MAX_TERMS) * MAX_SCALARS),
@@ -48,6 +50,11 @@ class ScalarStageArgs(C.Structure):
         ("vpower", (C.c_int8 * MAX_SCALARS) * MAX_TERMS),
         ("tune_xchunk", c_int32), ("tune_variant", c_int32),
     ]
+
+
+class PeerArgs(C.Structure):
+    _fields_ = [("nranks", c_int32), ("rank", c_int32), ("peer_slots", c_void_p),
+                ("peer_flags", c_void_p), ("epoch", c_void_p)]
 
 
 class ReduceArgs(C.Structure):
@@ -93,6 +100,9 @@ SYMBOLS = {
     "psb_energy_sums": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "psb_expansion_stage": (c_int, [c_void_p, c_int, c_double, c_double, c_double,
                                     c_double, c_double, c_void_p, c_void_p, c_void_p]),
+    "psb_expansion_stage_peer": (c_int, [C.POINTER(PeerArgs), c_void_p, c_int, c_double,
+                                         c_double, c_double, c_double, c_double, c_void_p,
+                                         c_void_p, c_void_p]),
     "psb_expansion_init": (c_int, [c_void_p, c_int, c_double, c_double, c_double,
                                    c_void_p, c_void_p, c_void_p]),
 }

@@ -106,6 +106,76 @@ __global__ void expansion_stage_kernel(const double* sums, int ns, double grid_s
   state[4] = kadot;
 }
 
+// All-gather of the energy sums over peer memory + inter-GPU barrier + expansion
+// stage, one CTA.  slots: [2][nranks][STRIDE] doubles, flags: [2][nranks] uint64 on
+// every rank (symmetric); parity = epoch & 1 double-buffers both.
+__global__ void __launch_bounds__(64)
+    expansion_stage_peer_kernel(psb_peer_args peers, const double* sums, int ns,
+                                double grid_size, double mpl, double dt, double A, double B,
+                                double* state, double* energies) {
+  __shared__ double total[PSB_ENERGY_STRIDE];
+  const int P = peers.nranks, me = peers.rank;
+  const unsigned long long epoch = *peers.epoch + 1ull;
+  const int par = (int)(epoch & 1ull);
+  const int nvals = ns > 0 ? 2 * ns + 1 : 0;
+  const int t = threadIdx.x;
+  // 1. my sums -> slot [par][me] of every rank (incl. myself)
+  for (int e = t; e < P * nvals; e += blockDim.x) {
+    const int q = e / nvals, r = e % nvals;
+    double* dst = static_cast<double*>(peers.peer_slots[q]) +
+                  ((int64_t)par * P + me) * PSB_ENERGY_STRIDE;
+    dst[r] = sums[r];
+  }
+  __threadfence_system();
+  __syncthreads();
+  // 2. raise my flag on every rank; everything this rank stored to its peers before
+  //    this kernel (the halo planes of the stage kernel) is ordered before it
+  if (t < P) {
+    unsigned long long* fl = static_cast<unsigned long long*>(peers.peer_flags[t]) +
+                             (int64_t)par * P + me;
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(fl), "l"(epoch) : "memory");
+  }
+  // 3. wait for every rank's flag
+  if (t < P) {
+    const unsigned long long* mine =
+        static_cast<unsigned long long*>(peers.peer_flags[me]) + (int64_t)par * P + t;
+    unsigned long long seen;
+    do {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(mine) : "memory");
+    } while (seen < epoch);
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (t == 0) *peers.epoch = epoch;
+  if (ns <= 0) return;
+  // 4. add the slots in rank order (identical on all ranks)
+  if (t < nvals) {
+    const volatile double* sl =
+        static_cast<double*>(peers.peer_slots[me]) + (int64_t)par * P * PSB_ENERGY_STRIDE;
+    double x = 0.0;
+    for (int q = 0; q < P; ++q) x += sl[q * PSB_ENERGY_STRIDE + t];
+    total[t] = x;
+  }
+  __syncthreads();
+  if (t != 0) return;
+  double a = state[0], adot = state[1], ka = state[3], kadot = state[4];
+  const Energies e = form_energies(total, ns, grid_size, a, energies);
+  const double pi = 3.141592653589793;
+  const double rhs_a = adot;
+  const double rhs_adot = 4.0 * pi * (a * a) / 3.0 / (mpl * mpl) *
+                          (e.total - 3.0 * e.pressure) * a;
+  ka = A * ka + dt * rhs_a;
+  a = a + B * ka;
+  kadot = A * kadot + dt * rhs_adot;
+  adot = adot + B * kadot;
+  state[0] = a;
+  state[1] = adot;
+  state[2] = adot / a;
+  state[3] = ka;
+  state[4] = kadot;
+}
+
 __global__ void expansion_init_kernel(const double* sums, int ns, double grid_size,
                                       double mpl, double a0, double* state,
                                       double* energies) {
@@ -165,6 +235,29 @@ extern "C" int psb_expansion_init(const double* sums, int nscalars, double grid_
   PSB_REQUIRE(grid_size > 0 && mpl > 0 && a0 > 0, "psb_expansion_init: bad scalars");
   expansion_init_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(
       sums, nscalars, grid_size, mpl, a0, state, energies);
+  PSB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int psb_expansion_stage_peer(const psb_peer_args* peers, const double* sums,
+                                        int nscalars, double grid_size, double mpl,
+                                        double dt, double A, double B, double* state,
+                                        double* energies, void* stream) {
+  using namespace psb;
+  PSB_REQUIRE(peers != nullptr, "psb_expansion_stage_peer: null peers");
+  PSB_REQUIRE(peers->nranks >= 1 && peers->nranks <= 64 && peers->rank >= 0 &&
+                  peers->rank < peers->nranks,
+              "psb_expansion_stage_peer: bad rank/nranks");
+  PSB_REQUIRE(peers->peer_slots && peers->peer_flags && peers->epoch,
+              "psb_expansion_stage_peer: null peer tables");
+  PSB_REQUIRE(nscalars >= 0 && nscalars <= PSB_MAX_SCALARS,
+              "psb_expansion_stage_peer: nscalars=%d out of range", nscalars);
+  if (nscalars > 0) {
+    PSB_REQUIRE(sums && state && energies, "psb_expansion_stage_peer: null pointer");
+    PSB_REQUIRE(grid_size > 0 && mpl > 0, "psb_expansion_stage_peer: bad grid_size/mpl");
+  }
+  expansion_stage_peer_kernel<<<1, 64, 0, static_cast<cudaStream_t>(stream)>>>(
+      *peers, sums, nscalars, grid_size, mpl, dt, A, B, state, energies);
   PSB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -38,6 +38,10 @@ template <typename T, int NF> struct FusedParams {
   int x_begin, x_end, xchunk;
   int x2_begin, x2_end, nchunks1;
   int wrap_x, wrap_y, wrap_z;
+  T* peer_lo;   // peer-mapped f_out of rank rx-1 / rx+1 (or null)
+  T* peer_hi;
+  int peer_lo_Nx;
+  int64_t peer_lo_stride, peer_hi_stride;
   T inv_dx2[3];
   T dt, A, B, a, hubble;
   const double* a_dev;
@@ -346,6 +350,17 @@ __global__ void __launch_bounds__(BY* TZ, MINB)
           if (i < H) st_plain<T, VEC>(fout + (int64_t)p.Nx * plane_stride, fo);
           if (i >= p.Nx - H) st_plain<T, VEC>(fout - (int64_t)p.Nx * plane_stride, fo);
         }
+        // NVLink: my boundary planes -> the neighbours' x halos (peer memory)
+        if (p.peer_lo != nullptr && i < H)
+          st_plain<T, VEC>(p.peer_lo + f * p.peer_lo_stride +
+                               (int64_t)(p.peer_lo_Nx + H + i) * plane_stride +
+                               (int64_t)(j + H) * Pz + (k + H),
+                           fo);
+        if (p.peer_hi != nullptr && i >= p.Nx - H)
+          st_plain<T, VEC>(p.peer_hi + f * p.peer_hi_stride +
+                               (int64_t)(i - p.Nx + H) * plane_stride +
+                               (int64_t)(j + H) * Pz + (k + H),
+                           fo);
         if (p.wrap_y) {
           if (j < H) st_plain<T, VEC>(fout + (int64_t)p.Ny * Pz, fo);
           if (j >= p.Ny - H) st_plain<T, VEC>(fout - (int64_t)p.Ny * Pz, fo);
@@ -449,6 +464,11 @@ static void fill_params(FusedParams<T, NF>& p, const psb_scalar_stage_args* a) {
   p.x_end = (int)a->x_end;
   p.x2_begin = (int)a->x2_begin;
   p.x2_end = (int)a->x2_end;
+  p.peer_lo = static_cast<T*>(a->peer_lo_f_out);
+  p.peer_hi = static_cast<T*>(a->peer_hi_f_out);
+  p.peer_lo_Nx = (int)a->peer_lo_Nx;
+  p.peer_lo_stride = a->peer_lo_stride;
+  p.peer_hi_stride = a->peer_hi_stride;
   p.wrap_x = a->wrap_x;
   p.wrap_y = a->wrap_y;
   p.wrap_z = a->wrap_z;

@@ -330,6 +330,17 @@ __global__ void __launch_bounds__(BY* TZ + 32, MINB)
             if (i < H) st_plain<T, VEC>(fout + (int64_t)p.Nx * plane_stride, fo);
             if (i >= p.Nx - H) st_plain<T, VEC>(fout - (int64_t)p.Nx * plane_stride, fo);
           }
+          // NVLink: my boundary planes -> the neighbours' x halos (peer memory)
+          if (p.peer_lo != nullptr && i < H)
+            st_plain<T, VEC>(p.peer_lo + f * p.peer_lo_stride +
+                                 (int64_t)(p.peer_lo_Nx + H + i) * plane_stride +
+                                 (int64_t)(j + H) * Pz + (k + H),
+                             fo);
+          if (p.peer_hi != nullptr && i >= p.Nx - H)
+            st_plain<T, VEC>(p.peer_hi + f * p.peer_hi_stride +
+                                 (int64_t)(i - p.Nx + H) * plane_stride +
+                                 (int64_t)(j + H) * Pz + (k + H),
+                             fo);
           if (p.wrap_y) {
             if (j < H) st_plain<T, VEC>(fout + (int64_t)p.Ny * Pz, fo);
             if (j >= p.Ny - H) st_plain<T, VEC>(fout - (int64_t)p.Ny * Pz, fo);

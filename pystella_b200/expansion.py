@@ -122,6 +122,14 @@ class DeviceExpansion:
         nvals = stepper.energy_nvals
         _kernels.energy_sums(stepper.energy_partials, stepper.energy_nslots, nvals,
                              self._sums_buf, queue, self.strict_fp)
+        pg = getattr(stepper, "_peer", None)
+        if pg is not None and getattr(stepper, "_halo_mode", None) == "peer":
+            # all-gather over peer memory + inter-GPU barrier + expansion, one kernel
+            _kernels.expansion_stage_peer(pg.args, self.sums, self.nscalars, self.grid_size,
+                                          self.mpl, dt, self._A[stage], self._B[stage],
+                                          self.state, self.energies, queue, self.strict_fp)
+            stepper._peer_barrier_pending = False
+            return
         if self.decomp is not None and self.decomp.nranks > 1:
             import torch.distributed as dist
             dist.all_reduce(self.sums, group=self.decomp.comm)

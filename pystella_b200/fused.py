@@ -23,6 +23,7 @@ of ``f`` taken before the call keep pointing at the old storage.
 
 import os
 
+import numpy as np
 import torch
 import torch.distributed as dist
 
@@ -108,6 +109,55 @@ def _launch_ranges(Nx, h, multi, chunk=16):
     return [(0, Nx)]   # slab so thin that everything is boundary
 
 
+def _halo_mode(stepper, decomp, multi):
+    """'peer' (stores over NVLink from inside the stage kernel) or 'nccl' (send/recv
+    on a side stream overlapped with the interior launch)."""
+    if not multi:
+        return "local"
+    mode = getattr(stepper, "_halo_mode", None)
+    if mode is None:
+        from pystella_b200.peer import PeerGroup, peer_memory_available
+        want = os.environ.get("PSB_HALO_MODE", "peer")
+        mode = "nccl"
+        if want == "peer" and peer_memory_available(decomp):
+            try:
+                stepper._peer = PeerGroup(decomp, torch.device("cuda",
+                                                               torch.cuda.current_device()))
+                mode = "peer"
+            except Exception as exc:  # noqa: BLE001
+                import logging
+                logging.getLogger(__name__).warning(
+                    "peer memory unavailable (%r): falling back to NCCL halos", exc)
+        # all ranks must agree
+        agreed = decomp.allreduce(1 if mode == "peer" else 0, op="min")
+        mode = "peer" if agreed == 1 else "nccl"
+        stepper._halo_mode = mode
+        stepper._peer_state = {}
+        stepper._peer_barrier_pending = False
+    return mode
+
+
+def _setup_peer_buffers(stepper, key, f, h):
+    """Move ``f`` into a symmetric buffer, create the symmetric twin, exchange the
+    geometry of the x neighbours."""
+    pg = stepper._peer
+    decomp = stepper.decomp
+    A, ptrsA = pg.symmetric_like(f)
+    B, ptrsB = pg.symmetric_like(f)
+    A.copy_(f)
+    B.copy_(f)
+    f.data = A
+    stepper._twins[key] = B
+    shapes = pg.gather_shapes(f.shape)
+    lo = decomp.rankID(decomp.rx - 1, decomp.ry, decomp.rz)
+    hi = decomp.rankID(decomp.rx + 1, decomp.ry, decomp.rz)
+    vol = [int(np.prod(sh[-3:])) for sh in shapes]
+    stepper._peer_state[key] = dict(
+        ids={A.data_ptr(): 0, B.data_ptr(): 1}, ptrs=[ptrsA, ptrsB], lo=lo, hi=hi,
+        lo_Nx=shapes[lo][-3] - 2 * h, lo_stride=vol[lo], hi_stride=vol[hi])
+    stepper._halos_fresh = False
+
+
 def fused_scalar_stage(stepper, system, f, common, queue):
     h = common["h"]
     decomp = stepper.decomp
@@ -120,6 +170,9 @@ def fused_scalar_stage(stepper, system, f, common, queue):
         raise ValueError("decomp.halo_shape differs from the stepper's halo_shape")
 
     key = system.f_name
+    mode = _halo_mode(stepper, decomp, multi)
+    if mode == "peer" and key not in stepper._twins:
+        _setup_peer_buffers(stepper, key, f, h)
     twin = stepper._twins.get(key)
     if twin is None or twin.shape != f.shape or twin.dtype != f.dtype \
             or twin.device != f.device:
@@ -153,8 +206,8 @@ def fused_scalar_stage(stepper, system, f, common, queue):
                 "fused energy sums need the potential V: construct the stepper from a "
                 "ScalarSector")
         args.update(V_terms=stepper._V_values)
-        ranges = _launch_ranges(Nx, h, multi, args["xchunk"] or 16)
-        lkey = (tuple(f.shape), f.dtype, multi, args["xchunk"], args["variant"])
+        ranges = _launch_ranges(Nx, h, multi and mode != "peer", args["xchunk"] or 16)
+        lkey = (tuple(f.shape), f.dtype, multi, mode, args["xchunk"], args["variant"])
         cache = stepper.__dict__.setdefault("_energy_layout", {})
         if lkey not in cache:
             cache[lkey] = [_kernels.scalar_stage(x_range=r, count_slots_only=True, **args)
@@ -175,6 +228,16 @@ def fused_scalar_stage(stepper, system, f, common, queue):
 
     if not multi:
         _kernels.scalar_stage(wrap=(True, True, True), **args, **energy_kw[0])
+    elif mode == "peer":
+        ps = stepper._peer_state[key]
+        if stepper._peer_barrier_pending:
+            # nobody folded the previous stage's barrier into an expansion step
+            stepper._peer.barrier_kernel(queue, stepper.strict_fp)
+        out_id = ps["ids"][twin.data_ptr()]
+        peer = dict(lo=ps["ptrs"][out_id][ps["lo"]], hi=ps["ptrs"][out_id][ps["hi"]],
+                    lo_Nx=ps["lo_Nx"], lo_stride=ps["lo_stride"], hi_stride=ps["hi_stride"])
+        _kernels.scalar_stage(wrap=(False, True, True), peer=peer, **args, **energy_kw[0])
+        stepper._peer_barrier_pending = True
     else:
         st = _ensure_streams(stepper)
         cur = queue if queue is not None else torch.cuda.current_stream()

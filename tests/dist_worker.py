@@ -89,13 +89,14 @@ def _reduction_case(rank, world, backend):
     assert np.isclose(red(None, f=t)["s"][0], full.sum(), rtol=1e-12, atol=1e-12)
 
 
-def _fused_case(rank, world, backend, nscalars, energy):
+def _fused_case(rank, world, backend, nscalars, energy, mode="peer"):
     """Multi-rank fused stepper (boundary/interior split + face exchange) == single rank."""
+    os.environ["PSB_HALO_MODE"] = mode
     import pystella_b200 as ps
     import oracle as O
     h = 2
-    grid = (8 * world + (4 if world == 2 else 0), 16, 32)   # uneven for world == 2? keep even
-    grid = (16 * world, 16, 32)
+    # 40 planes per rank: boundary chunks + interior in NCCL mode; uneven in peer mode
+    grid = (40 * world + (3 if mode == "peer" else 0), 16, 32)
     dx = tuple(5 / n for n in grid)
     dt = 0.1 * min(dx)
     rng = np.random.default_rng(99)
@@ -134,6 +135,7 @@ def _fused_case(rank, world, backend, nscalars, energy):
         for s in range(5):
             st(s, f=f, dfdt=d, a=1.05, hubble=0.2)
     torch.cuda.synchronize()
+    assert st._halo_mode == mode, (st._halo_mode, mode)
     inner = slice(start[0] + h, start[0] + h + rs[0])
     for n in range(nscalars):
         g = f[n].cpu().numpy()[h:-h, h:-h, h:-h]
@@ -145,13 +147,33 @@ def _fused_case(rank, world, backend, nscalars, energy):
         assert np.max(np.abs(g - r)) / np.max(np.abs(r)) < 1e-12
     if energy:
         # energy sums of the last stage's input state, all-reduced, vs. a global reduction
+        # energies of the last stage's INPUT state: reproduce with the oracle by
+        # re-running everything but that stage
+        fr2, dr2 = f0.copy(), d0.copy()
+        kf2, kd2 = np.zeros_like(fr2), np.zeros_like(fr2)
+        for i in range(nsteps * 5 - 1):
+            O.reference_schedule_stage(i % 5, fr2, dr2, kf2, kd2, lap, h, dx, dt, a=1.05,
+                                       hubble=0.2, potential_terms=terms)
+        fi, di, laps = [], [], []
+        for n in range(nscalars):
+            g = fr2[n].copy()
+            O.share_halos(g, h)
+            laps.append(O.laplacian(g, h, dx))
+            fi.append(O.interior(fr2[n], h))
+            di.append(O.interior(dr2[n], h))
+        ref = O.get_rho_and_p(O.scalar_energy(fi, di, laps, 1.3, terms))
         dexp = ps.DeviceExpansion(1.0, ps.LowStorageRK54, grid_size=float(np.prod(grid)),
-                                  decomp=decomp, nscalars=nscalars)
+                                  decomp=decomp, nscalars=nscalars, a0=1.3)
         dexp.step(0, st, dt)
-        sums = dexp.sums.cpu().numpy()
-        assert np.all(np.isfinite(sums[:2 * nscalars + 1]))
-        allr = decomp.allreduce(float(st.energy_nslots))
-        assert allr > 0
+        got = dexp.get()
+        assert np.isclose(got["total"], ref["total"], rtol=1e-12), (got["total"], ref["total"])
+        assert np.isclose(got["pressure"], ref["pressure"], rtol=1e-10, atol=1e-14)
+        # identical on all ranks, bit for bit
+        tot = torch.tensor([got["total"]], dtype=torch.float64, device="cuda")
+        lo, hi = tot.clone(), tot.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        assert float(lo) == float(hi)
 
 
 def _worker(rank, world, port, case, args):
@@ -173,7 +195,8 @@ def _worker(rank, world, port, case, args):
         elif case == "gpu_reduction":
             _reduction_case(rank, world, backend)
         elif case == "gpu_fused":
-            _fused_case(rank, world, backend, int(args[0]), args[1] == "1")
+            _fused_case(rank, world, backend, int(args[0]), args[1] == "1",
+                        args[2] if len(args) > 2 else "peer")
         else:
             raise ValueError(case)
         dist.barrier()

@@ -63,15 +63,19 @@ def test_reduction_nccl():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["peer", "nccl"])
 @pytest.mark.parametrize("nscalars,energy", [(1, "0"), (2, "1")])
-def test_fused_stepper_nccl(nscalars, energy):
+def test_fused_stepper_two_ranks(nscalars, energy, mode):
+    """peer: halo planes stored into the neighbour's memory by the stage kernel +
+    peer all-gather/barrier kernel; nccl: boundary-first schedule with send/recv."""
     if _ngpus() < 2:
         pytest.skip("needs 2 GPUs")
-    _run("gpu_fused", 2, str(nscalars), energy)
+    _run("gpu_fused", 2, str(nscalars), energy, mode)
 
 
 @pytest.mark.gpu
-def test_fused_stepper_nccl_4():
+@pytest.mark.parametrize("mode", ["peer", "nccl"])
+def test_fused_stepper_four_ranks(mode):
     if _ngpus() < 4:
         pytest.skip("needs 4 GPUs")
-    _run("gpu_fused", 4, "1", "1")
+    _run("gpu_fused", 4, "1", "1", mode)
