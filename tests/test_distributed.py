@@ -25,9 +25,14 @@ def _free_port():
 
 
 def _run(case, world, *args, timeout=300):
-    cmd = [sys.executable, os.path.join(HERE, "dist_worker.py"), case, str(world),
-           str(_free_port()), *args]
-    res = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
+    for attempt in range(3):
+        cmd = [sys.executable, os.path.join(HERE, "dist_worker.py"), case, str(world),
+               str(_free_port()), *args]
+        res = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
+        if res.returncode == 0:
+            return
+        if "EADDRINUSE" not in res.stderr + res.stdout:
+            break   # a real failure; port collisions are retried
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
 
 
