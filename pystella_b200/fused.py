@@ -153,9 +153,24 @@ def _setup_peer_buffers(stepper, key, f, h):
     hi = decomp.rankID(decomp.rx + 1, decomp.ry, decomp.rz)
     vol = [int(np.prod(sh[-3:])) for sh in shapes]
     stepper._peer_state[key] = dict(
-        ids={A.data_ptr(): 0, B.data_ptr(): 1}, ptrs=[ptrsA, ptrsB], lo=lo, hi=hi,
+        ids={A.data_ptr(): 0, B.data_ptr(): 1}, bufs=(A.view(A.shape), B.view(B.shape)),
+        ptrs=[ptrsA, ptrsB], lo=lo, hi=hi,
         lo_Nx=shapes[lo][-3] - 2 * h, lo_stride=vol[lo], hi_stride=vol[hi])
     stepper._halos_fresh = False
+
+
+def _adopt_into_peer_buffers(stepper, key, f):
+    """A tensor that does not live in the symmetric buffers was passed (e.g. freshly
+    uploaded initial conditions): move it in; the ping-pong restarts from buffer A."""
+    ps = stepper._peer_state[key]
+    A, B = ps["bufs"]
+    if tuple(A.shape) != tuple(f.shape) or A.dtype != f.dtype:
+        raise ValueError("array shape/dtype changed between calls of a multi-rank fused "
+                         "stepper; construct a new stepper")
+    A.copy_(f)
+    f.data = A
+    stepper._twins[key] = B.view(B.shape)   # a fresh object: .data swaps must not
+    stepper._halos_fresh = False             # touch the stable views in ps["bufs"]
 
 
 def fused_scalar_stage(stepper, system, f, common, queue):
@@ -171,8 +186,11 @@ def fused_scalar_stage(stepper, system, f, common, queue):
 
     key = system.f_name
     mode = _halo_mode(stepper, decomp, multi)
-    if mode == "peer" and key not in stepper._twins:
-        _setup_peer_buffers(stepper, key, f, h)
+    if mode == "peer":
+        if key not in stepper._peer_state:
+            _setup_peer_buffers(stepper, key, f, h)
+        elif f.data_ptr() not in stepper._peer_state[key]["ids"]:
+            _adopt_into_peer_buffers(stepper, key, f)
     twin = stepper._twins.get(key)
     if twin is None or twin.shape != f.shape or twin.dtype != f.dtype \
             or twin.device != f.device:
