@@ -131,6 +131,32 @@ int psb_scalar_stage_fused(const psb_scalar_stage_args* args, void* stream);
 int psb_scalar_stage_unfused(const psb_scalar_stage_args* args, void* stream);
 
 /* ------------------------------------------------------------------------
+ * Tensor-perturbation (gravitational-wave) sector stage, element-wise:
+ * TensorPerturbationSector.rhs_dict (pystella/sectors.py:187-204) with the
+ * trace-dropped scalar stress tensor (sectors.py:146-152) advanced by one
+ * low-storage RK stage (step.py:473-491).  For the six packed components
+ * c = tensor_index(i, j), i <= j (sectors.py:164-167):
+ *     rhs_hij    = dhijdt_c
+ *     rhs_dhijdt = lap_hij_c - 2*hubble*dhijdt_c
+ *                  + source_coef * sum_n dfdx[n][i-1] * dfdx[n][j-1]
+ * hij/dhijdt/k arrays are padded (6, Nx+2h, ..); lap_hij (6, N..) and
+ * dfdx (nscalars, 3, N..) are unpadded and precomputed (FiniteDifferencer).
+ * ---------------------------------------------------------------------- */
+typedef struct psb_tensor_stage_args {
+  int32_t dtype, nscalars, h, reserved;
+  int64_t Nx, Ny, Nz;
+  void* hij;
+  void* dhijdt;
+  void* khij;
+  void* kdhijdt;
+  const void* lap_hij;
+  const void* dfdx;
+  double dt, A, B, hubble, source_coef;
+  const double* hubble_dev;
+} psb_tensor_stage_args;
+int psb_tensor_stage_unfused(const psb_tensor_stage_args* args, void* stream);
+
+/* ------------------------------------------------------------------------
  * Finite differences: FiniteDifferencer.__call__ kernels lap_knl / grad_knl /
  * grad_lap_knl / pd{x,y,z}_knl / pd*_incr_knl (pystella/derivs.py:291-337).
  * `fx` is padded by `halo` >= h with valid halos; any of lap/pdx/pdy/pdz may be

@@ -52,6 +52,16 @@ class ScalarStageArgs(C.Structure):
     ]
 
 
+class TensorStageArgs(C.Structure):
+    _fields_ = [("dtype", c_int32), ("nscalars", c_int32), ("h", c_int32),
+                ("reserved", c_int32),
+                ("Nx", c_int64), ("Ny", c_int64), ("Nz", c_int64),
+                ("hij", c_void_p), ("dhijdt", c_void_p), ("khij", c_void_p),
+                ("kdhijdt", c_void_p), ("lap_hij", c_void_p), ("dfdx", c_void_p),
+                ("dt", c_double), ("A", c_double), ("B", c_double), ("hubble", c_double),
+                ("source_coef", c_double), ("hubble_dev", c_void_p)]
+
+
 class PeerArgs(C.Structure):
     _fields_ = [("nranks", c_int32), ("rank", c_int32), ("peer_slots", c_void_p),
                 ("peer_flags", c_void_p), ("epoch", c_void_p)]
@@ -80,6 +90,7 @@ SYMBOLS = {
     "psb_strict_fp": (c_int, []),
     "psb_scalar_stage_fused": (c_int, [C.POINTER(ScalarStageArgs), c_void_p]),
     "psb_scalar_stage_unfused": (c_int, [C.POINTER(ScalarStageArgs), c_void_p]),
+    "psb_tensor_stage_unfused": (c_int, [C.POINTER(TensorStageArgs), c_void_p]),
     "psb_finite_difference": (c_int, [c_void_p] * 5 + [c_int, c_int64, c_int64, c_int64,
                                                         c_int, c_int,
                                                         C.POINTER(c_double * 3), c_int,

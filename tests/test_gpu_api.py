@@ -435,3 +435,84 @@ def test_device_resident_preheating_loop(nscalars):
     for i in range(nscalars):
         assert scale_err(O.interior(f[i].cpu().numpy(), h), O.interior(fr[i], h)) < 1e-12
         assert scale_err(O.interior(dfdt[i].cpu().numpy(), h), O.interior(dr[i], h)) < 1e-12
+
+
+@pytest.mark.parametrize("fused_scalars", [False, True])
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-12), (np.float32, 3e-5)])
+def test_two_scalars_plus_gw_sector(fused_scalars, dtype, tol):
+    """
+    Config 4 structure: ScalarSector(2) + TensorPerturbationSector in one stepper
+    (examples/scalar_preheating.py:107-114, 258-266), derivatives by
+    FiniteDifferencer, against the oracle's scalar_rhs + gw_rhs + lsrk_stage.
+    """
+    rng = np.random.default_rng(5)
+    N, h = (16, 12, 20), 2
+    pad = tuple(n + 2 * h for n in N)
+    dx = tuple(5 / n for n in N)
+    dt = 0.1 * min(dx)
+    potential, terms = _example_potential(mphi=1.0, gsq=0.3)
+    f0 = (0.2 * rng.standard_normal((2,) + pad)).astype(dtype)
+    d0 = (0.2 * rng.standard_normal((2,) + pad)).astype(dtype)
+    h0 = (1e-2 * rng.standard_normal((6,) + pad)).astype(dtype)
+    dh0 = (1e-2 * rng.standard_normal((6,) + pad)).astype(dtype)
+    a, hubble = 1.1, 0.3
+
+    # ---- oracle
+    F, D, Hh, DH = (x.astype(np.float64) for x in (f0, d0, h0, dh0))
+    kF, kD, kH, kDH = (np.zeros_like(x) for x in (F, D, Hh, DH))
+    A_, B_, _ = O.LSRK_TABLES["LowStorageRK54"]
+
+    def derivs_all():
+        lapf, grd, laph = [], [], []
+        for n in range(2):
+            O.share_halos(F[n], h)
+            lapf.append(O.laplacian(F[n], h, dx))
+            grd.append(O.gradient(F[n], h, dx))
+        for c in range(6):
+            O.share_halos(Hh[c], h)
+            laph.append(O.laplacian(Hh[c], h, dx))
+        return lapf, np.stack(grd), laph
+
+    for s in range(5):
+        lapf, grd, laph = derivs_all()
+        Fi = [O.interior(F[n], h) for n in range(2)]
+        Di = [O.interior(D[n], h) for n in range(2)]
+        Hi = [O.interior(Hh[c], h) for c in range(6)]
+        DHi = [O.interior(DH[c], h) for c in range(6)]
+        rhs = [np.array(r) for r in O.scalar_rhs(Fi, Di, lapf, a, hubble, terms)]
+        rhs += [np.array(r) for r in O.gw_rhs(DHi, laph, grd, hubble)]
+        unk, tmp = [], []
+        for n in range(2):
+            unk += [Fi[n], Di[n]]
+            tmp += [O.interior(kF[n], h), O.interior(kD[n], h)]
+        for c in range(6):
+            unk += [Hi[c], DHi[c]]
+            tmp += [O.interior(kH[c], h), O.interior(kDH[c], h)]
+        O.lsrk_stage(A_[s], B_[s], dt, unk, tmp, rhs)
+
+    # ---- device, the reference's loop
+    decomp = ps.DomainDecomposition((1, 1, 1), h, N)
+    scalar_sector = ps.ScalarSector(2, potential=potential)
+    gw_sector = ps.TensorPerturbationSector([scalar_sector])
+    kw = dict(halo_shape=h, rank_shape=N, dt=dt)
+    if fused_scalars:
+        kw.update(MapKernel=ps.FusedStencilStage, dx=dx, decomp=decomp)
+    stepper = ps.LowStorageRK54([scalar_sector, gw_sector], **kw)
+    assert stepper.num_unknowns == 16
+    derivs = ps.FiniteDifferencer(decomp, h, dx, rank_shape=N)
+    f, dfdt, hij, dhijdt = (to_dev(x) for x in (f0, d0, h0, dh0))
+    tdt = f.dtype
+    lap_f = torch.zeros((2,) + N, dtype=tdt, device="cuda")
+    dfdx = torch.zeros((2, 3) + N, dtype=tdt, device="cuda")
+    lap_hij = torch.zeros((6,) + N, dtype=tdt, device="cuda")
+    for s in range(5):
+        derivs(None, fx=f, lap=lap_f, grd=dfdx)
+        derivs(None, fx=hij, lap=lap_hij)
+        stepper(s, queue=None, a=np.array(a), hubble=np.array(hubble), f=f, dfdt=dfdt,
+                dfdx=dfdx, lap_f=lap_f, hij=hij, dhijdt=dhijdt, lap_hij=lap_hij,
+                filter_args=True)
+    assert set(stepper.tmp_arrays) == {"_f_tmp", "_dfdt_tmp", "_hij_tmp", "_dhijdt_tmp"}
+    for got, ref in ((f, F), (dfdt, D), (hij, Hh), (dhijdt, DH)):
+        for c in range(ref.shape[0]):
+            assert scale_err(O.interior(got[c].cpu().numpy(), h),
+                             O.interior(ref[c], h)) < tol
