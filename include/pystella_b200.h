@@ -131,6 +131,34 @@ int psb_scalar_stage_fused(const psb_scalar_stage_args* args, void* stream);
 int psb_scalar_stage_unfused(const psb_scalar_stage_args* args, void* stream);
 
 /* ------------------------------------------------------------------------
+ * Classical Runge-Kutta stage (storage copies along a leading axis) of the scalar
+ * sector, element-wise: RungeKuttaStepper.make_steps (pystella/step.py:202-239)
+ * with the step_statements of RungeKutta4 / RK3 / RK2 (step.py:242-411).
+ * f, dfdt: (ncopies, nscalars, padded); lap_f: (nscalars, N) computed by the caller
+ * from copy `q_read` (0 at stage 0, else 1; step.py:231).  For both unknowns u:
+ *     u[dst[s]] = sum_m coef[s][m] * u[src[s][m]] + dt_coef[s] * dt * rhs_u(copy q_read)
+ * for s < nstatements, all right-hand sides and sources taken from the old state.
+ * ---------------------------------------------------------------------- */
+typedef struct psb_rk_stage_args {
+  int32_t dtype, nscalars, h, ncopies;
+  int64_t Nx, Ny, Nz;
+  void* f;
+  void* dfdt;
+  const void* lap_f;
+  int32_t q_read, nstatements;
+  int32_t dst[2];
+  int32_t ncomb[2];
+  int32_t src[2][2];
+  double coef[2][2];
+  double dt_coef[2];
+  double dt, a, hubble;
+  int32_t nterms[PSB_MAX_SCALARS];
+  double pcoef[PSB_MAX_SCALARS][PSB_MAX_TERMS];
+  int8_t power[PSB_MAX_SCALARS][PSB_MAX_TERMS][PSB_MAX_SCALARS];
+} psb_rk_stage_args;
+int psb_scalar_rk_stage(const psb_rk_stage_args* args, void* stream);
+
+/* ------------------------------------------------------------------------
  * Tensor-perturbation (gravitational-wave) sector stage, element-wise:
  * TensorPerturbationSector.rhs_dict (pystella/sectors.py:187-204) with the
  * trace-dropped scalar stress tensor (sectors.py:146-152) advanced by one

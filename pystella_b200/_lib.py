@@ -52,6 +52,21 @@ class ScalarStageArgs(C.Structure):
     ]
 
 
+class RKStageArgs(C.Structure):
+    _fields_ = [("dtype", c_int32), ("nscalars", c_int32), ("h", c_int32),
+                ("ncopies", c_int32),
+                ("Nx", c_int64), ("Ny", c_int64), ("Nz", c_int64),
+                ("f", c_void_p), ("dfdt", c_void_p), ("lap_f", c_void_p),
+                ("q_read", c_int32), ("nstatements", c_int32),
+                ("dst", c_int32 * 2), ("ncomb", c_int32 * 2),
+                ("src", (c_int32 * 2) * 2), ("coef", (c_double * 2) * 2),
+                ("dt_coef", c_double * 2),
+                ("dt", c_double), ("a", c_double), ("hubble", c_double),
+                ("nterms", c_int32 * MAX_SCALARS),
+                ("pcoef", (c_double * MAX_TERMS) * MAX_SCALARS),
+                ("power", ((C.c_int8 * MAX_SCALARS) * MAX_TERMS) * MAX_SCALARS)]
+
+
 class TensorStageArgs(C.Structure):
     _fields_ = [("dtype", c_int32), ("nscalars", c_int32), ("h", c_int32),
                 ("reserved", c_int32),
@@ -90,6 +105,7 @@ SYMBOLS = {
     "psb_strict_fp": (c_int, []),
     "psb_scalar_stage_fused": (c_int, [C.POINTER(ScalarStageArgs), c_void_p]),
     "psb_scalar_stage_unfused": (c_int, [C.POINTER(ScalarStageArgs), c_void_p]),
+    "psb_scalar_rk_stage": (c_int, [C.POINTER(RKStageArgs), c_void_p]),
     "psb_tensor_stage_unfused": (c_int, [C.POINTER(TensorStageArgs), c_void_p]),
     "psb_finite_difference": (c_int, [c_void_p] * 5 + [c_int, c_int64, c_int64, c_int64,
                                                         c_int, c_int,

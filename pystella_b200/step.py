@@ -680,8 +680,9 @@ class RungeKuttaStepper(Stepper):
     Subclasses provide :meth:`step_statements`: ``{copy: [(coef, src_copy), ...],
     rhs_coef}`` per stage.
 
-    Host NumPy arrays only in this build (the reference exercises these on its C
-    target, ``test/test_step.py:42-99``); device runs use the low-storage family.
+    Host NumPy arrays (scalar ODEs, as the reference's own test exercises them on its C
+    target, ``test/test_step.py:42-99``) or, for the scalar-sector / wave-equation menu,
+    device arrays with the copies axis first through ``psb_scalar_rk_stage``.
     """
 
     def step_statements(self, stage):
@@ -693,9 +694,7 @@ class RungeKuttaStepper(Stepper):
             raise IndexError(f"stage {stage} out of range for {type(self).__name__}")
         kwargs.pop("filter_args", None)
         if self._on_device(kwargs):
-            raise NotImplementedError(
-                f"{type(self).__name__} on device arrays: classical RK with storage "
-                "copies is host-only in this build; use a LowStorageRK* stepper")
+            return self._device_rk_stage(stage, queue, kwargs)
         ctx = dict(kwargs)
         if self.dt is not None:
             ctx["dt"] = self.dt
@@ -716,6 +715,68 @@ class RungeKuttaStepper(Stepper):
             for dst, val in new.items():
                 arr[(dst,) + sub] = val
         return None
+
+
+def _device_rk_stage(self, stage, queue, kwargs):
+    """Element-wise device stage for the scalar-sector menu (``psb_scalar_rk_stage``):
+    arrays carry the copies axis first, ``lap_f`` is computed by the caller from
+    copy ``q = 0 if stage == 0 else 1`` (pystella/step.py:181-187, 231)."""
+    import ctypes as C
+    from pystella_b200 import _lib
+    if self.fused:
+        raise NotImplementedError("FusedStencilStage with classical RK: use LowStorageRK*")
+    if len(self.systems) != 1 or hasattr(self.systems[0], "run_stage"):
+        raise NotImplementedError("device classical RK: a single scalar system")
+    system = self.systems[0]
+    dt = self._resolve_dt(kwargs)
+    f, dfdt = kwargs[system.f_name], kwargs[system.dot_name]
+    lap = kwargs.get(system.lap_name)
+    if lap is None:
+        raise TypeError(f"missing array argument '{system.lap_name}'")
+    h = self.halo_shape
+    if h is None:
+        raise ValueError("pass halo_shape= when constructing a device stepper")
+    n = system.nscalars
+    want = 5 if system.has_outer_axis else 4
+    if f.dim() != want or f.shape[0] != self.num_copies or dfdt.shape != f.shape:
+        raise ValueError(f"f / dfdt must have shape ({self.num_copies}, "
+                         f"{'n, ' if system.has_outer_axis else ''}Nx+2h, Ny+2h, Nz+2h)")
+    for name, t in ((system.f_name, f), (system.dot_name, dfdt), (system.lap_name, lap)):
+        _lib.require_cuda_tensor(t, name)
+    scal, dV = self._scalars(system, kwargs)
+    if scal["a"][1] is not None or scal["hubble"][1] is not None:
+        raise NotImplementedError("device scalars with classical RK")
+    Nx, Ny, Nz = (x - 2 * h for x in f.shape[-3:])
+    args = _lib.RKStageArgs()
+    args.dtype = _lib.torch_dtype_code(f)
+    args.nscalars, args.h, args.ncopies = n, h, self.num_copies
+    args.Nx, args.Ny, args.Nz = Nx, Ny, Nz
+    args.f, args.dfdt, args.lap_f = f.data_ptr(), dfdt.data_ptr(), lap.data_ptr()
+    args.q_read = 0 if stage == 0 else 1
+    stmts = self.step_statements(stage)
+    args.nstatements = len(stmts)
+    for s, (dst, combo, c_dt) in enumerate(stmts):
+        args.dst[s] = dst
+        args.ncomb[s] = len(combo)
+        args.dt_coef[s] = c_dt
+        for m, (c, src) in enumerate(combo):
+            args.coef[s][m] = c
+            args.src[s][m] = src
+    args.dt, args.a, args.hubble = dt, scal["a"][0], scal["hubble"][0]
+    for i in range(n):
+        args.nterms[i] = len(dV[i])
+        for t, (c, powers) in enumerate(dV[i]):
+            args.pcoef[i][t] = float(c)
+            for m in range(n):
+                args.power[i][t][m] = int(powers[m])
+    lib = _lib.load(self.strict_fp)
+    rc = lib.psb_scalar_rk_stage(C.byref(args), _lib.stream_ptr(queue))
+    _lib.check(lib, rc, "psb_scalar_rk_stage")
+    return None
+
+
+RungeKuttaStepper._device_rk_stage = _device_rk_stage
+RungeKuttaStepper._scalars = LowStorageRKStepper._scalars
 
 
 class RungeKutta4(RungeKuttaStepper):

@@ -516,3 +516,47 @@ def test_two_scalars_plus_gw_sector(fused_scalars, dtype, tol):
         for c in range(ref.shape[0]):
             assert scale_err(O.interior(got[c].cpu().numpy(), h),
                              O.interior(ref[c], h)) < tol
+
+
+@pytest.mark.parametrize("name", ["RungeKutta4", "RungeKutta3SSP", "RungeKutta2Midpoint"])
+def test_classical_rk_wave_equation_device(name):
+    """
+    BASELINE config 1 wording: wave equation, RK4 + 2nd-order Laplacian (h = 1), 64^3.
+    Classical RK with storage copies on device arrays vs the oracle's rk_stage.
+    """
+    rng = np.random.default_rng(12321)
+    N, h = ((64, 64, 64) if name == "RungeKutta4" else (24, 24, 24)), 1
+    dx = tuple(10 / n for n in N)
+    dt = min(dx) / 10
+    pad = tuple(n + 2 * h for n in N)
+    Stepper = getattr(ps, name)
+    nc = Stepper.num_copies
+    fq = np.zeros((nc,) + pad); dq = np.zeros((nc,) + pad)
+    fq[0], dq[0] = rng.random(pad), rng.random(pad)
+    f0, d0 = fq.copy(), dq.copy()
+
+    nsteps = 3
+    for _ in range(nsteps):
+        for s in range(Stepper.num_stages):
+            q = O.rk_rhs_copy(s)
+            O.share_halos(fq[q], h)
+            lap = O.laplacian(fq[q], h, dx)
+            rhs_f = np.array(O.interior(dq[q], h))
+            fi = fq[(slice(None),) + (slice(h, -h),) * 3]
+            di = dq[(slice(None),) + (slice(h, -h),) * 3]
+            O.rk_stage(name, s, dt, fi, rhs_f)
+            O.rk_stage(name, s, dt, di, lap)
+
+    decomp = ps.DomainDecomposition((1, 1, 1), h, N)
+    derivs = ps.FiniteDifferencer(decomp, h, dx)
+    f_ = ps.DynamicField("f", offset="h")
+    stepper = Stepper({f_: f_.dot, f_.dot: f_.lap}, dt=dt, halo_shape=h)
+    f, dfdt = to_dev(f0), to_dev(d0)
+    lap_f = torch.zeros(N, dtype=torch.float64, device="cuda")
+    for _ in range(nsteps):
+        for s in range(stepper.num_stages):
+            q = 0 if s == 0 else 1
+            derivs(None, fx=f[q], lap=lap_f)
+            stepper(s, queue=None, f=f, dfdt=dfdt, lap_f=lap_f)
+    for got, ref in ((f, fq), (dfdt, dq)):
+        assert scale_err(O.interior(got[0].cpu().numpy(), h), O.interior(ref[0], h)) < 1e-13
