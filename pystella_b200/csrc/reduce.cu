@@ -35,59 +35,61 @@ __device__ __forceinline__ double red_combine(int op, double a, double b) {
   return op == 0 ? a + b : (op == 1 ? fmax(a, b) : fmin(a, b));
 }
 
-template <typename T>
+// NARR / NOUT are compile-time bounds (rounded up by the host dispatch) so that the
+// per-site loops are short and fully unrolled; term ranges and powers stay runtime
+// (uniform, read from the kernel parameter space).
+template <typename T, int NARR, int NOUT>
 __global__ void __launch_bounds__(RED_THREADS)
     reduce_kernel(const __grid_constant__ RedParams<T> p) {
-  double acc[PSB_MAX_RED_OUTPUTS];
+  double acc[NOUT];
 #pragma unroll
-  for (int r = 0; r < PSB_MAX_RED_OUTPUTS; ++r)
-    acc[r] = red_identity(r < p.noutputs ? p.op[r] : 0);
+  for (int r = 0; r < NOUT; ++r) acc[r] = red_identity(r < p.noutputs ? p.op[r] : 0);
 
   const int64_t rows = (int64_t)p.Nx * p.Ny;
   const int lane_z = threadIdx.x % 64, sub = threadIdx.x / 64;
   for (int64_t row = (int64_t)blockIdx.x * 4 + sub; row < rows;
        row += (int64_t)gridDim.x * 4) {
     const int i = (int)(row / p.Ny), j = (int)(row % p.Ny);
-    const T* rp[PSB_MAX_RED_ARRAYS];
+    const T* rp[NARR];
 #pragma unroll
-    for (int m = 0; m < PSB_MAX_RED_ARRAYS; ++m) {
-      if (m < p.narrays) {
-        const int h = p.halo[m];
-        rp[m] = p.arrays[m] +
-                ((int64_t)(i + h) * (p.Ny + 2 * h) + (j + h)) * (p.Nz + 2 * h) + h;
-      } else {
-        rp[m] = nullptr;
-      }
+    for (int m = 0; m < NARR; ++m) {
+      const int h = p.halo[m];
+      rp[m] = (m < p.narrays)
+                  ? p.arrays[m] + ((int64_t)(i + h) * (p.Ny + 2 * h) + (j + h)) *
+                                          (p.Nz + 2 * h) + h
+                  : p.arrays[0];
     }
     for (int k = lane_z; k < p.Nz; k += 64) {
-      double v[PSB_MAX_RED_ARRAYS];
+      double v[NARR];
 #pragma unroll
-      for (int m = 0; m < PSB_MAX_RED_ARRAYS; ++m)
-        v[m] = (m < p.narrays) ? (double)rp[m][k] : 0.0;
+      for (int m = 0; m < NARR; ++m) v[m] = (double)__ldg(rp[m] + k);
 #pragma unroll
-      for (int r = 0; r < PSB_MAX_RED_OUTPUTS; ++r) {
+      for (int r = 0; r < NOUT; ++r) {
         if (r < p.noutputs) {
           double val = 0.0;
           for (int t = p.term_begin[r]; t < p.term_begin[r + 1]; ++t) {
             double term = p.coef[t];
 #pragma unroll
-            for (int m = 0; m < PSB_MAX_RED_ARRAYS; ++m) {
-              if (m < p.narrays)
-                for (int e = 0; e < p.power[t][m]; ++e) term *= v[m];
+            for (int m = 0; m < NARR; ++m) {
+              const int pw = p.power[t][m];
+              if (pw >= 1) term *= v[m];
+              if (pw >= 2) term *= v[m];
+              for (int e = 2; e < pw; ++e) term *= v[m];
             }
             val += term;
           }
           if (p.flags[r] & 1) val = fabs(val);
-          acc[r] = red_combine(p.op[r], acc[r], val);
+          const int op = p.op[r];
+          acc[r] = op == 0 ? acc[r] + val : red_combine(op, acc[r], val);
         }
       }
     }
   }
 
-  __shared__ double sh[RED_THREADS / 32][PSB_MAX_RED_OUTPUTS];
+  __shared__ double sh[RED_THREADS / 32][NOUT];
   const int lane = threadIdx.x % 32, warp = threadIdx.x / 32;
 #pragma unroll
-  for (int r = 0; r < PSB_MAX_RED_OUTPUTS; ++r) {
+  for (int r = 0; r < NOUT; ++r) {
     if (r < p.noutputs) {
       double x = acc[r];
       const int op = p.op[r];
@@ -104,6 +106,34 @@ __global__ void __launch_bounds__(RED_THREADS)
     for (int w = 1; w < RED_THREADS / 32; ++w) x = red_combine(op, x, sh[w][r]);
     p.partials[(int64_t)blockIdx.x * PSB_MAX_RED_OUTPUTS + r] = x;
   }
+}
+
+template <typename T, int NARR>
+static void launch_reduce_nout(const RedParams<T>& p, int nblocks, cudaStream_t s) {
+  if (p.noutputs <= 2)
+    reduce_kernel<T, NARR, 2><<<nblocks, RED_THREADS, 0, s>>>(p);
+  else if (p.noutputs <= 4)
+    reduce_kernel<T, NARR, 4><<<nblocks, RED_THREADS, 0, s>>>(p);
+  else if (p.noutputs <= 8)
+    reduce_kernel<T, NARR, 8><<<nblocks, RED_THREADS, 0, s>>>(p);
+  else
+    reduce_kernel<T, NARR, PSB_MAX_RED_OUTPUTS><<<nblocks, RED_THREADS, 0, s>>>(p);
+}
+
+template <typename T>
+static void launch_reduce(const RedParams<T>& p, int nblocks, cudaStream_t s) {
+  if (p.narrays <= 1)
+    launch_reduce_nout<T, 1>(p, nblocks, s);
+  else if (p.narrays <= 2)
+    launch_reduce_nout<T, 2>(p, nblocks, s);
+  else if (p.narrays <= 3)
+    launch_reduce_nout<T, 3>(p, nblocks, s);
+  else if (p.narrays <= 4)
+    launch_reduce_nout<T, 4>(p, nblocks, s);
+  else if (p.narrays <= 6)
+    launch_reduce_nout<T, 6>(p, nblocks, s);
+  else
+    launch_reduce_nout<T, PSB_MAX_RED_ARRAYS>(p, nblocks, s);
 }
 
 struct FinalizeParams {
@@ -169,9 +199,9 @@ static int reduce_typed(const psb_reduce_args* a, cudaStream_t s) {
 
   const int64_t rows = a->Nx * a->Ny;
   int nblocks = (int)((rows + 3) / 4);
-  const int cap = num_sms() * 4 < RED_MAX_BLOCKS ? num_sms() * 4 : RED_MAX_BLOCKS;
+  const int cap = num_sms() * 6 < RED_MAX_BLOCKS ? num_sms() * 6 : RED_MAX_BLOCKS;
   if (nblocks > cap) nblocks = cap;
-  reduce_kernel<T><<<nblocks, RED_THREADS, 0, s>>>(p);
+  launch_reduce<T>(p, nblocks, s);
   PSB_CHECK_CUDA(cudaGetLastError());
 
   FinalizeParams f;
