@@ -29,6 +29,7 @@ __global__ void __launch_bounds__(BY* BZ)
   __shared__ T tile[2][ROWS][W];
 
   const int tz = threadIdx.x, ty = threadIdx.y;
+  const int tid = ty * BZ + tz;
   const int z0 = blockIdx.x * BZ, y0 = blockIdx.y * BY;
   const int xs = blockIdx.z * p.xchunk;
   const int xe = min(xs + p.xchunk, p.Nx);
@@ -53,22 +54,14 @@ __global__ void __launch_bounds__(BY* BZ)
     q[2 * H] = col[(int64_t)(i + g + H) * plane];
 
     const int b = i & 1;
-    // stage the centre plane (with y/z halos) in shared memory: thread (ty, tz)
-    // covers rows ty, ty + BY and columns tz, tz + BZ of the (ROWS x W) tile
+    // stage the centre plane (with y/z halos) in shared memory
     const T* src = p.fx + (int64_t)(i + g) * plane;
-#pragma unroll
-    for (int rr = 0; rr < (ROWS + BY - 1) / BY; ++rr) {
-      const int r = ty + rr * BY;
-#pragma unroll
-      for (int cc = 0; cc < (W + BZ - 1) / BZ; ++cc) {
-        const int c = tz + cc * BZ;
-        if (r < ROWS && c < W) {
-          const int gy = y0 + r + g - H, gz = z0 + c + g - H;
-          T val = (T)0;
-          if (gy < Py && gz < Pz) val = src[(int64_t)gy * Pz + gz];
-          tile[b][r][c] = val;
-        }
-      }
+    for (int e = tid; e < ROWS * W; e += BY * BZ) {
+      const int r = e / W, c = e % W;
+      const int gy = y0 + r + g - H, gz = z0 + c + g - H;
+      T val = (T)0;
+      if (gy < Py && gz < Pz) val = src[(int64_t)gy * Pz + gz];
+      tile[b][r][c] = val;
     }
     __syncthreads();
 
