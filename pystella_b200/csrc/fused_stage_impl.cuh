@@ -577,13 +577,13 @@ static int fused_op(const psb_scalar_stage_args* a, cudaStream_t stream, int64_t
   return launch_fused<T, H, NF, VEC, BY, TZ, P, MINB>(a, stream);
 }
 
-template <typename T, int H, int NF, int BY, int TZ, int P, int MINB>
+template <typename T, int H, int NF, int BY, int TZ, int P, int MINB, int VEC = 2>
 static int ws_op(const psb_scalar_stage_args* a, cudaStream_t stream, int64_t* count) {
   if (count) {
-    *count = ws_grid_blocks<T, H, NF, BY, TZ, P>(a);
+    *count = ws_grid_blocks<T, H, NF, BY, TZ, P, VEC>(a);
     return 0;
   }
-  return launch_ws<T, H, NF, BY, TZ, P, MINB>(a, stream);
+  return launch_ws<T, H, NF, BY, TZ, P, MINB, VEC>(a, stream);
 }
 
 // can TMA describe all four arrays?  (mirrors encode_field_tensor_map's checks)
@@ -624,6 +624,14 @@ static int dispatch_vec(const psb_scalar_stage_args* a, cudaStream_t stream,
         if (var == 14) return ws_op<T, H, NF, 2, 64, 3, 3>(a, stream, count);
         return ws_op<T, H, NF, 4, 64, 3, 2>(a, stream, count);
       } else {
+        if constexpr (std::is_same<T, float>::value) {
+          // fp32: 4 sites per thread (16-byte shared-memory vectors) when rows allow
+          constexpr int TZ4 = ws_pick_tz(ES, H, NF, 4, 2, 4);
+          if constexpr (TZ4 > 0) {
+            if (a->Nz % 4 == 0 && var != 15)
+              return ws_op<T, H, NF, 4, TZ4, 2, 1, 4>(a, stream, count);
+          }
+        }
         constexpr int TZW = ws_pick_tz(ES, H, NF, 4, 2);
         if constexpr (TZW > 0) return ws_op<T, H, NF, 4, TZW, 2, 1>(a, stream, count);
       }

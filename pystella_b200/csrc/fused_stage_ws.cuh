@@ -20,10 +20,19 @@
 
 namespace psb {
 
-template <typename T, int H, int NF, int BY, int TZ, int P> struct WsCfg {
-  static constexpr int VEC = 2;
+constexpr int ws_gcd(int a, int b) { return b == 0 ? a : ws_gcd(b, a % b); }
+
+// VEC z-sites per thread (one 16-byte shared-memory vector: 2 doubles or 4 floats).
+// GV = elements per global / pointwise access piece: the interior starts H elements
+// into a row, so only gcd(VEC, H) consecutive elements are guaranteed aligned
+// (fp32, h = 2: 16-byte LDS of the f tile, 8-byte pieces for everything else).
+template <typename T, int H, int NF, int BY, int TZ, int P, int VEC_ = 2> struct WsCfg {
+  static constexpr int VEC = VEC_;
+  static constexpr int GV = ws_gcd(VEC_, H);
   static constexpr int BZ = TZ * VEC;
-  static constexpr int HL = ((H + VEC - 1) / VEC) * VEC;
+  // left pad of the f tile: the TMA box must start 16-byte aligned in global memory,
+  // i.e. at padded column z0 = z0 + H - HL with HL = H rounded up to GV elements
+  static constexpr int HL = ((H + GV - 1) / GV) * GV;
   static constexpr int WQ = 16 / (int)sizeof(T);
   static constexpr int W = ((BZ + 2 * HL + WQ - 1) / WQ) * WQ;
   static constexpr int ROWS = BY + 2 * H;
@@ -49,9 +58,10 @@ constexpr int SMEM_LIMIT = 200 * 1024;
 // in re-read prologue planes (measured at 512^3: 16 > 32 > 64 > 128)
 constexpr int WS_DEFAULT_XCHUNK = 16;
 
-constexpr int ws_smem_bytes(int es, int H, int NF, int BY, int TZ, int P) {
-  const int BZ = TZ * 2;
-  const int HL = ((H + 1) / 2) * 2;
+constexpr int ws_smem_bytes(int es, int H, int NF, int BY, int TZ, int P, int VEC = 2) {
+  const int BZ = TZ * VEC;
+  const int GV = ws_gcd(VEC, H);
+  const int HL = ((H + GV - 1) / GV) * GV;
   const int WQ = 16 / es;
   const int W = ((BZ + 2 * HL + WQ - 1) / WQ) * WQ;
   const int fplane = (((BY + 2 * H) * W * es + 127) / 128) * 128;
@@ -61,25 +71,52 @@ constexpr int ws_smem_bytes(int es, int H, int NF, int BY, int TZ, int P) {
          128;
 }
 // widest z tile (64, 32 or 16 threads of 2 sites) whose rings fit; 0 = none
-constexpr int ws_pick_tz(int es, int H, int NF, int BY, int P) {
-  for (int tz = 64; tz >= 16; tz /= 2)
-    if (ws_smem_bytes(es, H, NF, BY, tz, P) <= SMEM_LIMIT) return tz;
+constexpr int ws_pick_tz(int es, int H, int NF, int BY, int P, int VEC = 2) {
+  for (int tz = 128 / VEC; tz >= 16; tz /= 2)
+    if (ws_smem_bytes(es, H, NF, BY, tz, P, VEC) <= SMEM_LIMIT) return tz;
   return 0;
+}
+
+// VEC elements moved as VEC/GV aligned pieces
+template <typename T, int VEC, int GV>
+__device__ __forceinline__ Vec<T, VEC> ld_pieces(const T* p) {
+  Vec<T, VEC> r;
+#pragma unroll
+  for (int g = 0; g < VEC / GV; ++g) {
+    Vec<T, GV> t = ld_vec<T, GV>(p + g * GV);
+#pragma unroll
+    for (int v = 0; v < GV; ++v) r.v[g * GV + v] = t.v[v];
+  }
+  return r;
+}
+template <typename T, int VEC, int GV, bool STREAM>
+__device__ __forceinline__ void st_pieces(T* p, const Vec<T, VEC>& x) {
+#pragma unroll
+  for (int g = 0; g < VEC / GV; ++g) {
+    Vec<T, GV> t;
+#pragma unroll
+    for (int v = 0; v < GV; ++v) t.v[v] = x.v[g * GV + v];
+    if constexpr (STREAM)
+      st_stream<T, GV>(p + g * GV, t);
+    else
+      st_plain<T, GV>(p + g * GV, t);
+  }
 }
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-template <typename T, int H, int NF, int BY, int TZ, int P, bool ENERGY, int MINB>
+template <typename T, int H, int NF, int BY, int TZ, int P, bool ENERGY, int MINB,
+          int VEC_ = 2>
 __global__ void __launch_bounds__(BY* TZ + 32, MINB)
     fused_stage_ws_kernel(const __grid_constant__ FusedParams<T, NF> p,
                           const __grid_constant__ CUtensorMap map_f,
                           const __grid_constant__ CUtensorMap map_d,
                           const __grid_constant__ CUtensorMap map_kf,
                           const __grid_constant__ CUtensorMap map_kd) {
-  using C = WsCfg<T, H, NF, BY, TZ, P>;
-  constexpr int VEC = C::VEC, W = C::W, HL = C::HL, RF = C::RF, RP = C::RP;
+  using C = WsCfg<T, H, NF, BY, TZ, P, VEC_>;
+  constexpr int VEC = C::VEC, GV = C::GV, W = C::W, HL = C::HL, RF = C::RF, RP = C::RP;
   using V = Vec<T, VEC>;
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -206,7 +243,7 @@ __global__ void __launch_bounds__(BY* TZ + 32, MINB)
     for (int f = 0; f < NF; ++f) {
 #pragma unroll
       for (int s = 0; s < 2 * H; ++s) q[f][s] = q[f][s + 1];
-      q[f][2 * H] = ld_vec<T, VEC>(
+      q[f][2 * H] = ld_pieces<T, VEC, GV>(
           reinterpret_cast<const T*>(fring + (slot * NF + f) * C::FPLANE) + own_off);
     }
 
@@ -221,31 +258,31 @@ __global__ void __launch_bounds__(BY* TZ + 32, MINB)
         V lap[NF], dold[NF], kfo[NF], kdo[NF];
 #pragma unroll
         for (int f = 0; f < NF; ++f) {
-          dold[f] = ld_vec<T, VEC>(
+          dold[f] = ld_pieces<T, VEC, GV>(
               reinterpret_cast<const T*>(pw + (0 * NF + f) * C::PWTILE) + pw_off);
           if (read_k) {
-            kfo[f] = ld_vec<T, VEC>(
+            kfo[f] = ld_pieces<T, VEC, GV>(
                 reinterpret_cast<const T*>(pw + (1 * NF + f) * C::PWTILE) + pw_off);
-            kdo[f] = ld_vec<T, VEC>(
+            kdo[f] = ld_pieces<T, VEC, GV>(
                 reinterpret_cast<const T*>(pw + (2 * NF + f) * C::PWTILE) + pw_off);
           } else {
 #pragma unroll
             for (int v = 0; v < VEC; ++v) kfo[f].v[v] = kdo[f].v[v] = (T)0;
           }
           const T* pl = reinterpret_cast<const T*>(fring + (cslot * NF + f) * C::FPLANE);
-          constexpr int NVZ = 1 + 2 * (HL / VEC);
-          T zrow[NVZ * VEC];
+          constexpr int NVZ = (VEC + 2 * HL) / GV;  // aligned pieces covering the row
+          T zrow[NVZ * GV];
 #pragma unroll
           for (int w = 0; w < NVZ; ++w) {
-            V t = ld_vec<T, VEC>(pl + own_off - HL + w * VEC);
+            Vec<T, GV> t = ld_vec<T, GV>(pl + own_off - HL + w * GV);
 #pragma unroll
-            for (int v = 0; v < VEC; ++v) zrow[w * VEC + v] = t.v[v];
+            for (int v = 0; v < GV; ++v) zrow[w * GV + v] = t.v[v];
           }
           V yn[2 * H + 1];
 #pragma unroll
           for (int s = 1; s <= H; ++s) {
-            yn[H + s] = ld_vec<T, VEC>(pl + own_off + s * W);
-            yn[H - s] = ld_vec<T, VEC>(pl + own_off - s * W);
+            yn[H + s] = ld_pieces<T, VEC, GV>(pl + own_off + s * W);
+            yn[H - s] = ld_pieces<T, VEC, GV>(pl + own_off - s * W);
           }
 #pragma unroll
           for (int v = 0; v < VEC; ++v) {
@@ -321,29 +358,29 @@ __global__ void __launch_bounds__(BY* TZ + 32, MINB)
             dn.v[v] = d_old + p.B * kdv;
           }
           const int64_t fo_off = f * p.field_stride;
-          st_stream<T, VEC>(o_kf + fo_off, kfn);
-          st_stream<T, VEC>(o_kd + fo_off, kdn);
-          st_stream<T, VEC>(o_d + fo_off, dn);
+          st_pieces<T, VEC, GV, true>(o_kf + fo_off, kfn);
+          st_pieces<T, VEC, GV, true>(o_kd + fo_off, kdn);
+          st_pieces<T, VEC, GV, true>(o_d + fo_off, dn);
           T* fout = o_f + fo_off;
-          st_plain<T, VEC>(fout, fo);
+          st_pieces<T, VEC, GV, false>(fout, fo);
           if (p.wrap_x) {
-            if (i < H) st_plain<T, VEC>(fout + (int64_t)p.Nx * plane_stride, fo);
-            if (i >= p.Nx - H) st_plain<T, VEC>(fout - (int64_t)p.Nx * plane_stride, fo);
+            if (i < H) st_pieces<T, VEC, GV, false>(fout + (int64_t)p.Nx * plane_stride, fo);
+            if (i >= p.Nx - H) st_pieces<T, VEC, GV, false>(fout - (int64_t)p.Nx * plane_stride, fo);
           }
           // NVLink: my boundary planes -> the neighbours' x halos (peer memory)
           if (p.peer_lo != nullptr && i < H)
-            st_plain<T, VEC>(p.peer_lo + f * p.peer_lo_stride +
+            st_pieces<T, VEC, GV, false>(p.peer_lo + f * p.peer_lo_stride +
                                  (int64_t)(p.peer_lo_Nx + H + i) * plane_stride +
                                  (int64_t)(j + H) * Pz + (k + H),
                              fo);
           if (p.peer_hi != nullptr && i >= p.Nx - H)
-            st_plain<T, VEC>(p.peer_hi + f * p.peer_hi_stride +
+            st_pieces<T, VEC, GV, false>(p.peer_hi + f * p.peer_hi_stride +
                                  (int64_t)(i - p.Nx + H) * plane_stride +
                                  (int64_t)(j + H) * Pz + (k + H),
                              fo);
           if (p.wrap_y) {
-            if (j < H) st_plain<T, VEC>(fout + (int64_t)p.Ny * Pz, fo);
-            if (j >= p.Ny - H) st_plain<T, VEC>(fout - (int64_t)p.Ny * Pz, fo);
+            if (j < H) st_pieces<T, VEC, GV, false>(fout + (int64_t)p.Ny * Pz, fo);
+            if (j >= p.Ny - H) st_pieces<T, VEC, GV, false>(fout - (int64_t)p.Ny * Pz, fo);
           }
           if (p.wrap_z) {
 #pragma unroll
@@ -404,17 +441,17 @@ __global__ void __launch_bounds__(BY* TZ + 32, MINB)
 // host side
 // ---------------------------------------------------------------------------
 
-template <typename T, int H, int NF, int BY, int TZ, int P>
+template <typename T, int H, int NF, int BY, int TZ, int P, int VEC = 2>
 static int64_t ws_grid_blocks(const psb_scalar_stage_args* a) {
-  using C = WsCfg<T, H, NF, BY, TZ, P>;
+  using C = WsCfg<T, H, NF, BY, TZ, P, VEC>;
   const XLayout L = x_layout(a, WS_DEFAULT_XCHUNK);
   return ((a->Nz + C::BZ - 1) / C::BZ) * ((a->Ny + BY - 1) / BY) * (int64_t)(L.n1 + L.n2);
 }
 
 // returns 0 ok, >0 error, -1 = layout not TMA-able (caller falls back)
-template <typename T, int H, int NF, int BY, int TZ, int P, int MINB>
+template <typename T, int H, int NF, int BY, int TZ, int P, int MINB, int VEC = 2>
 static int launch_ws(const psb_scalar_stage_args* a, cudaStream_t stream) {
-  using C = WsCfg<T, H, NF, BY, TZ, P>;
+  using C = WsCfg<T, H, NF, BY, TZ, P, VEC>;
   const int64_t Px = a->Nx + 2 * H, Py = a->Ny + 2 * H, Pz = a->Nz + 2 * H;
   CUtensorMap mf, md, mkf, mkd;
   if (encode_field_tensor_map(&mf, a->dtype, a->f_in, NF, a->field_stride, Px, Py, Pz, 1,
@@ -437,12 +474,12 @@ static int launch_ws(const psb_scalar_stage_args* a, cudaStream_t stream) {
             (unsigned)(L.n1 + L.n2));
   dim3 block(C::THREADS, 1, 1);
   if (a->energy_partials != nullptr) {
-    auto kern = fused_stage_ws_kernel<T, H, NF, BY, TZ, P, true, MINB>;
+    auto kern = fused_stage_ws_kernel<T, H, NF, BY, TZ, P, true, MINB, VEC>;
     PSB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         C::SMEM_BYTES));
     kern<<<grid, block, C::SMEM_BYTES, stream>>>(p, mf, md, mkf, mkd);
   } else {
-    auto kern = fused_stage_ws_kernel<T, H, NF, BY, TZ, P, false, MINB>;
+    auto kern = fused_stage_ws_kernel<T, H, NF, BY, TZ, P, false, MINB, VEC>;
     PSB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         C::SMEM_BYTES));
     kern<<<grid, block, C::SMEM_BYTES, stream>>>(p, mf, md, mkf, mkd);
