@@ -301,8 +301,7 @@ def run_b200_arm(args):
         for s in range(NUM_STAGES):
             stepper(s, f=f, dfdt=dfdt, a=expand.a, hubble=expand.hubble)
             expand.step(s, stepper, dt)
-    n_stage_launches = 1 if world == 1 else 2
-    launches_per_step[0] = NUM_STAGES * (n_stage_launches + 2)
+    launches_per_step[0] = NUM_STAGES * 3
 
     def barrier():
         if world > 1:
@@ -312,6 +311,10 @@ def run_b200_arm(args):
     for _ in range(max(args.warmup, 3)):
         one_step()
     barrier()
+    # launches per stage: stage kernel(s) + energy fold + expansion; the NCCL fallback
+    # splits the stage into boundary + interior launches
+    halo_mode = getattr(stepper, "_halo_mode", "local")
+    launches_per_step[0] = NUM_STAGES * ((2 if halo_mode == "nccl" else 1) + 2)
 
     graph = None
     if not args.no_graph:
@@ -449,6 +452,10 @@ def run_b200_arm(args):
                             f"{'x'.join(str(n) for n in w['grid_shape'])} {args.dtype}",
                 "grid_shape": list(w["grid_shape"]), "rank_shape": list(w["rank_shape"]),
                 "parallelism": f"x-slabs over {world} GPU(s)",
+                "halo_exchange": {"local": "periodic wrap written by the stage kernel",
+                                  "peer": "stage kernel stores boundary planes into the "
+                                          "neighbours' halos over NVLink (peer memory)",
+                                  "nccl": "NCCL send/recv on a side stream"}[halo_mode],
                 "l2": "inputs larger than L2 (4 field arrays of "
                       f"{local_sites * S / 1e6:.0f} MB each per GPU vs 126 MB L2)",
                 "launch": "CUDA graph (2 steps per replay)" if graph is not None
