@@ -1,0 +1,168 @@
+"""
+Preheating of scalar fields in an expanding FLRW background: the time loop of the
+reference's examples/scalar_preheating.py (sectors, stepper, derivatives, energy
+reduction, expansion) on pystella_b200.  Spectral pieces of the reference driver
+(Rayleigh initial conditions, power spectra, projectors, HDF5 output) are outside
+the hot path and not provided: fluctuations are white Gaussian noise here.
+
+    python examples/scalar_preheating.py -grid 64 64 64 --end-time 1            # 1 GPU
+    torchrun --nproc-per-node 4 examples/scalar_preheating.py -grid 256 256 256 -proc 4 1 1
+Options: --reference-loop (derivs + Reduction + host Expansion per stage, exactly the
+reference's loop) instead of the default device-resident loop; -gws adds the tensor sector.
+"""
+import argparse
+import os
+import sys
+from time import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import pystella_b200 as ps  # noqa: E402
+
+parser = argparse.ArgumentParser()
+parser.add_argument("--grid-shape", "-grid", type=int, nargs=3, default=(128, 128, 128))
+parser.add_argument("--proc-shape", "-proc", type=int, nargs=3, default=(1, 1, 1))
+parser.add_argument("--dtype", default="float64", choices=["float64", "float32"])
+parser.add_argument("--halo-shape", type=int, default=2, metavar="h")
+parser.add_argument("--box-dim", "-box", type=float, nargs=3, default=(5, 5, 5))
+parser.add_argument("--kappa", type=float, default=1/10)
+parser.add_argument("--mpl", type=float, default=1)
+parser.add_argument("--mphi", type=float, default=1.20e-6)
+parser.add_argument("--mchi", type=float, default=0.)
+parser.add_argument("--gsq", type=float, default=2.5e-7)
+parser.add_argument("--sigma", type=float, default=0.)
+parser.add_argument("--lambda4", type=float, default=0.)
+parser.add_argument("--end-time", "-end-t", type=float, default=20)
+parser.add_argument("--end-scale-factor", "-end-a", type=float, default=20)
+parser.add_argument("--gravitational-waves", "-gws", action="store_true")
+parser.add_argument("--reference-loop", action="store_true")
+
+
+def main():
+    p = parser.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    device = ps.choose_device()
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    p.grid_shape = tuple(p.grid_shape)
+    p.grid_size = float(np.prod(p.grid_shape))
+    p.proc_shape = tuple(p.proc_shape)
+    h = p.halo_shape
+    dtype = getattr(torch, p.dtype)
+    p.dx = tuple(Li / Ni for Li, Ni in zip(p.box_dim, p.grid_shape))
+    dt = p.kappa * min(p.dx)
+
+    nscalars = 2
+    f0 = [.193 * p.mpl, 0]
+    df0 = [-.142231 * p.mpl, 0]
+    Stepper = ps.LowStorageRK54
+
+    decomp = ps.DomainDecomposition(p.proc_shape, h, grid_shape=p.grid_shape)
+    rank_shape = decomp.rank_shape
+    pencil_shape = tuple(ni + 2 * h for ni in rank_shape)
+    derivs = ps.FiniteDifferencer(decomp, h, p.dx, rank_shape=rank_shape)
+
+    def potential(f):
+        phi, chi = f[0], f[1]
+        unscaled = (p.mphi**2 / 2 * phi**2 + p.mchi**2 / 2 * chi**2
+                    + p.gsq / 2 * phi**2 * chi**2 + p.sigma / 2 * phi * chi**2
+                    + p.lambda4 / 4 * chi**4)
+        return unscaled / p.mphi**2
+
+    scalar_sector = ps.ScalarSector(nscalars, potential=potential)
+    sectors = [scalar_sector]
+    if p.gravitational_waves:
+        sectors += [ps.TensorPerturbationSector([scalar_sector])]
+
+    device_loop = not (p.reference_loop or p.gravitational_waves)
+    slab = p.proc_shape[1] == 1
+    fused = dict(MapKernel=ps.FusedStencilStage, dx=p.dx, decomp=decomp) if slab else {}
+    stepper = Stepper(sectors, halo_shape=h, rank_shape=rank_shape, dt=dt,
+                      energy=device_loop, **fused)
+
+    reduce_energy = ps.Reduction(decomp, scalar_sector, halo_shape=h,
+                                 callback=ps.get_rho_and_p, rank_shape=rank_shape,
+                                 grid_size=p.grid_size)
+    statistics = ps.FieldStatistics(decomp, h, rank_shape=rank_shape,
+                                    grid_size=p.grid_size)
+
+    # fields: homogeneous background + small Gaussian fluctuations
+    gen = torch.Generator(device=device).manual_seed(49279 * (decomp.rank + 1))
+    f = torch.empty((nscalars,) + pencil_shape, dtype=dtype, device=device)
+    dfdt = torch.empty_like(f)
+    for i in range(nscalars):
+        f[i] = f0[i] + 1e-6 * torch.randn(pencil_shape, dtype=dtype, device=device,
+                                          generator=gen)
+        dfdt[i] = df0[i] + 1e-6 * torch.randn(pencil_shape, dtype=dtype, device=device,
+                                              generator=gen)
+    dfdx = torch.zeros((nscalars, 3) + rank_shape, dtype=dtype, device=device)
+    lap_f = torch.zeros((nscalars,) + rank_shape, dtype=dtype, device=device)
+    if p.gravitational_waves:
+        hij = torch.zeros((6,) + pencil_shape, dtype=dtype, device=device)
+        dhijdt = torch.zeros_like(hij)
+        lap_hij = torch.zeros((6,) + rank_shape, dtype=dtype, device=device)
+    else:
+        hij = dhijdt = lap_hij = None
+
+    def compute_energy(a):
+        if p.gravitational_waves:
+            derivs(None, fx=f, lap=lap_f, grd=dfdx)
+        else:
+            derivs(None, fx=f, lap=lap_f)
+        return reduce_energy(None, f=f, dfdt=dfdt, lap_f=lap_f, a=np.array(a))
+
+    energy = compute_energy(1.)
+    if device_loop:
+        expand = ps.DeviceExpansion(energy["total"], Stepper, mpl=p.mpl,
+                                    grid_size=p.grid_size, decomp=decomp, nscalars=nscalars)
+    else:
+        expand = ps.Expansion(energy["total"], Stepper, mpl=p.mpl)
+        if p.gravitational_waves:
+            derivs(None, fx=hij, lap=lap_hij)
+
+    t, step_count = 0., 0
+    if decomp.rank == 0:
+        print("time\t\tscale factor\tconstraint\tms/step")
+    start = time()
+    a_now = 1.
+    while t < p.end_time and a_now < p.end_scale_factor:
+        for s in range(stepper.num_stages):
+            if device_loop:
+                stepper(s, f=f, dfdt=dfdt, a=expand.a, hubble=expand.hubble)
+                expand.step(s, stepper, dt)
+            else:
+                stepper(s, queue=None, a=expand.a, hubble=expand.hubble, f=f, dfdt=dfdt,
+                        dfdx=dfdx, lap_f=lap_f, hij=hij, dhijdt=dhijdt, lap_hij=lap_hij,
+                        filter_args=True)
+                expand.step(s, energy["total"], energy["pressure"], dt)
+                energy = compute_energy(expand.a)
+                if p.gravitational_waves:
+                    derivs(None, fx=hij, lap=lap_hij)
+        t += dt
+        step_count += 1
+        if step_count % 16 == 0 or t >= p.end_time:
+            if device_loop:
+                rec = expand.get()
+                a_now, constraint = float(rec["a"]), float(expand.constraint())
+            else:
+                a_now = float(expand.a[0])
+                constraint = float(expand.constraint(energy["total"]))
+            if decomp.rank == 0:
+                ms = (time() - start) * 1e3 / step_count
+                print(f"{t:<15.3f}\t{a_now:<15.6f}\t{constraint:<.3e}\t{ms:<.3f}")
+
+    stats = statistics(f)
+    if decomp.rank == 0:
+        print("field means", stats["mean"], "variances", stats["variance"])
+        print("Simulation complete")
+    if world > 1:
+        dist.barrier()
+        os._exit(0)
+
+
+if __name__ == "__main__":
+    main()

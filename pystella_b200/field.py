@@ -463,22 +463,23 @@ def index_fields(expr, prepend_with=None):
         if isinstance(e, Subscript) and isinstance(e.aggregate, Field):
             fld = e.aggregate
             pre = () if fld.ignore_prepends else prepend_with
-            full = pre + tuple(e.index) + fld.index_tuple
-            return _index_child(fld, full)
+            return _index_child(fld, pre + tuple(e.index), fld.index_tuple)
         if isinstance(e, Field):
             pre = () if e.ignore_prepends else prepend_with
-            full = pre + e.index_tuple
-            return _index_child(e, full)
+            return _index_child(e, pre, e.index_tuple)
         return None
 
     return _map(expr, fn)
 
 
-def _index_child(fld, full):
+def _index_child(fld, outer, spatial):
+    # prepended + user subscripts, then the child's own subscript, then i, j, k
     child = fld.child
+    own = ()
     if isinstance(child, Subscript):
-        full = tuple(child.index) + full
+        own = tuple(child.index)
         child = child.aggregate
+    full = tuple(outer) + own + tuple(spatial)
     return Subscript(child, full) if full else child
 
 
@@ -606,9 +607,13 @@ def evaluate(e, context):
             return math.pi
         raise KeyError(f"no value supplied for '{e.name}'")
     if isinstance(e, Subscript):
-        val = evaluate(e.aggregate, context)
         idx = tuple(int(evaluate(i, context)) for i in e.index)
-        return val[idx]
+        agg = e.aggregate
+        if isinstance(agg, Field) and isinstance(agg.child, Subscript):
+            # user subscripts come before the Field's own (index_fields order)
+            own = tuple(int(evaluate(i, context)) for i in agg.child.index)
+            return context[agg.name][idx + own]
+        return evaluate(agg, context)[idx]
     if isinstance(e, Sum):
         it = iter(e.children)
         out = evaluate(next(it), context)
@@ -761,7 +766,7 @@ def to_polynomial(e, arrays_ok=True):
             if not arrays_ok:
                 raise NotImplementedError("array in scalar context")
             sub = agg.child.index if isinstance(agg.child, Subscript) else ()
-            ref = ArrayRef(agg.name, _const_index(tuple(sub) + tuple(e.index)),
+            ref = ArrayRef(agg.name, _const_index(tuple(e.index) + tuple(sub)),
                            agg.base_offset, _field_shift(agg), agg)
             return {((ref, 1),): 1}
         return {(): e}

@@ -463,7 +463,7 @@ class LowStorageRKStepper(Stepper):
         for key, r in zip(self.rhs_dict.keys(), rhs):
             fld, sub = _unknown_parts(key)
             if isinstance(fld.child, Subscript):
-                sub = tuple(int(i) for i in fld.child.index) + sub
+                sub = sub + tuple(int(i) for i in fld.child.index)
             u = kwargs[fld.name]
             k = self.tmp_arrays[gen_tmp_name(fld.name)]
             idx = sub if sub else Ellipsis

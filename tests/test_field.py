@@ -1,0 +1,149 @@
+"""
+The symbolic front-end: indexing, shifting, differentiation and argument
+inference follow test/test_field.py:30-242 of the reference (compared through the
+printed form / numeric evaluation, since expression trees are our own).
+"""
+import numpy as np
+import pytest
+
+import pystella_b200 as ps
+from pystella_b200.field import (evaluate, index_fields, parse, shift_fields,
+                                 to_polynomial, var)
+
+
+def same(a, b):
+    return str(a).replace(" ", "") == str(b).replace(" ", "")
+
+
+def test_field_indexing():
+    y = ps.Field("y", offset="h")
+    assert same(index_fields(y), "y[i+h,j+h,k+h]")
+    y = ps.Field("y", offset="h", indices=("a", "b", "c"))
+    assert same(index_fields(y), "y[a+h,b+h,c+h]")
+    y = ps.Field("y", ignore_prepends=True)
+    assert same(index_fields(y, prepend_with=(0, 1)), "y[i,j,k]")
+    y = ps.Field("y[4, 5]", ignore_prepends=True)
+    assert same(index_fields(y, prepend_with=(0, 1)), "y[4,5,i,j,k]")
+    y = ps.Field("y", ignore_prepends=True)
+    assert same(index_fields(y[2, 3], prepend_with=(0, 1)), "y[2,3,i,j,k]")
+    y = ps.Field("y[4, 5]", ignore_prepends=True)
+    assert same(index_fields(y[2, 3], prepend_with=(0, 1)), "y[2,3,4,5,i,j,k]")
+    y = ps.Field("y", ignore_prepends=False)
+    assert same(index_fields(y, prepend_with=(0, 1)), "y[0,1,i,j,k]")
+    y = ps.Field("y[4, 5]", ignore_prepends=False)
+    assert same(index_fields(y, prepend_with=(0, 1)), "y[0,1,4,5,i,j,k]")
+    y = ps.Field("y", ignore_prepends=False)
+    assert same(index_fields(y[2, 3], prepend_with=(0, 1)), "y[0,1,2,3,i,j,k]")
+    y = ps.Field("y[4, 5]", ignore_prepends=False)
+    assert same(index_fields(y[2, 3], prepend_with=(0, 1)), "y[0,1,2,3,4,5,i,j,k]")
+    y = ps.Field("y", offset=("hx", "hy", "hz"))
+    assert same(index_fields(shift_fields(y, (1, 2, 3))), "y[i+hx+1,j+hy+2,k+hz+3]")
+    y = ps.Field("y", offset=("hx", var("hy"), "hz"))
+    assert same(index_fields(shift_fields(y, (1, 2, var("a")))),
+                "y[i+hx+1,j+hy+2,k+hz+a]")
+    with pytest.raises(ValueError):
+        ps.Field("y", offset=(1, 2))
+
+
+def test_dynamic_field():
+    y = ps.DynamicField("y", offset="h")
+    assert same(index_fields(y), "y[i+h,j+h,k+h]")
+    assert same(index_fields(y.lap), "lap_y[i,j,k]")
+    assert same(index_fields(y.dot), "dydt[i+h,j+h,k+h]")
+    assert same(index_fields(y.pd[var("x")]), "dydx[x,i,j,k]")
+    assert same(index_fields(y.d(1, 0)), "dydt[1,i+h,j+h,k+h]")
+    assert same(index_fields(y.d(1, 1)), "dydx[1,0,i,j,k]")
+    f = ps.DynamicField("f")
+    assert same(f.d(0), "dfdt") and same(f.d(1, 2, 0), "dfdt[1,2]")
+    assert same(f.d(2), "dfdx[1]") and same(f.d(0, 1, 3), "dfdx[0,1,2]")
+
+
+def test_field_diff():
+    from pystella_b200 import diff
+    y = ps.Field("y")
+    assert diff(y, y) == 1 and diff(y[0], y[0]) == 1 and diff(y[0], y[1]) == 0
+    y = ps.DynamicField("y")
+    assert diff(y, y) == 1 and diff(y[0], y[0]) == 1 and diff(y[0], y[1]) == 0
+    ctx = dict(y=1.7, dydt=0.3)
+    assert np.isclose(evaluate(diff(y**3, y, "t"), ctx), 3 * 2 * 1.7 * 0.3)
+    assert np.isclose(evaluate(diff(y**3, "t", y), ctx), 3 * 2 * 1.7 * 0.3)
+    for i, x in enumerate(["t", "x", "y", "z"]):
+        assert diff(y, x) == y.d(i)
+        assert diff(y[1, 3], x) == y.d(1, 3, i)
+    # chain / product / quotient rules, numerically
+    a, b = var("a"), var("b")
+    expr = (a**2 * b + 3) / (1 + b**2)
+    ctx = dict(a=0.7, b=1.3)
+    eps = 1e-6
+    num = (evaluate(expr, dict(a=0.7, b=1.3 + eps))
+           - evaluate(expr, dict(a=0.7, b=1.3 - eps))) / (2 * eps)
+    assert np.isclose(evaluate(diff(expr, b), ctx), num, rtol=1e-8)
+
+
+def test_get_field_args():
+    f = ps.DynamicField("f", offset="h", shape=(2,))
+    H = ps.Field("hubble", indices=[])
+    args = ps.get_field_args({f[0]: f.dot[0], f.dot[0]: f.lap[0] - 2 * H * f.dot[0]})
+    names = [a.name for a in args]
+    assert names == sorted(names) == ["dfdt", "f", "hubble", "lap_f"]
+    by = {a.name: a for a in args}
+    assert by["hubble"].is_value and not by["f"].is_value
+    assert len(by["f"].shape) == 4 and by["f"].shape[0] == 2
+    assert by["lap_f"].shape == (2, "Nx", "Ny", "Nz")
+
+
+def test_polynomial_normal_form_and_recognition():
+    f = ps.DynamicField("f", offset="h", shape=(2,))
+    a = ps.Field("a", indices=[])
+    poly = to_polynomial(a**2 * (f[0]**2 * f[1] + 3 * f[1]) / 2 - f.lap[0])
+    keys = {tuple((r.name, r.subscript, p) for r, p in m) for m in poly}
+    assert (("f", (0,), 2), ("f", (1,), 1)) in keys
+    assert (("f", (1,), 1),) in keys and (("lap_f", (0,), 1),) in keys
+    with pytest.raises(NotImplementedError):
+        to_polynomial(1 / f[0])
+    with pytest.raises(NotImplementedError):
+        to_polynomial(f[0]**0.5)
+
+    from pystella_b200.step import recognise_scalar_system, scalar_system_from_sector
+    sec = ps.ScalarSector(2, potential=lambda g: g[0]**2 / 2 + 0.25 * g[0]**2 * g[1]**2)
+    sysm = recognise_scalar_system(sec.rhs_dict)
+    assert sysm.nscalars == 2 and sysm.f_name == "f" and sysm.lap_name == "lap_f"
+    exact = scalar_system_from_sector(sec)
+    ctx = dict(a=1.3, hubble=0.2)
+    assert np.isclose(evaluate(sysm.hubble, ctx), 0.2)
+    for n in range(2):
+        got = sorted((p, float(evaluate(c, ctx))) for c, p in sysm.dV[n])
+        ref = sorted((p, 1.3**2 * float(evaluate(c, ctx))) for c, p in exact.dV[n])
+        assert [g[0] for g in got] == [r[0] for r in ref]
+        assert np.allclose([g[1] for g in got], [r[1] for r in ref])
+    # things outside the kernel menu are refused with a reason
+    bad = dict(sec.rhs_dict)
+    bad[f.dot[0]] = bad[f.dot[0]] + f.dot[1]
+    with pytest.raises(NotImplementedError):
+        recognise_scalar_system(bad)
+    g = ps.DynamicField("g", offset="h")
+    with pytest.raises(NotImplementedError):
+        recognise_scalar_system({g: g.dot, g.dot: g.lap * 2})
+
+
+def test_sector_dictionaries():
+    """Key order and contents of rhs_dict / reducers (sectors.py:117-144, 187-204)."""
+    sec = ps.ScalarSector(2, potential=lambda f: f[0]**2 / 2)
+    keys = [str(k) for k in sec.rhs_dict]
+    assert keys == ["f[0]", "dfdt[0]", "f[1]", "dfdt[1]"]
+    assert list(sec.reducers) == ["kinetic", "potential", "gradient"]
+    assert [len(v) for v in sec.reducers.values()] == [2, 1, 2]
+    gw = ps.TensorPerturbationSector([sec])
+    keys = [str(k) for k in gw.rhs_dict]
+    assert keys == [x for c in range(6) for x in (f"hij[{c}]", f"dhijdt[{c}]")]
+    assert gw.reducers == {}
+    # stress tensor: T_ij (trace dropped) = sum_n d_i f d_j f
+    T12 = sec.stress_tensor(1, 2, drop_trace=True)
+    ctx = {"dfdx": np.arange(6.).reshape(2, 3) + 1}
+    assert np.isclose(evaluate(T12, ctx), 1 * 2 + 4 * 5)
+    ctx.update(dfdt=np.array([0.3, 0.4]), f=np.array([0.5, 0.6]), a=1.2)
+    T00 = evaluate(sec.stress_tensor(0, 0), ctx)
+    kin = 0.3**2 + 0.4**2
+    grad2 = sum((ctx["dfdx"][n]**2).sum() for n in range(2))
+    lag = -(-kin / 1.2**2 + grad2 / 1.2**2) / 2 - 0.5**2 / 2
+    assert np.isclose(T00, kin + (-1.2**2) * lag)
