@@ -146,8 +146,9 @@ def main():
         step_count += 1
         if step_count % 16 == 0 or t >= p.end_time:
             if device_loop:
-                rec = expand.get()
-                a_now, constraint = float(rec["a"]), float(expand.constraint())
+                a_now = float(expand.get()["a"])
+                # energy of the current state for the output (stand-alone kernels)
+                constraint = float(expand.constraint(compute_energy(a_now)["total"]))
             else:
                 a_now = float(expand.a[0])
                 constraint = float(expand.constraint(energy["total"]))

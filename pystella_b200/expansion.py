@@ -147,8 +147,13 @@ class DeviceExpansion:
                     gradient=en[n + 1:2 * n + 1].copy(), total=en[2 * n + 1],
                     pressure=en[2 * n + 2])
 
-    def constraint(self):
-        """Friedmann-constraint violation with the last stage's energy (host)."""
-        g = self.get()
-        return abs(np.sqrt(8 * np.pi * g["a"]**2 / 3 / self.mpl**2 * g["total"]) * g["a"]
-                   / g["adot"] - 1)
+    def constraint(self, energy):
+        """
+        ``|sqrt(8 pi a^2 rho/(3 mpl^2)) a / adot - 1|`` for the energy density ``energy``
+        of the CURRENT state (e.g. from :class:`Reduction`); synchronises.  Note that
+        :attr:`energies` belongs to the state that *entered* the last stage, so it is
+        not the right input here.
+        """
+        st = self.state.cpu().numpy()
+        a, adot = st[0], st[1]
+        return abs(np.sqrt(8 * np.pi * a**2 / 3 / self.mpl**2 * float(energy)) * a / adot - 1)
