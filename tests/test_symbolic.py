@@ -15,34 +15,41 @@ def same(a, b):
     return str(a).replace(" ", "") == str(b).replace(" ", "")
 
 
-def test_field_indexing():
-    y = ps.Field("y", offset="h")
-    assert same(index_fields(y), "y[i+h,j+h,k+h]")
-    y = ps.Field("y", offset="h", indices=("a", "b", "c"))
-    assert same(index_fields(y), "y[a+h,b+h,c+h]")
-    y = ps.Field("y", ignore_prepends=True)
-    assert same(index_fields(y, prepend_with=(0, 1)), "y[i,j,k]")
-    y = ps.Field("y[4, 5]", ignore_prepends=True)
-    assert same(index_fields(y, prepend_with=(0, 1)), "y[4,5,i,j,k]")
-    y = ps.Field("y", ignore_prepends=True)
-    assert same(index_fields(y[2, 3], prepend_with=(0, 1)), "y[2,3,i,j,k]")
-    y = ps.Field("y[4, 5]", ignore_prepends=True)
-    assert same(index_fields(y[2, 3], prepend_with=(0, 1)), "y[2,3,4,5,i,j,k]")
-    y = ps.Field("y", ignore_prepends=False)
-    assert same(index_fields(y, prepend_with=(0, 1)), "y[0,1,i,j,k]")
-    y = ps.Field("y[4, 5]", ignore_prepends=False)
-    assert same(index_fields(y, prepend_with=(0, 1)), "y[0,1,4,5,i,j,k]")
-    y = ps.Field("y", ignore_prepends=False)
-    assert same(index_fields(y[2, 3], prepend_with=(0, 1)), "y[0,1,2,3,i,j,k]")
-    y = ps.Field("y[4, 5]", ignore_prepends=False)
-    assert same(index_fields(y[2, 3], prepend_with=(0, 1)), "y[0,1,2,3,4,5,i,j,k]")
-    y = ps.Field("y", offset=("hx", "hy", "hz"))
-    assert same(index_fields(shift_fields(y, (1, 2, 3))), "y[i+hx+1,j+hy+2,k+hz+3]")
-    y = ps.Field("y", offset=("hx", var("hy"), "hz"))
-    assert same(index_fields(shift_fields(y, (1, 2, var("a")))),
-                "y[i+hx+1,j+hy+2,k+hz+a]")
+# (child, constructor kwargs, subscript, prepend_with, shift) -> printed indexed form;
+# the cases of test/test_field.py:30-82
+INDEXING_CASES = [
+    ("y", dict(offset="h"), None, None, None, "y[i+h,j+h,k+h]"),
+    ("y", dict(offset="h", indices=("a", "b", "c")), None, None, None, "y[a+h,b+h,c+h]"),
+    ("y", dict(ignore_prepends=True), None, (0, 1), None, "y[i,j,k]"),
+    ("y[4, 5]", dict(ignore_prepends=True), None, (0, 1), None, "y[4,5,i,j,k]"),
+    ("y", dict(ignore_prepends=True), (2, 3), (0, 1), None, "y[2,3,i,j,k]"),
+    ("y[4, 5]", dict(ignore_prepends=True), (2, 3), (0, 1), None, "y[2,3,4,5,i,j,k]"),
+    ("y", dict(ignore_prepends=False), None, (0, 1), None, "y[0,1,i,j,k]"),
+    ("y[4, 5]", dict(ignore_prepends=False), None, (0, 1), None, "y[0,1,4,5,i,j,k]"),
+    ("y", dict(ignore_prepends=False), (2, 3), (0, 1), None, "y[0,1,2,3,i,j,k]"),
+    ("y[4, 5]", dict(ignore_prepends=False), (2, 3), (0, 1), None,
+     "y[0,1,2,3,4,5,i,j,k]"),
+    ("y", dict(offset=("hx", "hy", "hz")), None, None, (1, 2, 3),
+     "y[i+hx+1,j+hy+2,k+hz+3]"),
+    ("y", dict(offset=("hx", var("hy"), "hz")), None, None, (1, 2, var("a")),
+     "y[i+hx+1,j+hy+2,k+hz+a]"),
+]
+
+
+@pytest.mark.parametrize("child,kw,sub,prepend,shift,expected", INDEXING_CASES)
+def test_field_indexing(child, kw, sub, prepend, shift, expected):
+    expr = ps.Field(child, **kw)
+    if sub is not None:
+        expr = expr[sub]
+    if shift is not None:
+        expr = shift_fields(expr, shift)
+    assert same(index_fields(expr, prepend_with=prepend), expected)
+
+
+def test_field_offset_length_is_checked():
     with pytest.raises(ValueError):
         ps.Field("y", offset=(1, 2))
+    assert parse("f[0]") == var("f")[0]
 
 
 def test_dynamic_field():
