@@ -239,8 +239,17 @@ def reduce_poly(arrays, halos, terms, ops, flags, shape, queue=None, strict=Fals
     return out
 
 
+ENERGY_SUMS_DOUBLES = 16 + 64 * 16 + 2   # PSB_ENERGY_SUMS_DOUBLES of the header
+
+
 def energy_sums(partials, nslots, nvals, sums, queue=None, strict=False):
+    """``sums``: zero-initialised float64 buffer of ENERGY_SUMS_DOUBLES (result in [:16])."""
     lib = _lib.load(strict)
+    if sums.dtype != torch.float64 or sums.numel() < ENERGY_SUMS_DOUBLES:
+        raise ValueError(f"sums must be a float64 buffer of {ENERGY_SUMS_DOUBLES} elements "
+                         "(result + scratch rows + ticket)")
+    if partials.shape[0] < nslots:
+        raise ValueError("fewer partial rows than nslots")
     rc = lib.psb_energy_sums(_ptr(partials), nslots, nvals, _ptr(sums),
                              _lib.stream_ptr(queue))
     _lib.check(lib, rc, "psb_energy_sums")

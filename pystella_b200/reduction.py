@@ -157,8 +157,9 @@ class Reduction:
                 raise ValueError(f"'{ref.name}' has wrong number of outer axes")
             arrays.append(sub)
             halos.append(self._halo_of(ref, h))
-        shape = tuple(n - 2 * g for n, g in zip(arrays[0].shape, (halos[0],) * 3)) \
-            if arrays else None
+        if not arrays:
+            raise NotImplementedError("a Reduction needs at least one array operand")
+        shape = tuple(n - 2 * g for n, g in zip(arrays[0].shape, (halos[0],) * 3))
 
         ctx = {}
         for n in self._scalar_names:
