@@ -184,6 +184,27 @@ typedef struct psb_tensor_stage_args {
 } psb_tensor_stage_args;
 int psb_tensor_stage_unfused(const psb_tensor_stage_args* args, void* stream);
 
+/* EXPERIMENTAL (opt-in, not validated on hardware in round 1): the same stage with
+ * lap(hij_c) and the gradients of the source fields evaluated in-kernel from `hij_in`
+ * and `src` (the scalar fields' OLD values, padded, valid face halos), in the TMA
+ * pipeline of psb_scalar_stage_fused; hij ping-pongs into `hij_out`. */
+typedef struct psb_tensor_fused_args {
+  int32_t dtype, nscalars, h;
+  int32_t wrap_x, wrap_y, wrap_z;
+  int64_t Nx, Ny, Nz;
+  const void* hij_in;
+  void* hij_out;
+  void* dhijdt;
+  void* khij;
+  void* kdhijdt;
+  const void* src;               /* (nscalars, padded) source fields, field 0        */
+  int64_t src_stride;            /* elements between source fields                   */
+  double dx[3];
+  double dt, A, B, hubble, source_coef;
+  const double* hubble_dev;
+} psb_tensor_fused_args;
+int psb_tensor_stage_fused(const psb_tensor_fused_args* args, void* stream);
+
 /* ------------------------------------------------------------------------
  * Finite differences: FiniteDifferencer.__call__ kernels lap_knl / grad_knl /
  * grad_lap_knl / pd{x,y,z}_knl / pd*_incr_knl (pystella/derivs.py:291-337).

@@ -77,6 +77,17 @@ class TensorStageArgs(C.Structure):
                 ("source_coef", c_double), ("hubble_dev", c_void_p)]
 
 
+class TensorFusedArgs(C.Structure):
+    _fields_ = [("dtype", c_int32), ("nscalars", c_int32), ("h", c_int32),
+                ("wrap_x", c_int32), ("wrap_y", c_int32), ("wrap_z", c_int32),
+                ("Nx", c_int64), ("Ny", c_int64), ("Nz", c_int64),
+                ("hij_in", c_void_p), ("hij_out", c_void_p), ("dhijdt", c_void_p),
+                ("khij", c_void_p), ("kdhijdt", c_void_p), ("src", c_void_p),
+                ("src_stride", c_int64), ("dx", c_double * 3),
+                ("dt", c_double), ("A", c_double), ("B", c_double), ("hubble", c_double),
+                ("source_coef", c_double), ("hubble_dev", c_void_p)]
+
+
 class PeerArgs(C.Structure):
     _fields_ = [("nranks", c_int32), ("rank", c_int32), ("peer_slots", c_void_p),
                 ("peer_flags", c_void_p), ("epoch", c_void_p)]
@@ -106,6 +117,7 @@ SYMBOLS = {
     "psb_scalar_stage_fused": (c_int, [C.POINTER(ScalarStageArgs), c_void_p]),
     "psb_scalar_stage_unfused": (c_int, [C.POINTER(ScalarStageArgs), c_void_p]),
     "psb_scalar_rk_stage": (c_int, [C.POINTER(RKStageArgs), c_void_p]),
+    "psb_tensor_stage_fused": (c_int, [C.POINTER(TensorFusedArgs), c_void_p]),
     "psb_tensor_stage_unfused": (c_int, [C.POINTER(TensorStageArgs), c_void_p]),
     "psb_finite_difference": (c_int, [c_void_p] * 5 + [c_int, c_int64, c_int64, c_int64,
                                                         c_int, c_int,

@@ -1,0 +1,459 @@
+// EXPERIMENTAL (opt-in, PSB_FUSED_GW=1; not yet validated on hardware at the time of
+// writing -- the validated tensor-sector path is tensor_stage.cu).
+//
+// Fused stage of the tensor-perturbation sector in the warp-specialised TMA pipeline
+// of fused_stage_ws.cuh: lap(hij_c) and the gradient of the source fields are
+// evaluated in-kernel, so lap_hij / dfdx never touch HBM
+// (TensorPerturbationSector.rhs_dict, pystella/sectors.py:187-204; scalar stress tensor
+// with drop_trace=True, sectors.py:146-152; low-storage stage, step.py:473-491).
+//
+// One CTA column handles ONE packed component c (the component is the fastest grid
+// dimension, so the six CTAs of a tile run together and share the source tiles in L2):
+//   h ring  : R_f slots of the padded hij_c plane           (stencil: Laplacian)
+//   s ring  : R_f slots of the padded planes of the NS source fields (gradient)
+//   pw ring : R_p slots of {dhijdt_c, khij_c, kdhijdt_c} interior tiles
+// x neighbours of h and of the sources live in per-thread register queues.
+#include <math.h>
+#include <string.h>
+
+#include "fused_stage_impl.cuh"  // also brings in fused_stage_ws.cuh (the pipeline helpers)
+
+namespace psb {
+
+template <typename T> struct TensorFusedParams {
+  const T* h_in;
+  T* h_out;
+  T* dh;
+  T* kh;
+  T* kdh;
+  int64_t comp_stride;
+  int Nx, Ny, Nz;
+  int x_begin, x_end, xchunk;
+  int x2_begin, x2_end, nchunks1;
+  int wrap_x, wrap_y, wrap_z;
+  T inv_dx2[3];
+  T inv_dx[3];
+  T dt, A, B, hubble, coef;
+  const double* hubble_dev;
+};
+
+template <typename T, int H, int NS, int BY, int TZ, int P, int VEC_> struct TwsCfg {
+  using B = WsCfg<T, H, 1, BY, TZ, P, VEC_>;
+  static constexpr int RF = B::RF, RP = B::RP;
+  static constexpr int FSLOT = (1 + NS) * B::FPLANE;   // h plane + NS source planes
+  static constexpr int PWSLOT = 3 * B::PWTILE;
+  static constexpr int NBAR = 2 * RF + 2 * RP;
+  static constexpr int SMEM_BYTES = RF * FSLOT + RP * PWSLOT + NBAR * 8 + 128;
+  static constexpr int THREADS = BY * TZ + 32;
+  static constexpr int NCW = BY * TZ / 32;
+};
+
+template <typename T, int H, int NS, int BY, int TZ, int P, int MINB, int VEC_>
+__global__ void __launch_bounds__(BY* TZ + 32, MINB)
+    tensor_stage_ws_kernel(const __grid_constant__ TensorFusedParams<T> p,
+                           const __grid_constant__ CUtensorMap map_h,
+                           const __grid_constant__ CUtensorMap map_s,
+                           const __grid_constant__ CUtensorMap map_d,
+                           const __grid_constant__ CUtensorMap map_kh,
+                           const __grid_constant__ CUtensorMap map_kd) {
+  using C = TwsCfg<T, H, NS, BY, TZ, P, VEC_>;
+  using B = typename C::B;
+  constexpr int VEC = B::VEC, GV = B::GV, W = B::W, HL = B::HL, RF = C::RF, RP = C::RP;
+  using V = Vec<T, VEC>;
+
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned char* base = smem_raw + ((128 - (smem_u32(smem_raw) & 127)) & 127);
+  unsigned char* fring = base;
+  unsigned char* pring = base + RF * C::FSLOT;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(pring + RP * C::PWSLOT);
+  uint64_t* full_f = bars;
+  uint64_t* empty_f = bars + RF;
+  uint64_t* full_p = bars + 2 * RF;
+  uint64_t* empty_p = bars + 2 * RF + RP;
+
+  const int tid = threadIdx.x;
+  const int comp = blockIdx.x % 6;           // packed component (1,1),(1,2),(1,3),(2,2),...
+  const int z0 = (blockIdx.x / 6) * B::BZ, y0 = blockIdx.y * BY;
+  int zc = blockIdx.z, xb = p.x_begin, xlim = p.x_end;
+  if (zc >= p.nchunks1) {
+    zc -= p.nchunks1;
+    xb = p.x2_begin;
+    xlim = p.x2_end;
+  }
+  const int xs = xb + zc * p.xchunk;
+  const int xe = min(xs + p.xchunk, xlim);
+  const int nsteps = (xe - xs) + 2 * H;
+  const int ncomp = xe - xs;
+  const bool read_k = (p.A != (T)0);
+
+  if (tid == 0) {
+    for (int s = 0; s < RF; ++s) {
+      mbar_init(&full_f[s], 1);
+      mbar_init(&empty_f[s], C::NCW);
+    }
+    for (int s = 0; s < RP; ++s) {
+      mbar_init(&full_p[s], 1);
+      mbar_init(&empty_p[s], C::NCW);
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();
+
+  if (tid >= BY * TZ) {
+    if (tid == BY * TZ) {
+      tma_prefetch_desc(&map_h);
+      tma_prefetch_desc(&map_s);
+      tma_prefetch_desc(&map_d);
+      tma_prefetch_desc(&map_kh);
+      tma_prefetch_desc(&map_kd);
+      const uint32_t pw_bytes = (read_k ? 3u : 1u) * B::PWTILE_RAW;
+      for (int m = 0; m < nsteps; ++m) {
+        {
+          const int slot = m % RF;
+          if (m >= RF) mbar_wait(&empty_f[slot], ((m / RF) - 1) & 1);
+          mbar_expect_tx(&full_f[slot], (1 + NS) * B::FPLANE_RAW);
+          unsigned char* dst = fring + slot * C::FSLOT;
+          tma_load_4d(dst, &map_h, &full_f[slot], z0 + H - HL, y0, xs + m, comp);
+#pragma unroll
+          for (int n = 0; n < NS; ++n)
+            tma_load_4d(dst + (1 + n) * B::FPLANE, &map_s, &full_f[slot], z0 + H - HL, y0,
+                        xs + m, n);
+        }
+        const int c = m - 2 * H;
+        if (c >= 0 && c < ncomp) {
+          const int slot = c % RP;
+          if (c >= RP) mbar_wait(&empty_p[slot], ((c / RP) - 1) & 1);
+          mbar_expect_tx(&full_p[slot], pw_bytes);
+          unsigned char* dst = pring + slot * C::PWSLOT;
+          const int px = xs + c + H;
+          tma_load_4d(dst, &map_d, &full_p[slot], z0 + H - B::PWL, y0 + H, px, comp);
+          if (read_k) {
+            tma_load_4d(dst + B::PWTILE, &map_kh, &full_p[slot], z0 + H - B::PWL, y0 + H, px,
+                        comp);
+            tma_load_4d(dst + 2 * B::PWTILE, &map_kd, &full_p[slot], z0 + H - B::PWL, y0 + H,
+                        px, comp);
+          }
+        }
+      }
+    }
+    return;
+  }
+
+  const int tz = tid % TZ, ty = tid / TZ;
+  const int lane = tid & 31;
+  const int j = y0 + ty, k = z0 + tz * VEC;
+  const bool active = (j < p.Ny) && (k < p.Nz);
+  const int64_t Pz = p.Nz + 2 * H, Py = p.Ny + 2 * H;
+  const int64_t plane_stride = Py * Pz;
+  const int64_t site0 = ((int64_t)H * Py + (j + H)) * Pz + (k + H);
+
+  T hubble = p.hubble;
+  if (p.hubble_dev) hubble = (T)(*p.hubble_dev);
+  const T two_h = (T)2 * hubble;
+  // (i, j) of the packed component
+  const int ci = comp < 3 ? 0 : (comp < 5 ? 1 : 2);
+  const int cj = comp < 3 ? comp : (comp < 5 ? comp - 2 : 2);
+
+  const int own_off = (ty + H) * W + HL + tz * VEC;
+  const int pw_off = ty * B::PWW + B::PWL + tz * VEC;
+
+  V qh[2 * H + 1];
+  V qs[NS][2 * H + 1];
+#pragma unroll
+  for (int s = 0; s < 2 * H + 1; ++s) {
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) qh[s].v[v] = (T)0;
+#pragma unroll
+    for (int n = 0; n < NS; ++n)
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) qs[n][s].v[v] = (T)0;
+  }
+
+  const int64_t cofs = (int64_t)comp * p.comp_stride;
+  T* o_h = p.h_out + cofs + site0 + (int64_t)xs * plane_stride;
+  T* o_d = p.dh + cofs + site0 + (int64_t)xs * plane_stride;
+  T* o_kh = p.kh + cofs + site0 + (int64_t)xs * plane_stride;
+  T* o_kd = p.kdh + cofs + site0 + (int64_t)xs * plane_stride;
+
+  for (int n = 0; n < nsteps; ++n) {
+    const int slot = n % RF;
+    mbar_wait(&full_f[slot], (n / RF) & 1);
+    {
+      const unsigned char* sl = fring + slot * C::FSLOT;
+#pragma unroll
+      for (int s = 0; s < 2 * H; ++s) qh[s] = qh[s + 1];
+      qh[2 * H] = ld_pieces<T, VEC, GV>(reinterpret_cast<const T*>(sl) + own_off);
+#pragma unroll
+      for (int m = 0; m < NS; ++m) {
+#pragma unroll
+        for (int s = 0; s < 2 * H; ++s) qs[m][s] = qs[m][s + 1];
+        qs[m][2 * H] = ld_pieces<T, VEC, GV>(
+            reinterpret_cast<const T*>(sl + (1 + m) * B::FPLANE) + own_off);
+      }
+    }
+
+    if (n >= 2 * H) {
+      const int c = n - 2 * H;
+      const int i = xs + c;
+      const int cslot = (n - H) % RF;
+      const int pslot = c % RP;
+      mbar_wait(&full_p[pslot], (c / RP) & 1);
+      if (active) {
+        const unsigned char* pw = pring + pslot * C::PWSLOT;
+        const unsigned char* cen = fring + cslot * C::FSLOT;
+        V dold = ld_pieces<T, VEC, GV>(reinterpret_cast<const T*>(pw) + pw_off);
+        V kho, kdo;
+        if (read_k) {
+          kho = ld_pieces<T, VEC, GV>(reinterpret_cast<const T*>(pw + B::PWTILE) + pw_off);
+          kdo = ld_pieces<T, VEC, GV>(reinterpret_cast<const T*>(pw + 2 * B::PWTILE) + pw_off);
+        } else {
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) kho.v[v] = kdo.v[v] = (T)0;
+        }
+        constexpr int NVZ = (VEC + 2 * HL) / GV;
+
+        // ---- Laplacian of hij_c
+        V lap;
+        {
+          const T* pl = reinterpret_cast<const T*>(cen);
+          T zrow[NVZ * GV];
+#pragma unroll
+          for (int w = 0; w < NVZ; ++w) {
+            Vec<T, GV> t = ld_vec<T, GV>(pl + own_off - HL + w * GV);
+#pragma unroll
+            for (int v = 0; v < GV; ++v) zrow[w * GV + v] = t.v[v];
+          }
+          V yn[2 * H + 1];
+#pragma unroll
+          for (int s = 1; s <= H; ++s) {
+            yn[H + s] = ld_pieces<T, VEC, GV>(pl + own_off + s * W);
+            yn[H - s] = ld_pieces<T, VEC, GV>(pl + own_off - s * W);
+          }
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) {
+            const T cc = qh[H].v[v];
+            T sx = (T)lap_coef<H>(0) * cc, sy = sx, sz = sx;
+#pragma unroll
+            for (int s = 1; s <= H; ++s) {
+              const T cs = (T)lap_coef<H>(s);
+              sx = sx + cs * qh[H + s].v[v];
+              sx = sx + cs * qh[H - s].v[v];
+              sy = sy + cs * yn[H + s].v[v];
+              sy = sy + cs * yn[H - s].v[v];
+              sz = sz + cs * zrow[HL + v + s];
+              sz = sz + cs * zrow[HL + v - s];
+            }
+            lap.v[v] = sx * p.inv_dx2[0] + sy * p.inv_dx2[1] + sz * p.inv_dx2[2];
+          }
+        }
+
+        // ---- source term S_c = sum_n d_i f_n d_j f_n  (first-derivative stencils)
+        V S;
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) S.v[v] = (T)0;
+#pragma unroll
+        for (int m = 0; m < NS; ++m) {
+          const T* pl = reinterpret_cast<const T*>(cen + (1 + m) * B::FPLANE);
+          T zrow[NVZ * GV];
+#pragma unroll
+          for (int w = 0; w < NVZ; ++w) {
+            Vec<T, GV> t = ld_vec<T, GV>(pl + own_off - HL + w * GV);
+#pragma unroll
+            for (int v = 0; v < GV; ++v) zrow[w * GV + v] = t.v[v];
+          }
+          V yn[2 * H + 1];
+#pragma unroll
+          for (int s = 1; s <= H; ++s) {
+            yn[H + s] = ld_pieces<T, VEC, GV>(pl + own_off + s * W);
+            yn[H - s] = ld_pieces<T, VEC, GV>(pl + own_off - s * W);
+          }
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) {
+            T gx = (T)0, gy = (T)0, gz = (T)0;
+#pragma unroll
+            for (int s = 1; s <= H; ++s) {
+              const T cs = (T)grad_coef<H>(s);
+              gx = (s == 1) ? cs * qs[m][H + s].v[v] : gx + cs * qs[m][H + s].v[v];
+              gx = gx + (-cs) * qs[m][H - s].v[v];
+              gy = (s == 1) ? cs * yn[H + s].v[v] : gy + cs * yn[H + s].v[v];
+              gy = gy + (-cs) * yn[H - s].v[v];
+              gz = (s == 1) ? cs * zrow[HL + v + s] : gz + cs * zrow[HL + v + s];
+              gz = gz + (-cs) * zrow[HL + v - s];
+            }
+            gx = gx * p.inv_dx[0];
+            gy = gy * p.inv_dx[1];
+            gz = gz * p.inv_dx[2];
+            const T gi = ci == 0 ? gx : (ci == 1 ? gy : gz);
+            const T gj = cj == 0 ? gx : (cj == 1 ? gy : gz);
+            S.v[v] = (m == 0) ? gi * gj : S.v[v] + gi * gj;
+          }
+        }
+
+        V ho, dn, khn, kdn;
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+          const T d_old = dold.v[v];
+          const T rhs_d = (lap.v[v] - two_h * d_old) + p.coef * S.v[v];
+          T khv, kdv;
+          if (read_k) {
+            khv = p.A * kho.v[v] + p.dt * d_old;
+            kdv = p.A * kdo.v[v] + p.dt * rhs_d;
+          } else {
+            khv = p.dt * d_old;
+            kdv = p.dt * rhs_d;
+          }
+          khn.v[v] = khv;
+          kdn.v[v] = kdv;
+          ho.v[v] = qh[H].v[v] + p.B * khv;
+          dn.v[v] = d_old + p.B * kdv;
+        }
+        st_pieces<T, VEC, GV, true>(o_kh, khn);
+        st_pieces<T, VEC, GV, true>(o_kd, kdn);
+        st_pieces<T, VEC, GV, true>(o_d, dn);
+        st_pieces<T, VEC, GV, false>(o_h, ho);
+        if (p.wrap_x) {
+          if (i < H) st_pieces<T, VEC, GV, false>(o_h + (int64_t)p.Nx * plane_stride, ho);
+          if (i >= p.Nx - H)
+            st_pieces<T, VEC, GV, false>(o_h - (int64_t)p.Nx * plane_stride, ho);
+        }
+        if (p.wrap_y) {
+          if (j < H) st_pieces<T, VEC, GV, false>(o_h + (int64_t)p.Ny * Pz, ho);
+          if (j >= p.Ny - H) st_pieces<T, VEC, GV, false>(o_h - (int64_t)p.Ny * Pz, ho);
+        }
+        if (p.wrap_z) {
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) {
+            if (k + v < H) o_h[v + p.Nz] = ho.v[v];
+            if (k + v >= p.Nz - H) o_h[v - p.Nz] = ho.v[v];
+          }
+        }
+      }
+      o_h += plane_stride;
+      o_d += plane_stride;
+      o_kh += plane_stride;
+      o_kd += plane_stride;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_p[pslot]);
+    }
+    if (n >= H) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_f[(n - H) % RF]);
+    }
+  }
+}
+
+constexpr int tws_smem_bytes(int es, int H, int NS, int BY, int TZ, int P, int VEC) {
+  const int BZ = TZ * VEC;
+  const int GV = ws_gcd(VEC, H);
+  const int HL = ((H + GV - 1) / GV) * GV;
+  const int WQ = 16 / es;
+  const int W = ((BZ + 2 * HL + WQ - 1) / WQ) * WQ;
+  const int fplane = (((BY + 2 * H) * W * es + 127) / 128) * 128;
+  const int pww = ((BZ + H % WQ + WQ - 1) / WQ) * WQ;
+  const int pwtile = ((BY * pww * es + 127) / 128) * 128;
+  return (H + 1 + P) * (1 + NS) * fplane + (P + 1) * 3 * pwtile +
+         (2 * (H + 1 + P) + 2 * (P + 1)) * 8 + 128;
+}
+constexpr int tws_pick_tz(int es, int H, int NS, int BY, int P, int VEC) {
+  for (int tz = 128 / VEC; tz >= 16; tz /= 2)
+    if (tws_smem_bytes(es, H, NS, BY, tz, P, VEC) <= SMEM_LIMIT) return tz;
+  return 16;
+}
+
+template <typename T, int H, int NS, int VEC>
+static int launch_tensor_ws(const psb_tensor_fused_args* a, cudaStream_t stream) {
+  constexpr int BY = 4, P = 2;
+  constexpr int TZ = tws_pick_tz((int)sizeof(T), H, NS, BY, P, VEC);
+  using C = TwsCfg<T, H, NS, BY, TZ, P, VEC>;
+  using B = typename C::B;
+  static_assert(C::SMEM_BYTES <= 227 * 1024, "tensor pipeline does not fit shared memory");
+  const int64_t Px = a->Nx + 2 * H, Py = a->Ny + 2 * H, Pz = a->Nz + 2 * H;
+  const int64_t vol = Px * Py * Pz;
+  CUtensorMap mh, ms, md, mkh, mkd;
+  if (encode_field_tensor_map(&mh, a->dtype, a->hij_in, 6, vol, Px, Py, Pz, 1, B::ROWS,
+                              B::W) != 0 ||
+      encode_field_tensor_map(&ms, a->dtype, a->src, NS, a->src_stride, Px, Py, Pz, 1,
+                              B::ROWS, B::W) != 0 ||
+      encode_field_tensor_map(&md, a->dtype, a->dhijdt, 6, vol, Px, Py, Pz, 1, BY,
+                              B::PWW) != 0 ||
+      encode_field_tensor_map(&mkh, a->dtype, a->khij, 6, vol, Px, Py, Pz, 1, BY, B::PWW) !=
+          0 ||
+      encode_field_tensor_map(&mkd, a->dtype, a->kdhijdt, 6, vol, Px, Py, Pz, 1, BY,
+                              B::PWW) != 0) {
+    set_error("psb_tensor_stage_fused: layout not describable by TMA (use the element-wise "
+              "tensor stage)");
+    return 3;
+  }
+  TensorFusedParams<T> p;
+  p.h_in = static_cast<const T*>(a->hij_in);
+  p.h_out = static_cast<T*>(a->hij_out);
+  p.dh = static_cast<T*>(a->dhijdt);
+  p.kh = static_cast<T*>(a->khij);
+  p.kdh = static_cast<T*>(a->kdhijdt);
+  p.comp_stride = vol;
+  p.Nx = (int)a->Nx;
+  p.Ny = (int)a->Ny;
+  p.Nz = (int)a->Nz;
+  p.x_begin = 0;
+  p.x_end = (int)a->Nx;
+  p.x2_begin = p.x2_end = 0;
+  int xchunk = WS_DEFAULT_XCHUNK;
+  if (xchunk > a->Nx) xchunk = (int)a->Nx;
+  p.xchunk = xchunk;
+  p.nchunks1 = (int)((a->Nx + xchunk - 1) / xchunk);
+  p.wrap_x = a->wrap_x;
+  p.wrap_y = a->wrap_y;
+  p.wrap_z = a->wrap_z;
+  for (int d = 0; d < 3; ++d) {
+    p.inv_dx2[d] = (T)pow(a->dx[d], -2.0);
+    p.inv_dx[d] = (T)(1.0 / a->dx[d]);
+  }
+  p.dt = (T)a->dt;
+  p.A = (T)a->A;
+  p.B = (T)a->B;
+  p.hubble = (T)a->hubble;
+  p.coef = (T)a->source_coef;
+  p.hubble_dev = a->hubble_dev;
+  dim3 grid((unsigned)(6 * ((a->Nz + B::BZ - 1) / B::BZ)), (unsigned)((a->Ny + BY - 1) / BY),
+            (unsigned)p.nchunks1);
+  dim3 block(C::THREADS, 1, 1);
+  auto kern = tensor_stage_ws_kernel<T, H, NS, BY, TZ, P, 1, VEC>;
+  PSB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      C::SMEM_BYTES));
+  kern<<<grid, block, C::SMEM_BYTES, stream>>>(p, mh, ms, md, mkh, mkd);
+  PSB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <typename T, int H>
+static int tensor_fused_ns(const psb_tensor_fused_args* a, cudaStream_t s) {
+  constexpr int VEC = 2;   // 16-byte (fp64) / 8-byte (fp32) vectors; fp32 x4: later
+  switch (a->nscalars) {
+    case 1: return launch_tensor_ws<T, H, 1, VEC>(a, s);
+    case 2: return launch_tensor_ws<T, H, 2, VEC>(a, s);
+  }
+  set_error("psb_tensor_stage_fused: nscalars=%d (1 or 2 source fields)", a->nscalars);
+  return 1;
+}
+
+}  // namespace psb
+
+extern "C" int psb_tensor_stage_fused(const psb_tensor_fused_args* a, void* stream) {
+  using namespace psb;
+  PSB_REQUIRE(a != nullptr, "psb_tensor_stage_fused: null args");
+  PSB_REQUIRE(a->hij_in && a->hij_out && a->dhijdt && a->khij && a->kdhijdt && a->src,
+              "psb_tensor_stage_fused: null array pointer");
+  PSB_REQUIRE(a->hij_in != a->hij_out, "psb_tensor_stage_fused: hij_out must not alias hij_in");
+  PSB_REQUIRE(a->Nx > 0 && a->Ny > 0 && a->Nz > 0, "psb_tensor_stage_fused: empty grid");
+  PSB_REQUIRE(a->h == 2 || a->h == 4,
+              "psb_tensor_stage_fused: h=%d (even halos only; use the element-wise stage)",
+              a->h);
+  PSB_REQUIRE(a->Nz % 2 == 0, "psb_tensor_stage_fused: odd Nz (use the element-wise stage)");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (a->dtype == PSB_F64)
+    return a->h == 2 ? tensor_fused_ns<double, 2>(a, s) : tensor_fused_ns<double, 4>(a, s);
+  if (a->dtype == PSB_F32)
+    return a->h == 2 ? tensor_fused_ns<float, 2>(a, s) : tensor_fused_ns<float, 4>(a, s);
+  set_error("psb_tensor_stage_fused: unknown dtype %d", a->dtype);
+  return 1;
+}

@@ -6,6 +6,7 @@ Tensor-perturbation (gravitational-wave) sector on the device: recognises a
 
 import ctypes as C
 import math
+import os
 
 import torch
 
@@ -17,7 +18,8 @@ __all__ = ["TensorSystem", "tensor_system_from_sector"]
 class TensorSystem:
     """hij / dhijdt pairs sourced by ``16 pi sum_n d_i f_n d_j f_n``."""
 
-    def __init__(self, sector, grad_name, nscalars):
+    def __init__(self, sector, grad_name, nscalars, source_name="f"):
+        self.source_name = source_name
         hij = sector.hij
         self.h_name = hij.name
         self.dot_name = hij.dot.name
@@ -26,8 +28,62 @@ class TensorSystem:
         self.nscalars = nscalars
         self.source_coef = 16 * math.pi
 
+    # -- EXPERIMENTAL fused path (PSB_FUSED_GW=1): stencils evaluated in-kernel ---------
+    def _fused_ok(self, stepper, kwargs):
+        if os.environ.get("PSB_FUSED_GW", "0") != "1" or not stepper.fused:
+            return False
+        decomp = stepper.decomp
+        if decomp is not None and decomp.nranks > 1:
+            return False
+        h = stepper.halo_shape
+        hij = kwargs.get(self.h_name)
+        old_f = stepper._twins.get(self.source_name)
+        return (h in (2, 4) and hij is not None and hij.shape[-1] % 2 == 0
+                and old_f is not None and self.nscalars in (1, 2))
+
+    def _run_fused(self, stepper, queue, kwargs, dt, A, B):
+        from pystella_b200 import _kernels
+        from pystella_b200.fused import _swap_storage
+        from pystella_b200.step import _scalar_value, gen_tmp_name
+        hij, dhij = kwargs[self.h_name], kwargs[self.dot_name]
+        kh = stepper.tmp_arrays[gen_tmp_name(self.h_name)]
+        kd = stepper.tmp_arrays[gen_tmp_name(self.dot_name)]
+        old_f = stepper._twins[self.source_name]   # the scalar stage just swapped: OLD f
+        h = stepper.halo_shape
+        twin = stepper._twins.get(self.h_name)
+        if twin is None or twin.shape != hij.shape or twin.dtype != hij.dtype:
+            twin = hij.clone()
+            stepper._twins[self.h_name] = twin
+            for c in range(6):
+                _kernels.halo_wrap(hij[c], (h, h, h), 7, queue)
+        Nx, Ny, Nz = (n - 2 * h for n in hij.shape[-3:])
+        args = _lib.TensorFusedArgs()
+        args.dtype = _lib.torch_dtype_code(hij)
+        args.nscalars, args.h = self.nscalars, h
+        args.wrap_x = args.wrap_y = args.wrap_z = 1
+        args.Nx, args.Ny, args.Nz = Nx, Ny, Nz
+        args.hij_in, args.hij_out = hij.data_ptr(), twin.data_ptr()
+        args.dhijdt, args.khij, args.kdhijdt = dhij.data_ptr(), kh.data_ptr(), kd.data_ptr()
+        args.src = old_f.data_ptr()
+        args.src_stride = old_f.shape[-3] * old_f.shape[-2] * old_f.shape[-1]
+        for d in range(3):
+            args.dx[d] = float(stepper.dx[d])
+        args.dt, args.A, args.B = dt, A, B
+        args.source_coef = self.source_coef
+        hub = kwargs.get("hubble", 0.)
+        if isinstance(hub, torch.Tensor):
+            args.hubble_dev = hub.data_ptr()
+        else:
+            args.hubble = _scalar_value(hub)
+        lib = _lib.load(stepper.strict_fp)
+        rc = lib.psb_tensor_stage_fused(C.byref(args), _lib.stream_ptr(queue))
+        _lib.check(lib, rc, "psb_tensor_stage_fused")
+        _swap_storage(hij, twin)
+
     def run_stage(self, stepper, stage, queue, kwargs, dt, A, B):
         from pystella_b200.step import _scalar_value, gen_tmp_name
+        if self._fused_ok(stepper, kwargs):
+            return self._run_fused(stepper, queue, kwargs, dt, A, B)
         names = (self.h_name, self.dot_name, self.lap_name, self.grad_name)
         for n in names:
             if kwargs.get(n) is None:
@@ -76,4 +132,4 @@ def tensor_system_from_sector(sector):
         raise NotImplementedError(
             "device tensor sector: exactly one ScalarSector source is supported")
     src = sector.sectors[0]
-    return TensorSystem(sector, src.f.pd.name, src.nscalars)
+    return TensorSystem(sector, src.f.pd.name, src.nscalars, source_name=src.f.name)

@@ -49,20 +49,21 @@ def test_struct_layout_matches_header():
     import tempfile
     src = ('#include <stdio.h>\n#include "pystella_b200.h"\nint main(){printf("%zu %zu\\n",'
            'sizeof(psb_scalar_stage_args), sizeof(psb_reduce_args));'
-           'printf("%zu %zu %zu\\n", sizeof(psb_tensor_stage_args), sizeof(psb_peer_args),'
-           'sizeof(psb_rk_stage_args));'
+           'printf("%zu %zu %zu %zu\\n", sizeof(psb_tensor_stage_args), sizeof(psb_peer_args),'
+           'sizeof(psb_rk_stage_args), sizeof(psb_tensor_fused_args));'
            'return 0;}')
     with tempfile.TemporaryDirectory() as d:
         c = os.path.join(d, "p.c")
         open(c, "w").write(src)
         exe = os.path.join(d, "p")
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
-        a, b, c, d, e = subprocess.check_output([exe]).split()
+        a, b, c, d, e, f = subprocess.check_output([exe]).split()
     assert int(a) == ctypes.sizeof(_lib.ScalarStageArgs)
     assert int(b) == ctypes.sizeof(_lib.ReduceArgs)
     assert int(c) == ctypes.sizeof(_lib.TensorStageArgs)
     assert int(d) == ctypes.sizeof(_lib.PeerArgs)
     assert int(e) == ctypes.sizeof(_lib.RKStageArgs)
+    assert int(f) == ctypes.sizeof(_lib.TensorFusedArgs)
 
 
 def test_no_cpu_fallback():

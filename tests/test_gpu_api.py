@@ -560,3 +560,11 @@ def test_classical_rk_wave_equation_device(name):
             stepper(s, queue=None, f=f, dfdt=dfdt, lap_f=lap_f)
     for got, ref in ((f, fq), (dfdt, dq)):
         assert scale_err(O.interior(got[0].cpu().numpy(), h), O.interior(ref[0], h)) < 1e-13
+
+
+@pytest.mark.skipif(__import__("os").environ.get("PSB_FUSED_GW", "0") != "1",
+                    reason="experimental fused tensor-sector kernel: opt-in (PSB_FUSED_GW=1)")
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-12), (np.float32, 3e-5)])
+def test_fused_gw_sector_experimental(dtype, tol):
+    """Same check as test_two_scalars_plus_gw_sector, with lap_hij / dfdx never formed."""
+    test_two_scalars_plus_gw_sector(True, dtype, tol)
