@@ -81,11 +81,35 @@ def build_variant(name, extra_flags, force=False, verbose=False):
     return lib
 
 
+def build_jit(force=False, verbose=False):
+    """NVRTC + driver-API runtime of the experimental generated kernels (host code only;
+    separate so that the main library carries no NVRTC dependency)."""
+    os.makedirs(OUT, exist_ok=True)
+    src = os.path.join(CSRC, "jit.cpp")
+    hdr = os.path.join(ROOT, "include", "pystella_b200_jit.h")
+    lib = os.path.join(OUT, "libpystella_b200_jit.so")
+    stamp = lib + ".digest"
+    digest = _digest([src, hdr], "jit-v1")
+    if (not force and os.path.exists(lib) and os.path.exists(stamp)
+            and open(stamp).read() == digest):
+        return lib
+    cuda_lib = os.path.join(os.path.dirname(os.path.dirname(NVCC)), "lib64")
+    _run([NVCC, "-O2", "-std=c++17", "-Xcompiler", "-fPIC", "-I" + os.path.join(ROOT, "include"),
+          "-shared", "-o", lib, src, "-lnvrtc", "-lcudart_static", "-ldl", "-lrt", "-lpthread",
+          "-Xlinker", "-rpath", "-Xlinker", cuda_lib])
+    with open(stamp, "w") as fh:
+        fh.write(digest)
+    if verbose:
+        print("built", lib)
+    return lib
+
+
 def build(force=False, strict=True, verbose=False):
     libs = [build_variant("libpystella_b200", [], force, verbose)]
     if strict:
         libs.append(build_variant("libpystella_b200_strict",
                                   ["-fmad=false", "-DPSB_STRICT_FP=1"], force, verbose))
+    libs.append(build_jit(force, verbose))
     return libs
 
 

@@ -1,0 +1,376 @@
+"""
+EXPERIMENTAL (opt-in, ``PSB_JIT=1`` / ``jit=True``): run-time specialisation of
+element-wise statements, the role loopy plays in the reference
+(``pystella/elementwise.py:164-235``).
+
+A list of statements ``assignee = expr`` over :class:`~pystella_b200.Field` s is
+turned into ONE small CUDA C kernel (one thread per lattice site, all statements
+in program order, every array element touched once for reading and once for
+writing), compiled with NVRTC for sm_100a by ``libpystella_b200_jit.so``
+(``include/pystella_b200_jit.h``) and launched through the driver API.  The
+hand-written kernels stay the path for the sectors on the menu; this covers
+arbitrary ``rhs_dict`` / ``ElementWiseMap`` users (non-polynomial potentials,
+custom stencils, extra unknowns).
+
+Everything up to and including NVRTC compilation is exercised without a GPU
+(``tests/test_codegen.py``).
+"""
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from pystella_b200.field import (Call, Field, Power, Product, Quotient, Subscript, Sum,
+                                 Variable, _field_shift, _const_index, is_constant)
+
+__all__ = ["expr_to_c", "KernelSource", "generate_kernel", "JitLibrary", "GenericMap"]
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+MAX_ARRAYS, MAX_SCALARS = 48, 32
+
+_C_FUNCS = {"fabs": "fabs", "abs": "fabs", "sqrt": "sqrt", "exp": "exp", "log": "log",
+            "sin": "sin", "cos": "cos", "tan": "tan", "tanh": "tanh", "sinh": "sinh",
+            "cosh": "cosh"}
+
+
+class _Ref:
+    """One array operand: tensor name, constant outer subscript, stencil shift."""
+
+    def __init__(self, field, subscript, shift):
+        self.field = field
+        self.name = field.name
+        self.subscript = tuple(subscript)
+        self.shift = tuple(shift)
+
+    @property
+    def key(self):
+        return (self.name, self.subscript, self.shift)
+
+    @property
+    def slot_key(self):          # one pointer/halo slot per (array, outer subscript)
+        return (self.name, self.subscript)
+
+
+def _is_array(fld):
+    return isinstance(fld, Field) and len(fld.indices) > 0
+
+
+def _as_ref(e):
+    """-> _Ref if ``e`` denotes an array element, else None."""
+    if isinstance(e, Field) and _is_array(e):
+        sub = e.child.index if isinstance(e.child, Subscript) else ()
+        return _Ref(e, _const_index(sub), _field_shift(e))
+    if isinstance(e, Subscript) and _is_array(e.aggregate):
+        fld = e.aggregate
+        own = fld.child.index if isinstance(fld.child, Subscript) else ()
+        return _Ref(fld, _const_index(tuple(e.index) + tuple(own)), _field_shift(fld))
+    return None
+
+
+def _scalar_name(e):
+    """-> C-safe name if ``e`` is a by-value scalar: a Variable, an index-free Field, or
+    a constant subscript of either (``a[1]`` -> ``a__1``)."""
+    if isinstance(e, Variable):
+        return e.name
+    if isinstance(e, Field) and not _is_array(e) and not isinstance(e.child, Subscript):
+        return e.name
+    if isinstance(e, Subscript):
+        base = e.aggregate
+        if isinstance(base, Variable) or (isinstance(base, Field) and not _is_array(base)
+                                          and not isinstance(base.child, Subscript)):
+            try:
+                idx = _const_index(e.index)
+            except NotImplementedError:
+                return None
+            return base.name + "__" + "_".join(str(i) for i in idx)
+    return None
+
+
+def _lit(x):
+    if isinstance(x, (bool, np.bool_)):
+        x = int(x)
+    if isinstance(x, (int, np.integer)):
+        return f"(T)({int(x)})"
+    return f"(T)({float(x):.17g})"
+
+
+def expr_to_c(e, leaf):
+    """
+    C expression (type ``T``) for ``e``; ``leaf(node)`` must return the C name of
+    array elements / scalars / temporaries.  Small non-negative integer powers
+    become repeated products (what a code generator emits, and the association
+    order of the hand-written kernels); other powers use ``pow``.
+    """
+    if is_constant(e):
+        return _lit(e)
+    name = leaf(e)
+    if name is not None:
+        return name
+    if isinstance(e, Sum):
+        return "(" + " + ".join(expr_to_c(c, leaf) for c in e.children) + ")"
+    if isinstance(e, Product):
+        return "(" + " * ".join(expr_to_c(c, leaf) for c in e.children) + ")"
+    if isinstance(e, Quotient):
+        return f"({expr_to_c(e.numerator, leaf)} / {expr_to_c(e.denominator, leaf)})"
+    if isinstance(e, Power):
+        base = expr_to_c(e.base, leaf)
+        ex = e.exponent
+        if is_constant(ex) and float(ex).is_integer() and 0 <= int(ex) <= 8:
+            n = int(ex)
+            return "(T)(1)" if n == 0 else "(" + " * ".join([base] * n) + ")"
+        if is_constant(ex) and float(ex).is_integer() and -8 <= int(ex) < 0:
+            n = -int(ex)
+            return "((T)(1) / (" + " * ".join([base] * n) + "))"
+        return f"pow({base}, {expr_to_c(ex, leaf)})"
+    if isinstance(e, Call):
+        fn = _C_FUNCS.get(getattr(e.function, "name", None))
+        if fn is None:
+            raise NotImplementedError(f"function {e.function} in generated code")
+        return f"{fn}(" + ", ".join(expr_to_c(p, leaf) for p in e.parameters) + ")"
+    raise NotImplementedError(f"cannot generate code for {type(e).__name__}: {e}")
+
+
+class KernelSource:
+    """Generated source + the binding tables the launcher needs."""
+
+    def __init__(self, source, name, slots, scalars, dtype):
+        self.source = source
+        self.name = name
+        self.slots = slots          # list of (array name, outer subscript, Field)
+        self.scalars = scalars      # list of scalar names
+        self.dtype = dtype
+
+
+def generate_kernel(map_instructions, tmp_instructions=None, dtype="double",
+                    name="psb_generated_map"):
+    """
+    ``map_instructions`` / ``tmp_instructions``: lists of ``(assignee, expr)`` (dicts
+    are accepted).  Temporaries (Variables) are evaluated first, in order; then every
+    map statement in order, later statements seeing earlier assignments
+    (``elementwise.py:173-203``).
+    """
+    def as_list(x):
+        if x is None:
+            return []
+        return list(x.items()) if isinstance(x, dict) else list(x)
+
+    tmps, maps = as_list(tmp_instructions), as_list(map_instructions)
+    if not maps:
+        raise ValueError("no map instructions")
+
+    slots, slot_index = [], {}
+    refs, scalars = {}, []
+    tmp_names = []
+
+    def slot_of(ref):
+        if ref.slot_key not in slot_index:
+            if len(slots) >= MAX_ARRAYS:
+                raise NotImplementedError("too many distinct arrays in one generated kernel")
+            slot_index[ref.slot_key] = len(slots)
+            slots.append((ref.name, ref.subscript, ref.field))
+        return slot_index[ref.slot_key]
+
+    def local_of(ref):
+        if ref.key not in refs:
+            refs[ref.key] = dict(ref=ref, slot=slot_of(ref), var=f"a{len(refs)}",
+                                 read=False, written=False)
+        return refs[ref.key]
+
+    def leaf(node):
+        ref = _as_ref(node)
+        if ref is not None:
+            info = local_of(ref)
+            if not info["written"]:
+                info["read"] = True
+            return info["var"]
+        sname = _scalar_name(node)
+        if sname is not None:
+            if sname in tmp_names:
+                return f"t_{sname}"
+            if sname not in scalars:
+                if len(scalars) >= MAX_SCALARS:
+                    raise NotImplementedError("too many scalars in one generated kernel")
+                scalars.append(sname)
+            return f"s_{sname}"
+        return None
+
+    body = []
+    for lhs, rhs in tmps:
+        tname = _scalar_name(lhs)
+        if tname is None:
+            raise NotImplementedError("temporaries must be plain variables")
+        body.append(f"  const T t_{tname} = {expr_to_c(rhs, leaf)};")
+        tmp_names.append(tname)
+    for lhs, rhs in maps:
+        ref = _as_ref(lhs)
+        if ref is None:
+            raise ValueError("map assignees must be Fields (array elements)")
+        if any(ref.shift):
+            raise NotImplementedError("assignment to a shifted array element")
+        code = expr_to_c(rhs, leaf)
+        info = local_of(ref)
+        body.append(f"  {info['var']} = {code};")
+        info["written"] = True
+    # a shifted read of an array that is also written would see a mix of old and new
+    written = {info["ref"].slot_key for info in refs.values() if info["written"]}
+    for info in refs.values():
+        if any(info["ref"].shift) and info["ref"].slot_key in written:
+            raise NotImplementedError(
+                f"stencil read of '{info['ref'].name}', which the same kernel writes "
+                "(evaluate the stencil into a separate array first)")
+
+    lines = [
+        "// generated by pystella_b200.codegen -- do not edit",
+        f"typedef {dtype} T;",
+        "struct psb_jit_args {",
+        f"  void* arrays[{MAX_ARRAYS}]; int halos[{MAX_ARRAYS}];",
+        f"  double scalars[{MAX_SCALARS}]; long long Nx, Ny, Nz;",
+        "};",
+        "#define IDX(h, si, sj, sk) ((((long long)(i + (h) + (si))) * (Ny + 2 * (h)) + "
+        "(j + (h) + (sj))) * (Nz + 2 * (h)) + (k + (h) + (sk)))",
+        f'extern "C" __global__ void __launch_bounds__(256) {name}(const psb_jit_args args) {{',
+        "  const long long Ny = args.Ny, Nz = args.Nz;",
+        "  const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;",
+        "  const long long j = (long long)blockIdx.y * blockDim.y + threadIdx.y;",
+        "  const long long i = blockIdx.z;",
+        "  if (k >= Nz || j >= Ny || i >= args.Nx) return;",
+    ]
+    for n, sname in enumerate(scalars):
+        lines.append(f"  const T s_{sname} = (T)args.scalars[{n}];")
+    for info in refs.values():
+        s, (si, sj, sk) = info["slot"], info["ref"].shift
+        addr = f"((T*)args.arrays[{s}])[IDX(args.halos[{s}], {si}, {sj}, {sk})]"
+        info["addr"] = addr
+        if info["read"]:
+            lines.append(f"  T {info['var']} = {addr};")
+        else:
+            lines.append(f"  T {info['var']};")
+    lines += body
+    for info in refs.values():
+        if info["written"]:
+            lines.append(f"  {info['addr']} = {info['var']};")
+    lines.append("}")
+    return KernelSource("\n".join(lines) + "\n", name, slots, scalars, dtype)
+
+
+# ---------------------------------------------------------------------------
+# runtime
+# ---------------------------------------------------------------------------
+
+class JitArgs(C.Structure):
+    _fields_ = [("arrays", C.c_void_p * MAX_ARRAYS), ("halos", C.c_int32 * MAX_ARRAYS),
+                ("scalars", C.c_double * MAX_SCALARS),
+                ("Nx", C.c_int64), ("Ny", C.c_int64), ("Nz", C.c_int64)]
+
+
+class JitLibrary:
+    """ctypes binding of ``libpystella_b200_jit.so``."""
+
+    _lib = None
+
+    @classmethod
+    def get(cls):
+        if cls._lib is None:
+            from pystella_b200._lib import PsbError
+            path = os.path.join(HERE, "_C", "libpystella_b200_jit.so")
+            if not os.path.exists(path):
+                raise PsbError(f"{path} not found: python -m pystella_b200.build")
+            lib = C.CDLL(path)
+            lib.psb_jit_compile.restype = C.c_int64
+            lib.psb_jit_compile.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p]
+            lib.psb_jit_last_log.restype = C.c_char_p
+            lib.psb_jit_cubin_size.restype = C.c_size_t
+            lib.psb_jit_cubin_size.argtypes = [C.c_int64]
+            lib.psb_jit_launch.restype = C.c_int
+            lib.psb_jit_launch.argtypes = [C.c_int64, C.POINTER(JitArgs)] + [C.c_uint] * 6 \
+                + [C.c_void_p]
+            lib.psb_jit_release.restype = C.c_int
+            lib.psb_jit_release.argtypes = [C.c_int64]
+            cls._lib = lib
+        return cls._lib
+
+    @classmethod
+    def compile(cls, ksrc, arch="sm_100a"):
+        from pystella_b200._lib import PsbError
+        lib = cls.get()
+        h = lib.psb_jit_compile(ksrc.source.encode(), ksrc.name.encode(), arch.encode())
+        if h == 0:
+            raise PsbError("NVRTC compilation of a generated kernel failed:\n"
+                           + lib.psb_jit_last_log().decode(errors="replace")
+                           + "\n--- source ---\n" + ksrc.source)
+        return h
+
+
+class GenericMap:
+    """
+    A compiled element-wise map: the run-time generated counterpart of
+    ``pystella.ElementWiseMap`` (``elementwise.py:237-353``).  Call with the arrays
+    and scalars by keyword.
+    """
+
+    def __init__(self, map_instructions, tmp_instructions=None, dtype="float64",
+                 halo_shape=None, rank_shape=None):
+        self.dtype = np.dtype(dtype)
+        ctype = {"float64": "double", "float32": "float"}[self.dtype.name]
+        self.ksrc = generate_kernel(map_instructions, tmp_instructions, ctype)
+        self.halo_shape = halo_shape
+        self.rank_shape = tuple(rank_shape) if rank_shape is not None else None
+        self._handle = None
+
+    def _halo_of(self, field):
+        from pystella_b200.field import evaluate
+        off = field.base_offset[0] if field.base_offset else 0
+        if is_constant(off):
+            return int(off)
+        if self.halo_shape is None:
+            raise ValueError("pass halo_shape= for arrays with a symbolic offset")
+        h = self.halo_shape if not isinstance(self.halo_shape, (tuple, list)) \
+            else self.halo_shape[0]
+        return int(evaluate(off, {"h": h, "hx": h, "hy": h, "hz": h}))
+
+    def __call__(self, queue=None, filter_args=False, **kwargs):
+        import torch
+        from pystella_b200 import _lib
+        if self._handle is None:
+            self._handle = JitLibrary.compile(self.ksrc)
+        args = JitArgs()
+        shape = self.rank_shape
+        want = getattr(torch, self.dtype.name)
+        for n, (name, sub, field) in enumerate(self.ksrc.slots):
+            if name not in kwargs:
+                raise TypeError(f"missing array argument '{name}'")
+            t = _lib.require_cuda_tensor(kwargs[name], name)
+            if t.dtype != want:
+                raise ValueError(f"'{name}' has dtype {t.dtype}; this map was built for "
+                                 f"{self.dtype.name}")
+            view = t[sub] if sub else t
+            if view.dim() != 3:
+                raise ValueError(f"'{name}{list(sub)}' is not a 3-D array")
+            h = self._halo_of(field)
+            this = tuple(s - 2 * h for s in view.shape)
+            if shape is None:
+                shape = this
+            elif this != tuple(shape):
+                raise ValueError(f"'{name}' has rank shape {this}, expected {tuple(shape)}")
+            args.arrays[n] = view.data_ptr()
+            args.halos[n] = h
+        for n, sname in enumerate(self.ksrc.scalars):
+            base, _, idx = sname.partition("__")
+            if base not in kwargs:
+                raise TypeError(f"missing scalar argument '{base}'")
+            v = kwargs[base]
+            v = v.cpu().numpy() if isinstance(v, torch.Tensor) else v
+            v = np.asarray(v)
+            if idx:
+                v = v[tuple(int(i) for i in idx.split("_"))]
+            args.scalars[n] = float(v.reshape(-1)[0])
+        args.Nx, args.Ny, args.Nz = shape
+        lib = JitLibrary.get()
+        rc = lib.psb_jit_launch(self._handle, C.byref(args), (shape[2] + 63) // 64,
+                                (shape[1] + 3) // 4, shape[0], 64, 4, 1,
+                                _lib.stream_ptr(queue))
+        if rc != 0:
+            raise _lib.PsbError("launch of a generated kernel failed: "
+                                + lib.psb_jit_last_log().decode(errors="replace"))
+        return None, {}

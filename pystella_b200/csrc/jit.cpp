@@ -1,0 +1,162 @@
+// NVRTC + driver-API runtime for generated element-wise kernels (EXPERIMENTAL).
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <nvrtc.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "pystella_b200_jit.h"
+
+namespace {
+
+struct Entry {
+  std::string cubin;
+  std::string name;
+  CUmodule mod = nullptr;
+  CUfunction fn = nullptr;
+  bool loaded = false;
+  bool live = false;
+};
+
+std::vector<Entry> g_entries;
+std::mutex g_mutex;
+thread_local std::string g_log;
+
+template <typename F> F driver(const char* sym) {
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint(sym, &p, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess)
+    return nullptr;
+  return reinterpret_cast<F>(p);
+}
+
+typedef CUresult (*ModuleLoadData)(CUmodule*, const void*);
+typedef CUresult (*ModuleGetFunction)(CUfunction*, CUmodule, const char*);
+typedef CUresult (*ModuleUnload)(CUmodule);
+typedef CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned,
+                                 unsigned, unsigned, CUstream, void**, void**);
+
+}  // namespace
+
+extern "C" const char* psb_jit_last_log(void) { return g_log.c_str(); }
+
+extern "C" int64_t psb_jit_compile(const char* source, const char* kernel_name,
+                                   const char* arch) {
+  g_log.clear();
+  if (!source || !kernel_name) {
+    g_log = "psb_jit_compile: null source / kernel name";
+    return 0;
+  }
+  nvrtcProgram prog;
+  if (nvrtcCreateProgram(&prog, source, "psb_generated.cu", 0, nullptr, nullptr) !=
+      NVRTC_SUCCESS) {
+    g_log = "nvrtcCreateProgram failed";
+    return 0;
+  }
+  std::string archopt = std::string("--gpu-architecture=") + (arch ? arch : "sm_100a");
+  const char* opts[] = {archopt.c_str(), "--std=c++17", "-default-device",
+                        "--fmad=true"};
+  nvrtcResult rc = nvrtcCompileProgram(prog, 4, opts);
+  size_t logsz = 0;
+  nvrtcGetProgramLogSize(prog, &logsz);
+  if (logsz > 1) {
+    g_log.resize(logsz);
+    nvrtcGetProgramLog(prog, &g_log[0]);
+  }
+  if (rc != NVRTC_SUCCESS) {
+    g_log = std::string("NVRTC: ") + nvrtcGetErrorString(rc) + "\n" + g_log;
+    nvrtcDestroyProgram(&prog);
+    return 0;
+  }
+  size_t sz = 0;
+  if (nvrtcGetCUBINSize(prog, &sz) != NVRTC_SUCCESS || sz == 0) {
+    g_log = "NVRTC produced no cubin (is the architecture a real one, e.g. sm_100a?)";
+    nvrtcDestroyProgram(&prog);
+    return 0;
+  }
+  Entry e;
+  e.cubin.resize(sz);
+  nvrtcGetCUBIN(prog, &e.cubin[0]);
+  nvrtcDestroyProgram(&prog);
+  e.name = kernel_name;
+  e.live = true;
+  std::lock_guard<std::mutex> lock(g_mutex);
+  g_entries.push_back(std::move(e));
+  return (int64_t)g_entries.size();
+}
+
+extern "C" size_t psb_jit_cubin_size(int64_t handle) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  if (handle < 1 || handle > (int64_t)g_entries.size() || !g_entries[handle - 1].live) return 0;
+  return g_entries[handle - 1].cubin.size();
+}
+
+extern "C" int psb_jit_launch(int64_t handle, const psb_jit_args* args, unsigned gx,
+                              unsigned gy, unsigned gz, unsigned bx, unsigned by, unsigned bz,
+                              void* stream) {
+  g_log.clear();
+  Entry* e = nullptr;
+  {
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (handle < 1 || handle > (int64_t)g_entries.size() || !g_entries[handle - 1].live) {
+      g_log = "psb_jit_launch: bad handle";
+      return 1;
+    }
+    e = &g_entries[handle - 1];
+    if (!e->loaded) {
+      cudaFree(0);  // make sure the primary context exists
+      auto load = driver<ModuleLoadData>("cuModuleLoadData");
+      auto getf = driver<ModuleGetFunction>("cuModuleGetFunction");
+      if (!load || !getf) {
+        g_log = "psb_jit_launch: driver entry points unavailable";
+        return 2;
+      }
+      CUresult r = load(&e->mod, e->cubin.data());
+      if (r != CUDA_SUCCESS) {
+        g_log = "cuModuleLoadData failed (" + std::to_string((int)r) + ")";
+        return 2;
+      }
+      r = getf(&e->fn, e->mod, e->name.c_str());
+      if (r != CUDA_SUCCESS) {
+        g_log = "cuModuleGetFunction(" + e->name + ") failed (" + std::to_string((int)r) + ")";
+        return 2;
+      }
+      e->loaded = true;
+    }
+  }
+  if (!args) {
+    g_log = "psb_jit_launch: null args";
+    return 1;
+  }
+  static LaunchKernel launch = driver<LaunchKernel>("cuLaunchKernel");
+  if (!launch) {
+    g_log = "psb_jit_launch: cuLaunchKernel unavailable";
+    return 2;
+  }
+  psb_jit_args copy = *args;
+  void* params[] = {&copy};
+  CUresult r = launch(e->fn, gx, gy, gz, bx, by, bz, 0, static_cast<CUstream>(stream), params,
+                      nullptr);
+  if (r != CUDA_SUCCESS) {
+    g_log = "cuLaunchKernel failed (" + std::to_string((int)r) + ")";
+    return 2;
+  }
+  return 0;
+}
+
+extern "C" int psb_jit_release(int64_t handle) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  if (handle < 1 || handle > (int64_t)g_entries.size() || !g_entries[handle - 1].live) return 1;
+  Entry& e = g_entries[handle - 1];
+  if (e.loaded) {
+    auto unload = driver<ModuleUnload>("cuModuleUnload");
+    if (unload) unload(e.mod);
+  }
+  e = Entry();
+  return 0;
+}

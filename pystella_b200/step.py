@@ -38,13 +38,46 @@ __all__ = [
 ]
 
 
+def jit_enabled(flag=None):
+    """The experimental NVRTC path is opt-in: ``jit=True`` or ``PSB_JIT=1``."""
+    import os
+    return bool(flag) or os.environ.get("PSB_JIT", "0") == "1"
+
+
 class ElementWiseMap:
     """
-    Marker for "one element-wise kernel per stage" (``pystella/elementwise.py:81-361``).
-    On device arrays the stage is the hand-written scalar-sector kernel; there is
-    no run-time code generator in this build, so systems outside the kernel menu
-    raise :class:`NotImplementedError` with the reason.
+    "One element-wise kernel per stage" (``pystella/elementwise.py:81-361``).
+
+    As a ``MapKernel`` *class* it selects the element-wise stage of a stepper: the
+    hand-written scalar-sector / tensor-sector kernels for the systems on the menu.
+    Instantiated with statements (``ElementWiseMap(map_instructions,
+    tmp_instructions=..., halo_shape=..., rank_shape=..., dtype=...)``) it is the
+    reference's generic map; that needs the EXPERIMENTAL run-time generated kernels of
+    :mod:`pystella_b200.codegen` (opt-in: ``jit=True`` or ``PSB_JIT=1``) -- without
+    them, systems outside the menu raise :class:`NotImplementedError` with the reason.
     """
+
+    def __init__(self, map_instructions=None, **kwargs):
+        self._generic = None
+        if map_instructions is None:
+            return
+        if not jit_enabled(kwargs.pop("jit", None)):
+            raise NotImplementedError(
+                "generic ElementWiseMap needs the experimental generated kernels: pass "
+                "jit=True or set PSB_JIT=1 (the hand-written kernels cover ScalarSector, "
+                "TensorPerturbationSector and the wave equation)")
+        from pystella_b200.codegen import GenericMap
+        self._generic = GenericMap(
+            map_instructions, kwargs.pop("tmp_instructions", None),
+            dtype=kwargs.pop("dtype", None) or "float64",
+            halo_shape=kwargs.pop("halo_shape", None),
+            rank_shape=kwargs.pop("rank_shape", None))
+
+    def __call__(self, queue=None, filter_args=False, **kwargs):
+        """-> ``(None, {})`` like ``(evt, outputs)`` of the reference."""
+        if self._generic is None:
+            raise TypeError("this ElementWiseMap holds no statements")
+        return self._generic(queue, filter_args=filter_args, **kwargs)
 
 
 class FusedStencilStage(ElementWiseMap):
@@ -328,6 +361,8 @@ class Stepper:
         self.dx = kwargs.pop("dx", None)
         self.decomp = kwargs.pop("decomp", None)
         self.strict_fp = kwargs.pop("strict_fp", False)
+        self.jit = kwargs.pop("jit", None)
+        self._jit_maps = {}
         #: fused stage also accumulates the energy sums of its input state
         self.fused_energy = kwargs.pop("energy", False)
         self.energy_partials = None
@@ -472,10 +507,47 @@ class LowStorageRKStepper(Stepper):
         return None
 
     # -- device ---------------------------------------------------------------
+    def _jit_stage(self, stage, queue, kwargs):
+        """
+        EXPERIMENTAL: the reference's own construction (``step.py:473-491``) -- right-hand
+        sides into temporaries, then ``k = A k + dt rhs ; u = u + B k`` per unknown --
+        handed to the run-time code generator instead of loopy.
+        """
+        from pystella_b200.codegen import GenericMap
+        from pystella_b200.field import var
+        if stage not in self._jit_maps:
+            tmps, maps = [], []
+            for i, (key, val) in enumerate(self.rhs_dict.items()):
+                tmps.append((var(gen_tmp_name(key, suffix=f"_rhs_{i}")), val))
+            for i, key in enumerate(self.rhs_dict):
+                fld, sub = _unknown_parts(key)
+                twin = Field(gen_tmp_name(fld), offset=fld.offset, shape=fld.shape,
+                             indices=fld.indices)
+                k = twin[sub] if sub else twin
+                rhs = var(gen_tmp_name(key, suffix=f"_rhs_{i}"))
+                maps.append((k, self._A[stage] * k + var("dt") * rhs))
+                maps.append((key, key + self._B[stage] * k))
+            some = kwargs[next(iter(self.dof_names))]
+            dtype = str(some.dtype).replace("torch.", "")
+            self._jit_maps[stage] = GenericMap(maps, tmps, dtype=dtype,
+                                               halo_shape=self.halo_shape,
+                                               rank_shape=self.rank_shape)
+        call = dict(kwargs)
+        call.update(self.tmp_arrays)
+        call["dt"] = self._resolve_dt(kwargs)
+        self._jit_maps[stage](queue, **call)
+        return None
+
     def _device_stage(self, stage, queue, kwargs):
+        try:
+            systems = self.systems
+        except NotImplementedError:
+            if not jit_enabled(self.jit) or self.fused:
+                raise
+            return self._jit_stage(stage, queue, kwargs)
         dt = self._resolve_dt(kwargs)
         A, B = self._A[stage], self._B[stage]
-        for system in self.systems:
+        for system in systems:
             system_stage = getattr(system, "run_stage", None)
             if system_stage is not None:       # tensor sector etc.
                 system_stage(self, stage, queue, kwargs, dt, A, B)

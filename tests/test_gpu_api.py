@@ -568,3 +568,66 @@ def test_classical_rk_wave_equation_device(name):
 def test_fused_gw_sector_experimental(dtype, tol):
     """Same check as test_two_scalars_plus_gw_sector, with lap_hij / dfdx never formed."""
     test_two_scalars_plus_gw_sector(True, dtype, tol)
+
+
+_JIT = pytest.mark.skipif(__import__("os").environ.get("PSB_JIT", "0") != "1",
+                          reason="experimental run-time generated kernels: opt-in (PSB_JIT=1)")
+
+
+@_JIT
+@pytest.mark.parametrize("dtype,rtol", [(np.float64, 5e-14), (np.float32, 1e-5)])
+def test_generic_elementwise_map_experimental(dtype, rtol):
+    """test/test_elementwise.py:36-90: temporaries first, then statements in order."""
+    from pystella_b200.field import var
+    rng = np.random.default_rng(1)
+    N = (16, 12, 40)
+    a, b = var("a"), var("b")
+    x, y, z = ps.Field("x"), ps.Field("y"), ps.Field("z")
+    tmp_dict = {a[0]: x + 2, a[1]: 2 + x * y, b: x + y / 2}
+    map_dict = {x: a[0] * y**2 * x + a[1] * b, z: z + a[1] * b}
+    ew_map = ps.ElementWiseMap(map_dict, tmp_instructions=tmp_dict, dtype=dtype, jit=True)
+    xh, yh, zh = (rng.random(N).astype(dtype) for _ in range(3))
+    xd, yd, zd = to_dev(xh), to_dev(yh), to_dev(zh)
+    ew_map(None, x=xd, y=yd, z=zd)
+    a0, a1, bb = xh + 2, 2 + xh * yh, xh + yh / 2
+    x_true, z_true = a0 * yh**2 * xh + a1 * bb, zh + a1 * bb
+    assert O.get_errs(x_true, xd.cpu().numpy())[0] < rtol
+    assert O.get_errs(z_true, zd.cpu().numpy())[0] < rtol
+    assert torch.equal(yd, to_dev(yh))
+    single = ps.ElementWiseMap({x: y + z}, dtype=dtype, jit=True)
+    single(None, x=xd, y=yd, z=zd)
+    assert O.get_errs(yh + z_true, xd.cpu().numpy())[0] < rtol
+
+
+@_JIT
+def test_jit_stepper_experimental():
+    """A system outside the menu (sine-Gordon force) through the generated stage, and
+    the wave equation through it == the hand-written element-wise kernel."""
+    from pystella_b200.field import var
+    rng = np.random.default_rng(2)
+    N, h = (16, 16, 32), 2
+    dx = (0.2,) * 3
+    dt = 0.01
+    pad = tuple(n + 2 * h for n in N)
+    f0, d0 = rng.random(pad), rng.random(pad)
+    decomp = ps.DomainDecomposition((1, 1, 1), h, N)
+    derivs = ps.FiniteDifferencer(decomp, h, dx)
+    f_ = ps.DynamicField("f", offset="h")
+    sin = var("sin")
+    stepper = ps.LowStorageRK54({f_: f_.dot, f_.dot: f_.lap - sin(f_)}, dt=dt, halo_shape=h,
+                                jit=True)
+    f, dfdt = to_dev(f0), to_dev(d0)
+    lap_f = torch.zeros(N, dtype=torch.float64, device="cuda")
+    fr, dr = f0.copy(), d0.copy()
+    kf, kd = np.zeros_like(fr), np.zeros_like(fr)
+    A, B, _ = O.LSRK_TABLES["LowStorageRK54"]
+    for s in range(5):
+        derivs(None, fx=f, lap=lap_f)
+        stepper(s, f=f, dfdt=dfdt, lap_f=lap_f)
+        O.share_halos(fr, h)
+        lap = O.laplacian(fr, h, dx)
+        fi, di = O.interior(fr, h), O.interior(dr, h)
+        rhs = [np.array(di), lap - np.sin(fi)]
+        O.lsrk_stage(A[s], B[s], dt, [fi, di], [O.interior(kf, h), O.interior(kd, h)], rhs)
+    assert scale_err(O.interior(f.cpu().numpy(), h), O.interior(fr, h)) < 1e-12
+    assert scale_err(O.interior(dfdt.cpu().numpy(), h), O.interior(dr, h)) < 1e-12
