@@ -184,7 +184,7 @@ typedef struct psb_tensor_stage_args {
 } psb_tensor_stage_args;
 int psb_tensor_stage_unfused(const psb_tensor_stage_args* args, void* stream);
 
-/* EXPERIMENTAL (opt-in, not validated on hardware in round 1): the same stage with
+/* EXPERIMENTAL (opt-in; parity-green on B200, not yet timed): the same stage with
  * lap(hij_c) and the gradients of the source fields evaluated in-kernel from `hij_in`
  * and `src` (the scalar fields' OLD values, padded, valid face halos), in the TMA
  * pipeline of psb_scalar_stage_fused; hij ping-pongs into `hij_out`. */

@@ -1,5 +1,6 @@
-// EXPERIMENTAL (opt-in, PSB_FUSED_GW=1; not yet validated on hardware at the time of
-// writing -- the validated tensor-sector path is tensor_stage.cu).
+// EXPERIMENTAL (opt-in, PSB_FUSED_GW=1): parity-green against the oracle on B200
+// (tests/test_gpu_api.py::test_fused_gw_sector_experimental) but not yet timed or
+// profiled -- the default tensor-sector path is the element-wise tensor_stage.cu.
 //
 // Fused stage of the tensor-perturbation sector in the warp-specialised TMA pipeline
 // of fused_stage_ws.cuh: lap(hij_c) and the gradient of the source fields are

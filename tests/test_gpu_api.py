@@ -562,19 +562,14 @@ def test_classical_rk_wave_equation_device(name):
         assert scale_err(O.interior(got[0].cpu().numpy(), h), O.interior(ref[0], h)) < 1e-13
 
 
-@pytest.mark.skipif(__import__("os").environ.get("PSB_FUSED_GW", "0") != "1",
-                    reason="experimental fused tensor-sector kernel: opt-in (PSB_FUSED_GW=1)")
 @pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-12), (np.float32, 3e-5)])
-def test_fused_gw_sector_experimental(dtype, tol):
-    """Same check as test_two_scalars_plus_gw_sector, with lap_hij / dfdx never formed."""
+def test_fused_gw_sector_experimental(dtype, tol, monkeypatch):
+    """Same check as test_two_scalars_plus_gw_sector with the opt-in fused tensor stage
+    (PSB_FUSED_GW=1): lap_hij / dfdx are never formed, the stencils run in-kernel."""
+    monkeypatch.setenv("PSB_FUSED_GW", "1")
     test_two_scalars_plus_gw_sector(True, dtype, tol)
 
 
-_JIT = pytest.mark.skipif(__import__("os").environ.get("PSB_JIT", "0") != "1",
-                          reason="experimental run-time generated kernels: opt-in (PSB_JIT=1)")
-
-
-@_JIT
 @pytest.mark.parametrize("dtype,rtol", [(np.float64, 5e-14), (np.float32, 1e-5)])
 def test_generic_elementwise_map_experimental(dtype, rtol):
     """test/test_elementwise.py:36-90: temporaries first, then statements in order."""
@@ -599,7 +594,6 @@ def test_generic_elementwise_map_experimental(dtype, rtol):
     assert O.get_errs(yh + z_true, xd.cpu().numpy())[0] < rtol
 
 
-@_JIT
 def test_jit_stepper_experimental():
     """A system outside the menu (sine-Gordon force) through the generated stage, and
     the wave equation through it == the hand-written element-wise kernel."""
