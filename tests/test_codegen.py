@@ -137,3 +137,96 @@ def test_nvrtc_compiles_generated_kernels():
     with pytest.raises(ps.PsbError) as err:
         codegen.JitLibrary.compile(bad)
     assert "undeclared" in str(err.value)
+
+
+def _run_generated_on_host(ksrc, arrays, halos, scalars, shape):
+    """
+    Execute a generated kernel on the HOST: the CUDA source is turned into plain C by
+    replacing the thread-index prologue with loop indices (test-only transformation), so
+    that indexing, halos, shifts and statement order can be checked against NumPy here.
+    """
+    src = ksrc.source
+    head = f'extern "C" __global__ void __launch_bounds__(256) {ksrc.name}(const psb_jit_args args) {{'
+    assert head in src
+    src = src.replace(head, "static void site(const psb_jit_args args, long long i, "
+                            "long long j, long long k) {")
+    for line in ("  const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;\n",
+                 "  const long long j = (long long)blockIdx.y * blockDim.y + threadIdx.y;\n",
+                 "  const long long i = blockIdx.z;\n"):
+        assert line in src
+        src = src.replace(line, "")
+    src = src.replace("struct psb_jit_args {", "typedef struct {").replace(
+        "  double scalars[32]; long long Nx, Ny, Nz;\n};",
+        "  double scalars[32]; long long Nx, Ny, Nz;\n} psb_jit_args;")
+    src = "#include <math.h>\n" + src + (
+        "void run(const psb_jit_args* a) {\n"
+        "  for (long long i = 0; i < a->Nx; ++i) for (long long j = 0; j < a->Ny; ++j)\n"
+        "    for (long long k = 0; k < a->Nz; ++k) site(*a, i, j, k);\n}\n")
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, "k.c")
+        so = os.path.join(d, "k.so")
+        open(c, "w").write(src)
+        subprocess.check_call(["gcc", "-O1", "-ffp-contract=off", "-shared", "-fPIC", c, "-o",
+                               so, "-lm"])
+        lib = ctypes.CDLL(so)
+        args = codegen.JitArgs()
+        for n, (name, sub, _) in enumerate(ksrc.slots):
+            view = arrays[name][sub] if sub else arrays[name]
+            assert view.flags["C_CONTIGUOUS"]
+            args.arrays[n] = view.ctypes.data
+            args.halos[n] = halos[name]
+        for n, s in enumerate(ksrc.scalars):
+            args.scalars[n] = scalars[s]
+        args.Nx, args.Ny, args.Nz = shape
+        lib.run(ctypes.byref(args))
+
+
+def test_generated_lsrk_stage_semantics_on_host():
+    """The generated stage == the oracle's scalar-sector stage (two fields, potential)."""
+    import oracle as O
+    rng = np.random.default_rng(3)
+    N, h = (6, 5, 8), 2
+    pad = tuple(n + 2 * h for n in N)
+    f = rng.random((2,) + pad); d = rng.random((2,) + pad)
+    kf = rng.random((2,) + pad); kd = rng.random((2,) + pad)
+    lap = rng.random((2,) + N)
+    terms = [(0.5, (2, 0)), (0.5, (0, 2)), (0.5, (2, 2))]
+    sec = ps.ScalarSector(2, potential=lambda g: g[0]**2 / 2 + g[1]**2 / 2
+                          + g[0]**2 * g[1]**2 / 2)
+    A, B, dt, a, H = -0.4178904745, 0.3792103129999, 0.01, 1.3, 0.2
+    maps, tmps = _lsrk_statements(sec.rhs_dict, A, B)
+    ksrc = codegen.generate_kernel(maps, tmps)
+    arrays = {"f": f.copy(), "dfdt": d.copy(), "_f_tmp": kf.copy(), "_dfdt_tmp": kd.copy(),
+              "lap_f": lap}
+    halos = {"f": h, "dfdt": h, "_f_tmp": h, "_dfdt_tmp": h, "lap_f": 0}
+    _run_generated_on_host(ksrc, arrays, halos, {"dt": dt, "a": a, "hubble": H}, N)
+
+    fr, dr, kfr, kdr = f.copy(), d.copy(), kf.copy(), kd.copy()
+    fi = [O.interior(fr[i], h) for i in range(2)]
+    di = [O.interior(dr[i], h) for i in range(2)]
+    rhs = [np.array(r) for r in O.scalar_rhs(fi, di, [lap[0], lap[1]], a, H, terms)]
+    unk, tmp = [], []
+    for i in range(2):
+        unk += [fi[i], di[i]]
+        tmp += [O.interior(kfr[i], h), O.interior(kdr[i], h)]
+    O.lsrk_stage(A, B, dt, unk, tmp, rhs)
+    for got, ref in ((arrays["f"], fr), (arrays["dfdt"], dr), (arrays["_f_tmp"], kfr),
+                     (arrays["_dfdt_tmp"], kdr)):
+        assert np.allclose(got, ref, rtol=1e-14, atol=1e-15)     # halos untouched too
+
+
+def test_generated_stencil_map_on_host():
+    """Shifted reads (custom stencils) index correctly: == the oracle's lap / gradient."""
+    import oracle as O
+    rng = np.random.default_rng(4)
+    N, h = (5, 6, 7), 2
+    dx = (0.1, 0.2, 0.3)
+    y = ps.Field("y", offset="h")
+    lap_expr = sum(ps.SecondCenteredDifference(h)(y, d + 1) * dx[d]**-2 for d in range(3))
+    pdz_expr = ps.FirstCenteredDifference(h)(y, 3) * (1 / dx[2])
+    ksrc = codegen.generate_kernel([(ps.Field("lap"), lap_expr), (ps.Field("pdz"), pdz_expr)])
+    yy = rng.random(tuple(n + 2 * h for n in N))
+    arrays = {"y": yy, "lap": np.zeros(N), "pdz": np.zeros(N)}
+    _run_generated_on_host(ksrc, arrays, {"y": h, "lap": 0, "pdz": 0}, {}, N)
+    assert np.allclose(arrays["lap"], O.laplacian(yy, h, dx), rtol=1e-13, atol=1e-10)
+    assert np.allclose(arrays["pdz"], O.partial(yy, h, dx, 2), rtol=1e-13, atol=1e-12)
