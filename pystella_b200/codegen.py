@@ -347,6 +347,8 @@ class GenericMap:
             view = t[sub] if sub else t
             if view.dim() != 3:
                 raise ValueError(f"'{name}{list(sub)}' is not a 3-D array")
+            if not view.is_contiguous():
+                raise ValueError(f"'{name}{list(sub)}' is not contiguous (z fastest)")
             h = self._halo_of(field)
             this = tuple(s - 2 * h for s in view.shape)
             if shape is None:

@@ -135,7 +135,7 @@ class FiniteDifferencer:
     def __init__(self, decomp, halo_shape, dx, stream=False, rank_shape=None,
                  device=None, first_stencil=None, second_stencil=None,
                  gradlap_lsize=None, grad_lsize=None, lap_lsize=None,
-                 strict_fp=False):
+                 strict_fp=False, jit=None, dtype="float64"):
         if not isinstance(halo_shape, (int, np.integer)):
             raise NotImplementedError("halo_shape must currently be an int")
         self.decomp = decomp
@@ -145,20 +145,62 @@ class FiniteDifferencer:
         self.strict_fp = strict_fp
         first = first_stencil or FirstCenteredDifference(self.halo_shape)
         second = second_stencil or SecondCenteredDifference(self.halo_shape)
-        for st, table in ((first, _GRAD), (second, _LAP)):
+        self.first_stencil, self.second_stencil = first, second
+        self._generated = None
+
+        def standard(st, table):
             h = getattr(st, "h", None)
-            if h is None or st.coefs != table.get(h):
+            return h is not None and getattr(st, "coefs", None) == table.get(h)
+
+        if not (standard(first, _GRAD) and standard(second, _LAP) and first.h == second.h):
+            # custom stencils (derivs.py:254-263): callables (f, direction) -> expression
+            from pystella_b200.step import jit_enabled
+            if not jit_enabled(jit):
                 raise NotImplementedError(
-                    "custom stencils need a generated kernel; this build provides the "
+                    "custom stencils need run-time generated kernels (experimental: pass "
+                    "jit=True or set PSB_JIT=1); the hand-written kernels provide the "
                     "centred differences of radius 1..4")
-        if first.h != second.h:
-            raise NotImplementedError("first and second stencils of different radius")
+            self._generated = self._generate_custom(first, second, dtype)
+            self.h = self.halo_shape
+            return
         self.h = first.h
         if self.h > self.halo_shape:
             raise ValueError("stencil radius exceeds halo_shape")
-        self.first_stencil, self.second_stencil = first, second
+
+    def _custom_statements(self, first, second):
+        """The symbolic kernels of the reference (derivs.py:291-312) for arbitrary stencils."""
+        from pystella_b200.field import Field
+        fx = Field("fx", offset="h")
+        pd = {n: first(fx, i + 1) * (1 / dxi)
+              for i, (n, dxi) in enumerate(zip(("pdx", "pdy", "pdz"), self.dx))}
+        lap = 0
+        for i, dxi in enumerate(self.dx):
+            lap = lap + second(fx, i + 1) * dxi**-2
+        return fx, pd, lap
+
+    def _generate_custom(self, first, second, dtype):
+        from pystella_b200.codegen import GenericMap
+        from pystella_b200.field import Field
+        _, pd, lap = self._custom_statements(first, second)
+        kw = dict(dtype=dtype, halo_shape=self.halo_shape)
+        maps = {
+            ("lap",): GenericMap([(Field("lap"), lap)], **kw),
+            ("pdx", "pdy", "pdz"): GenericMap([(Field(n), e) for n, e in pd.items()], **kw),
+            ("lap", "pdx", "pdy", "pdz"): GenericMap(
+                [(Field(n), e) for n, e in pd.items()] + [(Field("lap"), lap)], **kw),
+        }
+        for n, e in pd.items():
+            maps[(n,)] = GenericMap([(Field(n), e)], **kw)
+            maps[(n, "incr")] = GenericMap([(Field("div"), Field("div") + e)], **kw)
+        return maps
 
     def _run(self, queue, fx, **outs):
+        if self._generated is not None:
+            key = tuple(n for n in ("lap", "pdx", "pdy", "pdz") if outs.get(n) is not None)
+            if key not in self._generated:
+                raise ValueError(f"unsupported output combination {key}")
+            self._generated[key](queue, fx=fx, **{n: outs[n] for n in key})
+            return
         _kernels.finite_difference(fx, h=self.h, halo=self.halo_shape, dx=self.dx,
                                    queue=queue, strict=self.strict_fp, **outs)
 
@@ -202,12 +244,12 @@ class FiniteDifferencer:
         for s in slices:
             self.decomp.share_halos(queue, vec[s][0])
             self._run(queue, vec[s][0], pdx=div[s])
-            self.decomp.share_halos(queue, vec[s][1])
-            _kernels.finite_difference(vec[s][1], pdy=div[s], h=self.h,
-                                       halo=self.halo_shape, dx=self.dx, accumulate=True,
-                                       queue=queue, strict=self.strict_fp)
-            self.decomp.share_halos(queue, vec[s][2])
-            _kernels.finite_difference(vec[s][2], pdz=div[s], h=self.h,
-                                       halo=self.halo_shape, dx=self.dx, accumulate=True,
-                                       queue=queue, strict=self.strict_fp)
+            for comp, name in ((1, "pdy"), (2, "pdz")):
+                self.decomp.share_halos(queue, vec[s][comp])
+                if self._generated is not None:
+                    self._generated[(name, "incr")](queue, fx=vec[s][comp], div=div[s])
+                else:
+                    _kernels.finite_difference(vec[s][comp], h=self.h, halo=self.halo_shape,
+                                               dx=self.dx, accumulate=True, queue=queue,
+                                               strict=self.strict_fp, **{name: div[s]})
         return None

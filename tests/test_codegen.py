@@ -230,3 +230,54 @@ def test_generated_stencil_map_on_host():
     _run_generated_on_host(ksrc, arrays, {"y": h, "lap": 0, "pdz": 0}, {}, N)
     assert np.allclose(arrays["lap"], O.laplacian(yy, h, dx), rtol=1e-13, atol=1e-10)
     assert np.allclose(arrays["pdz"], O.partial(yy, h, dx, 2), rtol=1e-13, atol=1e-12)
+
+
+class _OneSided:
+    """A custom (non-centred) first-derivative stencil: (-3f(x) + 4f(x+1) - f(x+2)) / 2."""
+
+    def __call__(self, f, direction):
+        from pystella_b200.derivs import expand_stencil
+        def off(s):
+            o = [0, 0, 0]
+            o[direction - 1] = s
+            return tuple(o)
+        return expand_stencil(f, {off(0): -1.5, off(1): 2.0, off(2): -0.5})
+
+
+def _one_sided_numpy(yy, h, N, axis, dxi):
+    def sl(s):
+        idx = [slice(h, h + n) for n in N]
+        idx[axis] = slice(h + s, h + s + N[axis])
+        return yy[tuple(idx)]
+    return (-1.5 * sl(0) + 2.0 * sl(1) - 0.5 * sl(2)) / dxi
+
+
+def test_custom_stencil_differencer_kernels_on_host():
+    """FiniteDifferencer(first_stencil=custom, jit=True) generates the reference's kernels
+    (derivs.py:254-263, 291-337) from the callable; run them on the host."""
+    import oracle as O
+    rng = np.random.default_rng(5)
+    N, h = (6, 5, 4), 2
+    dx = (0.1, 0.2, 0.3)
+    decomp = ps.DomainDecomposition((1, 1, 1), h, N)
+    with pytest.raises(NotImplementedError, match="custom stencils"):
+        ps.FiniteDifferencer(decomp, h, dx, first_stencil=_OneSided())
+    fd = ps.FiniteDifferencer(decomp, h, dx, first_stencil=_OneSided(), jit=True)
+    yy = rng.random(tuple(n + 2 * h for n in N))
+
+    gm = fd._generated[("lap", "pdx", "pdy", "pdz")]
+    arrays = {"fx": yy, **{n: np.zeros(N) for n in ("lap", "pdx", "pdy", "pdz")}}
+    halos = {"fx": h, "lap": 0, "pdx": 0, "pdy": 0, "pdz": 0}
+    _run_generated_on_host(gm.ksrc, arrays, halos, {}, N)
+    assert np.allclose(arrays["lap"], O.laplacian(yy, h, dx), rtol=1e-13, atol=1e-10)
+    for ax, n in enumerate(("pdx", "pdy", "pdz")):
+        assert np.allclose(arrays[n], _one_sided_numpy(yy, h, N, ax, dx[ax]),
+                           rtol=1e-13, atol=1e-11), n
+
+    # the accumulate kernels of divergence (derivs.py:321-337)
+    gm = fd._generated[("pdy", "incr")]
+    div0 = rng.random(N)
+    arrays = {"fx": yy, "div": div0.copy()}
+    _run_generated_on_host(gm.ksrc, arrays, {"fx": h, "div": 0}, {}, N)
+    assert np.allclose(arrays["div"], div0 + _one_sided_numpy(yy, h, N, 1, dx[1]),
+                       rtol=1e-13, atol=1e-11)

@@ -1,0 +1,51 @@
+"""
+GPU tests written after this round's B200 budget was spent: they exercise code whose
+semantics are verified on the host (tests/test_codegen.py) but which has not yet run on
+hardware.  Sorted last on purpose so that `-x` reaches them after the validated suite.
+"""
+import numpy as np
+import pytest
+
+import oracle as O
+import pystella_b200 as ps
+from helpers import to_dev
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+class OneSided:
+    def __call__(self, f, direction):
+        from pystella_b200.derivs import expand_stencil
+        def off(s):
+            o = [0, 0, 0]
+            o[direction - 1] = s
+            return tuple(o)
+        return expand_stencil(f, {off(0): -1.5, off(1): 2.0, off(2): -0.5})
+
+
+def one_sided(yy, h, N, axis, dxi):
+    def sl(s):
+        idx = [slice(h, h + n) for n in N]
+        idx[axis] = slice(h + s, h + s + N[axis])
+        return yy[tuple(idx)]
+    return (-1.5 * sl(0) + 2.0 * sl(1) - 0.5 * sl(2)) / dxi
+
+
+def test_custom_stencil_differencer():
+    """derivs.py:254-263: user stencils -> generated kernels (experimental JIT path)."""
+    rng = np.random.default_rng(11)
+    N, h = (16, 12, 40), 2
+    dx = (0.1, 0.2, 0.3)
+    decomp = ps.DomainDecomposition((1, 1, 1), h, N)
+    fd = ps.FiniteDifferencer(decomp, h, dx, first_stencil=OneSided(), jit=True)
+    yy = rng.random(tuple(n + 2 * h for n in N))
+    fx = to_dev(yy)
+    lap = torch.zeros(N, dtype=torch.float64, device="cuda")
+    grd = torch.zeros((3,) + N, dtype=torch.float64, device="cuda")
+    fd(None, fx=fx, lap=lap, grd=grd)
+    yw = fx.cpu().numpy()  # halos were shared by the call
+    assert np.allclose(lap.cpu().numpy(), O.laplacian(yw, h, dx), rtol=1e-12, atol=1e-9)
+    for ax in range(3):
+        assert np.allclose(grd[ax].cpu().numpy(), one_sided(yw, h, N, ax, dx[ax]),
+                           rtol=1e-12, atol=1e-10)
