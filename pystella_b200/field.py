@@ -472,6 +472,26 @@ def index_fields(expr, prepend_with=None):
     return _map(expr, fn)
 
 
+def prepend_subscript(expr, prepend_with):
+    """
+    The ``prepend_with`` half of :func:`index_fields` alone: every Field that does not
+    set ``ignore_prepends`` gains the leading subscript, and stays a Field (so that
+    stencil shifts and offsets survive for the code generator).
+    """
+    pre = tuple(prepend_with)
+
+    def fn(e):
+        if isinstance(e, Subscript) and isinstance(e.aggregate, Field):
+            fld = e.aggregate
+            idx = tuple(_map(i, fn) for i in e.index)
+            return Subscript(fld, (() if fld.ignore_prepends else pre) + idx)
+        if isinstance(e, Field):
+            return e if e.ignore_prepends else Subscript(e, pre)
+        return None
+
+    return _map(expr, fn)
+
+
 def _index_child(fld, outer, spatial):
     # prepended + user subscripts, then the child's own subscript, then i, j, k
     child = fld.child

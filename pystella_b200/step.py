@@ -514,19 +514,8 @@ class LowStorageRKStepper(Stepper):
         handed to the run-time code generator instead of loopy.
         """
         from pystella_b200.codegen import GenericMap
-        from pystella_b200.field import var
         if stage not in self._jit_maps:
-            tmps, maps = [], []
-            for i, (key, val) in enumerate(self.rhs_dict.items()):
-                tmps.append((var(gen_tmp_name(key, suffix=f"_rhs_{i}")), val))
-            for i, key in enumerate(self.rhs_dict):
-                fld, sub = _unknown_parts(key)
-                twin = Field(gen_tmp_name(fld), offset=fld.offset, shape=fld.shape,
-                             indices=fld.indices)
-                k = twin[sub] if sub else twin
-                rhs = var(gen_tmp_name(key, suffix=f"_rhs_{i}"))
-                maps.append((k, self._A[stage] * k + var("dt") * rhs))
-                maps.append((key, key + self._B[stage] * k))
+            maps, tmps = self._jit_statements(stage)
             some = kwargs[next(iter(self.dof_names))]
             dtype = str(some.dtype).replace("torch.", "")
             self._jit_maps[stage] = GenericMap(maps, tmps, dtype=dtype,
@@ -537,6 +526,22 @@ class LowStorageRKStepper(Stepper):
         call["dt"] = self._resolve_dt(kwargs)
         self._jit_maps[stage](queue, **call)
         return None
+
+    def _jit_statements(self, stage):
+        """-> (map_instructions, tmp_instructions) of one stage; step.py:473-491."""
+        from pystella_b200.field import var
+        tmps, maps = [], []
+        for i, (key, val) in enumerate(self.rhs_dict.items()):
+            tmps.append((var(gen_tmp_name(key, suffix=f"_rhs_{i}")), val))
+        for i, key in enumerate(self.rhs_dict):
+            fld, sub = _unknown_parts(key)
+            twin = Field(gen_tmp_name(fld), offset=fld.offset, shape=fld.shape,
+                         indices=fld.indices)
+            k = twin[sub] if sub else twin
+            rhs = var(gen_tmp_name(key, suffix=f"_rhs_{i}"))
+            maps.append((k, self._A[stage] * k + var("dt") * rhs))
+            maps.append((key, key + self._B[stage] * k))
+        return maps, tmps
 
     def _device_stage(self, stage, queue, kwargs):
         try:
@@ -766,7 +771,12 @@ class RungeKuttaStepper(Stepper):
             raise IndexError(f"stage {stage} out of range for {type(self).__name__}")
         kwargs.pop("filter_args", None)
         if self._on_device(kwargs):
-            return self._device_rk_stage(stage, queue, kwargs)
+            try:
+                return self._device_rk_stage(stage, queue, kwargs)
+            except NotImplementedError:
+                if not jit_enabled(self.jit) or self.fused:
+                    raise
+                return self._jit_rk_stage(stage, queue, kwargs)
         ctx = dict(kwargs)
         if self.dt is not None:
             ctx["dt"] = self.dt
@@ -787,6 +797,45 @@ class RungeKuttaStepper(Stepper):
             for dst, val in new.items():
                 arr[(dst,) + sub] = val
         return None
+
+
+def _jit_rk_stage(self, stage, queue, kwargs):
+    """
+    EXPERIMENTAL: the reference's construction (``step.py:181-239``) for any ``rhs_dict``:
+    right-hand sides (reading copy ``q``) into temporaries, then the stage's statements on
+    the copies axis, handed to the run-time code generator.
+    """
+    from pystella_b200.codegen import GenericMap
+    if stage not in self._jit_maps:
+        maps, tmps = self._jit_statements(stage)
+        some = kwargs[next(iter(self.dof_names))]
+        dtype = str(some.dtype).replace("torch.", "")
+        self._jit_maps[stage] = GenericMap(maps, tmps, dtype=dtype,
+                                           halo_shape=self.halo_shape,
+                                           rank_shape=self.rank_shape)
+    call = dict(kwargs)
+    call["dt"] = self._resolve_dt(kwargs)
+    self._jit_maps[stage](queue, **call)
+    return None
+
+
+def _jit_rk_statements(self, stage):
+    """-> (map_instructions, tmp_instructions) of one classical stage; step.py:181-239."""
+    from pystella_b200.field import prepend_subscript, var
+    q = 0 if stage == 0 else 1
+    tmps, maps = [], []
+    for i, (key, val) in enumerate(self.rhs_dict.items()):
+        tmps.append((var(gen_tmp_name(key, suffix=f"_rhs_{i}")),
+                     prepend_subscript(val, (q,))))
+    for i, key in enumerate(self.rhs_dict):
+        rhs = var(gen_tmp_name(key, suffix=f"_rhs_{i}"))
+        for dst, combo, c_dt in self.step_statements(stage):
+            expr = 0
+            for c, src in combo:
+                expr = expr + c * prepend_subscript(key, (src,))
+            expr = expr + c_dt * var("dt") * rhs
+            maps.append((prepend_subscript(key, (dst,)), expr))
+    return maps, tmps
 
 
 def _device_rk_stage(self, stage, queue, kwargs):
@@ -848,6 +897,8 @@ def _device_rk_stage(self, stage, queue, kwargs):
 
 
 RungeKuttaStepper._device_rk_stage = _device_rk_stage
+RungeKuttaStepper._jit_rk_stage = _jit_rk_stage
+RungeKuttaStepper._jit_statements = _jit_rk_statements
 RungeKuttaStepper._scalars = LowStorageRKStepper._scalars
 
 

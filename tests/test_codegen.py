@@ -193,8 +193,10 @@ def test_generated_lsrk_stage_semantics_on_host():
     terms = [(0.5, (2, 0)), (0.5, (0, 2)), (0.5, (2, 2))]
     sec = ps.ScalarSector(2, potential=lambda g: g[0]**2 / 2 + g[1]**2 / 2
                           + g[0]**2 * g[1]**2 / 2)
-    A, B, dt, a, H = -0.4178904745, 0.3792103129999, 0.01, 1.3, 0.2
-    maps, tmps = _lsrk_statements(sec.rhs_dict, A, B)
+    dt, a, H = 0.01, 1.3, 0.2
+    stepper = ps.LowStorageRK54(sec, dt=dt, halo_shape=h, jit=True)
+    A, B = stepper._A[1], stepper._B[1]
+    maps, tmps = stepper._jit_statements(1)          # what the product hands the generator
     ksrc = codegen.generate_kernel(maps, tmps)
     arrays = {"f": f.copy(), "dfdt": d.copy(), "_f_tmp": kf.copy(), "_dfdt_tmp": kd.copy(),
               "lap_f": lap}
@@ -281,3 +283,43 @@ def test_custom_stencil_differencer_kernels_on_host():
     _run_generated_on_host(gm.ksrc, arrays, {"fx": h, "div": 0}, {}, N)
     assert np.allclose(arrays["div"], div0 + _one_sided_numpy(yy, h, N, 1, dx[1]),
                        rtol=1e-13, atol=1e-11)
+
+
+@pytest.mark.parametrize("name", ["RungeKutta4", "RungeKutta3Heun", "RungeKutta3Nystrom",
+                                  "RungeKutta3Ralston", "RungeKutta3SSP",
+                                  "RungeKutta2Midpoint", "RungeKutta2Heun",
+                                  "RungeKutta2Ralston"])
+def test_generated_classical_rk_stages_on_host(name):
+    """Classical RK through the generator (step.py:181-239): copies axis first, the RHS
+    reads copy q, `lap_f` ignores the prepend (field/__init__.py:253-257)."""
+    import oracle as O
+    from pystella_b200.field import var
+    rng = np.random.default_rng(6)
+    N, h = (4, 5, 6), 1
+    pad = tuple(n + 2 * h for n in N)
+    dt = 0.05
+    f_ = ps.DynamicField("f", offset="h")
+    sin = var("sin")
+    stepper = getattr(ps, name)({f_: f_.dot, f_.dot: f_.lap - sin(f_)}, dt=dt, halo_shape=h,
+                                jit=True)
+    nc = stepper.num_copies
+    f, d = rng.random((nc,) + pad), rng.random((nc,) + pad)
+    fr, dr = f.copy(), d.copy()
+    for stage in range(stepper.num_stages):
+        lap = rng.random(N)
+        maps, tmps = stepper._jit_statements(stage)
+        ksrc = codegen.generate_kernel(maps, tmps)
+        arrays = {"f": f, "dfdt": d, "lap_f": lap}
+        _run_generated_on_host(ksrc, arrays, {"f": h, "dfdt": h, "lap_f": 0}, {"dt": dt}, N)
+
+        q = O.rk_rhs_copy(stage)
+        fi = np.stack([O.interior(fr[c], h) for c in range(nc)])
+        di = np.stack([O.interior(dr[c], h) for c in range(nc)])
+        rhs_f, rhs_d = di[q].copy(), lap - np.sin(fi[q])
+        O.rk_stage(name, stage, dt, fi, rhs_f)
+        O.rk_stage(name, stage, dt, di, rhs_d)
+        for c in range(nc):
+            O.interior(fr[c], h)[...] = fi[c]
+            O.interior(dr[c], h)[...] = di[c]
+        assert np.allclose(f, fr, rtol=1e-14, atol=1e-15), (name, stage)
+        assert np.allclose(d, dr, rtol=1e-14, atol=1e-15), (name, stage)

@@ -49,3 +49,34 @@ def test_custom_stencil_differencer():
     for ax in range(3):
         assert np.allclose(grd[ax].cpu().numpy(), one_sided(yw, h, N, ax, dx[ax]),
                            rtol=1e-12, atol=1e-10)
+
+
+@pytest.mark.parametrize("name", ["RungeKutta4", "RungeKutta3SSP", "RungeKutta2Heun"])
+def test_classical_rk_generated_stage(name):
+    """step.py:181-239 for a system outside the hand-written menu (sine-Gordon force)."""
+    from pystella_b200.field import var
+    rng = np.random.default_rng(12)
+    N, h = (16, 12, 40), 2
+    pad = tuple(n + 2 * h for n in N)
+    dt = 0.05
+    f_ = ps.DynamicField("f", offset="h")
+    sin = var("sin")
+    stepper = getattr(ps, name)({f_: f_.dot, f_.dot: f_.lap - sin(f_)}, dt=dt, halo_shape=h,
+                                jit=True)
+    nc = stepper.num_copies
+    fh, dh = rng.random((nc,) + pad), rng.random((nc,) + pad)
+    f, d = to_dev(fh), to_dev(dh)
+    for stage in range(stepper.num_stages):
+        laph = rng.random(N)
+        stepper(stage, None, f=f, dfdt=d, lap_f=to_dev(laph))
+        q = O.rk_rhs_copy(stage)
+        fi = np.stack([O.interior(fh[c], h) for c in range(nc)])
+        di = np.stack([O.interior(dh[c], h) for c in range(nc)])
+        rhs_f, rhs_d = di[q].copy(), laph - np.sin(fi[q])
+        O.rk_stage(name, stage, dt, fi, rhs_f)
+        O.rk_stage(name, stage, dt, di, rhs_d)
+        for c in range(nc):
+            O.interior(fh[c], h)[...] = fi[c]
+            O.interior(dh[c], h)[...] = di[c]
+        assert np.allclose(f.cpu().numpy(), fh, rtol=1e-13, atol=1e-14), (name, stage)
+        assert np.allclose(d.cpu().numpy(), dh, rtol=1e-13, atol=1e-14), (name, stage)
