@@ -60,6 +60,8 @@ class Reduction:
         self.halo_shape = kwargs.pop("halo_shape", None)
         self.rank_shape = kwargs.pop("rank_shape", None)
         self.strict_fp = kwargs.pop("strict_fp", False)
+        self.jit = kwargs.pop("jit", None)
+        self.dtype = kwargs.pop("dtype", "float64")
         tmp = kwargs.pop("tmp_instructions", None) or []
         if isinstance(tmp, dict):
             tmp = list(tmp.items())
@@ -86,15 +88,35 @@ class Reduction:
             subs[lhs] = substitute(rhs, subs)
         self._polys = []
         self._abs = []
-        for expr in flat:
+        generated = []      # (scratch Field, expression): reducers outside the menu
+        for r, expr in enumerate(flat):
             expr = substitute(expr, subs) if subs else expr
             absolute = False
+            inner = expr
             if isinstance(expr, Call) and getattr(expr.function, "name", "") in (
                     "fabs", "abs"):
                 absolute = True
-                expr = expr.parameters[0]
-            self._polys.append(to_polynomial(expr))
+                inner = expr.parameters[0]
+            try:
+                poly = to_polynomial(inner)
+            except NotImplementedError:
+                from pystella_b200.step import jit_enabled
+                if not jit_enabled(self.jit):
+                    raise
+                # EXPERIMENTAL: evaluate the reducer site by site with a generated
+                # element-wise kernel into a scratch array, then fold that array
+                scratch = Field(f"_psb_reducer_{r}")
+                generated.append((scratch, expr))
+                poly, absolute = to_polynomial(scratch), False
+            self._polys.append(poly)
             self._abs.append(absolute)
+        self._generated_map = None
+        self._scratch_names = [fld.name for fld, _ in generated]
+        if generated:
+            from pystella_b200.codegen import GenericMap
+            self._generated_map = GenericMap(generated, dtype=self.dtype,
+                                             halo_shape=self.halo_shape,
+                                             rank_shape=self.rank_shape)
 
         # the distinct arrays and scalars
         self._arrays = []
@@ -140,6 +162,8 @@ class Reduction:
         h = self.halo_shape
         if isinstance(h, (tuple, list)):
             h = h[0]
+        if self._generated_map is not None:
+            kwargs = self._run_generated(queue, kwargs)
         arrays, halos = [], []
         for ref in self._arrays:
             if ref.name not in kwargs:
@@ -204,6 +228,31 @@ class Reduction:
                 red.append(v)
             vals[key] = np.array(red)
         return self.callback(vals)
+
+    def _run_generated(self, queue, kwargs):
+        gm = self._generated_map
+        shape = gm.rank_shape
+        if shape is None:
+            for name, sub, field in gm.ksrc.slots:
+                if name in self._scratch_names:
+                    continue
+                if name not in kwargs:
+                    raise TypeError(f"missing array argument '{name}'")
+                t = kwargs[name][sub] if sub else kwargs[name]
+                g = gm._halo_of(field)
+                shape = tuple(n - 2 * g for n in t.shape[-3:])
+                device = t.device
+                break
+            else:
+                raise NotImplementedError("a Reduction needs at least one array operand")
+        else:
+            device = next(v.device for v in kwargs.values() if isinstance(v, torch.Tensor))
+        kwargs = dict(kwargs)
+        for name in self._scratch_names:
+            kwargs[name] = torch.empty(shape, dtype=getattr(torch, np.dtype(self.dtype).name),
+                                       device=device)
+        gm(queue, **kwargs)
+        return kwargs
 
     def _launch(self, arrays, halos, terms, ops, flags, shape, queue):
         # split into launches that respect the kernel's static limits

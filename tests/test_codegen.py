@@ -323,3 +323,31 @@ def test_generated_classical_rk_stages_on_host(name):
             O.interior(dr[c], h)[...] = di[c]
         assert np.allclose(f, fr, rtol=1e-14, atol=1e-15), (name, stage)
         assert np.allclose(d, dr, rtol=1e-14, atol=1e-15), (name, stage)
+
+
+def test_generated_reducers_on_host():
+    """Reducers outside the polynomial menu (reduction.py:80-190 accepts any expression):
+    evaluated by a generated kernel into scratch arrays which the fold kernel then reads."""
+    from pystella_b200.field import var
+    rng = np.random.default_rng(7)
+    N, h = (5, 4, 6), 2
+    f, g, a = ps.Field("f", offset="h"), ps.Field("g"), var("a")
+    decomp = ps.DomainDecomposition((1, 1, 1), h, N)
+    reducers = {"c": [var("cos")(f) * g / a, (f**0.5, "max")], "p": [f * g]}
+    with pytest.raises(NotImplementedError):
+        ps.Reduction(decomp, reducers, halo_shape=h)
+    red = ps.Reduction(decomp, reducers, halo_shape=h, jit=True)
+    assert red._scratch_names == ["_psb_reducer_0", "_psb_reducer_1"]
+    # the fold sees: scratch_0 (avg), scratch_1 (max), f*g (avg)
+    assert [sorted(ref.name for mono in poly for ref, _ in mono) for poly in red._polys] == [
+        ["_psb_reducer_0"], ["_psb_reducer_1"], ["f", "g"]]
+    assert red.reduction_ops == ["avg", "max", "avg"]
+
+    fh = rng.random(tuple(n + 2 * h for n in N)) + 0.1
+    gh = rng.random(N)
+    arrays = {"f": fh, "g": gh, "_psb_reducer_0": np.zeros(N), "_psb_reducer_1": np.zeros(N)}
+    halos = {"f": h, "g": 0, "_psb_reducer_0": 0, "_psb_reducer_1": 0}
+    _run_generated_on_host(red._generated_map.ksrc, arrays, halos, {"a": 1.7}, N)
+    fi = fh[h:-h, h:-h, h:-h]
+    assert np.allclose(arrays["_psb_reducer_0"], np.cos(fi) * gh / 1.7, rtol=1e-14)
+    assert np.allclose(arrays["_psb_reducer_1"], fi**0.5, rtol=1e-14)

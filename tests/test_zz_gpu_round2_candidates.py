@@ -80,3 +80,20 @@ def test_classical_rk_generated_stage(name):
             O.interior(dh[c], h)[...] = di[c]
         assert np.allclose(f.cpu().numpy(), fh, rtol=1e-13, atol=1e-14), (name, stage)
         assert np.allclose(d.cpu().numpy(), dh, rtol=1e-13, atol=1e-14), (name, stage)
+
+
+def test_reduction_with_generated_reducers():
+    """reduction.py:80-255 with reducers outside the polynomial menu (opt-in JIT)."""
+    from pystella_b200.field import var
+    rng = np.random.default_rng(13)
+    N, h = (16, 12, 40), 2
+    f, g, a = ps.Field("f", offset="h"), ps.Field("g"), var("a")
+    decomp = ps.DomainDecomposition((1, 1, 1), h, N)
+    red = ps.Reduction(decomp, {"c": [var("cos")(f) * g / a, (f**0.5, "max")],
+                                "p": [f * g]}, halo_shape=h, jit=True)
+    fh = rng.random(tuple(n + 2 * h for n in N)) + 0.1
+    gh = rng.random(N)
+    out = red(None, f=to_dev(fh), g=to_dev(gh), a=np.array(1.7))
+    fi = fh[h:-h, h:-h, h:-h]
+    assert np.allclose(out["c"], [np.mean(np.cos(fi) * gh / 1.7), np.max(fi**0.5)], rtol=1e-12)
+    assert np.allclose(out["p"], [np.mean(fi * gh)], rtol=1e-12)
