@@ -13,6 +13,7 @@ static int validate(const psb_scalar_stage_args* a) {
   PSB_REQUIRE(a->f_in != a->f_out,
               "psb_scalar_stage_fused: f_out must not alias f_in (ping-pong)");
   PSB_REQUIRE(a->Nx > 0 && a->Ny > 0 && a->Nz > 0, "psb_scalar_stage_fused: empty grid");
+  PSB_REQUIRE(a->h >= 1 && a->h <= 4, "psb_scalar_stage_fused: h=%d out of range 1..4", a->h);
   PSB_REQUIRE(a->Nx >= a->h && a->Ny >= a->h && a->Nz >= a->h,
               "psb_scalar_stage_fused: grid smaller than the halo");
   PSB_REQUIRE(a->x_begin >= 0 && a->x_end <= a->Nx && a->x_begin <= a->x_end,
@@ -29,6 +30,32 @@ static int validate(const psb_scalar_stage_args* a) {
                 "psb_scalar_stage_fused: too many potential terms");
   PSB_REQUIRE(a->nvterms >= 0 && a->nvterms <= PSB_MAX_TERMS,
               "psb_scalar_stage_fused: too many terms in V");
+  for (int f = 0; f < a->nscalars; ++f)
+    for (int t = 0; t < a->nterms[f]; ++t)
+      for (int m = 0; m < a->nscalars; ++m)
+        PSB_REQUIRE(a->power[f][t][m] >= 0,
+                    "psb_scalar_stage_fused: negative power %d of field %d (dV/df_%d, "
+                    "term %d)", a->power[f][t][m], m, f, t);
+  for (int t = 0; t < a->nvterms; ++t)
+    for (int m = 0; m < a->nscalars; ++m)
+      PSB_REQUIRE(a->vpower[t][m] >= 0,
+                  "psb_scalar_stage_fused: negative power %d of field %d (V, term %d)",
+                  a->vpower[t][m], m, t);
+  for (int d = 0; d < 3; ++d)
+    PSB_REQUIRE(a->dx[d] > 0.0 && a->dx[d] < 1e300,
+                "psb_scalar_stage_fused: grid spacing dx[%d]=%g must be positive and finite",
+                d, a->dx[d]);
+  {
+    const int64_t lim = (int64_t)1 << 30;   // plane/row indices are 32-bit in the kernels
+    PSB_REQUIRE(a->Nx < lim && a->Ny < lim && a->Nz < lim,
+                "psb_scalar_stage_fused: an extent exceeds 2^30 sites");
+    const int64_t vol = (a->Nx + 2 * a->h) * (a->Ny + 2 * a->h) * (a->Nz + 2 * a->h);
+    PSB_REQUIRE(a->nscalars == 1 || a->field_stride >= vol,
+                "psb_scalar_stage_fused: field_stride %lld smaller than one padded field "
+                "(%lld elements)", (long long)a->field_stride, (long long)vol);
+  }
+  PSB_REQUIRE(!(a->wrap_x && (a->peer_lo_f_out || a->peer_hi_f_out)),
+              "psb_scalar_stage_fused: wrap_x and peer halos are mutually exclusive");
   PSB_REQUIRE(a->dtype == PSB_F64 || a->dtype == PSB_F32,
               "psb_scalar_stage_fused: unknown dtype %d", a->dtype);
   return 0;

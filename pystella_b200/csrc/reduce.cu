@@ -237,9 +237,15 @@ extern "C" int psb_reduce(const psb_reduce_args* a, void* stream) {
     PSB_REQUIRE(a->arrays[m] != nullptr, "psb_reduce: null array %d", m);
   for (int r = 0; r < a->noutputs; ++r)
     PSB_REQUIRE(a->op[r] >= 0 && a->op[r] <= 2, "psb_reduce: unknown op %d", a->op[r]);
-  for (int t = 0; t < a->nterms; ++t)
+  for (int t = 0; t < a->nterms; ++t) {
     PSB_REQUIRE(a->term_output[t] >= 0 && a->term_output[t] < a->noutputs,
                 "psb_reduce: term %d feeds unknown output", t);
+    for (int m = 0; m < a->narrays; ++m)
+      PSB_REQUIRE(a->power[t][m] >= 0, "psb_reduce: negative power of array %d in term %d", m,
+                  t);
+  }
+  for (int m = 0; m < a->narrays; ++m)
+    PSB_REQUIRE(a->halo[m] >= 0, "psb_reduce: negative halo for array %d", m);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (a->dtype == PSB_F64) return reduce_typed<double>(a, s);
   if (a->dtype == PSB_F32) return reduce_typed<float>(a, s);

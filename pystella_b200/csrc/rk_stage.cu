@@ -138,6 +138,18 @@ extern "C" int psb_scalar_rk_stage(const psb_rk_stage_args* a, void* stream) {
       PSB_REQUIRE(a->src[s][m] >= 0 && a->src[s][m] < a->ncopies,
                   "psb_scalar_rk_stage: bad src");
   }
+  PSB_REQUIRE(a->nscalars >= 1 && a->nscalars <= PSB_MAX_SCALARS,
+              "psb_scalar_rk_stage: nscalars=%d out of range", a->nscalars);
+  PSB_REQUIRE(a->h >= 0, "psb_scalar_rk_stage: negative halo");
+  for (int f = 0; f < a->nscalars; ++f) {
+    PSB_REQUIRE(a->nterms[f] >= 0 && a->nterms[f] <= PSB_MAX_TERMS,
+                "psb_scalar_rk_stage: too many potential terms");
+    for (int t = 0; t < a->nterms[f]; ++t)
+      for (int m = 0; m < a->nscalars; ++m)
+        PSB_REQUIRE(a->power[f][t][m] >= 0,
+                    "psb_scalar_rk_stage: negative power of field %d (dV/df_%d, term %d)", m,
+                    f, t);
+  }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (a->dtype == PSB_F64) return rk_typed<double>(a, s);
   if (a->dtype == PSB_F32) return rk_typed<float>(a, s);

@@ -139,9 +139,17 @@ extern "C" int psb_scalar_stage_unfused(const psb_scalar_stage_args* a, void* st
   PSB_REQUIRE(a->h >= 0, "psb_scalar_stage_unfused: negative halo");
   PSB_REQUIRE(a->x_begin >= 0 && a->x_end <= a->Nx && a->x_begin <= a->x_end,
               "psb_scalar_stage_unfused: bad x range");
-  for (int f = 0; f < a->nscalars && f < PSB_MAX_SCALARS; ++f)
+  PSB_REQUIRE(a->nscalars >= 1 && a->nscalars <= PSB_MAX_SCALARS,
+              "psb_scalar_stage_unfused: nscalars=%d out of range", a->nscalars);
+  for (int f = 0; f < a->nscalars; ++f) {
     PSB_REQUIRE(a->nterms[f] >= 0 && a->nterms[f] <= PSB_MAX_TERMS,
                 "psb_scalar_stage_unfused: too many potential terms");
+    for (int t = 0; t < a->nterms[f]; ++t)
+      for (int m = 0; m < a->nscalars; ++m)
+        PSB_REQUIRE(a->power[f][t][m] >= 0,
+                    "psb_scalar_stage_unfused: negative power of field %d (dV/df_%d, term %d)",
+                    m, f, t);
+  }
   if (a->x_begin == a->x_end) return 0;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (a->dtype == PSB_F64) return dispatch_unfused<double>(a, s);

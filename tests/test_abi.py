@@ -79,3 +79,95 @@ def test_no_cpu_fallback():
     d = ps.DomainDecomposition((1, 1, 1), 1)
     with pytest.raises(ps.PsbError):
         d.share_halos(None, t)
+
+
+def _valid_stage_args():
+    """Arguments that pass every check up to the launch (pointers are dummies: the tests
+    below break one field each and must be refused BEFORE any CUDA call)."""
+    a = _lib.ScalarStageArgs()
+    a.dtype, a.nscalars, a.h = 0, 1, 2
+    a.Nx = a.Ny = a.Nz = 16
+    a.x_begin, a.x_end = 0, 16
+    a.field_stride = 20 ** 3
+    for name, val in (("f_in", 0x1000), ("f_out", 0x2000), ("dfdt", 0x3000), ("kf", 0x4000),
+                      ("kdfdt", 0x5000)):
+        setattr(a, name, val)
+    for d in range(3):
+        a.dx[d] = 0.1
+    a.nterms[0] = 1
+    a.coef[0][0] = 1.0
+    a.power[0][0][0] = 1
+    return a
+
+
+@pytest.mark.parametrize("mutate, message", [
+    (lambda a: setattr(a, "h", 5), b"h=5 out of range"),
+    (lambda a: setattr(a, "h", 0), b"out of range"),
+    (lambda a: setattr(a, "nscalars", 9), b"nscalars=9"),
+    (lambda a: setattr(a, "x_end", 17), b"bad x range"),
+    (lambda a: (setattr(a, "x2_begin", 4), setattr(a, "x2_end", 8)), b"overlap"),
+    (lambda a: setattr(a, "f_out", 0x1000), b"alias"),
+    (lambda a: a.dx.__setitem__(1, 0.0), b"dx[1]"),
+    (lambda a: a.dx.__setitem__(2, float("nan")), b"dx[2]"),
+    (lambda a: a.power[0][0].__setitem__(0, -1), b"negative power"),
+    (lambda a: (setattr(a, "nvterms", 1), a.vpower[0].__setitem__(0, -2)), b"negative power"),
+    (lambda a: a.nterms.__setitem__(0, 17), b"too many potential terms"),
+    (lambda a: (setattr(a, "nscalars", 2), setattr(a, "field_stride", 10)), b"field_stride"),
+    (lambda a: (setattr(a, "wrap_x", 1), setattr(a, "peer_lo_f_out", 0x9000)),
+     b"mutually exclusive"),
+    (lambda a: setattr(a, "dtype", 7), b"unknown dtype"),
+    (lambda a: setattr(a, "Nx", 1), b"smaller than the halo"),
+])
+def test_fused_stage_argument_validation(mutate, message):
+    lib = _lib.load()
+    a = _valid_stage_args()
+    mutate(a)
+    rc = lib.psb_scalar_stage_fused(ctypes.byref(a), None)
+    assert rc != 0
+    assert message in lib.psb_last_error(), lib.psb_last_error()
+
+
+def test_other_entry_points_validate_before_launching():
+    lib = _lib.load()
+    a = _valid_stage_args()
+    a.f_in = 0
+    a.lap_f = 0x6000
+    a.power[0][0][0] = -3
+    assert lib.psb_scalar_stage_unfused(ctypes.byref(a), None) != 0
+    assert b"negative power" in lib.psb_last_error()
+    a.power[0][0][0] = 1
+    a.nscalars = 0
+    assert lib.psb_scalar_stage_unfused(ctypes.byref(a), None) != 0
+    assert b"nscalars=0" in lib.psb_last_error()
+
+    r = _lib.ReduceArgs()
+    r.dtype, r.narrays, r.nterms, r.noutputs = 0, 1, 1, 1
+    r.Nx = r.Ny = r.Nz = 8
+    r.arrays[0] = 0x1000
+    r.partials, r.out = 0x2000, 0x3000
+    r.power[0][0] = -1
+    assert lib.psb_reduce(ctypes.byref(r), None) != 0
+    assert b"negative power" in lib.psb_last_error()
+    r.power[0][0] = 1
+    r.halo[0] = -2
+    assert lib.psb_reduce(ctypes.byref(r), None) != 0
+    assert b"negative halo" in lib.psb_last_error()
+    r.halo[0] = 0
+    r.op[0] = 5
+    assert lib.psb_reduce(ctypes.byref(r), None) != 0
+    assert b"unknown op" in lib.psb_last_error()
+
+    k = _lib.RKStageArgs()
+    k.dtype, k.nscalars, k.h, k.ncopies = 0, 1, 2, 3
+    k.Nx = k.Ny = k.Nz = 8
+    k.f, k.dfdt, k.lap_f = 0x1000, 0x2000, 0x3000
+    k.nstatements = 1
+    k.dst[0], k.ncomb[0] = 1, 1
+    k.nterms[0] = 1
+    k.power[0][0][0] = -1
+    assert lib.psb_scalar_rk_stage(ctypes.byref(k), None) != 0
+    assert b"negative power" in lib.psb_last_error()
+    k.power[0][0][0] = 1
+    k.dst[0] = 3
+    assert lib.psb_scalar_rk_stage(ctypes.byref(k), None) != 0
+    assert b"bad dst" in lib.psb_last_error()
