@@ -1,9 +1,10 @@
 """
 Preheating of scalar fields in an expanding FLRW background: the time loop of the
 reference's examples/scalar_preheating.py (sectors, stepper, derivatives, energy
-reduction, expansion) on pystella_b200.  Spectral pieces of the reference driver
-(Rayleigh initial conditions, power spectra, projectors, HDF5 output) are outside
-the hot path and not provided: fluctuations are white Gaussian noise here.
+reduction, expansion) on pystella_b200, with the reference's initial conditions: WKB
+vacuum fluctuations drawn by RayleighGenerator on top of the homogeneous background
+(single rank; multi-rank runs fall back to white noise until the distributed DFT exists).
+Projectors and HDF5 output are not provided.
 
     python examples/scalar_preheating.py -grid 64 64 64 --end-time 1            # 1 GPU
     torchrun --nproc-per-node 4 examples/scalar_preheating.py -grid 256 256 256 -proc 4 1 1
@@ -39,10 +40,48 @@ parser.add_argument("--end-time", "-end-t", type=float, default=20)
 parser.add_argument("--end-scale-factor", "-end-a", type=float, default=20)
 parser.add_argument("--gravitational-waves", "-gws", action="store_true")
 parser.add_argument("--reference-loop", action="store_true")
+parser.add_argument("--initial-conditions", "-ic", choices=["rayleigh", "white"],
+                    default=None, help="default: rayleigh on one rank, white otherwise")
+parser.add_argument("--seed", type=int, default=49279)
+parser.add_argument("--spectra", action="store_true",
+                    help="print the field power spectrum at the end (single rank)")
 
 
-def main():
-    p = parser.parse_args()
+def init_rayleigh(p, decomp, f, dfdt, f0, potential, energy, expand, backend=None):
+    """WKB vacuum fluctuations into (the interiors of) ``f`` and ``dfdt``: Hubble correction
+    to the effective masses from the background, then one draw per field (reference
+    example, lines 213-236).  ``backend="fftw"`` works on host arrays."""
+    from pystella_b200.field import evaluate, var
+    nscalars = len(f0)
+    addot = expand.addot_friedmann_2(expand.a, energy["total"], energy["pressure"])
+    hubble_correction = - addot / expand.a
+    fields = [var("f0")[i] for i in range(nscalars)]
+    d2Vd2f = [ps.diff(potential(fields), field, field) for field in fields]
+    eff_mass = [float(evaluate(x, {"f0": f0}) + hubble_correction[0]) for x in d2Vd2f]
+    fft = ps.DFT(decomp, None, None, p.grid_shape, p.dtype, backend=backend)
+    dk = tuple(2 * np.pi / Li for Li in p.box_dim)
+    volume = float(np.prod(p.box_dim))
+    modes = ps.RayleighGenerator(None, fft, dk, volume, seed=p.seed * (decomp.rank + 1))
+    for fld in range(nscalars):
+        modes.init_WKB_fields(f[fld], dfdt[fld], norm=p.mphi**2,
+                              omega_k=lambda k, fld=fld: np.sqrt(k**2 + eff_mass[fld]),
+                              hubble=expand.hubble[0])
+    return eff_mass
+
+
+def make_potential(p):
+    def potential(f):
+        phi, chi = f[0], f[1]
+        unscaled = (p.mphi**2 / 2 * phi**2 + p.mchi**2 / 2 * chi**2
+                    + p.gsq / 2 * phi**2 * chi**2 + p.sigma / 2 * phi * chi**2
+                    + p.lambda4 / 4 * chi**4)
+        return unscaled / p.mphi**2
+    return potential
+
+
+def main(argv=None):
+    """-> dict with the final time, scale factor, Friedmann constraint and energies."""
+    p = parser.parse_args(argv)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     device = ps.choose_device()
     if world > 1:
@@ -66,13 +105,7 @@ def main():
     pencil_shape = tuple(ni + 2 * h for ni in rank_shape)
     derivs = ps.FiniteDifferencer(decomp, h, p.dx, rank_shape=rank_shape)
 
-    def potential(f):
-        phi, chi = f[0], f[1]
-        unscaled = (p.mphi**2 / 2 * phi**2 + p.mchi**2 / 2 * chi**2
-                    + p.gsq / 2 * phi**2 * chi**2 + p.sigma / 2 * phi * chi**2
-                    + p.lambda4 / 4 * chi**4)
-        return unscaled / p.mphi**2
-
+    potential = make_potential(p)
     scalar_sector = ps.ScalarSector(nscalars, potential=potential)
     sectors = [scalar_sector]
     if p.gravitational_waves:
@@ -90,15 +123,12 @@ def main():
     statistics = ps.FieldStatistics(decomp, h, rank_shape=rank_shape,
                                     grid_size=p.grid_size)
 
-    # fields: homogeneous background + small Gaussian fluctuations
-    gen = torch.Generator(device=device).manual_seed(49279 * (decomp.rank + 1))
+    ic = p.initial_conditions or ("rayleigh" if p.proc_shape == (1, 1, 1) else "white")
     f = torch.empty((nscalars,) + pencil_shape, dtype=dtype, device=device)
     dfdt = torch.empty_like(f)
-    for i in range(nscalars):
-        f[i] = f0[i] + 1e-6 * torch.randn(pencil_shape, dtype=dtype, device=device,
-                                          generator=gen)
-        dfdt[i] = df0[i] + 1e-6 * torch.randn(pencil_shape, dtype=dtype, device=device,
-                                              generator=gen)
+    for i in range(nscalars):           # field means
+        f[i] = f0[i]
+        dfdt[i] = df0[i]
     dfdx = torch.zeros((nscalars, 3) + rank_shape, dtype=dtype, device=device)
     lap_f = torch.zeros((nscalars,) + rank_shape, dtype=dtype, device=device)
     if p.gravitational_waves:
@@ -115,7 +145,24 @@ def main():
             derivs(None, fx=f, lap=lap_f)
         return reduce_energy(None, f=f, dfdt=dfdt, lap_f=lap_f, a=np.array(a))
 
+    # energy of the background fields initialises the expansion
     energy = compute_energy(1.)
+    expand = ps.Expansion(energy["total"], Stepper, mpl=p.mpl)
+    if ic == "rayleigh":
+        init_rayleigh(p, decomp, f, dfdt, f0, potential, energy, expand)
+        for i in range(nscalars):
+            f[i] += f0[i]
+            dfdt[i] += df0[i]
+    else:
+        gen = torch.Generator(device=device).manual_seed(p.seed * (decomp.rank + 1))
+        for i in range(nscalars):
+            f[i] += 1e-6 * torch.randn(pencil_shape, dtype=dtype, device=device,
+                                       generator=gen)
+            dfdt[i] += 1e-6 * torch.randn(pencil_shape, dtype=dtype, device=device,
+                                          generator=gen)
+
+    # re-initialise energy and expansion
+    energy = compute_energy(expand.a[0])
     if device_loop:
         expand = ps.DeviceExpansion(energy["total"], Stepper, mpl=p.mpl,
                                     grid_size=p.grid_size, decomp=decomp, nscalars=nscalars)
@@ -144,7 +191,7 @@ def main():
                     derivs(None, fx=hij, lap=lap_hij)
         t += dt
         step_count += 1
-        if step_count % 16 == 0 or t >= p.end_time:
+        if step_count % 4 == 0 or t >= p.end_time:
             if device_loop:
                 a_now = float(expand.get()["a"])
                 # energy of the current state for the output (stand-alone kernels)
@@ -159,10 +206,20 @@ def main():
     stats = statistics(f)
     if decomp.rank == 0:
         print("field means", stats["mean"], "variances", stats["variance"])
+    if p.spectra and p.proc_shape == (1, 1, 1):
+        fft = ps.DFT(decomp, None, None, p.grid_shape, p.dtype)
+        dk = tuple(2 * np.pi / Li for Li in p.box_dim)
+        spectra = ps.PowerSpectra(decomp, fft, dk, float(np.prod(p.box_dim)))
+        print("k bins", spectra.bin_width * np.arange(spectra.num_bins))
+        print("scalar spectra", spectra(f))
+    if decomp.rank == 0:
         print("Simulation complete")
+    result = {"t": t, "steps": step_count, "a": a_now, "constraint": constraint,
+              "initial_conditions": ic}
     if world > 1:
         dist.barrier()
         os._exit(0)
+    return result
 
 
 if __name__ == "__main__":

@@ -25,6 +25,7 @@ from pystella_b200.derivs import (FiniteDifferencer, FirstCenteredDifference,
 from pystella_b200.decomp import DomainDecomposition
 from pystella_b200.reduction import Reduction, FieldStatistics
 from pystella_b200.expansion import Expansion, DeviceExpansion
+from pystella_b200.fourier import DFT, RayleighGenerator, PowerSpectra
 from pystella_b200._lib import PsbError
 
 __version__ = "0.1.0"
@@ -47,6 +48,7 @@ def choose_device(local_rank=None):
 __all__ = [
     "Field", "DynamicField", "index_fields", "shift_fields", "substitute", "diff",
     "get_field_args", "var",
+    "DFT", "RayleighGenerator", "PowerSpectra",
     "Sector", "ScalarSector", "TensorPerturbationSector", "tensor_index",
     "get_rho_and_p",
     "ElementWiseMap", "FusedStencilStage", "Stepper",

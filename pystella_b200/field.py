@@ -633,7 +633,12 @@ def evaluate(e, context):
             # user subscripts come before the Field's own (index_fields order)
             own = tuple(int(evaluate(i, context)) for i in agg.child.index)
             return context[agg.name][idx + own]
-        return evaluate(agg, context)[idx]
+        val = evaluate(agg, context)
+        if isinstance(val, (list, tuple)):       # evaluate_kw(x, f0=[...]) in the examples
+            for i in idx:
+                val = val[i]
+            return val
+        return val[idx]
     if isinstance(e, Sum):
         it = iter(e.children)
         out = evaluate(next(it), context)

@@ -154,6 +154,68 @@ def main():
                               "rankID_minus": rid_m})
     out["partition"] = parts
 
+    # Fourier-space helpers of the initial conditions (pure NumPy in the reference)
+    import pystella.fourier.dft as rdft
+    import pystella.fourier.rayleigh as rray
+
+    class _Arr:                      # stands in for a pyopencl array: only .get() is used
+        def __init__(self, a):
+            self.a = a
+
+        def get(self):
+            return self.a
+
+    out["fftfreq"] = {str(n): [float(x) for x in rdft.fftfreq(n)] for n in (4, 7, 8, 32)}
+    fgrid = (8, 6, 4)
+    kshape = (8, 6, 3)
+    rng = np.random.default_rng(20240917)
+    fk = rng.standard_normal(kshape) + 1j * rng.standard_normal(kshape)
+    herm = rray.make_hermitian(fk.copy())
+
+    class _F:
+        grid_shape = fgrid
+        sub_k = {n: _Arr(k) for n, k in zip(
+            ("momenta_x", "momenta_y", "momenta_z"),
+            [rdft.fftfreq(fgrid[0]), rdft.fftfreq(fgrid[1]),
+             np.fft.rfftfreq(fgrid[2], 1 / fgrid[2])])}
+
+    zeroed_imag = rdft.BaseDFT.zero_corner_modes(_F(), herm.copy(), only_imag=True)
+    zeroed = rdft.BaseDFT.zero_corner_modes(_F(), fk.copy())
+    wk = np.sqrt(rng.random(kshape) + 1.0)
+    km = wk.copy()
+    km[0, 0, 0] = 0.
+    wk_in = wk.copy()
+    power = rray.RayleighGenerator._ps_wrapper(None, lambda w: 1 / 2 / w, wk_in, km)
+    out["fourier"] = {
+        "grid_shape": fgrid, "seed": 20240917,
+        "fk": [fk.real.tolist(), fk.imag.tolist()],
+        "make_hermitian": [herm.real.tolist(), herm.imag.tolist()],
+        "zero_corner_modes_only_imag": [zeroed_imag.real.tolist(), zeroed_imag.imag.tolist()],
+        "zero_corner_modes": [zeroed.real.tolist(), zeroed.imag.tolist()],
+        "ps_wrapper": {"wk": wk.tolist(), "power": power.tolist(),
+                       "wk_after": wk_in.tolist()},
+    }
+
+    # the one stored golden number: test/test_examples.py:31-34, and the defaults of the
+    # example it runs (examples/scalar_preheating.py:32-66, 80-82)
+    import re
+    text = open(os.path.join(REFERENCE, "test", "test_examples.py")).read()
+    m = re.search(r'"examples/scalar_preheating.py":\s*([0-9.eE+-]+)', text)
+    ex = open(os.path.join(REFERENCE, "examples", "scalar_preheating.py")).read()
+
+    def default(flag):
+        mm = re.search(r'add_argument\("--' + flag + r'".*?default=(\([^)]*\)|[^,\n]+),', ex, re.S)
+        return mm.group(1).strip()
+
+    out["example"] = {
+        "constraint": float(m.group(1)),
+        "argv": ["--grid-shape", "32", "32", "32", "--end-time", "1"],
+        "defaults": {k: default(k) for k in ("halo-shape", "box-dim", "kappa", "mpl", "mphi",
+                                             "mchi", "gsq", "sigma", "lambda4")},
+        "f0": re.search(r"f0 = \[(.*?)\]", ex).group(1),
+        "df0": re.search(r"df0 = \[(.*?)\]", ex).group(1),
+    }
+
     here = os.path.dirname(os.path.abspath(__file__))
     with open(os.path.join(here, "reference_tables.json"), "w") as fh:
         json.dump(out, fh, indent=1, sort_keys=True)

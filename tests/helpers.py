@@ -66,3 +66,118 @@ def scale_err(got, ref):
 
 
 __all__ = ["HostOps", "periodic_global", "to_dev", "scale_err", "O"]
+
+
+# ---------------------------------------------------------------------------------------
+# the reference's preheating example, end to end on the oracle
+# ---------------------------------------------------------------------------------------
+
+def example_parameters(golden):
+    """Defaults of examples/scalar_preheating.py as extracted by make_golden.py."""
+    d = golden["example"]["defaults"]
+    num = lambda s: float(eval(s, {"__builtins__": {}}))  # noqa: E731  ("1/10", "1.20e-6")
+    mpl = num(d["mpl"])
+    env = {"__builtins__": {}, "p": type("P", (), {"mpl": mpl})}
+    return {
+        "h": int(d["halo-shape"]), "box": eval(d["box-dim"], {"__builtins__": {}}),
+        "kappa": num(d["kappa"]), "mpl": mpl, "mphi": num(d["mphi"]), "mchi": num(d["mchi"]),
+        "gsq": num(d["gsq"]), "sigma": num(d["sigma"]), "lambda4": num(d["lambda4"]),
+        "f0": list(eval("[" + golden["example"]["f0"] + "]", env)),
+        "df0": list(eval("[" + golden["example"]["df0"] + "]", env)),
+    }
+
+
+def example_potential_terms(p):
+    """examples/scalar_preheating.py:98-105 as polynomial terms (coef, (pow_phi, pow_chi))."""
+    m2 = p["mphi"]**2
+    terms = [(p["mphi"]**2 / 2 / m2, (2, 0)), (p["mchi"]**2 / 2 / m2, (0, 2)),
+             (p["gsq"] / 2 / m2, (2, 2)), (p["sigma"] / 2 / m2, (1, 2)),
+             (p["lambda4"] / 4 / m2, (0, 4))]
+    return [(c, pw) for c, pw in terms if c != 0]
+
+
+def example_initial_conditions(p, grid_shape, seed):
+    """
+    examples/scalar_preheating.py:193-236 on the oracle: homogeneous background ->
+    Hubble correction to the effective masses -> WKB Rayleigh modes -> re-initialised
+    expansion.  The uniform deviates come from NumPy (the reference's Threefry stream is
+    not available), so results agree with the reference statistically only.
+    -> dict(f, dfdt (padded, halos NOT yet shared), a, adot, hubble, energy, dx, dt, ...)
+    """
+    from oracle import c_oracle as OC, fourier_oracle as F
+    ns, h = 2, p["h"]
+    N = tuple(grid_shape)
+    dx = tuple(Li / Ni for Li, Ni in zip(p["box"], N))
+    dk = tuple(2 * np.pi / Li for Li in p["box"])
+    volume = float(np.prod(p["box"]))
+    dt = p["kappa"] * min(dx)
+    V = example_potential_terms(p)
+    pot = OC.make_potential(ns, V)
+    pad = tuple(n + 2 * h for n in N)
+    f, d = np.zeros((ns,) + pad), np.zeros((ns,) + pad)
+    lap = np.zeros((ns,) + N)
+    grid_size = float(np.prod(N))
+    for i in range(ns):
+        f[i], d[i] = p["f0"][i], p["df0"][i]
+
+    def energy(a):
+        for i in range(ns):
+            OC.share_halos(f[i], h)
+            OC.laplacian(f[i], lap[i], h, dx)
+        return OC.scalar_energy(f, d, lap, h, a, grid_size, pot)
+
+    def rho_p(en):
+        kin, potl, grad = en[:ns].sum(), en[ns], en[ns + 1:].sum()
+        return kin + potl + grad, kin - grad / 3 - potl        # sectors.py:211-229
+
+    total, pressure = rho_p(energy(1.))
+    ex = O.Expansion(total, "LowStorageRK54", mpl=p["mpl"])
+    addot = ex.addot_friedmann_2(ex.a, total, pressure)
+    correction = float((-addot / ex.a)[0])
+    m2 = p["mphi"]**2
+    f0 = p["f0"]
+    d2V = [(p["mphi"]**2 + p["gsq"] * f0[1]**2) / m2,              # d2V/dphi2 at f0
+           (p["mchi"]**2 + p["gsq"] * f0[0]**2 + p["sigma"] * f0[0]
+            + 3 * p["lambda4"] * f0[1]**2) / m2]                   # d2V/dchi2 at f0
+    eff_mass = [m + correction for m in d2V]
+
+    rng = np.random.default_rng(seed)
+    kshape = (N[0], N[1], N[2] // 2 + 1)
+    for fld in range(ns):
+        rands = rng.random((4,) + kshape)
+        rands[rands == 0] = 0.5
+        fx, dfx = F.init_wkb_fields(
+            rands, N, dk, volume, norm=p["mphi"]**2,
+            omega_k=lambda k, fld=fld: np.sqrt(k**2 + eff_mass[fld]),
+            hubble=float(ex.hubble[0]))
+        O.interior(f[fld], h)[...] = fx
+        O.interior(d[fld], h)[...] = dfx
+    for i in range(ns):
+        f[i] += p["f0"][i]
+        d[i] += p["df0"][i]
+    en = energy(float(ex.a[0]))
+    total, pressure = rho_p(en)
+    ex = O.Expansion(total, "LowStorageRK54", mpl=p["mpl"])
+    return {"f": f, "dfdt": d, "lap": lap, "energies": en, "expansion": ex, "pot": pot,
+            "V_terms": V, "dx": dx, "dt": dt, "grid_size": grid_size, "rho_p": rho_p,
+            "eff_mass": eff_mass}
+
+
+def example_run_oracle(p, ic, end_time):
+    """The time loop of examples/scalar_preheating.py:258-272 on the C oracle;
+    -> (number of steps, a, constraint (expansion.py:159-176), total energy)."""
+    from oracle import c_oracle as OC
+    f, d, lap, en, ex = ic["f"], ic["dfdt"], ic["lap"], ic["energies"], ic["expansion"]
+    A, B, _ = O.LSRK_TABLES["LowStorageRK54"]
+    state = np.array([ex.a[0], ex.adot[0], ex.hubble[0], 0., 0.])
+    kf, kd = np.zeros_like(f), np.zeros_like(d)
+    nsteps, t = 0, 0.
+    while t < end_time:
+        t += ic["dt"]
+        nsteps += 1
+    OC.preheating_steps(nsteps, A, B, f, d, kf, kd, lap, p["h"], ic["dx"], ic["dt"],
+                        p["mpl"], ic["grid_size"], ic["pot"], state, en)
+    total, _ = ic["rho_p"](en)
+    a, adot = state[0], state[1]
+    constraint = abs(np.sqrt(8 * np.pi * a**2 / 3 / p["mpl"]**2 * total) * a / adot - 1)
+    return nsteps, a, constraint, total

@@ -85,3 +85,57 @@ def test_partition(golden):
         assert list(s2) == case["rank_shape"] and list(st2) == case["rank_start"]
         assert d.rankID(*rt) == case["rankID"]
         assert d.rankID(rt[0] - 1, rt[1] - 1, 0) == case["rankID_minus"]
+
+
+def _cplx(pair):
+    return np.array(pair[0]) + 1j * np.array(pair[1])
+
+
+def test_fourier_helpers(golden):
+    """The oracle's restatement of the NumPy helpers behind RayleighGenerator ==
+    the reference functions themselves (run by make_golden.py)."""
+    from oracle import fourier_oracle as F
+    for n, ref in golden["fftfreq"].items():
+        assert F.fftfreq(int(n)).tolist() == ref
+    g = golden["fourier"]
+    grid = tuple(g["grid_shape"])
+    fk = _cplx(g["fk"])
+    herm = F.make_hermitian(fk.copy())
+    assert np.array_equal(herm, _cplx(g["make_hermitian"]))
+    assert np.array_equal(F.zero_corner_modes(herm.copy(), grid, only_imag=True),
+                          _cplx(g["zero_corner_modes_only_imag"]))
+    assert np.array_equal(F.zero_corner_modes(fk.copy(), grid), _cplx(g["zero_corner_modes"]))
+    wk = np.array(g["ps_wrapper"]["wk"])
+    km = wk.copy()
+    km[0, 0, 0] = 0.
+    power = F.ps_wrapper(lambda w: 1 / 2 / w, wk, km)
+    assert np.array_equal(power, np.array(g["ps_wrapper"]["power"]))
+    assert np.array_equal(wk, np.array(g["ps_wrapper"]["wk_after"]))
+    # a Hermitian half-spectrum transforms to a real field and back
+    fx = F.idft(F.zero_corner_modes(herm.copy(), grid, only_imag=True), grid)
+    assert np.allclose(F.dft(fx) / np.prod(grid), herm, atol=1e-13)
+
+
+def test_example_constraint_golden(golden):
+    """
+    THE stored golden number of the reference (test/test_examples.py:33): the Friedmann
+    constraint after `scalar_preheating.py --grid-shape 32 32 32 --end-time 1`.  The whole
+    pipeline on the oracle -- WKB Rayleigh initial conditions, 4th-order stencils,
+    LowStorageRK54 stages of the two-field sector, energies, FLRW expansion -- lands on it.
+    The reference's rtol 1e-3 presumes its own random stream (pyopencl Threefry); with
+    NumPy's the value scatters by ~0.5% from seed to seed around the stored number
+    (5.549e-8 .. 5.610e-8 for six seeds), hence 2e-2 here.
+    """
+    from helpers import example_initial_conditions, example_parameters, example_run_oracle
+    p = example_parameters(golden)
+    assert golden["example"]["argv"] == ["--grid-shape", "32", "32", "32", "--end-time", "1"]
+    ic = example_initial_conditions(p, (32, 32, 32), seed=49279)
+    nsteps, a, constraint, _ = example_run_oracle(p, ic, end_time=1.)
+    assert nsteps == 64
+    assert abs(constraint / golden["example"]["constraint"] - 1) < 2e-2, constraint
+    # and it is the fluctuations' spectrum that sets it: a homogeneous run misses it
+    ic0 = example_initial_conditions(p, (32, 32, 32), seed=49279)
+    for i in range(2):
+        ic0["f"][i], ic0["dfdt"][i] = p["f0"][i], p["df0"][i]
+    _, _, c0, _ = example_run_oracle(p, ic0, end_time=1.)
+    assert abs(c0 / golden["example"]["constraint"] - 1) > 0.2

@@ -97,3 +97,64 @@ def test_reduction_with_generated_reducers():
     fi = fh[h:-h, h:-h, h:-h]
     assert np.allclose(out["c"], [np.mean(np.cos(fi) * gh / 1.7), np.max(fi**0.5)], rtol=1e-12)
     assert np.allclose(out["p"], [np.mean(fi * gh)], rtol=1e-12)
+
+
+def _load_example(name):
+    import importlib.util
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                        "examples", name)
+    spec = importlib.util.spec_from_file_location("example_" + name.replace(".", "_"), path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@pytest.mark.parametrize("loop", ["device", "reference"])
+def test_example_golden_constraint(golden, loop):
+    """test/test_examples.py:31-67 on the product: the stored Friedmann constraint of
+    `scalar_preheating.py --grid-shape 32 32 32 --end-time 1` (statistical tolerance: our
+    random stream is not pyopencl's; see tests/test_oracle_golden.py)."""
+    example = _load_example("scalar_preheating.py")
+    argv = list(golden["example"]["argv"])
+    if loop == "reference":
+        argv.append("--reference-loop")
+    out = example.main(argv)
+    assert out["steps"] == 64 and out["initial_conditions"] == "rayleigh"
+    assert abs(out["constraint"] / golden["example"]["constraint"] - 1) < 2e-2, out
+
+
+def test_fourier_on_device():
+    """cuFFT path of DFT / RayleighGenerator / PowerSpectra == the host backend."""
+    rng = np.random.default_rng(14)
+    grid, h = (16, 12, 20), 2
+    decomp = ps.DomainDecomposition((1, 1, 1), h, grid_shape=grid)
+    dev = ps.DFT(decomp, None, None, grid, "float64")
+    host = ps.DFT(decomp, None, None, grid, "float64", backend="fftw")
+    assert dev.fk.is_cuda and not host.fk.is_cuda
+    pad = tuple(n + 2 * h for n in grid)
+    fx = rng.random(pad)
+    fk_d = dev.dft(to_dev(fx)).cpu().numpy()
+    fk_h = host.dft(fx).numpy()
+    assert np.allclose(fk_d, fk_h, rtol=1e-12, atol=1e-10)
+    back = torch.zeros(pad, dtype=torch.float64, device="cuda")
+    dev.idft(to_dev(fk_h), back)
+    assert np.allclose(back.cpu().numpy()[h:-h, h:-h, h:-h],
+                       np.prod(grid) * fx[h:-h, h:-h, h:-h], rtol=1e-11)
+    assert float(back[0].abs().max()) == 0.
+
+    L = (5., 6., 7.)
+    dk = tuple(2 * np.pi / Li for Li in L)
+    rands = rng.random((4,) + host.shape(True))
+    kw = dict(norm=1.44e-12, omega_k=lambda k: np.sqrt(k**2 + 0.7), hubble=0.31)
+    out = []
+    for fft in (dev, host):
+        modes = ps.RayleighGenerator(None, fft, dk, float(np.prod(L)), seed=1)
+        modes._uniform = lambda shape, fft=fft: torch.from_numpy(rands.copy()).to(fft.device)
+        out.append([x.cpu().numpy() for x in modes.generate_WKB(None, **kw)])
+    assert np.allclose(out[0][0], out[1][0], rtol=1e-12, atol=1e-24)
+    assert np.allclose(out[0][1], out[1][1], rtol=1e-12, atol=1e-24)
+    s_d = ps.PowerSpectra(decomp, dev, dk, float(np.prod(L)))(to_dev(fx))
+    s_h = ps.PowerSpectra(decomp, host, dk, float(np.prod(L)))(fx)
+    ok = np.isfinite(s_h)
+    assert np.allclose(s_d[ok], s_h[ok], rtol=1e-11)
