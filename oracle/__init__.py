@@ -13,8 +13,13 @@ tables extracted from the reference sources by ``tests/golden/make_golden.py``
 (committed as ``tests/golden/reference_tables.json``) and (ii) the reference's
 own known-answer tests re-expressed in ``tests/test_oracle_kat.py``
 (plane-wave eigenvalues, ``y' = y**n`` convergence, bit-exact periodic halos,
-FLRW expansion).  Per-stage array parity against the pyopencl path itself is
-unpinned by the reference (it stores no array fixtures).
+FLRW expansion) and (iii) the reference's one stored golden number: the Friedmann
+constraint of ``examples/scalar_preheating.py`` at 32^3 (``test/test_examples.py:33``),
+which the oracle reproduces end to end -- WKB Rayleigh initial conditions
+(``oracle/fourier_oracle.py``), stencils, LowStorageRK54, energies, expansion -- to 0.2%
+(statistically: the reference's random stream is pyopencl's).  Per-stage array parity
+against the pyopencl path itself is unpinned by the reference (it stores no array
+fixtures).
 """
 
 from oracle.numpy_oracle import *  # noqa: F401,F403
