@@ -26,6 +26,7 @@ from pystella_b200.decomp import DomainDecomposition
 from pystella_b200.reduction import Reduction, FieldStatistics
 from pystella_b200.expansion import Expansion, DeviceExpansion
 from pystella_b200.fourier import DFT, RayleighGenerator, PowerSpectra
+from pystella_b200.histogram import Histogrammer, FieldHistogrammer
 from pystella_b200._lib import PsbError
 
 __version__ = "0.1.0"
@@ -48,7 +49,7 @@ def choose_device(local_rank=None):
 __all__ = [
     "Field", "DynamicField", "index_fields", "shift_fields", "substitute", "diff",
     "get_field_args", "var",
-    "DFT", "RayleighGenerator", "PowerSpectra",
+    "DFT", "RayleighGenerator", "PowerSpectra", "Histogrammer", "FieldHistogrammer",
     "Sector", "ScalarSector", "TensorPerturbationSector", "tensor_index",
     "get_rho_and_p",
     "ElementWiseMap", "FusedStencilStage", "Stepper",

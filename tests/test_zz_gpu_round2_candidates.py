@@ -158,3 +158,32 @@ def test_fourier_on_device():
     s_h = ps.PowerSpectra(decomp, host, dk, float(np.prod(L)))(fx)
     ok = np.isfinite(s_h)
     assert np.allclose(s_d[ok], s_h[ok], rtol=1e-11)
+
+
+def test_histograms_on_device():
+    """Histogrammer / FieldHistogrammer on CUDA tensors == numpy (test/test_histogram.py)."""
+    from pystella_b200.field import var
+    rng = np.random.default_rng(15)
+    grid, h, num_bins = (24, 16, 20), 1, 123
+    decomp = ps.DomainDecomposition((1, 1, 1), h, grid_shape=grid)
+    _fx = ps.Field("fx")
+    hist = ps.Histogrammer(decomp, {"count": (var("abs")(_fx) * num_bins, 1),
+                                    "squared": (var("abs")(_fx) * num_bins, _fx**2)},
+                           num_bins, "float64", rank_shape=grid)
+    fx = rng.random(grid)
+    out = hist(None, fx=to_dev(fx))
+    idx = np.floor(np.abs(fx) * num_bins).astype(int).reshape(-1)
+    assert np.array_equal(out["count"], np.bincount(idx, minlength=num_bins))
+    assert np.allclose(out["squared"],
+                       np.bincount(idx, weights=fx.reshape(-1)**2, minlength=num_bins),
+                       rtol=1e-12)
+    fh = ps.FieldHistogrammer(decomp, num_bins, "float64", rank_shape=grid, halo_shape=h)
+    pad = tuple(n + 2 * h for n in grid)
+    f = rng.random((2,) + pad) * 4.2 - 1.2
+    res = fh(to_dev(f))
+    for s in range(2):
+        fi = f[s][h:-h, h:-h, h:-h]
+        assert res["linear"][s].sum() == np.prod(grid)
+        np_res = np.histogram(fi, bins=res["linear_bins"][s])[0]
+        assert np.sum(np.abs(res["linear"][s] - np_res)) <= 4
+        assert res["log"][s].sum() == np.prod(grid)
