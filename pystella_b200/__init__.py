@@ -27,6 +27,8 @@ from pystella_b200.reduction import Reduction, FieldStatistics
 from pystella_b200.expansion import Expansion, DeviceExpansion
 from pystella_b200.fourier import DFT, RayleighGenerator, PowerSpectra
 from pystella_b200.histogram import Histogrammer, FieldHistogrammer
+from pystella_b200 import output
+from pystella_b200.output import OutputFile
 from pystella_b200._lib import PsbError
 
 __version__ = "0.1.0"
@@ -50,6 +52,7 @@ __all__ = [
     "Field", "DynamicField", "index_fields", "shift_fields", "substitute", "diff",
     "get_field_args", "var",
     "DFT", "RayleighGenerator", "PowerSpectra", "Histogrammer", "FieldHistogrammer",
+    "OutputFile",
     "Sector", "ScalarSector", "TensorPerturbationSector", "tensor_index",
     "get_rho_and_p",
     "ElementWiseMap", "FusedStencilStage", "Stepper",
