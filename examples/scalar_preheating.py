@@ -3,7 +3,7 @@ Preheating of scalar fields in an expanding FLRW background: the time loop of th
 reference's examples/scalar_preheating.py (sectors, stepper, derivatives, energy
 reduction, expansion) on pystella_b200, with the reference's initial conditions: WKB
 vacuum fluctuations drawn by RayleighGenerator on top of the homogeneous background
-(single rank; multi-rank runs fall back to white noise until the distributed DFT exists).
+(slab decompositions (P, 1, 1); pencil decompositions fall back to white noise).
 Projectors and HDF5 output are not provided.
 
     python examples/scalar_preheating.py -grid 64 64 64 --end-time 1            # 1 GPU
@@ -41,10 +41,10 @@ parser.add_argument("--end-scale-factor", "-end-a", type=float, default=20)
 parser.add_argument("--gravitational-waves", "-gws", action="store_true")
 parser.add_argument("--reference-loop", action="store_true")
 parser.add_argument("--initial-conditions", "-ic", choices=["rayleigh", "white"],
-                    default=None, help="default: rayleigh on one rank, white otherwise")
+                    default=None, help="default: rayleigh for slab decompositions, else white")
 parser.add_argument("--seed", type=int, default=49279)
 parser.add_argument("--spectra", action="store_true",
-                    help="print the field power spectrum at the end (single rank)")
+                    help="print the field power spectra at the end")
 
 
 def init_rayleigh(p, decomp, f, dfdt, f0, potential, energy, expand, backend=None):
@@ -123,7 +123,7 @@ def main(argv=None):
     statistics = ps.FieldStatistics(decomp, h, rank_shape=rank_shape,
                                     grid_size=p.grid_size)
 
-    ic = p.initial_conditions or ("rayleigh" if p.proc_shape == (1, 1, 1) else "white")
+    ic = p.initial_conditions or ("rayleigh" if p.proc_shape[1:] == (1, 1) else "white")
     f = torch.empty((nscalars,) + pencil_shape, dtype=dtype, device=device)
     dfdt = torch.empty_like(f)
     for i in range(nscalars):           # field means
@@ -206,12 +206,14 @@ def main(argv=None):
     stats = statistics(f)
     if decomp.rank == 0:
         print("field means", stats["mean"], "variances", stats["variance"])
-    if p.spectra and p.proc_shape == (1, 1, 1):
+    if p.spectra and p.proc_shape[1:] == (1, 1):
         fft = ps.DFT(decomp, None, None, p.grid_shape, p.dtype)
         dk = tuple(2 * np.pi / Li for Li in p.box_dim)
         spectra = ps.PowerSpectra(decomp, fft, dk, float(np.prod(p.box_dim)))
-        print("k bins", spectra.bin_width * np.arange(spectra.num_bins))
-        print("scalar spectra", spectra(f))
+        scalar_spectra = spectra(f)
+        if decomp.rank == 0:
+            print("k bins", spectra.bin_width * np.arange(spectra.num_bins))
+            print("scalar spectra", scalar_spectra)
     if decomp.rank == 0:
         print("Simulation complete")
     result = {"t": t, "steps": step_count, "a": a_now, "constraint": constraint,

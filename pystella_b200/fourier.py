@@ -12,14 +12,21 @@ half, the Nyquist wavenumber is positive (``dft.py:326-332``).
 
 ``backend="fftw"`` selects host transforms on CPU tensors / NumPy arrays, the analogue of
 the reference's ``pDFT`` (``dft.py:350-428``); every other backend value means cuFFT on
-the current CUDA device.  Distributed transforms (``proc_shape != (1, 1, 1)``) are not
-implemented yet.
+the current CUDA device.
+
+Distributed transforms: slab decompositions ``proc_shape = (P, 1, 1)`` (the layout of the
+fused stepper).  Position space is split along x, momentum space along y, like
+mpi4py-fft's slab mode which the reference uses (``dft.py:391-407``): local 2-D transforms
+over (y, z), one all-to-all transpose (NCCL on GPUs, gloo on the host backend), 1-D
+transforms over x.  ``sub_k`` and all k-space arrays are the rank-local slices.  Pencil
+decompositions ``(Px, Py, 1)`` are not implemented.
 """
 
 from itertools import product
 
 import numpy as np
 import torch
+import torch.distributed as dist
 
 from pystella_b200._lib import PsbError
 
@@ -65,8 +72,9 @@ class DFT:
             raise TypeError("grid_shape is required")
         if "use_fftw" in kwargs and kwargs.pop("use_fftw"):
             backend = "fftw"
-        if tuple(decomp.proc_shape) != (1, 1, 1):
-            raise NotImplementedError("distributed transforms (proc_shape != (1, 1, 1))")
+        if decomp.proc_shape[1] != 1 or decomp.proc_shape[2] != 1:
+            raise NotImplementedError("distributed transforms need a slab decomposition "
+                                      "proc_shape = (P, 1, 1)")
         if backend not in (None, "vkfft", "clfft", "cufft", "fftw"):
             raise NotImplementedError(f"{backend} backend for DFTs.")
         self.decomp = decomp
@@ -85,12 +93,27 @@ class DFT:
                 raise PsbError("DFT: no CUDA device (pass backend='fftw' for host "
                                "transforms of NumPy arrays)")
             self.device = torch.device("cuda", torch.cuda.current_device())
-        self.fx = torch.zeros(self.grid_shape, dtype=_tdtype(self.dtype), device=self.device)
+        # slab layout: x split in position space, y split in momentum space, both with the
+        # uneven rule of decomp.py:322-337 (the first N % P ranks hold one more)
+        self.nranks, self.rank = decomp.nranks, decomp.rank
+        P = self.nranks
+
+        def split(n):
+            q, r = divmod(n, P)
+            return [q + (1 if i < r else 0) for i in range(P)]
+
+        self._x_sizes, self._y_sizes = split(self.grid_shape[0]), split(self.grid_shape[1])
+        self._y_start = sum(self._y_sizes[:self.rank])
+        if P > 1 and min(self._x_sizes + self._y_sizes) == 0:
+            raise ValueError(f"grid {self.grid_shape} too small for {P} slabs")
+        self.fx = torch.zeros(self.shape(False), dtype=_tdtype(self.dtype),
+                              device=self.device)
         self.fk = torch.zeros(self.shape(True), dtype=_tdtype(self.cdtype),
                               device=self.device)
         k = [fftfreq(n) for n in self.grid_shape]
         if self.is_real:
             k[-1] = np.fft.rfftfreq(self.grid_shape[-1], 1 / self.grid_shape[-1])
+        k[1] = k[1][self._y_start:self._y_start + self._y_sizes[self.rank]]
         self._k_host = [ki.astype(self.rdtype) for ki in k]
         self.sub_k = {name: torch.from_numpy(ki).to(self.device)
                       for name, ki in zip(("momenta_x", "momenta_y", "momenta_z"),
@@ -101,10 +124,67 @@ class DFT:
         return tuple(range(len(self.grid_shape)))
 
     def shape(self, forward_output=True):
-        """dft.py:483-489."""
-        if forward_output and self.is_real:
-            return self.grid_shape[:-1] + (self.grid_shape[-1] // 2 + 1,)
-        return self.grid_shape
+        """Rank-local shape of momentum-space (``True``) or position-space arrays
+        (dft.py:415-416, 483-489)."""
+        nx, ny, nz = self.grid_shape
+        if not forward_output:
+            return (self._x_sizes[self.rank], ny, nz)
+        return (nx, self._y_sizes[self.rank], nz // 2 + 1 if self.is_real else nz)
+
+    # -- slab transposes ------------------------------------------------------
+    def _all_to_all(self, send, in_splits, out_splits):
+        recv = torch.empty(sum(out_splits), dtype=send.dtype, device=send.device)
+        dist.all_to_all_single(recv, send, out_splits, in_splits, group=self.decomp.comm)
+        return recv
+
+    def _to_momentum_layout(self, a):
+        """(nx_loc, Ny, C) -> (Nx, ny_loc, C): every rank sends its x-slab of the y-range
+        owned by the receiver."""
+        nxl, _, c = a.shape
+        nyl = self._y_sizes[self.rank]
+        send = torch.view_as_real(a.permute(1, 0, 2).contiguous()).reshape(-1)
+        recv = self._all_to_all(send, [ny * nxl * c * 2 for ny in self._y_sizes],
+                                [nyl * nx * c * 2 for nx in self._x_sizes])
+        parts, off = [], 0
+        for nx in self._x_sizes:
+            n = nyl * nx * c * 2
+            parts.append(torch.view_as_complex(recv[off:off + n].view(nyl, nx, c, 2))
+                         .permute(1, 0, 2))
+            off += n
+        return torch.cat(parts, dim=0)
+
+    def _to_position_layout(self, b):
+        """(Nx, ny_loc, C) -> (nx_loc, Ny, C)."""
+        _, nyl, c = b.shape
+        nxl = self._x_sizes[self.rank]
+        send = torch.view_as_real(b.contiguous()).reshape(-1)
+        recv = self._all_to_all(send, [nx * nyl * c * 2 for nx in self._x_sizes],
+                                [nxl * ny * c * 2 for ny in self._y_sizes])
+        parts, off = [], 0
+        for ny in self._y_sizes:
+            n = nxl * ny * c * 2
+            parts.append(torch.view_as_complex(recv[off:off + n].view(nxl, ny, c, 2)))
+            off += n
+        return torch.cat(parts, dim=1)
+
+    def _forward(self, x):
+        if self.nranks == 1:
+            return (torch.fft.rfftn(x, dim=(-3, -2, -1)) if self.is_real
+                    else torch.fft.fftn(x, dim=(-3, -2, -1)))
+        a = (torch.fft.rfftn(x, dim=(-2, -1)) if self.is_real
+             else torch.fft.fftn(x, dim=(-2, -1)))
+        return torch.fft.fft(self._to_momentum_layout(a), dim=0)
+
+    def _backward(self, k):
+        if self.nranks == 1:
+            if self.is_real:
+                return torch.fft.irfftn(k, s=self.grid_shape, dim=(-3, -2, -1),
+                                        norm="forward")
+            return torch.fft.ifftn(k, dim=(-3, -2, -1), norm="forward")
+        a = self._to_position_layout(torch.fft.ifft(k, dim=0, norm="forward"))
+        if self.is_real:
+            return torch.fft.irfftn(a, s=self.grid_shape[1:], dim=(-2, -1), norm="forward")
+        return torch.fft.ifftn(a, dim=(-2, -1), norm="forward")
 
     # -- array plumbing -------------------------------------------------------
     def _halo(self):
@@ -114,19 +194,24 @@ class DFT:
         """-> unpadded tensor on ``self.device`` holding ``fx`` (dft.py:171-184)."""
         if fx is None:
             return self.fx
-        if tuple(fx.shape) != self.grid_shape:
-            padded = tuple(n + 2 * h for n, h in zip(self.grid_shape, self._halo()))
+        local = self.shape(False)
+        if tuple(fx.shape) != local:
+            padded = tuple(n + 2 * h for n, h in zip(local, self._halo()))
             if tuple(fx.shape) != padded:
-                raise ValueError(f"array of shape {tuple(fx.shape)} is neither the grid "
-                                 f"{self.grid_shape} nor the padded grid {padded}")
+                raise ValueError(f"array of shape {tuple(fx.shape)} is neither the rank's "
+                                 f"grid {local} nor its padded grid {padded}")
+            if tuple(self.fx.shape) != local:
+                self.fx = torch.zeros(local, dtype=_tdtype(self.dtype), device=self.device)
             if isinstance(fx, torch.Tensor) and fx.is_cuda and self.fx.is_cuda:
                 self.decomp.remove_halos(queue, fx, self.fx)
             else:
-                inner = tuple(slice(h, h + n) for n, h in zip(self.grid_shape, self._halo()))
+                inner = tuple(slice(h, h + n) for n, h in zip(local, self._halo()))
                 self.fx.copy_(self._to_device(fx[inner]))
             return self.fx
         if isinstance(fx, torch.Tensor) and fx.device == self.device:
             return fx
+        if tuple(self.fx.shape) != local:
+            self.fx = torch.zeros(local, dtype=_tdtype(self.dtype), device=self.device)
         self.fx.copy_(self._to_device(fx))
         return self.fx
 
@@ -148,11 +233,7 @@ class DFT:
     def dft(self, fx=None, fk=None, queue=None, **kwargs):
         """Forward transform of ``fx`` (padded or not, device tensor or NumPy array) into
         ``fk`` or the attached :attr:`fk`; unnormalised (dft.py:138-206)."""
-        x = self._position_input(fx, queue)
-        if self.is_real:
-            out = torch.fft.rfftn(x, dim=(-3, -2, -1))
-        else:
-            out = torch.fft.fftn(x, dim=(-3, -2, -1))
+        out = self._forward(self._position_input(fx, queue))
         if fk is None:
             self.fk = out
             return self.fk
@@ -161,24 +242,21 @@ class DFT:
     def idft(self, fk=None, fx=None, queue=None, **kwargs):
         """Backward transform, unnormalised; a padded ``fx`` has its interior written
         (halos are not filled, as ``restore_halos``) (dft.py:208-290)."""
-        k = self.fk if fk is None else self._to_device(fk)
-        if self.is_real:
-            out = torch.fft.irfftn(k, s=self.grid_shape, dim=(-3, -2, -1), norm="forward")
-        else:
-            out = torch.fft.ifftn(k, dim=(-3, -2, -1), norm="forward")
+        out = self._backward(self.fk if fk is None else self._to_device(fk))
         if fx is None:
             self.fx = out
             return self.fx
-        if tuple(fx.shape) == self.grid_shape:
+        local = self.shape(False)
+        if tuple(fx.shape) == local:
             return self._store(fx, out)
-        padded = tuple(n + 2 * h for n, h in zip(self.grid_shape, self._halo()))
+        padded = tuple(n + 2 * h for n, h in zip(local, self._halo()))
         if tuple(fx.shape) != padded:
-            raise ValueError(f"array of shape {tuple(fx.shape)} is neither the grid "
-                             f"{self.grid_shape} nor the padded grid {padded}")
+            raise ValueError(f"array of shape {tuple(fx.shape)} is neither the rank's grid "
+                             f"{local} nor its padded grid {padded}")
         if isinstance(fx, torch.Tensor) and fx.is_cuda and out.is_cuda:
             self.decomp.restore_halos(queue, out.contiguous(), fx)
         else:
-            inner = tuple(slice(h, h + n) for n, h in zip(self.grid_shape, self._halo()))
+            inner = tuple(slice(h, h + n) for n, h in zip(local, self._halo()))
             self._store(fx[inner], out)
         return fx
 
@@ -267,7 +345,11 @@ class RayleighGenerator:
         """rayleigh.py:160-171: Hermitian symmetry on the self-conjugate planes, corner
         modes real."""
         if self.fft.is_real:
-            fk = make_hermitian(fk)
+            if self.fft.nranks == 1:
+                # single-device transforms need the symmetry imposed by hand; the slab
+                # transform's final c2r pass discards the offending parts, as in the
+                # reference, which symmetrises for pyclDFT only (rayleigh.py:162-166)
+                fk = make_hermitian(fk)
             self.fft.zero_corner_modes(fk, only_imag=True)
         return fk
 
@@ -362,9 +444,11 @@ class PowerSpectra:
             counts[kvecs[2] == self.grid_shape[-1] // 2] = 1.
         else:
             counts = np.ones_like(kmags)
-        self.num_bins = int(np.max(kmags) / self.bin_width + .5) + 1
+        max_k = float(decomp.allreduce(float(np.max(kmags)), op="max"))   # spectra.py:87-91
+        self.num_bins = int(max_k / self.bin_width + .5) + 1
         edges = np.arange(-.5, self.num_bins + .5) * self.bin_width
-        self.bin_counts = np.histogram(kmags, weights=counts, bins=edges)[0]
+        self.bin_counts = decomp.allreduce(
+            np.histogram(kmags, weights=counts, bins=edges)[0])
         # per-mode bin index and multiplicity, resident on the device (spectra.py:103-117:
         # bin = round(|k| / bin_width), C rounding; weight = count * |k|**n * |f_k|**2, where the
         # kernel's count is 2 strictly inside 0 < k_z < N_z/2)
@@ -386,6 +470,8 @@ class PowerSpectra:
         weight = self._mult * self._kmag**k_power * (k.real.double()**2 + k.imag.double()**2)
         spectrum = torch.zeros(self.num_bins, dtype=torch.float64, device=k.device)
         spectrum.index_add_(0, self._bin, weight)
+        if self.decomp.comm is not None:
+            spectrum = self.decomp.allreduce(spectrum)
         with np.errstate(divide="ignore", invalid="ignore"):
             return spectrum.cpu().numpy() / self.bin_counts
 

@@ -176,6 +176,85 @@ def _fused_case(rank, world, backend, nscalars, energy, mode="peer"):
         assert float(lo) == float(hi)
 
 
+def _fourier_case(rank, world, backend):
+    """Slab-distributed DFT / RayleighGenerator / PowerSpectra == the single-rank results
+    on the gathered arrays (test/test_dft.py on more than one rank)."""
+    import pystella_b200 as ps
+    from oracle import fourier_oracle as F
+    cuda = backend == "nccl"
+    fft_backend = None if cuda else "fftw"
+    for grid, dtype in (((16, 12, 10), "float64"), ((9, 7, 8), "float64"),
+                        ((8, 6, 4), "complex128")):
+        h = 1
+        decomp = ps.DomainDecomposition((world, 1, 1), h, grid_shape=grid)
+        fft = ps.DFT(decomp, None, None, grid, dtype, backend=fft_backend)
+        rs, start = decomp.get_rank_shape_start(grid)
+        assert fft.shape(False) == rs
+        rng = np.random.default_rng(5)
+        full = rng.random(grid)
+        if not fft.is_real:
+            full = full + 1j * rng.random(grid)
+        loc = full[start[0]:start[0] + rs[0]].copy()
+        ref = np.fft.rfftn(full) if fft.is_real else np.fft.fftn(full)
+        ys, ny = fft._y_start, fft.shape(True)[1]
+        assert sum(fft._y_sizes) == grid[1]
+        arg = torch.from_numpy(loc).cuda() if cuda else loc
+        fk = fft.dft(arg)
+        assert tuple(fk.shape) == fft.shape(True)
+        got = fk.cpu().numpy().copy()
+        assert np.allclose(got, ref[:, ys:ys + ny], rtol=1e-11, atol=1e-11), (rank, grid)
+        # momenta are the local slices
+        ky = F.fftfreq(grid[1])[ys:ys + ny]
+        assert np.array_equal(fft.sub_k["momenta_y"].cpu().numpy(), ky)
+        # round trip, padded output
+        pad = np.zeros(tuple(n + 2 * h for n in rs), dtype)
+        out = torch.from_numpy(pad).cuda() if cuda else pad
+        fft.idft(fk, out)
+        back = out.cpu().numpy() if cuda else out
+        assert np.allclose(back[h:-h, h:-h, h:-h], loc * np.prod(grid), rtol=1e-11,
+                           atol=1e-11)
+        if not fft.is_real:
+            continue
+        # spectra: same bins and values as a single-rank evaluation of the full array
+        L = (5., 6., 7.)
+        dk = tuple(2 * np.pi / Li for Li in L)
+        spec = ps.PowerSpectra(decomp, fft, dk, float(np.prod(L)))
+        one = _single_rank_spectrum(full, grid, dk, float(np.prod(L)))
+        assert spec.num_bins == one[0] and np.array_equal(spec.bin_counts, one[1])
+        mine = spec(arg, k_power=2)
+        ok = one[1] > 0
+        assert np.allclose(mine[ok], one[2][ok], rtol=1e-11), rank
+        # Rayleigh modes: local slices, real field after the backward transform
+        modes = ps.RayleighGenerator(None, fft, dk, float(np.prod(L)), seed=11 * (rank + 1))
+        gk, dgk = modes.generate_WKB(None, hubble=0.1,
+                                     omega_k=lambda k: np.sqrt(k**2 + 0.5))
+        assert tuple(gk.shape) == fft.shape(True)
+        if ys == 0:
+            assert complex(gk[0, 0, 0]) == 0        # homogeneous mode carries no power
+        fx = fft.idft(gk).cpu().numpy()
+        assert fx.shape == rs and np.all(np.isfinite(fx)) and np.std(fx) > 0
+
+
+def _single_rank_spectrum(full, grid, dk, volume):
+    """PowerSpectra of the gathered array, evaluated without any decomposition."""
+    from oracle import fourier_oracle as F
+    fk = np.fft.rfftn(full)
+    kvecs = np.meshgrid(*F.momenta(grid), indexing="ij")
+    kmags = np.sqrt(sum((d * k)**2 for d, k in zip(dk, kvecs)))
+    counts = 2. * np.ones_like(kmags)
+    counts[kvecs[2] == 0] = 1.
+    counts[kvecs[2] == grid[-1] // 2] = 1.
+    bw = min(dk)
+    num_bins = int(np.max(kmags) / bw + .5) + 1
+    edges = np.arange(-.5, num_bins + .5) * bw
+    bin_counts = np.histogram(kmags, weights=counts, bins=edges)[0]
+    mult = np.where((kvecs[2] > 0) & (kvecs[2] < grid[-1] / 2), 2., 1.)
+    hist = np.histogram(kmags, weights=mult * kmags**2 * np.abs(fk)**2, bins=edges)[0]
+    norm = (1 / 2 / np.pi**2 / volume) * (volume / np.prod(grid))**2
+    with np.errstate(invalid="ignore", divide="ignore"):
+        return num_bins, bin_counts, norm * hist / bin_counts
+
+
 def _worker(rank, world, port, case, args):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank),
                       WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
@@ -192,6 +271,8 @@ def _worker(rank, world, port, case, args):
             for h, grid in ((1, (32, 32, 32)), (2, (19, 23, 16)), ((2, 0, 3), (32, 32, 32)),
                             ((0, 2, 1), (32, 32, 32)), (1, (109, 67, 32))):
                 _decomp_case(rank, world, proc_shape, h, grid, backend)
+        elif case in ("cpu_fourier", "gpu_fourier"):
+            _fourier_case(rank, world, backend)
         elif case == "gpu_reduction":
             _reduction_case(rank, world, backend)
         elif case == "gpu_fused":

@@ -44,6 +44,12 @@ def test_decomposition_gloo(proc_shape):
     _run("cpu_decomp", world, proc_shape)
 
 
+@pytest.mark.parametrize("world", [2, 3])
+def test_distributed_fourier_gloo(world):
+    """Slab DFT (all-to-all transposes), spectra and Rayleigh modes over gloo."""
+    _run("cpu_fourier", world)
+
+
 def _ngpus():
     try:
         import torch

@@ -187,3 +187,14 @@ def test_histograms_on_device():
         np_res = np.histogram(fi, bins=res["linear_bins"][s])[0]
         assert np.sum(np.abs(res["linear"][s] - np_res)) <= 4
         assert res["log"][s].sum() == np.prod(grid)
+
+
+def test_distributed_fourier_nccl():
+    """Slab DFT over NCCL all-to-all == numpy on the gathered array (2 GPUs)."""
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from test_distributed import _run
+    _run("gpu_fourier", 2)
