@@ -11,7 +11,12 @@ import pystella_b200 as ps
 from helpers import to_dev
 
 torch = pytest.importorskip("torch")
-pytestmark = pytest.mark.gpu
+# non-strict xfail: a pass is reported as XPASS, a failure does not break the validated
+# suite; scripts/round2_first_call.sh runs this file on its own first thing next round
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.xfail(strict=False, reason="written after the round-1 GPU budget "
+                                "was spent: semantics verified on the host, not yet run on "
+                                "a B200")]
 
 
 class OneSided:
