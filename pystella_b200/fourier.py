@@ -423,8 +423,9 @@ class PowerSpectra:
     Binned power spectra (spectra.py:29-253): ``PowerSpectra(decomp, fft, dk, volume,
     bin_width=min(dk))``; ``__call__(fx, queue=None, k_power=3)`` loops over the outer
     axes of ``fx`` and returns a NumPy array of shape ``outer + (num_bins,)``;
-    ``bin_power(fk, k_power=3)`` bins a momentum-space array.  Polarisation and
-    gravitational-wave spectra (which need the projectors) are not provided yet.
+    ``bin_power(fk, k_power=3)`` bins a momentum-space array; ``polarization``,
+    ``vector_decomposition``, ``gw`` and ``gw_polarization`` take a
+    :class:`~pystella_b200.Projector`.
     """
 
     def __init__(self, decomp, fft, dk, volume, **kwargs):
@@ -483,3 +484,58 @@ class PowerSpectra:
             fk = self.fft.dft(fx[s], queue=queue)
             out[s] = self.bin_power(fk, queue, k_power) * self.norm
         return out
+
+    def _transform_components(self, arrays, n, queue):
+        ks = torch.empty((n,) + tuple(self.kshape), dtype=_tdtype(self.cdtype),
+                         device=self.fft.device)
+        for mu in range(n):
+            self.fft.dft(arrays[mu], ks[mu], queue=queue)
+        return ks
+
+    def polarization(self, vector, projector, queue=None, k_power=3, allocator=None):
+        """Spectra of the plus and minus polarisations of a vector field; outer axes are
+        looped over: ``vector.shape[:-4] + (2, num_bins)`` (spectra.py:217-262)."""
+        outer = tuple(vector.shape[:-4])
+        out = np.zeros(outer + (2, self.num_bins), dtype=np.float64)
+        for s in product(*[range(n) for n in outer]):
+            vec_k = self._transform_components(vector[s], 3, queue)
+            projector.vec_to_pol(queue, vec_k[0], vec_k[1], vec_k)
+            out[s][0] = self.bin_power(vec_k[0], queue, k_power)
+            out[s][1] = self.bin_power(vec_k[1], queue, k_power)
+        return self.norm * out
+
+    def vector_decomposition(self, vector, projector, queue=None, k_power=3,
+                             allocator=None):
+        """As :meth:`polarization` plus the longitudinal component (times ``|k|``):
+        ``vector.shape[:-4] + (3, num_bins)`` (spectra.py:264-312)."""
+        outer = tuple(vector.shape[:-4])
+        out = np.zeros(outer + (3, self.num_bins), dtype=np.float64)
+        for s in product(*[range(n) for n in outer]):
+            vec_k = self._transform_components(vector[s], 3, queue)
+            projector.decompose_vector(queue, vec_k, vec_k[0], vec_k[1], vec_k[2],
+                                       times_abs_k=True)
+            for n in range(3):
+                out[s][n] = self.bin_power(vec_k[n], queue, k_power)
+        return self.norm * out
+
+    def gw(self, hij, projector, hubble, queue=None, k_power=3, allocator=None):
+        """Spectral abundance of transverse-traceless gravitational waves,
+        ``1/(24 pi^2 H^2 V) sum_ij int dOmega |k|^3 |h'_ij(k)|^2``; ``hij`` is the
+        length-6 position-space array of time derivatives (spectra.py:314-358)."""
+        hij_k = self._transform_components(hij, 6, queue)
+        projector.transverse_traceless(queue, hij_k)
+        spec = [self.bin_power(hij_k[mu], queue, k_power) for mu in range(6)]
+        from pystella_b200.sectors import tensor_index
+        total = sum(spec[tensor_index(i, j)] for i in range(1, 4) for j in range(1, 4))
+        return self.norm / 12 / float(np.asarray(hubble).reshape(-1)[0])**2 * total
+
+    def gw_polarization(self, hij, projector, hubble, queue=None, k_power=3,
+                        allocator=None):
+        """Gravitational-wave abundance on the circular polarisation basis, shape
+        ``(2, num_bins)`` (spectra.py:360-419)."""
+        hij_k = self._transform_components(hij, 6, queue)
+        projector.tensor_to_pol(queue, hij_k[0], hij_k[1], hij_k)
+        out = np.zeros((2, self.num_bins), dtype=np.float64)
+        out[0] = self.bin_power(hij_k[0], queue, k_power)
+        out[1] = self.bin_power(hij_k[1], queue, k_power)
+        return self.norm / 12 / float(np.asarray(hubble).reshape(-1)[0])**2 * out
