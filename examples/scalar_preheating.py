@@ -45,6 +45,9 @@ parser.add_argument("--initial-conditions", "-ic", choices=["rayleigh", "white"]
 parser.add_argument("--seed", type=int, default=49279)
 parser.add_argument("--spectra", action="store_true",
                     help="print the field power spectra at the end")
+parser.add_argument("--output", metavar="NAME", default=None,
+                    help="write energies, field statistics and spectra (every 5%% growth "
+                         "of the scale factor) to NAME.npz, like the reference's OutputFile")
 
 
 def init_rayleigh(p, decomp, f, dfdt, f0, potential, energy, expand, backend=None):
@@ -171,6 +174,35 @@ def main(argv=None):
         if p.gravitational_waves:
             derivs(None, fx=hij, lap=lap_hij)
 
+    # output as in the reference example (lines 135-190), minus the rho histogram
+    out = spectra = projector = None
+    if p.output is not None:
+        if decomp.rank == 0:
+            out = ps.OutputFile(name=p.output, runfile=__file__, grid_shape=p.grid_shape,
+                                proc_shape=p.proc_shape, dtype=p.dtype, mphi=p.mphi,
+                                gsq=p.gsq, initial_conditions=ic)
+        if slab:
+            dk = tuple(2 * np.pi / Li for Li in p.box_dim)
+            fft_out = ps.DFT(decomp, None, None, p.grid_shape, p.dtype)
+            spectra = ps.PowerSpectra(decomp, fft_out, dk, float(np.prod(p.box_dim)))
+            projector = ps.Projector(fft_out, h, dk, p.dx)
+    a_last_spec = [.1]
+
+    def output(t, a, hubble, energy, constraint):
+        f_stats = statistics(f)
+        if out is not None:
+            out.output("energy", t=t, a=a, hubble=hubble / a, constraint=constraint,
+                       eos=energy["pressure"] / energy["total"],
+                       **{k: np.asarray(v) for k, v in energy.items()})
+            out.output("statistics/f", t=t, a=a, **f_stats)
+        if spectra is not None and a / a_last_spec[0] >= 1.05:
+            a_last_spec[0] = a
+            spec_out = {"scalar": spectra(f)}
+            if p.gravitational_waves:
+                spec_out["gw"] = spectra.gw(dhijdt, projector, hubble)
+            if out is not None:
+                out.output("spectra", t=t, a=a, **spec_out)
+
     t, step_count = 0., 0
     if decomp.rank == 0:
         print("time\t\tscale factor\tconstraint\tms/step")
@@ -193,12 +225,16 @@ def main(argv=None):
         step_count += 1
         if step_count % 4 == 0 or t >= p.end_time:
             if device_loop:
-                a_now = float(expand.get()["a"])
+                rec = expand.get()
+                a_now, hubble_now = float(rec["a"]), float(rec["hubble"])
                 # energy of the current state for the output (stand-alone kernels)
-                constraint = float(expand.constraint(compute_energy(a_now)["total"]))
-            else:
-                a_now = float(expand.a[0])
+                energy = compute_energy(a_now)
                 constraint = float(expand.constraint(energy["total"]))
+            else:
+                a_now, hubble_now = float(expand.a[0]), float(expand.hubble[0])
+                constraint = float(expand.constraint(energy["total"]))
+            if p.output is not None:
+                output(t, a_now, hubble_now, energy, constraint)
             if decomp.rank == 0:
                 ms = (time() - start) * 1e3 / step_count
                 print(f"{t:<15.3f}\t{a_now:<15.6f}\t{constraint:<.3e}\t{ms:<.3f}")
@@ -214,6 +250,8 @@ def main(argv=None):
         if decomp.rank == 0:
             print("k bins", spectra.bin_width * np.arange(spectra.num_bins))
             print("scalar spectra", scalar_spectra)
+    if out is not None:
+        out.close()
     if decomp.rank == 0:
         print("Simulation complete")
     result = {"t": t, "steps": step_count, "a": a_now, "constraint": constraint,
