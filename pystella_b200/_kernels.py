@@ -109,7 +109,10 @@ def scalar_stage(*, fused, f_in, f_out, dfdt, kf, kdfdt, lap_f=None, h, dx=(1., 
         for t, (c, powers) in enumerate(V_terms):
             args.vcoef[t] = float(c)
             for m in range(nscalars):
-                args.vpower[t][m] = int(powers[m])
+                pw = int(powers[m])
+                if pw < 0 or pw > 127:
+                    raise ValueError("monomial powers must be in 0..127")
+                args.vpower[t][m] = pw
     if count_slots_only:
         n = lib.psb_scalar_stage_energy_slots(C.byref(args))
         if n < 0:

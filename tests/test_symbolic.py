@@ -154,3 +154,71 @@ def test_sector_dictionaries():
     grad2 = sum((ctx["dfdx"][n]**2).sum() for n in range(2))
     lag = -(-kin / 1.2**2 + grad2 / 1.2**2) / 2 - 0.5**2 / 2
     assert np.isclose(T00, kin + (-1.2**2) * lag)
+
+
+# ---------------------------------------------------------------------------------------
+# property test: what the stage kernels are told (coefficients, powers) == the symbolic RHS
+# ---------------------------------------------------------------------------------------
+
+from hypothesis import given, settings, strategies as st  # noqa: E402
+from pystella_b200.field import is_constant  # noqa: E402
+
+
+@st.composite
+def _potentials(draw):
+    n = draw(st.integers(1, 3))
+    nterms = draw(st.integers(1, 5))
+    terms = []
+    for _ in range(nterms):
+        powers = tuple(draw(st.integers(0, 4)) for _ in range(n))
+        if sum(powers) == 0:
+            powers = (2,) + powers[1:]
+        coef = draw(st.floats(-3, 3).filter(lambda c: abs(c) > 1e-3))
+        terms.append((coef, powers))
+    return n, terms
+
+
+@settings(max_examples=40, deadline=None)
+@given(_potentials(), st.integers(0, 2**31 - 1))
+def test_recognised_system_equals_symbolic_rhs(pot, seed):
+    """For random polynomial potentials: the (coefficient, powers) tables handed to the
+    C ABI, evaluated the way the kernels do (oracle.poly_eval), reproduce the sector's
+    symbolic right-hand sides and potential at random field values -- for both front ends
+    (the sector shortcut and the generic rhs_dict recogniser)."""
+    import oracle as O
+    from pystella_b200.step import recognise_scalar_system, scalar_system_from_sector
+    n, terms = pot
+
+    def potential(f):
+        total = 0
+        for c, pw in terms:
+            mono = c
+            for m, p in enumerate(pw):
+                if p:
+                    mono = mono * f[m]**p
+            total = total + mono
+        return total
+
+    sector = ps.ScalarSector(n, potential=potential)
+    rng = np.random.default_rng(seed)
+    fv, dv, lv = rng.random(n) + 0.5, rng.random(n), rng.random(n)
+    a, hubble = 1.3, 0.2
+    ctx = {"f": fv, "dfdt": dv, "lap_f": lv, "a": a, "hubble": hubble}
+    f = ps.DynamicField("f", offset="h", shape=(n,))
+    want_rhs = [float(evaluate(sector.rhs_dict[f.dot[i]], ctx)) for i in range(n)]
+    want_V = float(sum(c * np.prod(fv**np.array(pw)) for c, pw in terms))
+
+    for system, a_factor in ((scalar_system_from_sector(sector), a**2),
+                             (recognise_scalar_system(sector.rhs_dict), 1.0)):
+        assert system.nscalars == n
+        hub = float(evaluate(system.hubble, ctx))
+        assert np.isclose(hub, hubble, rtol=1e-14)
+        for i in range(n):
+            dV = [(float(c) if is_constant(c) else float(evaluate(c, ctx)), p)
+                  for c, p in system.dV[i]]
+            got = (lv[i] - 2 * hub * dv[i]) - a_factor * O.poly_eval(dV, list(fv))
+            assert np.isclose(got, want_rhs[i], rtol=1e-11, atol=1e-12), (i, terms)
+        if system.V is not None:
+            V = [(float(c) if is_constant(c) else float(evaluate(c, ctx)), p)
+                 for c, p in system.V]
+            assert np.isclose(O.poly_eval(V, list(fv)), want_V, rtol=1e-12, atol=1e-13)
