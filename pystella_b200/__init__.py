@@ -27,6 +27,7 @@ from pystella_b200.reduction import Reduction, FieldStatistics
 from pystella_b200.expansion import Expansion, DeviceExpansion
 from pystella_b200.fourier import DFT, RayleighGenerator, PowerSpectra
 from pystella_b200.projectors import Projector
+from pystella_b200.spectral import SpectralCollocator, SpectralPoissonSolver
 from pystella_b200.histogram import Histogrammer, FieldHistogrammer
 from pystella_b200 import output
 from pystella_b200.output import OutputFile
@@ -52,7 +53,8 @@ def choose_device(local_rank=None):
 __all__ = [
     "Field", "DynamicField", "index_fields", "shift_fields", "substitute", "diff",
     "get_field_args", "var",
-    "DFT", "RayleighGenerator", "PowerSpectra", "Projector", "Histogrammer", "FieldHistogrammer",
+    "DFT", "RayleighGenerator", "PowerSpectra", "Projector",
+    "SpectralCollocator", "SpectralPoissonSolver", "Histogrammer", "FieldHistogrammer",
     "OutputFile",
     "Sector", "ScalarSector", "TensorPerturbationSector", "tensor_index",
     "get_rho_and_p",
