@@ -13,7 +13,7 @@ from pystella_b200.field import (Field, DynamicField, index_fields, shift_fields
 from pystella_b200.sectors import (Sector, ScalarSector, TensorPerturbationSector,
                                    tensor_index, get_rho_and_p)
 from pystella_b200.step import (
-    ElementWiseMap, FusedStencilStage, Stepper,
+    ElementWiseMap, FusedStencilStage, Stencil, StreamingStencil, Stepper,
     RungeKutta4, RungeKutta3SSP, RungeKutta3Heun, RungeKutta3Nystrom,
     RungeKutta3Ralston, RungeKutta2Midpoint, RungeKutta2Heun, RungeKutta2Ralston,
     LowStorageRK54, LowStorageRK144, LowStorageRK134, LowStorageRK124,
@@ -50,6 +50,12 @@ def choose_device(local_rank=None):
     return torch.device("cuda", local_rank)
 
 
+def choose_device_and_make_context(platform_choice=None, device_choice=None):
+    """The reference's entry point (``pystella/__init__.py:45-102``): binds the process to
+    its GPU and returns the ``torch.device`` (there is no context object to make)."""
+    return choose_device(device_choice if isinstance(device_choice, int) else None)
+
+
 __all__ = [
     "Field", "DynamicField", "index_fields", "shift_fields", "substitute", "diff",
     "get_field_args", "var",
@@ -58,7 +64,8 @@ __all__ = [
     "OutputFile",
     "Sector", "ScalarSector", "TensorPerturbationSector", "tensor_index",
     "get_rho_and_p",
-    "ElementWiseMap", "FusedStencilStage", "Stepper",
+    "ElementWiseMap", "FusedStencilStage", "Stencil", "StreamingStencil", "Stepper",
+    "choose_device_and_make_context",
     "RungeKutta4", "RungeKutta3SSP", "RungeKutta3Heun", "RungeKutta3Nystrom",
     "RungeKutta3Ralston", "RungeKutta2Midpoint", "RungeKutta2Heun",
     "RungeKutta2Ralston",

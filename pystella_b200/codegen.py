@@ -35,13 +35,16 @@ _C_FUNCS = {"fabs": "fabs", "abs": "fabs", "sqrt": "sqrt", "exp": "exp", "log": 
 
 
 class _Ref:
-    """One array operand: tensor name, constant outer subscript, stencil shift."""
+    """One array operand: tensor name, constant outer subscript, stencil shift.  A raw
+    ``var("x")[i + a, j + b, k + c]`` operand has no Field: ``shift`` then holds the
+    absolute offsets ``(a, b, c)`` into the array as passed (``absolute``)."""
 
-    def __init__(self, field, subscript, shift):
+    def __init__(self, field, subscript, shift, name=None):
         self.field = field
-        self.name = field.name
+        self.name = field.name if field is not None else name
         self.subscript = tuple(subscript)
         self.shift = tuple(shift)
+        self.absolute = field is None
 
     @property
     def key(self):
@@ -56,8 +59,43 @@ def _is_array(fld):
     return isinstance(fld, Field) and len(fld.indices) > 0
 
 
+_HALO_VALUES = {}       # h, hx, hy, hz while a kernel is being generated
+
+
+def _raw_ref(e):
+    """``var("x")[..., i + a, j + b, k + c]`` (the reference's tests index plain variables
+    this way, test/test_stencil.py:48-56) -> _Ref with absolute offsets, else None."""
+    if not (isinstance(e, Subscript) and isinstance(e.aggregate, Variable)
+            and len(e.index) >= 3):
+        return None
+    from pystella_b200.field import evaluate
+    offsets = []
+    for axis, idx in zip("ijk", e.index[-3:]):
+        names = {n.name for n in _walk_vars(idx)}
+        if axis not in names or names - {axis, "h", "hx", "hy", "hz"}:
+            return None
+        base = dict(_HALO_VALUES, i=0, j=0, k=0)
+        try:
+            at0 = evaluate(idx, base)
+            at1 = evaluate(idx, dict(base, **{axis: 1}))
+        except KeyError:
+            raise ValueError("pass halo_shape= to fix `h` in array subscripts") from None
+        if at1 - at0 != 1 or int(at0) != at0:
+            return None
+        offsets.append(int(at0))
+    return _Ref(None, _const_index(e.index[:-3]), offsets, name=e.aggregate.name)
+
+
+def _walk_vars(e):
+    from pystella_b200.field import _walk
+    return [n for n in _walk(e) if isinstance(n, Variable)]
+
+
 def _as_ref(e):
     """-> _Ref if ``e`` denotes an array element, else None."""
+    raw = _raw_ref(e)
+    if raw is not None:
+        return raw
     if isinstance(e, Field) and _is_array(e):
         sub = e.child.index if isinstance(e.child, Subscript) else ()
         return _Ref(e, _const_index(sub), _field_shift(e))
@@ -134,16 +172,18 @@ def expr_to_c(e, leaf):
 class KernelSource:
     """Generated source + the binding tables the launcher needs."""
 
-    def __init__(self, source, name, slots, scalars, dtype):
+    def __init__(self, source, name, slots, scalars, dtype, domain_slots=()):
         self.source = source
         self.name = name
-        self.slots = slots          # list of (array name, outer subscript, Field)
+        self.slots = slots          # list of (array name, outer subscript, Field or None)
         self.scalars = scalars      # list of scalar names
         self.dtype = dtype
+        #: raw (Field-less) arrays written at offset (0, 0, 0): their shape is the domain
+        self.domain_slots = tuple(domain_slots)
 
 
 def generate_kernel(map_instructions, tmp_instructions=None, dtype="double",
-                    name="psb_generated_map"):
+                    name="psb_generated_map", halo_shape=None):
     """
     ``map_instructions`` / ``tmp_instructions``: lists of ``(assignee, expr)`` (dicts
     are accepted).  Temporaries (Variables) are evaluated first, in order; then every
@@ -158,6 +198,11 @@ def generate_kernel(map_instructions, tmp_instructions=None, dtype="double",
     tmps, maps = as_list(tmp_instructions), as_list(map_instructions)
     if not maps:
         raise ValueError("no map instructions")
+    _HALO_VALUES.clear()
+    if halo_shape is not None:
+        hs = (halo_shape,) * 3 if isinstance(halo_shape, (int, np.integer)) \
+            else tuple(halo_shape)
+        _HALO_VALUES.update(h=hs[0], hx=hs[0], hy=hs[1], hz=hs[2])
 
     slots, slot_index = [], {}
     refs, scalars = {}, []
@@ -206,16 +251,18 @@ def generate_kernel(map_instructions, tmp_instructions=None, dtype="double",
         ref = _as_ref(lhs)
         if ref is None:
             raise ValueError("map assignees must be Fields (array elements)")
-        if any(ref.shift):
+        if any(ref.shift) and not ref.absolute:
             raise NotImplementedError("assignment to a shifted array element")
         code = expr_to_c(rhs, leaf)
         info = local_of(ref)
         body.append(f"  {info['var']} = {code};")
         info["written"] = True
     # a shifted read of an array that is also written would see a mix of old and new
-    written = {info["ref"].slot_key for info in refs.values() if info["written"]}
+    written = {info["ref"].slot_key: info["ref"].shift
+               for info in refs.values() if info["written"]}
     for info in refs.values():
-        if any(info["ref"].shift) and info["ref"].slot_key in written:
+        key = info["ref"].slot_key
+        if key in written and info["ref"].shift != written[key]:
             raise NotImplementedError(
                 f"stencil read of '{info['ref'].name}', which the same kernel writes "
                 "(evaluate the stencil into a separate array first)")
@@ -229,6 +276,8 @@ def generate_kernel(map_instructions, tmp_instructions=None, dtype="double",
         "};",
         "#define IDX(h, si, sj, sk) ((((long long)(i + (h) + (si))) * (Ny + 2 * (h)) + "
         "(j + (h) + (sj))) * (Nz + 2 * (h)) + (k + (h) + (sk)))",
+        "#define IDXA(h, a, b, c) ((((long long)(i + (a))) * (Ny + 2 * (h)) + "
+        "(j + (b))) * (Nz + 2 * (h)) + (k + (c)))",
         f'extern "C" __global__ void __launch_bounds__(256) {name}(const psb_jit_args args) {{',
         "  const long long Ny = args.Ny, Nz = args.Nz;",
         "  const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;",
@@ -240,7 +289,8 @@ def generate_kernel(map_instructions, tmp_instructions=None, dtype="double",
         lines.append(f"  const T s_{sname} = (T)args.scalars[{n}];")
     for info in refs.values():
         s, (si, sj, sk) = info["slot"], info["ref"].shift
-        addr = f"((T*)args.arrays[{s}])[IDX(args.halos[{s}], {si}, {sj}, {sk})]"
+        macro = "IDXA" if info["ref"].absolute else "IDX"
+        addr = f"((T*)args.arrays[{s}])[{macro}(args.halos[{s}], {si}, {sj}, {sk})]"
         info["addr"] = addr
         if info["read"]:
             lines.append(f"  T {info['var']} = {addr};")
@@ -251,7 +301,10 @@ def generate_kernel(map_instructions, tmp_instructions=None, dtype="double",
         if info["written"]:
             lines.append(f"  {info['addr']} = {info['var']};")
     lines.append("}")
-    return KernelSource("\n".join(lines) + "\n", name, slots, scalars, dtype)
+    domain = sorted({info["slot"] for info in refs.values()
+                     if info["written"] and info["ref"].absolute
+                     and not any(info["ref"].shift)})
+    return KernelSource("\n".join(lines) + "\n", name, slots, scalars, dtype, domain)
 
 
 # ---------------------------------------------------------------------------
@@ -302,6 +355,40 @@ class JitLibrary:
         return h
 
 
+def infer_layout(ksrc, view_shapes, rank_shape, halo_of):
+    """
+    -> ``(rank_shape, [halo per array slot])`` for arrays of the given 3-D shapes.  The
+    domain is ``rank_shape`` if given, else the interior of the first Field operand, else
+    the shape of a Field-less array written at offset (0, 0, 0); the padding of Field-less
+    arrays is inferred from their shapes.
+    """
+    shape = tuple(rank_shape) if rank_shape is not None else None
+    if shape is None:
+        for vs, (name, sub, field) in zip(view_shapes, ksrc.slots):
+            if field is not None:
+                h = halo_of(field)
+                shape = tuple(s - 2 * h for s in vs)
+                break
+    if shape is None and ksrc.domain_slots:
+        shape = tuple(view_shapes[ksrc.domain_slots[0]])
+    if shape is None:
+        raise ValueError("cannot infer the domain: pass rank_shape=")
+    halos = []
+    for vs, (name, sub, field) in zip(view_shapes, ksrc.slots):
+        if field is not None:
+            h = halo_of(field)
+        else:
+            h, rem = divmod(vs[0] - shape[0], 2)
+            if rem or h < 0:
+                raise ValueError(f"'{name}' has shape {tuple(vs)}, not the domain "
+                                 f"{shape} plus symmetric padding")
+        if tuple(s - 2 * h for s in vs) != shape:
+            raise ValueError(f"'{name}' has rank shape {tuple(s - 2 * h for s in vs)}, "
+                             f"expected {shape}")
+        halos.append(h)
+    return shape, halos
+
+
 class GenericMap:
     """
     A compiled element-wise map: the run-time generated counterpart of
@@ -313,7 +400,8 @@ class GenericMap:
                  halo_shape=None, rank_shape=None):
         self.dtype = np.dtype(dtype)
         ctype = {"float64": "double", "float32": "float"}[self.dtype.name]
-        self.ksrc = generate_kernel(map_instructions, tmp_instructions, ctype)
+        self.ksrc = generate_kernel(map_instructions, tmp_instructions, ctype,
+                                    halo_shape=halo_shape)
         self.halo_shape = halo_shape
         self.rank_shape = tuple(rank_shape) if rank_shape is not None else None
         self._handle = None
@@ -337,7 +425,8 @@ class GenericMap:
         args = JitArgs()
         shape = self.rank_shape
         want = getattr(torch, self.dtype.name)
-        for n, (name, sub, field) in enumerate(self.ksrc.slots):
+        views = []
+        for name, sub, field in self.ksrc.slots:
             if name not in kwargs:
                 raise TypeError(f"missing array argument '{name}'")
             t = _lib.require_cuda_tensor(kwargs[name], name)
@@ -349,14 +438,12 @@ class GenericMap:
                 raise ValueError(f"'{name}{list(sub)}' is not a 3-D array")
             if not view.is_contiguous():
                 raise ValueError(f"'{name}{list(sub)}' is not contiguous (z fastest)")
-            h = self._halo_of(field)
-            this = tuple(s - 2 * h for s in view.shape)
-            if shape is None:
-                shape = this
-            elif this != tuple(shape):
-                raise ValueError(f"'{name}' has rank shape {this}, expected {tuple(shape)}")
+            views.append(view)
+        shape, halos = infer_layout(self.ksrc, [tuple(v.shape) for v in views], shape,
+                                    self._halo_of)
+        for n, view in enumerate(views):
             args.arrays[n] = view.data_ptr()
-            args.halos[n] = h
+            args.halos[n] = halos[n]
         for n, sname in enumerate(self.ksrc.scalars):
             base, _, idx = sname.partition("__")
             if base not in kwargs:

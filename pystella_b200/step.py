@@ -80,6 +80,35 @@ class ElementWiseMap:
         return self._generic(queue, filter_args=filter_args, **kwargs)
 
 
+class Stencil(ElementWiseMap):
+    """
+    ``Stencil(map_instructions, halo_shape, prefetch_args=[...], **kwargs)``
+    (``pystella/stencil.py:36-98``): an element-wise map whose statements read neighbouring
+    sites.  The reference stages ``prefetch_args`` in local memory; the generated kernel
+    reads neighbours through L1/L2 instead, so the argument only names the stencilled
+    arrays (the hand-written stencil kernels are :class:`FiniteDifferencer` and
+    :class:`FusedStencilStage`).  Needs the generated kernels (``jit=True`` / ``PSB_JIT=1``).
+    As a ``MapKernel`` class it behaves like :class:`ElementWiseMap`.
+    """
+
+    def __init__(self, map_instructions=None, halo_shape=None, **kwargs):
+        self.prefetch_args = kwargs.pop("prefetch_args", [])
+        kwargs.pop("lsize", None)
+        if map_instructions is not None and halo_shape is None:
+            raise TypeError("Stencil requires halo_shape")
+        super().__init__(map_instructions, halo_shape=halo_shape, **kwargs)
+
+
+class StreamingStencil(Stencil):
+    """``pystella/stencil.py:101-143``: the streaming-prefetch variant; same semantics."""
+
+    def __init__(self, map_instructions=None, halo_shape=None, **kwargs):
+        if len(kwargs.get("prefetch_args", [])) > 1:
+            raise NotImplementedError(
+                "Streaming codegen can only handle one prefetch array for now")
+        super().__init__(map_instructions, halo_shape, **kwargs)
+
+
 class FusedStencilStage(ElementWiseMap):
     """
     ``MapKernel`` that evaluates ``lap_f`` in-kernel from ``f`` (TMA-staged tile,

@@ -351,3 +351,42 @@ def test_generated_reducers_on_host():
     fi = fh[h:-h, h:-h, h:-h]
     assert np.allclose(arrays["_psb_reducer_0"], np.cos(fi) * gh / 1.7, rtol=1e-14)
     assert np.allclose(arrays["_psb_reducer_1"], fi**0.5, rtol=1e-14)
+
+
+@pytest.mark.parametrize("h", [1, 2])
+@pytest.mark.parametrize("cls", ["Stencil", "StreamingStencil"])
+def test_stencil_map_with_raw_subscripts_on_host(h, cls):
+    """test/test_stencil.py:36-90 verbatim in form: plain variables subscripted with
+    ``i + h +- h``; padding and domain are inferred from the arrays."""
+    from pystella_b200.field import var
+    rng = np.random.default_rng(9)
+    x, y = var("x"), var("y")
+    i, j, k = var("i"), var("j"), var("k")
+    map_dict = {y[i, j, k]: (x[i + h + h, j + h, k + h] + x[i + h, j + h + h, k + h]
+                             + x[i + h, j + h, k + h + h] + x[i - h + h, j + h, k + h]
+                             + x[i + h, j - h + h, k + h] + x[i + h, j + h, k - h + h])}
+    with pytest.raises(NotImplementedError, match="jit"):
+        getattr(ps, cls)(map_dict, h, prefetch_args=["x"])
+    with pytest.raises(TypeError):
+        ps.Stencil(map_dict, jit=True)
+    stencil_map = getattr(ps, cls)(map_dict, h, prefetch_args=["x"], jit=True)
+    assert stencil_map.prefetch_args == ["x"]
+    ksrc = stencil_map._generic.ksrc
+    N = (6, 5, 7)
+    x_h = rng.random(tuple(n + 2 * h for n in N))
+    y_h = rng.random(N)
+    shape, halos = codegen.infer_layout(ksrc, [x_h.shape, y_h.shape], None, None)
+    assert shape == N and halos == [h, 0]
+    _run_generated_on_host(ksrc, {"x": x_h, "y": y_h}, {"x": h, "y": 0}, {}, N)
+    y_true = (x_h[2*h:, h:-h, h:-h] + x_h[h:-h, 2*h:, h:-h] + x_h[h:-h, h:-h, 2*h:]
+              + x_h[:-2*h, h:-h, h:-h] + x_h[h:-h, :-2*h, h:-h] + x_h[h:-h, h:-h, :-2*h])
+    assert O_get_errs(y_true, y_h) < 5e-14
+    with pytest.raises(ValueError, match="symmetric padding"):
+        codegen.infer_layout(ksrc, [(N[0] + 3,) + x_h.shape[1:], y_h.shape], None, None)
+    with pytest.raises(NotImplementedError):
+        ps.StreamingStencil(map_dict, h, prefetch_args=["x", "y"], jit=True)
+
+
+def O_get_errs(a, b):
+    import oracle as O
+    return O.get_errs(a, b)[0]

@@ -203,3 +203,23 @@ def test_distributed_fourier_nccl():
         pytest.skip("needs 2 GPUs")
     from test_distributed import _run
     _run("gpu_fourier", 2)
+
+
+@pytest.mark.parametrize("cls", ["Stencil", "StreamingStencil"])
+def test_stencil_map_raw_subscripts(cls):
+    """test/test_stencil.py:36-90 through the generated kernels."""
+    from pystella_b200.field import var
+    rng = np.random.default_rng(16)
+    h, N = 2, (16, 12, 40)
+    x, y = var("x"), var("y")
+    i, j, k = var("i"), var("j"), var("k")
+    map_dict = {y[i, j, k]: (x[i + h + h, j + h, k + h] + x[i + h, j + h + h, k + h]
+                             + x[i + h, j + h, k + h + h] + x[i - h + h, j + h, k + h]
+                             + x[i + h, j - h + h, k + h] + x[i + h, j + h, k - h + h])}
+    stencil_map = getattr(ps, cls)(map_dict, h, prefetch_args=["x"], jit=True)
+    x_h = rng.random(tuple(n + 2 * h for n in N))
+    yd = torch.zeros(N, dtype=torch.float64, device="cuda")
+    stencil_map(None, x=to_dev(x_h), y=yd)
+    y_true = (x_h[2*h:, h:-h, h:-h] + x_h[h:-h, 2*h:, h:-h] + x_h[h:-h, h:-h, 2*h:]
+              + x_h[:-2*h, h:-h, h:-h] + x_h[h:-h, :-2*h, h:-h] + x_h[h:-h, h:-h, :-2*h])
+    assert O.get_errs(y_true, yd.cpu().numpy())[0] < 5e-14
