@@ -268,6 +268,32 @@ typedef struct psb_reduce_args {
 int64_t psb_reduce_workspace_doubles(int noutputs);
 int psb_reduce(const psb_reduce_args* args, void* stream);
 
+/* ------------------------------------------------------------------------
+ * Launch plan of the fused stage for an externally compiled kernel instance
+ * (EXPERIMENTAL; row f-2 of the scope table): pystella accepts arbitrary right-hand
+ * sides (pystella/step.py:473-491); for systems outside the polynomial menu the
+ * Python layer compiles pystella_b200/csrc/fused_stage_ws.cuh at run time with a
+ * generated RHS functor (NVRTC, include/pystella_b200_jit.h) and launches that instance
+ * with exactly the parameters the built-in launch would use.  This entry computes them
+ * without launching: the template arguments of the instance that matches the layout,
+ * the launch geometry, the by-value kernel parameter block and the four TMA
+ * descriptors (f_in, dfdt, kf, kdfdt).  Returns 3 when the layout is not eligible for
+ * the TMA pipeline (odd extents / unaligned pointers).
+ * ---------------------------------------------------------------------- */
+#define PSB_FUSED_PLAN_PARAM_BYTES 4096
+typedef struct psb_fused_plan {
+  int32_t dtype, h, nscalars;          /* T, H, NF                                    */
+  int32_t by, tz, p, minb, vec, energy;/* BY, TZ, P, MINB, VEC, ENERGY                */
+  uint32_t grid[3], threads, smem_bytes, params_bytes;
+  int32_t reserved;                    /* in: non-zero = dry run (geometry and parameter
+                                          block only, descriptors left zero; needs no
+                                          driver).  Keeps the descriptors at offset 64 */
+  unsigned char tensor_maps[4][128];   /* CUtensorMap x 4                             */
+  unsigned char params[PSB_FUSED_PLAN_PARAM_BYTES]; /* psb::FusedParams<T, NF>        */
+} psb_fused_plan;
+
+int psb_scalar_stage_fused_plan(const psb_scalar_stage_args* args, psb_fused_plan* plan);
+
 /* Number of energy-partial rows one psb_scalar_stage_fused launch with these
  * args writes (one per CTA). */
 int64_t psb_scalar_stage_energy_slots(const psb_scalar_stage_args* args);

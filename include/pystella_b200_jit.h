@@ -42,6 +42,30 @@ int psb_jit_launch(int64_t handle, const psb_jit_args* args, unsigned gx, unsign
                    unsigned gz, unsigned bx, unsigned by, unsigned bz, void* stream);
 int psb_jit_release(int64_t handle);
 
+/* General form used for the generated-RHS instantiation of the fused stage pipeline
+ * (pystella_b200/csrc/fused_stage_ws.cuh compiled with PSB_GENERATED_RHS):
+ *  - `options`: NVRTC options (include paths, defines); the architecture is appended;
+ *  - `header_names` / `header_sources`: in-memory headers (stand-ins for the host system
+ *    headers the device sources include);
+ *  - `name_expression`: a C++ name expression of a __global__ template instance (its
+ *    lowered name is looked up), or NULL when `kernel_name` is an extern "C" symbol. */
+int64_t psb_jit_compile_ex(const char* source, const char* kernel_name,
+                           const char* name_expression, const char* arch,
+                           const char* const* options, int noptions,
+                           const char* const* header_names,
+                           const char* const* header_sources, int nheaders);
+/* Lowered (mangled) symbol name of the compiled kernel. */
+const char* psb_jit_kernel_symbol(int64_t handle);
+/* Number of registers per thread / static shared memory of the compiled kernel are not
+ * available without a device; the cubin can be inspected with cuobjdump instead. */
+int psb_jit_write_cubin(int64_t handle, const char* path);
+/* Launch with an arbitrary parameter list: params[i] points to the i-th kernel parameter
+ * (cuLaunchKernel semantics).  `smem_bytes` of dynamic shared memory are opted into on
+ * first use. */
+int psb_jit_launch_params(int64_t handle, void** params, unsigned gx, unsigned gy,
+                          unsigned gz, unsigned bx, unsigned by, unsigned bz,
+                          unsigned smem_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -39,7 +39,7 @@ def scalar_stage(*, fused, f_in, f_out, dfdt, kf, kdfdt, lap_f=None, h, dx=(1., 
                  dV_terms=None, wrap=(True, True, True), x_range=None,
                  queue=None, strict=False, xchunk=0, variant=0,
                  energy_partials=None, energy_slot_offset=0, V_terms=None,
-                 count_slots_only=False, peer=None):
+                 count_slots_only=False, peer=None, generated=None):
     """
     One scalar-sector LSRK stage on padded arrays of shape ``(n, Nx+2h, Ny+2h, Nz+2h)``
     (or without the leading axis for a single field).
@@ -123,6 +123,13 @@ def scalar_stage(*, fused, f_in, f_out, dfdt, kf, kdfdt, lap_f=None, h, dx=(1., 
             raise ValueError("energy partials come from the fused stage only")
         args.energy_partials = _ptr(energy_partials)
         args.energy_slot_offset = energy_slot_offset
+    if generated is not None:
+        # EXPERIMENTAL: the same pipeline, compiled at run time with a generated RHS
+        if not fused:
+            raise ValueError("generated right-hand sides exist for the fused stage only")
+        launcher, values = generated
+        launcher.launch(lib, args, queue, values, strict)
+        return
     fn = lib.psb_scalar_stage_fused if fused else lib.psb_scalar_stage_unfused
     rc = fn(C.byref(args), _lib.stream_ptr(queue))
     _lib.check(lib, rc, fn.__name__)

@@ -110,6 +110,19 @@ class ReduceArgs(C.Structure):
 
 
 #: every symbol include/pystella_b200.h declares: (restype, argtypes)
+class FusedPlan(C.Structure):
+    """psb_fused_plan: launch parameters of the fused stage for an external kernel."""
+    _fields_ = [
+        ("dtype", c_int32), ("h", c_int32), ("nscalars", c_int32),
+        ("by", c_int32), ("tz", c_int32), ("p", c_int32), ("minb", c_int32),
+        ("vec", c_int32), ("energy", c_int32),
+        ("grid", C.c_uint32 * 3), ("threads", C.c_uint32), ("smem_bytes", C.c_uint32),
+        ("params_bytes", C.c_uint32), ("reserved", c_int32),
+        ("tensor_maps", (C.c_ubyte * 128) * 4),
+        ("params", C.c_ubyte * 4096),
+    ]
+
+
 SYMBOLS = {
     "psb_last_error": (C.c_char_p, []),
     "psb_abi_version": (c_int, []),
@@ -136,6 +149,8 @@ SYMBOLS = {
     "psb_reduce_workspace_doubles": (c_int64, [c_int]),
     "psb_reduce": (c_int, [C.POINTER(ReduceArgs), c_void_p]),
     "psb_scalar_stage_energy_slots": (c_int64, [C.POINTER(ScalarStageArgs)]),
+    "psb_scalar_stage_fused_plan": (c_int, [C.POINTER(ScalarStageArgs),
+                                            C.POINTER(FusedPlan)]),
     "psb_energy_sums": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "psb_expansion_stage": (c_int, [c_void_p, c_int, c_double, c_double, c_double,
                                     c_double, c_double, c_void_p, c_void_p, c_void_p]),

@@ -340,6 +340,17 @@ class JitLibrary:
                 + [C.c_void_p]
             lib.psb_jit_release.restype = C.c_int
             lib.psb_jit_release.argtypes = [C.c_int64]
+            lib.psb_jit_compile_ex.restype = C.c_int64
+            lib.psb_jit_compile_ex.argtypes = [
+                C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_char_p),
+                C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.c_int]
+            lib.psb_jit_kernel_symbol.restype = C.c_char_p
+            lib.psb_jit_kernel_symbol.argtypes = [C.c_int64]
+            lib.psb_jit_write_cubin.restype = C.c_int
+            lib.psb_jit_write_cubin.argtypes = [C.c_int64, C.c_char_p]
+            lib.psb_jit_launch_params.restype = C.c_int
+            lib.psb_jit_launch_params.argtypes = [C.c_int64, C.POINTER(C.c_void_p)] \
+                + [C.c_uint] * 7 + [C.c_void_p]
             cls._lib = lib
         return cls._lib
 

@@ -1,10 +1,27 @@
 // Shared helpers for the pystella_b200 CUDA translation units (sm_100a only).
 #pragma once
 
+#ifndef __CUDACC_RTC__
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#else
+// NVRTC (generated-RHS instantiation of the fused pipeline, see fused_stage_ws.cuh): no
+// host headers; the few types the device code needs are spelled out here
+typedef signed char int8_t;
+typedef unsigned char uint8_t;
+typedef short int16_t;
+typedef unsigned short uint16_t;
+typedef int int32_t;
+typedef unsigned int uint32_t;
+typedef long long int64_t;
+typedef unsigned long long uint64_t;
+typedef struct CUtensorMap_st {
+  alignas(64) unsigned long long opaque[16];
+} CUtensorMap;
+typedef struct CUstream_st* cudaStream_t;
+#endif
 
 #include "pystella_b200.h"
 
@@ -30,6 +47,7 @@ void set_error(const char* fmt, ...);
     }                                                                          \
   } while (0)
 
+#ifndef __CUDACC_RTC__
 inline int num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -40,6 +58,7 @@ inline int num_sms() {
   }
   return n;
 }
+#endif
 
 // --------------------------------------------------------------------------
 // finite-difference coefficient tables (pystella/derivs.py:127-131, 160-165),

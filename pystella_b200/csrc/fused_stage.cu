@@ -3,6 +3,7 @@
 #include "common.cuh"
 
 namespace psb {
+thread_local psb_fused_plan* t_fused_plan = nullptr;
 int fused_dispatch_f64(const psb_scalar_stage_args* a, cudaStream_t s, int64_t* count);
 int fused_dispatch_f32(const psb_scalar_stage_args* a, cudaStream_t s, int64_t* count);
 
@@ -69,6 +70,20 @@ extern "C" int psb_scalar_stage_fused(const psb_scalar_stage_args* a, void* stre
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   return a->dtype == PSB_F64 ? fused_dispatch_f64(a, s, nullptr)
                              : fused_dispatch_f32(a, s, nullptr);
+}
+
+extern "C" int psb_scalar_stage_fused_plan(const psb_scalar_stage_args* a,
+                                           psb_fused_plan* plan) {
+  using namespace psb;
+  PSB_REQUIRE(plan != nullptr, "psb_scalar_stage_fused_plan: null plan");
+  if (int rc = validate(a)) return rc;
+  PSB_REQUIRE(a->x_begin != a->x_end || a->x2_begin != a->x2_end,
+              "psb_scalar_stage_fused_plan: empty x range");
+  t_fused_plan = plan;
+  const int rc = a->dtype == PSB_F64 ? fused_dispatch_f64(a, nullptr, nullptr)
+                                     : fused_dispatch_f32(a, nullptr, nullptr);
+  t_fused_plan = nullptr;
+  return rc;
 }
 
 extern "C" int64_t psb_scalar_stage_energy_slots(const psb_scalar_stage_args* a) {

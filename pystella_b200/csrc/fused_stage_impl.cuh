@@ -18,10 +18,12 @@
 // HBM traffic per site and stage: read f, dfdt, kf, kdfdt; write f, dfdt, kf,
 // kdfdt = 8*sizeof(T) (6*sizeof(T) when A == 0: the twins are not read).
 #pragma once
+#ifndef __CUDACC_RTC__
 #include <math.h>
 #include <string.h>
 
 #include <type_traits>
+#endif
 
 #include "common.cuh"
 
@@ -432,6 +434,11 @@ __global__ void __launch_bounds__(BY* TZ, MINB)
 // ---------------------------------------------------------------------------
 
 // chunking of the (up to two) x ranges of one launch along gridDim.z
+#ifndef __CUDACC_RTC__   // host side: launch geometry, parameter marshalling, dispatch
+// set (per thread) by psb_scalar_stage_fused_plan: the dispatch then fills the plan of
+// the instance it would launch instead of launching it
+extern thread_local psb_fused_plan* t_fused_plan;
+
 struct XLayout {
   int xchunk, n1, n2;
 };
@@ -548,8 +555,10 @@ static int64_t fused_grid_blocks(const psb_scalar_stage_args* a) {
   return ((a->Nz + C::BZ - 1) / C::BZ) * ((a->Ny + BY - 1) / BY) * (int64_t)(L.n1 + L.n2);
 }
 
+#endif  // !__CUDACC_RTC__
 }  // namespace psb
 #include "fused_stage_ws.cuh"
+#ifndef __CUDACC_RTC__
 namespace psb {
 
 constexpr int v1_smem_bytes(int es, int H, int NF, int VEC, int BY, int TZ, int P) {
@@ -570,6 +579,12 @@ constexpr int v1_pick_tz(int es, int H, int NF, int VEC, int BY, int P) {
 
 template <typename T, int H, int NF, int VEC, int BY, int TZ, int P, int MINB>
 static int fused_op(const psb_scalar_stage_args* a, cudaStream_t stream, int64_t* count) {
+  if (t_fused_plan) {
+    set_error("psb_scalar_stage_fused_plan: this layout is served by the cooperative "
+              "loader, not by the TMA pipeline (needs even Nz, 16-byte aligned rows and "
+              "pointers)");
+    return 3;
+  }
   if (count) {
     *count = fused_grid_blocks<T, H, NF, VEC, BY, TZ, P>(a);
     return 0;
@@ -579,6 +594,7 @@ static int fused_op(const psb_scalar_stage_args* a, cudaStream_t stream, int64_t
 
 template <typename T, int H, int NF, int BY, int TZ, int P, int MINB, int VEC = 2>
 static int ws_op(const psb_scalar_stage_args* a, cudaStream_t stream, int64_t* count) {
+  if (t_fused_plan) return plan_ws<T, H, NF, BY, TZ, P, MINB, VEC>(a, t_fused_plan);
   if (count) {
     *count = ws_grid_blocks<T, H, NF, BY, TZ, P, VEC>(a);
     return 0;
@@ -676,4 +692,4 @@ static int dispatch_h(const psb_scalar_stage_args* a, cudaStream_t stream,
 }
 
 }  // namespace psb
-
+#endif  // !__CUDACC_RTC__

@@ -103,6 +103,21 @@ __device__ __forceinline__ void st_pieces(T* p, const Vec<T, VEC>& x) {
   }
 }
 
+#ifdef PSB_GENERATED_RHS
+// Generated-RHS instantiation (run-time compiled with NVRTC by pystella_b200/codegen.py):
+// the translation unit defines, before including this header,
+//   template <typename T> __device__ void psb_generated_rhs(int n, const T* f, const T* d,
+//       const T* lap, T a, T hubble, const double* s, T& rhs_f, T& rhs_d);
+//   template <typename T> __device__ T psb_generated_potential(const T* f, T a, T hubble,
+//       const double* s);
+// (values of all fields at one site; user scalars in s) and the kernel gains one
+// parameter carrying those scalars.  Everything else -- rings, stencil, stores, halos,
+// energy folding -- is the code below, unchanged.
+struct PsbJitScalars {
+  double v[32];
+};
+#endif
+
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -114,7 +129,12 @@ __global__ void __launch_bounds__(BY* TZ + 32, MINB)
                           const __grid_constant__ CUtensorMap map_f,
                           const __grid_constant__ CUtensorMap map_d,
                           const __grid_constant__ CUtensorMap map_kf,
-                          const __grid_constant__ CUtensorMap map_kd) {
+                          const __grid_constant__ CUtensorMap map_kd
+#ifdef PSB_GENERATED_RHS
+                          ,
+                          const __grid_constant__ PsbJitScalars jit_scalars
+#endif
+) {
   using C = WsCfg<T, H, NF, BY, TZ, P, VEC_>;
   constexpr int VEC = C::VEC, GV = C::GV, W = C::W, HL = C::HL, RF = C::RF, RP = C::RP;
   using V = Vec<T, VEC>;
@@ -313,6 +333,12 @@ __global__ void __launch_bounds__(BY* TZ + 32, MINB)
               e_kin[f] += (double)(dv * dv);
               e_grad[f] += (double)(-(q[f][H].v[v] * lap[f].v[v]));
             }
+#ifdef PSB_GENERATED_RHS
+            T fsite[NF];
+#pragma unroll
+            for (int m = 0; m < NF; ++m) fsite[m] = q[m][H].v[v];
+            const T Vv = psb_generated_potential<T>(fsite, a, hubble, jit_scalars.v);
+#else
             T Vv = (T)0;
             for (int t = 0; t < p.nvterms; ++t) {
               T term = p.vcoef[t];
@@ -323,6 +349,7 @@ __global__ void __launch_bounds__(BY* TZ + 32, MINB)
               }
               Vv = Vv + term;
             }
+#endif
             e_pot += (double)Vv;
           }
         }
@@ -332,6 +359,27 @@ __global__ void __launch_bounds__(BY* TZ + 32, MINB)
           V fo, dn, kfn, kdn;
 #pragma unroll
           for (int v = 0; v < VEC; ++v) {
+#ifdef PSB_GENERATED_RHS
+            T fsite[NF], dsite[NF], lsite[NF];
+#pragma unroll
+            for (int m = 0; m < NF; ++m) {
+              fsite[m] = q[m][H].v[v];
+              dsite[m] = dold[m].v[v];
+              lsite[m] = lap[m].v[v];
+            }
+            const T d_old = dold[f].v[v];
+            T rhs_f, rhs_d;
+            psb_generated_rhs<T>(f, fsite, dsite, lsite, a, hubble, jit_scalars.v, rhs_f,
+                                 rhs_d);
+            T kfv, kdv;
+            if (read_k) {
+              kfv = p.A * kfo[f].v[v] + p.dt * rhs_f;
+              kdv = p.A * kdo[f].v[v] + p.dt * rhs_d;
+            } else {
+              kfv = p.dt * rhs_f;
+              kdv = p.dt * rhs_d;
+            }
+#else
             T dV = (T)0;
             for (int t = 0; t < p.nterms[f]; ++t) {
               T term = p.coef[f][t];
@@ -352,6 +400,7 @@ __global__ void __launch_bounds__(BY* TZ + 32, MINB)
               kfv = p.dt * d_old;
               kdv = p.dt * rhs_d;
             }
+#endif
             kfn.v[v] = kfv;
             kdn.v[v] = kdv;
             fo.v[v] = q[f][H].v[v] + p.B * kfv;
@@ -440,12 +489,63 @@ __global__ void __launch_bounds__(BY* TZ + 32, MINB)
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
+#ifndef __CUDACC_RTC__
 
 template <typename T, int H, int NF, int BY, int TZ, int P, int VEC = 2>
 static int64_t ws_grid_blocks(const psb_scalar_stage_args* a) {
   using C = WsCfg<T, H, NF, BY, TZ, P, VEC>;
   const XLayout L = x_layout(a, WS_DEFAULT_XCHUNK);
   return ((a->Nz + C::BZ - 1) / C::BZ) * ((a->Ny + BY - 1) / BY) * (int64_t)(L.n1 + L.n2);
+}
+
+// parameters of the launch of this instance, for an externally compiled kernel
+template <typename T, int H, int NF, int BY, int TZ, int P, int MINB, int VEC = 2>
+static int plan_ws(const psb_scalar_stage_args* a, psb_fused_plan* plan) {
+  using C = WsCfg<T, H, NF, BY, TZ, P, VEC>;
+  static_assert(sizeof(FusedParams<T, NF>) <= PSB_FUSED_PLAN_PARAM_BYTES, "plan too small");
+  static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap size");
+  const int64_t Px = a->Nx + 2 * H, Py = a->Ny + 2 * H, Pz = a->Nz + 2 * H;
+  const bool dry_run = plan->reserved != 0;   // geometry only (no driver needed)
+  memset(plan, 0, sizeof(*plan));
+  CUtensorMap maps[4];
+  memset(maps, 0, sizeof(maps));
+  if (dry_run) {
+    // descriptors stay zero
+  } else if (encode_field_tensor_map(&maps[0], a->dtype, a->f_in, NF, a->field_stride, Px, Py, Pz,
+                              1, C::ROWS, C::W) != 0 ||
+      encode_field_tensor_map(&maps[1], a->dtype, a->dfdt, NF, a->field_stride, Px, Py, Pz,
+                              1, BY, C::PWW) != 0 ||
+      encode_field_tensor_map(&maps[2], a->dtype, a->kf, NF, a->field_stride, Px, Py, Pz, 1,
+                              BY, C::PWW) != 0 ||
+      encode_field_tensor_map(&maps[3], a->dtype, a->kdfdt, NF, a->field_stride, Px, Py, Pz,
+                              1, BY, C::PWW) != 0) {
+    set_error("psb_scalar_stage_fused_plan: TMA descriptors could not be encoded");
+    return 3;
+  }
+  for (int m = 0; m < 4; ++m) memcpy(plan->tensor_maps[m], &maps[m], sizeof(CUtensorMap));
+  FusedParams<T, NF> p;
+  memset(&p, 0, sizeof(p));
+  fill_params<T, NF>(p, a);
+  const XLayout L = x_layout(a, WS_DEFAULT_XCHUNK);
+  p.xchunk = L.xchunk;
+  p.nchunks1 = L.n1;
+  memcpy(plan->params, &p, sizeof(p));
+  plan->params_bytes = (uint32_t)sizeof(p);
+  plan->dtype = a->dtype;
+  plan->h = H;
+  plan->nscalars = NF;
+  plan->by = BY;
+  plan->tz = TZ;
+  plan->p = P;
+  plan->minb = MINB;
+  plan->vec = VEC;
+  plan->energy = a->energy_partials != nullptr ? 1 : 0;
+  plan->grid[0] = (uint32_t)((a->Nz + C::BZ - 1) / C::BZ);
+  plan->grid[1] = (uint32_t)((a->Ny + BY - 1) / BY);
+  plan->grid[2] = (uint32_t)(L.n1 + L.n2);
+  plan->threads = C::THREADS;
+  plan->smem_bytes = C::SMEM_BYTES;
+  return 0;
 }
 
 // returns 0 ok, >0 error, -1 = layout not TMA-able (caller falls back)
@@ -487,5 +587,7 @@ static int launch_ws(const psb_scalar_stage_args* a, cudaStream_t stream) {
   PSB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
+
+#endif  // !__CUDACC_RTC__
 
 }  // namespace psb

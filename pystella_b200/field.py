@@ -541,6 +541,20 @@ def substitute(expr, variable_assignments=None, **kwargs):
 _XMU = {"t": 0, "x": 1, "y": 2, "z": 3}
 
 
+# d f(u) / du for the elementary functions the code generator knows
+_DERIVATIVES = {
+    "sin": lambda u: var("cos")(u),
+    "cos": lambda u: -1 * var("sin")(u),
+    "tan": lambda u: 1 + var("tan")(u)**2,
+    "exp": lambda u: var("exp")(u),
+    "log": lambda u: 1 / u,
+    "sqrt": lambda u: 1 / (2 * var("sqrt")(u)),
+    "sinh": lambda u: var("cosh")(u),
+    "cosh": lambda u: var("sinh")(u),
+    "tanh": lambda u: 1 - var("tanh")(u)**2,
+}
+
+
 def _diff1(e, x):
     coord = x.name if isinstance(x, Variable) and x.name in _XMU else None
     if is_constant(e):
@@ -582,7 +596,14 @@ def _diff1(e, x):
             return 0
         return e.exponent * e.base**(e.exponent - 1) * db
     if isinstance(e, Call):
-        raise NotImplementedError("derivative of a function call")
+        name = getattr(e.function, "name", None)
+        if len(e.parameters) != 1 or name not in _DERIVATIVES:
+            raise NotImplementedError(f"derivative of a call to {e.function}")
+        u = e.parameters[0]
+        du = _diff1(u, x)
+        if is_constant(du) and du == 0:
+            return 0
+        return _DERIVATIVES[name](u) * du
     raise TypeError(f"cannot differentiate {type(e)}")
 
 

@@ -414,18 +414,35 @@ class Stepper:
 
     # -- device systems -------------------------------------------------------
     def _build_systems(self):
+        def general(rhs_dict, potential, reason):
+            # EXPERIMENTAL: outside the polynomial menu the fused pipeline is compiled at
+            # run time with a generated right-hand side (pystella_b200/fused_jit.py)
+            if not (self.fused and jit_enabled(self.jit)):
+                raise reason
+            from pystella_b200.fused_jit import recognise_general_system
+            return recognise_general_system(rhs_dict, potential)
+
         systems = []
         if self._sectors is not None:
             for s in self._sectors:
                 if isinstance(s, self._ScalarSector):
-                    systems.append(scalar_system_from_sector(s))
+                    try:
+                        systems.append(scalar_system_from_sector(s))
+                    except NotImplementedError as exc:
+                        systems.append(general(s.rhs_dict, s.potential(s.f), exc))
                 elif isinstance(s, self._TensorSector):
                     from pystella_b200.gw import tensor_system_from_sector
                     systems.append(tensor_system_from_sector(s))
                 else:
-                    systems.append(recognise_scalar_system(s.rhs_dict))
+                    try:
+                        systems.append(recognise_scalar_system(s.rhs_dict))
+                    except NotImplementedError as exc:
+                        systems.append(general(s.rhs_dict, None, exc))
         else:
-            systems.append(recognise_scalar_system(self.rhs_dict))
+            try:
+                systems.append(recognise_scalar_system(self.rhs_dict))
+            except NotImplementedError as exc:
+                systems.append(general(self.rhs_dict, None, exc))
         return systems
 
     @property
@@ -630,6 +647,19 @@ class LowStorageRKStepper(Stepper):
                       a=scal["a"][0], hubble=scal["hubble"][0],
                       a_dev=scal["a"][1], hubble_dev=scal["hubble"][1],
                       dV_terms=dV, queue=queue, strict=self.strict_fp)
+        generated = getattr(system, "generated", None)
+        if generated is not None:
+            values = []
+            for name in system.user_scalars:
+                if name not in kwargs:
+                    raise TypeError(f"missing scalar argument '{name}'")
+                value = _scalar_value(kwargs[name])
+                if value is None:
+                    raise TypeError(f"scalar '{name}' of a generated right-hand side must "
+                                    "be a host value (only `a` and `hubble` may live on "
+                                    "the device)")
+                values.append(value)
+            common["generated"] = (generated, values)
         if not self.fused:
             lap = kwargs.get(system.lap_name)
             if lap is None:

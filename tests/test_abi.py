@@ -51,19 +51,25 @@ def test_struct_layout_matches_header():
            'sizeof(psb_scalar_stage_args), sizeof(psb_reduce_args));'
            'printf("%zu %zu %zu %zu\\n", sizeof(psb_tensor_stage_args), sizeof(psb_peer_args),'
            'sizeof(psb_rk_stage_args), sizeof(psb_tensor_fused_args));'
+           'printf("%zu %zu %zu\\n", sizeof(psb_fused_plan), '
+           '__builtin_offsetof(psb_fused_plan, tensor_maps), '
+           '__builtin_offsetof(psb_fused_plan, params));'
            'return 0;}')
     with tempfile.TemporaryDirectory() as d:
         c = os.path.join(d, "p.c")
         open(c, "w").write(src)
         exe = os.path.join(d, "p")
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
-        a, b, c, d, e, f = subprocess.check_output([exe]).split()
+        a, b, c, d, e, f, g, off_maps, off_params = subprocess.check_output([exe]).split()
     assert int(a) == ctypes.sizeof(_lib.ScalarStageArgs)
     assert int(b) == ctypes.sizeof(_lib.ReduceArgs)
     assert int(c) == ctypes.sizeof(_lib.TensorStageArgs)
     assert int(d) == ctypes.sizeof(_lib.PeerArgs)
     assert int(e) == ctypes.sizeof(_lib.RKStageArgs)
     assert int(f) == ctypes.sizeof(_lib.TensorFusedArgs)
+    assert int(g) == ctypes.sizeof(_lib.FusedPlan)
+    assert int(off_maps) == _lib.FusedPlan.tensor_maps.offset == 64
+    assert int(off_params) == _lib.FusedPlan.params.offset == 576
 
 
 def test_no_cpu_fallback():

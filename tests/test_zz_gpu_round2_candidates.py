@@ -223,3 +223,49 @@ def test_stencil_map_raw_subscripts(cls):
     y_true = (x_h[2*h:, h:-h, h:-h] + x_h[h:-h, 2*h:, h:-h] + x_h[h:-h, h:-h, 2*h:]
               + x_h[:-2*h, h:-h, h:-h] + x_h[h:-h, :-2*h, h:-h] + x_h[h:-h, h:-h, :-2*h])
     assert O.get_errs(y_true, yd.cpu().numpy())[0] < 5e-14
+
+
+@pytest.mark.parametrize("dtype, rtol", [("float64", 1e-12), ("float32", 2e-5)])
+def test_fused_stage_with_generated_rhs(dtype, rtol):
+    """Row f-2: a non-polynomial potential (axion-like, V = lam (1 - cos f) + g^2 f^2 chi^2/2)
+    through the fused TMA pipeline compiled at run time with a generated right-hand side ==
+    the oracle's schedule (share_halos -> lap -> rhs -> low-storage stage)."""
+    from pystella_b200.field import var
+    cos = var("cos")
+    lam = var("lam")
+    rng = np.random.default_rng(17)
+    N, h = (16, 16, 32), 2
+    dx = (0.2, 0.25, 0.3)
+    dt, a, hubble, lam_v = 0.01, 1.1, 0.2, 0.7
+    sector = ps.ScalarSector(2, potential=lambda f: lam * (1 - cos(f[0]))
+                             + f[0]**2 * f[1]**2 / 2)
+    stepper = ps.LowStorageRK54(sector, halo_shape=h, dt=dt, dx=dx,
+                                MapKernel=ps.FusedStencilStage, jit=True)
+    pad = tuple(n + 2 * h for n in N)
+    fh = rng.random((2,) + pad).astype(dtype)
+    dh = rng.random((2,) + pad).astype(dtype)
+    f, d = to_dev(fh), to_dev(dh)
+    fr, dr = fh.astype(np.float64), dh.astype(np.float64)
+    kf, kd = np.zeros_like(fr), np.zeros_like(dr)
+    A, B, _ = O.LSRK_TABLES["LowStorageRK54"]
+    for step in range(2):
+        for s in range(5):
+            stepper(s, f=f, dfdt=d, a=a, hubble=hubble, lam=lam_v)
+            laps = []
+            for n in range(2):
+                O.share_halos(fr[n], h)
+                laps.append(O.laplacian(fr[n], h, dx))
+            fi = [O.interior(fr[n], h) for n in range(2)]
+            di = [O.interior(dr[n], h) for n in range(2)]
+            dV = [lam_v * np.sin(fi[0]) + fi[0] * fi[1]**2, fi[0]**2 * fi[1]]
+            rhs = []
+            for n in range(2):
+                rhs += [di[n].copy(), (laps[n] - 2 * hubble * di[n]) - a**2 * dV[n]]
+            unk = [fi[0], di[0], fi[1], di[1]]
+            tmp = [O.interior(kf[0], h), O.interior(kd[0], h), O.interior(kf[1], h),
+                   O.interior(kd[1], h)]
+            O.lsrk_stage(A[s], B[s], dt, unk, tmp, rhs)
+    inner = (slice(None),) + (slice(h, -h),) * 3
+    scale = np.max(np.abs(fr[inner]))
+    assert np.max(np.abs(f.cpu().numpy()[inner] - fr[inner])) < rtol * scale
+    assert np.max(np.abs(d.cpu().numpy()[inner] - dr[inner])) < rtol * np.max(np.abs(dr[inner]))
