@@ -46,6 +46,34 @@ def scalar_stage(N=512, dtype=torch.float64):
            f"generated element-wise stage {N}^3", 9 * S * sites)
 
 
+def fused_generated(N=512, dtype=torch.float64):
+    """The fused pipeline with the built-in polynomial RHS vs the same potential through the
+    generated functor (forced), and a non-polynomial potential."""
+    from pystella_b200.field import var
+    from pystella_b200.fused_jit import recognise_general_system
+    h, S = 2, torch.finfo(dtype).bits // 8
+    grid = (N,) * 3
+    dx = (5 / N,) * 3
+    pad = (1,) + tuple(n + 2 * h for n in grid)
+    sites = N**3
+    cases = [("built-in phi^2/2", lambda g: g[0]**2 / 2, False),
+             ("generated phi^2/2", lambda g: g[0]**2 / 2, True),
+             ("generated 1-cos(phi)", lambda g: 1 - var("cos")(g[0]), True)]
+    for name, pot, force in cases:
+        sector = ps.ScalarSector(1, potential=pot)
+        st = ps.LowStorageRK54(sector, halo_shape=h, dt=1e-3, dx=dx,
+                               MapKernel=ps.FusedStencilStage, jit=True)
+        if force:
+            st._systems = [recognise_general_system(sector.rhs_dict, sector.potential(sector.f))]
+        f = torch.rand(pad, dtype=dtype, device="cuda")
+        d = torch.rand_like(f)
+        try:
+            timeit(lambda: st(1, f=f, dfdt=d, a=1.0, hubble=0.1),
+                   f"fused stage {N}^3 {dtype}: {name}", 8 * S * sites)
+        except Exception as exc:  # noqa: BLE001
+            print(f"{name}: {type(exc).__name__}: {str(exc)[:300]}", flush=True)
+
+
 def tensor_stage(N=256, dtype=torch.float32):
     h, S = 2, torch.finfo(dtype).bits // 8
     grid = (N,) * 3
@@ -79,6 +107,8 @@ def tensor_stage(N=256, dtype=torch.float32):
 
 
 if __name__ == "__main__":
+    fused_generated(512, torch.float64)
+    fused_generated(512, torch.float32)
     scalar_stage(512, torch.float64)
     scalar_stage(512, torch.float32)
     tensor_stage(256, torch.float32)
