@@ -269,3 +269,61 @@ def test_fused_stage_with_generated_rhs(dtype, rtol):
     scale = np.max(np.abs(fr[inner]))
     assert np.max(np.abs(f.cpu().numpy()[inner] - fr[inner])) < rtol * scale
     assert np.max(np.abs(d.cpu().numpy()[inner] - dr[inner])) < rtol * np.max(np.abs(dr[inner]))
+
+
+def test_generated_rhs_device_resident_loop():
+    """Generated right-hand side + in-kernel energy sums (generated potential) +
+    DeviceExpansion with device-resident a / hubble == the reference loop on NumPy."""
+    from pystella_b200.field import var
+    cos = var("cos")
+    rng = np.random.default_rng(18)
+    N, h = (16, 24, 32), 2
+    pad = tuple(n + 2 * h for n in N)
+    dx = tuple(5 / n for n in N)
+    dt, mpl, gs = 0.1 * min(dx), 1.0, float(np.prod(N))
+    f0 = .4 + 1e-2 * rng.standard_normal((1,) + pad)
+    d0 = -.1 + 1e-2 * rng.standard_normal((1,) + pad)
+
+    def energy_of(fr, dr, a):
+        g = fr[0].copy()
+        O.share_halos(g, h)
+        lap = O.laplacian(g, h, dx)
+        fi, di = O.interior(fr[0], h), O.interior(dr[0], h)
+        kin = np.sum(di**2) / 2 / a**2 / gs
+        grad = np.sum(-fi * lap) / 2 / a**2 / gs
+        pot = np.sum(1 - np.cos(fi)) / gs
+        return dict(total=kin + grad + pot, pressure=kin - grad / 3 - pot), lap
+
+    fr, dr = f0.copy(), d0.copy()
+    kfr, kdr = np.zeros_like(fr), np.zeros_like(fr)
+    energy, lap = energy_of(fr, dr, 1.)
+    e0 = float(energy["total"])
+    expand = O.Expansion(energy["total"], "LowStorageRK54", mpl=mpl)
+    A, B, _ = O.LSRK_TABLES["LowStorageRK54"]
+    want = []
+    for _ in range(2):
+        for s in range(5):
+            want.append((float(energy["total"]), float(energy["pressure"])))
+            a, hub = expand.a[0], expand.hubble[0]
+            fi, di = O.interior(fr[0], h), O.interior(dr[0], h)
+            rhs = [di.copy(), (lap - 2 * hub * di) - a**2 * np.sin(fi)]
+            O.lsrk_stage(A[s], B[s], dt, [fi, di],
+                         [O.interior(kfr[0], h), O.interior(kdr[0], h)], rhs)
+            expand.step(s, energy["total"], energy["pressure"], dt)
+            energy, lap = energy_of(fr, dr, expand.a[0])
+
+    sector = ps.ScalarSector(1, potential=lambda f: 1 - cos(f[0]))
+    stepper = ps.LowStorageRK54(sector, halo_shape=h, dt=dt, dx=dx,
+                                MapKernel=ps.FusedStencilStage, energy=True, jit=True)
+    dexp = ps.DeviceExpansion(e0, ps.LowStorageRK54, mpl=mpl, grid_size=gs, nscalars=1)
+    f, dfdt = to_dev(f0), to_dev(d0)
+    got = []
+    for _ in range(2):
+        for s in range(5):
+            stepper(s, f=f, dfdt=dfdt, a=dexp.a, hubble=dexp.hubble)
+            dexp.step(s, stepper, dt)
+            g = dexp.get()
+            got.append((g["total"], g["pressure"]))
+    for (t0, p0), (t1, p1) in zip(want, got):
+        assert np.isclose(t1, t0, rtol=1e-11) and np.isclose(p1, p0, rtol=1e-10, atol=1e-15)
+    assert np.isclose(dexp.get()["a"], expand.a[0], rtol=1e-12)
