@@ -390,3 +390,44 @@ def test_stencil_map_with_raw_subscripts_on_host(h, cls):
 def O_get_errs(a, b):
     import oracle as O
     return O.get_errs(a, b)[0]
+
+
+def _random_expression(rng, depth, leaves):
+    from pystella_b200.field import var
+    if depth == 0 or rng.random() < 0.2:
+        if rng.random() < 0.3:
+            return float(np.round(rng.uniform(-2, 2), 3))
+        return leaves[rng.integers(len(leaves))]
+    kind = rng.integers(7)
+    a = _random_expression(rng, depth - 1, leaves)
+    b = _random_expression(rng, depth - 1, leaves)
+    if kind == 0:
+        return a + b
+    if kind == 1:
+        return a - b
+    if kind == 2:
+        return a * b
+    if kind == 3:
+        return a / (1.5 + b * b)                   # keep denominators away from zero
+    if kind == 4:
+        return a ** int(rng.integers(0, 5))
+    if kind == 5:
+        return var(["sin", "cos", "tanh", "exp"][rng.integers(4)])(a * 0.3)
+    return var("sqrt")(1.0 + a * a) + var("fabs")(b)
+
+
+def test_random_expression_trees_translate_exactly():
+    """60 random expression trees (sums, products, quotients, integer powers, elementary
+    functions): the generated C evaluates to what `evaluate` gives, to rounding."""
+    from pystella_b200.field import var
+    rng = np.random.default_rng(2024)
+    names = ["x", "y", "z"]
+    leaves = [var(n) for n in names]
+    exprs = [_random_expression(rng, 4, leaves) for _ in range(60)]
+    exprs = [e for e in exprs if not isinstance(e, float)]
+    vals = [0.37, -1.21, 0.83]
+    got = _host_eval(exprs, names, vals)
+    ctx = dict(zip(names, vals))
+    for e, g in zip(exprs, got):
+        want = float(evaluate(e, ctx))
+        assert np.isclose(g, want, rtol=1e-12, atol=1e-13), (str(e), g, want)
