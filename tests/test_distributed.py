@@ -24,16 +24,31 @@ def _free_port():
     return port
 
 
+def run_group(cmd, timeout):
+    """Run `cmd` in its own process group; on timeout the whole group (spawned ranks
+    included) is killed, so that nothing keeps spinning on a GPU afterwards."""
+    import signal
+    proc = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                            start_new_session=True)
+    try:
+        out, err = proc.communicate(timeout=timeout)
+    except subprocess.TimeoutExpired:
+        os.killpg(proc.pid, signal.SIGKILL)
+        out, err = proc.communicate()
+        return 124, out, err + f"\n[timed out after {timeout} s; process group killed]"
+    return proc.returncode, out, err
+
+
 def _run(case, world, *args, timeout=300):
     for attempt in range(3):
         cmd = [sys.executable, os.path.join(HERE, "dist_worker.py"), case, str(world),
                str(_free_port()), *args]
-        res = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
-        if res.returncode == 0:
+        rc, out, err = run_group(cmd, timeout)
+        if rc == 0:
             return
-        if "EADDRINUSE" not in res.stderr + res.stdout:
+        if "EADDRINUSE" not in err + out:
             break   # a real failure; port collisions are retried
-    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert rc == 0, out[-3000:] + err[-3000:]
 
 
 @pytest.mark.parametrize("proc_shape", ["2,1,1", "1,2,1", "2,2,1", "3,1,1"])

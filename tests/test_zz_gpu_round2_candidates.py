@@ -232,12 +232,10 @@ def test_stencil_map_raw_subscripts(cls):
 def _in_subprocess(case, *args, timeout=240):
     """Kernels with mbarrier pipelines that have never run on hardware are exercised in a
     child process: a dead-locked kernel then costs one test, not the session."""
-    import os
-    import subprocess
-    import sys
+    from test_distributed import run_group
     cmd = [sys.executable, os.path.abspath(__file__), case, *[str(a) for a in args]]
-    res = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
-    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    rc, out, err = run_group(cmd, timeout)
+    assert rc == 0, out[-3000:] + err[-3000:]
 
 
 @pytest.mark.parametrize("dtype, rtol", [("float64", 1e-12), ("float32", 2e-5)])
