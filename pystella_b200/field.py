@@ -908,3 +908,25 @@ def get_field_args(expressions, unpadded_shape=None, prepend_with=None):
         args.append(FieldArg(name, full, f.base_offset, f.dtype,
                              is_value=(len(full) == 0)))
     return args
+
+
+def collect_field_indices(expressions):
+    """Names of the index variables of every Field in ``expressions`` -- the loop
+    variables a kernel over them needs (``pystella/field/__init__.py:609-624``)."""
+    names = set()
+    for node in _walk(expressions):
+        if isinstance(node, Field):
+            for idx in node.indices:
+                names.add(getattr(idx, "name", str(idx)))
+    return names
+
+
+def indices_to_domain(indices):
+    """ISL-style domain string over ``indices`` (``field/__init__.py:627-630``)."""
+    constraints = " and ".join(f"0 <= {idx} < N{idx}" for idx in indices)
+    return "{{[{}]: {}}}".format(",".join(indices), constraints)
+
+
+def infer_field_domains(expressions):
+    """``field/__init__.py:633-635``."""
+    return indices_to_domain(sorted(collect_field_indices(expressions)))

@@ -222,3 +222,17 @@ def test_recognised_system_equals_symbolic_rhs(pot, seed):
             V = [(float(c) if is_constant(c) else float(evaluate(c, ctx)), p)
                  for c, p in system.V]
             assert np.isclose(O.poly_eval(V, list(fv)), want_V, rtol=1e-12, atol=1e-13)
+
+
+def test_collect_field_indices():
+    """test/test_field.py:177-199."""
+    from pystella_b200.field import collect_field_indices, infer_field_domains
+    x = ps.Field("x", offset=(1, 2, 3))
+    y = ps.Field("y", indices=("i", "x"), offset="h")
+    z = ps.DynamicField("z", shape=(2, "a"))
+    assert collect_field_indices({x: y, y: x * z + z.pd[0]}) == {"i", "j", "k", "x"}
+    assert collect_field_indices([x, z]) == {"i", "j", "k"}
+    assert collect_field_indices([shift_fields(x, (1, 2, 3)), y + z.pd[0], y * z**2]) \
+        == {"i", "j", "k", "x"}
+    assert infer_field_domains([x, z]) == \
+        "{[i,j,k]: 0 <= i < Ni and 0 <= j < Nj and 0 <= k < Nk}"
