@@ -14,12 +14,14 @@ half, the Nyquist wavenumber is positive (``dft.py:326-332``).
 the reference's ``pDFT`` (``dft.py:350-428``); every other backend value means cuFFT on
 the current CUDA device.
 
-Distributed transforms: slab decompositions ``proc_shape = (P, 1, 1)`` (the layout of the
-fused stepper).  Position space is split along x, momentum space along y, like
-mpi4py-fft's slab mode which the reference uses (``dft.py:391-407``): local 2-D transforms
-over (y, z), one all-to-all transpose (NCCL on GPUs, gloo on the host backend), 1-D
-transforms over x.  ``sub_k`` and all k-space arrays are the rank-local slices.  Pencil
-decompositions ``(Px, Py, 1)`` are not implemented.
+Distributed transforms follow mpi4py-fft, which the reference uses (``dft.py:391-407``).
+Slab decompositions ``proc_shape = (P, 1, 1)`` (the layout of the fused stepper): position
+space split along x, momentum space along y; local 2-D transforms over (y, z), one
+all-to-all transpose (NCCL on GPUs, gloo on the host backend), 1-D transforms over x.
+Pencil decompositions ``(Px, Py, 1)``: position space split along x and y, momentum space
+along y (over the ``Px`` ranks of a column) and z (over the ``Py`` ranks of a row); 1-D
+transforms along z, y, x with a transpose inside the row and one inside the column
+communicator in between.  ``sub_k`` and all k-space arrays are the rank-local slices.
 """
 
 from itertools import product
@@ -72,9 +74,8 @@ class DFT:
             raise TypeError("grid_shape is required")
         if "use_fftw" in kwargs and kwargs.pop("use_fftw"):
             backend = "fftw"
-        if decomp.proc_shape[1] != 1 or decomp.proc_shape[2] != 1:
-            raise NotImplementedError("distributed transforms need a slab decomposition "
-                                      "proc_shape = (P, 1, 1)")
+        if decomp.proc_shape[2] != 1:
+            raise NotImplementedError("decomposition in z")
         if backend not in (None, "vkfft", "clfft", "cufft", "fftw"):
             raise NotImplementedError(f"{backend} backend for DFTs.")
         self.decomp = decomp
@@ -93,19 +94,39 @@ class DFT:
                 raise PsbError("DFT: no CUDA device (pass backend='fftw' for host "
                                "transforms of NumPy arrays)")
             self.device = torch.device("cuda", torch.cuda.current_device())
-        # slab layout: x split in position space, y split in momentum space, both with the
-        # uneven rule of decomp.py:322-337 (the first N % P ranks hold one more)
+        # position space: x split over Px, y over Py; momentum space: y split over Px (the
+        # ranks of a column), z over Py (the ranks of a row); uneven rule of
+        # decomp.py:322-337 (the first N % P ranks hold one more)
         self.nranks, self.rank = decomp.nranks, decomp.rank
-        P = self.nranks
+        Px, Py = int(decomp.proc_shape[0]), int(decomp.proc_shape[1])
+        self._px, self._py = Px, Py
+        self._rx, self._ry = int(decomp.rank_tuple[0]), int(decomp.rank_tuple[1])
 
-        def split(n):
-            q, r = divmod(n, P)
-            return [q + (1 if i < r else 0) for i in range(P)]
+        def split(n, parts):
+            q, r = divmod(n, parts)
+            return [q + (1 if i < r else 0) for i in range(parts)]
 
-        self._x_sizes, self._y_sizes = split(self.grid_shape[0]), split(self.grid_shape[1])
-        self._y_start = sum(self._y_sizes[:self.rank])
-        if P > 1 and min(self._x_sizes + self._y_sizes) == 0:
-            raise ValueError(f"grid {self.grid_shape} too small for {P} slabs")
+        nzk = self.grid_shape[2] // 2 + 1 if self.is_real else self.grid_shape[2]
+        self._x_sizes = split(self.grid_shape[0], Px)        # position x, by rx
+        self._ypos_sizes = split(self.grid_shape[1], Py)     # position y, by ry
+        self._y_sizes = split(self.grid_shape[1], Px)        # momentum y, by rx
+        self._zk_sizes = split(nzk, Py)                      # momentum z, by ry
+        self._y_start = sum(self._y_sizes[:self._rx])
+        self._zk_start = sum(self._zk_sizes[:self._ry])
+        if min(self._x_sizes + self._ypos_sizes + self._y_sizes + self._zk_sizes) == 0:
+            raise ValueError(f"grid {self.grid_shape} too small for proc_shape "
+                             f"{tuple(decomp.proc_shape)}")
+        # communicators: the column (same ry, all rx) and, for pencils, the row
+        self._col_group, self._row_group = decomp.comm, None
+        if Py > 1:
+            for ry in range(Py):
+                g = dist.new_group([decomp.rankID(rx, ry, 0) for rx in range(Px)])
+                if ry == self._ry:
+                    self._col_group = g
+            for rx in range(Px):
+                g = dist.new_group([decomp.rankID(rx, ry, 0) for ry in range(Py)])
+                if rx == self._rx:
+                    self._row_group = g
         self.fx = torch.zeros(self.shape(False), dtype=_tdtype(self.dtype),
                               device=self.device)
         self.fk = torch.zeros(self.shape(True), dtype=_tdtype(self.cdtype),
@@ -113,7 +134,8 @@ class DFT:
         k = [fftfreq(n) for n in self.grid_shape]
         if self.is_real:
             k[-1] = np.fft.rfftfreq(self.grid_shape[-1], 1 / self.grid_shape[-1])
-        k[1] = k[1][self._y_start:self._y_start + self._y_sizes[self.rank]]
+        k[1] = k[1][self._y_start:self._y_start + self._y_sizes[self._rx]]
+        k[2] = k[2][self._zk_start:self._zk_start + self._zk_sizes[self._ry]]
         self._k_host = [ki.astype(self.rdtype) for ki in k]
         self.sub_k = {name: torch.from_numpy(ki).to(self.device)
                       for name, ki in zip(("momenta_x", "momenta_y", "momenta_z"),
@@ -128,52 +150,52 @@ class DFT:
         (dft.py:415-416, 483-489)."""
         nx, ny, nz = self.grid_shape
         if not forward_output:
-            return (self._x_sizes[self.rank], ny, nz)
-        return (nx, self._y_sizes[self.rank], nz // 2 + 1 if self.is_real else nz)
+            return (self._x_sizes[self._rx], self._ypos_sizes[self._ry], nz)
+        return (nx, self._y_sizes[self._rx], self._zk_sizes[self._ry])
 
-    # -- slab transposes ------------------------------------------------------
-    def _all_to_all(self, send, in_splits, out_splits):
+    # -- transposes -----------------------------------------------------------
+    def _redistribute(self, arr, group, me, full_axis, split_axis, full_sizes, split_sizes):
+        """``arr`` is complete along ``full_axis`` and holds slice ``me`` of
+        ``split_axis`` (which is cut into ``split_sizes`` over ``group``); returns the
+        array complete along ``split_axis`` holding slice ``me`` of ``full_axis`` cut into
+        ``full_sizes``.  One all-to-all; complex data travel as pairs of reals."""
+        pieces, start = [], 0
+        for n in full_sizes:
+            pieces.append(torch.view_as_real(arr.narrow(full_axis, start, n).contiguous())
+                          .reshape(-1))
+            start += n
+        send = torch.cat(pieces)
+        shapes = []
+        for n in split_sizes:
+            shp = list(arr.shape)
+            shp[full_axis] = full_sizes[me]
+            shp[split_axis] = n
+            shapes.append(shp)
+        out_splits = [2 * int(np.prod(shp)) for shp in shapes]
         recv = torch.empty(sum(out_splits), dtype=send.dtype, device=send.device)
-        dist.all_to_all_single(recv, send, out_splits, in_splits, group=self.decomp.comm)
-        return recv
-
-    def _to_momentum_layout(self, a):
-        """(nx_loc, Ny, C) -> (Nx, ny_loc, C): every rank sends its x-slab of the y-range
-        owned by the receiver."""
-        nxl, _, c = a.shape
-        nyl = self._y_sizes[self.rank]
-        send = torch.view_as_real(a.permute(1, 0, 2).contiguous()).reshape(-1)
-        recv = self._all_to_all(send, [ny * nxl * c * 2 for ny in self._y_sizes],
-                                [nyl * nx * c * 2 for nx in self._x_sizes])
+        dist.all_to_all_single(recv, send, out_splits, [p.numel() for p in pieces],
+                               group=group)
         parts, off = [], 0
-        for nx in self._x_sizes:
-            n = nyl * nx * c * 2
-            parts.append(torch.view_as_complex(recv[off:off + n].view(nyl, nx, c, 2))
-                         .permute(1, 0, 2))
+        for shp, n in zip(shapes, out_splits):
+            parts.append(torch.view_as_complex(recv[off:off + n].view(*shp, 2)))
             off += n
-        return torch.cat(parts, dim=0)
-
-    def _to_position_layout(self, b):
-        """(Nx, ny_loc, C) -> (nx_loc, Ny, C)."""
-        _, nyl, c = b.shape
-        nxl = self._x_sizes[self.rank]
-        send = torch.view_as_real(b.contiguous()).reshape(-1)
-        recv = self._all_to_all(send, [nx * nyl * c * 2 for nx in self._x_sizes],
-                                [nxl * ny * c * 2 for ny in self._y_sizes])
-        parts, off = [], 0
-        for ny in self._y_sizes:
-            n = nxl * ny * c * 2
-            parts.append(torch.view_as_complex(recv[off:off + n].view(nxl, ny, c, 2)))
-            off += n
-        return torch.cat(parts, dim=1)
+        return torch.cat(parts, dim=split_axis)
 
     def _forward(self, x):
         if self.nranks == 1:
             return (torch.fft.rfftn(x, dim=(-3, -2, -1)) if self.is_real
                     else torch.fft.fftn(x, dim=(-3, -2, -1)))
-        a = (torch.fft.rfftn(x, dim=(-2, -1)) if self.is_real
-             else torch.fft.fftn(x, dim=(-2, -1)))
-        return torch.fft.fft(self._to_momentum_layout(a), dim=0)
+        if self._py == 1:       # slab: (nx_l, Ny, Nz) -> 2-D transform -> x <-> y
+            a = (torch.fft.rfftn(x, dim=(-2, -1)) if self.is_real
+                 else torch.fft.fftn(x, dim=(-2, -1)))
+        else:                   # pencil: z, then y after the row transpose
+            a = torch.fft.rfft(x, dim=-1) if self.is_real else torch.fft.fft(x, dim=-1)
+            a = self._redistribute(a, self._row_group, self._ry, 2, 1, self._zk_sizes,
+                                   self._ypos_sizes)
+            a = torch.fft.fft(a, dim=1)
+        a = self._redistribute(a, self._col_group, self._rx, 1, 0, self._y_sizes,
+                               self._x_sizes)
+        return torch.fft.fft(a, dim=0)
 
     def _backward(self, k):
         if self.nranks == 1:
@@ -181,10 +203,20 @@ class DFT:
                 return torch.fft.irfftn(k, s=self.grid_shape, dim=(-3, -2, -1),
                                         norm="forward")
             return torch.fft.ifftn(k, dim=(-3, -2, -1), norm="forward")
-        a = self._to_position_layout(torch.fft.ifft(k, dim=0, norm="forward"))
+        a = torch.fft.ifft(k, dim=0, norm="forward")
+        a = self._redistribute(a, self._col_group, self._rx, 0, 1, self._x_sizes,
+                               self._y_sizes)
+        if self._py == 1:
+            if self.is_real:
+                return torch.fft.irfftn(a, s=self.grid_shape[1:], dim=(-2, -1),
+                                        norm="forward")
+            return torch.fft.ifftn(a, dim=(-2, -1), norm="forward")
+        a = torch.fft.ifft(a, dim=1, norm="forward")
+        a = self._redistribute(a, self._row_group, self._ry, 1, 2, self._ypos_sizes,
+                               self._zk_sizes)
         if self.is_real:
-            return torch.fft.irfftn(a, s=self.grid_shape[1:], dim=(-2, -1), norm="forward")
-        return torch.fft.ifftn(a, dim=(-2, -1), norm="forward")
+            return torch.fft.irfft(a, n=self.grid_shape[2], dim=-1, norm="forward")
+        return torch.fft.ifft(a, dim=-1, norm="forward")
 
     # -- array plumbing -------------------------------------------------------
     def _halo(self):
@@ -360,7 +392,10 @@ class RayleighGenerator:
         homogeneous = kmags[0, 0, 0] == 0.
         if homogeneous:
             saved = wk[0, 0, 0]
-            wk[0, 0, 0] = wk[0, 0, 1]
+            # any valid neighbour (the local z extent can be 1 on a pencil)
+            other = (0, 0, 1) if wk.shape[2] > 1 else (0, 1, 0) if wk.shape[1] > 1 \
+                else (1, 0, 0)
+            wk[0, 0, 0] = wk[other]
         power = np.asarray(ps_func(wk), dtype=np.float64) * np.ones_like(kmags)
         if homogeneous:
             power[0, 0, 0] = 0.

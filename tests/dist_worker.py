@@ -176,7 +176,7 @@ def _fused_case(rank, world, backend, nscalars, energy, mode="peer"):
         assert float(lo) == float(hi)
 
 
-def _fourier_case(rank, world, backend):
+def _fourier_case(rank, world, backend, proc_shape=None):
     """Slab-distributed DFT / RayleighGenerator / PowerSpectra == the single-rank results
     on the gathered arrays (test/test_dft.py on more than one rank)."""
     import pystella_b200 as ps
@@ -186,7 +186,7 @@ def _fourier_case(rank, world, backend):
     for grid, dtype in (((16, 12, 10), "float64"), ((9, 7, 8), "float64"),
                         ((8, 6, 4), "complex128")):
         h = 1
-        decomp = ps.DomainDecomposition((world, 1, 1), h, grid_shape=grid)
+        decomp = ps.DomainDecomposition(proc_shape or (world, 1, 1), h, grid_shape=grid)
         fft = ps.DFT(decomp, None, None, grid, dtype, backend=fft_backend)
         rs, start = decomp.get_rank_shape_start(grid)
         assert fft.shape(False) == rs
@@ -194,9 +194,11 @@ def _fourier_case(rank, world, backend):
         full = rng.random(grid)
         if not fft.is_real:
             full = full + 1j * rng.random(grid)
-        loc = full[start[0]:start[0] + rs[0]].copy()
+        loc = full[start[0]:start[0] + rs[0], start[1]:start[1] + rs[1]].copy()
         ref = np.fft.rfftn(full) if fft.is_real else np.fft.fftn(full)
         ys, ny = fft._y_start, fft.shape(True)[1]
+        zs, nzk = fft._zk_start, fft.shape(True)[2]
+        ref = ref[:, :, zs:zs + nzk]
         assert sum(fft._y_sizes) == grid[1]
         arg = torch.from_numpy(loc).cuda() if cuda else loc
         fk = fft.dft(arg)
@@ -229,7 +231,7 @@ def _fourier_case(rank, world, backend):
         gk, dgk = modes.generate_WKB(None, hubble=0.1,
                                      omega_k=lambda k: np.sqrt(k**2 + 0.5))
         assert tuple(gk.shape) == fft.shape(True)
-        if ys == 0:
+        if ys == 0 and zs == 0:
             assert complex(gk[0, 0, 0]) == 0        # homogeneous mode carries no power
         fx = fft.idft(gk).cpu().numpy()
         assert fx.shape == rs and np.all(np.isfinite(fx)) and np.std(fx) > 0
@@ -272,7 +274,8 @@ def _worker(rank, world, port, case, args):
                             ((0, 2, 1), (32, 32, 32)), (1, (109, 67, 32))):
                 _decomp_case(rank, world, proc_shape, h, grid, backend)
         elif case in ("cpu_fourier", "gpu_fourier"):
-            _fourier_case(rank, world, backend)
+            proc_shape = tuple(int(x) for x in args[0].split(",")) if args else None
+            _fourier_case(rank, world, backend, proc_shape)
         elif case == "gpu_reduction":
             _reduction_case(rank, world, backend)
         elif case == "gpu_fused":

@@ -65,6 +65,15 @@ def test_distributed_fourier_gloo(world):
     _run("cpu_fourier", world)
 
 
+@pytest.mark.parametrize("proc_shape", ["2,2,1", "1,2,1"])
+def test_pencil_fourier_gloo(proc_shape):
+    """Pencil DFT: transposes inside the row and the column communicator."""
+    world = 1
+    for p in proc_shape.split(","):
+        world *= int(p)
+    _run("cpu_fourier", world, proc_shape)
+
+
 def _ngpus():
     try:
         import torch
