@@ -3,7 +3,7 @@ Preheating of scalar fields in an expanding FLRW background: the time loop of th
 reference's examples/scalar_preheating.py (sectors, stepper, derivatives, energy
 reduction, expansion) on pystella_b200, with the reference's initial conditions: WKB
 vacuum fluctuations drawn by RayleighGenerator on top of the homogeneous background
-(slab decompositions (P, 1, 1); pencil decompositions fall back to white noise).
+(the distributed DFT covers slab and pencil decompositions).
 Projectors and HDF5 output are not provided.
 
     python examples/scalar_preheating.py -grid 64 64 64 --end-time 1            # 1 GPU
@@ -41,7 +41,7 @@ parser.add_argument("--end-scale-factor", "-end-a", type=float, default=20)
 parser.add_argument("--gravitational-waves", "-gws", action="store_true")
 parser.add_argument("--reference-loop", action="store_true")
 parser.add_argument("--initial-conditions", "-ic", choices=["rayleigh", "white"],
-                    default=None, help="default: rayleigh for slab decompositions, else white")
+                    default=None, help="default: rayleigh (WKB vacuum modes, like the reference)")
 parser.add_argument("--seed", type=int, default=49279)
 parser.add_argument("--spectra", action="store_true",
                     help="print the field power spectra at the end")
@@ -126,7 +126,7 @@ def main(argv=None):
     statistics = ps.FieldStatistics(decomp, h, rank_shape=rank_shape,
                                     grid_size=p.grid_size)
 
-    ic = p.initial_conditions or ("rayleigh" if p.proc_shape[1:] == (1, 1) else "white")
+    ic = p.initial_conditions or "rayleigh"
     f = torch.empty((nscalars,) + pencil_shape, dtype=dtype, device=device)
     dfdt = torch.empty_like(f)
     for i in range(nscalars):           # field means
@@ -181,7 +181,7 @@ def main(argv=None):
             out = ps.OutputFile(name=p.output, runfile=__file__, grid_shape=p.grid_shape,
                                 proc_shape=p.proc_shape, dtype=p.dtype, mphi=p.mphi,
                                 gsq=p.gsq, initial_conditions=ic)
-        if slab:
+        if True:
             dk = tuple(2 * np.pi / Li for Li in p.box_dim)
             fft_out = ps.DFT(decomp, None, None, p.grid_shape, p.dtype)
             spectra = ps.PowerSpectra(decomp, fft_out, dk, float(np.prod(p.box_dim)))
@@ -242,7 +242,7 @@ def main(argv=None):
     stats = statistics(f)
     if decomp.rank == 0:
         print("field means", stats["mean"], "variances", stats["variance"])
-    if p.spectra and p.proc_shape[1:] == (1, 1):
+    if p.spectra:
         fft = ps.DFT(decomp, None, None, p.grid_shape, p.dtype)
         dk = tuple(2 * np.pi / Li for Li in p.box_dim)
         spectra = ps.PowerSpectra(decomp, fft, dk, float(np.prod(p.box_dim)))
