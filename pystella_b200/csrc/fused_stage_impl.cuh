@@ -592,14 +592,15 @@ static int fused_op(const psb_scalar_stage_args* a, cudaStream_t stream, int64_t
   return launch_fused<T, H, NF, VEC, BY, TZ, P, MINB>(a, stream);
 }
 
-template <typename T, int H, int NF, int BY, int TZ, int P, int MINB, int VEC = 2>
+template <typename T, int H, int NF, int BY, int TZ, int P, int MINB, int VEC = 2,
+          bool AL = false>
 static int ws_op(const psb_scalar_stage_args* a, cudaStream_t stream, int64_t* count) {
-  if (t_fused_plan) return plan_ws<T, H, NF, BY, TZ, P, MINB, VEC>(a, t_fused_plan);
+  if (t_fused_plan) return plan_ws<T, H, NF, BY, TZ, P, MINB, VEC, AL>(a, t_fused_plan);
   if (count) {
-    *count = ws_grid_blocks<T, H, NF, BY, TZ, P, VEC>(a);
+    *count = ws_grid_blocks<T, H, NF, BY, TZ, P, VEC, AL>(a);
     return 0;
   }
-  return launch_ws<T, H, NF, BY, TZ, P, MINB, VEC>(a, stream);
+  return launch_ws<T, H, NF, BY, TZ, P, MINB, VEC, AL>(a, stream);
 }
 
 // can TMA describe all four arrays?  (mirrors encode_field_tensor_map's checks)
@@ -628,6 +629,22 @@ static int dispatch_vec(const psb_scalar_stage_args* a, cudaStream_t stream,
                     aligned(a->f_in) && aligned(a->f_out) && aligned(a->dfdt) &&
                     aligned(a->kf) && aligned(a->kdfdt) && a->tune_variant != 3;
   constexpr int ES = (int)sizeof(T);
+  if (a->tune_variant == 16) {
+    // EXPERIMENTAL aligned mapping: full 16-byte vectors for any radius (fp32: 4 sites per
+    // thread, fp64: 2), masked row ends.  Not yet run on hardware.
+    constexpr int VA = 16 / ES;
+    const bool ok16 = (Pz % VA == 0) && ((Py * Pz) % VA == 0) && (a->field_stride % VA == 0) &&
+                      tma_layout_ok<T>(a, H);
+    if (!ok16) {
+      set_error("psb_scalar_stage_fused: tune_variant 16 needs rows that are multiples of "
+                "16 bytes and 16-byte aligned pointers");
+      return 1;
+    }
+    if constexpr (WsCfg<T, H, NF, 4, 32, 2, VA, true>::SMEM_BYTES <= SMEM_LIMIT)
+      return ws_op<T, H, NF, 4, 32, 2, 1, VA, true>(a, stream, count);
+    else
+      return ws_op<T, H, NF, 4, 16, 2, 1, VA, true>(a, stream, count);
+  }
   if (vec2) {
     // warp-specialised TMA pipeline (default)
     const int var = a->tune_variant;

@@ -26,9 +26,16 @@ constexpr int ws_gcd(int a, int b) { return b == 0 ? a : ws_gcd(b, a % b); }
 // GV = elements per global / pointwise access piece: the interior starts H elements
 // into a row, so only gcd(VEC, H) consecutive elements are guaranteed aligned
 // (fp32, h = 2: 16-byte LDS of the f tile, 8-byte pieces for everything else).
-template <typename T, int H, int NF, int BY, int TZ, int P, int VEC_ = 2> struct WsCfg {
+//
+// AL ("aligned mapping", EXPERIMENTAL, tune_variant 16): the thread's VEC sites are shifted
+// left by SH = H mod VEC so that they start on a VEC-element boundary of the padded row:
+// every access is one full 16-byte vector for any radius; sites that fall outside
+// 0 <= z < Nz at the two ends of a row are masked.
+template <typename T, int H, int NF, int BY, int TZ, int P, int VEC_ = 2, bool AL = false>
+struct WsCfg {
   static constexpr int VEC = VEC_;
-  static constexpr int GV = ws_gcd(VEC_, H);
+  static constexpr int SH = AL ? H % VEC_ : 0;
+  static constexpr int GV = AL ? VEC_ : ws_gcd(VEC_, H);
   static constexpr int BZ = TZ * VEC;
   // left pad of the f tile: the TMA box must start 16-byte aligned in global memory,
   // i.e. at padded column z0 = z0 + H - HL with HL = H rounded up to GV elements
@@ -42,8 +49,11 @@ template <typename T, int H, int NF, int BY, int TZ, int P, int VEC_ = 2> struct
   static constexpr int FPLANE = ((FPLANE_RAW + 127) / 128) * 128;   // bytes, per field
   // TMA needs a 16-byte aligned start along z: pointwise tiles begin PWL elements
   // left of the first interior site of the tile (fp32, h = 2: two floats)
-  static constexpr int PWL = H % WQ;
+  static constexpr int PWL = AL ? 0 : H % WQ;
   static constexpr int PWW = ((BZ + PWL + WQ - 1) / WQ) * WQ;
+  // padded z coordinate (relative to z0) at which the f box / the pointwise boxes start
+  static constexpr int ZF = H - HL - SH;
+  static constexpr int ZP = H - PWL - SH;
   static constexpr int PWTILE_RAW = BY * PWW * (int)sizeof(T);
   static constexpr int PWTILE = ((PWTILE_RAW + 127) / 128) * 128;   // bytes, per array
   static constexpr int PWSLOT = 3 * NF * PWTILE;
@@ -118,12 +128,16 @@ struct PsbJitScalars {
 };
 #endif
 
+template <bool B> struct WsBool {
+  static constexpr bool value = B;
+};
+
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
 template <typename T, int H, int NF, int BY, int TZ, int P, bool ENERGY, int MINB,
-          int VEC_ = 2>
+          int VEC_ = 2, bool AL = false>
 __global__ void __launch_bounds__(BY* TZ + 32, MINB)
     fused_stage_ws_kernel(const __grid_constant__ FusedParams<T, NF> p,
                           const __grid_constant__ CUtensorMap map_f,
@@ -135,7 +149,7 @@ __global__ void __launch_bounds__(BY* TZ + 32, MINB)
                           const __grid_constant__ PsbJitScalars jit_scalars
 #endif
 ) {
-  using C = WsCfg<T, H, NF, BY, TZ, P, VEC_>;
+  using C = WsCfg<T, H, NF, BY, TZ, P, VEC_, AL>;
   constexpr int VEC = C::VEC, GV = C::GV, W = C::W, HL = C::HL, RF = C::RF, RP = C::RP;
   using V = Vec<T, VEC>;
 
@@ -192,7 +206,7 @@ __global__ void __launch_bounds__(BY* TZ + 32, MINB)
 #pragma unroll
           for (int f = 0; f < NF; ++f)
             tma_load_4d(fring + (slot * NF + f) * C::FPLANE, &map_f, &full_f[slot],
-                        z0 + H - HL, y0, xs + m, f);
+                        z0 + C::ZF, y0, xs + m, f);
         }
         // consumer step m needs f plane m and the pointwise planes of compute index
         // m - 2H: issue both in the same iteration so that both rings run P+1 ahead
@@ -206,12 +220,12 @@ __global__ void __launch_bounds__(BY* TZ + 32, MINB)
 #pragma unroll
           for (int f = 0; f < NF; ++f) {
             tma_load_4d(dst + (0 * NF + f) * C::PWTILE, &map_d, &full_p[slot],
-                        z0 + H - C::PWL, y0 + H, px, f);
+                        z0 + C::ZP, y0 + H, px, f);
             if (read_k) {
               tma_load_4d(dst + (1 * NF + f) * C::PWTILE, &map_kf, &full_p[slot],
-                          z0 + H - C::PWL, y0 + H, px, f);
+                          z0 + C::ZP, y0 + H, px, f);
               tma_load_4d(dst + (2 * NF + f) * C::PWTILE, &map_kd, &full_p[slot],
-                          z0 + H - C::PWL, y0 + H, px, f);
+                          z0 + C::ZP, y0 + H, px, f);
             }
           }
         }
@@ -223,8 +237,34 @@ __global__ void __launch_bounds__(BY* TZ + 32, MINB)
   // ============================ consumer warps ==================================
   const int tz = tid % TZ, ty = tid / TZ;
   const int lane = tid & 31;
-  const int j = y0 + ty, k = z0 + tz * VEC;
-  const bool active = (j < p.Ny) && (k < p.Nz);
+  const int j = y0 + ty, k = z0 + tz * VEC - C::SH;
+  // AL: sites k .. k+VEC-1 may stick out of the row at either end
+  bool ok[VEC];
+  bool all_ok = true, any_ok = false;
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) {
+    ok[v] = (j < p.Ny) && (k + v >= 0) && (k + v < p.Nz);
+    all_ok = all_ok && ok[v];
+    any_ok = any_ok || ok[v];
+  }
+  const bool active = AL ? any_ok : ((j < p.Ny) && (k < p.Nz));
+  // store VEC results: one (or VEC/GV) vector stores, element-wise where masked
+  auto put = [&](T* dst, const V& x, auto stream_tag) {
+    constexpr bool STREAM = decltype(stream_tag)::value;
+    if constexpr (!AL) {
+      st_pieces<T, VEC, GV, STREAM>(dst, x);
+    } else {
+      if (all_ok) {
+        st_pieces<T, VEC, GV, STREAM>(dst, x);
+      } else {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v)
+          if (ok[v]) dst[v] = x.v[v];
+      }
+    }
+  };
+  using TagStream = WsBool<true>;
+  using TagPlain = WsBool<false>;
   const int64_t Pz = p.Nz + 2 * H, Py = p.Ny + 2 * H;
   const int64_t plane_stride = Py * Pz;
   const int64_t site0 = ((int64_t)H * Py + (j + H)) * Pz + (k + H);
@@ -327,6 +367,9 @@ __global__ void __launch_bounds__(BY* TZ + 32, MINB)
         if constexpr (ENERGY) {
 #pragma unroll
           for (int v = 0; v < VEC; ++v) {
+            if constexpr (AL) {
+              if (!ok[v]) continue;
+            }
 #pragma unroll
             for (int f = 0; f < NF; ++f) {
               const T dv = dold[f].v[v];
@@ -407,33 +450,35 @@ __global__ void __launch_bounds__(BY* TZ + 32, MINB)
             dn.v[v] = d_old + p.B * kdv;
           }
           const int64_t fo_off = f * p.field_stride;
-          st_pieces<T, VEC, GV, true>(o_kf + fo_off, kfn);
-          st_pieces<T, VEC, GV, true>(o_kd + fo_off, kdn);
-          st_pieces<T, VEC, GV, true>(o_d + fo_off, dn);
+          put(o_kf + fo_off, kfn, TagStream{});
+          put(o_kd + fo_off, kdn, TagStream{});
+          put(o_d + fo_off, dn, TagStream{});
           T* fout = o_f + fo_off;
-          st_pieces<T, VEC, GV, false>(fout, fo);
+          put(fout, fo, TagPlain{});
           if (p.wrap_x) {
-            if (i < H) st_pieces<T, VEC, GV, false>(fout + (int64_t)p.Nx * plane_stride, fo);
-            if (i >= p.Nx - H) st_pieces<T, VEC, GV, false>(fout - (int64_t)p.Nx * plane_stride, fo);
+            if (i < H) put(fout + (int64_t)p.Nx * plane_stride, fo, TagPlain{});
+            if (i >= p.Nx - H) put(fout - (int64_t)p.Nx * plane_stride, fo, TagPlain{});
           }
           // NVLink: my boundary planes -> the neighbours' x halos (peer memory)
           if (p.peer_lo != nullptr && i < H)
-            st_pieces<T, VEC, GV, false>(p.peer_lo + f * p.peer_lo_stride +
-                                 (int64_t)(p.peer_lo_Nx + H + i) * plane_stride +
-                                 (int64_t)(j + H) * Pz + (k + H),
-                             fo);
+            put(p.peer_lo + f * p.peer_lo_stride +
+                    (int64_t)(p.peer_lo_Nx + H + i) * plane_stride + (int64_t)(j + H) * Pz +
+                    (k + H),
+                fo, TagPlain{});
           if (p.peer_hi != nullptr && i >= p.Nx - H)
-            st_pieces<T, VEC, GV, false>(p.peer_hi + f * p.peer_hi_stride +
-                                 (int64_t)(i - p.Nx + H) * plane_stride +
-                                 (int64_t)(j + H) * Pz + (k + H),
-                             fo);
+            put(p.peer_hi + f * p.peer_hi_stride + (int64_t)(i - p.Nx + H) * plane_stride +
+                    (int64_t)(j + H) * Pz + (k + H),
+                fo, TagPlain{});
           if (p.wrap_y) {
-            if (j < H) st_pieces<T, VEC, GV, false>(fout + (int64_t)p.Ny * Pz, fo);
-            if (j >= p.Ny - H) st_pieces<T, VEC, GV, false>(fout - (int64_t)p.Ny * Pz, fo);
+            if (j < H) put(fout + (int64_t)p.Ny * Pz, fo, TagPlain{});
+            if (j >= p.Ny - H) put(fout - (int64_t)p.Ny * Pz, fo, TagPlain{});
           }
           if (p.wrap_z) {
 #pragma unroll
             for (int v = 0; v < VEC; ++v) {
+              if constexpr (AL) {
+                if (!ok[v]) continue;
+              }
               if (k + v < H) fout[v + p.Nz] = fo.v[v];
               if (k + v >= p.Nz - H) fout[v - p.Nz] = fo.v[v];
             }
@@ -491,17 +536,23 @@ __global__ void __launch_bounds__(BY* TZ + 32, MINB)
 // ---------------------------------------------------------------------------
 #ifndef __CUDACC_RTC__
 
-template <typename T, int H, int NF, int BY, int TZ, int P, int VEC = 2>
+template <typename T, int H, int NF, int BY, int TZ, int P, int VEC = 2, bool AL = false>
 static int64_t ws_grid_blocks(const psb_scalar_stage_args* a) {
-  using C = WsCfg<T, H, NF, BY, TZ, P, VEC>;
+  using C = WsCfg<T, H, NF, BY, TZ, P, VEC, AL>;
   const XLayout L = x_layout(a, WS_DEFAULT_XCHUNK);
-  return ((a->Nz + C::BZ - 1) / C::BZ) * ((a->Ny + BY - 1) / BY) * (int64_t)(L.n1 + L.n2);
+  return ((a->Nz + C::SH + C::BZ - 1) / C::BZ) * ((a->Ny + BY - 1) / BY) *
+         (int64_t)(L.n1 + L.n2);
 }
 
 // parameters of the launch of this instance, for an externally compiled kernel
-template <typename T, int H, int NF, int BY, int TZ, int P, int MINB, int VEC = 2>
+template <typename T, int H, int NF, int BY, int TZ, int P, int MINB, int VEC = 2,
+          bool AL = false>
 static int plan_ws(const psb_scalar_stage_args* a, psb_fused_plan* plan) {
-  using C = WsCfg<T, H, NF, BY, TZ, P, VEC>;
+  using C = WsCfg<T, H, NF, BY, TZ, P, VEC, AL>;
+  if (AL) {
+    set_error("psb_scalar_stage_fused_plan: the aligned-mapping variant has no plan");
+    return 3;
+  }
   static_assert(sizeof(FusedParams<T, NF>) <= PSB_FUSED_PLAN_PARAM_BYTES, "plan too small");
   static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap size");
   const int64_t Px = a->Nx + 2 * H, Py = a->Ny + 2 * H, Pz = a->Nz + 2 * H;
@@ -540,7 +591,7 @@ static int plan_ws(const psb_scalar_stage_args* a, psb_fused_plan* plan) {
   plan->minb = MINB;
   plan->vec = VEC;
   plan->energy = a->energy_partials != nullptr ? 1 : 0;
-  plan->grid[0] = (uint32_t)((a->Nz + C::BZ - 1) / C::BZ);
+  plan->grid[0] = (uint32_t)((a->Nz + C::SH + C::BZ - 1) / C::BZ);
   plan->grid[1] = (uint32_t)((a->Ny + BY - 1) / BY);
   plan->grid[2] = (uint32_t)(L.n1 + L.n2);
   plan->threads = C::THREADS;
@@ -549,9 +600,11 @@ static int plan_ws(const psb_scalar_stage_args* a, psb_fused_plan* plan) {
 }
 
 // returns 0 ok, >0 error, -1 = layout not TMA-able (caller falls back)
-template <typename T, int H, int NF, int BY, int TZ, int P, int MINB, int VEC = 2>
+template <typename T, int H, int NF, int BY, int TZ, int P, int MINB, int VEC = 2,
+          bool AL = false>
 static int launch_ws(const psb_scalar_stage_args* a, cudaStream_t stream) {
-  using C = WsCfg<T, H, NF, BY, TZ, P, VEC>;
+  using C = WsCfg<T, H, NF, BY, TZ, P, VEC, AL>;
+  static_assert(C::SMEM_BYTES <= SMEM_LIMIT, "rings do not fit in shared memory");
   const int64_t Px = a->Nx + 2 * H, Py = a->Ny + 2 * H, Pz = a->Nz + 2 * H;
   CUtensorMap mf, md, mkf, mkd;
   if (encode_field_tensor_map(&mf, a->dtype, a->f_in, NF, a->field_stride, Px, Py, Pz, 1,
@@ -570,16 +623,16 @@ static int launch_ws(const psb_scalar_stage_args* a, cudaStream_t stream) {
   const XLayout L = x_layout(a, WS_DEFAULT_XCHUNK);
   p.xchunk = L.xchunk;
   p.nchunks1 = L.n1;
-  dim3 grid((unsigned)((a->Nz + C::BZ - 1) / C::BZ), (unsigned)((a->Ny + BY - 1) / BY),
-            (unsigned)(L.n1 + L.n2));
+  dim3 grid((unsigned)((a->Nz + C::SH + C::BZ - 1) / C::BZ),
+            (unsigned)((a->Ny + BY - 1) / BY), (unsigned)(L.n1 + L.n2));
   dim3 block(C::THREADS, 1, 1);
   if (a->energy_partials != nullptr) {
-    auto kern = fused_stage_ws_kernel<T, H, NF, BY, TZ, P, true, MINB, VEC>;
+    auto kern = fused_stage_ws_kernel<T, H, NF, BY, TZ, P, true, MINB, VEC, AL>;
     PSB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         C::SMEM_BYTES));
     kern<<<grid, block, C::SMEM_BYTES, stream>>>(p, mf, md, mkf, mkd);
   } else {
-    auto kern = fused_stage_ws_kernel<T, H, NF, BY, TZ, P, false, MINB, VEC>;
+    auto kern = fused_stage_ws_kernel<T, H, NF, BY, TZ, P, false, MINB, VEC, AL>;
     PSB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         C::SMEM_BYTES));
     kern<<<grid, block, C::SMEM_BYTES, stream>>>(p, mf, md, mkf, mkd);

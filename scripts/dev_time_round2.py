@@ -74,6 +74,25 @@ def fused_generated(N=512, dtype=torch.float64):
             print(f"{name}: {type(exc).__name__}: {str(exc)[:300]}", flush=True)
 
 
+def aligned_variant(N=512, dtype=torch.float32, h=2):
+    """Default pipeline vs the aligned-mapping variant (tune_variant 16)."""
+    S = torch.finfo(dtype).bits // 8
+    grid = (N,) * 3
+    dx = (5 / N,) * 3
+    pad = (1,) + tuple(n + 2 * h for n in grid)
+    sector = ps.ScalarSector(1, potential=lambda g: g[0]**2 / 2)
+    for variant in (0, 16):
+        st = ps.LowStorageRK54(sector, halo_shape=h, dt=1e-3, dx=dx,
+                               MapKernel=ps.FusedStencilStage, tune={"variant": variant})
+        f = torch.rand(pad, dtype=dtype, device="cuda")
+        d = torch.rand_like(f)
+        try:
+            timeit(lambda: st(1, f=f, dfdt=d, a=1.0, hubble=0.1),
+                   f"fused stage {N}^3 {dtype} h={h} variant {variant}", 8 * S * N**3)
+        except Exception as exc:  # noqa: BLE001
+            print(f"variant {variant}: {type(exc).__name__}: {str(exc)[:300]}", flush=True)
+
+
 def tensor_stage(N=256, dtype=torch.float32):
     h, S = 2, torch.finfo(dtype).bits // 8
     grid = (N,) * 3
@@ -107,6 +126,9 @@ def tensor_stage(N=256, dtype=torch.float32):
 
 
 if __name__ == "__main__":
+    aligned_variant(512, torch.float32, 2)
+    aligned_variant(512, torch.float64, 2)
+    aligned_variant(510, torch.float64, 1)      # odd radius: default = cooperative loader
     fused_generated(512, torch.float64)
     fused_generated(512, torch.float32)
     scalar_stage(512, torch.float64)

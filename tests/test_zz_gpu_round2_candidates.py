@@ -247,6 +247,77 @@ def test_generated_rhs_device_resident_loop():
     _in_subprocess("generated_loop")
 
 
+ALIGNED_CASES = [
+    # dtype, N, h, nscalars  (rows (Nz + 2h) must be multiples of 16 bytes)
+    ("float32", (20, 12, 60), 2, 1), ("float32", (8, 12, 124), 2, 2),
+    ("float32", (8, 8, 30), 1, 1), ("float32", (8, 8, 26), 3, 1), ("float32", (8, 8, 24), 4, 1),
+    ("float64", (20, 12, 60), 2, 1), ("float64", (8, 8, 30), 1, 1), ("float64", (8, 8, 26), 3, 2),
+]
+
+
+@pytest.mark.parametrize("case", range(len(ALIGNED_CASES)))
+def test_fused_stage_aligned_mapping(case):
+    """tune_variant 16: full 16-byte vectors for every radius, masked row ends."""
+    _in_subprocess("aligned", case)
+
+
+def _case_aligned(case):
+    from pystella_b200 import _kernels as K
+    from helpers import scale_err
+    dtype, N, h, n = ALIGNED_CASES[case]
+    rng = np.random.default_rng(20 + case)
+    shape = (n,) + tuple(x + 2 * h for x in N)
+    f = rng.random(shape).astype(dtype)
+    for i in range(n):
+        O.share_halos(f[i], h)
+    d, kf, kd = (rng.random(shape).astype(dtype) for _ in range(3))
+    pot = [(0.5, (2,) + (0,) * (n - 1)), (0.25, (2,) * n)]
+    dV = [O.poly_diff(pot, i) for i in range(n)]
+    dx, dt, a, hub = (0.1, 0.13, 0.07), 0.01, 1.3, 0.2
+    A, B, _ = O.LSRK_TABLES["LowStorageRK54"]
+    tol = 1e-12 if dtype == "float64" else 1e-5
+    for stage in (0, 2):
+        fo, do, kfo, kdo = (x.astype(np.float64) for x in (f, d, kf, kd))
+        lap = np.zeros((n,) + tuple(N))
+        O.reference_schedule_stage(stage, fo, do, kfo, kdo, lap, h, dx, dt, a=a, hubble=hub,
+                                   potential_terms=pot)
+        tf, td, tkf, tkd = (to_dev(x) for x in (f, d, kf, kd))
+        tfo = torch.full_like(tf, float("nan"))
+        nslots = K.scalar_stage(fused=True, f_in=tf, f_out=tfo, dfdt=td, kf=tkf, kdfdt=tkd,
+                                h=h, dx=dx, dt=dt, A=A[stage], B=B[stage], a=a, hubble=hub,
+                                dV_terms=dV, variant=16, count_slots_only=True)
+        partials = torch.zeros((nslots, 16), dtype=torch.float64, device="cuda")
+        K.scalar_stage(fused=True, f_in=tf, f_out=tfo, dfdt=td, kf=tkf, kdfdt=tkd, h=h, dx=dx,
+                       dt=dt, A=A[stage], B=B[stage], a=a, hubble=hub, dV_terms=dV,
+                       variant=16, energy_partials=partials, V_terms=pot)
+        torch.cuda.synchronize()
+        for g, r in ((tfo, fo), (td, do), (tkf, kfo), (tkd, kdo)):
+            assert scale_err(O.interior(g.cpu().numpy(), h), O.interior(r, h)) < tol
+        # pointwise arrays' halos untouched, f_out's faces periodic
+        for g, orig in ((td, d), (tkf, kf), (tkd, kd)):
+            arr = g.cpu().numpy()
+            mask = np.ones(arr.shape, bool)
+            O.interior(mask, h)[...] = False
+            assert np.array_equal(arr[mask], orig[mask])
+        full = fo.copy()
+        for i in range(n):
+            O.share_halos(full[i], h)
+        g = tfo.cpu().numpy()
+        s_ = slice(h, -h)
+        for i in range(n):
+            for sl in ((slice(0, h), s_, s_), (slice(-h, None), s_, s_), (s_, slice(0, h), s_),
+                       (s_, slice(-h, None), s_), (s_, s_, slice(0, h)),
+                       (s_, s_, slice(-h, None))):
+                assert scale_err(g[i][sl], full[i][sl]) < tol
+        # energy sums of the INPUT state
+        sums = partials.sum(0).cpu().numpy()
+        fi = [O.interior(f[i].astype(np.float64), h) for i in range(n)]
+        di = [O.interior(d[i].astype(np.float64), h) for i in range(n)]
+        for i in range(n):
+            assert np.isclose(sums[i], np.sum(di[i]**2), rtol=1e3 * tol)
+        assert np.isclose(sums[n], np.sum(O.poly_eval(pot, fi)), rtol=1e3 * tol)
+
+
 def _case_generated_rhs(dtype, rtol):
     """Row f-2: a non-polynomial potential (axion-like, V = lam (1 - cos f) + g^2 f^2 chi^2/2)
     through the fused TMA pipeline compiled at run time with a generated right-hand side ==
@@ -356,6 +427,8 @@ if __name__ == "__main__":
         _case_generated_rhs(sys.argv[2], float(sys.argv[3]))
     elif sys.argv[1] == "generated_loop":
         _case_generated_loop()
+    elif sys.argv[1] == "aligned":
+        _case_aligned(int(sys.argv[2]))
     else:
         raise SystemExit(f"unknown case {sys.argv[1]}")
     print("ok")
