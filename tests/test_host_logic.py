@@ -62,3 +62,99 @@ def test_reference_arm_prints_contract_line():
         assert key in line
     assert line["impl"] == "reference" and line["cpu_baseline"]["kind"] == "port"
     assert line["value"] > 0 and line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+# ---------------------------------------------------------------------------------------
+# index arithmetic of the warp-specialised pipeline (csrc/fused_stage_ws.cuh, WsCfg and the
+# consumer's own_off / pw_off / k), restated and checked by enumeration: every interior
+# site is owned exactly once, every stencil read lands on the shared-memory column that
+# holds the wanted padded coordinate, TMA boxes start 16-byte aligned, vector accesses are
+# aligned in shared and global memory, and the periodic z images go to the right halo cells.
+# ---------------------------------------------------------------------------------------
+import math  # noqa: E402
+
+def _ws_cfg(es, H, VEC, TZ, AL):
+    SH = H % VEC if AL else 0
+    GV = VEC if AL else math.gcd(VEC, H)
+    BZ = TZ * VEC
+    HL = -(-H // GV) * GV
+    WQ = 16 // es
+    W = -(-(BZ + 2 * HL) // WQ) * WQ
+    PWL = 0 if AL else H % WQ
+    PWW = -(-(BZ + PWL) // WQ) * WQ
+    ZF = H - HL - SH
+    ZP = H - PWL - SH
+    return dict(SH=SH, GV=GV, BZ=BZ, HL=HL, W=W, PWL=PWL, PWW=PWW, ZF=ZF, ZP=ZP, WQ=WQ)
+
+def _ws_check(es, H, VEC, TZ, Nz, AL):
+    c = _ws_cfg(es, H, VEC, TZ, AL)
+    Pz = Nz + 2 * H
+    ntiles = -(-(Nz + c["SH"]) // c["BZ"])
+    written = {}
+    halo_written = {}
+    for b in range(ntiles):
+        z0 = b * c["BZ"]
+        # TMA start coordinates must be 16-byte aligned
+        assert ((z0 + c["ZF"]) * es) % 16 == 0, ("f box", z0, c)
+        assert ((z0 + c["ZP"]) * es) % 16 == 0, ("pw box", z0, c)
+        for tz in range(TZ):
+            k = z0 + tz * VEC - c["SH"]
+            own = c["HL"] + tz * VEC
+            pw = c["PWL"] + tz * VEC
+            # vector accesses: alignment in shared memory and in global memory
+            assert (own * es) % (c["GV"] * es) == 0 and (pw * es) % (c["GV"] * es) == 0
+            assert ((k + H) % c["GV"]) == 0, ("global alignment", k, H, c)
+            assert own - c["HL"] >= 0 and own + VEC + c["HL"] <= c["W"]
+            assert pw + VEC <= c["PWW"]
+            for v in range(VEC):
+                z = k + v
+                ok = 0 <= z < Nz
+                if not AL:
+                    ok = k < Nz
+                    if ok:
+                        assert z < Nz, "non-AL needs Nz % VEC == 0"
+                if not ok:
+                    continue
+                # smem column <-> padded coordinate
+                assert z0 + c["ZF"] + own + v == z + H
+                assert z0 + c["ZP"] + pw + v == z + H
+                for s in range(-H, H + 1):
+                    col = own + v + s
+                    assert 0 <= col < c["W"]
+                    pz = z0 + c["ZF"] + col
+                    assert 0 <= pz < Pz, (pz, Pz)          # never an out-of-bounds column
+                assert z not in written
+                written[z] = (b, tz, v)
+                # fout pointer is at padded (k + H); element v; wrap images
+                base = k + H
+                if z < H:
+                    halo_written[base + v + Nz] = z
+                if z >= Nz - H:
+                    halo_written[base + v - Nz] = z
+    assert sorted(written) == list(range(Nz)), "every interior site exactly once"
+    for pz, z in halo_written.items():
+        assert (pz < H or pz >= Nz + H) and (pz - H) % Nz == z
+    assert len(halo_written) == 2 * H
+    return ntiles
+
+
+
+def test_pipeline_index_arithmetic_aligned_mapping():
+    """The experimental aligned mapping (template flag AL, tune_variant 16)."""
+    for es, VEC in ((4, 4), (8, 2)):
+        for H in (1, 2, 3, 4):
+            for TZ in (16, 32):
+                for Nz in range(max(4, H), 200):
+                    if ((Nz + 2 * H) * es) % 16:
+                        continue
+                    _ws_check(es, H, VEC, TZ, Nz, True)
+
+
+def test_pipeline_index_arithmetic_default_mapping():
+    """The mapping of the validated kernels, for the layouts it is dispatched for."""
+    for es, VEC, TZ in ((8, 2, 64), (4, 2, 64), (4, 4, 32)):
+        for H in (2, 4):
+            for Nz in range(8, 200, 2):
+                if ((Nz + 2 * H) * es) % 16 or Nz % VEC:
+                    continue
+                _ws_check(es, H, VEC, TZ, Nz, False)
