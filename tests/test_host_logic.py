@@ -158,3 +158,119 @@ def test_pipeline_index_arithmetic_default_mapping():
                 if ((Nz + 2 * H) * es) % 16 or Nz % VEC:
                     continue
                 _ws_check(es, H, VEC, TZ, Nz, False)
+
+
+# ---------------------------------------------------------------------------------------
+# ring protocol of the warp-specialised pipeline (csrc/fused_stage_ws.cuh): a discrete
+# simulation of the producer lane, the consumer warps and the asynchronous TMA completions
+# under random scheduling.  Checks: no dead-lock, no phase aliasing (a wait never sees a
+# barrier two phases ahead), every consumer reads the plane the producer loaded for it, and
+# no slot is overwritten while a warp still needs it.
+# ---------------------------------------------------------------------------------------
+
+class _Mbar:
+    def __init__(self, count):
+        self.count, self.pending, self.completed = count, count, 0
+
+    def arrive(self):
+        self.pending -= 1
+        assert self.pending >= 0
+        if self.pending == 0:
+            self.completed += 1
+            self.pending = self.count
+
+    def done(self, phase_index):
+        """wait(parity of phase_index): passes once that phase has completed; the protocol
+        must never let the barrier run two phases ahead of a waiter."""
+        assert self.completed <= phase_index + 1, "phase aliasing"
+        return self.completed > phase_index
+
+
+def _simulate_rings(H, P, ncomp, ncw, rng):
+    RF, RP = H + 1 + P, P + 1
+    nsteps = ncomp + 2 * H
+    full_f = [_Mbar(1) for _ in range(RF)]
+    empty_f = [_Mbar(ncw) for _ in range(RF)]
+    full_p = [_Mbar(1) for _ in range(RP)]
+    empty_p = [_Mbar(ncw) for _ in range(RP)]
+    fslot, pslot = [None] * RF, [None] * RP          # what the slots currently hold
+    in_flight = []                                   # issued TMA loads: (kind, slot, tag)
+    prod = {"m": 0, "stage": 0}
+    cons = [{"n": 0, "stage": 0} for _ in range(ncw)]
+
+    def producer_step():
+        m = prod["m"]
+        if m >= nsteps:
+            return False
+        if prod["stage"] == 0:
+            slot = m % RF
+            if m >= RF and not empty_f[slot].done(m // RF - 1):
+                return False
+            in_flight.append(("f", slot, m))
+            prod["stage"] = 1
+            return True
+        c = m - 2 * H
+        if 0 <= c < ncomp:
+            slot = c % RP
+            if c >= RP and not empty_p[slot].done(c // RP - 1):
+                return False
+            in_flight.append(("p", slot, c))
+        prod["m"], prod["stage"] = m + 1, 0
+        return True
+
+    def tma_step():
+        if not in_flight:
+            return False
+        kind, slot, tag = in_flight.pop(rng.integers(len(in_flight)))
+        if kind == "f":
+            fslot[slot] = tag
+            full_f[slot].arrive()
+        else:
+            pslot[slot] = tag
+            full_p[slot].arrive()
+        return True
+
+    def consumer_step(w):
+        st = cons[w]
+        n = st["n"]
+        if n >= nsteps:
+            return False
+        if st["stage"] == 0:                      # wait for f plane n, shift the x queue
+            if not full_f[n % RF].done(n // RF):
+                return False
+            assert fslot[n % RF] == n
+            st["stage"] = 1
+            return True
+        if st["stage"] == 1:                      # compute site plane c = n - 2H
+            if n >= 2 * H:
+                c = n - 2 * H
+                if not full_p[c % RP].done(c // RP):
+                    return False
+                assert pslot[c % RP] == c
+                assert fslot[(n - H) % RF] == n - H, "centre plane overwritten"
+                empty_p[c % RP].arrive()
+            st["stage"] = 2
+            return True
+        if n >= H:
+            empty_f[(n - H) % RF].arrive()
+        st["n"], st["stage"] = n + 1, 0
+        return True
+
+    idle = 0
+    while prod["m"] < nsteps or any(c["n"] < nsteps for c in cons) or in_flight:
+        actors = [producer_step, tma_step] + [lambda w=w: consumer_step(w) for w in range(ncw)]
+        moved = actors[rng.integers(len(actors))]()
+        idle = 0 if moved else idle + 1
+        if idle > 200 * (ncw + 2):
+            # nobody moved for a long time: make sure it is not just bad luck
+            assert any(a() for a in actors), "dead-lock"
+            idle = 0
+
+
+def test_pipeline_ring_protocol_is_deadlock_free():
+    rng = np.random.default_rng(5)
+    for H in (1, 2, 3, 4):
+        for P in (2, 3):
+            for ncomp in (1, 2, 5, 16):
+                for ncw in (1, 4, 8):
+                    _simulate_rings(H, P, ncomp, ncw, rng)
