@@ -6,6 +6,8 @@
 // plane staged in shared memory for y/z neighbours.  Outputs are unpadded.
 #include <math.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace psb {
@@ -121,8 +123,26 @@ __global__ void __launch_bounds__(BY* BZ)
   }
 }
 
+}  // namespace psb
+#include "fd_ws.cuh"
+namespace psb {
+
+static bool fd_pipeline_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("PSB_FD_PIPELINE");
+    return e != nullptr && e[0] == '1';
+  }();
+  return on;
+}
+
 template <typename T, int H, int MODE, bool ACC>
 static int launch_fd(const FDParams<T>& p, cudaStream_t stream) {
+  if constexpr (!ACC && (MODE == 1 || MODE == 14 || MODE == 15)) {
+    if (fd_pipeline_enabled()) {
+      const int rc = launch_fd_ws<T, H, MODE>(p, stream);
+      if (rc >= 0) return rc;
+    }
+  }
   constexpr int BY = 8, BZ = 64;
   FDParams<T> q = p;
   q.xchunk = 32;

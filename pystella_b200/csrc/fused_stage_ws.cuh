@@ -37,6 +37,7 @@ struct WsCfg {
   static constexpr int SH = AL ? H % VEC_ : 0;
   static constexpr int GV = AL ? VEC_ : ws_gcd(VEC_, H);
   static constexpr int BZ = TZ * VEC;
+  static constexpr int GVO = VEC_;   // un-padded arrays: a thread's sites start VEC-aligned
   // left pad of the f tile: the TMA box must start 16-byte aligned in global memory,
   // i.e. at padded column z0 = z0 + H - HL with HL = H rounded up to GV elements
   static constexpr int HL = ((H + GV - 1) / GV) * GV;

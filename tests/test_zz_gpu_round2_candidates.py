@@ -318,6 +318,43 @@ def _case_aligned(case):
         assert np.isclose(sums[n], np.sum(O.poly_eval(pot, fi)), rtol=1e3 * tol)
 
 
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+@pytest.mark.parametrize("h", [2, 4])
+def test_finite_difference_pipeline(dtype, h):
+    """PSB_FD_PIPELINE=1: lap / grad / lap+grad through the TMA pipeline == the oracle."""
+    _in_subprocess("fd_pipeline", dtype, h)
+
+
+def _case_fd_pipeline(dtype, h):
+    from helpers import scale_err
+    rng = np.random.default_rng(30 + h)
+    N = (20, 12, 136)
+    dx = (0.1, 0.2, 0.3)
+    decomp = ps.DomainDecomposition((1, 1, 1), h, N)
+    derivs = ps.FiniteDifferencer(decomp, h, dx)
+    fh = rng.random((2,) + tuple(n + 2 * h for n in N)).astype(dtype)
+    fx = to_dev(fh)
+    tdt = getattr(torch, dtype)
+    lap = torch.full((2,) + N, float("nan"), dtype=tdt, device="cuda")
+    grd = torch.full((2, 3) + N, float("nan"), dtype=tdt, device="cuda")
+    lap2 = torch.full_like(lap, float("nan"))
+    grd2 = torch.full_like(grd, float("nan"))
+    derivs(None, fx, lap=lap, grd=grd)          # MODE 15
+    derivs(None, fx, lap=lap2)                  # MODE 1
+    derivs(None, fx, grd=grd2)                  # MODE 14
+    torch.cuda.synchronize()
+    tol = 1e-12 if dtype == "float64" else 2e-5
+    f64 = fx.cpu().numpy().astype(np.float64)
+    for n in range(2):
+        want_lap = O.laplacian(f64[n], h, dx)
+        want_grd = O.gradient(f64[n], h, dx)
+        for got in (lap[n], lap2[n]):
+            assert scale_err(got.cpu().numpy(), want_lap) < tol
+        for got in (grd[n], grd2[n]):
+            for mu in range(3):
+                assert scale_err(got[mu].cpu().numpy(), want_grd[mu]) < tol
+
+
 def _case_generated_rhs(dtype, rtol):
     """Row f-2: a non-polynomial potential (axion-like, V = lam (1 - cos f) + g^2 f^2 chi^2/2)
     through the fused TMA pipeline compiled at run time with a generated right-hand side ==
@@ -429,6 +466,9 @@ if __name__ == "__main__":
         _case_generated_loop()
     elif sys.argv[1] == "aligned":
         _case_aligned(int(sys.argv[2]))
+    elif sys.argv[1] == "fd_pipeline":
+        os.environ["PSB_FD_PIPELINE"] = "1"
+        _case_fd_pipeline(sys.argv[2], int(sys.argv[3]))
     else:
         raise SystemExit(f"unknown case {sys.argv[1]}")
     print("ok")
