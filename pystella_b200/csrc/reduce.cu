@@ -5,6 +5,7 @@
 // pass (warp shuffle -> block -> per-block partials) and a single-block finalize
 // kernel folds the partials in a fixed order (deterministic for a given grid).
 #include <float.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -108,8 +109,135 @@ __global__ void __launch_bounds__(RED_THREADS)
   }
 }
 
+// EXPERIMENTAL (opt-in: PSB_REDUCE_V2=1; written after round 1's GPU budget was spent):
+// the same reduction with two sites per thread as one vector load per array and four
+// row segments in flight before the arithmetic starts (memory-level parallelism x8 per
+// thread).  Needs even Nz and halos and 2-element aligned rows; otherwise reduce_kernel.
+constexpr int RED_V2_UNROLL = 4;
+
+template <typename T, int NARR, int NOUT>
+__global__ void __launch_bounds__(RED_THREADS)
+    reduce_kernel_v2(const __grid_constant__ RedParams<T> p) {
+  double acc[NOUT];
+#pragma unroll
+  for (int r = 0; r < NOUT; ++r) acc[r] = red_identity(r < p.noutputs ? p.op[r] : 0);
+
+  const int64_t rows = (int64_t)p.Nx * p.Ny;
+  const int lane_z = threadIdx.x % 64, sub = threadIdx.x / 64;
+  constexpr int U = RED_V2_UNROLL;
+  for (int64_t row = (int64_t)blockIdx.x * 4 + sub; row < rows;
+       row += (int64_t)gridDim.x * 4) {
+    const int i = (int)(row / p.Ny), j = (int)(row % p.Ny);
+    const T* rp[NARR];
+#pragma unroll
+    for (int m = 0; m < NARR; ++m) {
+      const int h = p.halo[m];
+      rp[m] = (m < p.narrays)
+                  ? p.arrays[m] + ((int64_t)(i + h) * (p.Ny + 2 * h) + (j + h)) *
+                                          (p.Nz + 2 * h) + h
+                  : p.arrays[0];
+    }
+    for (int k0 = lane_z * 2; k0 < p.Nz; k0 += 64 * 2 * U) {
+      Vec<T, 2> raw[U][NARR];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int k = k0 + u * 128;
+#pragma unroll
+        for (int m = 0; m < NARR; ++m) {
+          if (k < p.Nz) {
+            raw[u][m] = ld_vec<T, 2>(rp[m] + k);
+          } else {
+            raw[u][m].v[0] = raw[u][m].v[1] = (T)0;
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (k0 + u * 128 >= p.Nz) continue;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          double v[NARR];
+#pragma unroll
+          for (int m = 0; m < NARR; ++m) v[m] = (double)raw[u][m].v[e];
+#pragma unroll
+          for (int r = 0; r < NOUT; ++r) {
+            if (r < p.noutputs) {
+              double val = 0.0;
+              for (int t = p.term_begin[r]; t < p.term_begin[r + 1]; ++t) {
+                double term = p.coef[t];
+#pragma unroll
+                for (int m = 0; m < NARR; ++m) {
+                  const int pw = p.power[t][m];
+                  if (pw >= 1) term *= v[m];
+                  if (pw >= 2) term *= v[m];
+                  for (int x = 2; x < pw; ++x) term *= v[m];
+                }
+                val += term;
+              }
+              if (p.flags[r] & 1) val = fabs(val);
+              const int op = p.op[r];
+              acc[r] = op == 0 ? acc[r] + val : red_combine(op, acc[r], val);
+            }
+          }
+        }
+      }
+    }
+  }
+
+  __shared__ double sh[RED_THREADS / 32][NOUT];
+  const int lane = threadIdx.x % 32, warp = threadIdx.x / 32;
+#pragma unroll
+  for (int r = 0; r < NOUT; ++r) {
+    if (r < p.noutputs) {
+      double x = acc[r];
+      const int op = p.op[r];
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1)
+        x = red_combine(op, x, __shfl_xor_sync(0xffffffffu, x, d));
+      if (lane == 0) sh[warp][r] = x;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < p.noutputs) {
+    const int r = threadIdx.x, op = p.op[r];
+    double x = sh[0][r];
+    for (int w = 1; w < RED_THREADS / 32; ++w) x = red_combine(op, x, sh[w][r]);
+    p.partials[(int64_t)blockIdx.x * PSB_MAX_RED_OUTPUTS + r] = x;
+  }
+}
+
+static bool reduce_v2_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("PSB_REDUCE_V2");
+    return e != nullptr && e[0] == '1';
+  }();
+  return on;
+}
+
+template <typename T> static bool reduce_v2_layout_ok(const RedParams<T>& p) {
+  if (p.Nz % 2) return false;
+  for (int m = 0; m < p.narrays; ++m) {
+    if (p.halo[m] % 2) return false;
+    if (reinterpret_cast<uintptr_t>(p.arrays[m]) % (2 * sizeof(T))) return false;
+  }
+  return true;
+}
+
 template <typename T, int NARR>
 static void launch_reduce_nout(const RedParams<T>& p, int nblocks, cudaStream_t s) {
+  if constexpr (NARR <= 4) {
+    if (reduce_v2_enabled() && reduce_v2_layout_ok(p)) {
+      if (p.noutputs <= 2)
+        reduce_kernel_v2<T, NARR, 2><<<nblocks, RED_THREADS, 0, s>>>(p);
+      else if (p.noutputs <= 4)
+        reduce_kernel_v2<T, NARR, 4><<<nblocks, RED_THREADS, 0, s>>>(p);
+      else if (p.noutputs <= 8)
+        reduce_kernel_v2<T, NARR, 8><<<nblocks, RED_THREADS, 0, s>>>(p);
+      else
+        reduce_kernel_v2<T, NARR, PSB_MAX_RED_OUTPUTS><<<nblocks, RED_THREADS, 0, s>>>(p);
+      return;
+    }
+  }
   if (p.noutputs <= 2)
     reduce_kernel<T, NARR, 2><<<nblocks, RED_THREADS, 0, s>>>(p);
   else if (p.noutputs <= 4)

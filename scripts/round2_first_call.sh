@@ -24,8 +24,8 @@ tail -c 600 "$out/bench_n1.json" | tee -a "$out/summary.txt"
 
 echo "== stand-alone kernels, fused GW vs unfused, generated stage vs hand-written ==" | tee -a "$out/summary.txt"
 timeout 600 python scripts/dev_time_api.py > "$out/time_api.log" 2>&1
-echo "-- with PSB_FD_PIPELINE=1" >> "$out/time_api.log"
-PSB_FD_PIPELINE=1 timeout 600 python scripts/dev_time_api.py >> "$out/time_api.log" 2>&1
+echo "-- with PSB_FD_PIPELINE=1 PSB_REDUCE_V2=1" >> "$out/time_api.log"
+PSB_FD_PIPELINE=1 PSB_REDUCE_V2=1 timeout 600 python scripts/dev_time_api.py >> "$out/time_api.log" 2>&1
 timeout 600 python scripts/dev_time_round2.py > "$out/time_round2.log" 2>&1
 cat "$out/time_api.log" "$out/time_round2.log" | tee -a "$out/summary.txt"
 

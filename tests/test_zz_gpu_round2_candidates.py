@@ -355,6 +355,39 @@ def _case_fd_pipeline(dtype, h):
                 assert scale_err(got[mu].cpu().numpy(), want_grd[mu]) < tol
 
 
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+def test_reduce_v2(dtype):
+    """PSB_REDUCE_V2=1 (vector loads, 8 sites in flight per thread) == numpy."""
+    _in_subprocess("reduce_v2", dtype)
+
+
+def _case_reduce_v2(dtype):
+    rng = np.random.default_rng(40)
+    N, h = (12, 10, 260), 2
+    decomp = ps.DomainDecomposition((1, 1, 1), h, N)
+    sector = ps.ScalarSector(2, potential=lambda f: f[0]**2 / 2 + f[0]**2 * f[1]**2 / 2)
+    red = ps.Reduction(decomp, sector, halo_shape=h, grid_size=float(np.prod(N)))
+    pad = tuple(n + 2 * h for n in N)
+    f = rng.random((2,) + pad).astype(dtype)
+    d = rng.random((2,) + pad).astype(dtype)
+    lap = rng.random((2,) + N).astype(dtype)
+    out = red(None, f=to_dev(f), dfdt=to_dev(d), lap_f=to_dev(lap), a=np.array(1.3))
+    fi = f[:, h:-h, h:-h, h:-h].astype(np.float64)
+    di = d[:, h:-h, h:-h, h:-h].astype(np.float64)
+    tol = 1e-12 if dtype == "float64" else 1e-5
+    want_kin = [np.mean(di[n]**2) / 2 / 1.3**2 for n in range(2)]
+    want_grad = [np.mean(-fi[n] * lap[n].astype(np.float64)) / 2 / 1.3**2 for n in range(2)]
+    want_pot = np.mean(fi[0]**2 / 2 + fi[0]**2 * fi[1]**2 / 2)
+    assert np.allclose(out["kinetic"], want_kin, rtol=tol)
+    assert np.allclose(out["gradient"], want_grad, rtol=tol)
+    assert np.allclose(out["potential"], [want_pot], rtol=tol)
+    stats = ps.FieldStatistics(decomp, h, max_min=True, grid_size=float(np.prod(N)))
+    st = stats(to_dev(f))
+    assert np.allclose(st["mean"], fi.mean(axis=(1, 2, 3)), rtol=tol)
+    assert np.allclose(st["max"], fi.max(axis=(1, 2, 3)), rtol=tol)
+    assert np.allclose(st["abs_min"], np.abs(fi).min(axis=(1, 2, 3)), rtol=tol)
+
+
 def _case_generated_rhs(dtype, rtol):
     """Row f-2: a non-polynomial potential (axion-like, V = lam (1 - cos f) + g^2 f^2 chi^2/2)
     through the fused TMA pipeline compiled at run time with a generated right-hand side ==
@@ -466,6 +499,9 @@ if __name__ == "__main__":
         _case_generated_loop()
     elif sys.argv[1] == "aligned":
         _case_aligned(int(sys.argv[2]))
+    elif sys.argv[1] == "reduce_v2":
+        os.environ["PSB_REDUCE_V2"] = "1"
+        _case_reduce_v2(sys.argv[2])
     elif sys.argv[1] == "fd_pipeline":
         os.environ["PSB_FD_PIPELINE"] = "1"
         _case_fd_pipeline(sys.argv[2], int(sys.argv[3]))
