@@ -30,6 +30,7 @@ from pystella_b200.projectors import Projector
 from pystella_b200.spectral import SpectralCollocator, SpectralPoissonSolver
 from pystella_b200.histogram import Histogrammer, FieldHistogrammer
 from pystella_b200 import output
+from pystella_b200.graph import StepGraph, capture_steps
 from pystella_b200.output import OutputFile
 from pystella_b200._lib import PsbError
 
@@ -61,7 +62,7 @@ __all__ = [
     "get_field_args", "var",
     "DFT", "RayleighGenerator", "PowerSpectra", "Projector",
     "SpectralCollocator", "SpectralPoissonSolver", "Histogrammer", "FieldHistogrammer",
-    "OutputFile",
+    "OutputFile", "StepGraph", "capture_steps",
     "Sector", "ScalarSector", "TensorPerturbationSector", "tensor_index",
     "get_rho_and_p",
     "ElementWiseMap", "FusedStencilStage", "Stencil", "StreamingStencil", "Stepper",

@@ -229,6 +229,44 @@ def test_stencil_map_raw_subscripts(cls):
     assert O.get_errs(y_true, yd.cpu().numpy())[0] < 5e-14
 
 
+def test_capture_steps_equals_eager():
+    """ps.capture_steps: graph replays == eager steps (fused stage + DeviceExpansion)."""
+    rng = np.random.default_rng(19)
+    N, h = (16, 16, 32), 2
+    dx = tuple(5 / n for n in N)
+    dt, gs = 0.1 * min(dx), float(np.prod(N))
+    pad = (1,) + tuple(n + 2 * h for n in N)
+    f0 = .2 + 1e-2 * rng.standard_normal(pad)
+    d0 = -.1 + 1e-2 * rng.standard_normal(pad)
+    sector = ps.ScalarSector(1, potential=lambda g: g[0]**2 / 2)
+    results = []
+    for use_graph in (False, True):
+        stepper = ps.LowStorageRK54(sector, halo_shape=h, dt=dt, dx=dx,
+                                    MapKernel=ps.FusedStencilStage, energy=True)
+        expand = ps.DeviceExpansion(0.03, ps.LowStorageRK54, grid_size=gs, nscalars=1)
+        f, d = to_dev(f0), to_dev(d0)
+
+        def one_step():
+            for s in range(stepper.num_stages):
+                stepper(s, f=f, dfdt=d, a=expand.a, hubble=expand.hubble)
+                expand.step(s, stepper, dt)
+        if use_graph:
+            # the capture's warm-up runs 2 steps, the replays 4 more, one eager: 7 in all
+            graph = ps.capture_steps(one_step, steps_per_replay=2, warmup=1)
+            assert graph.steps_per_replay == 2
+            graph.run(5)
+        else:
+            for _ in range(7):
+                one_step()
+        torch.cuda.synchronize()
+        results.append((f.cpu().numpy().copy(), d.cpu().numpy().copy(),
+                        float(expand.get()["a"])))
+    inner = (slice(None),) + (slice(h, -h),) * 3
+    assert np.array_equal(results[0][0][inner], results[1][0][inner])
+    assert np.array_equal(results[0][1][inner], results[1][1][inner])
+    assert results[0][2] == results[1][2]
+
+
 def _in_subprocess(case, *args, timeout=240):
     """Kernels with mbarrier pipelines that have never run on hardware are exercised in a
     child process: a dead-locked kernel then costs one test, not the session."""
