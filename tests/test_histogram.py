@@ -1,7 +1,7 @@
 """
 Histogrammer / FieldHistogrammer: the known-answer tests of
 test/test_histogram.py, on host tensors through the decomposition's test hook (the same
-tensor operations run on the GPU; tests/test_zz_gpu_round2_candidates.py).
+tensor operations run on the GPU; tests/test_gpu_generated.py).
 """
 from itertools import product
 
