@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PSB_ABI_VERSION 1
+#define PSB_ABI_VERSION 2
 
 #define PSB_F64 0
 #define PSB_F32 1
@@ -44,6 +44,47 @@ const char* psb_last_error(void);
 int psb_abi_version(void);
 /* Compiled with FMA contraction disabled (bit-comparable with the oracle)? */
 int psb_strict_fp(void);
+
+/* ------------------------------------------------------------------------
+ * Peer tables of one node (symmetric memory, NVLink): see psb_expansion_stage_peer.
+ * ---------------------------------------------------------------------- */
+typedef struct psb_peer_args {
+  int32_t nranks, rank;
+  void* const* peer_slots;       /* device array of nranks pointers                  */
+  void* const* peer_flags;       /* device array of nranks pointers                  */
+  uint64_t* epoch;               /* device counter (this rank)                       */
+} psb_peer_args;
+
+/* ------------------------------------------------------------------------
+ * In-kernel stage tail (optional, fused stage kernels): the LAST CTA of the launch
+ * (atomic tickets) performs what the reference does on the host between two stages --
+ * Reduction.__call__ -> get_rho_and_p -> Expansion.step (pystella/reduction.py:237-255,
+ * pystella/sectors.py:211-229, pystella/expansion.py:140-157) and, multi-rank, the
+ * allreduce of pystella/decomp.py:470-491 -- with no extra launch:
+ *   PSB_TAIL_FOLD    fold this launch's energy partial rows into workspace[0..2ns]
+ *                    (fixed order: groups of 64 CTAs, then the group rows);
+ *   PSB_TAIL_PEER    all-gather of those sums over peer memory + inter-GPU flag barrier
+ *                    (exactly psb_expansion_stage_peer's protocol; with nscalars == 0 a
+ *                    pure barrier that orders the peer halo stores of the kernel);
+ *   PSB_TAIL_EXPAND  energies with the current scale factor and one low-storage stage of
+ *                    (a, adot) as psb_expansion_stage.
+ * workspace: psb_stage_tail_workspace_doubles(workspace_groups) doubles, zeroed once by
+ * the caller; workspace_groups >= ceil(CTAs of the launch / 64).
+ * ---------------------------------------------------------------------- */
+#define PSB_TAIL_FOLD 1
+#define PSB_TAIL_EXPAND 2
+#define PSB_TAIL_PEER 4
+typedef struct psb_stage_tail {
+  int32_t mode;                  /* OR of PSB_TAIL_*; 0 = none                        */
+  int32_t nscalars;              /* fields in the energy sums (0: no sums)            */
+  double* workspace;             /* sums[16] | group rows | tickets                   */
+  int64_t workspace_groups;
+  double grid_size, mpl, dt, A, B;   /* EXPAND: background stage coefficients         */
+  double* state;                 /* {a, adot, hubble, ka, kadot}                      */
+  double* energies;              /* 2 nscalars + 3 doubles                            */
+  psb_peer_args peers;           /* PEER                                              */
+} psb_stage_tail;
+int64_t psb_stage_tail_workspace_doubles(int64_t workspace_groups);
 
 /* ------------------------------------------------------------------------
  * Scalar-sector Runge-Kutta stage.
@@ -125,6 +166,10 @@ typedef struct psb_scalar_stage_args {
   int8_t vpower[PSB_MAX_TERMS][PSB_MAX_SCALARS];
   int32_t tune_xchunk;           /* 0 = default; planes marched per CTA              */
   int32_t tune_variant;          /* 0 = auto; see DESIGN.md (kernel variants)        */
+  const psb_stage_tail* tail;    /* fused only; HOST pointer, NULL = no in-kernel tail */
+  int32_t store_flags;           /* fused: bit0 = streaming (evict-first) stores for f_out,
+                                    bit1 = plain stores for dfdt/kf/kdfdt (tuning)     */
+  int32_t reserved0;
 } psb_scalar_stage_args;
 
 int psb_scalar_stage_fused(const psb_scalar_stage_args* args, void* stream);
@@ -184,10 +229,16 @@ typedef struct psb_tensor_stage_args {
 } psb_tensor_stage_args;
 int psb_tensor_stage_unfused(const psb_tensor_stage_args* args, void* stream);
 
-/* EXPERIMENTAL (opt-in; parity-green on B200, not yet timed): the same stage with
- * lap(hij_c) and the gradients of the source fields evaluated in-kernel from `hij_in`
- * and `src` (the scalar fields' OLD values, padded, valid face halos), in the TMA
- * pipeline of psb_scalar_stage_fused; hij ping-pongs into `hij_out`. */
+/* The same stage with lap(hij_c) and the gradients of the source fields evaluated
+ * in-kernel from `hij_in` and `src` (the scalar fields' OLD values, padded, valid face
+ * halos), in the TMA pipeline of psb_scalar_stage_fused; hij ping-pongs into `hij_out`
+ * (write-through periodic halos where wrap_* is set).  This is the multi-array stencil of
+ * pystella/sectors.py:187-204 without lap_hij / dfdx ever touching HBM: per site and
+ * stage 6 x (read hij, dhijdt, 2 twins; write the same) = 48 S bytes + the source planes
+ * (2 S, shared by the six components through L2).  x-slab decompositions: the new hij of
+ * the h lowest / highest site planes is also stored into the neighbours' hij_out halos
+ * over peer memory (peer_*; as psb_scalar_stage_args), and `tail` lets the launch's last
+ * CTA run the inter-GPU barrier + background stage (psb_stage_tail; no PSB_TAIL_FOLD). */
 typedef struct psb_tensor_fused_args {
   int32_t dtype, nscalars, h;
   int32_t wrap_x, wrap_y, wrap_z;
@@ -202,6 +253,14 @@ typedef struct psb_tensor_fused_args {
   double dx[3];
   double dt, A, B, hubble, source_coef;
   const double* hubble_dev;
+  void* peer_lo_hij_out;         /* rank rx-1's hij_out, component 0 (or NULL)        */
+  void* peer_hi_hij_out;         /* rank rx+1's hij_out, component 0 (or NULL)        */
+  int64_t peer_lo_Nx;            /* x extent of rank rx-1                             */
+  int64_t peer_lo_stride;        /* component strides (elements) of the peers' buffers */
+  int64_t peer_hi_stride;
+  const psb_stage_tail* tail;    /* HOST pointer, NULL = none                         */
+  int32_t tune_xchunk;           /* 0 = default                                       */
+  int32_t tune_variant;          /* 0 = auto; 1 = 8-byte vectors for fp32             */
 } psb_tensor_fused_args;
 int psb_tensor_stage_fused(const psb_tensor_fused_args* args, void* stream);
 
@@ -333,12 +392,6 @@ int psb_expansion_stage(const double* sums, int nscalars, double grid_size, doub
  * the peer-memory halo stores of psb_scalar_stage_fused before the next stage.
  * `epoch` is a device counter the kernel increments (CUDA-graph friendly).
  * With nscalars == 0 only the barrier is performed (no energies / expansion). */
-typedef struct psb_peer_args {
-  int32_t nranks, rank;
-  void* const* peer_slots;       /* device array of nranks pointers                  */
-  void* const* peer_flags;       /* device array of nranks pointers                  */
-  uint64_t* epoch;               /* device counter (this rank)                       */
-} psb_peer_args;
 int psb_expansion_stage_peer(const psb_peer_args* peers, const double* sums, int nscalars,
                              double grid_size, double mpl, double dt, double A, double B,
                              double* state, double* energies, void* stream);

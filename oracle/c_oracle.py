@@ -101,5 +101,51 @@ def preheating_steps(nsteps, A, B, f, dfdt, kf, kd, lap, h, dx, dt, mpl, grid_si
         int(with_expansion))
 
 
+def gradient(f, grd, h, dx, native=False):
+    Nx, Ny, Nz = grd.shape[-3:]
+    dxa = np.asarray(dx, dtype=np.float64)
+    load(native).orc_gradient(_p(f), _p(grd), C.c_int64(Nx), C.c_int64(Ny), C.c_int64(Nz), h,
+                              _p(dxa))
+
+
+def tensor_stage(hij, dhij, kh, kdh, lap_hij, dfdx, h, dt, A, B, hubble, native=False):
+    Nx, Ny, Nz = lap_hij.shape[-3:]
+    load(native).orc_lsrk_tensor_stage(
+        _p(hij), _p(dhij), _p(kh), _p(kdh), _p(lap_hij), _p(dfdx), int(dfdx.shape[0]),
+        C.c_int64(Nx), C.c_int64(Ny), C.c_int64(Nz), h, C.c_double(dt), C.c_double(A),
+        C.c_double(B), C.c_double(hubble))
+
+
+def preheating_gw_steps(nsteps, A, B, f, dfdt, kf, kd, lap_f, dfdx, hij, dhij, kh, kdh, lap_hij,
+                        h, dx, dt, mpl, grid_size, pot, state, energies, with_expansion=True,
+                        native=False):
+    """Scalars + tensor perturbations + background, loop of scalar_preheating.py:258-266."""
+    Nx, Ny, Nz = lap_f.shape[-3:]
+    Aa, Ba = np.asarray(A, dtype=np.float64), np.asarray(B, dtype=np.float64)
+    dxa = np.asarray(dx, dtype=np.float64)
+    load(native).orc_preheating_gw_steps(
+        nsteps, len(Aa), _p(Aa), _p(Ba), _p(f), _p(dfdt), _p(kf), _p(kd), _p(lap_f), _p(dfdx),
+        _p(hij), _p(dhij), _p(kh), _p(kdh), _p(lap_hij),
+        C.c_int64(Nx), C.c_int64(Ny), C.c_int64(Nz), h, _p(dxa), C.c_double(dt),
+        C.c_double(mpl), C.c_double(grid_size), C.byref(pot), _p(state), _p(energies),
+        int(with_expansion))
+
+
+def gw_initial_derivatives(f, hij, h, dx, native=False):
+    """share_halos + (lap_f, dfdx, lap_hij) of the initial state, as the example computes
+    them before its loop (scalar_preheating.py:236-247)."""
+    ns = f.shape[0]
+    N = tuple(n - 2 * h for n in f.shape[-3:])
+    lap_f, dfdx, lap_hij = np.zeros((ns,) + N), np.zeros((ns, 3) + N), np.zeros((6,) + N)
+    for n in range(ns):
+        share_halos(f[n], h, native)
+        laplacian(f[n], lap_f[n], h, dx, native)
+        gradient(f[n], dfdx[n], h, dx, native)
+    for c in range(6):
+        share_halos(hij[c], h, native)
+        laplacian(hij[c], lap_hij[c], h, dx, native)
+    return lap_f, dfdx, lap_hij
+
+
 def num_threads(native=False):
     return load(native).orc_num_threads()

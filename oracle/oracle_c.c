@@ -221,6 +221,120 @@ void orc_preheating_steps(int nsteps, int nstages, const double* A, const double
     }
 }
 
+/* ---------------------------------------------------------------------------
+ * Tensor-perturbation sector (config 4): first-derivative stencils
+ * (pystella/derivs.py:127-131, 293-294; term order c1*f[+1], -c1*f[-1], c2*f[+2], ...),
+ * TensorPerturbationSector.rhs_dict (pystella/sectors.py:187-204) and the loop of
+ * examples/scalar_preheating.py:258-266 with gravitational waves enabled.
+ * ------------------------------------------------------------------------- */
+static const double GRADC[5][5] = {
+    {0, 0, 0, 0, 0},
+    {0, 1.0 / 2.0, 0, 0, 0},
+    {0, 8.0 / 12.0, -1.0 / 12.0, 0, 0},
+    {0, 45.0 / 60.0, -9.0 / 60.0, 1.0 / 60.0, 0},
+    {0, 672.0 / 840.0, -168.0 / 840.0, 32.0 / 840.0, -3.0 / 840.0}};
+
+/* grd: (3, Nx, Ny, Nz) */
+void orc_gradient(const double* f, double* grd, int64_t Nx, int64_t Ny, int64_t Nz, int h,
+                  const double* dx) {
+  const int64_t Py = Ny + 2 * h, Pz = Nz + 2 * h, ls = Nx * Ny * Nz;
+  const double wx = 1 / dx[0], wy = 1 / dx[1], wz = 1 / dx[2];
+  const double* c = GRADC[h];
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int64_t i = 0; i < Nx; ++i)
+    for (int64_t j = 0; j < Ny; ++j) {
+      const double* p = f + IDX(i + h, j + h, h);
+      double* out = grd + (i * Ny + j) * Nz;
+      for (int64_t k = 0; k < Nz; ++k) {
+        double gx = 0, gy = 0, gz = 0;
+        for (int s = 1; s <= h; ++s) {
+          if (s == 1) {
+            gx = c[s] * p[k + s * Py * Pz];
+            gy = c[s] * p[k + s * Pz];
+            gz = c[s] * p[k + s];
+          } else {
+            gx = gx + c[s] * p[k + s * Py * Pz];
+            gy = gy + c[s] * p[k + s * Pz];
+            gz = gz + c[s] * p[k + s];
+          }
+          gx = gx + (-1 * c[s]) * p[k - s * Py * Pz];
+          gy = gy + (-1 * c[s]) * p[k - s * Pz];
+          gz = gz + (-1 * c[s]) * p[k - s];
+        }
+        out[k] = gx * wx;
+        out[k + ls] = gy * wy;
+        out[k + 2 * ls] = gz * wz;
+      }
+    }
+}
+
+/* hij, dhij, kh, kdh: (6, padded); lap_hij: (6, N); dfdx: (ns, 3, N) */
+void orc_lsrk_tensor_stage(double* hij, double* dhij, double* kh, double* kdh,
+                           const double* lap_hij, const double* dfdx, int ns, int64_t Nx,
+                           int64_t Ny, int64_t Nz, int h, double dt, double A, double B,
+                           double hubble) {
+  const int64_t Px = Nx + 2 * h, Py = Ny + 2 * h, Pz = Nz + 2 * h;
+  const int64_t fs = Px * Py * Pz, ls = Nx * Ny * Nz;
+  static const int CI[6] = {0, 0, 0, 1, 1, 2}, CJ[6] = {0, 1, 2, 1, 2, 2};
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int64_t i = 0; i < Nx; ++i)
+    for (int64_t j = 0; j < Ny; ++j)
+      for (int64_t k = 0; k < Nz; ++k) {
+        const int64_t o = IDX(i + h, j + h, k + h), ol = (i * Ny + j) * Nz + k;
+        for (int c = 0; c < 6; ++c) {
+          double S = 0;
+          for (int n = 0; n < ns; ++n) {
+            const double t = dfdx[ol + (n * 3 + CI[c]) * ls] * dfdx[ol + (n * 3 + CJ[c]) * ls];
+            S = (n == 0) ? t : S + t;
+          }
+          const int64_t oc = o + c * fs;
+          const double dv = dhij[oc];
+          const double rhs = (lap_hij[ol + c * ls] - (2.0 * hubble) * dv) + (16.0 * M_PI) * S;
+          const double khv = A * kh[oc] + dt * dv;
+          const double kdv = A * kdh[oc] + dt * rhs;
+          kh[oc] = khv;
+          kdh[oc] = kdv;
+          hij[oc] = hij[oc] + B * khv;
+          dhij[oc] = dv + B * kdv;
+        }
+      }
+}
+
+/*
+ * nsteps full steps of scalar fields + tensor perturbations + background, in the order of
+ * examples/scalar_preheating.py:258-266: stepper (all sectors, from the old state) ->
+ * expand.step -> derivs(f: lap, grd) + energies -> derivs(hij: lap).  On entry lap_f, dfdx,
+ * lap_hij and energies must belong to the initial state.
+ */
+void orc_preheating_gw_steps(int nsteps, int nstages, const double* A, const double* B,
+                             double* f, double* dfdt, double* kf, double* kd, double* lap_f,
+                             double* dfdx, double* hij, double* dhij, double* kh, double* kdh,
+                             double* lap_hij, int64_t Nx, int64_t Ny, int64_t Nz, int h,
+                             const double* dx, double dt, double mpl, double grid_size,
+                             const orc_potential* pot, double* state, double* energies,
+                             int with_expansion) {
+  const int64_t fs = (Nx + 2 * h) * (Ny + 2 * h) * (Nz + 2 * h), ls = Nx * Ny * Nz;
+  const int ns = pot->nscalars;
+  for (int step = 0; step < nsteps; ++step)
+    for (int s = 0; s < nstages; ++s) {
+      orc_lsrk_scalar_stage(f, dfdt, kf, kd, lap_f, Nx, Ny, Nz, h, dt, A[s], B[s], state[0],
+                            state[2], pot);
+      orc_lsrk_tensor_stage(hij, dhij, kh, kdh, lap_hij, dfdx, ns, Nx, Ny, Nz, h, dt, A[s],
+                            B[s], state[2]);
+      if (with_expansion) expansion_stage(state, energies, ns, mpl, dt, A[s], B[s]);
+      for (int n = 0; n < ns; ++n) {
+        orc_share_halos(f + n * fs, Nx, Ny, Nz, h);
+        orc_laplacian(f + n * fs, lap_f + n * ls, Nx, Ny, Nz, h, dx);
+        orc_gradient(f + n * fs, dfdx + n * 3 * ls, Nx, Ny, Nz, h, dx);
+      }
+      orc_scalar_energy(f, dfdt, lap_f, Nx, Ny, Nz, h, state[0], grid_size, pot, energies);
+      for (int c = 0; c < 6; ++c) {
+        orc_share_halos(hij + c * fs, Nx, Ny, Nz, h);
+        orc_laplacian(hij + c * fs, lap_hij + c * ls, Nx, Ny, Nz, h, dx);
+      }
+    }
+}
+
 int orc_num_threads(void) {
   int n = 1;
 #ifdef _OPENMP

@@ -24,6 +24,25 @@ c_void_p, c_int, c_int32, c_int64, c_double = (
     C.c_void_p, C.c_int, C.c_int32, C.c_int64, C.c_double)
 
 
+class PeerArgs(C.Structure):
+    _fields_ = [("nranks", c_int32), ("rank", c_int32), ("peer_slots", c_void_p),
+                ("peer_flags", c_void_p), ("epoch", c_void_p)]
+
+
+TAIL_FOLD, TAIL_EXPAND, TAIL_PEER = 1, 2, 4
+TAIL_GROUP = 64
+
+
+class StageTail(C.Structure):
+    """psb_stage_tail: what the last CTA of a fused stage launch does (fold energy sums,
+    peer barrier, background stage)."""
+    _fields_ = [("mode", c_int32), ("nscalars", c_int32), ("workspace", c_void_p),
+                ("workspace_groups", c_int64),
+                ("grid_size", c_double), ("mpl", c_double), ("dt", c_double),
+                ("A", c_double), ("B", c_double),
+                ("state", c_void_p), ("energies", c_void_p), ("peers", PeerArgs)]
+
+
 class ScalarStageArgs(C.Structure):
     _fields_ = [
         ("dtype", c_int32), ("nscalars", c_int32), ("h", c_int32),
@@ -49,6 +68,8 @@ class ScalarStageArgs(C.Structure):
         ("vcoef", c_double * MAX_TERMS),
         ("vpower", (C.c_int8 * MAX_SCALARS) * MAX_TERMS),
         ("tune_xchunk", c_int32), ("tune_variant", c_int32),
+        ("tail", C.POINTER(StageTail)),
+        ("store_flags", c_int32), ("reserved0", c_int32),
     ]
 
 
@@ -85,12 +106,12 @@ class TensorFusedArgs(C.Structure):
                 ("khij", c_void_p), ("kdhijdt", c_void_p), ("src", c_void_p),
                 ("src_stride", c_int64), ("dx", c_double * 3),
                 ("dt", c_double), ("A", c_double), ("B", c_double), ("hubble", c_double),
-                ("source_coef", c_double), ("hubble_dev", c_void_p)]
-
-
-class PeerArgs(C.Structure):
-    _fields_ = [("nranks", c_int32), ("rank", c_int32), ("peer_slots", c_void_p),
-                ("peer_flags", c_void_p), ("epoch", c_void_p)]
+                ("source_coef", c_double), ("hubble_dev", c_void_p),
+                ("peer_lo_hij_out", c_void_p), ("peer_hi_hij_out", c_void_p),
+                ("peer_lo_Nx", c_int64), ("peer_lo_stride", c_int64),
+                ("peer_hi_stride", c_int64),
+                ("tail", C.POINTER(StageTail)),
+                ("tune_xchunk", c_int32), ("tune_variant", c_int32)]
 
 
 class ReduceArgs(C.Structure):
@@ -127,6 +148,7 @@ SYMBOLS = {
     "psb_last_error": (C.c_char_p, []),
     "psb_abi_version": (c_int, []),
     "psb_strict_fp": (c_int, []),
+    "psb_stage_tail_workspace_doubles": (c_int64, [c_int64]),
     "psb_scalar_stage_fused": (c_int, [C.POINTER(ScalarStageArgs), c_void_p]),
     "psb_scalar_stage_unfused": (c_int, [C.POINTER(ScalarStageArgs), c_void_p]),
     "psb_scalar_rk_stage": (c_int, [C.POINTER(RKStageArgs), c_void_p]),
@@ -188,7 +210,7 @@ def load(strict=False):
             fn = getattr(lib, name)  # AttributeError if the symbol is missing
             fn.restype = restype
             fn.argtypes = argtypes
-        if lib.psb_abi_version() != 1:
+        if lib.psb_abi_version() != 2:
             raise PsbError("ABI version mismatch")
         _libs[strict] = lib
     return _libs[strict]

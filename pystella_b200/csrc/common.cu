@@ -3,6 +3,7 @@
 #include <string.h>
 
 #include "common.cuh"
+#include "stage_tail.cuh"
 
 namespace psb {
 
@@ -65,9 +66,47 @@ int encode_field_tensor_map(CUtensorMap* map, int dtype, const void* base,
   return r == CUDA_SUCCESS ? 0 : 5;
 }
 
+int validate_tail(const psb_stage_tail* a, int64_t nblocks, bool has_partials,
+                  const char* who) {
+  if (a == nullptr || a->mode == 0) return 0;
+  PSB_REQUIRE((a->mode & ~(PSB_TAIL_FOLD | PSB_TAIL_EXPAND | PSB_TAIL_PEER)) == 0,
+              "%s: unknown stage-tail mode bits 0x%x", who, a->mode);
+  PSB_REQUIRE(a->workspace != nullptr, "%s: stage tail without a workspace", who);
+  PSB_REQUIRE(a->nscalars >= 0 && a->nscalars <= PSB_MAX_SCALARS,
+              "%s: stage tail nscalars=%d out of range", who, a->nscalars);
+  if (a->mode & PSB_TAIL_FOLD) {
+    PSB_REQUIRE(has_partials, "%s: PSB_TAIL_FOLD needs energy_partials", who);
+    PSB_REQUIRE(a->nscalars >= 1, "%s: PSB_TAIL_FOLD needs nscalars >= 1", who);
+    PSB_REQUIRE(a->workspace_groups >= (nblocks + TAIL_GROUP - 1) / TAIL_GROUP,
+                "%s: stage-tail workspace holds %lld group rows, the launch needs %lld", who,
+                (long long)a->workspace_groups,
+                (long long)((nblocks + TAIL_GROUP - 1) / TAIL_GROUP));
+  }
+  PSB_REQUIRE(a->workspace_groups >= 0, "%s: negative workspace_groups", who);
+  if (a->mode & PSB_TAIL_EXPAND) {
+    PSB_REQUIRE(a->nscalars >= 1 && a->state && a->energies,
+                "%s: PSB_TAIL_EXPAND needs nscalars >= 1, state and energies", who);
+    PSB_REQUIRE(a->grid_size > 0 && a->mpl > 0, "%s: stage tail: bad grid_size/mpl", who);
+  }
+  if (a->mode & PSB_TAIL_PEER) {
+    PSB_REQUIRE(a->peers.nranks >= 1 && a->peers.nranks <= 64 && a->peers.rank >= 0 &&
+                    a->peers.rank < a->peers.nranks,
+                "%s: stage tail: bad rank/nranks", who);
+    PSB_REQUIRE(a->peers.peer_slots && a->peers.peer_flags && a->peers.epoch,
+                "%s: stage tail: null peer tables", who);
+  }
+  return 0;
+}
+
 }  // namespace psb
 
 extern "C" {
+
+int64_t psb_stage_tail_workspace_doubles(int64_t workspace_groups) {
+  if (workspace_groups < 0) return -1;
+  // sums | group rows | tickets (uint32: one global + one per group), rounded up
+  return PSB_ENERGY_STRIDE * (1 + workspace_groups) + (workspace_groups + 2 + 1) / 2 + 1;
+}
 
 const char* psb_last_error(void) { return psb::g_error; }
 int psb_abi_version(void) { return PSB_ABI_VERSION; }

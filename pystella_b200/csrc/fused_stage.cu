@@ -1,6 +1,7 @@
 // C-ABI entry points of the fused stage; the kernels live in fused_stage_impl.cuh
 // and are instantiated per dtype in fused_stage_f64.cu / fused_stage_f32.cu.
 #include "common.cuh"
+#include "stage_tail.cuh"
 
 namespace psb {
 thread_local psb_fused_plan* t_fused_plan = nullptr;
@@ -66,7 +67,20 @@ static int validate(const psb_scalar_stage_args* a) {
 extern "C" int psb_scalar_stage_fused(const psb_scalar_stage_args* a, void* stream) {
   using namespace psb;
   if (int rc = validate(a)) return rc;
-  if (a->x_begin == a->x_end && a->x2_begin == a->x2_end) return 0;
+  if (a->x_begin == a->x_end && a->x2_begin == a->x2_end) {
+    PSB_REQUIRE(a->tail == nullptr || a->tail->mode == 0,
+                "psb_scalar_stage_fused: a stage tail needs a non-empty launch");
+    return 0;
+  }
+  if (a->tail != nullptr && a->tail->mode != 0) {
+    int64_t nblocks = 0;
+    const int rc0 = a->dtype == PSB_F64 ? fused_dispatch_f64(a, nullptr, &nblocks)
+                                        : fused_dispatch_f32(a, nullptr, &nblocks);
+    if (rc0) return rc0;
+    if (int rc = validate_tail(a->tail, nblocks, a->energy_partials != nullptr,
+                               "psb_scalar_stage_fused"))
+      return rc;
+  }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   return a->dtype == PSB_F64 ? fused_dispatch_f64(a, s, nullptr)
                              : fused_dispatch_f32(a, s, nullptr);
@@ -79,6 +93,15 @@ extern "C" int psb_scalar_stage_fused_plan(const psb_scalar_stage_args* a,
   if (int rc = validate(a)) return rc;
   PSB_REQUIRE(a->x_begin != a->x_end || a->x2_begin != a->x2_end,
               "psb_scalar_stage_fused_plan: empty x range");
+  if (a->tail != nullptr && a->tail->mode != 0) {
+    int64_t nblocks = 0;
+    const int rc0 = a->dtype == PSB_F64 ? fused_dispatch_f64(a, nullptr, &nblocks)
+                                        : fused_dispatch_f32(a, nullptr, &nblocks);
+    if (rc0) return rc0;
+    if (int rc = validate_tail(a->tail, nblocks, a->energy_partials != nullptr,
+                               "psb_scalar_stage_fused_plan"))
+      return rc;
+  }
   t_fused_plan = plan;
   const int rc = a->dtype == PSB_F64 ? fused_dispatch_f64(a, nullptr, nullptr)
                                      : fused_dispatch_f32(a, nullptr, nullptr);

@@ -26,6 +26,7 @@
 #endif
 
 #include "common.cuh"
+#include "stage_tail.cuh"
 
 namespace psb {
 
@@ -56,7 +57,39 @@ template <typename T, int NF> struct FusedParams {
   int nvterms;
   T vcoef[PSB_MAX_TERMS];
   int8_t vpower[PSB_MAX_TERMS][NF];
+  int st_flags;        // bit0: streaming stores for f_out, bit1: plain stores for pointwise
+  TailParams tail;     // in-kernel stage tail (stage_tail.cuh); mode 0 = none
 };
+
+// sum_t coef[t] * prod_m f_m^power[t][m] for the VEC sites of a thread at once: the loops
+// over terms and powers (run-time, uniform) are outermost, the sites innermost, so their
+// overhead is paid once per thread and not once per site.  Per site the association is
+// term = ((coef * f) * f) ..., out = out + term in term order -- identical to the oracle's.
+template <typename T, int NF, int VEC>
+__device__ __forceinline__ Vec<T, VEC> poly_eval(int nterms, const T* coef,
+                                                 const int8_t (*power)[NF],
+                                                 const Vec<T, VEC>* fc) {
+  Vec<T, VEC> out;
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) out.v[v] = (T)0;
+  for (int t = 0; t < nterms; ++t) {
+    Vec<T, VEC> term;
+    const T c = coef[t];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) term.v[v] = c;
+#pragma unroll
+    for (int m = 0; m < NF; ++m) {
+      const int pw = power[t][m];
+      for (int e = 0; e < pw; ++e) {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) term.v[v] = term.v[v] * fc[m].v[v];
+      }
+    }
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) out.v[v] = out.v[v] + term.v[v];
+  }
+  return out;
+}
 
 template <typename T, int VEC>
 __device__ __forceinline__ Vec<T, VEC> ld_stream(const T* p) {
@@ -285,46 +318,40 @@ __global__ void __launch_bounds__(BY* TZ, MINB)
         }
       }
 
+      V fc[NF];
+#pragma unroll
+      for (int f = 0; f < NF; ++f) fc[f] = q[f][H];
+
       if constexpr (ENERGY) {
+        // per-plane partial sums in T over the thread's VEC sites, one double add each
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) {
+        for (int f = 0; f < NF; ++f) {
+          T sk = (T)0, sg = (T)0;
 #pragma unroll
-          for (int f = 0; f < NF; ++f) {
+          for (int v = 0; v < VEC; ++v) {
             const T dv = cur_d[f].v[v];
-            e_kin[f] += (double)(dv * dv);
-            e_grad[f] += (double)(-(q[f][H].v[v] * lap[f].v[v]));
+            sk = sk + dv * dv;
+            sg = sg + (-(fc[f].v[v] * lap[f].v[v]));
           }
-          T Vv = (T)0;
-          for (int t = 0; t < p.nvterms; ++t) {
-            T term = p.vcoef[t];
-#pragma unroll
-            for (int m = 0; m < NF; ++m) {
-              const T fm = q[m][H].v[v];
-              for (int e = 0; e < p.vpower[t][m]; ++e) term = term * fm;
-            }
-            Vv = Vv + term;
-          }
-          e_pot += (double)Vv;
+          e_kin[f] += (double)sk;
+          e_grad[f] += (double)sg;
         }
+        const V Vv = poly_eval<T, NF, VEC>(p.nvterms, p.vcoef, p.vpower, fc);
+        T sp = (T)0;
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) sp = sp + Vv.v[v];
+        e_pot += (double)sp;
       }
 
       const int64_t off = site0 + (int64_t)i * plane_stride;
 #pragma unroll
       for (int f = 0; f < NF; ++f) {
         V fo, dn, kfn, kdn;
+        // dV/df_f = sum_t coef * prod_m f_m^power
+        const V dVv = poly_eval<T, NF, VEC>(p.nterms[f], p.coef[f], p.power[f], fc);
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
-          // dV/df_f = sum_t coef * prod_m f_m^power
-          T dV = (T)0;
-          for (int t = 0; t < p.nterms[f]; ++t) {
-            T term = p.coef[f][t];
-#pragma unroll
-            for (int m = 0; m < NF; ++m) {
-              const T fm = q[m][H].v[v];
-              for (int e = 0; e < p.power[f][t][m]; ++e) term = term * fm;
-            }
-            dV = dV + term;
-          }
+          const T dV = dVv.v[v];
           const T d_old = cur_d[f].v[v];
           const T rhs_f = d_old;
           const T rhs_d = (lap[f].v[v] - two_h * d_old) - a_sq * dV;
@@ -427,6 +454,13 @@ __global__ void __launch_bounds__(BY* TZ, MINB)
       p.energy_partials[(p.energy_slot_offset + blk) * PSB_ENERGY_STRIDE + tid] = x;
     }
   }
+  if (p.tail.mode != 0) {
+    const int64_t blk = ((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    const int64_t nblk = (int64_t)gridDim.x * gridDim.y * gridDim.z;
+    const bool peer_store = (p.peer_lo != nullptr && xs < H) ||
+                            (p.peer_hi != nullptr && xe > p.Nx - H);
+    stage_tail<0, C::THREADS>(p.tail, blk, nblk, tid, peer_store);
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -504,7 +538,10 @@ static void fill_params(FusedParams<T, NF>& p, const psb_scalar_stage_args* a) {
     p.vcoef[t] = (T)a->vcoef[t];
     for (int m = 0; m < NF; ++m) p.vpower[t][m] = a->vpower[t][m];
   }
-
+  p.st_flags = a->store_flags;
+  fill_tail(p.tail, a->tail,
+            a->energy_partials ? a->energy_partials + a->energy_slot_offset * PSB_ENERGY_STRIDE
+                               : nullptr);
 }
 
 template <typename T, int H, int NF, int VEC, int BY, int TZ, int P, int MINB>

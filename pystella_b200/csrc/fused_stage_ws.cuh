@@ -365,42 +365,58 @@ __global__ void __launch_bounds__(BY* TZ + 32, MINB)
           }
         }
 
+        V fc[NF];
+#pragma unroll
+        for (int f = 0; f < NF; ++f) fc[f] = q[f][H];
+
         if constexpr (ENERGY) {
+          // per-plane partial sums in T over the thread's VEC sites, one double add each
+#pragma unroll
+          for (int f = 0; f < NF; ++f) {
+            T sk = (T)0, sg = (T)0;
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+              if constexpr (AL) {
+                if (!ok[v]) continue;
+              }
+              const T dv = dold[f].v[v];
+              sk = sk + dv * dv;
+              sg = sg + (-(fc[f].v[v] * lap[f].v[v]));
+            }
+            e_kin[f] += (double)sk;
+            e_grad[f] += (double)sg;
+          }
+          T sp = (T)0;
+#ifdef PSB_GENERATED_RHS
 #pragma unroll
           for (int v = 0; v < VEC; ++v) {
             if constexpr (AL) {
               if (!ok[v]) continue;
             }
-#pragma unroll
-            for (int f = 0; f < NF; ++f) {
-              const T dv = dold[f].v[v];
-              e_kin[f] += (double)(dv * dv);
-              e_grad[f] += (double)(-(q[f][H].v[v] * lap[f].v[v]));
-            }
-#ifdef PSB_GENERATED_RHS
             T fsite[NF];
 #pragma unroll
-            for (int m = 0; m < NF; ++m) fsite[m] = q[m][H].v[v];
-            const T Vv = psb_generated_potential<T>(fsite, a, hubble, jit_scalars.v);
-#else
-            T Vv = (T)0;
-            for (int t = 0; t < p.nvterms; ++t) {
-              T term = p.vcoef[t];
-#pragma unroll
-              for (int m = 0; m < NF; ++m) {
-                const T fm = q[m][H].v[v];
-                for (int e = 0; e < p.vpower[t][m]; ++e) term = term * fm;
-              }
-              Vv = Vv + term;
-            }
-#endif
-            e_pot += (double)Vv;
+            for (int m = 0; m < NF; ++m) fsite[m] = fc[m].v[v];
+            sp = sp + psb_generated_potential<T>(fsite, a, hubble, jit_scalars.v);
           }
+#else
+          const V Vv = poly_eval<T, NF, VEC>(p.nvterms, p.vcoef, p.vpower, fc);
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) {
+            if constexpr (AL) {
+              if (!ok[v]) continue;
+            }
+            sp = sp + Vv.v[v];
+          }
+#endif
+          e_pot += (double)sp;
         }
 
 #pragma unroll
         for (int f = 0; f < NF; ++f) {
           V fo, dn, kfn, kdn;
+#ifndef PSB_GENERATED_RHS
+          const V dVv = poly_eval<T, NF, VEC>(p.nterms[f], p.coef[f], p.power[f], fc);
+#endif
 #pragma unroll
           for (int v = 0; v < VEC; ++v) {
 #ifdef PSB_GENERATED_RHS
@@ -424,16 +440,7 @@ __global__ void __launch_bounds__(BY* TZ + 32, MINB)
               kdv = p.dt * rhs_d;
             }
 #else
-            T dV = (T)0;
-            for (int t = 0; t < p.nterms[f]; ++t) {
-              T term = p.coef[f][t];
-#pragma unroll
-              for (int m = 0; m < NF; ++m) {
-                const T fm = q[m][H].v[v];
-                for (int e = 0; e < p.power[f][t][m]; ++e) term = term * fm;
-              }
-              dV = dV + term;
-            }
+            const T dV = dVv.v[v];
             const T d_old = dold[f].v[v];
             const T rhs_d = (lap[f].v[v] - two_h * d_old) - a_sq * dV;
             T kfv, kdv;
@@ -451,11 +458,20 @@ __global__ void __launch_bounds__(BY* TZ + 32, MINB)
             dn.v[v] = d_old + p.B * kdv;
           }
           const int64_t fo_off = f * p.field_stride;
-          put(o_kf + fo_off, kfn, TagStream{});
-          put(o_kd + fo_off, kdn, TagStream{});
-          put(o_d + fo_off, dn, TagStream{});
+          if (p.st_flags & 2) {
+            put(o_kf + fo_off, kfn, TagPlain{});
+            put(o_kd + fo_off, kdn, TagPlain{});
+            put(o_d + fo_off, dn, TagPlain{});
+          } else {
+            put(o_kf + fo_off, kfn, TagStream{});
+            put(o_kd + fo_off, kdn, TagStream{});
+            put(o_d + fo_off, dn, TagStream{});
+          }
           T* fout = o_f + fo_off;
-          put(fout, fo, TagPlain{});
+          if (p.st_flags & 1)
+            put(fout, fo, TagStream{});
+          else
+            put(fout, fo, TagPlain{});
           if (p.wrap_x) {
             if (i < H) put(fout + (int64_t)p.Nx * plane_stride, fo, TagPlain{});
             if (i >= p.Nx - H) put(fout - (int64_t)p.Nx * plane_stride, fo, TagPlain{});
@@ -529,6 +545,14 @@ __global__ void __launch_bounds__(BY* TZ + 32, MINB)
                           blockIdx.x;
       p.energy_partials[(p.energy_slot_offset + blk) * PSB_ENERGY_STRIDE + tid] = x;
     }
+  }
+  if (p.tail.mode != 0) {
+    // consumer warps only (the producer warp has exited): named barrier 1
+    const int64_t blk = ((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    const int64_t nblk = (int64_t)gridDim.x * gridDim.y * gridDim.z;
+    const bool peer_store = (p.peer_lo != nullptr && xs < H) ||
+                            (p.peer_hi != nullptr && xe > p.Nx - H);
+    stage_tail<1, BY * TZ>(p.tail, blk, nblk, tid, peer_store);
   }
 }
 

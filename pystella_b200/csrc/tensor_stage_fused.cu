@@ -1,7 +1,3 @@
-// EXPERIMENTAL (opt-in, PSB_FUSED_GW=1): parity-green against the oracle on B200
-// (tests/test_gpu_api.py::test_fused_gw_sector_experimental) but not yet timed or
-// profiled -- the default tensor-sector path is the element-wise tensor_stage.cu.
-//
 // Fused stage of the tensor-perturbation sector in the warp-specialised TMA pipeline
 // of fused_stage_ws.cuh: lap(hij_c) and the gradient of the source fields are
 // evaluated in-kernel, so lap_hij / dfdx never touch HBM
@@ -36,6 +32,11 @@ template <typename T> struct TensorFusedParams {
   T inv_dx[3];
   T dt, A, B, hubble, coef;
   const double* hubble_dev;
+  T* peer_lo;   // peer-mapped hij_out of rank rx-1 / rx+1 (component 0) or null
+  T* peer_hi;
+  int peer_lo_Nx;
+  int64_t peer_lo_stride, peer_hi_stride;
+  TailParams tail;
 };
 
 template <typename T, int H, int NS, int BY, int TZ, int P, int VEC_> struct TwsCfg {
@@ -317,6 +318,18 @@ __global__ void __launch_bounds__(BY* TZ + 32, MINB)
           if (i >= p.Nx - H)
             st_pieces<T, VEC, GV, false>(o_h - (int64_t)p.Nx * plane_stride, ho);
         }
+        // NVLink: my boundary planes -> the neighbours' x halos (peer memory)
+        if (p.peer_lo != nullptr && i < H)
+          st_pieces<T, VEC, GV, false>(
+              p.peer_lo + comp * p.peer_lo_stride +
+                  (int64_t)(p.peer_lo_Nx + H + i) * plane_stride + (int64_t)(j + H) * Pz +
+                  (k + H),
+              ho);
+        if (p.peer_hi != nullptr && i >= p.Nx - H)
+          st_pieces<T, VEC, GV, false>(
+              p.peer_hi + comp * p.peer_hi_stride + (int64_t)(i - p.Nx + H) * plane_stride +
+                  (int64_t)(j + H) * Pz + (k + H),
+              ho);
         if (p.wrap_y) {
           if (j < H) st_pieces<T, VEC, GV, false>(o_h + (int64_t)p.Ny * Pz, ho);
           if (j >= p.Ny - H) st_pieces<T, VEC, GV, false>(o_h - (int64_t)p.Ny * Pz, ho);
@@ -340,6 +353,13 @@ __global__ void __launch_bounds__(BY* TZ + 32, MINB)
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty_f[(n - H) % RF]);
     }
+  }
+  if (p.tail.mode != 0) {
+    const int64_t blk = ((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    const int64_t nblk = (int64_t)gridDim.x * gridDim.y * gridDim.z;
+    const bool peer_store = (p.peer_lo != nullptr && xs < H) ||
+                            (p.peer_hi != nullptr && xe > p.Nx - H);
+    stage_tail<1, BY * TZ>(p.tail, blk, nblk, tid, peer_store);
   }
 }
 
@@ -398,7 +418,7 @@ static int launch_tensor_ws(const psb_tensor_fused_args* a, cudaStream_t stream)
   p.x_begin = 0;
   p.x_end = (int)a->Nx;
   p.x2_begin = p.x2_end = 0;
-  int xchunk = WS_DEFAULT_XCHUNK;
+  int xchunk = a->tune_xchunk > 0 ? a->tune_xchunk : WS_DEFAULT_XCHUNK;
   if (xchunk > a->Nx) xchunk = (int)a->Nx;
   p.xchunk = xchunk;
   p.nchunks1 = (int)((a->Nx + xchunk - 1) / xchunk);
@@ -415,8 +435,17 @@ static int launch_tensor_ws(const psb_tensor_fused_args* a, cudaStream_t stream)
   p.hubble = (T)a->hubble;
   p.coef = (T)a->source_coef;
   p.hubble_dev = a->hubble_dev;
+  p.peer_lo = static_cast<T*>(a->peer_lo_hij_out);
+  p.peer_hi = static_cast<T*>(a->peer_hi_hij_out);
+  p.peer_lo_Nx = (int)a->peer_lo_Nx;
+  p.peer_lo_stride = a->peer_lo_stride;
+  p.peer_hi_stride = a->peer_hi_stride;
   dim3 grid((unsigned)(6 * ((a->Nz + B::BZ - 1) / B::BZ)), (unsigned)((a->Ny + BY - 1) / BY),
             (unsigned)p.nchunks1);
+  if (int rc = validate_tail(a->tail, (int64_t)grid.x * grid.y * grid.z, false,
+                             "psb_tensor_stage_fused"))
+    return rc;
+  fill_tail(p.tail, a->tail, nullptr);
   dim3 block(C::THREADS, 1, 1);
   auto kern = tensor_stage_ws_kernel<T, H, NS, BY, TZ, P, 1, VEC>;
   PSB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -428,7 +457,16 @@ static int launch_tensor_ws(const psb_tensor_fused_args* a, cudaStream_t stream)
 
 template <typename T, int H>
 static int tensor_fused_ns(const psb_tensor_fused_args* a, cudaStream_t s) {
-  constexpr int VEC = 2;   // 16-byte (fp64) / 8-byte (fp32) vectors; fp32 x4: later
+  // 16-byte shared-memory vectors: 2 doubles, or 4 floats when the rows allow it
+  if constexpr (sizeof(T) == 4) {
+    if (a->Nz % 4 == 0 && a->tune_variant != 1) {
+      switch (a->nscalars) {
+        case 1: return launch_tensor_ws<T, H, 1, 4>(a, s);
+        case 2: return launch_tensor_ws<T, H, 2, 4>(a, s);
+      }
+    }
+  }
+  constexpr int VEC = 2;
   switch (a->nscalars) {
     case 1: return launch_tensor_ws<T, H, 1, VEC>(a, s);
     case 2: return launch_tensor_ws<T, H, 2, VEC>(a, s);
@@ -450,6 +488,8 @@ extern "C" int psb_tensor_stage_fused(const psb_tensor_fused_args* a, void* stre
               "psb_tensor_stage_fused: h=%d (even halos only; use the element-wise stage)",
               a->h);
   PSB_REQUIRE(a->Nz % 2 == 0, "psb_tensor_stage_fused: odd Nz (use the element-wise stage)");
+  PSB_REQUIRE(!(a->wrap_x && (a->peer_lo_hij_out || a->peer_hi_hij_out)),
+              "psb_tensor_stage_fused: wrap_x and peer halos are mutually exclusive");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (a->dtype == PSB_F64)
     return a->h == 2 ? tensor_fused_ns<double, 2>(a, s) : tensor_fused_ns<double, 4>(a, s);

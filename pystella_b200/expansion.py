@@ -113,27 +113,61 @@ class DeviceExpansion:
         self.sums = self._sums_buf[:16]
         self.energies = torch.zeros(2 * nscalars + 3, dtype=torch.float64, device=dev)
 
+    def attach(self, stepper):
+        """Advance this background inside ``stepper``'s stage kernels (their last CTA folds
+        the energy sums, runs the inter-GPU exchange and the stage of ``(a, adot)``):
+        nothing is launched between two stages.  :meth:`step` does this on its first call."""
+        stepper.attach_expansion(self)
+        return self
+
+    def detach(self, stepper):
+        if getattr(stepper, "_expansion", None) is self:
+            stepper._expansion = None
+        self._auto_attach = False
+
     def step(self, stage, stepper, dt, queue=None):
-        """Fold the stepper's energy partials and advance one stage (no host sync)."""
+        """Advance one stage with the energy sums of the stepper's last stage (no host
+        sync).  When the stage kernel has already done it in its tail (see :meth:`attach`)
+        this returns immediately."""
         from pystella_b200 import _kernels
+        if getattr(stepper, "_expansion", None) is self \
+                and getattr(stepper, "_expanded_stage", None) == stage:
+            stepper._expanded_stage = None
+            sdt = stepper.dt
+            if sdt is not None and abs(float(np.asarray(sdt).reshape(-1)[0]) - float(dt)) \
+                    > 1e-14 * abs(float(dt)):
+                raise ValueError("DeviceExpansion.step: dt differs from the stepper's dt, "
+                                 "which the in-kernel background stage has already used")
+            return
         if stepper.energy_partials is None or stepper.energy_nslots == 0:
             raise ValueError("the stepper has produced no energy sums: construct it with "
                              "MapKernel=FusedStencilStage, energy=True and call it first")
         nvals = stepper.energy_nvals
-        _kernels.energy_sums(stepper.energy_partials, stepper.energy_nslots, nvals,
-                             self._sums_buf, queue, self.strict_fp)
+        if getattr(stepper, "_sums_folded", False):
+            sums = stepper.energy_sums          # folded by the stage kernel's last CTA
+        else:
+            _kernels.energy_sums(stepper.energy_partials, stepper.energy_nslots, nvals,
+                                 self._sums_buf, queue, self.strict_fp)
+            sums = self.sums
+        if getattr(self, "_auto_attach", True) and getattr(stepper, "fused", False) \
+                and getattr(stepper, "_expansion", None) is None \
+                and getattr(stepper, "_halo_mode", "local") in ("local", "peer"):
+            stepper.attach_expansion(self)      # from the next stage on: in-kernel
         pg = getattr(stepper, "_peer", None)
         if pg is not None and getattr(stepper, "_halo_mode", None) == "peer":
             # all-gather over peer memory + inter-GPU barrier + expansion, one kernel
-            _kernels.expansion_stage_peer(pg.args, self.sums, self.nscalars, self.grid_size,
+            _kernels.expansion_stage_peer(pg.args, sums, self.nscalars, self.grid_size,
                                           self.mpl, dt, self._A[stage], self._B[stage],
                                           self.state, self.energies, queue, self.strict_fp)
             stepper._peer_barrier_pending = False
             return
         if self.decomp is not None and self.decomp.nranks > 1:
             import torch.distributed as dist
-            dist.all_reduce(self.sums, group=self.decomp.comm)
-        _kernels.expansion_stage(self.sums, self.nscalars, self.grid_size, self.mpl, dt,
+            if sums is not self.sums:
+                self.sums.copy_(sums)
+                sums = self.sums
+            dist.all_reduce(sums, group=self.decomp.comm)
+        _kernels.expansion_stage(sums, self.nscalars, self.grid_size, self.mpl, dt,
                                  self._A[stage], self._B[stage], self.state, self.energies,
                                  queue, self.strict_fp)
 

@@ -37,6 +37,34 @@ def _swap_storage(a, b):
     a.data, b.data = b_data, a_data
 
 
+def halos_are_fresh(stepper, key, f):
+    """Were the halos of ``f`` last written by this stepper's own stage kernel?  Tracked per
+    system: the tensor object, its storage and its version counter must all be the ones the
+    stepper left behind (a different tensor, a re-uploaded field or an in-place edit between
+    steps -- rescaling, checkpoint load -- all get a fresh ``share_halos``, as the reference
+    does on every derivative call, ``pystella/derivs.py:412``)."""
+    rec = stepper.__dict__.setdefault("_fresh", {}).get(key)
+    return (rec is not None and not stepper.__dict__.get("_force_refresh", False)
+            and rec[0]() is f and rec[1] == f.data_ptr() and rec[2] == f._version)
+
+
+def mark_halos_fresh(stepper, key, f):
+    import weakref
+    stepper.__dict__.setdefault("_fresh", {})[key] = (weakref.ref(f), f.data_ptr(),
+                                                      f._version)
+
+
+def fill_halos(stepper, f, h, queue):
+    """share_halos of every field of padded ``f`` (rank-local wrap or exchange)."""
+    decomp = stepper.decomp
+    views = [f[n] for n in range(f.shape[0])] if f.dim() == 4 else [f]
+    for v in views:
+        if decomp is not None:
+            decomp.share_halos(queue, v)
+        else:
+            _kernels.halo_wrap(v, (h, h, h), 7, queue)
+
+
 TIMELINE = os.environ.get("PSB_TIMELINE", "0") == "1"
 _timeline = []   # (label, event) tuples appended in issue order when PSB_TIMELINE=1
 
@@ -148,6 +176,7 @@ def _setup_peer_buffers(stepper, key, f, h):
     B.copy_(f)
     f.data = A
     stepper._twins[key] = B
+    stepper.__dict__.setdefault("_fresh", {}).pop(key, None)
     shapes = pg.gather_shapes(f.shape)
     lo = decomp.rankID(decomp.rx - 1, decomp.ry, decomp.rz)
     hi = decomp.rankID(decomp.rx + 1, decomp.ry, decomp.rz)
@@ -156,7 +185,6 @@ def _setup_peer_buffers(stepper, key, f, h):
         ids={A.data_ptr(): 0, B.data_ptr(): 1}, bufs=(A.view(A.shape), B.view(B.shape)),
         ptrs=[ptrsA, ptrsB], lo=lo, hi=hi,
         lo_Nx=shapes[lo][-3] - 2 * h, lo_stride=vol[lo], hi_stride=vol[hi])
-    stepper._halos_fresh = False
 
 
 def _adopt_into_peer_buffers(stepper, key, f):
@@ -170,7 +198,7 @@ def _adopt_into_peer_buffers(stepper, key, f):
     A.copy_(f)
     f.data = A
     stepper._twins[key] = B.view(B.shape)   # a fresh object: .data swaps must not
-    stepper._halos_fresh = False             # touch the stable views in ps["bufs"]
+    stepper.__dict__.setdefault("_fresh", {}).pop(key, None)   # touch the views in ps["bufs"]
 
 
 def fused_scalar_stage(stepper, system, f, common, queue):
@@ -199,25 +227,23 @@ def fused_scalar_stage(stepper, system, f, common, queue):
         # defined values once
         twin.copy_(f)
         stepper._twins[key] = twin
-        stepper._halos_fresh = False
+        stepper.__dict__.setdefault("_fresh", {}).pop(key, None)
 
-    if not stepper._halos_fresh:
-        # halos of the user's array are of unknown age: fill them once
-        views = [f[n] for n in range(f.shape[0])] if f.dim() == 4 else [f]
-        if decomp is not None:
-            for v in views:
-                decomp.share_halos(queue, v)
-        else:
-            for v in views:
-                _kernels.halo_wrap(v, (h, h, h), 7, queue)
-        stepper._halos_fresh = True
+    if not halos_are_fresh(stepper, key, f):
+        # halos of the user's array are of unknown age: fill them
+        if mode == "peer" and stepper._peer_barrier_pending:
+            stepper._peer.barrier_kernel(queue, stepper.strict_fp)
+            stepper._peer_barrier_pending = False
+        fill_halos(stepper, f, h, queue)
 
     Nx = f.shape[-3] - 2 * h
     args = dict(common)
     args.update(fused=True, f_in=f, f_out=twin, dx=stepper.dx)
     tune = stepper.tune or {}
-    args.update(xchunk=tune.get("xchunk", 0), variant=tune.get("variant", 0))
+    args.update(xchunk=tune.get("xchunk", 0), variant=tune.get("variant", 0),
+                store_flags=tune.get("store_flags", 0))
 
+    nslots = 0
     if stepper.fused_energy:
         if stepper._V_values is None:
             raise NotImplementedError(
@@ -228,7 +254,8 @@ def fused_scalar_stage(stepper, system, f, common, queue):
         lkey = (tuple(f.shape), f.dtype, multi, mode, args["xchunk"], args["variant"])
         cache = stepper.__dict__.setdefault("_energy_layout", {})
         if lkey not in cache:
-            cache[lkey] = [_kernels.scalar_stage(x_range=r, count_slots_only=True, **args)
+            probe = {k: v for k, v in args.items() if k != "generated"}
+            cache[lkey] = [_kernels.scalar_stage(x_range=r, count_slots_only=True, **probe)
                            for r in ranges]
         counts = cache[lkey]
         total = sum(counts)
@@ -241,21 +268,33 @@ def fused_scalar_stage(stepper, system, f, common, queue):
         offsets = [sum(counts[:i]) for i in range(len(counts))]
         energy_kw = [dict(energy_partials=stepper.energy_partials, energy_slot_offset=o)
                      for o in offsets]
+        nslots = total
     else:
         energy_kw = [{}, {}]
+    stepper._sums_folded = False
 
     if not multi:
-        _kernels.scalar_stage(wrap=(True, True, True), **args, **energy_kw[0])
+        # one launch; its last CTA folds the energy sums and, with an attached
+        # DeviceExpansion, advances the background: no other kernel in the stage
+        tail = stepper._make_tail(fold=stepper.fused_energy, dt=common["dt"], nslots=nslots,
+                                  device=f.device)
+        _kernels.scalar_stage(wrap=(True, True, True), tail=tail, **args, **energy_kw[0])
+        stepper._tail_issued(tail)
     elif mode == "peer":
         ps = stepper._peer_state[key]
         if stepper._peer_barrier_pending:
-            # nobody folded the previous stage's barrier into an expansion step
+            # the previous stage's last kernel did not carry the barrier
             stepper._peer.barrier_kernel(queue, stepper.strict_fp)
+            stepper._peer_barrier_pending = False
         out_id = ps["ids"][twin.data_ptr()]
         peer = dict(lo=ps["ptrs"][out_id][ps["lo"]], hi=ps["ptrs"][out_id][ps["hi"]],
                     lo_Nx=ps["lo_Nx"], lo_stride=ps["lo_stride"], hi_stride=ps["hi_stride"])
-        _kernels.scalar_stage(wrap=(False, True, True), peer=peer, **args, **energy_kw[0])
         stepper._peer_barrier_pending = True
+        tail = stepper._make_tail(fold=stepper.fused_energy, dt=common["dt"], nslots=nslots,
+                                  device=f.device)
+        _kernels.scalar_stage(wrap=(False, True, True), peer=peer, tail=tail, **args,
+                              **energy_kw[0])
+        stepper._tail_issued(tail)
     else:
         st = _ensure_streams(stepper)
         cur = queue if queue is not None else torch.cuda.current_stream()
@@ -283,3 +322,5 @@ def fused_scalar_stage(stepper, system, f, common, queue):
         _mark("joined", cur)
 
     _swap_storage(f, twin)
+    mark_halos_fresh(stepper, key, f)
+    stepper.__dict__.setdefault("_stage_serial", {})[key] = stepper.__dict__.get("_call_serial")

@@ -499,7 +499,7 @@ class LowStorageRKStepper(Stepper):
         super().__init__(*args, **kwargs)
         self.tmp_arrays = {}
         self._twins = {}        # fused: second padded buffer per stencilled unknown
-        self._halos_fresh = False
+        self._fresh = {}        # fused: per system, whose halos the stage kernel last wrote
         self._streams = None
 
     def get_tmp_arrays_like(self, **kwargs):
@@ -518,8 +518,10 @@ class LowStorageRKStepper(Stepper):
         return tmp_arrays
 
     def reset(self):
-        """Forget halo freshness (call after writing to ``f`` outside the stepper)."""
-        self._halos_fresh = False
+        """Forget halo freshness.  Not needed after in-place edits or when passing a new
+        tensor (both are detected, see :func:`pystella_b200.fused.halos_are_fresh`); kept for
+        writes through raw pointers the stepper cannot see."""
+        self._fresh = {}
 
     def __call__(self, stage, *, queue=None, **kwargs):
         if not 0 <= stage < self.num_stages:
@@ -598,13 +600,81 @@ class LowStorageRKStepper(Stepper):
             return self._jit_stage(stage, queue, kwargs)
         dt = self._resolve_dt(kwargs)
         A, B = self._A[stage], self._B[stage]
-        for system in systems:
+        self._stage_index = stage
+        self._call_serial = self.__dict__.get("_call_serial", 0) + 1
+        for n, system in enumerate(systems):
+            # the last kernel of the stage carries the in-kernel tail (inter-GPU barrier,
+            # background stage): pystella_b200/csrc/stage_tail.cuh
+            self._last_of_stage = (n == len(systems) - 1)
             system_stage = getattr(system, "run_stage", None)
             if system_stage is not None:       # tensor sector etc.
                 system_stage(self, stage, queue, kwargs, dt, A, B)
             else:
                 self._scalar_stage(system, stage, queue, kwargs, dt, A, B)
         return None
+
+    # -- in-kernel stage tail ---------------------------------------------------
+    def attach_expansion(self, expand):
+        """Let the last kernel of every stage advance ``expand`` (a
+        :class:`~pystella_b200.DeviceExpansion`) in its last CTA: no launch between stages.
+        ``expand.step(stage, stepper, dt)`` then returns immediately."""
+        self._expansion = expand
+
+    def _make_tail(self, *, fold, dt, nslots=0, device=None):
+        """psb_stage_tail of the launch being issued (None when there is nothing to do)."""
+        from pystella_b200 import _lib
+        mode = 0
+        if fold:
+            mode |= _lib.TAIL_FOLD
+        peer_mode = getattr(self, "_halo_mode", None) == "peer"
+        expand = getattr(self, "_expansion", None)
+        last = getattr(self, "_last_of_stage", True)
+        if last and peer_mode:
+            mode |= _lib.TAIL_PEER
+        if last and expand is not None and self.fused_energy:
+            mode |= _lib.TAIL_EXPAND
+        if mode == 0:
+            return None
+        ws = getattr(self, "_tail_ws", None)
+        need = max(1, (int(nslots) + _lib.TAIL_GROUP - 1) // _lib.TAIL_GROUP)
+        if ws is None or self._tail_groups < need:
+            if ws is not None:
+                torch.cuda.current_stream().synchronize()
+            ws, groups = _kernels.stage_tail_workspace(max(nslots, 1), device, self.strict_fp)
+            self._tail_ws, self._tail_groups = ws, groups
+            #: folded energy sums {sum dfdt_n^2.., sum V, sum -f_n lap f_n..} of the state
+            #: that entered the last stage (device, float64[16])
+            self.energy_sums = ws[:16]
+        tail = _lib.StageTail()
+        tail.mode = mode
+        tail.workspace = self._tail_ws.data_ptr()
+        tail.workspace_groups = self._tail_groups
+        if self.fused_energy:
+            tail.nscalars = self.energy_nvals // 2 if getattr(self, "energy_nvals", 0) else 0
+        if mode & _lib.TAIL_EXPAND:
+            stage = self._stage_index
+            tail.nscalars = expand.nscalars
+            tail.grid_size, tail.mpl, tail.dt = expand.grid_size, expand.mpl, float(dt)
+            tail.A, tail.B = expand._A[stage], expand._B[stage]
+            tail.state = expand.state.data_ptr()
+            tail.energies = expand.energies.data_ptr()
+        if mode & _lib.TAIL_PEER:
+            pa = self._peer.args
+            tail.peers.nranks, tail.peers.rank = pa.nranks, pa.rank
+            tail.peers.peer_slots, tail.peers.peer_flags = pa.peer_slots, pa.peer_flags
+            tail.peers.epoch = pa.epoch
+        return tail
+
+    def _tail_issued(self, tail):
+        """Book-keeping after a launch that carried ``tail``."""
+        from pystella_b200 import _lib
+        mode = tail.mode if tail is not None else 0
+        if mode & _lib.TAIL_FOLD:
+            self._sums_folded = True
+        if mode & _lib.TAIL_PEER:
+            self._peer_barrier_pending = False
+        if mode & _lib.TAIL_EXPAND:
+            self._expanded_stage = self._stage_index
 
     def _scalars(self, system, kwargs):
         out = {}
@@ -619,7 +689,12 @@ class LowStorageRKStepper(Stepper):
                 continue
             ctx = {n: _scalar_value(kwargs[n]) for n in system.scalar_names()
                    if n in kwargs and not isinstance(kwargs[n], torch.Tensor)}
-            val = expr if is_constant(expr) else evaluate(expr, ctx)
+            try:
+                val = expr if is_constant(expr) else evaluate(expr, ctx)
+            except KeyError as exc:
+                # the reference's kernel fails on a missing argument as well
+                raise TypeError(f"missing scalar argument of the stage kernel: {exc}") \
+                    from None
             out[which] = (float(val), None)
         ctx = {n: _scalar_value(kwargs[n]) for n in system.scalar_names()
                if n in kwargs and not isinstance(kwargs[n], torch.Tensor)}

@@ -29,7 +29,7 @@ def test_library_exports_header_symbols(strict):
 
 def test_loader_and_error_channel():
     lib = _lib.load()
-    assert lib.psb_abi_version() == 1
+    assert lib.psb_abi_version() == 2
     assert lib.psb_strict_fp() == 0
     assert _lib.load(strict=True).psb_strict_fp() == 1
     # argument validation happens before any CUDA call: safe without a GPU
@@ -54,13 +54,17 @@ def test_struct_layout_matches_header():
            'printf("%zu %zu %zu\\n", sizeof(psb_fused_plan), '
            '__builtin_offsetof(psb_fused_plan, tensor_maps), '
            '__builtin_offsetof(psb_fused_plan, params));'
+           'printf("%zu %zu %zu\\n", sizeof(psb_stage_tail), '
+           '__builtin_offsetof(psb_scalar_stage_args, tail), '
+           '__builtin_offsetof(psb_tensor_fused_args, tail));'
            'return 0;}')
     with tempfile.TemporaryDirectory() as d:
         c = os.path.join(d, "p.c")
         open(c, "w").write(src)
         exe = os.path.join(d, "p")
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
-        a, b, c, d, e, f, g, off_maps, off_params = subprocess.check_output([exe]).split()
+        (a, b, c, d, e, f, g, off_maps, off_params, tail_size, off_tail,
+         off_ttail) = subprocess.check_output([exe]).split()
     assert int(a) == ctypes.sizeof(_lib.ScalarStageArgs)
     assert int(b) == ctypes.sizeof(_lib.ReduceArgs)
     assert int(c) == ctypes.sizeof(_lib.TensorStageArgs)
@@ -70,6 +74,9 @@ def test_struct_layout_matches_header():
     assert int(g) == ctypes.sizeof(_lib.FusedPlan)
     assert int(off_maps) == _lib.FusedPlan.tensor_maps.offset == 64
     assert int(off_params) == _lib.FusedPlan.params.offset == 576
+    assert int(tail_size) == ctypes.sizeof(_lib.StageTail)
+    assert int(off_tail) == _lib.ScalarStageArgs.tail.offset
+    assert int(off_ttail) == _lib.TensorFusedArgs.tail.offset
 
 
 def test_no_cpu_fallback():

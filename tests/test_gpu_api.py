@@ -563,11 +563,35 @@ def test_classical_rk_wave_equation_device(name):
 
 
 @pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-12), (np.float32, 3e-5)])
-def test_fused_gw_sector_experimental(dtype, tol, monkeypatch):
-    """Same check as test_two_scalars_plus_gw_sector with the opt-in fused tensor stage
-    (PSB_FUSED_GW=1): lap_hij / dfdx are never formed, the stencils run in-kernel."""
-    monkeypatch.setenv("PSB_FUSED_GW", "1")
+def test_unfused_gw_sector_with_fused_scalars(dtype, tol, monkeypatch):
+    """test_two_scalars_plus_gw_sector(fused_scalars=True) runs the fused tensor stage (the
+    default under FusedStencilStage: lap_hij / dfdx are never read); PSB_FUSED_GW=0 forces the
+    element-wise tensor stage fed by FiniteDifferencer next to the fused scalar stage."""
+    monkeypatch.setenv("PSB_FUSED_GW", "0")
     test_two_scalars_plus_gw_sector(True, dtype, tol)
+
+
+def test_fused_gw_sector_contract():
+    """Sector order and the hubble argument are checked: the fused tensor stage
+    reads the OLD scalar fields from the scalar stage of the same call."""
+    rng = np.random.default_rng(6)
+    N, h = (16, 12, 20), 2
+    pad = tuple(n + 2 * h for n in N)
+    dx = tuple(5 / n for n in N)
+    potential, _ = _example_potential(mphi=1.0, gsq=0.3)
+    scalar_sector = ps.ScalarSector(2, potential=potential)
+    gw_sector = ps.TensorPerturbationSector([scalar_sector])
+    arrays = dict(f=to_dev(rng.standard_normal((2,) + pad)),
+                  dfdt=to_dev(rng.standard_normal((2,) + pad)),
+                  hij=to_dev(rng.standard_normal((6,) + pad)),
+                  dhijdt=to_dev(rng.standard_normal((6,) + pad)))
+    kw = dict(halo_shape=h, dt=1e-3, dx=dx, MapKernel=ps.FusedStencilStage)
+    st = ps.LowStorageRK54([scalar_sector, gw_sector], **kw)
+    with pytest.raises(TypeError, match="hubble"):
+        st(0, a=np.array(1.0), **arrays)
+    st = ps.LowStorageRK54([gw_sector, scalar_sector], **kw)
+    with pytest.raises(ValueError, match="ScalarSector before"):
+        st(0, a=np.array(1.0), hubble=np.array(0.1), **arrays)
 
 
 @pytest.mark.parametrize("dtype,rtol", [(np.float64, 5e-14), (np.float32, 1e-5)])
