@@ -56,35 +56,40 @@ typedef struct psb_peer_args {
 } psb_peer_args;
 
 /* ------------------------------------------------------------------------
- * In-kernel stage tail (optional, fused stage kernels): the LAST CTA of the launch
- * (atomic tickets) performs what the reference does on the host between two stages --
+ * In-kernel stage tail (optional, fused stage kernels): CTA 0 of the launch (the "watcher")
+ * performs what the reference does on the host between two stages --
  * Reduction.__call__ -> get_rho_and_p -> Expansion.step (pystella/reduction.py:237-255,
  * pystella/sectors.py:211-229, pystella/expansion.py:140-157) and, multi-rank, the
- * allreduce of pystella/decomp.py:470-491 -- with no extra launch:
- *   PSB_TAIL_FOLD    fold this launch's energy partial rows into workspace[0..2ns]
- *                    (fixed order: groups of 64 CTAs, then the group rows);
- *   PSB_TAIL_PEER    all-gather of those sums over peer memory + inter-GPU flag barrier
+ * allreduce of pystella/decomp.py:470-491 -- with no extra launch and no fence or atomic in
+ * the other CTAs: every CTA publishes one row of PSB_ENERGY_STRIDE doubles when it is done
+ * (its energy partial sums -- the energy_partials rows of the launch -- or, for kernels
+ * without energy sums, a marker in `rows`); rows must hold the bit pattern
+ * PSB_TAIL_SENTINEL in every double before the launch (the watcher re-arms them), a value
+ * is valid when it differs from it.  The watcher adds the rows in a fixed order and then
+ *   PSB_TAIL_FOLD    writes the sums to sums[0..2ns];
+ *   PSB_TAIL_PEER    all-gathers sums[0..2ns] over peer memory + inter-GPU flag barrier
  *                    (exactly psb_expansion_stage_peer's protocol; with nscalars == 0 a
  *                    pure barrier that orders the peer halo stores of the kernel);
  *   PSB_TAIL_EXPAND  energies with the current scale factor and one low-storage stage of
  *                    (a, adot) as psb_expansion_stage.
- * workspace: psb_stage_tail_workspace_doubles(workspace_groups) doubles, zeroed once by
- * the caller; workspace_groups >= ceil(CTAs of the launch / 64).
+ * Without PSB_TAIL_FOLD, sums must have been folded by an earlier kernel of the stage.
  * ---------------------------------------------------------------------- */
 #define PSB_TAIL_FOLD 1
 #define PSB_TAIL_EXPAND 2
 #define PSB_TAIL_PEER 4
+#define PSB_TAIL_SENTINEL 0x7ff8dead0000beefULL
 typedef struct psb_stage_tail {
   int32_t mode;                  /* OR of PSB_TAIL_*; 0 = none                        */
   int32_t nscalars;              /* fields in the energy sums (0: no sums)            */
-  double* workspace;             /* sums[16] | group rows | tickets                   */
-  int64_t workspace_groups;
+  double* rows;                  /* marker rows, one per CTA (kernels without energy
+                                    partials); sentinel-initialised                   */
+  int64_t nrows;                 /* capacity of `rows` in rows                        */
+  double* sums;                  /* PSB_ENERGY_STRIDE doubles                         */
   double grid_size, mpl, dt, A, B;   /* EXPAND: background stage coefficients         */
   double* state;                 /* {a, adot, hubble, ka, kadot}                      */
   double* energies;              /* 2 nscalars + 3 doubles                            */
   psb_peer_args peers;           /* PEER                                              */
 } psb_stage_tail;
-int64_t psb_stage_tail_workspace_doubles(int64_t workspace_groups);
 
 /* ------------------------------------------------------------------------
  * Scalar-sector Runge-Kutta stage.
@@ -167,9 +172,6 @@ typedef struct psb_scalar_stage_args {
   int32_t tune_xchunk;           /* 0 = default; planes marched per CTA              */
   int32_t tune_variant;          /* 0 = auto; see DESIGN.md (kernel variants)        */
   const psb_stage_tail* tail;    /* fused only; HOST pointer, NULL = no in-kernel tail */
-  int32_t store_flags;           /* fused: bit0 = streaming (evict-first) stores for f_out,
-                                    bit1 = plain stores for dfdt/kf/kdfdt (tuning)     */
-  int32_t reserved0;
 } psb_scalar_stage_args;
 
 int psb_scalar_stage_fused(const psb_scalar_stage_args* args, void* stream);
@@ -263,6 +265,8 @@ typedef struct psb_tensor_fused_args {
   int32_t tune_variant;          /* 0 = auto; 1 = 8-byte vectors for fp32             */
 } psb_tensor_fused_args;
 int psb_tensor_stage_fused(const psb_tensor_fused_args* args, void* stream);
+/* CTAs of that launch (= marker rows its stage tail needs); -1 on error. */
+int64_t psb_tensor_stage_fused_rows(const psb_tensor_fused_args* args);
 
 /* ------------------------------------------------------------------------
  * Finite differences: FiniteDifferencer.__call__ kernels lap_knl / grad_knl /

@@ -147,5 +147,33 @@ def gw_initial_derivatives(f, hij, h, dx, native=False):
     return lap_f, dfdx, lap_hij
 
 
+def scalar_stage(f, dfdt, kf, kd, lap, h, dt, A, B, a, hubble, pot, native=False):
+    """One LSRK stage of the scalar sector (orc_lsrk_scalar_stage)."""
+    Nx, Ny, Nz = lap.shape[-3:]
+    load(native).orc_lsrk_scalar_stage(
+        _p(f), _p(dfdt), _p(kf), _p(kd), _p(lap), C.c_int64(Nx), C.c_int64(Ny),
+        C.c_int64(Nz), h, C.c_double(dt), C.c_double(A), C.c_double(B), C.c_double(a),
+        C.c_double(hubble), C.byref(pot))
+
+
+def first_touch_copy(src, native=False):
+    """A copy of float64 ``src`` whose pages are first touched by the OpenMP threads that will
+    work on them (NUMA placement of the timed CPU baseline)."""
+    src = np.ascontiguousarray(src, dtype=np.float64)
+    dst = np.empty_like(src)
+    row = src.shape[-1] if src.ndim else 1
+    load(native).orc_first_touch_copy(_p(dst), _p(src), C.c_int64(src.size // row),
+                                      C.c_int64(row))
+    return dst
+
+
+def first_touch_zeros(shape, native=False):
+    dst = np.empty(shape, dtype=np.float64)
+    row = dst.shape[-1]
+    load(native).orc_first_touch_copy(_p(dst), None, C.c_int64(dst.size // row),
+                                      C.c_int64(row))
+    return dst
+
+
 def num_threads(native=False):
     return load(native).orc_num_threads()

@@ -39,8 +39,7 @@ def scalar_stage(*, fused, f_in, f_out, dfdt, kf, kdfdt, lap_f=None, h, dx=(1., 
                  dV_terms=None, wrap=(True, True, True), x_range=None,
                  queue=None, strict=False, xchunk=0, variant=0,
                  energy_partials=None, energy_slot_offset=0, V_terms=None,
-                 count_slots_only=False, peer=None, generated=None, tail=None,
-                 store_flags=0):
+                 count_slots_only=False, peer=None, generated=None, tail=None):
     """
     One scalar-sector LSRK stage on padded arrays of shape ``(n, Nx+2h, Ny+2h, Nz+2h)``
     (or without the leading axis for a single field).
@@ -103,7 +102,6 @@ def scalar_stage(*, fused, f_in, f_out, dfdt, kf, kdfdt, lap_f=None, h, dx=(1., 
     fill_potential(args, dV_terms, nscalars)
     args.tune_xchunk = xchunk
     args.tune_variant = variant
-    args.store_flags = int(store_flags)
     if tail is not None:
         if not fused:
             raise ValueError("the in-kernel stage tail exists for the fused stage only")
@@ -258,13 +256,12 @@ def reduce_poly(arrays, halos, terms, ops, flags, shape, queue=None, strict=Fals
 ENERGY_SUMS_DOUBLES = 16 + 64 * 16 + 2   # PSB_ENERGY_SUMS_DOUBLES of the header
 
 
-def stage_tail_workspace(nslots, device, strict=False):
-    """Zeroed workspace of the in-kernel stage tail for launches of up to ``nslots`` CTAs:
-    ``(tensor, groups)``; the folded energy sums appear in ``tensor[:16]``."""
-    lib = _lib.load(strict)
-    groups = max(1, (int(nslots) + _lib.TAIL_GROUP - 1) // _lib.TAIL_GROUP)
-    n = lib.psb_stage_tail_workspace_doubles(groups)
-    return torch.zeros(n, dtype=torch.float64, device=device), groups
+def sentinel_rows(nrows, device):
+    """``(nrows, 16)`` float64 rows holding PSB_TAIL_SENTINEL: the state in which the
+    in-kernel stage tail expects (and leaves) its rows."""
+    rows = torch.empty((int(nrows), _lib.ENERGY_STRIDE), dtype=torch.float64, device=device)
+    rows.view(torch.int64).fill_(_lib.TAIL_SENTINEL)
+    return rows
 
 
 def energy_sums(partials, nslots, nvals, sums, queue=None, strict=False):

@@ -30,14 +30,15 @@ class PeerArgs(C.Structure):
 
 
 TAIL_FOLD, TAIL_EXPAND, TAIL_PEER = 1, 2, 4
-TAIL_GROUP = 64
+#: bit pattern (a NaN payload) of a not-yet-published value in a stage-tail row
+TAIL_SENTINEL = 0x7ff8dead0000beef
 
 
 class StageTail(C.Structure):
-    """psb_stage_tail: what the last CTA of a fused stage launch does (fold energy sums,
-    peer barrier, background stage)."""
-    _fields_ = [("mode", c_int32), ("nscalars", c_int32), ("workspace", c_void_p),
-                ("workspace_groups", c_int64),
+    """psb_stage_tail: what CTA 0 of a fused stage launch does once every CTA has published
+    its row (fold energy sums, peer barrier, background stage)."""
+    _fields_ = [("mode", c_int32), ("nscalars", c_int32), ("rows", c_void_p),
+                ("nrows", c_int64), ("sums", c_void_p),
                 ("grid_size", c_double), ("mpl", c_double), ("dt", c_double),
                 ("A", c_double), ("B", c_double),
                 ("state", c_void_p), ("energies", c_void_p), ("peers", PeerArgs)]
@@ -69,7 +70,6 @@ class ScalarStageArgs(C.Structure):
         ("vpower", (C.c_int8 * MAX_SCALARS) * MAX_TERMS),
         ("tune_xchunk", c_int32), ("tune_variant", c_int32),
         ("tail", C.POINTER(StageTail)),
-        ("store_flags", c_int32), ("reserved0", c_int32),
     ]
 
 
@@ -148,11 +148,11 @@ SYMBOLS = {
     "psb_last_error": (C.c_char_p, []),
     "psb_abi_version": (c_int, []),
     "psb_strict_fp": (c_int, []),
-    "psb_stage_tail_workspace_doubles": (c_int64, [c_int64]),
     "psb_scalar_stage_fused": (c_int, [C.POINTER(ScalarStageArgs), c_void_p]),
     "psb_scalar_stage_unfused": (c_int, [C.POINTER(ScalarStageArgs), c_void_p]),
     "psb_scalar_rk_stage": (c_int, [C.POINTER(RKStageArgs), c_void_p]),
     "psb_tensor_stage_fused": (c_int, [C.POINTER(TensorFusedArgs), c_void_p]),
+    "psb_tensor_stage_fused_rows": (c_int64, [C.POINTER(TensorFusedArgs)]),
     "psb_tensor_stage_unfused": (c_int, [C.POINTER(TensorStageArgs), c_void_p]),
     "psb_finite_difference": (c_int, [c_void_p] * 5 + [c_int, c_int64, c_int64, c_int64,
                                                         c_int, c_int,
@@ -193,6 +193,8 @@ _libs = {}
 
 def lib_path(strict=False):
     name = "libpystella_b200_strict.so" if strict else "libpystella_b200.so"
+    if not strict and os.environ.get("PSB_DEV_LIB"):   # development A/B builds
+        name = os.environ["PSB_DEV_LIB"]
     return os.path.join(HERE, "_C", name)
 
 

@@ -71,18 +71,18 @@ int validate_tail(const psb_stage_tail* a, int64_t nblocks, bool has_partials,
   if (a == nullptr || a->mode == 0) return 0;
   PSB_REQUIRE((a->mode & ~(PSB_TAIL_FOLD | PSB_TAIL_EXPAND | PSB_TAIL_PEER)) == 0,
               "%s: unknown stage-tail mode bits 0x%x", who, a->mode);
-  PSB_REQUIRE(a->workspace != nullptr, "%s: stage tail without a workspace", who);
   PSB_REQUIRE(a->nscalars >= 0 && a->nscalars <= PSB_MAX_SCALARS,
               "%s: stage tail nscalars=%d out of range", who, a->nscalars);
   if (a->mode & PSB_TAIL_FOLD) {
     PSB_REQUIRE(has_partials, "%s: PSB_TAIL_FOLD needs energy_partials", who);
     PSB_REQUIRE(a->nscalars >= 1, "%s: PSB_TAIL_FOLD needs nscalars >= 1", who);
-    PSB_REQUIRE(a->workspace_groups >= (nblocks + TAIL_GROUP - 1) / TAIL_GROUP,
-                "%s: stage-tail workspace holds %lld group rows, the launch needs %lld", who,
-                (long long)a->workspace_groups,
-                (long long)((nblocks + TAIL_GROUP - 1) / TAIL_GROUP));
   }
-  PSB_REQUIRE(a->workspace_groups >= 0, "%s: negative workspace_groups", who);
+  if (!has_partials)
+    PSB_REQUIRE(a->rows != nullptr && a->nrows >= nblocks,
+                "%s: stage tail needs %lld marker rows (has %lld)", who, (long long)nblocks,
+                (long long)(a->rows ? a->nrows : 0));
+  if (a->nscalars > 0)
+    PSB_REQUIRE(a->sums != nullptr, "%s: stage tail without a sums buffer", who);
   if (a->mode & PSB_TAIL_EXPAND) {
     PSB_REQUIRE(a->nscalars >= 1 && a->state && a->energies,
                 "%s: PSB_TAIL_EXPAND needs nscalars >= 1, state and energies", who);
@@ -101,12 +101,6 @@ int validate_tail(const psb_stage_tail* a, int64_t nblocks, bool has_partials,
 }  // namespace psb
 
 extern "C" {
-
-int64_t psb_stage_tail_workspace_doubles(int64_t workspace_groups) {
-  if (workspace_groups < 0) return -1;
-  // sums | group rows | tickets (uint32: one global + one per group), rounded up
-  return PSB_ENERGY_STRIDE * (1 + workspace_groups) + (workspace_groups + 2 + 1) / 2 + 1;
-}
 
 const char* psb_last_error(void) { return psb::g_error; }
 int psb_abi_version(void) { return PSB_ABI_VERSION; }

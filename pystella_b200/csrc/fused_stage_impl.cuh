@@ -57,7 +57,6 @@ template <typename T, int NF> struct FusedParams {
   int nvterms;
   T vcoef[PSB_MAX_TERMS];
   int8_t vpower[PSB_MAX_TERMS][NF];
-  int st_flags;        // bit0: streaming stores for f_out, bit1: plain stores for pointwise
   TailParams tail;     // in-kernel stage tail (stage_tail.cuh); mode 0 = none
 };
 
@@ -70,6 +69,23 @@ __device__ __forceinline__ Vec<T, VEC> poly_eval(int nterms, const T* coef,
                                                  const int8_t (*power)[NF],
                                                  const Vec<T, VEC>* fc) {
   Vec<T, VEC> out;
+#ifdef PSB_POLY_PER_SITE
+  // development switch: the round-1 formulation (all loops per site)
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) {
+    T acc = (T)0;
+    for (int t = 0; t < nterms; ++t) {
+      T term = coef[t];
+#pragma unroll
+      for (int m = 0; m < NF; ++m) {
+        const T fm = fc[m].v[v];
+        for (int e = 0; e < power[t][m]; ++e) term = term * fm;
+      }
+      acc = acc + term;
+    }
+    out.v[v] = acc;
+  }
+#else
 #pragma unroll
   for (int v = 0; v < VEC; ++v) out.v[v] = (T)0;
   for (int t = 0; t < nterms; ++t) {
@@ -88,6 +104,7 @@ __device__ __forceinline__ Vec<T, VEC> poly_eval(int nterms, const T* coef,
 #pragma unroll
     for (int v = 0; v < VEC; ++v) out.v[v] = out.v[v] + term.v[v];
   }
+#endif
   return out;
 }
 
@@ -425,6 +442,7 @@ __global__ void __launch_bounds__(BY* TZ, MINB)
     }
   }
 
+  double xrow = 0.0;
   if constexpr (ENERGY) {
     // block reduction of the 2*NF+1 sums -> one partials row per CTA
     constexpr int NV = 2 * NF + 1;
@@ -449,17 +467,23 @@ __global__ void __launch_bounds__(BY* TZ, MINB)
     if (tid < NV) {
       double x = 0.0;
       for (int w = 0; w < NW; ++w) x += red[w * NV + tid];
-      const int64_t blk = ((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x +
-                          blockIdx.x;
-      p.energy_partials[(p.energy_slot_offset + blk) * PSB_ENERGY_STRIDE + tid] = x;
+      if (p.tail.mode == 0) {
+        const int64_t blk = ((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x +
+                            blockIdx.x;
+        p.energy_partials[(p.energy_slot_offset + blk) * PSB_ENERGY_STRIDE + tid] = x;
+      }
+      xrow = x;
     }
   }
   if (p.tail.mode != 0) {
+    constexpr int NVROW = ENERGY ? 2 * NF + 1 : 0;
     const int64_t blk = ((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
-    const int64_t nblk = (int64_t)gridDim.x * gridDim.y * gridDim.z;
     const bool peer_store = (p.peer_lo != nullptr && xs < H) ||
                             (p.peer_hi != nullptr && xe > p.Nx - H);
-    stage_tail<0, C::THREADS>(p.tail, blk, nblk, tid, peer_store);
+    tail_publish_row<0, C::THREADS>(p.tail, blk, tid, NVROW, xrow, peer_store);
+    if (blk == 0)
+      tail_watch<0, C::THREADS>(p.tail, (int64_t)gridDim.x * gridDim.y * gridDim.z, NVROW,
+                                tid);
   }
 }
 
@@ -538,7 +562,6 @@ static void fill_params(FusedParams<T, NF>& p, const psb_scalar_stage_args* a) {
     p.vcoef[t] = (T)a->vcoef[t];
     for (int m = 0; m < NF; ++m) p.vpower[t][m] = a->vpower[t][m];
   }
-  p.st_flags = a->store_flags;
   fill_tail(p.tail, a->tail,
             a->energy_partials ? a->energy_partials + a->energy_slot_offset * PSB_ENERGY_STRIDE
                                : nullptr);

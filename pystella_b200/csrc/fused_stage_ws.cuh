@@ -264,8 +264,12 @@ __global__ void __launch_bounds__(BY* TZ + 32, MINB)
       }
     }
   };
-  using TagStream = WsBool<true>;
   using TagPlain = WsBool<false>;
+#ifdef PSB_STREAM_POINTWISE
+  using TagPointwise = WsBool<true>;
+#else
+  using TagPointwise = WsBool<false>;
+#endif
   const int64_t Pz = p.Nz + 2 * H, Py = p.Ny + 2 * H;
   const int64_t plane_stride = Py * Pz;
   const int64_t site0 = ((int64_t)H * Py + (j + H)) * Pz + (k + H);
@@ -458,20 +462,13 @@ __global__ void __launch_bounds__(BY* TZ + 32, MINB)
             dn.v[v] = d_old + p.B * kdv;
           }
           const int64_t fo_off = f * p.field_stride;
-          if (p.st_flags & 2) {
-            put(o_kf + fo_off, kfn, TagPlain{});
-            put(o_kd + fo_off, kdn, TagPlain{});
-            put(o_d + fo_off, dn, TagPlain{});
-          } else {
-            put(o_kf + fo_off, kfn, TagStream{});
-            put(o_kd + fo_off, kdn, TagStream{});
-            put(o_d + fo_off, dn, TagStream{});
-          }
+          // plain stores for all four outputs: measured on B200 they beat evict-first
+          // (st.cs) stores at both traffic mixes (stage 0: 2R:4W, stages 1-4: 4R:4W)
+          put(o_kf + fo_off, kfn, TagPointwise{});
+          put(o_kd + fo_off, kdn, TagPointwise{});
+          put(o_d + fo_off, dn, TagPointwise{});
           T* fout = o_f + fo_off;
-          if (p.st_flags & 1)
-            put(fout, fo, TagStream{});
-          else
-            put(fout, fo, TagPlain{});
+          put(fout, fo, TagPlain{});
           if (p.wrap_x) {
             if (i < H) put(fout + (int64_t)p.Nx * plane_stride, fo, TagPlain{});
             if (i >= p.Nx - H) put(fout - (int64_t)p.Nx * plane_stride, fo, TagPlain{});
@@ -517,6 +514,7 @@ __global__ void __launch_bounds__(BY* TZ + 32, MINB)
     }
   }
 
+  double xrow = 0.0;
   if constexpr (ENERGY) {
     // consumer-only reduction (the producer warp has exited): named barrier 1
     constexpr int NV = 2 * NF + 1;
@@ -541,18 +539,23 @@ __global__ void __launch_bounds__(BY* TZ + 32, MINB)
     if (tid < NV) {
       double x = 0.0;
       for (int w = 0; w < C::NCW; ++w) x += red[w * NV + tid];
-      const int64_t blk = ((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x +
-                          blockIdx.x;
-      p.energy_partials[(p.energy_slot_offset + blk) * PSB_ENERGY_STRIDE + tid] = x;
+      if (p.tail.mode == 0) {
+        const int64_t blk = ((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x +
+                            blockIdx.x;
+        p.energy_partials[(p.energy_slot_offset + blk) * PSB_ENERGY_STRIDE + tid] = x;
+      }
+      xrow = x;
     }
   }
   if (p.tail.mode != 0) {
     // consumer warps only (the producer warp has exited): named barrier 1
+    constexpr int NVROW = ENERGY ? 2 * NF + 1 : 0;
     const int64_t blk = ((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
-    const int64_t nblk = (int64_t)gridDim.x * gridDim.y * gridDim.z;
     const bool peer_store = (p.peer_lo != nullptr && xs < H) ||
                             (p.peer_hi != nullptr && xe > p.Nx - H);
-    stage_tail<1, BY * TZ>(p.tail, blk, nblk, tid, peer_store);
+    tail_publish_row<1, BY * TZ>(p.tail, blk, tid, NVROW, xrow, peer_store);
+    if (blk == 0)
+      tail_watch<1, BY * TZ>(p.tail, (int64_t)gridDim.x * gridDim.y * gridDim.z, NVROW, tid);
   }
 }
 

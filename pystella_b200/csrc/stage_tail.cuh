@@ -1,16 +1,31 @@
 // In-kernel tail of an RK stage: what used to be two or three tiny launches between the
-// stage kernels (psb_energy_sums, psb_expansion_stage / psb_expansion_stage_peer) runs in
-// the LAST CTA of the stage kernel itself (atomic tickets, threadFenceReduction pattern):
+// stage kernels (psb_energy_sums, psb_expansion_stage / psb_expansion_stage_peer) runs inside
+// the stage kernel itself, in CTA 0 (the "watcher"), with NO fence, atomic or barrier added
+// to the other CTAs:
 //
-//   FOLD    the per-CTA energy partial rows are folded in a fixed order -- groups of 64
-//           consecutive CTAs by the last CTA of each group, the group rows by the last
-//           group -- into sums[0..2ns] (deterministic: the order of the additions depends
-//           on indices only, never on which CTA happens to be last);
-//   PEER    all-gather of the sums over peer memory, flag barrier between the GPUs of the
-//           node (orders the halo planes this kernel stored into the neighbours' memory
-//           before anybody's next stage, and protects the ping-pong buffers);
-//   EXPAND  energies with the current scale factor, then one low-storage RK stage of the
-//           FLRW background (pystella/expansion.py:119-157).
+//   * every CTA publishes one row of doubles when it is done -- its energy partial sums, or
+//     a single marker for kernels without energy sums -- with plain 8-byte stores.  Rows are
+//     pre-set to a sentinel bit pattern (PSB_TAIL_SENTINEL, a NaN payload no computation
+//     produces), so a value is valid exactly when it differs from the sentinel: 8-byte
+//     stores are single-copy atomic, no ordering between a row's values is needed (the
+//     Lamport-style self-validating packets of the low-latency all-reduce protocols);
+//   * CTA 0 first does its own tile, then consumes the rows in index order as they appear
+//     (thread t adds rows t, t+NT, ... in increasing order, then a fixed tree: the sum is
+//     deterministic, independent of timing), re-arms each row to the sentinel for the next
+//     launch, and finally
+//   FOLD    writes the sums to sums[0..2ns];
+//   PEER    all-gathers them over peer memory and runs the flag barrier between the GPUs of
+//           the node (CTAs that stored halo planes into a neighbour's memory publish their
+//           row only after a system-scope fence, so "all rows seen" implies "all peer stores
+//           visible"; this orders the halo stores before anybody's next stage and protects
+//           the ping-pong buffers);
+//   EXPAND  forms the energies with the current scale factor and advances the FLRW
+//           background by one low-storage stage (pystella/expansion.py:119-157).
+//
+// Why not the classic last-CTA ticket (threadFenceReduction)?  Measured on B200 (512^3 fp64,
+// 16384 CTAs of ~25 us): the __threadfence() + atomic at the end of EVERY CTA keeps its SM
+// slot occupied until all of its stores have drained -- 7 % of the kernel time.  The watcher
+// costs one of 296 CTA slots.
 //
 // Per stage this replaces Reduction.__call__ -> get_rho_and_p -> Expansion.step
 // (pystella/reduction.py:237-255, sectors.py:211-229, expansion.py:140-157) and, multi-rank,
@@ -24,14 +39,13 @@
 namespace psb {
 
 constexpr int TAIL_FOLD = 1, TAIL_EXPAND = 2, TAIL_PEER = 4;
-constexpr int TAIL_GROUP = 64;   // CTAs per first-level fold
+constexpr unsigned long long TAIL_SENTINEL = PSB_TAIL_SENTINEL;
 
 struct TailParams {
   int mode;             // 0 = no tail
   int ns;               // scalar fields in the energy sums (nvals = 2 ns + 1); 0 = none
-  double* partials;     // row 0 of this launch's partial rows (FOLD)
-  double* ws;           // sums[16] | group rows [ng][16] | tickets (uint32: global, groups)
-  int64_t ws_groups;    // capacity (group rows) of ws; tickets start behind them
+  double* rows;         // one row of PSB_ENERGY_STRIDE doubles per CTA, sentinel-initialised
+  double* sums;         // [16]: folded sums (written with FOLD, read otherwise)
   double grid_size, mpl, dt, A, B;
   double* state;        // {a, adot, hubble, ka, kadot}
   double* energies;     // {kinetic.., potential, gradient.., total, pressure}
@@ -39,14 +53,15 @@ struct TailParams {
 };
 
 #ifndef __CUDACC_RTC__
-inline void fill_tail(TailParams& t, const psb_stage_tail* a, double* partials_row0) {
+// rows_energy: row 0 of the launch's energy partial rows (kernels with energy sums publish
+// through them), else the tail's own marker rows are used
+inline void fill_tail(TailParams& t, const psb_stage_tail* a, double* rows_energy) {
   memset(&t, 0, sizeof(t));
   if (a == nullptr || a->mode == 0) return;
   t.mode = a->mode;
   t.ns = a->nscalars;
-  t.partials = partials_row0;
-  t.ws = a->workspace;
-  t.ws_groups = a->workspace_groups;
+  t.rows = rows_energy != nullptr ? rows_energy : a->rows;
+  t.sums = a->sums;
   t.grid_size = a->grid_size;
   t.mpl = a->mpl;
   t.dt = a->dt;
@@ -61,6 +76,15 @@ int validate_tail(const psb_stage_tail* a, int64_t nblocks, bool has_partials, c
 
 template <int BAR, int NT> __device__ __forceinline__ void tail_bar() {
   asm volatile("bar.sync %0, %1;" ::"n"(BAR), "n"(NT) : "memory");
+}
+
+__device__ __forceinline__ void tail_publish(double* p, double x) {
+  asm volatile("st.volatile.global.f64 [%0], %1;" ::"l"(p), "d"(x) : "memory");
+}
+__device__ __forceinline__ unsigned long long tail_peek(const double* p) {
+  unsigned long long v;
+  asm volatile("ld.volatile.global.b64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
 }
 
 struct TailEnergies {
@@ -129,8 +153,8 @@ __device__ inline void tail_peer_exchange(const psb_peer_args& peers, const doub
   __threadfence_system();
   tail_bar<BAR, NT>();
   // 2. raise my flag on every rank: everything this rank stored to its peers before (the
-  //    halo planes of this kernel, published by every CTA with a system fence ahead of its
-  //    ticket) is ordered before it
+  //    halo planes of this kernel: their CTAs fenced at system scope before publishing the
+  //    rows this CTA has consumed) is ordered before it
   for (int q = tid; q < P; q += NT) {
     unsigned long long* fl =
         static_cast<unsigned long long*>(peers.peer_flags[q]) + (int64_t)par * P + me;
@@ -160,80 +184,81 @@ __device__ inline void tail_peer_exchange(const psb_peer_args& peers, const doub
   tail_bar<BAR, NT>();
 }
 
-// Called by the NT threads of barrier BAR of EVERY CTA of the launch, after their last
-// global store.  blk = linear CTA index, nblk = CTAs in the launch; did_peer_store: this CTA
-// stored into a neighbour's memory.
+// Every CTA: publish this CTA's row.  vals[0..nv) are the values of thread `tid` == r (the
+// caller passes x for tid < nv); kernels without energy sums pass nv = 0 and a marker is
+// written.  CTAs that stored into a neighbour's memory fence at system scope first.
 template <int BAR, int NT>
-__device__ inline void stage_tail(const TailParams& t, int64_t blk, int64_t nblk, int tid,
-                                  bool did_peer_store) {
-  __shared__ int s_last;
-  __shared__ double s_total[PSB_ENERGY_STRIDE];
-  const int nvals = t.ns > 0 ? 2 * t.ns + 1 : 0;
-  const int lane = tid & 31, warp = tid >> 5;
-  constexpr int NW = NT / 32;
-  double* sums = t.ws;
-  double* grows = t.ws + PSB_ENERGY_STRIDE;
-  unsigned int* tickets =
-      reinterpret_cast<unsigned int*>(t.ws + PSB_ENERGY_STRIDE * (1 + t.ws_groups));
-
-  if ((t.mode & TAIL_PEER) && did_peer_store)
+__device__ __forceinline__ void tail_publish_row(const TailParams& t, int64_t blk, int tid,
+                                                 int nv, double x, bool did_peer_store) {
+  if ((t.mode & TAIL_PEER) && did_peer_store) {
     __threadfence_system();
-  else
-    __threadfence();
-  tail_bar<BAR, NT>();
-
-  if (t.mode & TAIL_FOLD) {
-    const int64_t ng = (nblk + TAIL_GROUP - 1) / TAIL_GROUP;
-    const int64_t g = blk / TAIL_GROUP;
-    const int64_t left = nblk - g * TAIL_GROUP;
-    const int gsize = left < TAIL_GROUP ? (int)left : TAIL_GROUP;
-    if (tid == 0) s_last = (atomicAdd(&tickets[1 + g], 1u) == (unsigned)(gsize - 1));
     tail_bar<BAR, NT>();
-    if (!s_last) return;
-    __threadfence();
-    for (int r = warp; r < nvals; r += NW) {
-      double x = 0.0;
-      for (int row = lane; row < gsize; row += 32)
-        x += __ldcg(&t.partials[(g * TAIL_GROUP + row) * PSB_ENERGY_STRIDE + r]);
-#pragma unroll
-      for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
-      if (lane == 0) grows[g * PSB_ENERGY_STRIDE + r] = x;
-    }
-    __threadfence();
-    tail_bar<BAR, NT>();
-    if (tid == 0) {
-      tickets[1 + g] = 0u;   // re-arm for the next launch
-      s_last = (atomicAdd(&tickets[0], 1u) == (unsigned)(ng - 1));
-    }
-    tail_bar<BAR, NT>();
-    if (!s_last) return;
-    __threadfence();
-    for (int r = warp; r < nvals; r += NW) {
-      double x = 0.0;
-      for (int64_t row = lane; row < ng; row += 32)
-        x += __ldcg(&grows[row * PSB_ENERGY_STRIDE + r]);
-#pragma unroll
-      for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
-      if (lane == 0) sums[r] = x;
-    }
-    if (tid == 0) tickets[0] = 0u;
-    __threadfence();
-    tail_bar<BAR, NT>();
-  } else {
-    if (tid == 0) s_last = (atomicAdd(&tickets[0], 1u) == (unsigned)(nblk - 1));
-    tail_bar<BAR, NT>();
-    if (!s_last) return;
-    if (tid == 0) tickets[0] = 0u;
-    __threadfence();
   }
-  if (!(t.mode & (TAIL_EXPAND | TAIL_PEER))) return;
+  double* row = t.rows + blk * PSB_ENERGY_STRIDE;
+  if (nv > 0) {
+    if (tid < nv) tail_publish(row + tid, x);
+  } else if (tid == 0) {
+    tail_publish(row, 1.0);
+  }
+}
 
-  // ---- this is the last CTA of the launch: every other CTA has published its stores
-  if (t.mode & TAIL_PEER) {
-    tail_peer_exchange<BAR, NT>(t.peers, sums, nvals, s_total, tid);
-  } else {
-    if (tid < nvals) s_total[tid] = __ldcg(&sums[tid]);
+// CTA 0 only, after its own tile: consume all rows, then fold / exchange / expand.
+template <int BAR, int NT>
+__device__ __noinline__ void tail_watch(const TailParams& t, int64_t nblk, int nv, int tid) {
+  __shared__ double s_red[NT / 32][PSB_ENERGY_STRIDE];
+  __shared__ double s_total[PSB_ENERGY_STRIDE];
+  const int nvals = t.ns > 0 ? 2 * t.ns + 1 : 0;   // values of the energy sums
+  const int nread = nv > 0 ? nv : 1;               // values per row of THIS launch
+  const int lane = tid & 31, warp = tid >> 5;
+  double acc[2 * PSB_MAX_SCALARS + 1];
+#pragma unroll
+  for (int r = 0; r < 2 * PSB_MAX_SCALARS + 1; ++r) acc[r] = 0.0;
+  const double sentinel = __longlong_as_double((long long)TAIL_SENTINEL);
+  for (int64_t row = tid; row < nblk; row += NT) {
+    double* p = t.rows + row * PSB_ENERGY_STRIDE;
+#pragma unroll
+    for (int r = 0; r < 2 * PSB_MAX_SCALARS + 1; ++r) {
+      if (r < nread) {
+        unsigned long long v = tail_peek(p + r);
+        unsigned ns_sleep = 32;
+        while (v == TAIL_SENTINEL) {
+          __nanosleep(ns_sleep);
+          if (ns_sleep < 512) ns_sleep *= 2;
+          v = tail_peek(p + r);
+        }
+        acc[r] += __longlong_as_double((long long)v);
+        tail_publish(p + r, sentinel);   // re-arm for the next launch
+      }
+    }
+  }
+  if (t.mode & TAIL_FOLD) {
+    // fixed tree: lanes (xor shuffle), then warps in index order
+#pragma unroll
+    for (int r = 0; r < 2 * PSB_MAX_SCALARS + 1; ++r) {
+      if (r < nv) {
+        double x = acc[r];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
+        if (lane == 0) s_red[warp][r] = x;
+      }
+    }
     tail_bar<BAR, NT>();
+    if (tid < nv) {
+      double x = 0.0;
+      for (int w = 0; w < NT / 32; ++w) x += s_red[w][tid];
+      t.sums[tid] = x;
+      s_total[tid] = x;
+    }
+  } else {
+    tail_bar<BAR, NT>();   // every thread has seen its rows
+    if (tid < nvals) s_total[tid] = t.sums[tid];   // folded by an earlier kernel of the stage
+  }
+  tail_bar<BAR, NT>();
+  if (!(t.mode & (TAIL_EXPAND | TAIL_PEER))) return;
+  if (t.mode & TAIL_PEER) {
+    if (tid < nvals) s_red[0][tid] = s_total[tid];
+    tail_bar<BAR, NT>();
+    tail_peer_exchange<BAR, NT>(t.peers, s_red[0], nvals, s_total, tid);
   }
   if ((t.mode & TAIL_EXPAND) && tid == 0)
     tail_expansion_update(s_total, t.ns, t.grid_size, t.mpl, t.dt, t.A, t.B, t.state,

@@ -309,9 +309,9 @@ __global__ void __launch_bounds__(BY* TZ + 32, MINB)
           ho.v[v] = qh[H].v[v] + p.B * khv;
           dn.v[v] = d_old + p.B * kdv;
         }
-        st_pieces<T, VEC, GV, true>(o_kh, khn);
-        st_pieces<T, VEC, GV, true>(o_kd, kdn);
-        st_pieces<T, VEC, GV, true>(o_d, dn);
+        st_pieces<T, VEC, GV, false>(o_kh, khn);
+        st_pieces<T, VEC, GV, false>(o_kd, kdn);
+        st_pieces<T, VEC, GV, false>(o_d, dn);
         st_pieces<T, VEC, GV, false>(o_h, ho);
         if (p.wrap_x) {
           if (i < H) st_pieces<T, VEC, GV, false>(o_h + (int64_t)p.Nx * plane_stride, ho);
@@ -356,10 +356,11 @@ __global__ void __launch_bounds__(BY* TZ + 32, MINB)
   }
   if (p.tail.mode != 0) {
     const int64_t blk = ((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
-    const int64_t nblk = (int64_t)gridDim.x * gridDim.y * gridDim.z;
     const bool peer_store = (p.peer_lo != nullptr && xs < H) ||
                             (p.peer_hi != nullptr && xe > p.Nx - H);
-    stage_tail<1, BY * TZ>(p.tail, blk, nblk, tid, peer_store);
+    tail_publish_row<1, BY * TZ>(p.tail, blk, tid, 0, 0.0, peer_store);
+    if (blk == 0)
+      tail_watch<1, BY * TZ>(p.tail, (int64_t)gridDim.x * gridDim.y * gridDim.z, 0, tid);
   }
 }
 
@@ -382,11 +383,19 @@ constexpr int tws_pick_tz(int es, int H, int NS, int BY, int P, int VEC) {
 }
 
 template <typename T, int H, int NS, int VEC>
-static int launch_tensor_ws(const psb_tensor_fused_args* a, cudaStream_t stream) {
+static int launch_tensor_ws(const psb_tensor_fused_args* a, cudaStream_t stream,
+                            int64_t* count) {
   constexpr int BY = 4, P = 2;
   constexpr int TZ = tws_pick_tz((int)sizeof(T), H, NS, BY, P, VEC);
   using C = TwsCfg<T, H, NS, BY, TZ, P, VEC>;
   using B = typename C::B;
+  if (count != nullptr) {
+    int64_t xc = a->tune_xchunk > 0 ? a->tune_xchunk : WS_DEFAULT_XCHUNK;
+    if (xc > a->Nx) xc = a->Nx;
+    *count = 6 * ((a->Nz + B::BZ - 1) / B::BZ) * ((a->Ny + BY - 1) / BY) *
+             ((a->Nx + xc - 1) / xc);
+    return 0;
+  }
   static_assert(C::SMEM_BYTES <= 227 * 1024, "tensor pipeline does not fit shared memory");
   const int64_t Px = a->Nx + 2 * H, Py = a->Ny + 2 * H, Pz = a->Nz + 2 * H;
   const int64_t vol = Px * Py * Pz;
@@ -456,20 +465,20 @@ static int launch_tensor_ws(const psb_tensor_fused_args* a, cudaStream_t stream)
 }
 
 template <typename T, int H>
-static int tensor_fused_ns(const psb_tensor_fused_args* a, cudaStream_t s) {
+static int tensor_fused_ns(const psb_tensor_fused_args* a, cudaStream_t s, int64_t* count) {
   // 16-byte shared-memory vectors: 2 doubles, or 4 floats when the rows allow it
   if constexpr (sizeof(T) == 4) {
     if (a->Nz % 4 == 0 && a->tune_variant != 1) {
       switch (a->nscalars) {
-        case 1: return launch_tensor_ws<T, H, 1, 4>(a, s);
-        case 2: return launch_tensor_ws<T, H, 2, 4>(a, s);
+        case 1: return launch_tensor_ws<T, H, 1, 4>(a, s, count);
+        case 2: return launch_tensor_ws<T, H, 2, 4>(a, s, count);
       }
     }
   }
   constexpr int VEC = 2;
   switch (a->nscalars) {
-    case 1: return launch_tensor_ws<T, H, 1, VEC>(a, s);
-    case 2: return launch_tensor_ws<T, H, 2, VEC>(a, s);
+    case 1: return launch_tensor_ws<T, H, 1, VEC>(a, s, count);
+    case 2: return launch_tensor_ws<T, H, 2, VEC>(a, s, count);
   }
   set_error("psb_tensor_stage_fused: nscalars=%d (1 or 2 source fields)", a->nscalars);
   return 1;
@@ -477,7 +486,7 @@ static int tensor_fused_ns(const psb_tensor_fused_args* a, cudaStream_t s) {
 
 }  // namespace psb
 
-extern "C" int psb_tensor_stage_fused(const psb_tensor_fused_args* a, void* stream) {
+static int tensor_fused_entry(const psb_tensor_fused_args* a, void* stream, int64_t* count) {
   using namespace psb;
   PSB_REQUIRE(a != nullptr, "psb_tensor_stage_fused: null args");
   PSB_REQUIRE(a->hij_in && a->hij_out && a->dhijdt && a->khij && a->kdhijdt && a->src,
@@ -492,9 +501,20 @@ extern "C" int psb_tensor_stage_fused(const psb_tensor_fused_args* a, void* stre
               "psb_tensor_stage_fused: wrap_x and peer halos are mutually exclusive");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (a->dtype == PSB_F64)
-    return a->h == 2 ? tensor_fused_ns<double, 2>(a, s) : tensor_fused_ns<double, 4>(a, s);
+    return a->h == 2 ? tensor_fused_ns<double, 2>(a, s, count)
+                     : tensor_fused_ns<double, 4>(a, s, count);
   if (a->dtype == PSB_F32)
-    return a->h == 2 ? tensor_fused_ns<float, 2>(a, s) : tensor_fused_ns<float, 4>(a, s);
+    return a->h == 2 ? tensor_fused_ns<float, 2>(a, s, count)
+                     : tensor_fused_ns<float, 4>(a, s, count);
   set_error("psb_tensor_stage_fused: unknown dtype %d", a->dtype);
   return 1;
+}
+
+extern "C" int psb_tensor_stage_fused(const psb_tensor_fused_args* a, void* stream) {
+  return tensor_fused_entry(a, stream, nullptr);
+}
+
+extern "C" int64_t psb_tensor_stage_fused_rows(const psb_tensor_fused_args* a) {
+  int64_t count = 0;
+  return tensor_fused_entry(a, nullptr, &count) == 0 ? count : -1;
 }

@@ -201,6 +201,20 @@ def _adopt_into_peer_buffers(stepper, key, f):
     stepper.__dict__.setdefault("_fresh", {}).pop(key, None)   # touch the views in ps["bufs"]
 
 
+def _marker_rows(stepper, args, peer):
+    """CTAs of the launch when it carries no energy partials but needs a stage tail (the
+    inter-GPU barrier of a multi-rank stepper without energy sums): marker rows."""
+    if stepper.fused_energy or peer is None:
+        return 0
+    f = args["f_in"]
+    key = ("rows", tuple(f.shape), f.dtype, args["xchunk"], args["variant"])
+    cache = stepper.__dict__.setdefault("_energy_layout", {})
+    if key not in cache:
+        probe = {k: v for k, v in args.items() if k != "generated"}
+        cache[key] = _kernels.scalar_stage(count_slots_only=True, **probe)
+    return cache[key]
+
+
 def fused_scalar_stage(stepper, system, f, common, queue):
     h = common["h"]
     decomp = stepper.decomp
@@ -240,8 +254,7 @@ def fused_scalar_stage(stepper, system, f, common, queue):
     args = dict(common)
     args.update(fused=True, f_in=f, f_out=twin, dx=stepper.dx)
     tune = stepper.tune or {}
-    args.update(xchunk=tune.get("xchunk", 0), variant=tune.get("variant", 0),
-                store_flags=tune.get("store_flags", 0))
+    args.update(xchunk=tune.get("xchunk", 0), variant=tune.get("variant", 0))
 
     nslots = 0
     if stepper.fused_energy:
@@ -260,9 +273,8 @@ def fused_scalar_stage(stepper, system, f, common, queue):
         counts = cache[lkey]
         total = sum(counts)
         if stepper.energy_partials is None or stepper.energy_partials.shape[0] < total:
-            from pystella_b200._lib import ENERGY_STRIDE
-            stepper.energy_partials = torch.zeros(
-                (total, ENERGY_STRIDE), dtype=torch.float64, device=f.device)
+            # rows start out (and are left by the in-kernel tail) as "not yet published"
+            stepper.energy_partials = _kernels.sentinel_rows(total, f.device)
         stepper.energy_nslots = total
         stepper.energy_nvals = 2 * system.nscalars + 1
         offsets = [sum(counts[:i]) for i in range(len(counts))]
@@ -276,7 +288,8 @@ def fused_scalar_stage(stepper, system, f, common, queue):
     if not multi:
         # one launch; its last CTA folds the energy sums and, with an attached
         # DeviceExpansion, advances the background: no other kernel in the stage
-        tail = stepper._make_tail(fold=stepper.fused_energy, dt=common["dt"], nslots=nslots,
+        tail = stepper._make_tail(fold=stepper.fused_energy, dt=common["dt"],
+                                  nrows=_marker_rows(stepper, args, None),
                                   device=f.device)
         _kernels.scalar_stage(wrap=(True, True, True), tail=tail, **args, **energy_kw[0])
         stepper._tail_issued(tail)
@@ -290,8 +303,8 @@ def fused_scalar_stage(stepper, system, f, common, queue):
         peer = dict(lo=ps["ptrs"][out_id][ps["lo"]], hi=ps["ptrs"][out_id][ps["hi"]],
                     lo_Nx=ps["lo_Nx"], lo_stride=ps["lo_stride"], hi_stride=ps["hi_stride"])
         stepper._peer_barrier_pending = True
-        tail = stepper._make_tail(fold=stepper.fused_energy, dt=common["dt"], nslots=nslots,
-                                  device=f.device)
+        tail = stepper._make_tail(fold=stepper.fused_energy, dt=common["dt"],
+                                  nrows=_marker_rows(stepper, args, peer), device=f.device)
         _kernels.scalar_stage(wrap=(False, True, True), peer=peer, tail=tail, **args,
                               **energy_kw[0])
         stepper._tail_issued(tail)

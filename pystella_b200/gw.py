@@ -115,10 +115,16 @@ class TensorSystem:
             args.peer_lo_Nx = ps["lo_Nx"]
             args.peer_lo_stride, args.peer_hi_stride = ps["lo_stride"], ps["hi_stride"]
             stepper._peer_barrier_pending = True
-        tail = stepper._make_tail(fold=False, dt=dt, device=hij.device)
+        lib = _lib.load(stepper.strict_fp)
+        rkey = ("gw_rows", tuple(hij.shape), hij.dtype, args.tune_xchunk, args.tune_variant)
+        cache = stepper.__dict__.setdefault("_energy_layout", {})
+        if rkey not in cache:
+            cache[rkey] = lib.psb_tensor_stage_fused_rows(C.byref(args))
+            if cache[rkey] < 0:
+                _lib.check(lib, 1, "psb_tensor_stage_fused_rows")
+        tail = stepper._make_tail(fold=False, dt=dt, nrows=cache[rkey], device=hij.device)
         if tail is not None:
             args.tail = C.pointer(tail)
-        lib = _lib.load(stepper.strict_fp)
         rc = lib.psb_tensor_stage_fused(C.byref(args), _lib.stream_ptr(queue))
         _lib.check(lib, rc, "psb_tensor_stage_fused")
         stepper._tail_issued(tail)

@@ -520,8 +520,13 @@ class LowStorageRKStepper(Stepper):
     def reset(self):
         """Forget halo freshness.  Not needed after in-place edits or when passing a new
         tensor (both are detected, see :func:`pystella_b200.fused.halos_are_fresh`); kept for
-        writes through raw pointers the stepper cannot see."""
+        writes through raw pointers the stepper cannot see.  Also re-arms the rows of the
+        in-kernel stage tail (needed only after a kernel was aborted mid-run)."""
         self._fresh = {}
+        from pystella_b200 import _lib
+        for rows in (self.__dict__.get("energy_partials"), self.__dict__.get("_tail_rows")):
+            if rows is not None:
+                rows.view(torch.int64).fill_(_lib.TAIL_SENTINEL)
 
     def __call__(self, stage, *, queue=None, **kwargs):
         if not 0 <= stage < self.num_stages:
@@ -606,11 +611,20 @@ class LowStorageRKStepper(Stepper):
             # the last kernel of the stage carries the in-kernel tail (inter-GPU barrier,
             # background stage): pystella_b200/csrc/stage_tail.cuh
             self._last_of_stage = (n == len(systems) - 1)
+            hook = self.__dict__.get("_timing_hook")
+            if hook is not None:               # per-kernel CUDA events (bench.py roofline)
+                cur = queue if queue is not None else torch.cuda.current_stream()
+                ev0 = torch.cuda.Event(enable_timing=True)
+                ev1 = torch.cuda.Event(enable_timing=True)
+                ev0.record(cur)
             system_stage = getattr(system, "run_stage", None)
             if system_stage is not None:       # tensor sector etc.
                 system_stage(self, stage, queue, kwargs, dt, A, B)
             else:
                 self._scalar_stage(system, stage, queue, kwargs, dt, A, B)
+            if hook is not None:
+                ev1.record(cur)
+                hook.append((stage, n, ev0, ev1))
         return None
 
     # -- in-kernel stage tail ---------------------------------------------------
@@ -620,8 +634,9 @@ class LowStorageRKStepper(Stepper):
         ``expand.step(stage, stepper, dt)`` then returns immediately."""
         self._expansion = expand
 
-    def _make_tail(self, *, fold, dt, nslots=0, device=None):
-        """psb_stage_tail of the launch being issued (None when there is nothing to do)."""
+    def _make_tail(self, *, fold, dt, nrows=0, device=None):
+        """psb_stage_tail of the launch being issued (None when there is nothing to do).
+        ``nrows``: CTAs of a launch WITHOUT energy partials (it publishes marker rows)."""
         from pystella_b200 import _lib
         mode = 0
         if fold:
@@ -635,20 +650,22 @@ class LowStorageRKStepper(Stepper):
             mode |= _lib.TAIL_EXPAND
         if mode == 0:
             return None
-        ws = getattr(self, "_tail_ws", None)
-        need = max(1, (int(nslots) + _lib.TAIL_GROUP - 1) // _lib.TAIL_GROUP)
-        if ws is None or self._tail_groups < need:
-            if ws is not None:
-                torch.cuda.current_stream().synchronize()
-            ws, groups = _kernels.stage_tail_workspace(max(nslots, 1), device, self.strict_fp)
-            self._tail_ws, self._tail_groups = ws, groups
+        if getattr(self, "_tail_sums", None) is None:
             #: folded energy sums {sum dfdt_n^2.., sum V, sum -f_n lap f_n..} of the state
             #: that entered the last stage (device, float64[16])
-            self.energy_sums = ws[:16]
+            self._tail_sums = torch.zeros(16, dtype=torch.float64, device=device)
+            self.energy_sums = self._tail_sums
         tail = _lib.StageTail()
         tail.mode = mode
-        tail.workspace = self._tail_ws.data_ptr()
-        tail.workspace_groups = self._tail_groups
+        tail.sums = self._tail_sums.data_ptr()
+        if not fold and nrows > 0:
+            rows = getattr(self, "_tail_rows", None)
+            if rows is None or rows.shape[0] < nrows:
+                if rows is not None:
+                    torch.cuda.synchronize()
+                rows = _kernels.sentinel_rows(nrows, device)
+                self._tail_rows = rows
+            tail.rows, tail.nrows = rows.data_ptr(), rows.shape[0]
         if self.fused_energy:
             tail.nscalars = self.energy_nvals // 2 if getattr(self, "energy_nvals", 0) else 0
         if mode & _lib.TAIL_EXPAND:

@@ -95,6 +95,13 @@ if __name__ == "__main__":
     which = sys.argv[1:] or ["scalar", "chunk", "store", "gw"]
     F64, F32 = torch.float64, torch.float32
     N5 = (512,) * 3
+    if "ab" in which:      # A/B of library builds (PSB_DEV_LIB): the cases that moved
+        for dt_ in (F64, F32):
+            for stage in (1, 0):
+                scalar_case(N5, dt_, stage, False)
+                scalar_case(N5, dt_, stage, True)
+        scalar_case(N5, F32, 1, True, nscalars=2)
+        scalar_case((256,) * 3, F64, 1, True)
     if "scalar" in which:
         for dt_ in (F64, F32):
             for stage in (1, 0):
@@ -113,9 +120,6 @@ if __name__ == "__main__":
         for xc in (8, 16, 32):
             scalar_case((128, 1024, 1024), F32, 1, True, tune={"xchunk": xc})
     if "store" in which:
-        for fl in (0, 1, 2, 3):
-            scalar_case(N5, F64, 0, True, tune={"store_flags": fl})
-            scalar_case(N5, F64, 1, True, tune={"store_flags": fl})
         for var in (10, 11, 12, 13, 14):
             scalar_case(N5, F64, 0, True, tune={"variant": var})
     if "gw" in which:

@@ -1,0 +1,97 @@
+"""
+Parity at the sizes BASELINE.json's configurations are quoted on: the CUDA path through the
+public API (fused stage kernels, in-kernel energy sums and background stage) against the C
+oracle's reference loop (oracle/oracle_c.c: stepper -> expand.step -> share_halos + lap +
+energies, examples/scalar_preheating.py:258-266) on the SAME seeded initial conditions as
+bench.py -- config 2 (256^3 fp64, two full steps), one full step of config 3 (512^3 fp64),
+and the bench's own window check (the path SCALE records run at N > 1) at N = 1 for every
+configuration family.  fp64: <= 1e-12 of the array scale after every comparison.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import oracle as O  # noqa: E402
+from oracle import c_oracle as CO  # noqa: E402
+import pystella_b200 as ps  # noqa: E402
+import bench  # noqa: E402
+
+torch = pytest.importorskip("torch")
+pytestmark = [pytest.mark.gpu]
+
+
+def scale_err(a, b):
+    return float(np.max(np.abs(a - b)) / np.max(np.abs(b)))
+
+
+def _oracle_run(w, nsteps):
+    h = w["h"]
+    f0, d0 = bench.initial_fields(w)
+    f, d = f0.astype(np.float64), d0.astype(np.float64)
+    kf, kd = np.zeros_like(f), np.zeros_like(f)
+    N = w["rank_shape"]
+    lap = np.zeros((w["nscalars"],) + N)
+    pot = CO.make_potential(w["nscalars"], bench.potential_terms(w))
+    gs = float(np.prod(N))
+    for n in range(w["nscalars"]):
+        CO.share_halos(f[n], h)
+        CO.laplacian(f[n], lap[n], h, w["dx"])
+    en = CO.scalar_energy(f, d, lap, h, 1.0, gs, pot)
+    # the background starts from the homogeneous-mode energy, as bench.py's DeviceExpansion
+    adot = float(np.sqrt(8 * np.pi / 3 / w["mpl"]**2 * bench.background_energy(w)))
+    state = np.array([1.0, adot, adot, 0.0, 0.0])
+    A, B, _ = O.LSRK_TABLES["LowStorageRK54"]
+    CO.preheating_steps(nsteps, A, B, f, d, kf, kd, lap, h, w["dx"], w["dt"], w["mpl"], gs,
+                        pot, state, en, True)
+    return f, d, state
+
+
+@pytest.mark.parametrize("config,nsteps", [("c2", 2), ("c3", 1)])
+def test_config_size_parity_fp64(config, nsteps):
+    cfg = dict(bench.CONFIGS[config], name=config)
+    w = bench.workload(cfg, 1, 0)
+    h = w["h"]
+    f_ref, d_ref, state_ref = _oracle_run(w, nsteps)
+
+    decomp = ps.DomainDecomposition((1, 1, 1), h, rank_shape=w["rank_shape"])
+    sector = ps.ScalarSector(1, potential=bench.potential_callable(w))
+    stepper = ps.LowStorageRK54(sector, halo_shape=h, dt=w["dt"], dx=w["dx"], decomp=decomp,
+                                MapKernel=ps.FusedStencilStage, energy=True)
+    f0, d0 = bench.initial_fields(w)
+    f, dfdt = torch.from_numpy(f0).cuda(), torch.from_numpy(d0).cuda()
+    expand = ps.DeviceExpansion(bench.background_energy(w), ps.LowStorageRK54, mpl=w["mpl"],
+                                grid_size=float(np.prod(w["grid_shape"])), nscalars=1)
+    for _ in range(nsteps):
+        for s in range(5):
+            stepper(s, f=f, dfdt=dfdt, a=expand.a, hubble=expand.hubble)
+            expand.step(s, stepper, w["dt"])
+    torch.cuda.synchronize()
+    got = expand.get()
+    assert np.isclose(got["a"], state_ref[0], rtol=1e-13)
+    assert np.isclose(got["adot"], state_ref[1], rtol=1e-12)
+    assert np.isclose(got["hubble"], state_ref[2], rtol=1e-12)
+    for g, r in ((f, f_ref), (dfdt, d_ref)):
+        assert scale_err(O.interior(g[0].cpu().numpy(), h), O.interior(r[0], h)) < 1e-12
+
+
+@pytest.mark.parametrize("config,grid", [("c2", None), ("c4", 128), ("c5", None)])
+def test_bench_window_parity_single_gpu(config, grid):
+    """bench.py's own parity block (x-window across the periodic boundary vs the oracle on a
+    sub-box), run here so that a regression fails the suite and not only a bench line."""
+    cfg = dict(bench.CONFIGS[config], name=config)
+    if grid:
+        cfg["grid"] = (grid,) * 3
+    if config == "c5":
+        cfg["grid"] = (128, 256, 256)
+    w = bench.workload(cfg, 1, 0)
+    decomp = ps.DomainDecomposition((1, 1, 1), w["h"], rank_shape=w["rank_shape"])
+    job = bench.Job(ps, torch, cfg, w, decomp, torch.device("cuda", 0), {"xchunk": 0,
+                    "variant": 0}, float(np.prod(w["grid_shape"])))
+    par = bench.run_parity(job, cfg, w, 1, 0, None)
+    assert par["ok"], par
+    if cfg["dtype"] == "f64":
+        assert par["max_rel"] < 1e-12

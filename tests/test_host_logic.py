@@ -35,16 +35,29 @@ def test_launch_ranges_cover_the_slab_once():
 def test_bench_workload_partition():
     sys.path.insert(0, ROOT)
     bench = importlib.import_module("bench")
+    c3 = dict(bench.CONFIGS["c3"], name="c3")
     for world in (1, 2, 3, 8):
-        shapes = [bench.workload(512, "f64", world, r, "strong")["rank_shape"]
-                  for r in range(world)]
-        assert sum(s[0] for s in shapes) == 512
-        assert all(s[1:] == (512, 512) for s in shapes)
-    w = bench.workload(1024, "f32", 8, 3, "weak", nx=1024)
+        ws = [bench.workload(c3, world, r) for r in range(world)]
+        assert sum(w["rank_shape"][0] for w in ws) == 512
+        assert all(w["rank_shape"][1:] == (512, 512) for w in ws)
+        assert [w["x_start"] for w in ws] == list(np.cumsum([0] + [w["rank_shape"][0]
+                                                                  for w in ws[:-1]]))
+    c5 = dict(bench.CONFIGS["c5"], name="c5")
+    w = bench.workload(c5, 8, 3)
     assert w["grid_shape"] == (1024, 1024, 1024) and w["rank_shape"] == (128, 1024, 1024)
-    assert w["np_dtype"] == np.float32
-    f, d = bench.initial_fields(bench.workload(16, "f64", 1, 0, "strong"))
+    assert w["np_dtype"] == np.float32 and w["dx"] == (5 / 1024,) * 3
+    c4 = dict(bench.CONFIGS["c4"], name="c4")
+    w4 = bench.workload(c4, 8, 0)
+    assert w4["gw"] and w4["nscalars"] == 2 and w4["rank_shape"] == (64, 512, 512)
+    assert bench.config_dict(c4, w4, 8) == bench.config_dict(c4, bench.workload(c4, 8, 5), 8)
+    small = dict(c3, grid=(16, 16, 16))
+    f, d = bench.initial_fields(bench.workload(small, 1, 0))
     assert f.shape == (1, 20, 20, 20) and abs(f.mean() - 0.193) < 1e-5
+    # the potential callable and its monomial table describe the same function
+    V = bench.potential_callable(w4)
+    x = [0.3, -0.7]
+    ref = sum(c * x[0]**p[0] * x[1]**p[1] for c, p in bench.potential_terms(w4))
+    assert abs(V(x) - ref) < 1e-12 * abs(ref)
 
 
 def test_reference_arm_prints_contract_line():
@@ -62,6 +75,12 @@ def test_reference_arm_prints_contract_line():
         assert key in line
     assert line["impl"] == "reference" and line["cpu_baseline"]["kind"] == "port"
     assert line["value"] > 0 and line["e2e"]["h2d_bytes_per_step"] == 0
+    assert line["steps"] == 2 and line["config"]["grid_shape"] == [32, 32, 32]
+    # both arms describe the workload with the same keys
+    sys.path.insert(0, ROOT)
+    bench = importlib.import_module("bench")
+    cfg = dict(bench.CONFIGS["c3"], name="c3", grid=(32, 32, 32))
+    assert line["config"] == bench.config_dict(cfg, bench.workload(cfg, 1, 0), 1)
 
 
 # ---------------------------------------------------------------------------------------
