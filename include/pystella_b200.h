@@ -279,6 +279,13 @@ int psb_finite_difference(const void* fx, void* lap, void* pdx, void* pdy, void*
                           int dtype, int64_t Nx, int64_t Ny, int64_t Nz,
                           int h, int halo, const double dx[3], int accumulate,
                           void* stream);
+/* The same with an explicit kernel choice: variant 0 = auto (the TMA pipeline of
+ * csrc/fd_ws.cuh for lap / grad / lap+grad with even radii and TMA-able layouts, else the
+ * generic tile kernel), 1 = generic tile kernel. */
+int psb_finite_difference_v(const void* fx, void* lap, void* pdx, void* pdy, void* pdz,
+                            int dtype, int64_t Nx, int64_t Ny, int64_t Nz,
+                            int h, int halo, const double dx[3], int accumulate,
+                            int variant, void* stream);
 
 /* ------------------------------------------------------------------------
  * Periodic halo fill of one rank-local padded array, order z -> x -> y, each
@@ -326,6 +333,8 @@ typedef struct psb_reduce_args {
   int32_t flags[PSB_MAX_RED_OUTPUTS];
   double* partials;              /* workspace: psb_reduce_workspace_doubles() */
   double* out;                   /* noutputs doubles (device)                 */
+  int32_t tune_variant;          /* 0 = auto; 1 = generic (scalar-load) kernel */
+  int32_t reserved0;
 } psb_reduce_args;
 
 int64_t psb_reduce_workspace_doubles(int noutputs);

@@ -54,6 +54,9 @@ int64_t psb_jit_compile_ex(const char* source, const char* kernel_name,
                            const char* const* options, int noptions,
                            const char* const* header_names,
                            const char* const* header_sources, int nheaders);
+/* Register an already compiled cubin (e.g. from the on-disk cache the Python layer keeps,
+ * written with psb_jit_write_cubin) whose kernel has the lowered name `symbol`. */
+int64_t psb_jit_load_cubin(const void* cubin, size_t size, const char* symbol);
 /* Lowered (mangled) symbol name of the compiled kernel. */
 const char* psb_jit_kernel_symbol(int64_t handle);
 /* Number of registers per thread / static shared memory of the compiled kernel are not

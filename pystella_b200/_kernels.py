@@ -140,7 +140,7 @@ def scalar_stage(*, fused, f_in, f_out, dfdt, kf, kdfdt, lap_f=None, h, dx=(1., 
 
 
 def finite_difference(fx, *, lap=None, pdx=None, pdy=None, pdz=None, h, halo=None,
-                      dx, accumulate=False, queue=None, strict=False):
+                      dx, accumulate=False, queue=None, strict=False, variant=0):
     lib = _lib.load(strict)
     _lib.require_cuda_tensor(fx, "fx")
     halo = h if halo is None else halo
@@ -154,10 +154,10 @@ def finite_difference(fx, *, lap=None, pdx=None, pdy=None, pdz=None, h, halo=Non
                 f"{name} has shape {tuple(t.shape)}/{t.dtype}; expected {(Nx, Ny, Nz)}/"
                 f"{fx.dtype}")
     dxa = (C.c_double * 3)(*[float(d) for d in dx])
-    rc = lib.psb_finite_difference(_ptr(fx), _ptr(lap), _ptr(pdx), _ptr(pdy), _ptr(pdz),
-                                   _lib.torch_dtype_code(fx), Nx, Ny, Nz, h, halo,
-                                   C.byref(dxa), int(accumulate),
-                                   _lib.stream_ptr(queue))
+    rc = lib.psb_finite_difference_v(_ptr(fx), _ptr(lap), _ptr(pdx), _ptr(pdy), _ptr(pdz),
+                                     _lib.torch_dtype_code(fx), Nx, Ny, Nz, h, halo,
+                                     C.byref(dxa), int(accumulate), int(variant),
+                                     _lib.stream_ptr(queue))
     _lib.check(lib, rc, "psb_finite_difference")
 
 
@@ -209,7 +209,8 @@ def remove_halos(padded, unpadded, halo_shape, queue=None, restore=False, strict
 _reduce_ws = {}
 
 
-def reduce_poly(arrays, halos, terms, ops, flags, shape, queue=None, strict=False):
+def reduce_poly(arrays, halos, terms, ops, flags, shape, queue=None, strict=False,
+                variant=0):
     """
     ``arrays``: list of tensors; ``halos``: their padding; ``terms``: list of
     ``(output, coef, powers)``; ``ops``: per-output op code (0 sum, 1 max, 2 min).
@@ -246,6 +247,7 @@ def reduce_poly(arrays, halos, terms, ops, flags, shape, queue=None, strict=Fals
         n = lib.psb_reduce_workspace_doubles(_lib.MAX_RED_OUTPUTS)
         _reduce_ws[key] = torch.empty(n, dtype=torch.float64, device=dev)
     out = torch.empty(len(ops), dtype=torch.float64, device=dev)
+    args.tune_variant = int(variant)
     args.partials = _reduce_ws[key].data_ptr()
     args.out = out.data_ptr()
     rc = lib.psb_reduce(C.byref(args), _lib.stream_ptr(queue))

@@ -127,6 +127,7 @@ class ReduceArgs(C.Structure):
         ("op", c_int32 * MAX_RED_OUTPUTS),
         ("flags", c_int32 * MAX_RED_OUTPUTS),
         ("partials", c_void_p), ("out", c_void_p),
+        ("tune_variant", c_int32), ("reserved0", c_int32),
     ]
 
 
@@ -158,6 +159,10 @@ SYMBOLS = {
                                                         c_int, c_int,
                                                         C.POINTER(c_double * 3), c_int,
                                                         c_void_p]),
+    "psb_finite_difference_v": (c_int, [c_void_p] * 5 + [c_int, c_int64, c_int64, c_int64,
+                                                          c_int, c_int,
+                                                          C.POINTER(c_double * 3), c_int,
+                                                          c_int, c_void_p]),
     "psb_halo_wrap": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64,
                               c_int, c_int, c_int, c_int, c_void_p]),
     "psb_halo_pack": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_int64,

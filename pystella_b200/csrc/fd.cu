@@ -18,7 +18,7 @@ template <typename T> struct FDParams {
   T* pdx;
   T* pdy;
   T* pdz;
-  int Nx, Ny, Nz, halo, xchunk;
+  int Nx, Ny, Nz, halo, xchunk, variant;
   T inv_dx2[3];
   T inv_dx[3];
 };
@@ -127,18 +127,10 @@ __global__ void __launch_bounds__(BY* BZ)
 #include "fd_ws.cuh"
 namespace psb {
 
-static bool fd_pipeline_enabled() {
-  static const bool on = [] {
-    const char* e = getenv("PSB_FD_PIPELINE");
-    return e != nullptr && e[0] == '1';
-  }();
-  return on;
-}
-
 template <typename T, int H, int MODE, bool ACC>
 static int launch_fd(const FDParams<T>& p, cudaStream_t stream) {
   if constexpr (!ACC && (MODE == 1 || MODE == 14 || MODE == 15)) {
-    if (fd_pipeline_enabled()) {
+    if (p.variant != 1) {
       const int rc = launch_fd_ws<T, H, MODE>(p, stream);
       if (rc >= 0) return rc;
     }
@@ -181,8 +173,9 @@ static int dispatch_mode(const FDParams<T>& p, int mode, bool acc, cudaStream_t 
 template <typename T>
 static int fd_typed(const void* fx, void* lap, void* pdx, void* pdy, void* pdz,
                     int64_t Nx, int64_t Ny, int64_t Nz, int h, int halo,
-                    const double dx[3], int accumulate, cudaStream_t s) {
+                    const double dx[3], int accumulate, int variant, cudaStream_t s) {
   FDParams<T> p;
+  p.variant = variant;
   p.fx = static_cast<const T*>(fx);
   p.lap = static_cast<T*>(lap);
   p.pdx = static_cast<T*>(pdx);
@@ -210,20 +203,32 @@ static int fd_typed(const void* fx, void* lap, void* pdx, void* pdy, void* pdz,
 
 }  // namespace psb
 
-extern "C" int psb_finite_difference(const void* fx, void* lap, void* pdx, void* pdy,
-                                     void* pdz, int dtype, int64_t Nx, int64_t Ny,
-                                     int64_t Nz, int h, int halo, const double dx[3],
-                                     int accumulate, void* stream) {
+extern "C" int psb_finite_difference_v(const void* fx, void* lap, void* pdx, void* pdy,
+                                       void* pdz, int dtype, int64_t Nx, int64_t Ny,
+                                       int64_t Nz, int h, int halo, const double dx[3],
+                                       int accumulate, int variant, void* stream) {
   using namespace psb;
   PSB_REQUIRE(fx != nullptr, "psb_finite_difference: null input");
   PSB_REQUIRE(Nx > 0 && Ny > 0 && Nz > 0, "psb_finite_difference: empty grid");
   PSB_REQUIRE(halo >= h, "psb_finite_difference: halo %d smaller than stencil radius %d",
               halo, h);
+  PSB_REQUIRE(variant == 0 || variant == 1, "psb_finite_difference: unknown variant %d",
+              variant);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (dtype == PSB_F64)
-    return fd_typed<double>(fx, lap, pdx, pdy, pdz, Nx, Ny, Nz, h, halo, dx, accumulate, s);
+    return fd_typed<double>(fx, lap, pdx, pdy, pdz, Nx, Ny, Nz, h, halo, dx, accumulate,
+                            variant, s);
   if (dtype == PSB_F32)
-    return fd_typed<float>(fx, lap, pdx, pdy, pdz, Nx, Ny, Nz, h, halo, dx, accumulate, s);
+    return fd_typed<float>(fx, lap, pdx, pdy, pdz, Nx, Ny, Nz, h, halo, dx, accumulate,
+                           variant, s);
   set_error("psb_finite_difference: unknown dtype %d", dtype);
   return 1;
+}
+
+extern "C" int psb_finite_difference(const void* fx, void* lap, void* pdx, void* pdy,
+                                     void* pdz, int dtype, int64_t Nx, int64_t Ny,
+                                     int64_t Nz, int h, int halo, const double dx[3],
+                                     int accumulate, void* stream) {
+  return psb_finite_difference_v(fx, lap, pdx, pdy, pdz, dtype, Nx, Ny, Nz, h, halo, dx,
+                                 accumulate, 0, stream);
 }

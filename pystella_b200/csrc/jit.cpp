@@ -116,6 +116,21 @@ extern "C" int64_t psb_jit_compile(const char* source, const char* kernel_name,
   return (int64_t)g_entries.size();
 }
 
+extern "C" int64_t psb_jit_load_cubin(const void* cubin, size_t size, const char* symbol) {
+  g_log.clear();
+  if (!cubin || size == 0 || !symbol) {
+    g_log = "psb_jit_load_cubin: null cubin / symbol";
+    return 0;
+  }
+  Entry e;
+  e.cubin.assign(static_cast<const char*>(cubin), size);
+  e.name = symbol;
+  e.live = true;
+  std::lock_guard<std::mutex> lock(g_mutex);
+  g_entries.push_back(std::move(e));
+  return (int64_t)g_entries.size();
+}
+
 extern "C" int64_t psb_jit_compile_ex(const char* source, const char* kernel_name,
                                       const char* name_expression, const char* arch,
                                       const char* const* options, int noptions,

@@ -27,6 +27,7 @@ template <typename T> struct RedParams {
   int flags[PSB_MAX_RED_OUTPUTS];
   double* partials;
   double* out;
+  int variant;   // 0 = auto (vectorised kernel when the layout allows), 1 = generic kernel
 };
 
 __device__ __forceinline__ double red_identity(int op) {
@@ -109,10 +110,13 @@ __global__ void __launch_bounds__(RED_THREADS)
   }
 }
 
-// EXPERIMENTAL (opt-in: PSB_REDUCE_V2=1; written after round 1's GPU budget was spent):
-// the same reduction with two sites per thread as one vector load per array and four
-// row segments in flight before the arithmetic starts (memory-level parallelism x8 per
-// thread).  Needs even Nz and halos and 2-element aligned rows; otherwise reduce_kernel.
+// Vectorised variant (default when the layout allows): every thread owns U row segments of
+// two sites each (one 16-byte / 8-byte vector load per array and segment, all issued before
+// the arithmetic starts), and the run-time loops over terms and powers are OUTSIDE the loop
+// over those 2U sites, so their overhead (uniform loads of coefficients and powers, branches)
+// is paid once per 2U sites.  Per site the association is the oracle's:
+// term = ((coef * a) * a) ..., value = value + term in term order.  Needs even Nz and halos
+// and 2-element aligned rows; otherwise reduce_kernel.
 constexpr int RED_V2_UNROLL = 4;
 
 template <typename T, int NARR, int NOUT>
@@ -124,7 +128,7 @@ __global__ void __launch_bounds__(RED_THREADS)
 
   const int64_t rows = (int64_t)p.Nx * p.Ny;
   const int lane_z = threadIdx.x % 64, sub = threadIdx.x / 64;
-  constexpr int U = RED_V2_UNROLL;
+  constexpr int U = RED_V2_UNROLL, S = 2 * U;
   for (int64_t row = (int64_t)blockIdx.x * 4 + sub; row < rows;
        row += (int64_t)gridDim.x * 4) {
     const int i = (int)(row / p.Ny), j = (int)(row % p.Ny);
@@ -138,45 +142,67 @@ __global__ void __launch_bounds__(RED_THREADS)
                   : p.arrays[0];
     }
     for (int k0 = lane_z * 2; k0 < p.Nz; k0 += 64 * 2 * U) {
-      Vec<T, 2> raw[U][NARR];
+      double v[NARR][S];
+      bool live[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int k = k0 + u * 128;
+        live[u] = k < p.Nz;
 #pragma unroll
         for (int m = 0; m < NARR; ++m) {
-          if (k < p.Nz) {
-            raw[u][m] = ld_vec<T, 2>(rp[m] + k);
+          Vec<T, 2> raw;
+          if (live[u]) {
+            raw = ld_vec<T, 2>(rp[m] + k);
           } else {
-            raw[u][m].v[0] = raw[u][m].v[1] = (T)0;
+            raw.v[0] = raw.v[1] = (T)0;
           }
+          v[m][2 * u] = (double)raw.v[0];
+          v[m][2 * u + 1] = (double)raw.v[1];
         }
       }
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        if (k0 + u * 128 >= p.Nz) continue;
+      for (int r = 0; r < NOUT; ++r) {
+        if (r < p.noutputs) {
+          double val[S];
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          double v[NARR];
+          for (int s = 0; s < S; ++s) val[s] = 0.0;
+          for (int t = p.term_begin[r]; t < p.term_begin[r + 1]; ++t) {
+            double term[S];
+            const double c = p.coef[t];
 #pragma unroll
-          for (int m = 0; m < NARR; ++m) v[m] = (double)raw[u][m].v[e];
+            for (int s = 0; s < S; ++s) term[s] = c;
 #pragma unroll
-          for (int r = 0; r < NOUT; ++r) {
-            if (r < p.noutputs) {
-              double val = 0.0;
-              for (int t = p.term_begin[r]; t < p.term_begin[r + 1]; ++t) {
-                double term = p.coef[t];
+            for (int m = 0; m < NARR; ++m) {
+              const int pw = p.power[t][m];
+              for (int e = 0; e < pw; ++e) {
 #pragma unroll
-                for (int m = 0; m < NARR; ++m) {
-                  const int pw = p.power[t][m];
-                  if (pw >= 1) term *= v[m];
-                  if (pw >= 2) term *= v[m];
-                  for (int x = 2; x < pw; ++x) term *= v[m];
-                }
-                val += term;
+                for (int s = 0; s < S; ++s) term[s] *= v[m][s];
               }
-              if (p.flags[r] & 1) val = fabs(val);
-              const int op = p.op[r];
-              acc[r] = op == 0 ? acc[r] + val : red_combine(op, acc[r], val);
+            }
+#pragma unroll
+            for (int s = 0; s < S; ++s) val[s] += term[s];
+          }
+          const bool take_abs = (p.flags[r] & 1) != 0;
+          const int op = p.op[r];
+          if (op == 0) {
+            double part = 0.0;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+              if (live[u]) {
+                const double a0 = take_abs ? fabs(val[2 * u]) : val[2 * u];
+                const double a1 = take_abs ? fabs(val[2 * u + 1]) : val[2 * u + 1];
+                part += a0 + a1;
+              }
+            }
+            acc[r] += part;
+          } else {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+              if (live[u]) {
+                const double a0 = take_abs ? fabs(val[2 * u]) : val[2 * u];
+                const double a1 = take_abs ? fabs(val[2 * u + 1]) : val[2 * u + 1];
+                acc[r] = red_combine(op, acc[r], red_combine(op, a0, a1));
+              }
             }
           }
         }
@@ -206,14 +232,6 @@ __global__ void __launch_bounds__(RED_THREADS)
   }
 }
 
-static bool reduce_v2_enabled() {
-  static const bool on = [] {
-    const char* e = getenv("PSB_REDUCE_V2");
-    return e != nullptr && e[0] == '1';
-  }();
-  return on;
-}
-
 template <typename T> static bool reduce_v2_layout_ok(const RedParams<T>& p) {
   if (p.Nz % 2) return false;
   for (int m = 0; m < p.narrays; ++m) {
@@ -226,7 +244,7 @@ template <typename T> static bool reduce_v2_layout_ok(const RedParams<T>& p) {
 template <typename T, int NARR>
 static void launch_reduce_nout(const RedParams<T>& p, int nblocks, cudaStream_t s) {
   if constexpr (NARR <= 4) {
-    if (reduce_v2_enabled() && reduce_v2_layout_ok(p)) {
+    if (p.variant != 1 && reduce_v2_layout_ok(p)) {
       if (p.noutputs <= 2)
         reduce_kernel_v2<T, NARR, 2><<<nblocks, RED_THREADS, 0, s>>>(p);
       else if (p.noutputs <= 4)
@@ -324,6 +342,7 @@ static int reduce_typed(const psb_reduce_args* a, cudaStream_t s) {
   p.nterms = nt;
   p.partials = a->partials;
   p.out = a->out;
+  p.variant = a->tune_variant;
 
   const int64_t rows = a->Nx * a->Ny;
   int nblocks = (int)((rows + 3) / 4);

@@ -382,10 +382,9 @@ constexpr int tws_pick_tz(int es, int H, int NS, int BY, int P, int VEC) {
   return 16;
 }
 
-template <typename T, int H, int NS, int VEC>
+template <typename T, int H, int NS, int VEC, int BY = 4, int P = 2, int MINB = 1>
 static int launch_tensor_ws(const psb_tensor_fused_args* a, cudaStream_t stream,
                             int64_t* count) {
-  constexpr int BY = 4, P = 2;
   constexpr int TZ = tws_pick_tz((int)sizeof(T), H, NS, BY, P, VEC);
   using C = TwsCfg<T, H, NS, BY, TZ, P, VEC>;
   using B = typename C::B;
@@ -456,7 +455,7 @@ static int launch_tensor_ws(const psb_tensor_fused_args* a, cudaStream_t stream,
     return rc;
   fill_tail(p.tail, a->tail, nullptr);
   dim3 block(C::THREADS, 1, 1);
-  auto kern = tensor_stage_ws_kernel<T, H, NS, BY, TZ, P, 1, VEC>;
+  auto kern = tensor_stage_ws_kernel<T, H, NS, BY, TZ, P, MINB, VEC>;
   PSB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       C::SMEM_BYTES));
   kern<<<grid, block, C::SMEM_BYTES, stream>>>(p, mh, ms, md, mkh, mkd);
@@ -467,6 +466,16 @@ static int launch_tensor_ws(const psb_tensor_fused_args* a, cudaStream_t stream,
 template <typename T, int H>
 static int tensor_fused_ns(const psb_tensor_fused_args* a, cudaStream_t s, int64_t* count) {
   // 16-byte shared-memory vectors: 2 doubles, or 4 floats when the rows allow it
+  if constexpr (H == 2) {
+    // development variants of the headline radius (tile height, pipeline depth, CTAs/SM)
+    constexpr int VV = sizeof(T) == 4 ? 4 : 2;
+    if (a->nscalars == 2 && (sizeof(T) == 8 || a->Nz % 4 == 0)) {
+      if (a->tune_variant == 2) return launch_tensor_ws<T, H, 2, VV, 4, 1, 3>(a, s, count);
+      if (a->tune_variant == 3) return launch_tensor_ws<T, H, 2, VV, 8, 1, 2>(a, s, count);
+      if (a->tune_variant == 4) return launch_tensor_ws<T, H, 2, VV, 8, 2, 1>(a, s, count);
+      if (a->tune_variant == 5) return launch_tensor_ws<T, H, 2, VV, 4, 1, 2>(a, s, count);
+    }
+  }
   if constexpr (sizeof(T) == 4) {
     if (a->Nz % 4 == 0 && a->tune_variant != 1) {
       switch (a->nscalars) {

@@ -135,7 +135,7 @@ class FiniteDifferencer:
     def __init__(self, decomp, halo_shape, dx, stream=False, rank_shape=None,
                  device=None, first_stencil=None, second_stencil=None,
                  gradlap_lsize=None, grad_lsize=None, lap_lsize=None,
-                 strict_fp=False, jit=None, dtype="float64"):
+                 strict_fp=False, jit=None, dtype="float64", tune=None):
         if not isinstance(halo_shape, (int, np.integer)):
             raise NotImplementedError("halo_shape must currently be an int")
         self.decomp = decomp
@@ -143,6 +143,8 @@ class FiniteDifferencer:
         self.dx = tuple(float(d) for d in dx)
         self.rank_shape = rank_shape
         self.strict_fp = strict_fp
+        #: kernel choice of psb_finite_difference_v: {"variant": 0 auto | 1 generic tile kernel}
+        self.tune = dict(tune or {})
         first = first_stencil or FirstCenteredDifference(self.halo_shape)
         second = second_stencil or SecondCenteredDifference(self.halo_shape)
         self.first_stencil, self.second_stencil = first, second
@@ -157,9 +159,9 @@ class FiniteDifferencer:
             from pystella_b200.step import jit_enabled
             if not jit_enabled(jit):
                 raise NotImplementedError(
-                    "custom stencils need run-time generated kernels (experimental: pass "
-                    "jit=True or set PSB_JIT=1); the hand-written kernels provide the "
-                    "centred differences of radius 1..4")
+                    "custom stencils need the run-time generated kernels, which were "
+                    "switched off (jit=False / PSB_JIT=0); the hand-written kernels provide "
+                    "the centred differences of radius 1..4")
             self._generated = self._generate_custom(first, second, dtype)
             self.h = self.halo_shape
             return
@@ -202,7 +204,8 @@ class FiniteDifferencer:
             self._generated[key](queue, fx=fx, **{n: outs[n] for n in key})
             return
         _kernels.finite_difference(fx, h=self.h, halo=self.halo_shape, dx=self.dx,
-                                   queue=queue, strict=self.strict_fp, **outs)
+                                   queue=queue, strict=self.strict_fp,
+                                   variant=self.tune.get("variant", 0), **outs)
 
     def __call__(self, queue, fx, *, lap=None, pdx=None, pdy=None, pdz=None,
                  grd=None, allocator=None):

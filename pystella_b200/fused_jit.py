@@ -208,15 +208,26 @@ class GeneratedFusedStage:
                     b"-I" + os.path.join(ROOT, "include").encode()]
             hnames = [b"stdint.h", b"stddef.h"]
             hsrc = [b"", b""]
-            handle = lib.psb_jit_compile_ex(
-                self.source.encode(), None, self.name_expression(plan).encode(), b"sm_100a",
-                (C.c_char_p * len(opts))(*opts), len(opts),
-                (C.c_char_p * 2)(*hnames), (C.c_char_p * 2)(*hsrc), 2)
-            if handle == 0:
-                raise _lib.PsbError(
-                    "NVRTC compilation of the fused stage with a generated right-hand side "
-                    "failed:\n" + lib.psb_jit_last_log().decode(errors="replace")
-                    + "\n--- functor ---\n" + self.source)
+            name_expr = self.name_expression(plan)
+
+            def build():
+                handle = lib.psb_jit_compile_ex(
+                    self.source.encode(), None, name_expr.encode(), b"sm_100a",
+                    (C.c_char_p * len(opts))(*opts), len(opts),
+                    (C.c_char_p * 2)(*hnames), (C.c_char_p * 2)(*hsrc), 2)
+                if handle == 0:
+                    raise _lib.PsbError(
+                        "NVRTC compilation of the fused stage with a generated right-hand "
+                        "side failed:\n" + lib.psb_jit_last_log().decode(errors="replace")
+                        + "\n--- functor ---\n" + self.source)
+                return handle
+            csrc = os.path.join(HERE, "csrc")
+            headers = [os.path.join(csrc, n) for n in ("fused_stage_ws.cuh",
+                                                       "fused_stage_impl.cuh",
+                                                       "stage_tail.cuh", "common.cuh")]
+            headers.append(os.path.join(ROOT, "include", "pystella_b200.h"))
+            handle = JitLibrary.cached(self.source, name_expr, [o.decode() for o in opts],
+                                       headers, build)
             self._handles[key] = handle
         return self._handles[key]
 

@@ -56,6 +56,8 @@ class Reduction:
             raise NotImplementedError
 
         self.grid_size = kwargs.pop("grid_size", None)
+        #: kernel choice of psb_reduce: {"variant": 0 auto | 1 generic scalar-load kernel}
+        self.tune = dict(kwargs.pop("tune", None) or {})
         self.callback = kwargs.pop("callback", lambda x: x)
         self.halo_shape = kwargs.pop("halo_shape", None)
         self.rank_shape = kwargs.pop("rank_shape", None)
@@ -273,7 +275,7 @@ class Reduction:
             sel_terms = [(r - start, c, p) for r, c, p in terms if start <= r < stop]
             out[start:stop] = _kernels.reduce_poly(
                 arrays, halos, sel_terms, ops[start:stop], flags[start:stop], shape,
-                queue=queue, strict=self.strict_fp)
+                queue=queue, strict=self.strict_fp, variant=self.tune.get("variant", 0))
             start = stop
         return out
 

@@ -95,6 +95,19 @@ if __name__ == "__main__":
     which = sys.argv[1:] or ["scalar", "chunk", "store", "gw"]
     F64, F32 = torch.float64, torch.float32
     N5 = (512,) * 3
+    if "gwvar" in which:
+        for var in (0, 2, 3, 4, 5):
+            gw_case(512, F32, tune={"gw_variant": var})
+        gw_case(512, F32, tune={"gw_variant": 2, "gw_xchunk": 32})
+        gw_case(512, F32, tune={"gw_variant": 3, "gw_xchunk": 32})
+        gw_case(256, F64, tune={"gw_variant": 2})
+        scalar_case(N5, F32, 1, True, nscalars=2, tune={"variant": 15})
+        scalar_case((256,) * 3, F64, 1, True, nscalars=2)
+    if "gwprof" in which:
+        gw_case(384, F32)
+    if "f32prof" in which:
+        scalar_case(N5, F32, 1, True)
+        scalar_case(N5, F64, 0, True)
     if "ab" in which:      # A/B of library builds (PSB_DEV_LIB): the cases that moved
         for dt_ in (F64, F32):
             for stage in (1, 0):

@@ -263,8 +263,8 @@ def test_custom_stencil_differencer_kernels_on_host():
     dx = (0.1, 0.2, 0.3)
     decomp = ps.DomainDecomposition((1, 1, 1), h, N)
     with pytest.raises(NotImplementedError, match="custom stencils"):
-        ps.FiniteDifferencer(decomp, h, dx, first_stencil=_OneSided())
-    fd = ps.FiniteDifferencer(decomp, h, dx, first_stencil=_OneSided(), jit=True)
+        ps.FiniteDifferencer(decomp, h, dx, first_stencil=_OneSided(), jit=False)
+    fd = ps.FiniteDifferencer(decomp, h, dx, first_stencil=_OneSided())   # default: generated
     yy = rng.random(tuple(n + 2 * h for n in N))
 
     gm = fd._generated[("lap", "pdx", "pdy", "pdz")]
@@ -335,8 +335,8 @@ def test_generated_reducers_on_host():
     decomp = ps.DomainDecomposition((1, 1, 1), h, N)
     reducers = {"c": [var("cos")(f) * g / a, (f**0.5, "max")], "p": [f * g]}
     with pytest.raises(NotImplementedError):
-        ps.Reduction(decomp, reducers, halo_shape=h)
-    red = ps.Reduction(decomp, reducers, halo_shape=h, jit=True)
+        ps.Reduction(decomp, reducers, halo_shape=h, jit=False)
+    red = ps.Reduction(decomp, reducers, halo_shape=h)   # default: generated evaluation
     assert red._scratch_names == ["_psb_reducer_0", "_psb_reducer_1"]
     # the fold sees: scratch_0 (avg), scratch_1 (max), f*g (avg)
     assert [sorted(ref.name for mono in poly for ref, _ in mono) for poly in red._polys] == [
@@ -366,10 +366,11 @@ def test_stencil_map_with_raw_subscripts_on_host(h, cls):
                              + x[i + h, j + h, k + h + h] + x[i - h + h, j + h, k + h]
                              + x[i + h, j - h + h, k + h] + x[i + h, j + h, k - h + h])}
     with pytest.raises(NotImplementedError, match="jit"):
-        getattr(ps, cls)(map_dict, h, prefetch_args=["x"])
+        getattr(ps, cls)(map_dict, h, prefetch_args=["x"], jit=False)
     with pytest.raises(TypeError):
-        ps.Stencil(map_dict, jit=True)
-    stencil_map = getattr(ps, cls)(map_dict, h, prefetch_args=["x"], jit=True)
+        ps.Stencil(map_dict)
+    # the reference's call, no flag (test/test_stencil.py:37-90)
+    stencil_map = getattr(ps, cls)(map_dict, h, prefetch_args=["x"])
     assert stencil_map.prefetch_args == ["x"]
     ksrc = stencil_map._generic.ksrc
     N = (6, 5, 7)

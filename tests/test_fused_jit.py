@@ -43,11 +43,11 @@ def test_recognition_and_refusals():
     with pytest.raises(NotImplementedError):
         fused_jit.recognise_general_system({g: g})
 
-    # stepper wiring: opt-in, fused only
+    # stepper wiring: the default fallback of fused steppers (jit=False switches it off)
     kw = dict(halo_shape=2, dt=0.01, dx=(0.1,) * 3, MapKernel=ps.FusedStencilStage)
     with pytest.raises(NotImplementedError):
-        ps.LowStorageRK54(sector, **kw).systems
-    st = ps.LowStorageRK54(sector, jit=True, **kw)
+        ps.LowStorageRK54(sector, jit=False, **kw).systems
+    st = ps.LowStorageRK54(sector, **kw)
     assert isinstance(st.systems[0], fused_jit.GeneralScalarSystem)
     assert st.systems[0].potential is not None
     with pytest.raises(NotImplementedError):

@@ -152,7 +152,7 @@ def test_generic_dict_with_friction_matches_sector():
 def test_unsupported_systems_fail_loudly():
     f_ = ps.DynamicField("f", offset="h")
     bad = {f_: f_.dot, f_.dot: f_.lap / (1 + f_)}
-    st = ps.LowStorageRK54(bad, halo_shape=1, dt=0.1)
+    st = ps.LowStorageRK54(bad, halo_shape=1, dt=0.1, jit=False)
     t = torch.zeros(6, 6, 6, dtype=torch.float64, device="cuda")
     with pytest.raises(NotImplementedError):
         st(0, f=t, dfdt=t.clone(), lap_f=torch.zeros(4, 4, 4, dtype=torch.float64,

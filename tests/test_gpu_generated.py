@@ -358,7 +358,8 @@ def _case_aligned(case):
 @pytest.mark.parametrize("dtype", ["float64", "float32"])
 @pytest.mark.parametrize("h", [2, 4])
 def test_finite_difference_pipeline(dtype, h):
-    """PSB_FD_PIPELINE=1: lap / grad / lap+grad through the TMA pipeline == the oracle."""
+    """lap / grad / lap+grad through the TMA pipeline (the default for even radii) and
+    through the generic tile kernel (tune variant 1) == the oracle."""
     _in_subprocess("fd_pipeline", dtype, h)
 
 
@@ -368,33 +369,39 @@ def _case_fd_pipeline(dtype, h):
     N = (20, 12, 136)
     dx = (0.1, 0.2, 0.3)
     decomp = ps.DomainDecomposition((1, 1, 1), h, N)
-    derivs = ps.FiniteDifferencer(decomp, h, dx)
     fh = rng.random((2,) + tuple(n + 2 * h for n in N)).astype(dtype)
-    fx = to_dev(fh)
     tdt = getattr(torch, dtype)
-    lap = torch.full((2,) + N, float("nan"), dtype=tdt, device="cuda")
-    grd = torch.full((2, 3) + N, float("nan"), dtype=tdt, device="cuda")
-    lap2 = torch.full_like(lap, float("nan"))
-    grd2 = torch.full_like(grd, float("nan"))
-    derivs(None, fx, lap=lap, grd=grd)          # MODE 15
-    derivs(None, fx, lap=lap2)                  # MODE 1
-    derivs(None, fx, grd=grd2)                  # MODE 14
-    torch.cuda.synchronize()
-    tol = 1e-12 if dtype == "float64" else 2e-5
-    f64 = fx.cpu().numpy().astype(np.float64)
-    for n in range(2):
-        want_lap = O.laplacian(f64[n], h, dx)
-        want_grd = O.gradient(f64[n], h, dx)
-        for got in (lap[n], lap2[n]):
-            assert scale_err(got.cpu().numpy(), want_lap) < tol
-        for got in (grd[n], grd2[n]):
-            for mu in range(3):
-                assert scale_err(got[mu].cpu().numpy(), want_grd[mu]) < tol
+    results = []
+    for variant in (0, 1):
+        derivs = ps.FiniteDifferencer(decomp, h, dx, tune={"variant": variant})
+        fx = to_dev(fh)
+        lap = torch.full((2,) + N, float("nan"), dtype=tdt, device="cuda")
+        grd = torch.full((2, 3) + N, float("nan"), dtype=tdt, device="cuda")
+        lap2 = torch.full_like(lap, float("nan"))
+        grd2 = torch.full_like(grd, float("nan"))
+        derivs(None, fx, lap=lap, grd=grd)          # MODE 15
+        derivs(None, fx, lap=lap2)                  # MODE 1
+        derivs(None, fx, grd=grd2)                  # MODE 14
+        torch.cuda.synchronize()
+        tol = 1e-12 if dtype == "float64" else 2e-5
+        f64 = fx.cpu().numpy().astype(np.float64)
+        for n in range(2):
+            want_lap = O.laplacian(f64[n], h, dx)
+            want_grd = O.gradient(f64[n], h, dx)
+            for got in (lap[n], lap2[n]):
+                assert scale_err(got.cpu().numpy(), want_lap) < tol
+            for got in (grd[n], grd2[n]):
+                for mu in range(3):
+                    assert scale_err(got[mu].cpu().numpy(), want_grd[mu]) < tol
+        results.append((lap.cpu().numpy(), grd.cpu().numpy()))
+    # same term order in both kernels
+    assert scale_err(results[0][0], results[1][0]) < (1e-14 if dtype == "float64" else 1e-6)
 
 
 @pytest.mark.parametrize("dtype", ["float64", "float32"])
 def test_reduce_v2(dtype):
-    """PSB_REDUCE_V2=1 (vector loads, 8 sites in flight per thread) == numpy."""
+    """The vectorised reduction (default: vector loads, 8 sites in flight per thread) and the
+    generic kernel (tune variant 1) == numpy."""
     _in_subprocess("reduce_v2", dtype)
 
 
@@ -403,21 +410,23 @@ def _case_reduce_v2(dtype):
     N, h = (12, 10, 260), 2
     decomp = ps.DomainDecomposition((1, 1, 1), h, N)
     sector = ps.ScalarSector(2, potential=lambda f: f[0]**2 / 2 + f[0]**2 * f[1]**2 / 2)
-    red = ps.Reduction(decomp, sector, halo_shape=h, grid_size=float(np.prod(N)))
     pad = tuple(n + 2 * h for n in N)
     f = rng.random((2,) + pad).astype(dtype)
     d = rng.random((2,) + pad).astype(dtype)
     lap = rng.random((2,) + N).astype(dtype)
-    out = red(None, f=to_dev(f), dfdt=to_dev(d), lap_f=to_dev(lap), a=np.array(1.3))
     fi = f[:, h:-h, h:-h, h:-h].astype(np.float64)
     di = d[:, h:-h, h:-h, h:-h].astype(np.float64)
     tol = 1e-12 if dtype == "float64" else 1e-5
     want_kin = [np.mean(di[n]**2) / 2 / 1.3**2 for n in range(2)]
     want_grad = [np.mean(-fi[n] * lap[n].astype(np.float64)) / 2 / 1.3**2 for n in range(2)]
     want_pot = np.mean(fi[0]**2 / 2 + fi[0]**2 * fi[1]**2 / 2)
-    assert np.allclose(out["kinetic"], want_kin, rtol=tol)
-    assert np.allclose(out["gradient"], want_grad, rtol=tol)
-    assert np.allclose(out["potential"], [want_pot], rtol=tol)
+    for variant in (0, 1):
+        red = ps.Reduction(decomp, sector, halo_shape=h, grid_size=float(np.prod(N)),
+                           tune={"variant": variant})
+        out = red(None, f=to_dev(f), dfdt=to_dev(d), lap_f=to_dev(lap), a=np.array(1.3))
+        assert np.allclose(out["kinetic"], want_kin, rtol=tol)
+        assert np.allclose(out["gradient"], want_grad, rtol=tol)
+        assert np.allclose(out["potential"], [want_pot], rtol=tol)
     stats = ps.FieldStatistics(decomp, h, max_min=True, grid_size=float(np.prod(N)))
     st = stats(to_dev(f))
     assert np.allclose(st["mean"], fi.mean(axis=(1, 2, 3)), rtol=tol)
@@ -537,10 +546,8 @@ if __name__ == "__main__":
     elif sys.argv[1] == "aligned":
         _case_aligned(int(sys.argv[2]))
     elif sys.argv[1] == "reduce_v2":
-        os.environ["PSB_REDUCE_V2"] = "1"
         _case_reduce_v2(sys.argv[2])
     elif sys.argv[1] == "fd_pipeline":
-        os.environ["PSB_FD_PIPELINE"] = "1"
         _case_fd_pipeline(sys.argv[2], int(sys.argv[3]))
     else:
         raise SystemExit(f"unknown case {sys.argv[1]}")
