@@ -40,6 +40,7 @@ template <typename T, int NF> struct FusedParams {
   int Nx, Ny, Nz;
   int x_begin, x_end, xchunk;
   int x2_begin, x2_end, nchunks1;
+  int nmain, split_len;   // x-chunk schedule of range 1 (chunk_range())
   int wrap_x, wrap_y, wrap_z;
   T* peer_lo;   // peer-mapped f_out of rank rx-1 / rx+1 (or null)
   T* peer_hi;
@@ -141,6 +142,34 @@ __device__ __forceinline__ void st_plain(T* p, const Vec<T, VEC>& v) {
   *reinterpret_cast<Vec<T, VEC>*>(p) = v;
 }
 
+// x-chunk schedule of a launch (gridDim.z = chunk index, the slowest dispatch dimension):
+// range 1 = [x_begin, x_end) is marched in chunks of `xchunk` planes, except that its LAST
+// `split_len` planes are cut into split_len/2, /4, /4: the CTAs dispatched last are short, so
+// the tail in which SMs run out of work is a quarter as long (measured: ~10 % of a 64-plane
+// launch was idle SM time with uniform 16-plane chunks).  Range 2 (second boundary slab of
+// the NCCL fallback) is uniform.  nmain = ordinary chunks of range 1 before the split.
+struct ChunkRange {
+  int xs, xe;
+};
+__device__ __forceinline__ ChunkRange chunk_range(int zc, int x_begin, int x_end, int x2_begin,
+                                                  int x2_end, int xchunk, int nchunks1,
+                                                  int nmain, int split_len) {
+  ChunkRange r;
+  if (zc >= nchunks1) {   // second x range of the launch
+    r.xs = x2_begin + (zc - nchunks1) * xchunk;
+    r.xe = min(r.xs + xchunk, x2_end);
+  } else if (zc < nmain) {
+    r.xs = x_begin + zc * xchunk;
+    r.xe = min(r.xs + xchunk, x_end - split_len);
+  } else {
+    const int t = zc - nmain, base = x_end - split_len;
+    const int h2 = split_len / 2, q = split_len / 4;
+    r.xs = base + (t == 0 ? 0 : (t == 1 ? h2 : h2 + q));
+    r.xe = base + (t == 0 ? h2 : (t == 1 ? h2 + q : split_len));
+  }
+  return r;
+}
+
 template <typename T, int H, int NF, int VEC, int BY, int TZ, int P>
 struct FusedCfg {
   static constexpr int BZ = TZ * VEC;
@@ -175,14 +204,9 @@ __global__ void __launch_bounds__(BY* TZ, MINB)
   const int tz = threadIdx.x, ty = threadIdx.y;
   const int tid = ty * TZ + tz;
   const int z0 = blockIdx.x * C::BZ, y0 = blockIdx.y * BY;
-  int zc = blockIdx.z, xb = p.x_begin, xlim = p.x_end;
-  if (zc >= p.nchunks1) {  // second x range of the launch
-    zc -= p.nchunks1;
-    xb = p.x2_begin;
-    xlim = p.x2_end;
-  }
-  const int xs = xb + zc * p.xchunk;
-  const int xe = min(xs + p.xchunk, xlim);
+  const ChunkRange cr = chunk_range(blockIdx.z, p.x_begin, p.x_end, p.x2_begin, p.x2_end,
+                                    p.xchunk, p.nchunks1, p.nmain, p.split_len);
+  const int xs = cr.xs, xe = cr.xe;
   const int nsteps = (xe - xs) + 2 * H;
 
   const int j = y0 + ty, k = z0 + tz * VEC;
@@ -498,18 +522,24 @@ __global__ void __launch_bounds__(BY* TZ, MINB)
 extern thread_local psb_fused_plan* t_fused_plan;
 
 struct XLayout {
-  int xchunk, n1, n2;
+  int xchunk, n1, n2, nmain, split_len;
 };
+// tune_xchunk: 0 = default chunk with the split tail, > 0 = that chunk with the split tail,
+// < 0 = uniform chunks of -tune_xchunk planes (no split)
 static inline XLayout x_layout(const psb_scalar_stage_args* a, int default_chunk) {
   const int64_t nx1 = a->x_end - a->x_begin;
   const int64_t nx2 = a->x2_end > a->x2_begin ? a->x2_end - a->x2_begin : 0;
-  int64_t xc = a->tune_xchunk > 0 ? a->tune_xchunk : default_chunk;
+  const bool uniform = a->tune_xchunk < 0;
+  int64_t xc = a->tune_xchunk > 0 ? a->tune_xchunk
+                                  : (a->tune_xchunk < 0 ? -a->tune_xchunk : default_chunk);
   const int64_t nmax = nx1 > nx2 ? nx1 : nx2;
   if (xc > nmax) xc = nmax;
   if (xc < 1) xc = 1;
   XLayout L;
   L.xchunk = (int)xc;
-  L.n1 = (int)((nx1 + xc - 1) / xc);
+  L.split_len = (!uniform && xc >= 8 && xc % 4 == 0 && nx1 >= 2 * xc) ? (int)xc : 0;
+  L.nmain = (int)((nx1 - L.split_len + xc - 1) / xc);
+  L.n1 = L.nmain + (L.split_len ? 3 : 0);
   L.n2 = (int)((nx2 + xc - 1) / xc);
   return L;
 }
@@ -575,6 +605,8 @@ static int launch_fused(const psb_scalar_stage_args* a, cudaStream_t stream) {
   const XLayout L = x_layout(a, 64);
   p.xchunk = L.xchunk;
   p.nchunks1 = L.n1;
+  p.nmain = L.nmain;
+  p.split_len = L.split_len;
   dim3 grid((unsigned)((a->Nz + C::BZ - 1) / C::BZ), (unsigned)((a->Ny + BY - 1) / BY),
             (unsigned)(L.n1 + L.n2));
   dim3 block(TZ, BY, 1);
@@ -717,6 +749,17 @@ static int dispatch_vec(const psb_scalar_stage_args* a, cudaStream_t stream,
         if (var == 14) return ws_op<T, H, NF, 2, 64, 3, 3>(a, stream, count);
         return ws_op<T, H, NF, 4, 64, 3, 2>(a, stream, count);
       } else {
+        if constexpr (NF >= 2) {
+          // several fields: the rings of the default depth leave room for 8 consumer warps
+          // per SM only (latency-bound, ncu: 58 % of the cycles no warp is eligible); with a
+          // one-plane-shallower pipeline three CTAs fit (tune_variant 20 while it is measured)
+          constexpr int VV = std::is_same<T, float>::value ? 4 : 2;
+          constexpr int TZ3 = ws_pick_tz(ES, H, NF, 4, 1, VV, SMEM_LIMIT_3);
+          if constexpr (TZ3 > 0) {
+            if (var == 20 && a->Nz % VV == 0)
+              return ws_op<T, H, NF, 4, TZ3, 1, 3, VV>(a, stream, count);
+          }
+        }
         if constexpr (std::is_same<T, float>::value) {
           // fp32: 4 sites per thread (16-byte shared-memory vectors) when rows allow
           constexpr int TZ4 = ws_pick_tz(ES, H, NF, 4, 2, 4);

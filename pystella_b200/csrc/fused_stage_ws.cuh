@@ -82,11 +82,14 @@ constexpr int ws_smem_bytes(int es, int H, int NF, int BY, int TZ, int P, int VE
          128;
 }
 // widest z tile (64, 32 or 16 threads of 2 sites) whose rings fit; 0 = none
-constexpr int ws_pick_tz(int es, int H, int NF, int BY, int P, int VEC = 2) {
+constexpr int ws_pick_tz(int es, int H, int NF, int BY, int P, int VEC = 2,
+                         int limit = SMEM_LIMIT) {
   for (int tz = 128 / VEC; tz >= 16; tz /= 2)
-    if (ws_smem_bytes(es, H, NF, BY, tz, P, VEC) <= SMEM_LIMIT) return tz;
+    if (ws_smem_bytes(es, H, NF, BY, tz, P, VEC) <= limit) return tz;
   return 0;
 }
+// three CTAs per SM (227 KB of shared memory, 1 KB reserved per CTA)
+constexpr int SMEM_LIMIT_3 = 74 * 1024;
 
 // VEC elements moved as VEC/GV aligned pieces
 template <typename T, int VEC, int GV>
@@ -166,14 +169,9 @@ __global__ void __launch_bounds__(BY* TZ + 32, MINB)
 
   const int tid = threadIdx.x;
   const int z0 = blockIdx.x * C::BZ, y0 = blockIdx.y * BY;
-  int zc = blockIdx.z, xb = p.x_begin, xlim = p.x_end;
-  if (zc >= p.nchunks1) {  // second x range of the launch
-    zc -= p.nchunks1;
-    xb = p.x2_begin;
-    xlim = p.x2_end;
-  }
-  const int xs = xb + zc * p.xchunk;
-  const int xe = min(xs + p.xchunk, xlim);
+  const ChunkRange cr = chunk_range(blockIdx.z, p.x_begin, p.x_end, p.x2_begin, p.x2_end,
+                                    p.xchunk, p.nchunks1, p.nmain, p.split_len);
+  const int xs = cr.xs, xe = cr.xe;
   const int nsteps = (xe - xs) + 2 * H;   // f planes streamed
   const int ncomp = xe - xs;              // site planes computed
   const bool read_k = (p.A != (T)0);
@@ -608,6 +606,8 @@ static int plan_ws(const psb_scalar_stage_args* a, psb_fused_plan* plan) {
   const XLayout L = x_layout(a, WS_DEFAULT_XCHUNK);
   p.xchunk = L.xchunk;
   p.nchunks1 = L.n1;
+  p.nmain = L.nmain;
+  p.split_len = L.split_len;
   memcpy(plan->params, &p, sizeof(p));
   plan->params_bytes = (uint32_t)sizeof(p);
   plan->dtype = a->dtype;
@@ -651,6 +651,8 @@ static int launch_ws(const psb_scalar_stage_args* a, cudaStream_t stream) {
   const XLayout L = x_layout(a, WS_DEFAULT_XCHUNK);
   p.xchunk = L.xchunk;
   p.nchunks1 = L.n1;
+  p.nmain = L.nmain;
+  p.split_len = L.split_len;
   dim3 grid((unsigned)((a->Nz + C::SH + C::BZ - 1) / C::BZ),
             (unsigned)((a->Ny + BY - 1) / BY), (unsigned)(L.n1 + L.n2));
   dim3 block(C::THREADS, 1, 1);

@@ -27,6 +27,7 @@ template <typename T> struct TensorFusedParams {
   int Nx, Ny, Nz;
   int x_begin, x_end, xchunk;
   int x2_begin, x2_end, nchunks1;
+  int nmain, split_len;
   int wrap_x, wrap_y, wrap_z;
   T inv_dx2[3];
   T inv_dx[3];
@@ -50,14 +51,22 @@ template <typename T, int H, int NS, int BY, int TZ, int P, int VEC_> struct Tws
   static constexpr int NCW = BY * TZ / 32;
 };
 
-template <typename T, int H, int NS, int BY, int TZ, int P, int MINB, int VEC_>
-__global__ void __launch_bounds__(BY* TZ + 32, MINB)
-    tensor_stage_ws_kernel(const __grid_constant__ TensorFusedParams<T> p,
-                           const __grid_constant__ CUtensorMap map_h,
-                           const __grid_constant__ CUtensorMap map_s,
-                           const __grid_constant__ CUtensorMap map_d,
-                           const __grid_constant__ CUtensorMap map_kh,
-                           const __grid_constant__ CUtensorMap map_kd) {
+// Body of one CTA for the packed component (CI, CJ), CI <= CJ, known at compile time: only
+// the gradient axes the component needs are evaluated -- xx needs d_x only (no y/z neighbour
+// loads of the source planes), yy / yz / zz need no x register queue of the sources at all --
+// which removes a third of the shared-memory loads and of the arithmetic of the generic
+// formulation and most of its selects.
+template <typename T, int H, int NS, int BY, int TZ, int P, int VEC_, int CI, int CJ>
+__device__ __forceinline__ void tensor_stage_body(const TensorFusedParams<T>& p,
+                                                  const CUtensorMap& map_h,
+                                                  const CUtensorMap& map_s,
+                                                  const CUtensorMap& map_d,
+                                                  const CUtensorMap& map_kh,
+                                                  const CUtensorMap& map_kd) {
+  constexpr bool NX = (CI == 0);                 // d_x of the sources needed
+  constexpr bool NY = (CI == 1 || CJ == 1);      // d_y
+  constexpr bool NZ = (CJ == 2);                 // d_z
+  constexpr int comp = CI == 0 ? CJ : (CI == 1 ? 2 + CJ : 5);
   using C = TwsCfg<T, H, NS, BY, TZ, P, VEC_>;
   using B = typename C::B;
   constexpr int VEC = B::VEC, GV = B::GV, W = B::W, HL = B::HL, RF = C::RF, RP = C::RP;
@@ -74,16 +83,10 @@ __global__ void __launch_bounds__(BY* TZ + 32, MINB)
   uint64_t* empty_p = bars + 2 * RF + RP;
 
   const int tid = threadIdx.x;
-  const int comp = blockIdx.x % 6;           // packed component (1,1),(1,2),(1,3),(2,2),...
   const int z0 = (blockIdx.x / 6) * B::BZ, y0 = blockIdx.y * BY;
-  int zc = blockIdx.z, xb = p.x_begin, xlim = p.x_end;
-  if (zc >= p.nchunks1) {
-    zc -= p.nchunks1;
-    xb = p.x2_begin;
-    xlim = p.x2_end;
-  }
-  const int xs = xb + zc * p.xchunk;
-  const int xe = min(xs + p.xchunk, xlim);
+  const ChunkRange cr = chunk_range(blockIdx.z, p.x_begin, p.x_end, p.x2_begin, p.x2_end,
+                                    p.xchunk, p.nchunks1, p.nmain, p.split_len);
+  const int xs = cr.xs, xe = cr.xe;
   const int nsteps = (xe - xs) + 2 * H;
   const int ncomp = xe - xs;
   const bool read_k = (p.A != (T)0);
@@ -152,21 +155,18 @@ __global__ void __launch_bounds__(BY* TZ + 32, MINB)
   T hubble = p.hubble;
   if (p.hubble_dev) hubble = (T)(*p.hubble_dev);
   const T two_h = (T)2 * hubble;
-  // (i, j) of the packed component
-  const int ci = comp < 3 ? 0 : (comp < 5 ? 1 : 2);
-  const int cj = comp < 3 ? comp : (comp < 5 ? comp - 2 : 2);
 
   const int own_off = (ty + H) * W + HL + tz * VEC;
   const int pw_off = ty * B::PWW + B::PWL + tz * VEC;
 
   V qh[2 * H + 1];
-  V qs[NS][2 * H + 1];
+  V qs[NX ? NS : 1][2 * H + 1];   // x register queue of the sources: only for d_x
 #pragma unroll
   for (int s = 0; s < 2 * H + 1; ++s) {
 #pragma unroll
     for (int v = 0; v < VEC; ++v) qh[s].v[v] = (T)0;
 #pragma unroll
-    for (int n = 0; n < NS; ++n)
+    for (int n = 0; n < (NX ? NS : 1); ++n)
 #pragma unroll
       for (int v = 0; v < VEC; ++v) qs[n][s].v[v] = (T)0;
   }
@@ -185,12 +185,14 @@ __global__ void __launch_bounds__(BY* TZ + 32, MINB)
 #pragma unroll
       for (int s = 0; s < 2 * H; ++s) qh[s] = qh[s + 1];
       qh[2 * H] = ld_pieces<T, VEC, GV>(reinterpret_cast<const T*>(sl) + own_off);
+      if constexpr (NX) {
 #pragma unroll
-      for (int m = 0; m < NS; ++m) {
+        for (int m = 0; m < NS; ++m) {
 #pragma unroll
-        for (int s = 0; s < 2 * H; ++s) qs[m][s] = qs[m][s + 1];
-        qs[m][2 * H] = ld_pieces<T, VEC, GV>(
-            reinterpret_cast<const T*>(sl + (1 + m) * B::FPLANE) + own_off);
+          for (int s = 0; s < 2 * H; ++s) qs[m][s] = qs[m][s + 1];
+          qs[m][2 * H] = ld_pieces<T, VEC, GV>(
+              reinterpret_cast<const T*>(sl + (1 + m) * B::FPLANE) + own_off);
+        }
       }
     }
 
@@ -249,44 +251,71 @@ __global__ void __launch_bounds__(BY* TZ + 32, MINB)
           }
         }
 
-        // ---- source term S_c = sum_n d_i f_n d_j f_n  (first-derivative stencils)
+        // ---- source term S_c = sum_n d_i f_n d_j f_n  (first-derivative stencils; only
+        // the axes this component needs)
         V S;
 #pragma unroll
         for (int v = 0; v < VEC; ++v) S.v[v] = (T)0;
 #pragma unroll
         for (int m = 0; m < NS; ++m) {
           const T* pl = reinterpret_cast<const T*>(cen + (1 + m) * B::FPLANE);
-          T zrow[NVZ * GV];
+          V gx, gy, gz;
+          if constexpr (NX) {
 #pragma unroll
-          for (int w = 0; w < NVZ; ++w) {
-            Vec<T, GV> t = ld_vec<T, GV>(pl + own_off - HL + w * GV);
+            for (int v = 0; v < VEC; ++v) {
+              T g = (T)0;
 #pragma unroll
-            for (int v = 0; v < GV; ++v) zrow[w * GV + v] = t.v[v];
+              for (int s = 1; s <= H; ++s) {
+                const T cs = (T)grad_coef<H>(s);
+                g = (s == 1) ? cs * qs[m][H + s].v[v] : g + cs * qs[m][H + s].v[v];
+                g = g + (-cs) * qs[m][H - s].v[v];
+              }
+              gx.v[v] = g * p.inv_dx[0];
+            }
           }
-          V yn[2 * H + 1];
+          if constexpr (NY) {
+            V yn[2 * H + 1];
 #pragma unroll
-          for (int s = 1; s <= H; ++s) {
-            yn[H + s] = ld_pieces<T, VEC, GV>(pl + own_off + s * W);
-            yn[H - s] = ld_pieces<T, VEC, GV>(pl + own_off - s * W);
+            for (int s = 1; s <= H; ++s) {
+              yn[H + s] = ld_pieces<T, VEC, GV>(pl + own_off + s * W);
+              yn[H - s] = ld_pieces<T, VEC, GV>(pl + own_off - s * W);
+            }
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+              T g = (T)0;
+#pragma unroll
+              for (int s = 1; s <= H; ++s) {
+                const T cs = (T)grad_coef<H>(s);
+                g = (s == 1) ? cs * yn[H + s].v[v] : g + cs * yn[H + s].v[v];
+                g = g + (-cs) * yn[H - s].v[v];
+              }
+              gy.v[v] = g * p.inv_dx[1];
+            }
+          }
+          if constexpr (NZ) {
+            T zrow[NVZ * GV];
+#pragma unroll
+            for (int w = 0; w < NVZ; ++w) {
+              Vec<T, GV> t = ld_vec<T, GV>(pl + own_off - HL + w * GV);
+#pragma unroll
+              for (int v = 0; v < GV; ++v) zrow[w * GV + v] = t.v[v];
+            }
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+              T g = (T)0;
+#pragma unroll
+              for (int s = 1; s <= H; ++s) {
+                const T cs = (T)grad_coef<H>(s);
+                g = (s == 1) ? cs * zrow[HL + v + s] : g + cs * zrow[HL + v + s];
+                g = g + (-cs) * zrow[HL + v - s];
+              }
+              gz.v[v] = g * p.inv_dx[2];
+            }
           }
 #pragma unroll
           for (int v = 0; v < VEC; ++v) {
-            T gx = (T)0, gy = (T)0, gz = (T)0;
-#pragma unroll
-            for (int s = 1; s <= H; ++s) {
-              const T cs = (T)grad_coef<H>(s);
-              gx = (s == 1) ? cs * qs[m][H + s].v[v] : gx + cs * qs[m][H + s].v[v];
-              gx = gx + (-cs) * qs[m][H - s].v[v];
-              gy = (s == 1) ? cs * yn[H + s].v[v] : gy + cs * yn[H + s].v[v];
-              gy = gy + (-cs) * yn[H - s].v[v];
-              gz = (s == 1) ? cs * zrow[HL + v + s] : gz + cs * zrow[HL + v + s];
-              gz = gz + (-cs) * zrow[HL + v - s];
-            }
-            gx = gx * p.inv_dx[0];
-            gy = gy * p.inv_dx[1];
-            gz = gz * p.inv_dx[2];
-            const T gi = ci == 0 ? gx : (ci == 1 ? gy : gz);
-            const T gj = cj == 0 ? gx : (cj == 1 ? gy : gz);
+            const T gi = CI == 0 ? gx.v[v] : (CI == 1 ? gy.v[v] : gz.v[v]);
+            const T gj = CJ == 0 ? gx.v[v] : (CJ == 1 ? gy.v[v] : gz.v[v]);
             S.v[v] = (m == 0) ? gi * gj : S.v[v] + gi * gj;
           }
         }
@@ -364,6 +393,25 @@ __global__ void __launch_bounds__(BY* TZ + 32, MINB)
   }
 }
 
+template <typename T, int H, int NS, int BY, int TZ, int P, int MINB, int VEC_>
+__global__ void __launch_bounds__(BY* TZ + 32, MINB)
+    tensor_stage_ws_kernel(const __grid_constant__ TensorFusedParams<T> p,
+                           const __grid_constant__ CUtensorMap map_h,
+                           const __grid_constant__ CUtensorMap map_s,
+                           const __grid_constant__ CUtensorMap map_d,
+                           const __grid_constant__ CUtensorMap map_kh,
+                           const __grid_constant__ CUtensorMap map_kd) {
+  // packed component (1,1),(1,2),(1,3),(2,2),(2,3),(3,3) = fastest grid dimension
+  switch (blockIdx.x % 6) {
+    case 0: tensor_stage_body<T, H, NS, BY, TZ, P, VEC_, 0, 0>(p, map_h, map_s, map_d, map_kh, map_kd); break;
+    case 1: tensor_stage_body<T, H, NS, BY, TZ, P, VEC_, 0, 1>(p, map_h, map_s, map_d, map_kh, map_kd); break;
+    case 2: tensor_stage_body<T, H, NS, BY, TZ, P, VEC_, 0, 2>(p, map_h, map_s, map_d, map_kh, map_kd); break;
+    case 3: tensor_stage_body<T, H, NS, BY, TZ, P, VEC_, 1, 1>(p, map_h, map_s, map_d, map_kh, map_kd); break;
+    case 4: tensor_stage_body<T, H, NS, BY, TZ, P, VEC_, 1, 2>(p, map_h, map_s, map_d, map_kh, map_kd); break;
+    default: tensor_stage_body<T, H, NS, BY, TZ, P, VEC_, 2, 2>(p, map_h, map_s, map_d, map_kh, map_kd); break;
+  }
+}
+
 constexpr int tws_smem_bytes(int es, int H, int NS, int BY, int TZ, int P, int VEC) {
   const int BZ = TZ * VEC;
   const int GV = ws_gcd(VEC, H);
@@ -388,11 +436,15 @@ static int launch_tensor_ws(const psb_tensor_fused_args* a, cudaStream_t stream,
   constexpr int TZ = tws_pick_tz((int)sizeof(T), H, NS, BY, P, VEC);
   using C = TwsCfg<T, H, NS, BY, TZ, P, VEC>;
   using B = typename C::B;
+  // the scalar stage's x-chunk schedule (split tail included)
+  psb_scalar_stage_args xa;
+  memset(&xa, 0, sizeof(xa));
+  xa.x_begin = 0;
+  xa.x_end = a->Nx;
+  xa.tune_xchunk = a->tune_xchunk;
+  const XLayout L = x_layout(&xa, WS_DEFAULT_XCHUNK);
   if (count != nullptr) {
-    int64_t xc = a->tune_xchunk > 0 ? a->tune_xchunk : WS_DEFAULT_XCHUNK;
-    if (xc > a->Nx) xc = a->Nx;
-    *count = 6 * ((a->Nz + B::BZ - 1) / B::BZ) * ((a->Ny + BY - 1) / BY) *
-             ((a->Nx + xc - 1) / xc);
+    *count = 6 * ((a->Nz + B::BZ - 1) / B::BZ) * ((a->Ny + BY - 1) / BY) * (int64_t)L.n1;
     return 0;
   }
   static_assert(C::SMEM_BYTES <= 227 * 1024, "tensor pipeline does not fit shared memory");
@@ -426,10 +478,10 @@ static int launch_tensor_ws(const psb_tensor_fused_args* a, cudaStream_t stream,
   p.x_begin = 0;
   p.x_end = (int)a->Nx;
   p.x2_begin = p.x2_end = 0;
-  int xchunk = a->tune_xchunk > 0 ? a->tune_xchunk : WS_DEFAULT_XCHUNK;
-  if (xchunk > a->Nx) xchunk = (int)a->Nx;
-  p.xchunk = xchunk;
-  p.nchunks1 = (int)((a->Nx + xchunk - 1) / xchunk);
+  p.xchunk = L.xchunk;
+  p.nchunks1 = L.n1;
+  p.nmain = L.nmain;
+  p.split_len = L.split_len;
   p.wrap_x = a->wrap_x;
   p.wrap_y = a->wrap_y;
   p.wrap_z = a->wrap_z;

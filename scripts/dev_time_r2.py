@@ -96,13 +96,16 @@ if __name__ == "__main__":
     F64, F32 = torch.float64, torch.float32
     N5 = (512,) * 3
     if "gwvar" in which:
-        for var in (0, 2, 3, 4, 5):
+        for var in (0, 2, 4, 1):
             gw_case(512, F32, tune={"gw_variant": var})
         gw_case(512, F32, tune={"gw_variant": 2, "gw_xchunk": 32})
-        gw_case(512, F32, tune={"gw_variant": 3, "gw_xchunk": 32})
-        gw_case(256, F64, tune={"gw_variant": 2})
-        scalar_case(N5, F32, 1, True, nscalars=2, tune={"variant": 15})
-        scalar_case((256,) * 3, F64, 1, True, nscalars=2)
+        gw_case(512, F32, tune={"gw_variant": 0, "gw_xchunk": 32})
+        gw_case(512, F32, tune={"gw_variant": 0, "gw_xchunk": -16})
+        gw_case(256, F64)
+        for var in (0, 20):
+            scalar_case(N5, F32, 1, True, nscalars=2, tune={"variant": var})
+            scalar_case((256,) * 3, F64, 1, True, nscalars=2, tune={"variant": var})
+            scalar_case((256,) * 3, F64, 1, True, nscalars=3, tune={"variant": var})
     if "gwprof" in which:
         gw_case(384, F32)
     if "f32prof" in which:
@@ -126,12 +129,14 @@ if __name__ == "__main__":
         scalar_case((256,) * 3, F64, 1, True, nscalars=2)
         scalar_case(N5, F32, 1, True, nscalars=2)
     if "chunk" in which:
-        for xc in (4, 8, 16, 32):
+        for xc in (-16, 16, 32, -32, 8):
             scalar_case((64, 512, 512), F64, 1, True, tune={"xchunk": xc})
-        for xc in (8, 16, 32):
+        for xc in (-16, 16, 32):
             scalar_case((256,) * 3, F64, 1, True, tune={"xchunk": xc})
-        for xc in (8, 16, 32):
+        for xc in (-16, 16, 32):
             scalar_case((128, 1024, 1024), F32, 1, True, tune={"xchunk": xc})
+        for xc in (-16, 16, 32):
+            scalar_case(N5, F64, 1, True, tune={"xchunk": xc})
     if "store" in which:
         for var in (10, 11, 12, 13, 14):
             scalar_case(N5, F64, 0, True, tune={"variant": var})
