@@ -526,7 +526,8 @@ struct XLayout {
 };
 // tune_xchunk: 0 = default chunk with the split tail, > 0 = that chunk with the split tail,
 // < 0 = uniform chunks of -tune_xchunk planes (no split)
-static inline XLayout x_layout(const psb_scalar_stage_args* a, int default_chunk) {
+static inline XLayout x_layout(const psb_scalar_stage_args* a, int default_chunk,
+                               int64_t tiles = 0) {
   const int64_t nx1 = a->x_end - a->x_begin;
   const int64_t nx2 = a->x2_end > a->x2_begin ? a->x2_end - a->x2_begin : 0;
   const bool uniform = a->tune_xchunk < 0;
@@ -537,7 +538,12 @@ static inline XLayout x_layout(const psb_scalar_stage_args* a, int default_chunk
   if (xc < 1) xc = 1;
   XLayout L;
   L.xchunk = (int)xc;
-  L.split_len = (!uniform && xc >= 8 && xc % 4 == 0 && nx1 >= 2 * xc) ? (int)xc : 0;
+  // the short chunks re-read their 2h prologue planes for little work: worth it only when a
+  // chunk index holds few waves of CTAs (measured: 512^2 planes, 512 tiles: +2..3 %;
+  // 1024^2 planes, 2048 tiles: -5 %)
+  const bool few_tiles = tiles <= 0 || tiles <= 1024;
+  L.split_len =
+      (!uniform && few_tiles && xc >= 8 && xc % 4 == 0 && nx1 >= 2 * xc) ? (int)xc : 0;
   L.nmain = (int)((nx1 - L.split_len + xc - 1) / xc);
   L.n1 = L.nmain + (L.split_len ? 3 : 0);
   L.n2 = (int)((nx2 + xc - 1) / xc);
@@ -602,7 +608,7 @@ static int launch_fused(const psb_scalar_stage_args* a, cudaStream_t stream) {
   using C = FusedCfg<T, H, NF, VEC, BY, TZ, P>;
   FusedParams<T, NF> p;
   fill_params<T, NF>(p, a);
-  const XLayout L = x_layout(a, 64);
+  const XLayout L = x_layout(a, 64, ((a->Nz + C::BZ - 1) / C::BZ) * ((a->Ny + BY - 1) / BY));
   p.xchunk = L.xchunk;
   p.nchunks1 = L.n1;
   p.nmain = L.nmain;
@@ -643,7 +649,7 @@ static int launch_fused(const psb_scalar_stage_args* a, cudaStream_t stream) {
 template <typename T, int H, int NF, int VEC, int BY, int TZ, int P>
 static int64_t fused_grid_blocks(const psb_scalar_stage_args* a) {
   using C = FusedCfg<T, H, NF, VEC, BY, TZ, P>;
-  const XLayout L = x_layout(a, 64);
+  const XLayout L = x_layout(a, 64, ((a->Nz + C::BZ - 1) / C::BZ) * ((a->Ny + BY - 1) / BY));
   return ((a->Nz + C::BZ - 1) / C::BZ) * ((a->Ny + BY - 1) / BY) * (int64_t)(L.n1 + L.n2);
 }
 
@@ -752,11 +758,13 @@ static int dispatch_vec(const psb_scalar_stage_args* a, cudaStream_t stream,
         if constexpr (NF >= 2) {
           // several fields: the rings of the default depth leave room for 8 consumer warps
           // per SM only (latency-bound, ncu: 58 % of the cycles no warp is eligible); with a
-          // one-plane-shallower pipeline three CTAs fit (tune_variant 20 while it is measured)
+          // one-plane-shallower pipeline three CTAs fit: measured 0.56 -> 0.75 of the HBM
+          // roofline (2 fields fp32 512^3), 0.62 -> 0.79 (2 fields fp64), 0.40 -> 0.66
+          // (3 fields fp64).  tune_variant 21 = the deeper two-CTA configuration.
           constexpr int VV = std::is_same<T, float>::value ? 4 : 2;
           constexpr int TZ3 = ws_pick_tz(ES, H, NF, 4, 1, VV, SMEM_LIMIT_3);
           if constexpr (TZ3 > 0) {
-            if (var == 20 && a->Nz % VV == 0)
+            if (var != 21 && var != 15 && a->Nz % VV == 0)
               return ws_op<T, H, NF, 4, TZ3, 1, 3, VV>(a, stream, count);
           }
         }

@@ -565,7 +565,8 @@ __global__ void __launch_bounds__(BY* TZ + 32, MINB)
 template <typename T, int H, int NF, int BY, int TZ, int P, int VEC = 2, bool AL = false>
 static int64_t ws_grid_blocks(const psb_scalar_stage_args* a) {
   using C = WsCfg<T, H, NF, BY, TZ, P, VEC, AL>;
-  const XLayout L = x_layout(a, WS_DEFAULT_XCHUNK);
+  const XLayout L = x_layout(a, WS_DEFAULT_XCHUNK, ((a->Nz + C::SH + C::BZ - 1) / C::BZ) *
+                                                        ((a->Ny + BY - 1) / BY));
   return ((a->Nz + C::SH + C::BZ - 1) / C::BZ) * ((a->Ny + BY - 1) / BY) *
          (int64_t)(L.n1 + L.n2);
 }
@@ -603,7 +604,8 @@ static int plan_ws(const psb_scalar_stage_args* a, psb_fused_plan* plan) {
   FusedParams<T, NF> p;
   memset(&p, 0, sizeof(p));
   fill_params<T, NF>(p, a);
-  const XLayout L = x_layout(a, WS_DEFAULT_XCHUNK);
+  const XLayout L = x_layout(a, WS_DEFAULT_XCHUNK, ((a->Nz + C::SH + C::BZ - 1) / C::BZ) *
+                                                        ((a->Ny + BY - 1) / BY));
   p.xchunk = L.xchunk;
   p.nchunks1 = L.n1;
   p.nmain = L.nmain;
@@ -648,7 +650,8 @@ static int launch_ws(const psb_scalar_stage_args* a, cudaStream_t stream) {
 
   FusedParams<T, NF> p;
   fill_params<T, NF>(p, a);
-  const XLayout L = x_layout(a, WS_DEFAULT_XCHUNK);
+  const XLayout L = x_layout(a, WS_DEFAULT_XCHUNK, ((a->Nz + C::SH + C::BZ - 1) / C::BZ) *
+                                                        ((a->Ny + BY - 1) / BY));
   p.xchunk = L.xchunk;
   p.nchunks1 = L.n1;
   p.nmain = L.nmain;

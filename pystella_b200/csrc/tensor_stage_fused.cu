@@ -40,9 +40,14 @@ template <typename T> struct TensorFusedParams {
   TailParams tail;
 };
 
-template <typename T, int H, int NS, int BY, int TZ, int P, int VEC_> struct TwsCfg {
+// SMEMX: the x neighbours are read from the ring in shared memory (which then keeps the 2H
+// planes behind the newest one: R_f = 2H+1+P) instead of living in per-thread register
+// queues that are shifted once per plane -- ncu showed a third of the executed instructions
+// of the register-queue formulation to be those moves (IMAD.MOV) and integer bookkeeping.
+template <typename T, int H, int NS, int BY, int TZ, int P, int VEC_, bool SMEMX = false>
+struct TwsCfg {
   using B = WsCfg<T, H, 1, BY, TZ, P, VEC_>;
-  static constexpr int RF = B::RF, RP = B::RP;
+  static constexpr int RF = SMEMX ? 2 * H + 1 + P : B::RF, RP = B::RP;
   static constexpr int FSLOT = (1 + NS) * B::FPLANE;   // h plane + NS source planes
   static constexpr int PWSLOT = 3 * B::PWTILE;
   static constexpr int NBAR = 2 * RF + 2 * RP;
@@ -56,7 +61,8 @@ template <typename T, int H, int NS, int BY, int TZ, int P, int VEC_> struct Tws
 // loads of the source planes), yy / yz / zz need no x register queue of the sources at all --
 // which removes a third of the shared-memory loads and of the arithmetic of the generic
 // formulation and most of its selects.
-template <typename T, int H, int NS, int BY, int TZ, int P, int VEC_, int CI, int CJ>
+template <typename T, int H, int NS, int BY, int TZ, int P, int VEC_, bool SMEMX, int CI,
+          int CJ>
 __device__ __forceinline__ void tensor_stage_body(const TensorFusedParams<T>& p,
                                                   const CUtensorMap& map_h,
                                                   const CUtensorMap& map_s,
@@ -67,7 +73,7 @@ __device__ __forceinline__ void tensor_stage_body(const TensorFusedParams<T>& p,
   constexpr bool NY = (CI == 1 || CJ == 1);      // d_y
   constexpr bool NZ = (CJ == 2);                 // d_z
   constexpr int comp = CI == 0 ? CJ : (CI == 1 ? 2 + CJ : 5);
-  using C = TwsCfg<T, H, NS, BY, TZ, P, VEC_>;
+  using C = TwsCfg<T, H, NS, BY, TZ, P, VEC_, SMEMX>;
   using B = typename C::B;
   constexpr int VEC = B::VEC, GV = B::GV, W = B::W, HL = B::HL, RF = C::RF, RP = C::RP;
   using V = Vec<T, VEC>;
@@ -180,7 +186,7 @@ __device__ __forceinline__ void tensor_stage_body(const TensorFusedParams<T>& p,
   for (int n = 0; n < nsteps; ++n) {
     const int slot = n % RF;
     mbar_wait(&full_f[slot], (n / RF) & 1);
-    {
+    if constexpr (!SMEMX) {
       const unsigned char* sl = fring + slot * C::FSLOT;
 #pragma unroll
       for (int s = 0; s < 2 * H; ++s) qh[s] = qh[s + 1];
@@ -215,6 +221,24 @@ __device__ __forceinline__ void tensor_stage_body(const TensorFusedParams<T>& p,
           for (int v = 0; v < VEC; ++v) kho.v[v] = kdo.v[v] = (T)0;
         }
         constexpr int NVZ = (VEC + 2 * HL) / GV;
+        if constexpr (SMEMX) {
+          // x neighbours of the centre plane n-H: planes n-2H .. n, all still in the ring
+          int xslot = (n - 2 * H) % RF;
+#pragma unroll
+          for (int s = 0; s < 2 * H + 1; ++s) {
+            const unsigned char* sl = fring + xslot * C::FSLOT;
+            qh[s] = ld_pieces<T, VEC, GV>(reinterpret_cast<const T*>(sl) + own_off);
+            if constexpr (NX) {
+              if (s != H) {
+#pragma unroll
+                for (int m = 0; m < NS; ++m)
+                  qs[m][s] = ld_pieces<T, VEC, GV>(
+                      reinterpret_cast<const T*>(sl + (1 + m) * B::FPLANE) + own_off);
+              }
+            }
+            xslot = (xslot + 1 == RF) ? 0 : xslot + 1;
+          }
+        }
 
         // ---- Laplacian of hij_c
         V lap;
@@ -378,7 +402,13 @@ __device__ __forceinline__ void tensor_stage_body(const TensorFusedParams<T>& p,
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty_p[pslot]);
     }
-    if (n >= H) {
+    if constexpr (SMEMX) {
+      // the oldest plane of the x stencil is no longer needed
+      if (n >= 2 * H) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_f[(n - 2 * H) % RF]);
+      }
+    } else if (n >= H) {
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty_f[(n - H) % RF]);
     }
@@ -393,7 +423,7 @@ __device__ __forceinline__ void tensor_stage_body(const TensorFusedParams<T>& p,
   }
 }
 
-template <typename T, int H, int NS, int BY, int TZ, int P, int MINB, int VEC_>
+template <typename T, int H, int NS, int BY, int TZ, int P, int MINB, int VEC_, bool SMEMX>
 __global__ void __launch_bounds__(BY* TZ + 32, MINB)
     tensor_stage_ws_kernel(const __grid_constant__ TensorFusedParams<T> p,
                            const __grid_constant__ CUtensorMap map_h,
@@ -402,17 +432,22 @@ __global__ void __launch_bounds__(BY* TZ + 32, MINB)
                            const __grid_constant__ CUtensorMap map_kh,
                            const __grid_constant__ CUtensorMap map_kd) {
   // packed component (1,1),(1,2),(1,3),(2,2),(2,3),(3,3) = fastest grid dimension
+#define PSB_TENSOR_BODY(CI_, CJ_)                                                        \
+  tensor_stage_body<T, H, NS, BY, TZ, P, VEC_, SMEMX, CI_, CJ_>(p, map_h, map_s, map_d,    \
+                                                                 map_kh, map_kd)
   switch (blockIdx.x % 6) {
-    case 0: tensor_stage_body<T, H, NS, BY, TZ, P, VEC_, 0, 0>(p, map_h, map_s, map_d, map_kh, map_kd); break;
-    case 1: tensor_stage_body<T, H, NS, BY, TZ, P, VEC_, 0, 1>(p, map_h, map_s, map_d, map_kh, map_kd); break;
-    case 2: tensor_stage_body<T, H, NS, BY, TZ, P, VEC_, 0, 2>(p, map_h, map_s, map_d, map_kh, map_kd); break;
-    case 3: tensor_stage_body<T, H, NS, BY, TZ, P, VEC_, 1, 1>(p, map_h, map_s, map_d, map_kh, map_kd); break;
-    case 4: tensor_stage_body<T, H, NS, BY, TZ, P, VEC_, 1, 2>(p, map_h, map_s, map_d, map_kh, map_kd); break;
-    default: tensor_stage_body<T, H, NS, BY, TZ, P, VEC_, 2, 2>(p, map_h, map_s, map_d, map_kh, map_kd); break;
+    case 0: PSB_TENSOR_BODY(0, 0); break;
+    case 1: PSB_TENSOR_BODY(0, 1); break;
+    case 2: PSB_TENSOR_BODY(0, 2); break;
+    case 3: PSB_TENSOR_BODY(1, 1); break;
+    case 4: PSB_TENSOR_BODY(1, 2); break;
+    default: PSB_TENSOR_BODY(2, 2); break;
   }
+#undef PSB_TENSOR_BODY
 }
 
-constexpr int tws_smem_bytes(int es, int H, int NS, int BY, int TZ, int P, int VEC) {
+constexpr int tws_smem_bytes(int es, int H, int NS, int BY, int TZ, int P, int VEC,
+                             bool smemx) {
   const int BZ = TZ * VEC;
   const int GV = ws_gcd(VEC, H);
   const int HL = ((H + GV - 1) / GV) * GV;
@@ -421,20 +456,24 @@ constexpr int tws_smem_bytes(int es, int H, int NS, int BY, int TZ, int P, int V
   const int fplane = (((BY + 2 * H) * W * es + 127) / 128) * 128;
   const int pww = ((BZ + H % WQ + WQ - 1) / WQ) * WQ;
   const int pwtile = ((BY * pww * es + 127) / 128) * 128;
-  return (H + 1 + P) * (1 + NS) * fplane + (P + 1) * 3 * pwtile +
-         (2 * (H + 1 + P) + 2 * (P + 1)) * 8 + 128;
+  const int rf = smemx ? 2 * H + 1 + P : H + 1 + P;
+  return rf * (1 + NS) * fplane + (P + 1) * 3 * pwtile + (2 * rf + 2 * (P + 1)) * 8 + 128;
 }
-constexpr int tws_pick_tz(int es, int H, int NS, int BY, int P, int VEC) {
+// two CTAs per SM where possible (113 KB each), else whatever fits
+constexpr int tws_pick_tz(int es, int H, int NS, int BY, int P, int VEC, bool smemx) {
   for (int tz = 128 / VEC; tz >= 16; tz /= 2)
-    if (tws_smem_bytes(es, H, NS, BY, tz, P, VEC) <= SMEM_LIMIT) return tz;
+    if (tws_smem_bytes(es, H, NS, BY, tz, P, VEC, smemx) <= 113 * 1024) return tz;
+  for (int tz = 128 / VEC; tz >= 16; tz /= 2)
+    if (tws_smem_bytes(es, H, NS, BY, tz, P, VEC, smemx) <= SMEM_LIMIT) return tz;
   return 16;
 }
 
-template <typename T, int H, int NS, int VEC, int BY = 4, int P = 2, int MINB = 1>
+template <typename T, int H, int NS, int VEC, int BY = 4, int P = 2, int MINB = 1,
+          bool SMEMX = false>
 static int launch_tensor_ws(const psb_tensor_fused_args* a, cudaStream_t stream,
                             int64_t* count) {
-  constexpr int TZ = tws_pick_tz((int)sizeof(T), H, NS, BY, P, VEC);
-  using C = TwsCfg<T, H, NS, BY, TZ, P, VEC>;
+  constexpr int TZ = tws_pick_tz((int)sizeof(T), H, NS, BY, P, VEC, SMEMX);
+  using C = TwsCfg<T, H, NS, BY, TZ, P, VEC, SMEMX>;
   using B = typename C::B;
   // the scalar stage's x-chunk schedule (split tail included)
   psb_scalar_stage_args xa;
@@ -442,7 +481,8 @@ static int launch_tensor_ws(const psb_tensor_fused_args* a, cudaStream_t stream,
   xa.x_begin = 0;
   xa.x_end = a->Nx;
   xa.tune_xchunk = a->tune_xchunk;
-  const XLayout L = x_layout(&xa, WS_DEFAULT_XCHUNK);
+  const XLayout L = x_layout(&xa, WS_DEFAULT_XCHUNK,
+                             6 * ((a->Nz + B::BZ - 1) / B::BZ) * ((a->Ny + BY - 1) / BY));
   if (count != nullptr) {
     *count = 6 * ((a->Nz + B::BZ - 1) / B::BZ) * ((a->Ny + BY - 1) / BY) * (int64_t)L.n1;
     return 0;
@@ -507,7 +547,7 @@ static int launch_tensor_ws(const psb_tensor_fused_args* a, cudaStream_t stream,
     return rc;
   fill_tail(p.tail, a->tail, nullptr);
   dim3 block(C::THREADS, 1, 1);
-  auto kern = tensor_stage_ws_kernel<T, H, NS, BY, TZ, P, MINB, VEC>;
+  auto kern = tensor_stage_ws_kernel<T, H, NS, BY, TZ, P, MINB, VEC, SMEMX>;
   PSB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       C::SMEM_BYTES));
   kern<<<grid, block, C::SMEM_BYTES, stream>>>(p, mh, ms, md, mkh, mkd);
@@ -523,9 +563,13 @@ static int tensor_fused_ns(const psb_tensor_fused_args* a, cudaStream_t s, int64
     constexpr int VV = sizeof(T) == 4 ? 4 : 2;
     if (a->nscalars == 2 && (sizeof(T) == 8 || a->Nz % 4 == 0)) {
       if (a->tune_variant == 2) return launch_tensor_ws<T, H, 2, VV, 4, 1, 3>(a, s, count);
-      if (a->tune_variant == 3) return launch_tensor_ws<T, H, 2, VV, 8, 1, 2>(a, s, count);
       if (a->tune_variant == 4) return launch_tensor_ws<T, H, 2, VV, 8, 2, 1>(a, s, count);
-      if (a->tune_variant == 5) return launch_tensor_ws<T, H, 2, VV, 4, 1, 2>(a, s, count);
+      if (a->tune_variant == 6)
+        return launch_tensor_ws<T, H, 2, VV, 4, 2, 2, true>(a, s, count);
+      if (a->tune_variant == 7)
+        return launch_tensor_ws<T, H, 2, VV, 4, 1, 2, true>(a, s, count);
+      if (a->tune_variant == 8)
+        return launch_tensor_ws<T, H, 2, VV, 4, 1, 3, true>(a, s, count);
     }
   }
   if constexpr (sizeof(T) == 4) {

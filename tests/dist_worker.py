@@ -176,6 +176,73 @@ def _fused_case(rank, world, backend, nscalars, energy, mode="peer"):
         assert float(lo) == float(hi)
 
 
+def _fused_gw_case(rank, world, backend, dtype):
+    """Config-4 structure on several ranks: fused scalar stage + fused tensor stage, both with
+    peer-memory halos, the stage's inter-GPU barrier and the background in the tensor kernel's
+    watcher CTA == the C oracle on the global lattice."""
+    import pystella_b200 as ps
+    import oracle as O
+    from oracle import c_oracle as CO
+    h = 2
+    grid = (20 * world + 4, 12, 16)          # uneven slabs
+    dx = tuple(5 / n for n in grid)
+    dt = 0.1 * min(dx)
+    rng = np.random.default_rng(7)
+    pad = tuple(n + 2 * h for n in grid)
+    npdt = np.float64 if dtype == "f64" else np.float32
+    f0 = (0.2 + 1e-2 * rng.standard_normal((2,) + pad)).astype(npdt)
+    d0 = (-0.1 + 1e-2 * rng.standard_normal((2,) + pad)).astype(npdt)
+    h0 = (1e-3 * rng.standard_normal((6,) + pad)).astype(npdt)
+    dh0 = (1e-3 * rng.standard_normal((6,) + pad)).astype(npdt)
+    terms = [(0.5, (2, 0)), (0.3, (2, 2))]
+    gs = float(np.prod(grid))
+
+    # ---- oracle: global lattice, reference loop with the background
+    F, D, Hh, DH = (x.astype(np.float64) for x in (f0, d0, h0, dh0))
+    kF, kD, kH, kDH = (np.zeros_like(x) for x in (F, D, Hh, DH))
+    pot = CO.make_potential(2, terms)
+    lap_f, dfdx, lap_hij = CO.gw_initial_derivatives(F, Hh, h, dx)
+    en = CO.scalar_energy(F, D, lap_f, h, 1.0, gs, pot)
+    e0 = 0.37
+    adot = float(np.sqrt(8 * np.pi / 3 * e0))
+    state = np.array([1.0, adot, adot, 0.0, 0.0])
+    A, B, _ = O.LSRK_TABLES["LowStorageRK54"]
+    nsteps = 2
+    CO.preheating_gw_steps(nsteps, A, B, F, D, kF, kD, lap_f, dfdx, Hh, DH, kH, kDH, lap_hij, h,
+                           dx, dt, 1.0, gs, pot, state, en, True)
+
+    # ---- device, x-slabs
+    decomp = ps.DomainDecomposition((world, 1, 1), h, grid_shape=grid)
+    rs, start = decomp.get_rank_shape_start(grid)
+    sl = slice(start[0], start[0] + rs[0] + 2 * h)
+    arrays = dict(f=f0, dfdt=d0, hij=h0, dhijdt=dh0)
+    arrays = {k: torch.from_numpy(np.ascontiguousarray(v[:, sl])).cuda()
+              for k, v in arrays.items()}
+    scalar = ps.ScalarSector(2, potential=lambda g: g[0]**2 / 2 + 0.3 * g[0]**2 * g[1]**2)
+    gw = ps.TensorPerturbationSector([scalar])
+    st = ps.LowStorageRK54([scalar, gw], halo_shape=h, dt=dt, dx=dx, decomp=decomp,
+                           MapKernel=ps.FusedStencilStage, energy=True)
+    dexp = ps.DeviceExpansion(e0, ps.LowStorageRK54, grid_size=gs, decomp=decomp, nscalars=2)
+    dexp.attach(st)
+    for _ in range(nsteps):
+        for s in range(5):
+            st(s, a=dexp.a, hubble=dexp.hubble, **arrays)
+            dexp.step(s, st, dt)
+    torch.cuda.synchronize()
+    assert st._halo_mode == "peer"
+    got = dexp.get()
+    tol = 1e-12 if dtype == "f64" else 3e-5
+    assert np.isclose(got["a"], state[0], rtol=1e-13 if dtype == "f64" else 1e-6)
+    assert np.isclose(got["hubble"], state[2], rtol=1e-11 if dtype == "f64" else 1e-5)
+    inner = slice(start[0] + h, start[0] + h + rs[0])
+    for name, ref in (("f", F), ("dfdt", D), ("hij", Hh), ("dhijdt", DH)):
+        for c in range(ref.shape[0]):
+            g = arrays[name][c].cpu().numpy()[h:-h, h:-h, h:-h].astype(np.float64)
+            r = ref[c][inner, h:-h, h:-h]
+            err = np.max(np.abs(g - r)) / np.max(np.abs(ref[c]))
+            assert err < tol, f"rank {rank} {name}[{c}]: {err}"
+
+
 def _fourier_case(rank, world, backend, proc_shape=None):
     """Slab-distributed DFT / RayleighGenerator / PowerSpectra == the single-rank results
     on the gathered arrays (test/test_dft.py on more than one rank)."""
@@ -278,6 +345,8 @@ def _worker(rank, world, port, case, args):
             _fourier_case(rank, world, backend, proc_shape)
         elif case == "gpu_reduction":
             _reduction_case(rank, world, backend)
+        elif case == "gpu_fused_gw":
+            _fused_gw_case(rank, world, backend, args[0])
         elif case == "gpu_fused":
             _fused_case(rank, world, backend, int(args[0]), args[1] == "1",
                         args[2] if len(args) > 2 else "peer")

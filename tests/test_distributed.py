@@ -114,3 +114,14 @@ def test_fused_stepper_four_ranks(mode):
     if _ngpus() < 4:
         pytest.skip("needs 4 GPUs")
     _run("gpu_fused", 4, "1", "1", mode)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+def test_fused_scalar_plus_tensor_two_ranks(dtype):
+    """Config-4 structure over peer memory: scalar + tensor stage kernels store their
+    boundary planes into the neighbour's halos, the tensor kernel's watcher CTA runs the
+    inter-GPU barrier and the background stage; == the C oracle on the global lattice."""
+    if _ngpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    _run("gpu_fused_gw", 2, dtype)
