@@ -242,7 +242,7 @@ def reduce_poly(arrays, halos, terms, ops, flags, shape, queue=None, strict=Fals
     for r, (op, fl) in enumerate(zip(ops, flags)):
         args.op[r] = op
         args.flags[r] = fl
-    key = (dev.index, torch.cuda.current_stream().cuda_stream)
+    key = (dev.index, _lib.stream_ptr(queue))   # the stream the kernels actually run on
     if key not in _reduce_ws:
         n = lib.psb_reduce_workspace_doubles(_lib.MAX_RED_OUTPUTS)
         _reduce_ws[key] = torch.empty(n, dtype=torch.float64, device=dev)

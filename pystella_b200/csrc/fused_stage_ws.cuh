@@ -117,6 +117,35 @@ __device__ __forceinline__ void st_pieces(T* p, const Vec<T, VEC>& x) {
   }
 }
 
+// "Split" vectors: when the interior starts only GV < VEC elements aligned (fp32, h = 2:
+// 8 bytes), a thread's VEC sites are NOT consecutive but VEC/GV pieces of GV consecutive
+// sites, GS = TZ*GV elements apart, so that the lanes of a warp touch CONSECUTIVE GV-element
+// pieces: every shared-memory load and every global store of a piece is one contiguous
+// 32*GV-element span (ncu, consecutive mapping: 8-byte pieces at a 16-byte lane stride took
+// twice the ideal shared-memory wavefronts and L2 store sectors -- 43 % of all wavefronts).
+template <typename T, int VEC, int GV, int GS>
+__device__ __forceinline__ Vec<T, VEC> ld_pieces_s(const T* p) {
+  Vec<T, VEC> r;
+#pragma unroll
+  for (int g = 0; g < VEC / GV; ++g) {
+    Vec<T, GV> t = ld_vec<T, GV>(p + g * GS);
+#pragma unroll
+    for (int v = 0; v < GV; ++v) r.v[g * GV + v] = t.v[v];
+  }
+  return r;
+}
+// pact[g]: piece g lies inside the lattice
+template <typename T, int VEC, int GV, int GS>
+__device__ __forceinline__ void st_pieces_s(T* p, const Vec<T, VEC>& x, const bool* pact) {
+#pragma unroll
+  for (int g = 0; g < VEC / GV; ++g) {
+    Vec<T, GV> t;
+#pragma unroll
+    for (int v = 0; v < GV; ++v) t.v[v] = x.v[g * GV + v];
+    if (pact[g]) st_plain<T, GV>(p + g * GS, t);
+  }
+}
+
 #ifdef PSB_GENERATED_RHS
 // Generated-RHS instantiation (run-time compiled with NVRTC by pystella_b200/codegen.py):
 // the translation unit defines, before including this header,
@@ -234,23 +263,38 @@ __global__ void __launch_bounds__(BY* TZ + 32, MINB)
   }
 
   // ============================ consumer warps ==================================
+  // split vectors (fp32, h = 2, consecutive mapping impossible at 16-byte alignment): the
+  // thread's VEC sites are VEC/GV pieces of GV sites, GS apart; see ld_pieces_s
+  constexpr bool SPLIT = !AL && (GV < VEC);
+  constexpr int NG = VEC / GV;
+  constexpr int TS = SPLIT ? GV : VEC;        // z stride between threads (sites)
+  constexpr int GS = SPLIT ? TZ * GV : GV;    // z stride between the pieces of a vector
+  constexpr int ZG = SPLIT ? NG : 1;          // row segments a thread differentiates along z
+  constexpr int ZW = SPLIT ? GV : VEC;        // sites per segment
+  auto voff = [](int v) { return (v / GV) * GS + (v % GV); };   // element offset of site v
   const int tz = tid % TZ, ty = tid / TZ;
   const int lane = tid & 31;
-  const int j = y0 + ty, k = z0 + tz * VEC - C::SH;
-  // AL: sites k .. k+VEC-1 may stick out of the row at either end
+  const int j = y0 + ty, k = z0 + tz * TS - C::SH;
+  // AL: sites k .. k+VEC-1 may stick out of the row at either end; SPLIT: whole pieces may
+  // lie beyond the end of the row
   bool ok[VEC];
   bool all_ok = true, any_ok = false;
 #pragma unroll
   for (int v = 0; v < VEC; ++v) {
-    ok[v] = (j < p.Ny) && (k + v >= 0) && (k + v < p.Nz);
+    ok[v] = (j < p.Ny) && (k + voff(v) >= 0) && (k + voff(v) < p.Nz);
     all_ok = all_ok && ok[v];
     any_ok = any_ok || ok[v];
   }
-  const bool active = AL ? any_ok : ((j < p.Ny) && (k < p.Nz));
+  bool pact[NG];
+#pragma unroll
+  for (int g = 0; g < NG; ++g) pact[g] = ok[g * GV];
+  const bool active = (AL || SPLIT) ? any_ok : ((j < p.Ny) && (k < p.Nz));
   // store VEC results: one (or VEC/GV) vector stores, element-wise where masked
   auto put = [&](T* dst, const V& x, auto stream_tag) {
     constexpr bool STREAM = decltype(stream_tag)::value;
-    if constexpr (!AL) {
+    if constexpr (SPLIT) {
+      st_pieces_s<T, VEC, GV, GS>(dst, x, pact);
+    } else if constexpr (!AL) {
       st_pieces<T, VEC, GV, STREAM>(dst, x);
     } else {
       if (all_ok) {
@@ -278,8 +322,8 @@ __global__ void __launch_bounds__(BY* TZ + 32, MINB)
   const T two_h = (T)2 * hubble;
   const T a_sq = a * a;
 
-  const int own_off = (ty + H) * W + HL + tz * VEC;   // elements, within an f plane
-  const int pw_off = ty * C::PWW + C::PWL + tz * VEC;  // elements, within a pw tile
+  const int own_off = (ty + H) * W + HL + tz * TS;   // elements, within an f plane
+  const int pw_off = ty * C::PWW + C::PWL + tz * TS;  // elements, within a pw tile
 
   V q[NF][2 * H + 1];
 #pragma unroll
@@ -306,7 +350,7 @@ __global__ void __launch_bounds__(BY* TZ + 32, MINB)
     for (int f = 0; f < NF; ++f) {
 #pragma unroll
       for (int s = 0; s < 2 * H; ++s) q[f][s] = q[f][s + 1];
-      q[f][2 * H] = ld_pieces<T, VEC, GV>(
+      q[f][2 * H] = ld_pieces_s<T, VEC, GV, GS>(
           reinterpret_cast<const T*>(fring + (slot * NF + f) * C::FPLANE) + own_off);
     }
 
@@ -321,31 +365,33 @@ __global__ void __launch_bounds__(BY* TZ + 32, MINB)
         V lap[NF], dold[NF], kfo[NF], kdo[NF];
 #pragma unroll
         for (int f = 0; f < NF; ++f) {
-          dold[f] = ld_pieces<T, VEC, GV>(
+          dold[f] = ld_pieces_s<T, VEC, GV, GS>(
               reinterpret_cast<const T*>(pw + (0 * NF + f) * C::PWTILE) + pw_off);
           if (read_k) {
-            kfo[f] = ld_pieces<T, VEC, GV>(
+            kfo[f] = ld_pieces_s<T, VEC, GV, GS>(
                 reinterpret_cast<const T*>(pw + (1 * NF + f) * C::PWTILE) + pw_off);
-            kdo[f] = ld_pieces<T, VEC, GV>(
+            kdo[f] = ld_pieces_s<T, VEC, GV, GS>(
                 reinterpret_cast<const T*>(pw + (2 * NF + f) * C::PWTILE) + pw_off);
           } else {
 #pragma unroll
             for (int v = 0; v < VEC; ++v) kfo[f].v[v] = kdo[f].v[v] = (T)0;
           }
           const T* pl = reinterpret_cast<const T*>(fring + (cslot * NF + f) * C::FPLANE);
-          constexpr int NVZ = (VEC + 2 * HL) / GV;  // aligned pieces covering the row
-          T zrow[NVZ * GV];
+          constexpr int NVZ = (ZW + 2 * HL) / GV;  // aligned pieces covering a row segment
+          T zrow[ZG][ZW + 2 * HL];
 #pragma unroll
-          for (int w = 0; w < NVZ; ++w) {
-            Vec<T, GV> t = ld_vec<T, GV>(pl + own_off - HL + w * GV);
+          for (int zg = 0; zg < ZG; ++zg)
 #pragma unroll
-            for (int v = 0; v < GV; ++v) zrow[w * GV + v] = t.v[v];
-          }
+            for (int w = 0; w < NVZ; ++w) {
+              Vec<T, GV> t = ld_vec<T, GV>(pl + own_off + zg * GS - HL + w * GV);
+#pragma unroll
+              for (int v = 0; v < GV; ++v) zrow[zg][w * GV + v] = t.v[v];
+            }
           V yn[2 * H + 1];
 #pragma unroll
           for (int s = 1; s <= H; ++s) {
-            yn[H + s] = ld_pieces<T, VEC, GV>(pl + own_off + s * W);
-            yn[H - s] = ld_pieces<T, VEC, GV>(pl + own_off - s * W);
+            yn[H + s] = ld_pieces_s<T, VEC, GV, GS>(pl + own_off + s * W);
+            yn[H - s] = ld_pieces_s<T, VEC, GV, GS>(pl + own_off - s * W);
           }
 #pragma unroll
           for (int v = 0; v < VEC; ++v) {
@@ -360,8 +406,8 @@ __global__ void __launch_bounds__(BY* TZ + 32, MINB)
               sx = sx + cs * q[f][H - s].v[v];
               sy = sy + cs * yn[H + s].v[v];
               sy = sy + cs * yn[H - s].v[v];
-              sz = sz + cs * zrow[HL + v + s];
-              sz = sz + cs * zrow[HL + v - s];
+              sz = sz + cs * zrow[SPLIT ? v / GV : 0][HL + (SPLIT ? v % GV : v) + s];
+              sz = sz + cs * zrow[SPLIT ? v / GV : 0][HL + (SPLIT ? v % GV : v) - s];
             }
             lap[f].v[v] = sx * p.inv_dx2[0] + sy * p.inv_dx2[1] + sz * p.inv_dx2[2];
           }
@@ -378,7 +424,7 @@ __global__ void __launch_bounds__(BY* TZ + 32, MINB)
             T sk = (T)0, sg = (T)0;
 #pragma unroll
             for (int v = 0; v < VEC; ++v) {
-              if constexpr (AL) {
+              if constexpr (AL || SPLIT) {
                 if (!ok[v]) continue;
               }
               const T dv = dold[f].v[v];
@@ -392,7 +438,7 @@ __global__ void __launch_bounds__(BY* TZ + 32, MINB)
 #ifdef PSB_GENERATED_RHS
 #pragma unroll
           for (int v = 0; v < VEC; ++v) {
-            if constexpr (AL) {
+            if constexpr (AL || SPLIT) {
               if (!ok[v]) continue;
             }
             T fsite[NF];
@@ -404,7 +450,7 @@ __global__ void __launch_bounds__(BY* TZ + 32, MINB)
           const V Vv = poly_eval<T, NF, VEC>(p.nvterms, p.vcoef, p.vpower, fc);
 #pragma unroll
           for (int v = 0; v < VEC; ++v) {
-            if constexpr (AL) {
+            if constexpr (AL || SPLIT) {
               if (!ok[v]) continue;
             }
             sp = sp + Vv.v[v];
@@ -488,11 +534,11 @@ __global__ void __launch_bounds__(BY* TZ + 32, MINB)
           if (p.wrap_z) {
 #pragma unroll
             for (int v = 0; v < VEC; ++v) {
-              if constexpr (AL) {
+              if constexpr (AL || SPLIT) {
                 if (!ok[v]) continue;
               }
-              if (k + v < H) fout[v + p.Nz] = fo.v[v];
-              if (k + v >= p.Nz - H) fout[v - p.Nz] = fo.v[v];
+              if (k + voff(v) < H) fout[voff(v) + p.Nz] = fo.v[v];
+              if (k + voff(v) >= p.Nz - H) fout[voff(v) - p.Nz] = fo.v[v];
             }
           }
         }

@@ -150,10 +150,21 @@ __device__ __forceinline__ void tensor_stage_body(const TensorFusedParams<T>& p,
     return;
   }
 
+  // split vectors (fp32, h = 2): pieces of GV sites, GS apart; see ld_pieces_s
+  constexpr bool SPLIT = (GV < VEC);
+  constexpr int NG = VEC / GV;
+  constexpr int TS = SPLIT ? GV : VEC;        // z stride between threads (sites)
+  constexpr int GS = SPLIT ? TZ * GV : GV;    // z stride between the pieces of a vector
+  constexpr int ZG = SPLIT ? NG : 1;          // row segments a thread differentiates along z
+  constexpr int ZW = SPLIT ? GV : VEC;        // sites per segment
+  auto voff = [](int v) { return (v / GV) * GS + (v % GV); };   // element offset of site v
   const int tz = tid % TZ, ty = tid / TZ;
   const int lane = tid & 31;
-  const int j = y0 + ty, k = z0 + tz * VEC;
-  const bool active = (j < p.Ny) && (k < p.Nz);
+  const int j = y0 + ty, k = z0 + tz * TS;
+  bool pact[NG];
+#pragma unroll
+  for (int g = 0; g < NG; ++g) pact[g] = (j < p.Ny) && (k + g * GS < p.Nz);
+  const bool active = pact[0];
   const int64_t Pz = p.Nz + 2 * H, Py = p.Ny + 2 * H;
   const int64_t plane_stride = Py * Pz;
   const int64_t site0 = ((int64_t)H * Py + (j + H)) * Pz + (k + H);
@@ -162,8 +173,8 @@ __device__ __forceinline__ void tensor_stage_body(const TensorFusedParams<T>& p,
   if (p.hubble_dev) hubble = (T)(*p.hubble_dev);
   const T two_h = (T)2 * hubble;
 
-  const int own_off = (ty + H) * W + HL + tz * VEC;
-  const int pw_off = ty * B::PWW + B::PWL + tz * VEC;
+  const int own_off = (ty + H) * W + HL + tz * TS;
+  const int pw_off = ty * B::PWW + B::PWL + tz * TS;
 
   V qh[2 * H + 1];
   V qs[NX ? NS : 1][2 * H + 1];   // x register queue of the sources: only for d_x
@@ -190,13 +201,13 @@ __device__ __forceinline__ void tensor_stage_body(const TensorFusedParams<T>& p,
       const unsigned char* sl = fring + slot * C::FSLOT;
 #pragma unroll
       for (int s = 0; s < 2 * H; ++s) qh[s] = qh[s + 1];
-      qh[2 * H] = ld_pieces<T, VEC, GV>(reinterpret_cast<const T*>(sl) + own_off);
+      qh[2 * H] = ld_pieces_s<T, VEC, GV, GS>(reinterpret_cast<const T*>(sl) + own_off);
       if constexpr (NX) {
 #pragma unroll
         for (int m = 0; m < NS; ++m) {
 #pragma unroll
           for (int s = 0; s < 2 * H; ++s) qs[m][s] = qs[m][s + 1];
-          qs[m][2 * H] = ld_pieces<T, VEC, GV>(
+          qs[m][2 * H] = ld_pieces_s<T, VEC, GV, GS>(
               reinterpret_cast<const T*>(sl + (1 + m) * B::FPLANE) + own_off);
         }
       }
@@ -211,28 +222,28 @@ __device__ __forceinline__ void tensor_stage_body(const TensorFusedParams<T>& p,
       if (active) {
         const unsigned char* pw = pring + pslot * C::PWSLOT;
         const unsigned char* cen = fring + cslot * C::FSLOT;
-        V dold = ld_pieces<T, VEC, GV>(reinterpret_cast<const T*>(pw) + pw_off);
+        V dold = ld_pieces_s<T, VEC, GV, GS>(reinterpret_cast<const T*>(pw) + pw_off);
         V kho, kdo;
         if (read_k) {
-          kho = ld_pieces<T, VEC, GV>(reinterpret_cast<const T*>(pw + B::PWTILE) + pw_off);
-          kdo = ld_pieces<T, VEC, GV>(reinterpret_cast<const T*>(pw + 2 * B::PWTILE) + pw_off);
+          kho = ld_pieces_s<T, VEC, GV, GS>(reinterpret_cast<const T*>(pw + B::PWTILE) + pw_off);
+          kdo = ld_pieces_s<T, VEC, GV, GS>(reinterpret_cast<const T*>(pw + 2 * B::PWTILE) + pw_off);
         } else {
 #pragma unroll
           for (int v = 0; v < VEC; ++v) kho.v[v] = kdo.v[v] = (T)0;
         }
-        constexpr int NVZ = (VEC + 2 * HL) / GV;
+        constexpr int NVZ = (ZW + 2 * HL) / GV;   // aligned pieces covering one row segment
         if constexpr (SMEMX) {
           // x neighbours of the centre plane n-H: planes n-2H .. n, all still in the ring
           int xslot = (n - 2 * H) % RF;
 #pragma unroll
           for (int s = 0; s < 2 * H + 1; ++s) {
             const unsigned char* sl = fring + xslot * C::FSLOT;
-            qh[s] = ld_pieces<T, VEC, GV>(reinterpret_cast<const T*>(sl) + own_off);
+            qh[s] = ld_pieces_s<T, VEC, GV, GS>(reinterpret_cast<const T*>(sl) + own_off);
             if constexpr (NX) {
               if (s != H) {
 #pragma unroll
                 for (int m = 0; m < NS; ++m)
-                  qs[m][s] = ld_pieces<T, VEC, GV>(
+                  qs[m][s] = ld_pieces_s<T, VEC, GV, GS>(
                       reinterpret_cast<const T*>(sl + (1 + m) * B::FPLANE) + own_off);
               }
             }
@@ -244,18 +255,20 @@ __device__ __forceinline__ void tensor_stage_body(const TensorFusedParams<T>& p,
         V lap;
         {
           const T* pl = reinterpret_cast<const T*>(cen);
-          T zrow[NVZ * GV];
+          T zrow[ZG][ZW + 2 * HL];
 #pragma unroll
-          for (int w = 0; w < NVZ; ++w) {
-            Vec<T, GV> t = ld_vec<T, GV>(pl + own_off - HL + w * GV);
+          for (int zg = 0; zg < ZG; ++zg)
 #pragma unroll
-            for (int v = 0; v < GV; ++v) zrow[w * GV + v] = t.v[v];
-          }
+            for (int w = 0; w < NVZ; ++w) {
+              Vec<T, GV> t = ld_vec<T, GV>(pl + own_off + zg * GS - HL + w * GV);
+#pragma unroll
+              for (int v = 0; v < GV; ++v) zrow[zg][w * GV + v] = t.v[v];
+            }
           V yn[2 * H + 1];
 #pragma unroll
           for (int s = 1; s <= H; ++s) {
-            yn[H + s] = ld_pieces<T, VEC, GV>(pl + own_off + s * W);
-            yn[H - s] = ld_pieces<T, VEC, GV>(pl + own_off - s * W);
+            yn[H + s] = ld_pieces_s<T, VEC, GV, GS>(pl + own_off + s * W);
+            yn[H - s] = ld_pieces_s<T, VEC, GV, GS>(pl + own_off - s * W);
           }
 #pragma unroll
           for (int v = 0; v < VEC; ++v) {
@@ -268,8 +281,8 @@ __device__ __forceinline__ void tensor_stage_body(const TensorFusedParams<T>& p,
               sx = sx + cs * qh[H - s].v[v];
               sy = sy + cs * yn[H + s].v[v];
               sy = sy + cs * yn[H - s].v[v];
-              sz = sz + cs * zrow[HL + v + s];
-              sz = sz + cs * zrow[HL + v - s];
+              sz = sz + cs * zrow[SPLIT ? v / GV : 0][HL + (SPLIT ? v % GV : v) + s];
+              sz = sz + cs * zrow[SPLIT ? v / GV : 0][HL + (SPLIT ? v % GV : v) - s];
             }
             lap.v[v] = sx * p.inv_dx2[0] + sy * p.inv_dx2[1] + sz * p.inv_dx2[2];
           }
@@ -301,8 +314,8 @@ __device__ __forceinline__ void tensor_stage_body(const TensorFusedParams<T>& p,
             V yn[2 * H + 1];
 #pragma unroll
             for (int s = 1; s <= H; ++s) {
-              yn[H + s] = ld_pieces<T, VEC, GV>(pl + own_off + s * W);
-              yn[H - s] = ld_pieces<T, VEC, GV>(pl + own_off - s * W);
+              yn[H + s] = ld_pieces_s<T, VEC, GV, GS>(pl + own_off + s * W);
+              yn[H - s] = ld_pieces_s<T, VEC, GV, GS>(pl + own_off - s * W);
             }
 #pragma unroll
             for (int v = 0; v < VEC; ++v) {
@@ -317,21 +330,24 @@ __device__ __forceinline__ void tensor_stage_body(const TensorFusedParams<T>& p,
             }
           }
           if constexpr (NZ) {
-            T zrow[NVZ * GV];
+            T zrow[ZG][ZW + 2 * HL];
 #pragma unroll
-            for (int w = 0; w < NVZ; ++w) {
-              Vec<T, GV> t = ld_vec<T, GV>(pl + own_off - HL + w * GV);
+            for (int zg = 0; zg < ZG; ++zg)
 #pragma unroll
-              for (int v = 0; v < GV; ++v) zrow[w * GV + v] = t.v[v];
-            }
+              for (int w = 0; w < NVZ; ++w) {
+                Vec<T, GV> t = ld_vec<T, GV>(pl + own_off + zg * GS - HL + w * GV);
+#pragma unroll
+                for (int v = 0; v < GV; ++v) zrow[zg][w * GV + v] = t.v[v];
+              }
 #pragma unroll
             for (int v = 0; v < VEC; ++v) {
               T g = (T)0;
 #pragma unroll
               for (int s = 1; s <= H; ++s) {
                 const T cs = (T)grad_coef<H>(s);
-                g = (s == 1) ? cs * zrow[HL + v + s] : g + cs * zrow[HL + v + s];
-                g = g + (-cs) * zrow[HL + v - s];
+                const int zg = SPLIT ? v / GV : 0, ze = SPLIT ? v % GV : v;
+                g = (s == 1) ? cs * zrow[zg][HL + ze + s] : g + cs * zrow[zg][HL + ze + s];
+                g = g + (-cs) * zrow[zg][HL + ze - s];
               }
               gz.v[v] = g * p.inv_dx[2];
             }
@@ -362,36 +378,37 @@ __device__ __forceinline__ void tensor_stage_body(const TensorFusedParams<T>& p,
           ho.v[v] = qh[H].v[v] + p.B * khv;
           dn.v[v] = d_old + p.B * kdv;
         }
-        st_pieces<T, VEC, GV, false>(o_kh, khn);
-        st_pieces<T, VEC, GV, false>(o_kd, kdn);
-        st_pieces<T, VEC, GV, false>(o_d, dn);
-        st_pieces<T, VEC, GV, false>(o_h, ho);
+        st_pieces_s<T, VEC, GV, GS>(o_kh, khn, pact);
+        st_pieces_s<T, VEC, GV, GS>(o_kd, kdn, pact);
+        st_pieces_s<T, VEC, GV, GS>(o_d, dn, pact);
+        st_pieces_s<T, VEC, GV, GS>(o_h, ho, pact);
         if (p.wrap_x) {
-          if (i < H) st_pieces<T, VEC, GV, false>(o_h + (int64_t)p.Nx * plane_stride, ho);
+          if (i < H) st_pieces_s<T, VEC, GV, GS>(o_h + (int64_t)p.Nx * plane_stride, ho, pact);
           if (i >= p.Nx - H)
-            st_pieces<T, VEC, GV, false>(o_h - (int64_t)p.Nx * plane_stride, ho);
+            st_pieces_s<T, VEC, GV, GS>(o_h - (int64_t)p.Nx * plane_stride, ho, pact);
         }
         // NVLink: my boundary planes -> the neighbours' x halos (peer memory)
         if (p.peer_lo != nullptr && i < H)
-          st_pieces<T, VEC, GV, false>(
+          st_pieces_s<T, VEC, GV, GS>(
               p.peer_lo + comp * p.peer_lo_stride +
                   (int64_t)(p.peer_lo_Nx + H + i) * plane_stride + (int64_t)(j + H) * Pz +
                   (k + H),
-              ho);
+              ho, pact);
         if (p.peer_hi != nullptr && i >= p.Nx - H)
-          st_pieces<T, VEC, GV, false>(
+          st_pieces_s<T, VEC, GV, GS>(
               p.peer_hi + comp * p.peer_hi_stride + (int64_t)(i - p.Nx + H) * plane_stride +
                   (int64_t)(j + H) * Pz + (k + H),
-              ho);
+              ho, pact);
         if (p.wrap_y) {
-          if (j < H) st_pieces<T, VEC, GV, false>(o_h + (int64_t)p.Ny * Pz, ho);
-          if (j >= p.Ny - H) st_pieces<T, VEC, GV, false>(o_h - (int64_t)p.Ny * Pz, ho);
+          if (j < H) st_pieces_s<T, VEC, GV, GS>(o_h + (int64_t)p.Ny * Pz, ho, pact);
+          if (j >= p.Ny - H) st_pieces_s<T, VEC, GV, GS>(o_h - (int64_t)p.Ny * Pz, ho, pact);
         }
         if (p.wrap_z) {
 #pragma unroll
           for (int v = 0; v < VEC; ++v) {
-            if (k + v < H) o_h[v + p.Nz] = ho.v[v];
-            if (k + v >= p.Nz - H) o_h[v - p.Nz] = ho.v[v];
+            if (!pact[v / GV]) continue;
+            if (k + voff(v) < H) o_h[voff(v) + p.Nz] = ho.v[v];
+            if (k + voff(v) >= p.Nz - H) o_h[voff(v) - p.Nz] = ho.v[v];
           }
         }
       }

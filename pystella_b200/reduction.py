@@ -205,17 +205,23 @@ class Reduction:
                 cval = c if is_constant(c) else evaluate(c, ctx)
                 terms.append((r, float(cval), powers))
 
-        out = self._launch(arrays, halos, terms, ops, flags, shape, queue)
+        # everything after the launch (slicing, the all-reduce, the read-back) is ordered on
+        # the stream the kernels run on: `queue` may be a non-current stream (the reference
+        # passes the queue explicitly, pystella/reduction.py:206)
+        import contextlib
+        ctx_stream = torch.cuda.stream(queue) if queue is not None else contextlib.nullcontext()
+        with ctx_stream:
+            out = self._launch(arrays, halos, terms, ops, flags, shape, queue)
 
-        # one allreduce per distinct operation
-        if self.decomp.comm is not None:
-            for opname, code in (("sum", 0), ("max", 1), ("min", 2)):
-                idx = [r for r, o in enumerate(ops) if o == code]
-                if idx:
-                    sel = out[idx].contiguous()
-                    sel = self.decomp.allreduce(sel, op=opname)
-                    out[idx] = sel
-        host = out.cpu().numpy()
+            # one allreduce per distinct operation
+            if self.decomp.comm is not None:
+                for opname, code in (("sum", 0), ("max", 1), ("min", 2)):
+                    idx = [r for r, o in enumerate(ops) if o == code]
+                    if idx:
+                        sel = out[idx].contiguous()
+                        sel = self.decomp.allreduce(sel, op=opname)
+                        out[idx] = sel
+            host = out.cpu().numpy()
 
         grid_size = self.grid_size
         if grid_size is None and "avg" in self.reduction_ops:

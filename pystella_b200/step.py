@@ -547,7 +547,19 @@ class LowStorageRKStepper(Stepper):
         return self._host_stage(stage, kwargs)
 
     # -- host scalar ODEs -------------------------------------------------------
+    #: host evaluation exists for the scalar ODEs the reference itself integrates on the
+    #: host (Expansion through loopy's C target, pystella/expansion.py:91-99; the steppers'
+    #: own order tests, test/test_step.py): NOT a CPU fallback for lattices
+    HOST_MAX_ELEMENTS = 4096
+
     def _host_stage(self, stage, kwargs):
+        for name in self.dof_names:
+            if np.asarray(kwargs[name]).size > self.HOST_MAX_ELEMENTS:
+                raise PsbError(
+                    f"'{name}' is a NumPy array of {np.asarray(kwargs[name]).size} elements: "
+                    "lattice fields must be torch tensors on the GPU (the host path only "
+                    "integrates small ODE systems such as the FLRW background; there is no "
+                    "CPU fallback)")
         ctx = dict(kwargs)
         ctx.update(self.tmp_arrays)
         if self.dt is not None:
