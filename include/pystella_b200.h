@@ -172,6 +172,9 @@ typedef struct psb_scalar_stage_args {
   int32_t tune_xchunk;           /* 0 = default; planes marched per CTA              */
   int32_t tune_variant;          /* 0 = auto; see DESIGN.md (kernel variants)        */
   const psb_stage_tail* tail;    /* fused only; HOST pointer, NULL = no in-kernel tail */
+  int32_t tune_prefetch;         /* fused: planes the producer prefetches into L2 ahead of
+                                    its loads; 0 = default, < 0 = none                  */
+  int32_t reserved0;
 } psb_scalar_stage_args;
 
 int psb_scalar_stage_fused(const psb_scalar_stage_args* args, void* stream);
@@ -263,6 +266,8 @@ typedef struct psb_tensor_fused_args {
   const psb_stage_tail* tail;    /* HOST pointer, NULL = none                         */
   int32_t tune_xchunk;           /* 0 = default                                       */
   int32_t tune_variant;          /* 0 = auto; 1 = 8-byte vectors for fp32             */
+  int32_t tune_prefetch;         /* L2 prefetch distance in planes; 0 = default, < 0 none */
+  int32_t reserved0;
 } psb_tensor_fused_args;
 int psb_tensor_stage_fused(const psb_tensor_fused_args* args, void* stream);
 /* CTAs of that launch (= marker rows its stage tail needs); -1 on error. */

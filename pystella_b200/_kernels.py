@@ -39,7 +39,8 @@ def scalar_stage(*, fused, f_in, f_out, dfdt, kf, kdfdt, lap_f=None, h, dx=(1., 
                  dV_terms=None, wrap=(True, True, True), x_range=None,
                  queue=None, strict=False, xchunk=0, variant=0,
                  energy_partials=None, energy_slot_offset=0, V_terms=None,
-                 count_slots_only=False, peer=None, generated=None, tail=None):
+                 count_slots_only=False, peer=None, generated=None, tail=None,
+                 prefetch=0):
     """
     One scalar-sector LSRK stage on padded arrays of shape ``(n, Nx+2h, Ny+2h, Nz+2h)``
     (or without the leading axis for a single field).
@@ -102,6 +103,7 @@ def scalar_stage(*, fused, f_in, f_out, dfdt, kf, kdfdt, lap_f=None, h, dx=(1., 
     fill_potential(args, dV_terms, nscalars)
     args.tune_xchunk = xchunk
     args.tune_variant = variant
+    args.tune_prefetch = int(prefetch)
     if tail is not None:
         if not fused:
             raise ValueError("the in-kernel stage tail exists for the fused stage only")

@@ -70,6 +70,7 @@ class ScalarStageArgs(C.Structure):
         ("vpower", (C.c_int8 * MAX_SCALARS) * MAX_TERMS),
         ("tune_xchunk", c_int32), ("tune_variant", c_int32),
         ("tail", C.POINTER(StageTail)),
+        ("tune_prefetch", c_int32), ("reserved0", c_int32),
     ]
 
 
@@ -111,7 +112,8 @@ class TensorFusedArgs(C.Structure):
                 ("peer_lo_Nx", c_int64), ("peer_lo_stride", c_int64),
                 ("peer_hi_stride", c_int64),
                 ("tail", C.POINTER(StageTail)),
-                ("tune_xchunk", c_int32), ("tune_variant", c_int32)]
+                ("tune_xchunk", c_int32), ("tune_variant", c_int32),
+                ("tune_prefetch", c_int32), ("reserved0", c_int32)]
 
 
 class ReduceArgs(C.Structure):

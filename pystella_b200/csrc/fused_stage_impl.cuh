@@ -30,6 +30,8 @@
 
 namespace psb {
 
+#define PSB_DEFAULT_PREFETCH 6
+
 template <typename T, int NF> struct FusedParams {
   const T* f_in;
   T* f_out;
@@ -41,6 +43,7 @@ template <typename T, int NF> struct FusedParams {
   int x_begin, x_end, xchunk;
   int x2_begin, x2_end, nchunks1;
   int nmain, split_len;   // x-chunk schedule of range 1 (chunk_range())
+  int pf_dist;            // L2 prefetch distance of the pipeline's producer (planes; 0 = off)
   int wrap_x, wrap_y, wrap_z;
   T* peer_lo;   // peer-mapped f_out of rank rx-1 / rx+1 (or null)
   T* peer_hi;
@@ -598,6 +601,8 @@ static void fill_params(FusedParams<T, NF>& p, const psb_scalar_stage_args* a) {
     p.vcoef[t] = (T)a->vcoef[t];
     for (int m = 0; m < NF; ++m) p.vpower[t][m] = a->vpower[t][m];
   }
+  p.pf_dist = a->tune_prefetch == 0 ? PSB_DEFAULT_PREFETCH
+                                    : (a->tune_prefetch < 0 ? 0 : a->tune_prefetch);
   fill_tail(p.tail, a->tail,
             a->energy_partials ? a->energy_partials + a->energy_slot_offset * PSB_ENERGY_STRIDE
                                : nullptr);

@@ -117,6 +117,13 @@ __device__ __forceinline__ void st_pieces(T* p, const Vec<T, VEC>& x) {
   }
 }
 
+// Measured (B200, 512^3 fp32): the split mapping halves the shared-memory wavefronts (ncu: Mem
+// Busy 76 % -> 37 %) but the kernels are latency-bound, not LSU-bound, and its per-piece
+// predicates cost more than it saves: 0.92 -> 0.70 of the roofline for one field.  Off.
+#ifndef PSB_SPLIT_VECTORS
+#define PSB_SPLIT_VECTORS 0
+#endif
+
 // "Split" vectors: when the interior starts only GV < VEC elements aligned (fp32, h = 2:
 // 8 bytes), a thread's VEC sites are NOT consecutive but VEC/GV pieces of GV consecutive
 // sites, GS = TZ*GV elements apart, so that the lanes of a warp touch CONSECUTIVE GV-element
@@ -226,7 +233,33 @@ __global__ void __launch_bounds__(BY* TZ + 32, MINB)
       tma_prefetch_desc(&map_kf);
       tma_prefetch_desc(&map_kd);
       const uint32_t pw_bytes = (read_k ? 3u : 1u) * NF * C::PWTILE_RAW;
+      const int pf = p.pf_dist;
+      auto prefetch_f = [&](int m) {
+#pragma unroll
+        for (int f = 0; f < NF; ++f) tma_prefetch_4d(&map_f, z0 + C::ZF, y0, xs + m, f);
+      };
+      auto prefetch_pw = [&](int c) {
+        const int px = xs + c + H;
+#pragma unroll
+        for (int f = 0; f < NF; ++f) {
+          tma_prefetch_4d(&map_d, z0 + C::ZP, y0 + H, px, f);
+          if (read_k) {
+            tma_prefetch_4d(&map_kf, z0 + C::ZP, y0 + H, px, f);
+            tma_prefetch_4d(&map_kd, z0 + C::ZP, y0 + H, px, f);
+          }
+        }
+      };
       for (int m = 0; m < nsteps; ++m) {
+        if (pf > 0) {
+          // pf planes ahead of the loads (the first RF / RP planes are loaded right away)
+          if (m == 0)
+            for (int q = RF; q < pf && q < nsteps; ++q) prefetch_f(q);
+          if (m + pf >= RF && m + pf < nsteps) prefetch_f(m + pf);
+          const int c0 = m - 2 * H;
+          if (c0 == 0)
+            for (int q = RP; q < pf && q < ncomp; ++q) prefetch_pw(q);
+          if (c0 >= 0 && c0 + pf >= RP && c0 + pf < ncomp) prefetch_pw(c0 + pf);
+        }
         {  // f plane m: interior x index xs - H + m -> padded index xs + m
           const int slot = m % RF;
           if (m >= RF) mbar_wait(&empty_f[slot], ((m / RF) - 1) & 1);
@@ -265,7 +298,7 @@ __global__ void __launch_bounds__(BY* TZ + 32, MINB)
   // ============================ consumer warps ==================================
   // split vectors (fp32, h = 2, consecutive mapping impossible at 16-byte alignment): the
   // thread's VEC sites are VEC/GV pieces of GV sites, GS apart; see ld_pieces_s
-  constexpr bool SPLIT = !AL && (GV < VEC);
+  constexpr bool SPLIT = PSB_SPLIT_VECTORS && !AL && (GV < VEC);
   constexpr int NG = VEC / GV;
   constexpr int TS = SPLIT ? GV : VEC;        // z stride between threads (sites)
   constexpr int GS = SPLIT ? TZ * GV : GV;    // z stride between the pieces of a vector

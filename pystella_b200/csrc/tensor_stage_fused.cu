@@ -28,6 +28,7 @@ template <typename T> struct TensorFusedParams {
   int x_begin, x_end, xchunk;
   int x2_begin, x2_end, nchunks1;
   int nmain, split_len;
+  int pf_dist;
   int wrap_x, wrap_y, wrap_z;
   T inv_dx2[3];
   T inv_dx[3];
@@ -118,7 +119,33 @@ __device__ __forceinline__ void tensor_stage_body(const TensorFusedParams<T>& p,
       tma_prefetch_desc(&map_kh);
       tma_prefetch_desc(&map_kd);
       const uint32_t pw_bytes = (read_k ? 3u : 1u) * B::PWTILE_RAW;
+      const int pf = p.pf_dist;
+      auto prefetch_f = [&](int m) {
+        tma_prefetch_4d(&map_h, z0 + H - HL, y0, xs + m, comp);
+        // the source planes are shared by the six components of a tile: one of them asks
+#pragma unroll
+        for (int n = 0; n < NS; ++n)
+          if (comp == n) tma_prefetch_4d(&map_s, z0 + H - HL, y0, xs + m, n);
+      };
+      auto prefetch_pw = [&](int c) {
+        const int px = xs + c + H;
+        tma_prefetch_4d(&map_d, z0 + H - B::PWL, y0 + H, px, comp);
+        if (read_k) {
+          tma_prefetch_4d(&map_kh, z0 + H - B::PWL, y0 + H, px, comp);
+          tma_prefetch_4d(&map_kd, z0 + H - B::PWL, y0 + H, px, comp);
+        }
+      };
       for (int m = 0; m < nsteps; ++m) {
+        if (pf > 0) {
+          // pf planes ahead of the loads (the first RF / RP planes are loaded right away)
+          if (m == 0)
+            for (int q = RF; q < pf && q < nsteps; ++q) prefetch_f(q);
+          if (m + pf >= RF && m + pf < nsteps) prefetch_f(m + pf);
+          const int c0 = m - 2 * H;
+          if (c0 == 0)
+            for (int q = RP; q < pf && q < ncomp; ++q) prefetch_pw(q);
+          if (c0 >= 0 && c0 + pf >= RP && c0 + pf < ncomp) prefetch_pw(c0 + pf);
+        }
         {
           const int slot = m % RF;
           if (m >= RF) mbar_wait(&empty_f[slot], ((m / RF) - 1) & 1);
@@ -151,7 +178,7 @@ __device__ __forceinline__ void tensor_stage_body(const TensorFusedParams<T>& p,
   }
 
   // split vectors (fp32, h = 2): pieces of GV sites, GS apart; see ld_pieces_s
-  constexpr bool SPLIT = (GV < VEC);
+  constexpr bool SPLIT = PSB_SPLIT_VECTORS && (GV < VEC);
   constexpr int NG = VEC / GV;
   constexpr int TS = SPLIT ? GV : VEC;        // z stride between threads (sites)
   constexpr int GS = SPLIT ? TZ * GV : GV;    // z stride between the pieces of a vector
@@ -539,6 +566,8 @@ static int launch_tensor_ws(const psb_tensor_fused_args* a, cudaStream_t stream,
   p.nchunks1 = L.n1;
   p.nmain = L.nmain;
   p.split_len = L.split_len;
+  p.pf_dist = a->tune_prefetch == 0 ? PSB_DEFAULT_PREFETCH
+                                    : (a->tune_prefetch < 0 ? 0 : a->tune_prefetch);
   p.wrap_x = a->wrap_x;
   p.wrap_y = a->wrap_y;
   p.wrap_z = a->wrap_z;

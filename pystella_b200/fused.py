@@ -254,7 +254,8 @@ def fused_scalar_stage(stepper, system, f, common, queue):
     args = dict(common)
     args.update(fused=True, f_in=f, f_out=twin, dx=stepper.dx)
     tune = stepper.tune or {}
-    args.update(xchunk=tune.get("xchunk", 0), variant=tune.get("variant", 0))
+    args.update(xchunk=tune.get("xchunk", 0), variant=tune.get("variant", 0),
+                prefetch=tune.get("prefetch", 0))
 
     nslots = 0
     if stepper.fused_energy:

@@ -102,6 +102,7 @@ class TensorSystem:
         tune = stepper.tune or {}
         args.tune_xchunk = tune.get("gw_xchunk", 0)
         args.tune_variant = tune.get("gw_variant", 0)
+        args.tune_prefetch = tune.get("gw_prefetch", tune.get("prefetch", 0))
         hub = kwargs["hubble"]
         if isinstance(hub, torch.Tensor):
             args.hubble_dev = hub.data_ptr()

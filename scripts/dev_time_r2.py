@@ -96,16 +96,18 @@ if __name__ == "__main__":
     F64, F32 = torch.float64, torch.float32
     N5 = (512,) * 3
     if "gwvar" in which:
-        for var in (0, 6, 2):
-            gw_case(512, F32, tune={"gw_variant": var})
+        for pf in (-1, 0, 3, 10):
+            gw_case(512, F32, tune={"prefetch": pf})
         gw_case(512, F32, tune={"gw_xchunk": 32})
-        gw_case(512, F32, stage=0)
         gw_case(256, F64)
-        for stage in (1, 0):
-            scalar_case(N5, F32, stage, True)
-            scalar_case(N5, F32, stage, True, nscalars=2)
-        scalar_case((128, 1024, 1024), F32, 1, True)
-        scalar_case((128, 1024, 1024), F32, 0, True)
+        gw_case(256, F64, tune={"prefetch": -1})
+        for pf in (-1, 0, 10):
+            scalar_case(N5, F32, 1, True, nscalars=2, tune={"prefetch": pf})
+            scalar_case(N5, F32, 1, True, tune={"prefetch": pf})
+            scalar_case(N5, F64, 1, True, tune={"prefetch": pf})
+            scalar_case(N5, F64, 0, True, tune={"prefetch": pf})
+            scalar_case((256,) * 3, F64, 1, True, nscalars=2, tune={"prefetch": pf})
+            scalar_case((64, 512, 512), F64, 1, True, tune={"prefetch": pf})
     if "gwprof" in which:
         gw_case(384, F32)
     if "f32prof" in which:

@@ -170,13 +170,76 @@ def test_pipeline_index_arithmetic_aligned_mapping():
 
 
 def test_pipeline_index_arithmetic_default_mapping():
-    """The mapping of the validated kernels, for the layouts it is dispatched for."""
+    """The mapping of the validated kernels, for the layouts it is dispatched for (consecutive
+    sites per thread: GV == VEC, i.e. fp64 and fp32 with radius 4)."""
     for es, VEC, TZ in ((8, 2, 64), (4, 2, 64), (4, 4, 32)):
         for H in (2, 4):
+            if math.gcd(VEC, H) != VEC:
+                continue          # split mapping: test below
             for Nz in range(8, 200, 2):
                 if ((Nz + 2 * H) * es) % 16 or Nz % VEC:
                     continue
                 _ws_check(es, H, VEC, TZ, Nz, False)
+
+
+def _ws_check_split(es, H, VEC, TZ, Nz):
+    """Split vectors (csrc/fused_stage_ws.cuh, SPLIT: GV = gcd(VEC, H) < VEC): a thread's VEC
+    sites are VEC/GV pieces of GV consecutive sites, TZ*GV apart.  Every interior site is owned
+    exactly once, pieces are GV-aligned in shared and global memory, the lanes of a warp touch
+    consecutive pieces (one contiguous span per vector access), stencil reads stay inside the
+    tile, and the periodic z images land on the right halo cells."""
+    c = _ws_cfg(es, H, VEC, TZ, False)
+    GV, BZ, HL = c["GV"], c["BZ"], c["HL"]
+    assert GV < VEC
+    NG, GS = VEC // GV, TZ * GV
+    Pz = Nz + 2 * H
+    ntiles = -(-Nz // BZ)
+    written, halo_written = {}, {}
+    for b in range(ntiles):
+        z0 = b * BZ
+        assert ((z0 + c["ZF"]) * es) % 16 == 0 and ((z0 + c["ZP"]) * es) % 16 == 0
+        for g in range(NG):
+            starts = []
+            for tz in range(TZ):
+                k = z0 + tz * GV                       # thread's first site
+                own = HL + tz * GV + g * GS            # smem column of piece g
+                pw = c["PWL"] + tz * GV + g * GS
+                starts.append(own)
+                assert own % GV == 0 and pw % GV == 0 and (k + g * GS + H) % GV == 0
+                assert own - HL >= 0 and own + GV + HL <= c["W"] and pw + GV <= c["PWW"]
+                if not (k + g * GS < Nz):              # pact[g]
+                    continue
+                for e in range(GV):
+                    z = k + g * GS + e
+                    assert z < Nz, "needs Nz % GV == 0"
+                    assert z0 + c["ZF"] + own + e == z + H
+                    assert z0 + c["ZP"] + pw + e == z + H
+                    for s_ in range(-H, H + 1):
+                        col = own + e + s_
+                        assert 0 <= col < c["W"] and 0 <= z0 + c["ZF"] + col < Pz
+                    assert z not in written
+                    written[z] = (b, tz, g, e)
+                    voff = g * GS + e                  # element offset from the first site
+                    base = k + H
+                    if z < H:
+                        halo_written[base + voff + Nz] = z
+                    if z >= Nz - H:
+                        halo_written[base + voff - Nz] = z
+            # lanes of a warp (consecutive tz) read consecutive pieces: contiguous span
+            assert all(b_ - a_ == GV for a_, b_ in zip(starts, starts[1:]))
+    assert sorted(written) == list(range(Nz))
+    for pz, z in halo_written.items():
+        assert (pz < H or pz >= Nz + H) and (pz - H) % Nz == z
+    assert len(halo_written) == 2 * H
+
+
+def test_pipeline_index_arithmetic_split_mapping():
+    """fp32, radius 2: 16-byte vectors as two 8-byte pieces 64 sites apart."""
+    for TZ in (16, 32):
+        for Nz in range(8, 300, 2):
+            if ((Nz + 4) * 4) % 16:
+                continue
+            _ws_check_split(4, 2, 4, TZ, Nz)
 
 
 # ---------------------------------------------------------------------------------------
