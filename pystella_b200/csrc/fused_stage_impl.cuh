@@ -30,7 +30,10 @@
 
 namespace psb {
 
-#define PSB_DEFAULT_PREFETCH 6
+// measured (B200): prefetching planes into L2 ahead of the TMA loads makes every configuration
+// slower (fp64 single field 0.946 -> 0.871 of the roofline, tensor stage fp32 0.650 -> 0.492): the
+// pipelines are not bound by DRAM latency.  Kept as an opt-in tuning knob (tune_prefetch > 0).
+#define PSB_DEFAULT_PREFETCH 0
 
 template <typename T, int NF> struct FusedParams {
   const T* f_in;
