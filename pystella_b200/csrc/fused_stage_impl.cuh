@@ -159,8 +159,15 @@ struct ChunkRange {
 };
 __device__ __forceinline__ ChunkRange chunk_range(int zc, int x_begin, int x_end, int x2_begin,
                                                   int x2_end, int xchunk, int nchunks1,
-                                                  int nmain, int split_len) {
+                                                  int nmain, int split_len,
+                                                  bool top_first = false) {
   ChunkRange r;
+  // top_first (launches that store halo planes into a neighbour's memory): the chunk holding
+  // the HIGHEST planes is dispatched second instead of last, so that both boundary chunks'
+  // NVLink stores and system-scope fences overlap with the bulk of the launch instead of
+  // sitting on its critical path
+  if (top_first && zc < nchunks1 && nchunks1 > 2)
+    zc = zc == 0 ? 0 : (zc == 1 ? nchunks1 - 1 : zc - 1);
   if (zc >= nchunks1) {   // second x range of the launch
     r.xs = x2_begin + (zc - nchunks1) * xchunk;
     r.xe = min(r.xs + xchunk, x2_end);
@@ -211,7 +218,8 @@ __global__ void __launch_bounds__(BY* TZ, MINB)
   const int tid = ty * TZ + tz;
   const int z0 = blockIdx.x * C::BZ, y0 = blockIdx.y * BY;
   const ChunkRange cr = chunk_range(blockIdx.z, p.x_begin, p.x_end, p.x2_begin, p.x2_end,
-                                    p.xchunk, p.nchunks1, p.nmain, p.split_len);
+                                    p.xchunk, p.nchunks1, p.nmain, p.split_len,
+                                    p.peer_hi != nullptr);
   const int xs = cr.xs, xe = cr.xe;
   const int nsteps = (xe - xs) + 2 * H;
 

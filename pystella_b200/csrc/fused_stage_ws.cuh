@@ -206,7 +206,8 @@ __global__ void __launch_bounds__(BY* TZ + 32, MINB)
   const int tid = threadIdx.x;
   const int z0 = blockIdx.x * C::BZ, y0 = blockIdx.y * BY;
   const ChunkRange cr = chunk_range(blockIdx.z, p.x_begin, p.x_end, p.x2_begin, p.x2_end,
-                                    p.xchunk, p.nchunks1, p.nmain, p.split_len);
+                                    p.xchunk, p.nchunks1, p.nmain, p.split_len,
+                                    p.peer_hi != nullptr);
   const int xs = cr.xs, xe = cr.xe;
   const int nsteps = (xe - xs) + 2 * H;   // f planes streamed
   const int ncomp = xe - xs;              // site planes computed
