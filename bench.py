@@ -473,7 +473,9 @@ def run_b200_arm(args):
     halo_mode = getattr(stepper, "_halo_mode", "local")
     # kernels per stage: the scalar stage (+ the tensor stage); the NCCL fallback splits the
     # scalar stage into boundary + interior launches and keeps the fold / expansion kernels
-    kernels_per_stage = (1 + (1 if w["gw"] else 0)) if halo_mode != "nccl" else 4
+    kernels_per_stage = {"local": 1 + (1 if w["gw"] else 0),
+                         # + the inter-GPU exchange / background kernel
+                         "peer": 2 + (1 if w["gw"] else 0), "nccl": 4}[halo_mode]
     launches_per_step = NUM_STAGES * kernels_per_stage
 
     graph = None
@@ -624,8 +626,9 @@ def run_b200_arm(args):
                 "halo_exchange": {"local": "periodic wrap written by the stage kernel",
                                   "peer": "stage kernels store their boundary planes into "
                                           "the neighbours' halos over NVLink (peer memory); "
-                                          "inter-GPU barrier + energy all-gather in the "
-                                          "last CTA of the stage's last kernel",
+                                          "one tiny kernel per stage all-gathers the energy "
+                                          "sums over peer memory, is the inter-GPU barrier "
+                                          "and advances the background",
                                   "nccl": "NCCL send/recv on a side stream"}[halo_mode],
                 "launch": "CUDA graph (2 steps per replay)" if not args.no_graph
                           else "eager launches",

@@ -663,9 +663,16 @@ class LowStorageRKStepper(Stepper):
         peer_mode = getattr(self, "_halo_mode", None) == "peer"
         expand = getattr(self, "_expansion", None)
         last = getattr(self, "_last_of_stage", True)
-        if last and peer_mode:
+        # Multi-rank: the inter-GPU exchange stays a separate tiny kernel after the stage
+        # (psb_expansion_stage_peer).  Doing it in the watcher CTA needs a system-scope fence
+        # in every CTA that stored halo planes into a neighbour's memory, and that fence keeps
+        # the CTA's SM slot for ~5 us: measured at 8 GPUs +35 us per stage at 512^3 (a third of
+        # the CTAs are boundary CTAs) and +68 us at 1024^3.  tune={"peer_tail": True} selects
+        # the in-kernel variant.
+        peer_tail = bool((self.tune or {}).get("peer_tail", False))
+        if last and peer_mode and peer_tail:
             mode |= _lib.TAIL_PEER
-        if last and expand is not None and self.fused_energy:
+        if last and expand is not None and self.fused_energy and (not peer_mode or peer_tail):
             mode |= _lib.TAIL_EXPAND
         if mode == 0:
             return None

@@ -91,6 +91,9 @@ def _reduction_case(rank, world, backend):
 
 def _fused_case(rank, world, backend, nscalars, energy, mode="peer"):
     """Multi-rank fused stepper (boundary/interior split + face exchange) == single rank."""
+    peer_tail = mode == "peertail"     # in-kernel inter-GPU exchange (watcher CTA)
+    if peer_tail:
+        mode = "peer"
     os.environ["PSB_HALO_MODE"] = mode
     import pystella_b200 as ps
     import oracle as O
@@ -129,7 +132,8 @@ def _fused_case(rank, world, backend, nscalars, energy, mode="peer"):
     d = torch.from_numpy(np.ascontiguousarray(d0[:, sl])).cuda()
     sector = ps.ScalarSector(nscalars, potential=potential)
     st = ps.LowStorageRK54(sector, halo_shape=h, dt=dt, dx=dx, decomp=decomp,
-                           MapKernel=ps.FusedStencilStage, energy=energy)
+                           MapKernel=ps.FusedStencilStage, energy=energy,
+                           tune={"peer_tail": peer_tail})
     dexp = None
     for _ in range(nsteps):
         for s in range(5):
@@ -176,7 +180,7 @@ def _fused_case(rank, world, backend, nscalars, energy, mode="peer"):
         assert float(lo) == float(hi)
 
 
-def _fused_gw_case(rank, world, backend, dtype):
+def _fused_gw_case(rank, world, backend, dtype, peer_tail=False):
     """Config-4 structure on several ranks: fused scalar stage + fused tensor stage, both with
     peer-memory halos, the stage's inter-GPU barrier and the background in the tensor kernel's
     watcher CTA == the C oracle on the global lattice."""
@@ -221,7 +225,8 @@ def _fused_gw_case(rank, world, backend, dtype):
     scalar = ps.ScalarSector(2, potential=lambda g: g[0]**2 / 2 + 0.3 * g[0]**2 * g[1]**2)
     gw = ps.TensorPerturbationSector([scalar])
     st = ps.LowStorageRK54([scalar, gw], halo_shape=h, dt=dt, dx=dx, decomp=decomp,
-                           MapKernel=ps.FusedStencilStage, energy=True)
+                           MapKernel=ps.FusedStencilStage, energy=True,
+                           tune={"peer_tail": peer_tail})
     dexp = ps.DeviceExpansion(e0, ps.LowStorageRK54, grid_size=gs, decomp=decomp, nscalars=2)
     dexp.attach(st)
     for _ in range(nsteps):
@@ -346,7 +351,7 @@ def _worker(rank, world, port, case, args):
         elif case == "gpu_reduction":
             _reduction_case(rank, world, backend)
         elif case == "gpu_fused_gw":
-            _fused_gw_case(rank, world, backend, args[0])
+            _fused_gw_case(rank, world, backend, args[0], len(args) > 1 and args[1] == "1")
         elif case == "gpu_fused":
             _fused_case(rank, world, backend, int(args[0]), args[1] == "1",
                         args[2] if len(args) > 2 else "peer")

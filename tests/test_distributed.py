@@ -98,11 +98,12 @@ def test_reduction_nccl():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("mode", ["peer", "nccl"])
+@pytest.mark.parametrize("mode", ["peer", "peertail", "nccl"])
 @pytest.mark.parametrize("nscalars,energy", [(1, "0"), (2, "1")])
 def test_fused_stepper_two_ranks(nscalars, energy, mode):
     """peer: halo planes stored into the neighbour's memory by the stage kernel +
-    peer all-gather/barrier kernel; nccl: boundary-first schedule with send/recv."""
+    peer all-gather/barrier kernel; peertail: the same exchange inside the stage kernel's
+    watcher CTA; nccl: boundary-first schedule with send/recv."""
     if _ngpus() < 2:
         pytest.skip("needs 2 GPUs")
     _run("gpu_fused", 2, str(nscalars), energy, mode)
@@ -117,11 +118,12 @@ def test_fused_stepper_four_ranks(mode):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("peer_tail", ["0", "1"])
 @pytest.mark.parametrize("dtype", ["f64", "f32"])
-def test_fused_scalar_plus_tensor_two_ranks(dtype):
+def test_fused_scalar_plus_tensor_two_ranks(dtype, peer_tail):
     """Config-4 structure over peer memory: scalar + tensor stage kernels store their
     boundary planes into the neighbour's halos, the tensor kernel's watcher CTA runs the
     inter-GPU barrier and the background stage; == the C oracle on the global lattice."""
     if _ngpus() < 2:
         pytest.skip("needs 2 GPUs")
-    _run("gpu_fused_gw", 2, dtype)
+    _run("gpu_fused_gw", 2, dtype, peer_tail)
