@@ -779,6 +779,11 @@ static int dispatch_vec(const psb_scalar_stage_args* a, cudaStream_t stream,
           // (3 fields fp64).  tune_variant 21 = the deeper two-CTA configuration.
           constexpr int VV = std::is_same<T, float>::value ? 4 : 2;
           constexpr int TZ3 = ws_pick_tz(ES, H, NF, 4, 1, VV, SMEM_LIMIT_3);
+          constexpr int TZ2 = ws_pick_tz(ES, H, NF, 4, 3, VV, 113 * 1024);
+          if constexpr (TZ2 > 0) {   // two CTAs with a deeper (P = 3) pipeline
+            if (var == 22 && a->Nz % VV == 0)
+              return ws_op<T, H, NF, 4, TZ2, 3, 2, VV>(a, stream, count);
+          }
           if constexpr (TZ3 > 0) {
             if (var != 21 && var != 15 && a->Nz % VV == 0)
               return ws_op<T, H, NF, 4, TZ3, 1, 3, VV>(a, stream, count);

@@ -513,7 +513,10 @@ constexpr int tws_pick_tz(int es, int H, int NS, int BY, int P, int VEC, bool sm
   return 16;
 }
 
-template <typename T, int H, int NS, int VEC, int BY = 4, int P = 2, int MINB = 1,
+// Default configuration: BY = 4 rows, pipeline depth P = 3, two CTAs per SM (measured, 512^3
+// fp32: P = 2 0.650 of the roofline, P = 3 0.665, with 32-plane x-chunks 0.681; fp64 256^3:
+// 0.710 -> 0.783).
+template <typename T, int H, int NS, int VEC, int BY = 4, int P = 3, int MINB = 2,
           bool SMEMX = false>
 static int launch_tensor_ws(const psb_tensor_fused_args* a, cudaStream_t stream,
                             int64_t* count) {
@@ -526,7 +529,7 @@ static int launch_tensor_ws(const psb_tensor_fused_args* a, cudaStream_t stream,
   xa.x_begin = 0;
   xa.x_end = a->Nx;
   xa.tune_xchunk = a->tune_xchunk;
-  const XLayout L = x_layout(&xa, WS_DEFAULT_XCHUNK,
+  const XLayout L = x_layout(&xa, a->Nx >= 64 ? 32 : WS_DEFAULT_XCHUNK,
                              6 * ((a->Nz + B::BZ - 1) / B::BZ) * ((a->Ny + BY - 1) / BY));
   if (count != nullptr) {
     *count = 6 * ((a->Nz + B::BZ - 1) / B::BZ) * ((a->Ny + BY - 1) / BY) * (int64_t)L.n1;
@@ -611,6 +614,7 @@ static int tensor_fused_ns(const psb_tensor_fused_args* a, cudaStream_t s, int64
     if (a->nscalars == 2 && (sizeof(T) == 8 || a->Nz % 4 == 0)) {
       if (a->tune_variant == 2) return launch_tensor_ws<T, H, 2, VV, 4, 1, 3>(a, s, count);
       if (a->tune_variant == 4) return launch_tensor_ws<T, H, 2, VV, 8, 2, 1>(a, s, count);
+      if (a->tune_variant == 10) return launch_tensor_ws<T, H, 2, VV, 4, 2, 1>(a, s, count);
       if (a->tune_variant == 6)
         return launch_tensor_ws<T, H, 2, VV, 4, 2, 2, true>(a, s, count);
       if (a->tune_variant == 7)

@@ -96,18 +96,13 @@ if __name__ == "__main__":
     F64, F32 = torch.float64, torch.float32
     N5 = (512,) * 3
     if "gwvar" in which:
-        for pf in (-1, 0, 3, 10):
-            gw_case(512, F32, tune={"prefetch": pf})
-        gw_case(512, F32, tune={"gw_xchunk": 32})
-        gw_case(256, F64)
-        gw_case(256, F64, tune={"prefetch": -1})
-        for pf in (-1, 0, 10):
-            scalar_case(N5, F32, 1, True, nscalars=2, tune={"prefetch": pf})
-            scalar_case(N5, F32, 1, True, tune={"prefetch": pf})
-            scalar_case(N5, F64, 1, True, tune={"prefetch": pf})
-            scalar_case(N5, F64, 0, True, tune={"prefetch": pf})
-            scalar_case((256,) * 3, F64, 1, True, nscalars=2, tune={"prefetch": pf})
-            scalar_case((64, 512, 512), F64, 1, True, tune={"prefetch": pf})
+        for var in (0, 9):
+            gw_case(512, F32, tune={"gw_variant": var})
+            gw_case(256, F64, tune={"gw_variant": var})
+        gw_case(512, F32, tune={"gw_variant": 9, "gw_xchunk": 32})
+        for var in (0, 22):
+            scalar_case(N5, F32, 1, True, nscalars=2, tune={"variant": var})
+            scalar_case((256,) * 3, F64, 1, True, nscalars=2, tune={"variant": var})
     if "gwprof" in which:
         gw_case(384, F32)
     if "f32prof" in which:
