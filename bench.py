@@ -240,14 +240,34 @@ class ClockSampler:
 # ---------------------------------------------------------------------------
 
 def _cpu_threads_policy():
-    """Fixed thread policy for the timed CPU baseline: one thread per hardware thread the
-    process may use, bound close to each other, pages first-touched in parallel."""
-    os.environ.setdefault("OMP_PROC_BIND", "close")
+    """Thread policy of the timed CPU baseline: threads spread over the cores the process may
+    use (OMP_PROC_BIND=spread), pages first-touched in parallel by the same threads.  The
+    thread COUNT is calibrated (see _calibrate_threads): this bandwidth-bound loop is not
+    fastest with every hardware thread (measured on one 128-thread host: 172 MLUPS with 128
+    threads, 600-1200 with 32)."""
+    os.environ.setdefault("OMP_PROC_BIND", "spread")
     os.environ.setdefault("OMP_PLACES", "threads")
     try:
         return len(os.sched_getaffinity(0))
     except AttributeError:
         return os.cpu_count() or 1
+
+
+def _calibrate_threads(lib, nmax, setup, run, cfg):
+    """Best OpenMP thread count among nmax, nmax/2, nmax/4, nmax/8 on a 128^3 sample of the
+    same system (first touch repeated for every candidate); a few tenths of a second each."""
+    small = dict(cfg, scaling="strong", grid=(128, 128, 128))
+    best = None
+    for nt in sorted({nmax, max(1, nmax // 2), max(1, nmax // 4), max(1, nmax // 8)},
+                     reverse=True):
+        lib.omp_set_num_threads(nt)
+        st = setup(small)
+        run(st, 1)
+        t = min(run(st, 1) for _ in range(2))
+        if best is None or t < best[0]:
+            best = (t, nt)
+        del st
+    return best[1]
 
 
 def cpu_reference_steps(cfg, nsteps, warmup, budget_s=150.0):
@@ -259,10 +279,6 @@ def cpu_reference_steps(cfg, nsteps, warmup, budget_s=150.0):
     from oracle import c_oracle as CO
     native = True
     lib = CO.load(native)
-    try:
-        lib.omp_set_num_threads(nthreads)
-    except Exception:  # noqa: BLE001
-        pass
     A, B, _ = O.LSRK_TABLES["LowStorageRK54"]
 
     def setup(cfgx):
@@ -316,6 +332,11 @@ def cpu_reference_steps(cfg, nsteps, warmup, budget_s=150.0):
 
     # the sample: shrink the lattice (x first, then all axes) until a step fits the budget;
     # the tensor configuration needs 50 fp64 arrays, so it starts at 256^3
+    try:
+        nthreads = _calibrate_threads(lib, nthreads, setup, run, cfg)
+        lib.omp_set_num_threads(nthreads)
+    except Exception:  # noqa: BLE001
+        pass
     cfgx = dict(cfg, scaling="strong")
     g = list(workload(cfg, 1, 0)["grid_shape"])
     if cfg["system"] == "scalar2gw":
@@ -346,8 +367,9 @@ def cpu_reference_steps(cfg, nsteps, warmup, budget_s=150.0):
     sample = (f"{N[0]}x{N[1]}x{N[2]} lattice" + (" (reduced from the configuration's "
               "lattice to bound the CPU time and memory)" if reduced else "")
               + f", full LSRK54 steps in fp64, best of {reps} x {nsteps} steps after "
-              f"{max(warmup, 1)} warm-up, {CO.num_threads(native)} OpenMP threads "
-              "(OMP_PROC_BIND=close, parallel first touch), unfused reference schedule "
+              f"{max(warmup, 1)} warm-up, {CO.num_threads(native)} OpenMP threads (count "
+              "calibrated on a 128^3 sample, OMP_PROC_BIND=spread, parallel first touch), "
+              "unfused reference schedule "
               "(share_halos -> lap -> stage -> energy -> expansion), oracle/oracle_c.c")
     return dict(mlups=mlups, ms_per_step=total / nsteps * 1e3, steps=nsteps,
                 cores=CO.num_threads(native), sample=sample, spread=[min(times), max(times)])
@@ -528,6 +550,9 @@ def run_b200_arm(args):
     stepper._timing_hook = []
     reps = max(2, min(steps, 6))
     for _ in range(reps):
+        # keep the device busy while the host queues the five stages, so that every event
+        # pair brackets exactly one kernel (no idle time of a slow host inside the interval)
+        torch.cuda._sleep(20_000_000)
         one_step()
     torch.cuda.synchronize()
     hook, stepper._timing_hook = stepper._timing_hook, None
