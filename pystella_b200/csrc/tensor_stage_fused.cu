@@ -538,6 +538,12 @@ static int launch_tensor_ws(const psb_tensor_fused_args* a, cudaStream_t stream,
   static_assert(C::SMEM_BYTES <= 227 * 1024, "tensor pipeline does not fit shared memory");
   const int64_t Px = a->Nx + 2 * H, Py = a->Ny + 2 * H, Pz = a->Nz + 2 * H;
   const int64_t vol = Px * Py * Pz;
+  // argument checks first (they need no driver), then the TMA descriptors
+  if (int rc = validate_tail(a->tail,
+                             6 * ((a->Nz + B::BZ - 1) / B::BZ) * ((a->Ny + BY - 1) / BY) *
+                                 (int64_t)L.n1,
+                             false, "psb_tensor_stage_fused"))
+    return rc;
   CUtensorMap mh, ms, md, mkh, mkd;
   if (encode_field_tensor_map(&mh, a->dtype, a->hij_in, 6, vol, Px, Py, Pz, 1, B::ROWS,
                               B::W) != 0 ||
@@ -592,9 +598,6 @@ static int launch_tensor_ws(const psb_tensor_fused_args* a, cudaStream_t stream,
   p.peer_hi_stride = a->peer_hi_stride;
   dim3 grid((unsigned)(6 * ((a->Nz + B::BZ - 1) / B::BZ)), (unsigned)((a->Ny + BY - 1) / BY),
             (unsigned)p.nchunks1);
-  if (int rc = validate_tail(a->tail, (int64_t)grid.x * grid.y * grid.z, false,
-                             "psb_tensor_stage_fused"))
-    return rc;
   fill_tail(p.tail, a->tail, nullptr);
   dim3 block(C::THREADS, 1, 1);
   auto kern = tensor_stage_ws_kernel<T, H, NS, BY, TZ, P, MINB, VEC, SMEMX>;

@@ -65,7 +65,17 @@ class OutputFile:
         except ImportError:
             pass
         for key, val in kwargs.items():
-            if isinstance(val, (int, float, str, bool, np.ndarray, np.generic, tuple, list)):
+            if isinstance(val, (tuple, list)):
+                # a mixed list / tuple would become an object array, which read()
+                # (allow_pickle=False) cannot load: store it as text instead
+                try:
+                    arr = np.asarray(val) if len(val) else np.asarray(val, dtype=np.float64)
+                    plain = arr.dtype != object and arr.dtype.kind in "biufc" or (
+                        arr.dtype.kind in "SU" and all(isinstance(v, str) for v in val))
+                except ValueError:          # ragged
+                    plain = False
+                self.attrs[key] = val if plain else str(val)
+            elif isinstance(val, (int, float, str, bool, np.ndarray, np.generic)):
                 self.attrs[key] = val
             elif isinstance(val, type):
                 self.attrs[key] = val.__name__

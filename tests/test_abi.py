@@ -184,3 +184,107 @@ def test_other_entry_points_validate_before_launching():
     k.dst[0] = 3
     assert lib.psb_scalar_rk_stage(ctypes.byref(k), None) != 0
     assert b"bad dst" in lib.psb_last_error()
+
+
+def _stage_args(nscalars=1, N=(8, 8, 8), h=2):
+    """ScalarStageArgs that pass validation up to the stage tail (fake, aligned pointers: the
+    calls below must be refused before anything is launched)."""
+    a = _lib.ScalarStageArgs()
+    a.dtype, a.nscalars, a.h = _lib.PSB_F64, nscalars, h
+    a.Nx, a.Ny, a.Nz = N
+    a.x_begin, a.x_end = 0, N[0]
+    a.field_stride = (N[0] + 2 * h) * (N[1] + 2 * h) * (N[2] + 2 * h)
+    for i, name in enumerate(("f_in", "f_out", "dfdt", "kf", "kdfdt")):
+        setattr(a, name, 0x10000 * (i + 1))
+    for d in range(3):
+        a.dx[d] = 0.1
+    a.dt, a.A, a.B, a.a = 1e-3, -0.4, 0.3, 1.0
+    a.wrap_x = a.wrap_y = a.wrap_z = 1
+    return a
+
+
+def test_stage_tail_validation():
+    """psb_stage_tail is checked before the launch (include/pystella_b200.h): unknown mode
+    bits, FOLD without energy partials, missing marker rows / sums / state, bad peer tables."""
+    lib = _lib.load()
+    cases = [
+        (dict(mode=64), b"unknown stage-tail mode"),
+        (dict(mode=_lib.TAIL_FOLD, nscalars=1, sums=0x9000), b"needs energy_partials"),
+        (dict(mode=_lib.TAIL_PEER, nscalars=0), b"marker rows"),
+        (dict(mode=_lib.TAIL_PEER, nscalars=0, rows=0x9000, nrows=1), b"marker rows"),
+        (dict(mode=_lib.TAIL_EXPAND, nscalars=1, rows=0x9000, nrows=1 << 20), b"sums"),
+        (dict(mode=_lib.TAIL_EXPAND, nscalars=1, rows=0x9000, nrows=1 << 20, sums=0x9100),
+         b"state and energies"),
+        (dict(mode=_lib.TAIL_PEER, nscalars=0, rows=0x9000, nrows=1 << 20), b"rank/nranks"),
+    ]
+    for fields, msg in cases:
+        tail = _lib.StageTail()
+        for k, v in fields.items():
+            setattr(tail, k, v)
+        args = _stage_args()
+        args.tail = ctypes.pointer(tail)
+        rc = lib.psb_scalar_stage_fused(ctypes.byref(args), None)
+        assert rc != 0 and msg in lib.psb_last_error(), (fields, lib.psb_last_error())
+    # the same rules guard the tensor stage (no FOLD there: it has no energy partials)
+    t = _lib.TensorFusedArgs()
+    t.dtype, t.nscalars, t.h = _lib.PSB_F32, 2, 2
+    t.Nx, t.Ny, t.Nz = 8, 8, 8
+    for i, name in enumerate(("hij_in", "hij_out", "dhijdt", "khij", "kdhijdt", "src")):
+        setattr(t, name, 0x10000 * (i + 1))
+    for d in range(3):
+        t.dx[d] = 0.1
+    assert lib.psb_tensor_stage_fused_rows(ctypes.byref(t)) == 6 * 1 * 2 * 1
+    tail = _lib.StageTail()
+    tail.mode = _lib.TAIL_FOLD
+    tail.nscalars = 2
+    tail.sums = 0x9000
+    tail.rows, tail.nrows = 0x9100, 1 << 20
+    t.tail = ctypes.pointer(tail)
+    rc = lib.psb_tensor_stage_fused(ctypes.byref(t), None)
+    assert rc != 0 and b"needs energy_partials" in lib.psb_last_error()
+
+
+def test_tail_mode_selection():
+    """Which part of the stage tail runs where (pystella_b200/step.py::_make_tail): single GPU
+    -- fold + background in the stage's last kernel; x-slab ranks over peer memory -- fold
+    only (the exchange kernel does the rest) unless tune['peer_tail']."""
+    import torch
+    import pystella_b200 as ps
+    sector = ps.ScalarSector(1, potential=lambda f: f[0]**2 / 2)
+
+    class FakeExpansion:
+        nscalars, grid_size, mpl = 1, 512.0, 1.0
+        _A, _B = ps.LowStorageRK54._A, ps.LowStorageRK54._B
+        state = torch.zeros(5, dtype=torch.float64)
+        energies = torch.zeros(5, dtype=torch.float64)
+
+    def make(**tune):
+        st = ps.LowStorageRK54(sector, halo_shape=2, dt=1e-3, dx=(0.1,) * 3,
+                               MapKernel=ps.FusedStencilStage, energy=True, tune=tune)
+        st.energy_nvals, st._stage_index = 3, 1
+        return st
+
+    F, E, P = _lib.TAIL_FOLD, _lib.TAIL_EXPAND, _lib.TAIL_PEER
+    st = make()
+    assert st._make_tail(fold=True, dt=1e-3, device="cpu").mode == F
+    st.attach_expansion(FakeExpansion())
+    tail = st._make_tail(fold=True, dt=1e-3, device="cpu")
+    assert tail.mode == F | E and tail.nscalars == 1 and tail.A == ps.LowStorageRK54._A[1]
+    st._last_of_stage = False                       # a tensor sector follows
+    assert st._make_tail(fold=True, dt=1e-3, device="cpu").mode == F
+    st._last_of_stage = True
+    assert st._make_tail(fold=False, dt=1e-3, nrows=7, device="cpu").mode == E  # tensor kernel
+
+    class FakePeer:
+        args = _lib.PeerArgs()
+    for tune, want in ((dict(), F), (dict(peer_tail=True), F | E | P)):
+        st = make(**tune)
+        st._halo_mode, st._peer = "peer", FakePeer()
+        st.attach_expansion(FakeExpansion())
+        assert st._make_tail(fold=True, dt=1e-3, device="cpu").mode == want
+    st = make(peer_tail=True)
+    st._halo_mode, st._peer, st.fused_energy = "peer", FakePeer(), False
+    tail = st._make_tail(fold=False, dt=1e-3, nrows=5, device="cpu")       # pure barrier
+    assert tail.mode == P and tail.nscalars == 0 and tail.nrows >= 5
+    rows = st._tail_rows.view(torch.int64)
+    assert int(rows[0, 0]) == _lib.TAIL_SENTINEL and bool((rows == _lib.TAIL_SENTINEL).all())

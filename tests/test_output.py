@@ -37,3 +37,19 @@ def test_output_file_default_name(tmp_path, monkeypatch):
     out.close()
     assert out.filename.startswith("20") and out.filename.endswith(".npz")
     assert ps.OutputFile.read(out.filename)["g"]["x"].tolist() == [1]
+
+
+def test_mixed_attributes_are_readable(tmp_path):
+    """a mixed list / tuple attribute must not become an unreadable object array."""
+    import os
+    import pystella_b200 as ps
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        out = ps.OutputFile(name="attrs", grid=(4, 4, 4), mixed=[1, "a", 2.5], nested=((1, 2), 3))
+        out.output("energy", t=0.0, a=1.0)
+        out.close() if hasattr(out, "close") else out.flush()
+        data = ps.OutputFile.read(out.filename)
+    finally:
+        os.chdir(cwd)
+    assert "energy" in data
