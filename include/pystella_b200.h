@@ -175,6 +175,9 @@ typedef struct psb_scalar_stage_args {
   int32_t tune_prefetch;         /* fused: planes the producer prefetches into L2 ahead of
                                     its loads; 0 = default, < 0 = none                  */
   int32_t reserved0;
+  void* pws_sched;               /* fused, optional: 16 zeroed bytes of device memory (work
+                                    scheduler of the persistent kernel variant, re-armed
+                                    by the kernel); NULL = one-chunk-per-CTA kernels only */
 } psb_scalar_stage_args;
 
 int psb_scalar_stage_fused(const psb_scalar_stage_args* args, void* stream);

@@ -40,7 +40,7 @@ def scalar_stage(*, fused, f_in, f_out, dfdt, kf, kdfdt, lap_f=None, h, dx=(1., 
                  queue=None, strict=False, xchunk=0, variant=0,
                  energy_partials=None, energy_slot_offset=0, V_terms=None,
                  count_slots_only=False, peer=None, generated=None, tail=None,
-                 prefetch=0):
+                 prefetch=0, pws_sched=None):
     """
     One scalar-sector LSRK stage on padded arrays of shape ``(n, Nx+2h, Ny+2h, Nz+2h)``
     (or without the leading axis for a single field).
@@ -104,6 +104,8 @@ def scalar_stage(*, fused, f_in, f_out, dfdt, kf, kdfdt, lap_f=None, h, dx=(1., 
     args.tune_xchunk = xchunk
     args.tune_variant = variant
     args.tune_prefetch = int(prefetch)
+    if pws_sched is not None:
+        args.pws_sched = _ptr(pws_sched)
     if tail is not None:
         if not fused:
             raise ValueError("the in-kernel stage tail exists for the fused stage only")

@@ -71,6 +71,7 @@ class ScalarStageArgs(C.Structure):
         ("tune_xchunk", c_int32), ("tune_variant", c_int32),
         ("tail", C.POINTER(StageTail)),
         ("tune_prefetch", c_int32), ("reserved0", c_int32),
+        ("pws_sched", c_void_p),
     ]
 
 

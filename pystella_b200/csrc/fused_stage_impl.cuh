@@ -47,6 +47,7 @@ template <typename T, int NF> struct FusedParams {
   int x2_begin, x2_end, nchunks1;
   int nmain, split_len;   // x-chunk schedule of range 1 (chunk_range())
   int pf_dist;            // L2 prefetch distance of the pipeline's producer (planes; 0 = off)
+  int pws_rows;           // persistent kernel: chunks (= published rows) of the launch
   int wrap_x, wrap_y, wrap_z;
   T* peer_lo;   // peer-mapped f_out of rank rx-1 / rx+1 (or null)
   T* peer_hi;
@@ -672,6 +673,7 @@ static int64_t fused_grid_blocks(const psb_scalar_stage_args* a) {
 #endif  // !__CUDACC_RTC__
 }  // namespace psb
 #include "fused_stage_ws.cuh"
+#include "fused_stage_pws.cuh"
 #ifndef __CUDACC_RTC__
 namespace psb {
 
@@ -715,6 +717,20 @@ static int ws_op(const psb_scalar_stage_args* a, cudaStream_t stream, int64_t* c
     return 0;
   }
   return launch_ws<T, H, NF, BY, TZ, P, MINB, VEC, AL>(a, stream);
+}
+
+// persistent variant (fused_stage_pws.cuh): MINB = resident CTAs per SM the grid is sized for
+template <typename T, int H, int NF, int BY, int TZ, int P, int MINB, int VEC = 2>
+static int pws_op(const psb_scalar_stage_args* a, cudaStream_t stream, int64_t* count) {
+  if (t_fused_plan) {
+    set_error("psb_scalar_stage_fused_plan: the persistent variant has no plan");
+    return 3;
+  }
+  if (count) {
+    *count = pws_rows<T, H, NF, BY, TZ, P, MINB, VEC>(a);
+    return 0;
+  }
+  return launch_pws<T, H, NF, BY, TZ, P, MINB, VEC>(a, stream);
 }
 
 // can TMA describe all four arrays?  (mirrors encode_field_tensor_map's checks)
@@ -763,6 +779,28 @@ static int dispatch_vec(const psb_scalar_stage_args* a, cudaStream_t stream,
     // warp-specialised TMA pipeline (default)
     const int var = a->tune_variant;
     if ((var == 0 || var >= 10) && tma_layout_ok<T>(a, H)) {
+      if constexpr (H == 2 && NF <= 2) {
+        // persistent CTAs with a continuous pipeline and guided self-scheduling
+        // (fused_stage_pws.cuh); tune_variant 30 while it is being measured
+        if (var == 30 && pws_eligible(a)) {
+          if constexpr (std::is_same<T, double>::value && NF == 1) {
+            return pws_op<T, H, NF, 4, 64, 3, 2>(a, stream, count);
+          } else if constexpr (std::is_same<T, double>::value) {
+            constexpr int TZp = ws_pick_tz(ES, H, NF, 4, 1, 2, SMEM_LIMIT_3);
+            return pws_op<T, H, NF, 4, TZp, 1, 3>(a, stream, count);
+          } else if constexpr (NF == 1) {
+            if (a->Nz % 4 == 0) {
+              constexpr int TZp = ws_pick_tz(ES, H, NF, 4, 2, 4);
+              return pws_op<T, H, NF, 4, TZp, 2, 3, 4>(a, stream, count);
+            }
+          } else {
+            if (a->Nz % 4 == 0) {
+              constexpr int TZp = ws_pick_tz(ES, H, NF, 4, 1, 4, SMEM_LIMIT_3);
+              return pws_op<T, H, NF, 4, TZp, 1, 3, 4>(a, stream, count);
+            }
+          }
+        }
+      }
       if constexpr (std::is_same<T, double>::value && H == 2 && NF == 1) {
         // tuned configurations of the headline case
         if (var == 11) return ws_op<T, H, NF, 8, 64, 3, 1>(a, stream, count);

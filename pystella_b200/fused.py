@@ -256,6 +256,10 @@ def fused_scalar_stage(stepper, system, f, common, queue):
     tune = stepper.tune or {}
     args.update(xchunk=tune.get("xchunk", 0), variant=tune.get("variant", 0),
                 prefetch=tune.get("prefetch", 0))
+    if stepper.__dict__.get("_pws_sched") is None:
+        # scheduler words of the persistent kernel variant (zero between launches)
+        stepper._pws_sched = torch.zeros(2, dtype=torch.int64, device=f.device)
+    args.update(pws_sched=stepper._pws_sched)
 
     nslots = 0
     if stepper.fused_energy:

@@ -103,6 +103,13 @@ if __name__ == "__main__":
         for var in (0, 22):
             scalar_case(N5, F32, 1, True, nscalars=2, tune={"variant": var})
             scalar_case((256,) * 3, F64, 1, True, nscalars=2, tune={"variant": var})
+    if "pws" in which:
+        for var in (0, 30):
+            for shape in (N5, (64, 512, 512), (256,) * 3):
+                scalar_case(shape, F64, 1, True, tune={"variant": var})
+            scalar_case(N5, F64, 0, True, tune={"variant": var})
+            scalar_case((128, 1024, 1024), F32, 1, True, tune={"variant": var})
+            scalar_case(N5, F32, 1, True, nscalars=2, tune={"variant": var})
     if "gwprof" in which:
         gw_case(384, F32)
     if "f32prof" in which:

@@ -356,3 +356,161 @@ def test_pipeline_ring_protocol_is_deadlock_free():
             for ncomp in (1, 2, 5, 16):
                 for ncw in (1, 4, 8):
                     _simulate_rings(H, P, ncomp, ncw, rng)
+
+
+# ---------------------------------------------------------------------------------------
+# persistent variant (csrc/fused_stage_pws.cuh): the same rings run CONTINUOUSLY across
+# segments; slots carry headers; at the end of a segment the consumer releases the H trailing
+# planes as well.  The simulation restates producer and consumer loops and checks, under
+# random scheduling: no dead-lock, no phase aliasing, every consumer sees the header and the
+# plane the producer meant for that step, centre planes are still intact when they are read,
+# every slot use is released exactly once, every site plane of every segment is produced
+# exactly once, and the guided schedule partitions the items identically for every run.
+# ---------------------------------------------------------------------------------------
+
+def _pws_chunk_items(remaining, ncta, kmax=32):
+    return min(max(remaining // (2 * ncta), 1), kmax, remaining)
+
+
+def _pws_chunks(total, ncta):
+    cur, out = 0, []
+    while cur < total:
+        k = _pws_chunk_items(total - cur, ncta)
+        out.append((cur, k))
+        cur += k
+    return out
+
+
+def test_pws_schedule_is_a_static_partition():
+    for total, ncta in ((8192, 296), (65536, 296), (37, 296), (1000, 7), (1, 1)):
+        chunks = _pws_chunks(total, ncta)
+        assert chunks[0][0] == 0 and sum(k for _, k in chunks) == total
+        assert all(a + k == b for (a, k), (b, _) in zip(chunks, chunks[1:]))
+        # large chunks first, single items at the end
+        sizes = [k for _, k in chunks]
+        assert sizes == sorted(sizes, reverse=True) and sizes[-1] == 1
+        if total >= 64 * ncta:
+            assert sizes[0] == 32
+
+
+def _simulate_pws(H, P, segments, ncw, rng):
+    """segments: list of (out_lo, out_hi) handled by one CTA, in order."""
+    RF, RP = H + 1 + P, P + 1
+    full_f = [_Mbar(1) for _ in range(RF)]
+    empty_f = [_Mbar(ncw) for _ in range(RF)]
+    full_p = [_Mbar(1) for _ in range(RP)]
+    empty_p = [_Mbar(ncw) for _ in range(RP)]
+    fslot, pslot, hdr = [None] * RF, [None] * RP, [None] * RF
+    in_flight = []
+    # the producer's plan: one entry per f plane (+ the terminate marker)
+    plan = []
+    for si, (lo, hi) in enumerate(segments):
+        nseg = (hi - lo) + 2 * H
+        for m in range(nseg):
+            plan.append(dict(seg=si, xpad=lo + m, lo=lo, hi=hi, end=(m == nseg - 1), term=False))
+    plan.append(dict(term=True))
+    prod = {"g": 0, "gp": 0, "stage": 0}
+    cons = [{"g": 0, "gp": 0, "done": False} for _ in range(ncw)]
+    produced = []
+
+    def producer_step():
+        g = prod["g"]
+        if g >= len(plan):
+            return False
+        e = plan[g]
+        slot = g % RF
+        if prod["stage"] == 0:
+            if g >= RF and not empty_f[slot].done(g // RF - 1):
+                return False
+            hdr[slot] = e
+            if e["term"]:
+                full_f[slot].arrive()
+                prod["g"] = g + 1
+                return True
+            in_flight.append(("f", slot, g))
+            prod["stage"] = 1
+            return True
+        m = e["xpad"] - e["lo"]
+        if m >= 2 * H:
+            gp = prod["gp"]
+            ps_ = gp % RP
+            if gp >= RP and not empty_p[ps_].done(gp // RP - 1):
+                return False
+            in_flight.append(("p", ps_, (e["seg"], e["xpad"] - 2 * H)))
+            prod["gp"] = gp + 1
+        prod["g"], prod["stage"] = g + 1, 0
+        return True
+
+    def tma_step():
+        if not in_flight:
+            return False
+        kind, slot, tag = in_flight.pop(rng.integers(len(in_flight)))
+        if kind == "f":
+            fslot[slot] = tag
+            full_f[slot].arrive()
+        else:
+            pslot[slot] = tag
+            full_p[slot].arrive()
+        return True
+
+    def consumer_step(w):
+        c = cons[w]
+        if c["done"]:
+            return False
+        g = c["g"]
+        slot = g % RF
+        if not full_f[slot].done(g // RF):
+            return False
+        e = hdr[slot]
+        assert e is plan[g], "header of another step"
+        if e["term"]:
+            c["done"] = True
+            return True
+        assert fslot[slot] == g, "own plane overwritten"
+        m = e["xpad"] - e["lo"]
+        if m >= 2 * H:
+            gp = c["gp"]
+            ps_ = gp % RP
+            if not full_p[ps_].done(gp // RP):
+                return False
+            assert fslot[(g - H) % RF] == g - H, "centre plane overwritten"
+            assert pslot[ps_] == (e["seg"], e["xpad"] - 2 * H), "wrong pointwise plane"
+            if w == 0:
+                produced.append((e["seg"], e["xpad"] - 2 * H))
+            empty_p[ps_].arrive()
+            c["gp"] = gp + 1
+        if m >= H:
+            empty_f[(g - H) % RF].arrive()
+        if e["end"]:
+            for s in range(H - 1, -1, -1):
+                empty_f[(g - s) % RF].arrive()
+        c["g"] = g + 1
+        return True
+
+    idle = 0
+    while not all(c["done"] for c in cons):
+        actors = [producer_step, tma_step] + [lambda w=w: consumer_step(w) for w in range(ncw)]
+        if actors[rng.integers(len(actors))]():
+            idle = 0
+        else:
+            idle += 1
+            assert idle < 20000, "dead-lock"
+    want = [(si, i) for si, (lo, hi) in enumerate(segments) for i in range(lo, hi)]
+    assert produced == want
+    # every slot use released exactly once: the barriers are back in their initial state
+    nplanes = len(plan) - 1
+    for s in range(RF):
+        uses = len(range(s, nplanes, RF))
+        assert empty_f[s].completed == uses and empty_f[s].pending == ncw
+
+
+def test_pws_ring_protocol_simulation():
+    rng = np.random.default_rng(2024)
+    for H, P in ((2, 3), (2, 2), (2, 1), (1, 2), (4, 1)):
+        for _ in range(6):
+            nseg = int(rng.integers(1, 5))
+            segments = []
+            for _s in range(nseg):
+                lo = int(rng.integers(0, 40)) * 4
+                segments.append((lo, lo + int(rng.integers(1, 9)) * 4 - int(rng.integers(0, 3))))
+            _simulate_pws(H, P, segments, int(rng.integers(1, 5)), rng)
