@@ -10,11 +10,10 @@
 //
 // Work decomposition: the lattice is cut into columns (BY x BZ tiles marched along x) and
 // every column into items of PWS_ITEM consecutive site planes; items are numbered column by
-// column.  CTAs claim CHUNKS of consecutive items from one packed 64-bit word
-// (chunk count << 32 | next item) with a CAS; the chunk size is a function of the number of
-// items still unclaimed only (guided self-scheduling: large chunks first -- few prologues --
-// and single items at the end -- a short tail), so the PARTITION of items into chunks is the
-// same in every run, whatever the timing; only which CTA executes a chunk varies.  Each chunk
+// column.  CTAs claim CHUNKS of consecutive items by chunk number (one atomicAdd); the chunk
+// sizes follow a tabulated guided schedule (large chunks first -- few prologues -- and single
+// items at the end -- a short tail), so the PARTITION of items into chunks is the same in
+// every run, whatever the timing; only which CTA executes a chunk varies.  Each chunk
 // publishes one row of energy partial sums (row index = chunk index): the watcher CTA's sum
 // over the rows is deterministic, as in the one-chunk-per-CTA kernel.
 //
@@ -29,15 +28,7 @@ namespace psb {
 
 constexpr int PWS_ITEM = 4;          // site planes per work item
 constexpr int PWS_MAX_CHUNK = 32;    // items (128 planes)
-
-// items claimed by the next chunk when `remaining` items are unclaimed and `ncta` CTAs run
-__host__ __device__ inline unsigned pws_chunk_items(unsigned remaining, unsigned ncta) {
-  unsigned k = remaining / (2u * ncta);
-  if (k < 1u) k = 1u;
-  if (k > (unsigned)PWS_MAX_CHUNK) k = (unsigned)PWS_MAX_CHUNK;
-  if (k > remaining) k = remaining;
-  return k;
-}
+constexpr int PWS_PHASES = 6;        // chunk sizes 32, 16, 8, 4, 2, 1 items
 
 struct PwsHeader {
   int col;        // column (tile) index
@@ -52,13 +43,38 @@ constexpr int PWS_TERMINATE = 1;   // no more work: consumers leave
 constexpr int PWS_SEG_END = 2;     // last plane of a segment: release the trailing planes
 constexpr int PWS_FLUSH = 4;       // last plane of a chunk: publish the chunk's row
 
+// The schedule: chunks of 32 items while at least ncta chunks' worth of items remain,
+// then 16, 8, ... 1 (guided self-scheduling in six phases: few prologues early, a short tail
+// at the end).  It is a pure function of (total items, ncta), tabulated on the host; chunk
+// number i is claimed with ONE atomicAdd (a CAS loop on a packed word was measured first:
+// 296 producers retrying against each other cost 0.5 ms per launch).
 struct PwsSched {
-  unsigned long long* word;   // chunk count << 32 | next item; zero between launches
+  unsigned int* counter;      // chunks claimed beyond the first one of every CTA; zero
+                              // between launches (re-armed by the last CTA)
   unsigned int* done;         // CTAs that have finished claiming
-  unsigned total_items;
+  unsigned nchunks;
+  unsigned phase_chunk0[PWS_PHASES + 1];   // first chunk index of each phase
+  unsigned phase_item0[PWS_PHASES + 1];    // first item of each phase
   int items_per_col;          // ceil(Nx / PWS_ITEM)
   int tiles_z;                // columns: col = ty * tiles_z + tz
 };
+
+// chunk i -> (first item, number of items)
+__host__ __device__ inline void pws_chunk(const PwsSched& s, unsigned i, unsigned* item0,
+                                          unsigned* nitems) {
+  unsigned k = (unsigned)PWS_MAX_CHUNK;
+  int ph = 0;
+#pragma unroll
+  for (int j = 1; j < PWS_PHASES; ++j) {
+    if (i >= s.phase_chunk0[j]) {
+      ph = j;
+      k = (unsigned)PWS_MAX_CHUNK >> j;
+    }
+  }
+  *item0 = s.phase_item0[ph] + (i - s.phase_chunk0[ph]) * k;
+  const unsigned end = s.phase_item0[ph + 1];
+  *nitems = (*item0 + k <= end) ? k : end - *item0;
+}
 
 template <typename T, int H, int NF, int BY, int TZ, int P, bool ENERGY, int MINB, int VEC_ = 2>
 __global__ void __launch_bounds__(BY* TZ + 32, MINB)
@@ -115,23 +131,20 @@ __global__ void __launch_bounds__(BY* TZ + 32, MINB)
         if (g >= (unsigned)RF) mbar_wait(&empty_f[slot], ((g / RF) - 1) & 1);
         return slot;
       };
+      bool first = true;
       for (;;) {
-        // ---- claim the next chunk
-        unsigned item0 = 0, nitems = 0, row = 0;
-        for (;;) {
-          const unsigned long long w = atomicAdd(sched.word, 0ull);
-          const unsigned cur = (unsigned)(w & 0xffffffffull), cnt = (unsigned)(w >> 32);
-          if (cur >= sched.total_items) break;
-          const unsigned k = pws_chunk_items(sched.total_items - cur, gridDim.x);
-          const unsigned long long nw = ((unsigned long long)(cnt + 1) << 32) | (cur + k);
-          if (atomicCAS(sched.word, w, nw) == w) {
-            item0 = cur;
-            nitems = k;
-            row = cnt;
-            break;
-          }
+        // ---- claim the next chunk: the CTA's own index first, then one atomicAdd each
+        unsigned ci;
+        if (first) {
+          ci = blockIdx.x;
+          first = false;
+        } else {
+          ci = gridDim.x + atomicAdd(sched.counter, 1u);
         }
-        if (nitems == 0) break;
+        if (ci >= sched.nchunks) break;
+        unsigned item0, nitems;
+        pws_chunk(sched, ci, &item0, &nitems);
+        const unsigned row = ci;
         // ---- its segments: maximal runs of items inside one column
         unsigned it = item0;
         const unsigned item_end = item0 + nitems;
@@ -197,7 +210,7 @@ __global__ void __launch_bounds__(BY* TZ + 32, MINB)
         mbar_arrive(&full_f[slot]);
       }
       if (atomicAdd(sched.done, 1u) == gridDim.x - 1) {
-        atomicExch(sched.word, 0ull);
+        atomicExch(sched.counter, 0u);
         atomicExch(sched.done, 0u);
       }
     }
@@ -462,15 +475,29 @@ __global__ void __launch_bounds__(BY* TZ + 32, MINB)
 // ---------------------------------------------------------------------------
 #ifndef __CUDACC_RTC__
 
-// chunks (= rows) of the schedule for `total` items on `ncta` CTAs
-static inline int64_t pws_count_chunks(unsigned total, unsigned ncta) {
-  int64_t n = 0;
-  unsigned cur = 0;
-  while (cur < total) {
-    cur += pws_chunk_items(total - cur, ncta);
-    ++n;
+// tabulate the schedule for `total` items on `ncta` CTAs
+static inline void pws_make_schedule(PwsSched& s, unsigned total, unsigned ncta) {
+  unsigned item = 0, chunk = 0;
+  for (int j = 0; j < PWS_PHASES; ++j) {
+    const unsigned k = (unsigned)PWS_MAX_CHUNK >> j;
+    s.phase_chunk0[j] = chunk;
+    s.phase_item0[j] = item;
+    const unsigned rem = total - item;
+    unsigned n;
+    if (k == 1u) {
+      n = rem;                       // everything that is left, item by item
+    } else {
+      // chunks of k items as long as at least ncta * k items remain afterwards (one more
+      // round of this size would leave the CTAs unbalanced by up to a whole chunk)
+      const unsigned keep = ncta * k;
+      n = rem > keep ? (rem - keep) / k : 0u;
+    }
+    item += n * k;
+    chunk += n;
   }
-  return n;
+  s.phase_chunk0[PWS_PHASES] = chunk;
+  s.phase_item0[PWS_PHASES] = total;
+  s.nchunks = chunk;
 }
 
 template <typename T, int H, int NF, int BY, int TZ, int P, int VEC>
@@ -507,7 +534,9 @@ static int64_t pws_rows(const psb_scalar_stage_args* a) {
   unsigned total;
   int ipc, tz;
   const unsigned grid = pws_grid<T, H, NF, BY, TZ, P, MINB, VEC>(a, &total, &ipc, &tz);
-  return pws_count_chunks(total, grid);
+  PwsSched s;
+  pws_make_schedule(s, total, grid);
+  return s.nchunks;
 }
 
 template <typename T, int H, int NF, int BY, int TZ, int P, int MINB, int VEC = 2>
@@ -532,12 +561,12 @@ static int launch_pws(const psb_scalar_stage_args* a, cudaStream_t stream) {
   int ipc, tz;
   unsigned total;
   const unsigned grid = pws_grid<T, H, NF, BY, TZ, P, MINB, VEC>(a, &total, &ipc, &tz);
-  s.word = reinterpret_cast<unsigned long long*>(a->pws_sched);
+  s.counter = reinterpret_cast<unsigned int*>(a->pws_sched);
   s.done = reinterpret_cast<unsigned int*>(a->pws_sched) + 2;
-  s.total_items = total;
   s.items_per_col = ipc;
   s.tiles_z = tz;
-  p.pws_rows = (int)pws_count_chunks(total, grid);
+  pws_make_schedule(s, total, grid);
+  p.pws_rows = (int)s.nchunks;
   dim3 block(C::THREADS, 1, 1);
   if (a->energy_partials != nullptr) {
     auto kern = fused_stage_pws_kernel<T, H, NF, BY, TZ, P, true, MINB, VEC>;

@@ -368,29 +368,43 @@ def test_pipeline_ring_protocol_is_deadlock_free():
 # exactly once, and the guided schedule partitions the items identically for every run.
 # ---------------------------------------------------------------------------------------
 
-def _pws_chunk_items(remaining, ncta, kmax=32):
-    return min(max(remaining // (2 * ncta), 1), kmax, remaining)
-
-
-def _pws_chunks(total, ncta):
-    cur, out = 0, []
-    while cur < total:
-        k = _pws_chunk_items(total - cur, ncta)
-        out.append((cur, k))
-        cur += k
+def _pws_schedule(total, ncta, kmax=32, phases=6):
+    """csrc/fused_stage_pws.cuh::pws_make_schedule + pws_chunk, restated."""
+    item, chunk, table = 0, 0, []
+    for j in range(phases):
+        k = kmax >> j
+        rem = total - item
+        n = rem if k == 1 else ((rem - ncta * k) // k if rem > ncta * k else 0)
+        table.append((chunk, item, k))
+        item += n * k
+        chunk += n
+    nchunks = chunk
+    out = []
+    for i in range(nchunks):
+        ph = max(j for j, (c0, _, _) in enumerate(table) if i >= c0 and
+                 (j == phases - 1 or table[j + 1][0] > i or table[j + 1][0] == c0))
+        # the device picks the LAST phase whose first chunk index is <= i
+        ph = max(j for j, (c0, _, _) in enumerate(table) if i >= c0)
+        c0, i0, k = table[ph]
+        end = table[ph + 1][1] if ph + 1 < phases else total
+        start = i0 + (i - c0) * k
+        out.append((start, min(k, end - start)))
     return out
 
 
 def test_pws_schedule_is_a_static_partition():
-    for total, ncta in ((8192, 296), (65536, 296), (37, 296), (1000, 7), (1, 1)):
-        chunks = _pws_chunks(total, ncta)
+    for total, ncta in ((8192, 296), (65536, 296), (37, 296), (1000, 7), (1, 1), (40000, 148)):
+        chunks = _pws_schedule(total, ncta)
         assert chunks[0][0] == 0 and sum(k for _, k in chunks) == total
+        assert all(k >= 1 for _, k in chunks)
         assert all(a + k == b for (a, k), (b, _) in zip(chunks, chunks[1:]))
-        # large chunks first, single items at the end
+        # large chunks first, single items at the end; at least 2 * ncta single items
         sizes = [k for _, k in chunks]
         assert sizes == sorted(sizes, reverse=True) and sizes[-1] == 1
         if total >= 64 * ncta:
             assert sizes[0] == 32
+        if total >= 2 * ncta:
+            assert sizes.count(1) >= ncta
 
 
 def _simulate_pws(H, P, segments, ncw, rng):
