@@ -95,3 +95,37 @@ def test_bench_window_parity_single_gpu(config, grid):
     assert par["ok"], par
     if cfg["dtype"] == "f64":
         assert par["max_rel"] < 1e-12
+
+
+@pytest.mark.parametrize("dtype,tol", [("f64", 1e-12), ("f32", 2e-4)])
+@pytest.mark.parametrize("nscalars", [1, 2])
+def test_persistent_variant_parity(dtype, tol, nscalars):
+    """tune_variant 30 (csrc/fused_stage_pws.cuh: persistent CTAs, continuous pipeline, guided
+    self-scheduling) through bench.py's parity block: window across the periodic boundary
+    against the C oracle, energies and background included; and field-for-field against the
+    default kernel (same per-site arithmetic: only the order of the energy sums differs)."""
+    cfg = dict(bench.CONFIGS["c3"], name="c3", dtype=dtype, grid=(72, 40, 128))
+    if nscalars == 2:
+        cfg["system"] = "scalar2gw"     # exercises the two-field instance (+ tensor kernel)
+        cfg["amp"] = 1e-2
+    w = bench.workload(cfg, 1, 0)
+    decomp = ps.DomainDecomposition((1, 1, 1), w["h"], rank_shape=w["rank_shape"])
+    results = {}
+    for variant in (30, 0):
+        job = bench.Job(ps, torch, cfg, w, decomp, torch.device("cuda", 0),
+                        {"xchunk": 0, "variant": variant}, float(np.prod(w["grid_shape"])))
+        par = bench.run_parity(job, cfg, w, 1, 0, None, half=8, margin=22)
+        assert par["ok"] and par["max_rel"] < tol, (variant, par)
+        stepper = job.make_stepper()
+        arrays = job.upload()
+        expand = job.make_expansion()
+        for s in range(5):
+            stepper(s, a=expand.a, hubble=expand.hubble, **arrays)
+            expand.step(s, stepper, w["dt"])
+        torch.cuda.synchronize()
+        results[variant] = ({k: v.cpu().numpy() for k, v in arrays.items()}, expand.get())
+    for name in results[0][0]:
+        a30, a0 = results[30][0][name], results[0][0][name]
+        scale = np.max(np.abs(a0)) or 1.0
+        assert np.max(np.abs(a30 - a0)) / scale < (1e-13 if dtype == "f64" else 1e-6), name
+    assert np.isclose(results[30][1]["a"], results[0][1]["a"], rtol=1e-13)
