@@ -9,11 +9,10 @@
 // (config 3 per GPU at N = 8) and of 256^3 (config 2).
 //
 // Work decomposition: the lattice is cut into columns (BY x BZ tiles marched along x) and
-// every column into items of PWS_ITEM consecutive site planes; items are numbered column by
-// column.  CTAs claim CHUNKS of consecutive items by chunk number (one atomicAdd); the chunk
-// sizes follow a tabulated guided schedule (large chunks first -- few prologues -- and single
-// items at the end -- a short tail), so the PARTITION of items into chunks is the same in
-// every run, whatever the timing; only which CTA executes a chunk varies.  Each chunk
+// every column into chunks of 128 ... 4 site planes (long chunks for the bulk -- few
+// prologues --, short ones at the end of the launch -- a short tail; see PwsSched).  CTAs
+// claim chunks by number (one atomicAdd); the partition is static, only which CTA executes a
+// chunk varies from run to run.  Each chunk
 // publishes one row of energy partial sums (row index = chunk index): the watcher CTA's sum
 // over the rows is deterministic, as in the one-chunk-per-CTA kernel.
 //
@@ -26,9 +25,8 @@
 
 namespace psb {
 
-constexpr int PWS_ITEM = 4;          // site planes per work item
-constexpr int PWS_MAX_CHUNK = 32;    // items (128 planes)
-constexpr int PWS_PHASES = 6;        // chunk sizes 32, 16, 8, 4, 2, 1 items
+constexpr int PWS_MAX_CHUNK = 128;   // site planes of the longest chunks
+constexpr int PWS_PHASES = 6;        // chunk lengths 128, 64, 32, 16, 8, 4 planes
 
 struct PwsHeader {
   int col;        // column (tile) index
@@ -43,37 +41,45 @@ constexpr int PWS_TERMINATE = 1;   // no more work: consumers leave
 constexpr int PWS_SEG_END = 2;     // last plane of a segment: release the trailing planes
 constexpr int PWS_FLUSH = 4;       // last plane of a chunk: publish the chunk's row
 
-// The schedule: chunks of 32 items while at least ncta chunks' worth of items remain,
-// then 16, 8, ... 1 (guided self-scheduling in six phases: few prologues early, a short tail
-// at the end).  It is a pure function of (total items, ncta), tabulated on the host; chunk
-// number i is claimed with ONE atomicAdd (a CAS loop on a packed word was measured first:
-// 296 producers retrying against each other cost 0.5 ms per launch).
+// The schedule.  A chunk is an x range of ONE column; the x axis is cut into six phases with
+// chunk lengths 128, 64, ... 4 planes (every phase leaves at least one chunk length for the
+// shorter ones: few prologues for the bulk, short chunks at the end of the launch).  Chunks
+// are numbered phase by phase, inside a phase x-range by x-range, inside an x-range column by
+// column -- so the CTAs that run together work on NEIGHBOURING tiles of the SAME x range and
+// share their y/z halo rows through L2, like the one-chunk-per-CTA kernel (a column-major
+// numbering was measured first: 12 % slower at 512^3, the halo rows then come from DRAM).
+// The numbering is a pure function of (Nx, columns): which CTA runs a chunk varies from run
+// to run, the partition (and with it the order of the energy sums) does not.  Chunk i is
+// claimed with ONE atomicAdd (a CAS loop on a packed word was measured first: 296 producers
+// retrying against each other cost 0.5 ms per launch).
 struct PwsSched {
   unsigned int* counter;      // chunks claimed beyond the first one of every CTA; zero
                               // between launches (re-armed by the last CTA)
   unsigned int* done;         // CTAs that have finished claiming
   unsigned nchunks;
+  unsigned ncol;              // columns (tiles)
   unsigned phase_chunk0[PWS_PHASES + 1];   // first chunk index of each phase
-  unsigned phase_item0[PWS_PHASES + 1];    // first item of each phase
-  int items_per_col;          // ceil(Nx / PWS_ITEM)
-  int tiles_z;                // columns: col = ty * tiles_z + tz
+  int phase_x0[PWS_PHASES + 1];            // first site plane of each phase
+  int tiles_z;                // col = ty * tiles_z + tz
 };
 
-// chunk i -> (first item, number of items)
-__host__ __device__ inline void pws_chunk(const PwsSched& s, unsigned i, unsigned* item0,
-                                          unsigned* nitems) {
-  unsigned k = (unsigned)PWS_MAX_CHUNK;
-  int ph = 0;
+// chunk i -> (column, [out_lo, out_hi))
+__host__ __device__ inline void pws_chunk(const PwsSched& s, unsigned i, int* col, int* out_lo,
+                                          int* out_hi) {
+  int len = PWS_MAX_CHUNK, ph = 0;
 #pragma unroll
   for (int j = 1; j < PWS_PHASES; ++j) {
     if (i >= s.phase_chunk0[j]) {
       ph = j;
-      k = (unsigned)PWS_MAX_CHUNK >> j;
+      len = PWS_MAX_CHUNK >> j;
     }
   }
-  *item0 = s.phase_item0[ph] + (i - s.phase_chunk0[ph]) * k;
-  const unsigned end = s.phase_item0[ph + 1];
-  *nitems = (*item0 + k <= end) ? k : end - *item0;
+  const unsigned local = i - s.phase_chunk0[ph];
+  const int xb = (int)(local / s.ncol);
+  *col = (int)(local % s.ncol);
+  *out_lo = s.phase_x0[ph] + xb * len;
+  const int end = s.phase_x0[ph + 1];
+  *out_hi = *out_lo + len < end ? *out_lo + len : end;
 }
 
 template <typename T, int H, int NF, int BY, int TZ, int P, bool ENERGY, int MINB, int VEC_ = 2>
@@ -142,20 +148,10 @@ __global__ void __launch_bounds__(BY* TZ + 32, MINB)
           ci = gridDim.x + atomicAdd(sched.counter, 1u);
         }
         if (ci >= sched.nchunks) break;
-        unsigned item0, nitems;
-        pws_chunk(sched, ci, &item0, &nitems);
         const unsigned row = ci;
-        // ---- its segments: maximal runs of items inside one column
-        unsigned it = item0;
-        const unsigned item_end = item0 + nitems;
-        while (it < item_end) {
-          const int col = (int)(it / (unsigned)sched.items_per_col);
-          const int b0 = (int)(it % (unsigned)sched.items_per_col);
-          int nb = sched.items_per_col - b0;
-          if ((unsigned)nb > item_end - it) nb = (int)(item_end - it);
-          it += (unsigned)nb;
-          const int out_lo = b0 * PWS_ITEM;
-          const int out_hi = min((b0 + nb) * PWS_ITEM, p.Nx);
+        {
+          int col, out_lo, out_hi;
+          pws_chunk(sched, ci, &col, &out_lo, &out_hi);
           const int z0 = (col % sched.tiles_z) * C::BZ, y0 = (col / sched.tiles_z) * BY;
           const int nseg = (out_hi - out_lo) + 2 * H;
           for (int m = 0; m < nseg; ++m) {
@@ -166,8 +162,7 @@ __global__ void __launch_bounds__(BY* TZ + 32, MINB)
             h.out_lo = out_lo;
             h.out_hi = out_hi;
             h.row = (int)row;
-            h.flags = (m == nseg - 1 ? PWS_SEG_END : 0) |
-                      ((m == nseg - 1 && it >= item_end) ? PWS_FLUSH : 0);
+            h.flags = (m == nseg - 1) ? (PWS_SEG_END | PWS_FLUSH) : 0;
             h.pad0 = h.pad1 = 0;
             hdr[slot] = h;
             mbar_expect_tx(&full_f[slot], NF * C::FPLANE_RAW);
@@ -475,28 +470,26 @@ __global__ void __launch_bounds__(BY* TZ + 32, MINB)
 // ---------------------------------------------------------------------------
 #ifndef __CUDACC_RTC__
 
-// tabulate the schedule for `total` items on `ncta` CTAs
-static inline void pws_make_schedule(PwsSched& s, unsigned total, unsigned ncta) {
-  unsigned item = 0, chunk = 0;
+// tabulate the schedule for columns of Nx site planes
+static inline void pws_make_schedule(PwsSched& s, int Nx, unsigned ncol) {
+  int x = 0;
+  unsigned chunk = 0;
+  s.ncol = ncol;
   for (int j = 0; j < PWS_PHASES; ++j) {
-    const unsigned k = (unsigned)PWS_MAX_CHUNK >> j;
+    const int len = PWS_MAX_CHUNK >> j;
     s.phase_chunk0[j] = chunk;
-    s.phase_item0[j] = item;
-    const unsigned rem = total - item;
-    unsigned n;
-    if (k == 1u) {
-      n = rem;                       // everything that is left, item by item
-    } else {
-      // chunks of k items as long as at least ncta * k items remain afterwards (one more
-      // round of this size would leave the CTAs unbalanced by up to a whole chunk)
-      const unsigned keep = ncta * k;
-      n = rem > keep ? (rem - keep) / k : 0u;
-    }
-    item += n * k;
-    chunk += n;
+    s.phase_x0[j] = x;
+    const int rem = Nx - x;
+    int n;   // chunks of this length along x, per column
+    if (j == PWS_PHASES - 1)
+      n = (rem + len - 1) / len;                 // whatever is left, in the shortest chunks
+    else
+      n = rem > len ? (rem - len) / len : 0;     // leave at least `len` planes for them
+    x += (j == PWS_PHASES - 1) ? rem : n * len;
+    chunk += (unsigned)n * ncol;
   }
   s.phase_chunk0[PWS_PHASES] = chunk;
-  s.phase_item0[PWS_PHASES] = total;
+  s.phase_x0[PWS_PHASES] = Nx;
   s.nchunks = chunk;
 }
 
@@ -507,18 +500,15 @@ struct PwsGeom {
       C::SMEM_BYTES + C::RF * (int)sizeof(PwsHeader) + C::NCW * (2 * NF + 1) * 8 + 64;
 };
 
-// CTAs of the persistent launch: resident slots (MINB per SM), never more than there is work
+// CTAs of the persistent launch: resident slots (MINB per SM), never more than chunks
 template <typename T, int H, int NF, int BY, int TZ, int P, int MINB, int VEC>
-static unsigned pws_grid(const psb_scalar_stage_args* a, unsigned* total_items, int* ipc,
-                         int* tiles_z) {
+static unsigned pws_grid(const psb_scalar_stage_args* a, PwsSched* s) {
   using C = WsCfg<T, H, NF, BY, TZ, P, VEC, false>;
   const int tz = (int)((a->Nz + C::BZ - 1) / C::BZ), ty = (int)((a->Ny + BY - 1) / BY);
-  const int items = (int)((a->Nx + PWS_ITEM - 1) / PWS_ITEM);
-  *total_items = (unsigned)((int64_t)tz * ty * items);
-  *ipc = items;
-  *tiles_z = tz;
+  s->tiles_z = tz;
+  pws_make_schedule(*s, (int)a->Nx, (unsigned)(tz * ty));
   unsigned grid = (unsigned)(num_sms() * MINB);
-  if (grid > *total_items) grid = *total_items;
+  if (grid > s->nchunks) grid = s->nchunks;
   return grid;
 }
 
@@ -531,11 +521,8 @@ static inline bool pws_eligible(const psb_scalar_stage_args* a) {
 
 template <typename T, int H, int NF, int BY, int TZ, int P, int MINB, int VEC = 2>
 static int64_t pws_rows(const psb_scalar_stage_args* a) {
-  unsigned total;
-  int ipc, tz;
-  const unsigned grid = pws_grid<T, H, NF, BY, TZ, P, MINB, VEC>(a, &total, &ipc, &tz);
   PwsSched s;
-  pws_make_schedule(s, total, grid);
+  pws_grid<T, H, NF, BY, TZ, P, MINB, VEC>(a, &s);
   return s.nchunks;
 }
 
@@ -558,14 +545,9 @@ static int launch_pws(const psb_scalar_stage_args* a, cudaStream_t stream) {
   FusedParams<T, NF> p;
   fill_params<T, NF>(p, a);
   PwsSched s;
-  int ipc, tz;
-  unsigned total;
-  const unsigned grid = pws_grid<T, H, NF, BY, TZ, P, MINB, VEC>(a, &total, &ipc, &tz);
+  const unsigned grid = pws_grid<T, H, NF, BY, TZ, P, MINB, VEC>(a, &s);
   s.counter = reinterpret_cast<unsigned int*>(a->pws_sched);
   s.done = reinterpret_cast<unsigned int*>(a->pws_sched) + 2;
-  s.items_per_col = ipc;
-  s.tiles_z = tz;
-  pws_make_schedule(s, total, grid);
   p.pws_rows = (int)s.nchunks;
   dim3 block(C::THREADS, 1, 1);
   if (a->energy_partials != nullptr) {

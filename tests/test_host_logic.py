@@ -368,43 +368,44 @@ def test_pipeline_ring_protocol_is_deadlock_free():
 # exactly once, and the guided schedule partitions the items identically for every run.
 # ---------------------------------------------------------------------------------------
 
-def _pws_schedule(total, ncta, kmax=32, phases=6):
-    """csrc/fused_stage_pws.cuh::pws_make_schedule + pws_chunk, restated."""
-    item, chunk, table = 0, 0, []
+def _pws_schedule(Nx, ncol, lmax=128, phases=6):
+    """csrc/fused_stage_pws.cuh::pws_make_schedule + pws_chunk, restated: chunk number ->
+    (column, out_lo, out_hi)."""
+    x, chunk, table = 0, 0, []
     for j in range(phases):
-        k = kmax >> j
-        rem = total - item
-        n = rem if k == 1 else ((rem - ncta * k) // k if rem > ncta * k else 0)
-        table.append((chunk, item, k))
-        item += n * k
-        chunk += n
-    nchunks = chunk
+        ln = lmax >> j
+        rem = Nx - x
+        n = -(-rem // ln) if j == phases - 1 else ((rem - ln) // ln if rem > ln else 0)
+        table.append((chunk, x, ln))
+        x += rem if j == phases - 1 else n * ln
+        chunk += n * ncol
+    ends = [t[1] for t in table[1:]] + [Nx]
     out = []
-    for i in range(nchunks):
-        ph = max(j for j, (c0, _, _) in enumerate(table) if i >= c0 and
-                 (j == phases - 1 or table[j + 1][0] > i or table[j + 1][0] == c0))
-        # the device picks the LAST phase whose first chunk index is <= i
+    for i in range(chunk):
         ph = max(j for j, (c0, _, _) in enumerate(table) if i >= c0)
-        c0, i0, k = table[ph]
-        end = table[ph + 1][1] if ph + 1 < phases else total
-        start = i0 + (i - c0) * k
-        out.append((start, min(k, end - start)))
+        c0, x0, ln = table[ph]
+        local = i - c0
+        lo = x0 + (local // ncol) * ln
+        out.append((local % ncol, lo, min(lo + ln, ends[ph])))
     return out
 
 
 def test_pws_schedule_is_a_static_partition():
-    for total, ncta in ((8192, 296), (65536, 296), (37, 296), (1000, 7), (1, 1), (40000, 148)):
-        chunks = _pws_schedule(total, ncta)
-        assert chunks[0][0] == 0 and sum(k for _, k in chunks) == total
-        assert all(k >= 1 for _, k in chunks)
-        assert all(a + k == b for (a, k), (b, _) in zip(chunks, chunks[1:]))
-        # large chunks first, single items at the end; at least 2 * ncta single items
-        sizes = [k for _, k in chunks]
-        assert sizes == sorted(sizes, reverse=True) and sizes[-1] == 1
-        if total >= 64 * ncta:
-            assert sizes[0] == 32
-        if total >= 2 * ncta:
-            assert sizes.count(1) >= ncta
+    for Nx, ncol in ((64, 512), (512, 512), (128, 2048), (37, 12), (4, 3), (1, 1), (300, 7)):
+        chunks = _pws_schedule(Nx, ncol)
+        cover = np.zeros((ncol, Nx), int)
+        for col, lo, hi in chunks:
+            assert 0 <= lo < hi <= Nx
+            cover[col, lo:hi] += 1
+        assert (cover == 1).all()                     # every site plane exactly once
+        lens = [hi - lo for _, lo, hi in chunks]
+        assert max(lens) <= 128 and lens[-1] <= 4      # short chunks last
+        # neighbouring chunk numbers = neighbouring columns of the same x range
+        for (c0, lo0, hi0), (c1, lo1, hi1) in zip(chunks, chunks[1:]):
+            if c1 == c0 + 1:
+                assert (lo0, hi0) == (lo1, hi1)
+        if Nx >= 256:
+            assert lens[0] == 128
 
 
 def _simulate_pws(H, P, segments, ncw, rng):
