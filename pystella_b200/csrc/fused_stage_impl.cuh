@@ -48,6 +48,7 @@ template <typename T, int NF> struct FusedParams {
   int nmain, split_len;   // x-chunk schedule of range 1 (chunk_range())
   int pf_dist;            // L2 prefetch distance of the pipeline's producer (planes; 0 = off)
   int pws_rows;           // persistent kernel: chunks (= published rows) of the launch
+  int quadratic;          // one field, V = c f^2 (dV/df = c' f): loop-free evaluation
   int wrap_x, wrap_y, wrap_z;
   T* peer_lo;   // peer-mapped f_out of rank rx-1 / rx+1 (or null)
   T* peer_hi;
@@ -613,6 +614,12 @@ static void fill_params(FusedParams<T, NF>& p, const psb_scalar_stage_args* a) {
     p.vcoef[t] = (T)a->vcoef[t];
     for (int m = 0; m < NF; ++m) p.vpower[t][m] = a->vpower[t][m];
   }
+  // the most common potential (m^2 f^2 / 2, one field) is evaluated without the run-time
+  // loops over terms and powers; same association as poly_eval, hence the same bits
+  p.quadratic = (NF == 1 && a->nterms[0] == 1 && a->power[0][0][0] == 1 &&
+                 (a->nvterms == 0 || (a->nvterms == 1 && a->vpower[0][0] == 2)))
+                    ? 1
+                    : 0;
   p.pf_dist = a->tune_prefetch == 0 ? PSB_DEFAULT_PREFETCH
                                     : (a->tune_prefetch < 0 ? 0 : a->tune_prefetch);
   fill_tail(p.tail, a->tail,

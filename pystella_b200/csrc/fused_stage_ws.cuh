@@ -481,7 +481,14 @@ __global__ void __launch_bounds__(BY* TZ + 32, MINB)
             sp = sp + psb_generated_potential<T>(fsite, a, hubble, jit_scalars.v);
           }
 #else
-          const V Vv = poly_eval<T, NF, VEC>(p.nvterms, p.vcoef, p.vpower, fc);
+          V Vv;
+          if (NF == 1 && p.quadratic) {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v)
+              Vv.v[v] = p.nvterms ? (T)0 + (p.vcoef[0] * fc[0].v[v]) * fc[0].v[v] : (T)0;
+          } else {
+            Vv = poly_eval<T, NF, VEC>(p.nvterms, p.vcoef, p.vpower, fc);
+          }
 #pragma unroll
           for (int v = 0; v < VEC; ++v) {
             if constexpr (AL || SPLIT) {
@@ -497,7 +504,13 @@ __global__ void __launch_bounds__(BY* TZ + 32, MINB)
         for (int f = 0; f < NF; ++f) {
           V fo, dn, kfn, kdn;
 #ifndef PSB_GENERATED_RHS
-          const V dVv = poly_eval<T, NF, VEC>(p.nterms[f], p.coef[f], p.power[f], fc);
+          V dVv;
+          if (NF == 1 && p.quadratic) {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) dVv.v[v] = (T)0 + p.coef[0][0] * fc[0].v[v];
+          } else {
+            dVv = poly_eval<T, NF, VEC>(p.nterms[f], p.coef[f], p.power[f], fc);
+          }
 #endif
 #pragma unroll
           for (int v = 0; v < VEC; ++v) {
