@@ -110,6 +110,34 @@ if __name__ == "__main__":
             scalar_case(N5, F64, 0, True, tune={"variant": var})
             scalar_case((128, 1024, 1024), F32, 1, True, tune={"variant": var})
             scalar_case(N5, F32, 1, True, nscalars=2, tune={"variant": var})
+    if "jit2" in which:
+        # two-field scalar stage (config 4's): polynomial tables vs the generated functor
+        from pystella_b200.fused_jit import recognise_general_system
+        h = 2
+        for dtype in (F32, F64):
+            N = 512 if dtype == F32 else 320
+            dx = (5 / N,) * 3
+            pad = (2,) + (N + 2 * h,) * 3
+            pot = lambda g: g[0]**2 / 2 + 86805.5 * g[0]**2 * g[1]**2  # noqa: E731
+            for forced in (False, True):
+                sector = ps.ScalarSector(2, potential=pot)
+                st = ps.LowStorageRK54(sector, halo_shape=h, dt=1e-3, dx=dx,
+                                       MapKernel=ps.FusedStencilStage, energy=True)
+                if forced:
+                    st._systems = [recognise_general_system(sector.rhs_dict,
+                                                            sector.potential(sector.f))]
+                f = torch.rand(pad, dtype=dtype, device="cuda") * 1e-2
+                d = torch.rand_like(f)
+                ex = ps.DeviceExpansion(1.0, ps.LowStorageRK54, grid_size=float(N**3), nscalars=2)
+                ex.attach(st)
+                S = torch.finfo(dtype).bits // 8
+                for stage in (1, 0):
+                    def go():
+                        st(stage, f=f, dfdt=d, a=ex.a, hubble=ex.hubble)
+                        ex.step(stage, st, 1e-3)
+                    timeit(go, f"2 fields {N}^3 {str(dtype)[6:]} stage={stage} "
+                               f"{'generated functor' if forced else 'polynomial tables'}",
+                           (6 if stage == 0 else 8) * S * 2 * float(N**3))
     if "gwprof" in which:
         gw_case(384, F32)
     if "f32prof" in which:
