@@ -451,8 +451,10 @@ class Stepper:
                     # 1.815 -> 1.474 ms per stage, 0.73 -> 0.90 of the roofline), so fused
                     # steppers prefer it whenever run-time compilation is available.
                     # tune={"tables": True} keeps the table-driven kernel.
+                    tune = self.tune or {}
                     if (self.fused and jit_enabled(self.jit) and not _is_quadratic(system)
-                            and not (self.tune or {}).get("tables", False)):
+                            and not tune.get("tables", False)
+                            and tune.get("variant", 0) == 0):   # explicit variants: tables
                         try:
                             system = general(s.rhs_dict, s.potential(s.f), None)
                         except NotImplementedError:
