@@ -5,7 +5,7 @@ out=gpurun_out/r2n8
 mkdir -p "$out"
 export PYTHONUNBUFFERED=1
 nvidia-smi -L | wc -l
-for c in c3 c4 c5; do
+for c in c3 c4; do
   timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29512 \
      bench.py --gpus 8 --config $c --steps 20 --warmup 3 --no-e2e > "$out/bench_${c}_n8.json" 2> "$out/bench_${c}_n8.err"
   echo "bench $c N=8 exit $?"
