@@ -67,6 +67,8 @@ def parse():
     p.add_argument("--no-parity", action="store_true")
     p.add_argument("--xchunk", type=int, default=0)
     p.add_argument("--variant", type=int, default=0)
+    p.add_argument("--pdl", type=int, default=-1, choices=[-1, 0, 1],
+                   help="programmatic dependent launch of the stage kernels (-1: library default)")
     return p.parse_args()
 
 
@@ -470,7 +472,9 @@ def run_b200_arm(args):
     ns = w["nscalars"]
 
     decomp = ps.DomainDecomposition((world, 1, 1), h, rank_shape=w["rank_shape"])
-    tune = {"xchunk": args.xchunk, "variant": args.variant,}
+    tune = {"xchunk": args.xchunk, "variant": args.variant}
+    if args.pdl >= 0:
+        tune["pdl"] = bool(args.pdl)
     job = Job(ps, torch, cfg, w, decomp, dev, tune, global_sites)
 
     def barrier():

@@ -74,6 +74,15 @@ typedef struct psb_peer_args {
  *                    (a, adot) as psb_expansion_stage.
  * Without PSB_TAIL_FOLD, sums must have been folded by an earlier kernel of the stage.
  * ---------------------------------------------------------------------- */
+/* Launch flags of the fused stage kernels and of psb_expansion_stage_peer_v.
+ * PSB_LAUNCH_PDL: programmatic dependent launch -- the kernel may be scheduled while the
+ * previous kernel of the stream drains (its CTAs set up their barriers and descriptors, then
+ * wait in `griddepcontrol.wait` until the previous kernel has completed and its stores are
+ * visible).  Every kernel of this library that can precede such a launch executes
+ * `griddepcontrol.launch_dependents` and `griddepcontrol.wait` itself, so chains of stage
+ * kernels stay transitively ordered.  Capturable in CUDA graphs (programmatic edges). */
+#define PSB_LAUNCH_PDL 1
+
 #define PSB_TAIL_FOLD 1
 #define PSB_TAIL_EXPAND 2
 #define PSB_TAIL_PEER 4
@@ -174,7 +183,7 @@ typedef struct psb_scalar_stage_args {
   const psb_stage_tail* tail;    /* fused only; HOST pointer, NULL = no in-kernel tail */
   int32_t tune_prefetch;         /* fused: planes the producer prefetches into L2 ahead of
                                     its loads; 0 = default, < 0 = none                  */
-  int32_t reserved0;
+  int32_t launch_flags;          /* OR of PSB_LAUNCH_*                                  */
   void* pws_sched;               /* fused, optional: 16 zeroed bytes of device memory (work
                                     scheduler of the persistent kernel variant, re-armed
                                     by the kernel); NULL = one-chunk-per-CTA kernels only */
@@ -270,7 +279,7 @@ typedef struct psb_tensor_fused_args {
   int32_t tune_xchunk;           /* 0 = default                                       */
   int32_t tune_variant;          /* 0 = auto; 1 = 8-byte vectors for fp32             */
   int32_t tune_prefetch;         /* L2 prefetch distance in planes; 0 = default, < 0 none */
-  int32_t reserved0;
+  int32_t launch_flags;          /* OR of PSB_LAUNCH_*                                  */
 } psb_tensor_fused_args;
 int psb_tensor_stage_fused(const psb_tensor_fused_args* args, void* stream);
 /* CTAs of that launch (= marker rows its stage tail needs); -1 on error. */
@@ -416,6 +425,11 @@ int psb_expansion_stage(const double* sums, int nscalars, double grid_size, doub
 int psb_expansion_stage_peer(const psb_peer_args* peers, const double* sums, int nscalars,
                              double grid_size, double mpl, double dt, double A, double B,
                              double* state, double* energies, void* stream);
+/* Same, with launch flags (PSB_LAUNCH_PDL). */
+int psb_expansion_stage_peer_v(const psb_peer_args* peers, const double* sums, int nscalars,
+                               double grid_size, double mpl, double dt, double A, double B,
+                               double* state, double* energies, int launch_flags,
+                               void* stream);
 
 /* adot = sqrt(8 pi a^2 rho / (3 mpl^2)) a from energies (first Friedmann equation,
  * pystella/expansion.py:101-117): initialises state = {a, adot, hubble, 0, 0}. */

@@ -68,6 +68,10 @@ int psb_jit_write_cubin(int64_t handle, const char* path);
 int psb_jit_launch_params(int64_t handle, void** params, unsigned gx, unsigned gy,
                           unsigned gz, unsigned bx, unsigned by, unsigned bz,
                           unsigned smem_bytes, void* stream);
+/* Same, with launch flags (PSB_LAUNCH_PDL of pystella_b200.h). */
+int psb_jit_launch_params_v(int64_t handle, void** params, unsigned gx, unsigned gy,
+                            unsigned gz, unsigned bx, unsigned by, unsigned bz,
+                            unsigned smem_bytes, int launch_flags, void* stream);
 
 #ifdef __cplusplus
 }

@@ -40,7 +40,7 @@ def scalar_stage(*, fused, f_in, f_out, dfdt, kf, kdfdt, lap_f=None, h, dx=(1., 
                  queue=None, strict=False, xchunk=0, variant=0,
                  energy_partials=None, energy_slot_offset=0, V_terms=None,
                  count_slots_only=False, peer=None, generated=None, tail=None,
-                 prefetch=0, pws_sched=None):
+                 prefetch=0, pws_sched=None, launch_flags=0):
     """
     One scalar-sector LSRK stage on padded arrays of shape ``(n, Nx+2h, Ny+2h, Nz+2h)``
     (or without the leading axis for a single field).
@@ -104,6 +104,7 @@ def scalar_stage(*, fused, f_in, f_out, dfdt, kf, kdfdt, lap_f=None, h, dx=(1., 
     args.tune_xchunk = xchunk
     args.tune_variant = variant
     args.tune_prefetch = int(prefetch)
+    args.launch_flags = int(launch_flags)
     if pws_sched is not None:
         args.pws_sched = _ptr(pws_sched)
     if tail is not None:
@@ -302,12 +303,12 @@ def expansion_init(sums, nscalars, grid_size, mpl, a0, state, energies, queue=No
 
 
 def expansion_stage_peer(peer_args, sums, nscalars, grid_size, mpl, dt, A, B, state,
-                         energies, queue=None, strict=False):
+                         energies, queue=None, strict=False, launch_flags=0):
     """All-gather of the sums over peer memory + barrier + expansion stage (one kernel);
     ``nscalars == 0``: barrier only."""
     lib = _lib.load(strict)
-    rc = lib.psb_expansion_stage_peer(C.byref(peer_args), _ptr(sums), nscalars,
-                                      float(grid_size), float(mpl), float(dt), float(A),
-                                      float(B), _ptr(state), _ptr(energies),
-                                      _lib.stream_ptr(queue))
-    _lib.check(lib, rc, "psb_expansion_stage_peer")
+    rc = lib.psb_expansion_stage_peer_v(C.byref(peer_args), _ptr(sums), nscalars,
+                                        float(grid_size), float(mpl), float(dt), float(A),
+                                        float(B), _ptr(state), _ptr(energies),
+                                        int(launch_flags), _lib.stream_ptr(queue))
+    _lib.check(lib, rc, "psb_expansion_stage_peer_v")

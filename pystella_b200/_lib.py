@@ -30,6 +30,7 @@ class PeerArgs(C.Structure):
 
 
 TAIL_FOLD, TAIL_EXPAND, TAIL_PEER = 1, 2, 4
+LAUNCH_PDL = 1          # PSB_LAUNCH_PDL
 #: bit pattern (a NaN payload) of a not-yet-published value in a stage-tail row
 TAIL_SENTINEL = 0x7ff8dead0000beef
 
@@ -70,7 +71,7 @@ class ScalarStageArgs(C.Structure):
         ("vpower", (C.c_int8 * MAX_SCALARS) * MAX_TERMS),
         ("tune_xchunk", c_int32), ("tune_variant", c_int32),
         ("tail", C.POINTER(StageTail)),
-        ("tune_prefetch", c_int32), ("reserved0", c_int32),
+        ("tune_prefetch", c_int32), ("launch_flags", c_int32),
         ("pws_sched", c_void_p),
     ]
 
@@ -114,7 +115,7 @@ class TensorFusedArgs(C.Structure):
                 ("peer_hi_stride", c_int64),
                 ("tail", C.POINTER(StageTail)),
                 ("tune_xchunk", c_int32), ("tune_variant", c_int32),
-                ("tune_prefetch", c_int32), ("reserved0", c_int32)]
+                ("tune_prefetch", c_int32), ("launch_flags", c_int32)]
 
 
 class ReduceArgs(C.Structure):
@@ -187,6 +188,9 @@ SYMBOLS = {
     "psb_expansion_stage_peer": (c_int, [C.POINTER(PeerArgs), c_void_p, c_int, c_double,
                                          c_double, c_double, c_double, c_double, c_void_p,
                                          c_void_p, c_void_p]),
+    "psb_expansion_stage_peer_v": (c_int, [C.POINTER(PeerArgs), c_void_p, c_int, c_double,
+                                           c_double, c_double, c_double, c_double,
+                                           c_void_p, c_void_p, c_int, c_void_p]),
     "psb_expansion_init": (c_int, [c_void_p, c_int, c_double, c_double, c_double,
                                    c_void_p, c_void_p, c_void_p]),
 }

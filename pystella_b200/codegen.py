@@ -353,6 +353,9 @@ class JitLibrary:
             lib.psb_jit_launch_params.restype = C.c_int
             lib.psb_jit_launch_params.argtypes = [C.c_int64, C.POINTER(C.c_void_p)] \
                 + [C.c_uint] * 7 + [C.c_void_p]
+            lib.psb_jit_launch_params_v.restype = C.c_int
+            lib.psb_jit_launch_params_v.argtypes = [C.c_int64, C.POINTER(C.c_void_p)] \
+                + [C.c_uint] * 7 + [C.c_int, C.c_void_p]
             cls._lib = lib
         return cls._lib
 

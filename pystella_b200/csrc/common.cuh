@@ -48,6 +48,24 @@ void set_error(const char* fmt, ...);
   } while (0)
 
 #ifndef __CUDACC_RTC__
+// One launch path for the stage kernels: plain stream order, or (launch_flags &
+// PSB_LAUNCH_PDL) with the programmatic-stream-serialization attribute.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                 cudaStream_t stream, int launch_flags, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (launch_flags & PSB_LAUNCH_PDL) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 inline int num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -161,6 +179,17 @@ __device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* map, int c0, 
                    reinterpret_cast<uint64_t>(map)),
                "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                : "memory");
+}
+
+// Programmatic dependent launch (PSB_LAUNCH_PDL): `pdl_launch_dependents` lets the next
+// kernel of the stream be scheduled once every CTA of this grid has executed it (i.e. once
+// the whole grid has been dispatched); `pdl_wait` blocks until the previous kernel has
+// completed and flushed.  Both are no-ops for launches without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {

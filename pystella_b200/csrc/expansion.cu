@@ -114,6 +114,10 @@ __global__ void __launch_bounds__(64)
                                 double grid_size, double mpl, double dt, double A, double B,
                                 double* state, double* energies) {
   __shared__ double total[PSB_ENERGY_STRIDE];
+  // PSB_LAUNCH_PDL: scheduled while the stage kernel drains; nothing is read or signalled
+  // before that kernel has completed (its peer stores are what the flag below publishes)
+  pdl_launch_dependents();
+  pdl_wait();
   const int P = peers.nranks, me = peers.rank;
   const unsigned long long epoch = *peers.epoch + 1ull;
   const int par = (int)(epoch & 1ull);
@@ -239,25 +243,35 @@ extern "C" int psb_expansion_init(const double* sums, int nscalars, double grid_
   return 0;
 }
 
+extern "C" int psb_expansion_stage_peer_v(const psb_peer_args* peers, const double* sums,
+                                          int nscalars, double grid_size, double mpl,
+                                          double dt, double A, double B, double* state,
+                                          double* energies, int launch_flags,
+                                          void* stream) {
+  using namespace psb;
+  PSB_REQUIRE(peers != nullptr, "psb_expansion_stage_peer_v: null peers");
+  PSB_REQUIRE(peers->nranks >= 1 && peers->nranks <= 64 && peers->rank >= 0 &&
+                  peers->rank < peers->nranks,
+              "psb_expansion_stage_peer_v: bad rank/nranks");
+  PSB_REQUIRE(peers->peer_slots && peers->peer_flags && peers->epoch,
+              "psb_expansion_stage_peer_v: null peer tables");
+  PSB_REQUIRE(nscalars >= 0 && nscalars <= PSB_MAX_SCALARS,
+              "psb_expansion_stage_peer_v: nscalars=%d out of range", nscalars);
+  if (nscalars > 0) {
+    PSB_REQUIRE(sums && state && energies, "psb_expansion_stage_peer_v: null pointer");
+    PSB_REQUIRE(grid_size > 0 && mpl > 0, "psb_expansion_stage_peer_v: bad grid_size/mpl");
+  }
+  PSB_CHECK_CUDA(launch_kernel(expansion_stage_peer_kernel, dim3(1), dim3(64), 0,
+                               static_cast<cudaStream_t>(stream), launch_flags, *peers, sums,
+                               nscalars, grid_size, mpl, dt, A, B, state, energies));
+  PSB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int psb_expansion_stage_peer(const psb_peer_args* peers, const double* sums,
                                         int nscalars, double grid_size, double mpl,
                                         double dt, double A, double B, double* state,
                                         double* energies, void* stream) {
-  using namespace psb;
-  PSB_REQUIRE(peers != nullptr, "psb_expansion_stage_peer: null peers");
-  PSB_REQUIRE(peers->nranks >= 1 && peers->nranks <= 64 && peers->rank >= 0 &&
-                  peers->rank < peers->nranks,
-              "psb_expansion_stage_peer: bad rank/nranks");
-  PSB_REQUIRE(peers->peer_slots && peers->peer_flags && peers->epoch,
-              "psb_expansion_stage_peer: null peer tables");
-  PSB_REQUIRE(nscalars >= 0 && nscalars <= PSB_MAX_SCALARS,
-              "psb_expansion_stage_peer: nscalars=%d out of range", nscalars);
-  if (nscalars > 0) {
-    PSB_REQUIRE(sums && state && energies, "psb_expansion_stage_peer: null pointer");
-    PSB_REQUIRE(grid_size > 0 && mpl > 0, "psb_expansion_stage_peer: bad grid_size/mpl");
-  }
-  expansion_stage_peer_kernel<<<1, 64, 0, static_cast<cudaStream_t>(stream)>>>(
-      *peers, sums, nscalars, grid_size, mpl, dt, A, B, state, energies);
-  PSB_CHECK_CUDA(cudaGetLastError());
-  return 0;
+  return psb_expansion_stage_peer_v(peers, sums, nscalars, grid_size, mpl, dt, A, B, state,
+                                    energies, 0, stream);
 }

@@ -225,6 +225,10 @@ __global__ void __launch_bounds__(BY* TZ + 32, MINB)
     fence_barrier_init();
   }
   __syncthreads();
+  // PSB_LAUNCH_PDL: everything above overlaps the previous kernel's tail; nothing below may
+  // run before that kernel has completed (inputs, ping-pong buffers, marker rows).
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (tid >= BY * TZ) {
     // ======================= producer warp (one elected lane) ===================
@@ -756,12 +760,14 @@ static int launch_ws(const psb_scalar_stage_args* a, cudaStream_t stream) {
     auto kern = fused_stage_ws_kernel<T, H, NF, BY, TZ, P, true, MINB, VEC, AL>;
     PSB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         C::SMEM_BYTES));
-    kern<<<grid, block, C::SMEM_BYTES, stream>>>(p, mf, md, mkf, mkd);
+    PSB_CHECK_CUDA(launch_kernel(kern, grid, block, C::SMEM_BYTES, stream, a->launch_flags, p,
+                                 mf, md, mkf, mkd));
   } else {
     auto kern = fused_stage_ws_kernel<T, H, NF, BY, TZ, P, false, MINB, VEC, AL>;
     PSB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         C::SMEM_BYTES));
-    kern<<<grid, block, C::SMEM_BYTES, stream>>>(p, mf, md, mkf, mkd);
+    PSB_CHECK_CUDA(launch_kernel(kern, grid, block, C::SMEM_BYTES, stream, a->launch_flags, p,
+                                 mf, md, mkf, mkd));
   }
   PSB_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -9,6 +9,7 @@
 #include <string>
 #include <vector>
 
+#include "pystella_b200.h"
 #include "pystella_b200_jit.h"
 
 namespace {
@@ -42,6 +43,7 @@ typedef CUresult (*ModuleUnload)(CUmodule);
 typedef CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned,
                                  unsigned, unsigned, CUstream, void**, void**);
 typedef CUresult (*FuncSetAttribute)(CUfunction, CUfunction_attribute, int);
+typedef CUresult (*LaunchKernelEx)(const CUlaunchConfig*, CUfunction, void**, void**);
 
 // loads the module of entry `e` on first use; g_mutex must be held
 int ensure_loaded(Entry* e) {
@@ -216,6 +218,13 @@ extern "C" int psb_jit_write_cubin(int64_t handle, const char* path) {
 extern "C" int psb_jit_launch_params(int64_t handle, void** params, unsigned gx, unsigned gy,
                                      unsigned gz, unsigned bx, unsigned by, unsigned bz,
                                      unsigned smem_bytes, void* stream) {
+  return psb_jit_launch_params_v(handle, params, gx, gy, gz, bx, by, bz, smem_bytes, 0, stream);
+}
+
+extern "C" int psb_jit_launch_params_v(int64_t handle, void** params, unsigned gx,
+                                       unsigned gy, unsigned gz, unsigned bx, unsigned by,
+                                       unsigned bz, unsigned smem_bytes, int launch_flags,
+                                       void* stream) {
   g_log.clear();
   if (!params) {
     g_log = "psb_jit_launch_params: null parameter list";
@@ -240,6 +249,31 @@ extern "C" int psb_jit_launch_params(int64_t handle, void** params, unsigned gx,
       }
       e->smem_opted = smem_bytes;
     }
+  }
+  if (launch_flags & PSB_LAUNCH_PDL) {
+    // programmatic dependent launch (the generated instance of the fused pipeline executes
+    // griddepcontrol.wait like the precompiled one)
+    static LaunchKernelEx launch_ex = driver<LaunchKernelEx>("cuLaunchKernelEx");
+    if (!launch_ex) {
+      g_log = "psb_jit_launch_params_v: cuLaunchKernelEx unavailable";
+      return 2;
+    }
+    CUlaunchConfig cfg = {};
+    cfg.gridDimX = gx, cfg.gridDimY = gy, cfg.gridDimZ = gz;
+    cfg.blockDimX = bx, cfg.blockDimY = by, cfg.blockDimZ = bz;
+    cfg.sharedMemBytes = smem_bytes;
+    cfg.hStream = static_cast<CUstream>(stream);
+    CUlaunchAttribute attr[1];
+    attr[0].id = CU_LAUNCH_ATTRIBUTE_PROGRAMMATIC_STREAM_SERIALIZATION;
+    attr[0].value.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CUresult r = launch_ex(&cfg, e->fn, params, nullptr);
+    if (r != CUDA_SUCCESS) {
+      g_log = "cuLaunchKernelEx failed (" + std::to_string((int)r) + ")";
+      return 2;
+    }
+    return 0;
   }
   static LaunchKernel launch = driver<LaunchKernel>("cuLaunchKernel");
   if (!launch) {

@@ -111,6 +111,8 @@ __device__ __forceinline__ void tensor_stage_body(const TensorFusedParams<T>& p,
     fence_barrier_init();
   }
   __syncthreads();
+  pdl_launch_dependents();   // PSB_LAUNCH_PDL, see fused_stage_ws.cuh
+  pdl_wait();
 
   if (tid >= BY * TZ) {
     if (tid == BY * TZ) {
@@ -603,7 +605,8 @@ static int launch_tensor_ws(const psb_tensor_fused_args* a, cudaStream_t stream,
   auto kern = tensor_stage_ws_kernel<T, H, NS, BY, TZ, P, MINB, VEC, SMEMX>;
   PSB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       C::SMEM_BYTES));
-  kern<<<grid, block, C::SMEM_BYTES, stream>>>(p, mh, ms, md, mkh, mkd);
+  PSB_CHECK_CUDA(launch_kernel(kern, grid, block, C::SMEM_BYTES, stream, a->launch_flags, p, mh,
+                               ms, md, mkh, mkd));
   PSB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

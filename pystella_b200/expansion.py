@@ -158,7 +158,8 @@ class DeviceExpansion:
             # all-gather over peer memory + inter-GPU barrier + expansion, one kernel
             _kernels.expansion_stage_peer(pg.args, sums, self.nscalars, self.grid_size,
                                           self.mpl, dt, self._A[stage], self._B[stage],
-                                          self.state, self.energies, queue, self.strict_fp)
+                                          self.state, self.energies, queue, self.strict_fp,
+                                          getattr(stepper, "launch_flags", 0))
             stepper._peer_barrier_pending = False
             return
         if self.decomp is not None and self.decomp.nranks > 1:

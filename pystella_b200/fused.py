@@ -246,7 +246,7 @@ def fused_scalar_stage(stepper, system, f, common, queue):
     if not halos_are_fresh(stepper, key, f):
         # halos of the user's array are of unknown age: fill them
         if mode == "peer" and stepper._peer_barrier_pending:
-            stepper._peer.barrier_kernel(queue, stepper.strict_fp)
+            stepper._peer.barrier_kernel(queue, stepper.strict_fp, stepper.launch_flags)
             stepper._peer_barrier_pending = False
         fill_halos(stepper, f, h, queue)
 
@@ -255,7 +255,7 @@ def fused_scalar_stage(stepper, system, f, common, queue):
     args.update(fused=True, f_in=f, f_out=twin, dx=stepper.dx)
     tune = stepper.tune or {}
     args.update(xchunk=tune.get("xchunk", 0), variant=tune.get("variant", 0),
-                prefetch=tune.get("prefetch", 0))
+                prefetch=tune.get("prefetch", 0), launch_flags=stepper.launch_flags)
     if stepper.__dict__.get("_pws_sched") is None:
         # scheduler words of the persistent kernel variant (zero between launches)
         stepper._pws_sched = torch.zeros(2, dtype=torch.int64, device=f.device)
@@ -302,7 +302,7 @@ def fused_scalar_stage(stepper, system, f, common, queue):
         ps = stepper._peer_state[key]
         if stepper._peer_barrier_pending:
             # the previous stage's last kernel did not carry the barrier
-            stepper._peer.barrier_kernel(queue, stepper.strict_fp)
+            stepper._peer.barrier_kernel(queue, stepper.strict_fp, stepper.launch_flags)
             stepper._peer_barrier_pending = False
         out_id = ps["ids"][twin.data_ptr()]
         peer = dict(lo=ps["ptrs"][out_id][ps["lo"]], hi=ps["ptrs"][out_id][ps["hi"]],

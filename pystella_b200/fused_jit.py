@@ -249,9 +249,9 @@ class GeneratedFusedStage:
               for m in range(4)],
             C.addressof(js))
         jit = JitLibrary.get()
-        rc = jit.psb_jit_launch_params(handle, params, plan.grid[0], plan.grid[1],
-                                       plan.grid[2], plan.threads, 1, 1, plan.smem_bytes,
-                                       _lib.stream_ptr(queue))
+        rc = jit.psb_jit_launch_params_v(handle, params, plan.grid[0], plan.grid[1],
+                                         plan.grid[2], plan.threads, 1, 1, plan.smem_bytes,
+                                         int(args.launch_flags), _lib.stream_ptr(queue))
         if rc != 0:
             raise _lib.PsbError("launch of the generated fused stage failed: "
                                 + jit.psb_jit_last_log().decode(errors="replace"))

@@ -82,7 +82,7 @@ class TensorSystem:
             stepper.__dict__.setdefault("_fresh", {}).pop(key, None)
         if not fused.halos_are_fresh(stepper, key, hij):
             if multi and stepper._peer_barrier_pending:
-                stepper._peer.barrier_kernel(queue, stepper.strict_fp)
+                stepper._peer.barrier_kernel(queue, stepper.strict_fp, stepper.launch_flags)
                 stepper._peer_barrier_pending = False
             fused.fill_halos(stepper, hij, h, queue)
         Nx, Ny, Nz = (n - 2 * h for n in hij.shape[-3:])
@@ -103,6 +103,7 @@ class TensorSystem:
         args.tune_xchunk = tune.get("gw_xchunk", 0)
         args.tune_variant = tune.get("gw_variant", 0)
         args.tune_prefetch = tune.get("gw_prefetch", tune.get("prefetch", 0))
+        args.launch_flags = stepper.launch_flags
         hub = kwargs["hubble"]
         if isinstance(hub, torch.Tensor):
             args.hubble_dev = hub.data_ptr()

@@ -90,8 +90,8 @@ class PeerGroup:
         dist.all_gather_object(out, tuple(int(x) for x in shape), group=self.decomp.comm)
         return out
 
-    def barrier_kernel(self, queue=None, strict=False):
+    def barrier_kernel(self, queue=None, strict=False, launch_flags=0):
         """Inter-GPU barrier as a kernel on ``queue`` (orders peer stores)."""
         from pystella_b200 import _kernels
         _kernels.expansion_stage_peer(self.args, self._dummy, 0, 1.0, 1.0, 0.0, 0.0, 0.0,
-                                      self._dummy, self._dummy, queue, strict)
+                                      self._dummy, self._dummy, queue, strict, launch_flags)

@@ -22,7 +22,7 @@ evaluated on the host.
 import numpy as np
 import torch
 
-from pystella_b200 import _kernels
+from pystella_b200 import _kernels, _lib
 from pystella_b200._lib import PsbError
 from pystella_b200.field import (DynamicField, Field, Subscript, Variable, evaluate,
                                  is_constant, to_polynomial)
@@ -48,6 +48,10 @@ def jit_enabled(flag=None):
     if flag is not None:
         return bool(flag)
     return os.environ.get("PSB_JIT", "1") != "0"
+
+
+#: programmatic dependent launch of the fused stage kernels; per stepper: ``tune={"pdl": bool}``
+DEFAULT_PDL = False
 
 
 class ElementWiseMap:
@@ -410,6 +414,10 @@ class Stepper:
         self.energy_partials = None
         self.energy_nslots = 0
         self.tune = kwargs.pop("tune", None)
+        #: PSB_LAUNCH_* flags of the fused stage kernels and the peer exchange kernel:
+        #: ``tune={"pdl": bool}`` -- programmatic dependent launch, the next kernel's CTAs
+        #: set up while the previous kernel drains (include/pystella_b200.h)
+        self.launch_flags = _lib.LAUNCH_PDL if (self.tune or {}).get("pdl", DEFAULT_PDL) else 0
         self._ignored_kwargs = kwargs  # target=, lsize=, args=, options= ...
 
         if self.fused and self.dx is None:

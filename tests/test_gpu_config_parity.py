@@ -129,3 +129,53 @@ def test_persistent_variant_parity(dtype, tol, nscalars):
         scale = np.max(np.abs(a0)) or 1.0
         assert np.max(np.abs(a30 - a0)) / scale < (1e-13 if dtype == "f64" else 1e-6), name
     assert np.isclose(results[30][1]["a"], results[0][1]["a"], rtol=1e-13)
+
+
+@pytest.mark.parametrize("system,dtype", [("scalar1", "f64"), ("scalar1", "f32"),
+                                          ("scalar2gw", "f32"), ("scalar2gw", "f64")])
+def test_programmatic_dependent_launch_is_bit_identical(system, dtype):
+    """``tune={"pdl": True}`` (PSB_LAUNCH_PDL, include/pystella_b200.h): the stage kernels are
+    scheduled while the previous kernel drains and block in ``griddepcontrol.wait`` before they
+    touch memory.  Same kernels, same order of every sum -> the fields and the background
+    must be BIT-identical to plain stream order, for launches issued back to back (no host
+    synchronisation in the loop) and for the CUDA-graph replay bench.py times; the plain
+    result is the one the oracle tests above pin."""
+    cfg = dict(bench.CONFIGS["c3"], name="c3", dtype=dtype, grid=(96, 64, 128))
+    if system == "scalar2gw":
+        cfg["system"] = "scalar2gw"     # generated two-field stage + tensor kernel
+        cfg["amp"] = 1e-2
+    w = bench.workload(cfg, 1, 0)
+    decomp = ps.DomainDecomposition((1, 1, 1), w["h"], rank_shape=w["rank_shape"])
+    dev = torch.device("cuda", 0)
+
+    def run(pdl, graph):
+        job = bench.Job(ps, torch, cfg, w, decomp, dev, {"xchunk": 0, "variant": 0,
+                        "pdl": pdl}, float(np.prod(w["grid_shape"])))
+        stepper = job.make_stepper()
+        assert stepper.launch_flags == (1 if pdl else 0)
+        arrays = job.upload()
+        expand = job.make_expansion()
+        expand.attach(stepper)
+
+        def one_step():
+            for s in range(5):
+                stepper(s, a=expand.a, hubble=expand.hubble, **arrays)
+                expand.step(s, stepper, w["dt"])
+        if graph:
+            g = ps.capture_steps(one_step, steps_per_replay=2, warmup=1, stepper=stepper)
+            g.replay()
+            g.replay()
+        else:
+            for _ in range(6):
+                one_step()
+        torch.cuda.synchronize()
+        return ({k: v.cpu().numpy().copy() for k, v in arrays.items()},
+                expand.state.cpu().numpy().copy())
+
+    for graph in (False, True):
+        ref_arrays, ref_state = run(False, graph)
+        got_arrays, got_state = run(True, graph)
+        for name in ref_arrays:
+            assert np.isfinite(ref_arrays[name]).all(), name
+            assert np.array_equal(got_arrays[name], ref_arrays[name]), (name, graph)
+        assert np.array_equal(got_state, ref_state), graph
