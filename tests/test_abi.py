@@ -57,6 +57,9 @@ def test_struct_layout_matches_header():
            'printf("%zu %zu %zu\\n", sizeof(psb_stage_tail), '
            '__builtin_offsetof(psb_scalar_stage_args, tail), '
            '__builtin_offsetof(psb_tensor_fused_args, tail));'
+           'printf("%zu %zu %zu %d\\n", __builtin_offsetof(psb_scalar_stage_args, launch_flags), '
+           '__builtin_offsetof(psb_tensor_fused_args, launch_flags), '
+           '__builtin_offsetof(psb_scalar_stage_args, pws_sched), PSB_LAUNCH_PDL);'
            'return 0;}')
     with tempfile.TemporaryDirectory() as d:
         c = os.path.join(d, "p.c")
@@ -64,7 +67,7 @@ def test_struct_layout_matches_header():
         exe = os.path.join(d, "p")
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
         (a, b, c, d, e, f, g, off_maps, off_params, tail_size, off_tail,
-         off_ttail) = subprocess.check_output([exe]).split()
+         off_ttail, off_lf, off_tlf, off_sched, pdl) = subprocess.check_output([exe]).split()
     assert int(a) == ctypes.sizeof(_lib.ScalarStageArgs)
     assert int(b) == ctypes.sizeof(_lib.ReduceArgs)
     assert int(c) == ctypes.sizeof(_lib.TensorStageArgs)
@@ -77,6 +80,10 @@ def test_struct_layout_matches_header():
     assert int(tail_size) == ctypes.sizeof(_lib.StageTail)
     assert int(off_tail) == _lib.ScalarStageArgs.tail.offset
     assert int(off_ttail) == _lib.TensorFusedArgs.tail.offset
+    assert int(off_lf) == _lib.ScalarStageArgs.launch_flags.offset
+    assert int(off_tlf) == _lib.TensorFusedArgs.launch_flags.offset
+    assert int(off_sched) == _lib.ScalarStageArgs.pws_sched.offset
+    assert int(pdl) == _lib.LAUNCH_PDL
 
 
 def test_no_cpu_fallback():
