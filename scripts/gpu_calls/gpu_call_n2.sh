@@ -1,5 +1,5 @@
 #!/bin/bash
-# gpurun --gpus 2 -- 'bash scripts/gpu_call_n2.sh'
+# gpurun --gpus 2 -- 'bash scripts/gpu_calls/gpu_call_n2.sh'
 set -u
 out=gpurun_out/r2n2
 mkdir -p "$out"

@@ -1,5 +1,5 @@
 #!/bin/bash
-# gpurun --gpus 2 -- 'bash scripts/gpu_call_n2b.sh': bench lines of the final tree on 2 GPUs
+# gpurun --gpus 2 -- 'bash scripts/gpu_calls/gpu_call_n2b.sh': bench lines of the final tree on 2 GPUs
 # (in-bench parity across the rank boundary), plus the same with programmatic dependent launch
 set -u
 out=gpurun_out/r2n2b

@@ -1,5 +1,5 @@
 #!/bin/bash
-# gpurun --gpus 8 -- 'bash scripts/gpu_call_n8.sh'
+# gpurun --gpus 8 -- 'bash scripts/gpu_calls/gpu_call_n8.sh'
 set -u
 out=gpurun_out/r2n8
 mkdir -p "$out"
