@@ -67,6 +67,14 @@ def parse():
     p.add_argument("--no-parity", action="store_true")
     p.add_argument("--xchunk", type=int, default=0)
     p.add_argument("--variant", type=int, default=0)
+    p.add_argument("--no-extras", action="store_true",
+                   help="skip the extra records of the default N=1 run (other configurations "
+                        "and the diagnostics kernels, each in its own bounded subprocess)")
+    p.add_argument("--extras-budget", type=float, default=240.0,
+                   help="wall-clock budget (s) of all extra records together")
+    p.add_argument("--diagnostics", action="store_true",
+                   help="time the diagnostics kernels only (histograms, spectrum binning) "
+                        "and print their JSON record")
     p.add_argument("--pdl", type=int, default=-1, choices=[-1, 0, 1],
                    help="programmatic dependent launch of the stage kernels (-1: library default)")
     return p.parse_args()
@@ -642,6 +650,14 @@ def run_b200_arm(args):
             cpu = {"value": None, "unit": UNIT, "cores": None, "kind": "port",
                    "sample": f"failed: {exc!r}"}
 
+    # ---------------- extra records (default N = 1 run only) -------------------------
+    extras = None
+    if (rank == 0 and world == 1 and not args.no_extras and args.config == "c3"
+            and not (args.grid or args.nx or args.dtype or args.scaling)):
+        del job
+        torch.cuda.empty_cache()
+        extras = run_extras(args)
+
     if rank == 0:
         config = config_dict(cfg, w, world)
         line = {
@@ -665,7 +681,7 @@ def run_b200_arm(args):
                 "full_step_mlups": value / NUM_STAGES,
             },
             "clocks": clk, "roofline": roofline, "parity": parity, "cpu_baseline": cpu,
-            "e2e": e2e, "e2e_dropin": e2e_dropin,
+            "e2e": e2e, "e2e_dropin": e2e_dropin, "extras": extras,
             "gpu_launches": launches_per_step * steps,
             "background": {"a": bg["a"], "hubble": bg["hubble"]},
         }
@@ -679,6 +695,180 @@ def run_b200_arm(args):
         except Exception:  # noqa: BLE001
             pass
         os._exit(0)
+
+
+# ---------------------------------------------------------------------------
+# extra records of the default run: the other single-GPU configurations of BASELINE.json and
+# the diagnostics kernels, each in its own subprocess under a time limit, AFTER everything
+# the headline line reports has been measured (a failure or timeout here costs one entry
+# of "extras", never the line)
+# ---------------------------------------------------------------------------
+
+def _last_json_line(text):
+    for ln in reversed(text.strip().splitlines()):
+        ln = ln.strip()
+        if ln.startswith("{") and ln.endswith("}"):
+            try:
+                return json.loads(ln)
+            except ValueError:
+                continue
+    return None
+
+
+def run_extras(args):
+    import subprocess
+    t_start = time.perf_counter()
+    budget = float(args.extras_budget)
+    out = {"what": "measured by the same bench.py in separate processes after the headline "
+                   "configuration: `--config cX --steps S --warmup 3 --no-e2e --no-cpu` "
+                   "(parity window kept) and `--diagnostics`; values are whole-GPU MLUPS",
+           "budget_s": budget}
+    jobs = [("c2", ["--config", "c2", "--steps", "40"]),
+            ("c5", ["--config", "c5", "--steps", "10"]),
+            ("diagnostics", ["--diagnostics"]),
+            ("c4", ["--config", "c4", "--steps", "6"])]
+    for name, extra in jobs:
+        left = budget - (time.perf_counter() - t_start)
+        if left < 20:
+            out[name] = {"skipped": "extras budget exhausted"}
+            continue
+        cmd = [sys.executable, os.path.abspath(__file__), "--gpus", "1", "--warmup", "3",
+               "--no-e2e", "--no-cpu", "--no-extras"] + extra
+        t0 = time.perf_counter()
+        try:
+            res = subprocess.run(cmd, capture_output=True, text=True, timeout=min(left, 150.0),
+                                 cwd=ROOT)
+            rec = _last_json_line(res.stdout)
+            if rec is None:
+                out[name] = {"error": f"rc={res.returncode}", "stderr_tail": res.stderr[-400:]}
+                continue
+        except subprocess.TimeoutExpired:
+            out[name] = {"error": "timeout"}
+            continue
+        except Exception as exc:  # noqa: BLE001
+            out[name] = {"error": repr(exc)}
+            continue
+        if name == "diagnostics":
+            rec["seconds"] = time.perf_counter() - t0
+            out[name] = rec
+            continue
+        roof = rec.get("roofline") or {}
+        par = rec.get("parity") or {}
+        summary = {
+            "workload": (rec.get("config") or {}).get("workload"),
+            "value": rec.get("value"), "unit": rec.get("unit"), "steps": rec.get("steps"),
+            "ms_per_step": rec.get("ms_per_step"), "dtype": rec.get("dtype"),
+            "roofline_frac": roof.get("frac"), "roofline_kernel": roof.get("kernel"),
+            "frac_per_stage": roof.get("frac_per_stage"),
+            "whole_stage": roof.get("whole_stage"),
+            "parity_ok": par.get("ok"), "parity_max_rel": par.get("max_rel"),
+            "parity_tol": par.get("tol"), "clocks": rec.get("clocks"),
+            "gpu_launches": rec.get("gpu_launches"),
+            "seconds": time.perf_counter() - t0,
+        }
+        out[name] = summary
+    out["seconds"] = time.perf_counter() - t_start
+    return out
+
+
+def run_diagnostics(args):
+    """Times the diagnostics kernels of row f-4 at the headline lattice (512^3 fp64):
+    FieldHistogrammer (bounds through psb_reduce + the generated two-histogram kernel) and
+    PowerSpectra.bin_power (psb_bin_power), each against its algorithmic traffic (one read
+    of the array) and against the tensor-operation formulation it replaces, which is also
+    the correctness check.  CUDA events on the current stream, 3 warm-up + 10 timed calls."""
+    import torch
+    import pystella_b200 as ps
+    from pystella_b200 import _kernels
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    n = args.grid or 512
+    h, nb = 2, 432
+    grid = (n, n, n)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak = json.load(open(peaks_path))["hbm_gbs"] if os.path.exists(peaks_path) else 6650.0
+
+    def timed(fn, reps=10, warm=3):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    rec = {"lattice": list(grid), "dtype": "f64", "peak_gbs": peak}
+    decomp = ps.DomainDecomposition((1, 1, 1), h, grid_shape=grid)
+    gen = torch.Generator(device=dev).manual_seed(11)
+    f = torch.randn((1,) + tuple(m + 2 * h for m in grid), dtype=torch.float64, device=dev,
+                    generator=gen)
+    sites = float(n)**3
+
+    # ---- FieldHistogrammer: bounds + two histograms
+    fh = ps.FieldHistogrammer(decomp, nb, "float64", halo_shape=h)
+    bounds = fh._bounds(f[0])
+    ms_bounds = timed(lambda: fh._bounds(f[0]))
+    gen_hist = lambda: ps.Histogrammer._device_histograms(fh, None, dict(f=f[0], **bounds))  # noqa: E731
+    got = gen_hist()
+    ms_hist = timed(gen_hist)
+    eager = lambda: ps.Histogrammer._host_histograms(fh, dict(f=f[0], **bounds))  # noqa: E731
+    ref = eager()
+    ms_eager = timed(eager, reps=3, warm=1)
+    diff = float((got - ref).abs().sum())
+    rec["field_histogram"] = {
+        "num_bins": nb, "histograms": 2,
+        "bounds_ms": ms_bounds, "bounds_gbs": sites * 8 / ms_bounds / 1e6,
+        "bounds_what": "one psb_reduce launch pair (max f, min f, max |f|, min |f|) + the "
+                       "host read-back of 4 doubles",
+        "kernel_ms": ms_hist, "kernel_gbs": sites * 8 / ms_hist / 1e6,
+        "kernel_frac_of_peak": sites * 8 / ms_hist / 1e6 / peak,
+        "tensor_ops_ms": ms_eager, "speedup_vs_tensor_ops": ms_eager / ms_hist,
+        "sites_counted": [float(got[0].sum()), float(got[1].sum())],
+        "abs_count_difference_vs_tensor_ops": diff,
+        "ok": bool(got[0].sum() == sites and got[1].sum() == sites and diff <= 16),
+        "kernel": "generated (NVRTC) two-histogram kernel, csrc/hist_accum.cuh",
+    }
+    del f, got, ref
+    torch.cuda.empty_cache()
+
+    # ---- PowerSpectra.bin_power
+    fft = ps.DFT(decomp, None, None, grid, "float64")
+    L = 5.0
+    dk = (2 * np.pi / L,) * 3
+    spectra = ps.PowerSpectra(decomp, fft, dk, L**3)
+    K = tuple(fft.shape(True))
+    fk = torch.view_as_complex(torch.randn(K + (2,), dtype=torch.float64, device=dev,
+                                           generator=gen))
+    momenta = [fft.sub_k[m] for m in ("momenta_x", "momenta_y", "momenta_z")]
+    run = lambda: _kernels.bin_power(fk, momenta, dk, spectra.bin_width, 3, n / 2,  # noqa: E731
+                                     spectra.num_bins, True)
+    got = run()
+    ms_bin = timed(run)
+    bins, mult, kmag = (t.to(dev) for t in spectra._host_tables())
+
+    def eager_spec():
+        k = fk.reshape(-1)
+        wgt = mult * kmag**3 * (k.real**2 + k.imag**2)
+        out = torch.zeros(spectra.num_bins, dtype=torch.float64, device=dev)
+        out.index_add_(0, bins, wgt)
+        return out
+    ref = eager_spec()
+    ms_eager = timed(eager_spec, reps=3, warm=1)
+    modes = float(np.prod(K))
+    err = float(((got - ref).abs().max() / ref.abs().max()))
+    rec["bin_power"] = {
+        "kshape": list(K), "num_bins": spectra.num_bins,
+        "kernel_ms": ms_bin, "kernel_gbs": modes * 16 / ms_bin / 1e6,
+        "kernel_frac_of_peak": modes * 16 / ms_bin / 1e6 / peak,
+        "tensor_ops_ms": ms_eager, "speedup_vs_tensor_ops": ms_eager / ms_bin,
+        "max_rel_difference_vs_tensor_ops": err, "ok": bool(err < 1e-12),
+        "kernel": "psb::bin_power_kernel<double, true> (csrc/diag.cu), algorithmic traffic "
+                  "16 B per mode",
+    }
+    print(json.dumps(rec), flush=True)
 
 
 # ---------------------------------------------------------------------------
@@ -971,5 +1161,7 @@ if __name__ == "__main__":
     a = parse()
     if a.impl == "reference":
         run_reference_arm(a)
+    elif a.diagnostics:
+        run_diagnostics(a)
     else:
         run_b200_arm(a)

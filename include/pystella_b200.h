@@ -358,6 +358,34 @@ int64_t psb_reduce_workspace_doubles(int noutputs);
 int psb_reduce(const psb_reduce_args* args, void* stream);
 
 /* ------------------------------------------------------------------------
+ * Binning pass of PowerSpectra.bin_power (pystella/fourier/spectra.py:103-131, a
+ * Histogrammer over momentum space, pystella/histogram.py:60-170):
+ *     spectrum[round(|k| / bin_width)] += count * |k|^k_power * |fk|^2
+ * over the rank-local momentum-space array fk (Kx, Ky, Kz), C order, complex128
+ * (dtype PSB_F64) or complex64 (PSB_F32);  |k|^2 = sum_mu (dk[mu] * momenta_mu[i_mu])^2
+ * with the three 1-D momenta arrays of DFT.sub_k (real, same precision as fk);
+ * count = 2 where is_real and 0 < momenta_z < nyquist, else 1.  `spectrum` (num_bins
+ * doubles) is accumulated into: the caller zeroes it.  One pass over fk: 2 S bytes per
+ * mode.  Accumulation order across warps is not fixed (atomics, as in the reference).
+ * ---------------------------------------------------------------------- */
+typedef struct psb_bin_power_args {
+  int32_t dtype;
+  int32_t is_real;
+  int64_t Kx, Ky, Kz;
+  const void* fk;
+  const void* momenta_x;
+  const void* momenta_y;
+  const void* momenta_z;
+  double dk[3];
+  double bin_width, k_power, nyquist;
+  int32_t num_bins;
+  int32_t tune_blocks;           /* 0 = automatic (4 CTAs per SM) */
+  double* spectrum;
+} psb_bin_power_args;
+
+int psb_bin_power(const psb_bin_power_args* args, void* stream);
+
+/* ------------------------------------------------------------------------
  * Launch plan of the fused stage for an externally compiled kernel instance
  * (EXPERIMENTAL; row f-2 of the scope table): pystella accepts arbitrary right-hand
  * sides (pystella/step.py:473-491); for systems outside the polynomial menu the

@@ -3,6 +3,7 @@ Thin Python wrappers around the C ABI: they only marshal tensors / scalars into
 the argument structs of ``include/pystella_b200.h`` and raise on error.
 """
 
+import contextlib
 import ctypes as C
 
 import torch
@@ -258,6 +259,48 @@ def reduce_poly(arrays, halos, terms, ops, flags, shape, queue=None, strict=Fals
     rc = lib.psb_reduce(C.byref(args), _lib.stream_ptr(queue))
     _lib.check(lib, rc, "psb_reduce")
     return out
+
+
+def bin_power(fk, momenta, dk, bin_width, k_power, nyquist, num_bins, is_real,
+              queue=None, blocks=0):
+    """
+    Binning pass of ``PowerSpectra.bin_power`` (``psb_bin_power``): ``fk`` is a contiguous
+    complex CUDA tensor ``(Kx, Ky, Kz)``, ``momenta`` the three 1-D real mode-number tensors
+    of ``DFT.sub_k``.  Returns a float64 device tensor of ``num_bins`` sums.
+    """
+    lib = _lib.load(False)
+    _lib.require_cuda_tensor(fk, "fk")
+    if fk.dim() != 3:
+        raise ValueError("fk must be a 3-D momentum-space array")
+    if fk.dtype == torch.complex128:
+        code, rdtype = _lib.PSB_F64, torch.float64
+    elif fk.dtype == torch.complex64:
+        code, rdtype = _lib.PSB_F32, torch.float32
+    else:
+        raise TypeError(f"fk has dtype {fk.dtype} (complex128/complex64 only)")
+    args = _lib.BinPowerArgs()
+    args.dtype, args.is_real = code, int(bool(is_real))
+    args.Kx, args.Ky, args.Kz = fk.shape
+    args.fk = fk.data_ptr()
+    keep = []
+    for name, m, n in zip(("momenta_x", "momenta_y", "momenta_z"), momenta, fk.shape):
+        _lib.require_cuda_tensor(m, name)
+        if m.dtype != rdtype:
+            m = m.to(rdtype)
+            keep.append(m)
+        if m.numel() != n:
+            raise ValueError(f"{name} has {m.numel()} entries, fk has extent {n}")
+        setattr(args, name, m.data_ptr())
+    for mu in range(3):
+        args.dk[mu] = float(dk[mu])
+    args.bin_width, args.k_power, args.nyquist = float(bin_width), float(k_power), float(nyquist)
+    args.num_bins, args.tune_blocks = int(num_bins), int(blocks)
+    with torch.cuda.stream(queue) if queue is not None else contextlib.nullcontext():
+        spectrum = torch.zeros(int(num_bins), dtype=torch.float64, device=fk.device)
+    args.spectrum = spectrum.data_ptr()
+    rc = lib.psb_bin_power(C.byref(args), _lib.stream_ptr(queue))
+    _lib.check(lib, rc, "psb_bin_power")
+    return spectrum
 
 
 ENERGY_SUMS_DOUBLES = 16 + 64 * 16 + 2   # PSB_ENERGY_SUMS_DOUBLES of the header

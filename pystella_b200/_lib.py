@@ -135,6 +135,20 @@ class ReduceArgs(C.Structure):
     ]
 
 
+class BinPowerArgs(C.Structure):
+    """psb_bin_power_args: binning pass of PowerSpectra.bin_power."""
+    _fields_ = [
+        ("dtype", c_int32), ("is_real", c_int32),
+        ("Kx", c_int64), ("Ky", c_int64), ("Kz", c_int64),
+        ("fk", c_void_p), ("momenta_x", c_void_p), ("momenta_y", c_void_p),
+        ("momenta_z", c_void_p),
+        ("dk", c_double * 3),
+        ("bin_width", c_double), ("k_power", c_double), ("nyquist", c_double),
+        ("num_bins", c_int32), ("tune_blocks", c_int32),
+        ("spectrum", c_void_p),
+    ]
+
+
 #: every symbol include/pystella_b200.h declares: (restype, argtypes)
 class FusedPlan(C.Structure):
     """psb_fused_plan: launch parameters of the fused stage for an external kernel."""
@@ -179,6 +193,7 @@ SYMBOLS = {
                                   c_int, c_int, c_int, c_void_p]),
     "psb_reduce_workspace_doubles": (c_int64, [c_int]),
     "psb_reduce": (c_int, [C.POINTER(ReduceArgs), c_void_p]),
+    "psb_bin_power": (c_int, [C.POINTER(BinPowerArgs), c_void_p]),
     "psb_scalar_stage_energy_slots": (c_int64, [C.POINTER(ScalarStageArgs)]),
     "psb_scalar_stage_fused_plan": (c_int, [C.POINTER(ScalarStageArgs),
                                             C.POINTER(FusedPlan)]),

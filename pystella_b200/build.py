@@ -27,7 +27,8 @@ COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
           "-I" + os.path.join(ROOT, "include"), "-I" + CSRC]
 
 SOURCES = ["common.cu", "fused_stage.cu", "fused_stage_f64.cu", "fused_stage_f32.cu",
-           "stage_unfused.cu", "tensor_stage.cu", "tensor_stage_fused.cu", "rk_stage.cu", "fd.cu", "halo.cu", "reduce.cu", "expansion.cu"]
+           "stage_unfused.cu", "tensor_stage.cu", "tensor_stage_fused.cu", "rk_stage.cu", "fd.cu", "halo.cu", "reduce.cu", "expansion.cu",
+           "diag.cu"]
 
 
 def _digest(paths, extra):

@@ -24,14 +24,16 @@ import numpy as np
 from pystella_b200.field import (Call, Field, Power, Product, Quotient, Subscript, Sum,
                                  Variable, _field_shift, _const_index, is_constant)
 
-__all__ = ["expr_to_c", "KernelSource", "generate_kernel", "JitLibrary", "GenericMap"]
+__all__ = ["expr_to_c", "KernelSource", "generate_kernel", "JitLibrary", "GenericMap",
+           "generate_histogram_kernel", "GeneratedHistogram"]
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 MAX_ARRAYS, MAX_SCALARS = 48, 32
 
 _C_FUNCS = {"fabs": "fabs", "abs": "fabs", "sqrt": "sqrt", "exp": "exp", "log": "log",
             "sin": "sin", "cos": "cos", "tan": "tan", "tanh": "tanh", "sinh": "sinh",
-            "cosh": "cosh"}
+            "cosh": "cosh", "floor": "floor", "round": "round", "min": "fmin",
+            "max": "fmax", "fmin": "fmin", "fmax": "fmax"}
 
 
 class _Ref:
@@ -308,6 +310,177 @@ def generate_kernel(map_instructions, tmp_instructions=None, dtype="double",
 
 
 # ---------------------------------------------------------------------------
+# histograms (pystella/histogram.py:60-170)
+# ---------------------------------------------------------------------------
+
+HIST_WARPS = 8                 # block = (32, HIST_WARPS): a warp owns one y row at a time
+HIST_SMEM_BYTES = 48 * 1024    # static shared memory limit: one copy of the bins must fit
+HIST_COPY_BYTES = 24 * 1024    # ... further per-warp copies only up to here (occupancy)
+HIST_UNROLL = 4                # z chunks of 32 sites whose loads are issued together
+
+
+class _Operands:
+    """Array / scalar operands of a set of read-only expressions (the binding tables of
+    :class:`KernelSource`)."""
+
+    def __init__(self):
+        self.slots, self.slot_index = [], {}
+        self.refs, self.scalars = {}, []
+
+    def leaf(self, node):
+        ref = _as_ref(node)
+        if ref is not None:
+            if ref.key not in self.refs:
+                if ref.slot_key not in self.slot_index:
+                    if len(self.slots) >= MAX_ARRAYS - 1:      # the last slot: the histogram
+                        raise NotImplementedError("too many distinct arrays in one kernel")
+                    self.slot_index[ref.slot_key] = len(self.slots)
+                    self.slots.append((ref.name, ref.subscript, ref.field))
+                n = len(self.refs)
+                self.refs[ref.key] = dict(ref=ref, slot=self.slot_index[ref.slot_key],
+                                          base=f"a{n}", var=f"a{n}[u]")
+            return self.refs[ref.key]["var"]
+        sname = _scalar_name(node)
+        if sname is not None:
+            if sname not in self.scalars:
+                if len(self.scalars) >= MAX_SCALARS:
+                    raise NotImplementedError("too many scalars in one generated kernel")
+                self.scalars.append(sname)
+            return f"s_{sname}"
+        return None
+
+
+def histogram_layout(num_hists, num_bins):
+    """-> ``(use_shared, copies)``: block-private copies of all histograms in shared memory
+    (one per warp while they fit in 48 KB, at least one), else global atomics."""
+    one = num_hists * num_bins * 8
+    if one > HIST_SMEM_BYTES:
+        return False, 0
+    return True, max(1, min(HIST_WARPS, HIST_COPY_BYTES // one))
+
+
+def generate_histogram_kernel(histograms, num_bins, dtype="double",
+                              name="psb_generated_histogram", halo_shape=None):
+    """
+    ``histograms``: list of ``(bin_expr, weight_expr)``.  One kernel evaluates all of them
+    in a single pass over the lattice: ``hist[j, floor(bin_j)] += weight_j`` in float64,
+    bins outside ``[0, num_bins)`` (and NaN) dropped.  The histogram array (``num_hists *
+    num_bins`` doubles, zeroed by the caller) is passed in array slot ``len(slots)``.
+    Accumulation: warp-aggregated runs -> block-private shared-memory copies -> one global
+    atomic per bin and block (``csrc/hist_accum.cuh``, inlined into the source).
+    """
+    hists = list(histograms)
+    if not hists:
+        raise ValueError("no histograms")
+    num_bins, nh = int(num_bins), len(hists)
+    if num_bins < 1:
+        raise ValueError("num_bins must be positive")
+    _HALO_VALUES.clear()
+    if halo_shape is not None:
+        hs = (halo_shape,) * 3 if isinstance(halo_shape, (int, np.integer)) \
+            else tuple(halo_shape)
+        _HALO_VALUES.update(h=hs[0], hx=hs[0], hy=hs[1], hz=hs[2])
+    ops = _Operands()
+    code = [(expr_to_c(b, ops.leaf), expr_to_c(w, ops.leaf)) for b, w in hists]
+    use_shared, copies = histogram_layout(nh, num_bins)
+    hist_slot = len(ops.slots)
+    with open(os.path.join(HERE, "csrc", "hist_accum.cuh")) as fh:
+        accum = fh.read().replace("#pragma once\n", "")
+
+    lines = [
+        "// generated by pystella_b200.codegen -- do not edit",
+        f"typedef {dtype} T;",
+        "struct psb_jit_args {",
+        f"  void* arrays[{MAX_ARRAYS}]; int halos[{MAX_ARRAYS}];",
+        f"  double scalars[{MAX_SCALARS}]; long long Nx, Ny, Nz;",
+        "};",
+        accum,
+        "#define IDX(h, si, sj, sk) ((((long long)(i + (h) + (si))) * (Ny + 2 * (h)) + "
+        "(j + (h) + (sj))) * (Nz + 2 * (h)) + (k + (h) + (sk)))",
+        "#define IDXA(h, a, b, c) ((((long long)(i + (a))) * (Ny + 2 * (h)) + "
+        "(j + (b))) * (Nz + 2 * (h)) + (k + (c)))",
+        f"#define NUM_HISTS {nh}",
+        f"#define NUM_BINS {num_bins}",
+        f"#define HIST_WARPS {HIST_WARPS}",
+        f"#define HIST_COPIES {max(copies, 1)}",
+        f"#define HIST_UNROLL {HIST_UNROLL}",
+        f'extern "C" __global__ void __launch_bounds__({32 * HIST_WARPS}) {name}'
+        "(const psb_jit_args args) {",
+        "  const long long Nx = args.Nx, Ny = args.Ny, Nz = args.Nz;",
+        "  const int lane = threadIdx.x, warp = threadIdx.y;",
+        "  const int tid = warp * 32 + lane, nthreads = 32 * HIST_WARPS;",
+        f"  double* const hist = (double*)args.arrays[{hist_slot}];",
+    ]
+    if use_shared:
+        lines += [
+            "  __shared__ double temp[HIST_COPIES * NUM_HISTS * NUM_BINS];",
+            "  for (int b = tid; b < HIST_COPIES * NUM_HISTS * NUM_BINS; b += nthreads) "
+            "temp[b] = 0.0;",
+            "  __syncthreads();",
+            "  double* const mine = temp + (warp % HIST_COPIES) * (NUM_HISTS * NUM_BINS);",
+        ]
+    else:
+        lines.append("  double* const mine = hist;")
+    for n, sname in enumerate(ops.scalars):
+        lines.append(f"  const T s_{sname} = (T)args.scalars[{n}];")
+    lines += [
+        "  const long long ngy = (Ny + HIST_WARPS - 1) / HIST_WARPS;",
+        "  const long long ngroups = Nx * ngy;",
+        "  for (long long g = blockIdx.x; g < ngroups; g += gridDim.x) {",
+        "    const long long i = g / ngy;",
+        "    const long long j = (g - i * ngy) * HIST_WARPS + warp;",
+        "    if (j >= Ny) continue;                 // uniform in the warp",
+        "    for (long long k0 = 0; k0 < Nz; k0 += 32 * HIST_UNROLL) {",
+        "      bool valid[HIST_UNROLL];",
+    ]
+    for info in ops.refs.values():
+        lines.append(f"      T {info['base']}[HIST_UNROLL];")
+    lines += [
+        "      #pragma unroll",
+        "      for (int u = 0; u < HIST_UNROLL; ++u) {      // all loads first",
+        "        const long long k = k0 + 32 * u + lane;",
+        "        valid[u] = k < Nz;",
+        "        if (valid[u]) {",
+    ]
+    for info in ops.refs.values():
+        s_, (si, sj, sk) = info["slot"], info["ref"].shift
+        macro = "IDXA" if info["ref"].absolute else "IDX"
+        lines.append(f"          {info['var']} = ((const T*)args.arrays[{s_}])"
+                     f"[{macro}(args.halos[{s_}], {si}, {sj}, {sk})];")
+    lines += [
+        "        }",
+        "      }",
+        "      #pragma unroll",
+        "      for (int u = 0; u < HIST_UNROLL; ++u) {",
+        "        if (k0 + 32 * u >= Nz) break;              // uniform in the warp",
+    ]
+    for j in range(nh):
+        lines += [f"        int bin{j} = -1;", f"        double w{j} = 0.0;"]
+    lines.append("        if (valid[u]) {")
+    for j, (bcode, wcode) in enumerate(code):
+        lines += [
+            f"          const T q{j} = floor({bcode});",
+            f"          if (q{j} >= (T)0 && q{j} < (T)NUM_BINS) bin{j} = (int)q{j};",
+            f"          w{j} = (double)({wcode});",
+        ]
+    lines.append("        }")
+    for j in range(nh):
+        lines.append(f"        psb::hist_accumulate(mine + {j} * NUM_BINS, NUM_BINS, bin{j}, "
+                     f"w{j}, lane);")
+    lines.append("      }")
+    lines += ["    }", "  }"]
+    if use_shared:
+        lines += ["  __syncthreads();",
+                  "  psb::hist_flush(temp, HIST_COPIES, NUM_HISTS * NUM_BINS, hist, tid, "
+                  "nthreads);"]
+    lines.append("}")
+    ksrc = KernelSource("\n".join(lines) + "\n", name, ops.slots, ops.scalars, dtype)
+    ksrc.hist_slot = hist_slot
+    ksrc.num_hists, ksrc.num_bins = nh, num_bins
+    return ksrc
+
+
+# ---------------------------------------------------------------------------
 # runtime
 # ---------------------------------------------------------------------------
 
@@ -545,3 +718,94 @@ class GenericMap:
             raise _lib.PsbError("launch of a generated kernel failed: "
                                 + lib.psb_jit_last_log().decode(errors="replace"))
         return None, {}
+
+
+def _bind_operands(ksrc, kwargs, dtype, rank_shape, halo_of, args):
+    """Fill array pointers, halos, scalars and the domain of ``args`` from keyword
+    arguments (shared by the generated maps and histograms); -> rank shape."""
+    import torch
+    from pystella_b200 import _lib
+    want = getattr(torch, dtype.name)
+    views = []
+    for name, sub, field in ksrc.slots:
+        if name not in kwargs:
+            raise TypeError(f"missing array argument '{name}'")
+        t = _lib.require_cuda_tensor(kwargs[name], name)
+        if t.dtype != want:
+            raise ValueError(f"'{name}' has dtype {t.dtype}; this kernel was built for "
+                             f"{dtype.name}")
+        view = t[sub] if sub else t
+        if view.dim() != 3:
+            raise ValueError(f"'{name}{list(sub)}' is not a 3-D array")
+        if not view.is_contiguous():
+            raise ValueError(f"'{name}{list(sub)}' is not contiguous (z fastest)")
+        views.append(view)
+    shape, halos = infer_layout(ksrc, [tuple(v.shape) for v in views], rank_shape, halo_of)
+    for n, view in enumerate(views):
+        args.arrays[n] = view.data_ptr()
+        args.halos[n] = halos[n]
+    for n, sname in enumerate(ksrc.scalars):
+        base, _, idx = sname.partition("__")
+        if base not in kwargs:
+            if base == "pi":
+                args.scalars[n] = float(np.pi)
+                continue
+            raise TypeError(f"missing scalar argument '{base}'")
+        v = kwargs[base]
+        v = v.cpu().numpy() if isinstance(v, torch.Tensor) else v
+        v = np.asarray(v)
+        if idx:
+            v = v[tuple(int(i) for i in idx.split("_"))]
+        args.scalars[n] = float(v.reshape(-1)[0])
+    args.Nx, args.Ny, args.Nz = shape
+    return shape, views
+
+
+class GeneratedHistogram:
+    """
+    The compiled kernel behind :class:`pystella_b200.Histogrammer` (the reference builds
+    its histogram kernels with loopy, ``pystella/histogram.py:60-170``): all histograms of
+    one ``Histogrammer`` in a single pass.  ``__call__`` returns a float64 CUDA tensor
+    ``(num_hists, num_bins)`` on the launch stream.
+    """
+
+    def __init__(self, histograms, num_bins, dtype="float64", halo_shape=None,
+                 rank_shape=None):
+        self.dtype = np.dtype(dtype)
+        ctype = {"float64": "double", "float32": "float"}[self.dtype.name]
+        self.ksrc = generate_histogram_kernel(histograms, num_bins, ctype,
+                                              halo_shape=halo_shape)
+        self.halo_shape = halo_shape
+        self.rank_shape = tuple(rank_shape) if rank_shape is not None else None
+        self._handle = None
+
+    _halo_of = GenericMap._halo_of
+
+    def __call__(self, queue=None, blocks=0, **kwargs):
+        import contextlib
+        import torch
+        from pystella_b200 import _lib
+        if self._handle is None:
+            self._handle = JitLibrary.compile(self.ksrc)
+        if not self.ksrc.slots and self.rank_shape is None:
+            raise ValueError("no array argument: pass rank_shape= to the constructor")
+        args = JitArgs()
+        shape, views = _bind_operands(self.ksrc, kwargs, self.dtype, self.rank_shape,
+                                      self._halo_of, args)
+        device = views[0].device if views else torch.device("cuda",
+                                                            torch.cuda.current_device())
+        nh, nb = self.ksrc.num_hists, self.ksrc.num_bins
+        with torch.cuda.stream(queue) if queue is not None else contextlib.nullcontext():
+            hist = torch.zeros((nh, nb), dtype=torch.float64, device=device)
+        args.arrays[self.ksrc.hist_slot] = hist.data_ptr()
+        ngroups = shape[0] * ((shape[1] + HIST_WARPS - 1) // HIST_WARPS)
+        if blocks <= 0:
+            blocks = 4 * torch.cuda.get_device_properties(device).multi_processor_count
+        blocks = max(1, min(int(blocks), ngroups))
+        lib = JitLibrary.get()
+        rc = lib.psb_jit_launch(self._handle, C.byref(args), blocks, 1, 1, 32, HIST_WARPS, 1,
+                                _lib.stream_ptr(queue))
+        if rc != 0:
+            raise _lib.PsbError("launch of a generated histogram kernel failed: "
+                                + lib.psb_jit_last_log().decode(errors="replace"))
+        return hist

@@ -485,27 +485,47 @@ class PowerSpectra:
         edges = np.arange(-.5, self.num_bins + .5) * self.bin_width
         self.bin_counts = decomp.allreduce(
             np.histogram(kmags, weights=counts, bins=edges)[0])
-        # per-mode bin index and multiplicity, resident on the device (spectra.py:103-117:
-        # bin = round(|k| / bin_width), C rounding; weight = count * |k|**n * |f_k|**2, where the
-        # kernel's count is 2 strictly inside 0 < k_z < N_z/2)
-        dev = fft.device
-        self._bin = torch.from_numpy(np.floor(kmags / self.bin_width + .5).astype(np.int64)
-                                     .reshape(-1)).to(dev)
-        if fft.is_real:
-            kz = kvecs[2]
-            mult = np.where((kz > 0) & (kz < self.grid_shape[-1] / 2), 2., 1.)
-        else:
-            mult = np.ones_like(kmags)
-        self._mult = torch.from_numpy(mult.reshape(-1)).to(dev)
-        self._kmag = torch.from_numpy(kmags.reshape(-1)).to(dev)
+        # device arrays are binned by csrc/diag.cu, which forms |k|, the bin and the
+        # multiplicity on the fly (spectra.py:103-117: bin = round(|k| / bin_width), C
+        # rounding; weight = count * |k|**n * |f_k|**2, count = 2 strictly inside
+        # 0 < k_z < N_z/2); the per-mode tables below serve host arrays only
+        self._tables = None
+
+    def _host_tables(self):
+        if self._tables is None:
+            fft = self.fft
+            kvecs = np.meshgrid(*fft._k_host, indexing="ij", sparse=False)
+            kmags = np.sqrt(sum((dki * ki)**2 for dki, ki in zip(self.dk, kvecs)))
+            if fft.is_real:
+                kz = kvecs[2]
+                mult = np.where((kz > 0) & (kz < self.grid_shape[-1] / 2), 2., 1.)
+            else:
+                mult = np.ones_like(kmags)
+            self._tables = (
+                torch.from_numpy(np.floor(kmags / self.bin_width + .5).astype(np.int64)
+                                 .reshape(-1)),
+                torch.from_numpy(mult.reshape(-1)), torch.from_numpy(kmags.reshape(-1)))
+        return self._tables
 
     def bin_power(self, fk, queue=None, k_power=3, allocator=None):
         """-> NumPy array: the unnormalised binned spectrum of ``fk`` divided by the bin
         multiplicities (spectra.py:132-163)."""
-        k = self.fft._to_device(fk).reshape(-1)
-        weight = self._mult * self._kmag**k_power * (k.real.double()**2 + k.imag.double()**2)
-        spectrum = torch.zeros(self.num_bins, dtype=torch.float64, device=k.device)
-        spectrum.index_add_(0, self._bin, weight)
+        k = self.fft._to_device(fk)
+        if k.is_cuda:
+            # one pass over fk, |k| formed on the fly from the 1-D momenta (csrc/diag.cu)
+            from pystella_b200 import _kernels
+            k = k.contiguous().reshape(self.kshape)
+            spectrum = _kernels.bin_power(
+                k, [self.fft.sub_k[n] for n in ("momenta_x", "momenta_y", "momenta_z")],
+                self.dk, self.bin_width, k_power, self.grid_shape[-1] / 2, self.num_bins,
+                self.fft.is_real, queue=queue)
+        else:
+            # host arrays (the decomposition's host test backend)
+            k = k.reshape(-1)
+            bins, mult, kmag = self._host_tables()
+            weight = mult * kmag**k_power * (k.real.double()**2 + k.imag.double()**2)
+            spectrum = torch.zeros(self.num_bins, dtype=torch.float64, device=k.device)
+            spectrum.index_add_(0, bins, weight)
         if self.decomp.comm is not None:
             spectrum = self.decomp.allreduce(spectrum)
         with np.errstate(divide="ignore", invalid="ignore"):

@@ -3,15 +3,21 @@ Histograms next to the time loop: :class:`Histogr
 and :class:`FieldHistogrammer` with the call contracts of ``pystella/histogram.py:29-350``.
 
 A histogram is ``hist[floor(bin_expr)] += weight_expr`` over all sites, where both
-expressions are symbolic (Fields, scalars by keyword).  They run once per output slice:
-the expressions are evaluated with device-wide tensor operations and binned with one
-``index_add_`` in float64; out-of-range bins are dropped (the reference's kernel would
-write out of bounds; its :class:`FieldHistogrammer` clips, as does this one).
+expressions are symbolic (Fields, scalars by keyword).  As in the reference (which has loopy
+generate the kernel, histogram.py:60-170) ALL histograms of one :class:`Histogrammer` are
+evaluated by ONE run-time generated kernel in a single pass over the arrays
+(``codegen.generate_histogram_kernel``: warp-aggregated runs -> block-private shared-memory
+copies -> one global atomic per bin and block, accumulation in float64); out-of-range bins
+are dropped (the reference's kernel would write out of bounds; its
+:class:`FieldHistogrammer` clips, as does this one).  The bounds of
+:class:`FieldHistogrammer` come from one ``psb_reduce`` launch (max/min of ``f`` and
+``|f|``).
 
-Arrays must be CUDA tensors (host tensors are accepted only under the decomposition's
-``host_ops`` test hook, like ``share_halos``).
+Arrays must be CUDA tensors; host tensors are accepted only under the decomposition's
+``host_ops`` test hook (like ``share_halos``) and are then evaluated with tensor operations.
 """
 
+from contextlib import nullcontext as _nullcontext
 from itertools import product
 
 import numpy as np
@@ -166,6 +172,7 @@ class Histogrammer:
         self.halo_shape = kwargs.pop("halo_shape", 0)
         self.rank_shape = kwargs.pop("rank_shape", None)
         self._ignored_kwargs = kwargs
+        self._generated = {}
 
     def _check_device(self, kwargs):
         for name, v in kwargs.items():
@@ -174,9 +181,38 @@ class Histogrammer:
                 raise PsbError(f"'{name}' lives on {v.device}: histograms run on the GPU "
                                "only (no CPU fallback)")
 
+    def _device_histograms(self, queue, kwargs):
+        """-> float64 CUDA tensor (num_hists, num_bins) from the generated kernel."""
+        from pystella_b200.codegen import GeneratedHistogram
+        arrays = [v for v in kwargs.values() if isinstance(v, torch.Tensor) and v.dim() >= 3]
+        tdtype = arrays[0].dtype if arrays else torch.float64
+        if tdtype not in (torch.float64, torch.float32):
+            raise TypeError(f"histograms of {tdtype} arrays are not supported")
+        key = str(tdtype)
+        if key not in self._generated:
+            self._generated[key] = GeneratedHistogram(
+                list(self.histograms.values()), self.num_bins,
+                dtype=str(tdtype).replace("torch.", ""), halo_shape=self.halo_shape,
+                rank_shape=self.rank_shape)
+        return self._generated[key](queue, **kwargs)
+
     def __call__(self, queue=None, filter_args=False, **kwargs):
         kwargs.pop("allocator", None)
         self._check_device(kwargs)
+        on_host = any(isinstance(v, torch.Tensor) and v.dim() >= 3 and not v.is_cuda
+                      for v in kwargs.values())
+        if on_host or (getattr(self.decomp, "host_ops", None) is not None
+                       and not torch.cuda.is_available()):
+            hist = self._host_histograms(kwargs)
+        else:
+            hist = self._device_histograms(queue, kwargs)
+        if self.decomp.comm is not None:
+            hist = self.decomp.allreduce(hist)
+        full = hist.cpu().numpy().astype(self.dtype)
+        return {name: full[j] for j, name in enumerate(self.histograms)}
+
+    def _host_histograms(self, kwargs):
+        """Host tensors (test hook of the decomposition): tensor operations + index_add_."""
         ev = _TensorEvaluator(kwargs, self.halo_shape, self.rank_shape)
         rows = []
         for bin_expr, weight_expr in self.histograms.values():
@@ -187,8 +223,7 @@ class Histogrammer:
             raise ValueError("no array argument: pass rank_shape= to the constructor")
         device = ev.device
         if device is None:
-            device = (torch.device("cuda", torch.cuda.current_device())
-                      if torch.cuda.is_available() else torch.device("cpu"))
+            device = torch.device("cpu")
         nsites = int(np.prod(shape))
         hist = torch.zeros((len(rows), self.num_bins), dtype=torch.float64, device=device)
         for j, (b, w) in enumerate(rows):
@@ -203,10 +238,7 @@ class Histogrammer:
                   else torch.full((nsites,), float(w), dtype=torch.float64, device=device))
             ok = (idx >= 0) & (idx < self.num_bins)
             hist[j].index_add_(0, idx[ok], wt[ok])
-        if self.decomp.comm is not None:
-            hist = self.decomp.allreduce(hist)
-        full = hist.cpu().numpy().astype(self.dtype)
-        return {name: full[j] for j, name in enumerate(self.histograms)}
+        return hist
 
 
 class FieldHistogrammer(Histogrammer):
@@ -239,16 +271,31 @@ class FieldHistogrammer(Histogrammer):
         self._f = f
         self._bound_names = ("max_f", "min_f", "max_log_f", "min_log_f")
 
-    def _bounds(self, f):
-        ev = _TensorEvaluator({"f": f}, self.halo_shape, None)
-        x = ev(self._f)
-        lx = torch.log(torch.abs(x))
-        vals = torch.stack([x.max(), -x.min(), lx.max(), -lx.min()]).double()
+    def _bounds(self, f, queue=None):
+        if f.is_cuda:
+            # one pass: max f, min f, max |f|, min |f| (psb_reduce ops 1 = max, 2 = min,
+            # flag 1 = absolute value); log is monotone, so the bounds of log|f| are the
+            # logs of the bounds of |f|
+            from pystella_b200 import _kernels
+            h = _TensorEvaluator({"f": f}, self.halo_shape, None)._halo_of(self._f)
+            shape = tuple(n - 2 * h for n in f.shape[-3:])
+            terms = [(r, 1.0, (1,)) for r in range(4)]
+            with torch.cuda.stream(queue) if queue is not None else _nullcontext():
+                vals = _kernels.reduce_poly([f], [h], terms, [1, 2, 1, 2], [0, 0, 1, 1],
+                                            shape, queue=queue)
+                vals = vals * torch.tensor([1., -1., 1., -1.], dtype=torch.float64,
+                                           device=f.device)
+        else:
+            ev = _TensorEvaluator({"f": f}, self.halo_shape, None)
+            x = ev(self._f)
+            ax = torch.abs(x)
+            vals = torch.stack([x.max(), -x.min(), ax.max(), -ax.min()]).double()
         if self.decomp.comm is not None:
             vals = self.decomp.allreduce(vals, op="max")
         vals = vals.cpu().numpy()
-        return {"max_f": vals[0], "min_f": -vals[1], "max_log_f": vals[2],
-                "min_log_f": -vals[3]}
+        with np.errstate(divide="ignore"):
+            return {"max_f": vals[0], "min_f": -vals[1], "max_log_f": np.log(vals[2]),
+                    "min_log_f": np.log(-vals[3])}
 
     def __call__(self, f, queue=None, **kwargs):
         kwargs.pop("allocator", None)
@@ -263,7 +310,7 @@ class FieldHistogrammer(Histogrammer):
             if bounds_passed:
                 bounds = {k: float(np.asarray(kwargs[k])[s]) for k in self._bound_names}
             else:
-                bounds = self._bounds(f[s])
+                bounds = self._bounds(f[s], queue)
             hists = super().__call__(queue, f=f[s], **bounds)
             for key, val in hists.items():
                 out[key][s] = val

@@ -1,0 +1,201 @@
+// Test infrastructure: a tiny CUDA-on-CPU execution model, so that block-level kernels
+// (shared memory, __syncthreads, shared/global atomics, warp shuffles) can be EXECUTED
+// in the CPU test suite of a container that has no GPU.  Not part of the product.
+//
+// Model: one OS thread per CUDA thread of a block; the blocks of a grid run one after
+// the other on the same team of threads.  `__shared__` becomes a function-local static
+// (one copy, i.e. per block since blocks are sequential), `__syncthreads()` a team
+// barrier, atomics are real atomics, warp shuffles exchange through a per-warp buffer.
+// What this checks: indexing, tails, barriers placed consistently, accumulation logic.
+// What it cannot check: memory-model races between warps, alignment traps, performance.
+//
+// Usage (see tests/test_cuda_emu.py): compile a translation unit with
+//   g++ -std=c++17 -O1 -pthread -x c++ -include tests/cuda_emu/cuda_emu.h kernel_source ...
+// and launch with emu::launch(grid, block, [&]{ kernel(args...); }).
+#pragma once
+#include <atomic>
+#include <cmath>
+#include <condition_variable>
+#include <cstdint>
+#include <cstring>
+#include <functional>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#define PSB_CUDA_EMU 1
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __restrict__
+#define __launch_bounds__(...)
+#define __shared__ static
+#define __align__(n) alignas(n)
+
+struct dim3 {
+  unsigned x, y, z;
+  dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {}
+};
+struct uint3_emu { unsigned x, y, z; };
+struct double2 { double x, y; };
+struct float2 { float x, y; };
+struct alignas(16) float4 { float x, y, z, w; };
+static inline double2 make_double2(double a, double b) { return {a, b}; }
+static inline float2 make_float2(float a, float b) { return {a, b}; }
+
+namespace emu {
+
+class Barrier {      // reusable counting barrier (sense-reversing)
+ public:
+  void reset(int n) { n_ = n; count_ = 0; gen_ = 0; }
+  void wait() {
+    std::unique_lock<std::mutex> lk(m_);
+    const unsigned long g = gen_;
+    if (++count_ == n_) { count_ = 0; ++gen_; cv_.notify_all(); return; }
+    cv_.wait(lk, [&] { return gen_ != g; });
+  }
+ private:
+  std::mutex m_;
+  std::condition_variable cv_;
+  int n_ = 1, count_ = 0;
+  unsigned long gen_ = 0;
+};
+
+struct Team {
+  Barrier block;
+  std::vector<Barrier> warps;
+  std::vector<std::vector<unsigned long long>> warp_buf;   // 32 slots of 8 bytes per warp
+};
+
+inline Team*& team() { static Team* t = nullptr; return t; }
+inline thread_local uint3_emu t_threadIdx, t_blockIdx;
+inline thread_local int t_linear = 0;
+inline dim3& g_blockDim() { static dim3 d; return d; }
+inline dim3& g_gridDim() { static dim3 d; return d; }
+
+template <class F>
+void launch(dim3 grid, dim3 block, F&& body) {
+  const int nt = int(block.x * block.y * block.z);
+  Team tm;
+  tm.block.reset(nt);
+  const int nw = (nt + 31) / 32;
+  tm.warps = std::vector<Barrier>(nw);
+  tm.warp_buf.assign(nw, std::vector<unsigned long long>(32, 0));
+  for (int w = 0; w < nw; ++w) tm.warps[w].reset(std::min(32, nt - 32 * w));
+  team() = &tm;
+  g_blockDim() = block;
+  g_gridDim() = grid;
+  std::vector<std::thread> ths;
+  for (int t = 0; t < nt; ++t) {
+    ths.emplace_back([&, t] {
+      t_linear = t;
+      t_threadIdx = {unsigned(t % block.x), unsigned((t / block.x) % block.y),
+                     unsigned(t / (block.x * block.y))};
+      for (unsigned bz = 0; bz < grid.z; ++bz)
+        for (unsigned by = 0; by < grid.y; ++by)
+          for (unsigned bx = 0; bx < grid.x; ++bx) {
+            t_blockIdx = {bx, by, bz};
+            body();
+            tm.block.wait();          // the next block reuses the statics ("shared memory")
+          }
+    });
+  }
+  for (auto& th : ths) th.join();
+  team() = nullptr;
+}
+
+// dynamic shared memory of the running block (size fixed by launch_smem)
+inline std::vector<double>& dyn_smem_store() { static std::vector<double> v; return v; }
+inline double* dynamic_smem() { return dyn_smem_store().data(); }
+
+template <class F>
+void launch_smem(dim3 grid, dim3 block, size_t smem_bytes, F&& body) {
+  // fill with a non-zero pattern: kernels must initialise what they read
+  dyn_smem_store().assign((smem_bytes + 7) / 8, -12345.678);
+  launch(grid, block, body);
+}
+
+template <class T>
+T shfl(T v, int src_lane) {
+  static_assert(sizeof(T) <= 8, "shuffle of at most 8 bytes");
+  Team& tm = *team();
+  const int w = t_linear / 32, lane = t_linear % 32;
+  unsigned long long bits = 0;
+  std::memcpy(&bits, &v, sizeof(T));
+  tm.warp_buf[w][lane] = bits;
+  tm.warps[w].wait();
+  unsigned long long got = tm.warp_buf[w][src_lane & 31];
+  tm.warps[w].wait();
+  T out;
+  std::memcpy(&out, &got, sizeof(T));
+  return out;
+}
+
+inline unsigned ballot(bool pred) {
+  Team& tm = *team();
+  const int w = t_linear / 32, lane = t_linear % 32;
+  tm.warp_buf[w][lane] = pred ? 1ull : 0ull;
+  tm.warps[w].wait();
+  unsigned bits = 0;
+  for (int l = 0; l < 32; ++l) bits |= unsigned(tm.warp_buf[w][l] & 1ull) << l;
+  tm.warps[w].wait();
+  return bits;
+}
+
+template <class T>
+T atomic_add(T* p, T v) {
+  // CAS loop on the bit pattern: works for float / double / integers
+  using U = typename std::conditional<sizeof(T) == 8, unsigned long long, unsigned>::type;
+  U* up = reinterpret_cast<U*>(p);
+  U old = __atomic_load_n(up, __ATOMIC_RELAXED);
+  for (;;) {
+    T cur;
+    std::memcpy(&cur, &old, sizeof(T));
+    T nxt = cur + v;
+    U nbits;
+    std::memcpy(&nbits, &nxt, sizeof(T));
+    if (__atomic_compare_exchange_n(up, &old, nbits, false, __ATOMIC_SEQ_CST, __ATOMIC_RELAXED))
+      return cur;
+  }
+}
+
+}  // namespace emu
+
+#define threadIdx (emu::t_threadIdx)
+#define blockIdx (emu::t_blockIdx)
+#define blockDim (emu::g_blockDim())
+#define gridDim (emu::g_gridDim())
+
+static inline void __syncthreads() { emu::team()->block.wait(); }
+static inline void __syncwarp(unsigned = 0xffffffffu) { emu::team()->warps[emu::t_linear / 32].wait(); }
+static inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+
+static inline double atomicAdd(double* p, double v) { return emu::atomic_add(p, v); }
+static inline float atomicAdd(float* p, float v) { return emu::atomic_add(p, v); }
+static inline int atomicAdd(int* p, int v) { return emu::atomic_add(p, v); }
+static inline unsigned atomicAdd(unsigned* p, unsigned v) { return emu::atomic_add(p, v); }
+static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) {
+  return emu::atomic_add(p, v);
+}
+
+template <class T> static inline T __shfl_sync(unsigned, T v, int lane) { return emu::shfl(v, lane); }
+template <class T> static inline T __shfl_down_sync(unsigned, T v, unsigned d) {
+  const int lane = emu::t_linear % 32;
+  return emu::shfl(v, lane + int(d) < 32 ? lane + int(d) : lane);
+}
+template <class T> static inline T __shfl_up_sync(unsigned, T v, unsigned d) {
+  const int lane = emu::t_linear % 32;
+  return emu::shfl(v, lane - int(d) >= 0 ? lane - int(d) : lane);
+}
+static inline unsigned __ballot_sync(unsigned, bool pred) { return emu::ballot(pred); }
+static inline int __ffs(unsigned x) { return __builtin_ffs(int(x)); }
+template <class T> static inline T __shfl_xor_sync(unsigned, T v, int m) {
+  return emu::shfl(v, (emu::t_linear % 32) ^ m);
+}
+
+static inline double __ldg(const double* p) { return *p; }
+static inline float __ldg(const float* p) { return *p; }
+static inline int __ldg(const int* p) { return *p; }
+static inline double2 __ldg(const double2* p) { return *p; }
+static inline float2 __ldg(const float2* p) { return *p; }

@@ -60,6 +60,8 @@ def test_struct_layout_matches_header():
            'printf("%zu %zu %zu %d\\n", __builtin_offsetof(psb_scalar_stage_args, launch_flags), '
            '__builtin_offsetof(psb_tensor_fused_args, launch_flags), '
            '__builtin_offsetof(psb_scalar_stage_args, pws_sched), PSB_LAUNCH_PDL);'
+           'printf("%zu %zu\\n", sizeof(psb_bin_power_args), '
+           '__builtin_offsetof(psb_bin_power_args, spectrum));'
            'return 0;}')
     with tempfile.TemporaryDirectory() as d:
         c = os.path.join(d, "p.c")
@@ -67,7 +69,10 @@ def test_struct_layout_matches_header():
         exe = os.path.join(d, "p")
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
         (a, b, c, d, e, f, g, off_maps, off_params, tail_size, off_tail,
-         off_ttail, off_lf, off_tlf, off_sched, pdl) = subprocess.check_output([exe]).split()
+         off_ttail, off_lf, off_tlf, off_sched, pdl, bp_size,
+         bp_spec) = subprocess.check_output([exe]).split()
+    assert int(bp_size) == ctypes.sizeof(_lib.BinPowerArgs)
+    assert int(bp_spec) == _lib.BinPowerArgs.spectrum.offset
     assert int(a) == ctypes.sizeof(_lib.ScalarStageArgs)
     assert int(b) == ctypes.sizeof(_lib.ReduceArgs)
     assert int(c) == ctypes.sizeof(_lib.TensorStageArgs)

@@ -1,0 +1,209 @@
+"""
+Block-level kernels EXECUTED without a GPU: the diagnostics kernels (row f-4 of the scope
+table) use shared memory, barriers, shared/global atomics and warp shuffles, which the
+per-site source transformation of test_codegen.py cannot run.  tests/cuda_emu/cuda_emu.h is a
+small CUDA-on-CPU execution model (one OS thread per CUDA thread of a block, blocks in
+sequence); the device code is compiled unchanged with g++ on top of it and checked against
+NumPy.  The same kernels are checked on the GPU in tests/test_zz_gpu_diagnostics.py.
+"""
+
+import ctypes as C
+import hashlib
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+from pystella_b200 import codegen
+from pystella_b200.field import Field, var
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMU = os.path.join(ROOT, "tests", "cuda_emu")
+CSRC = os.path.join(ROOT, "pystella_b200", "csrc")
+_cache = {}
+
+
+def build_emu(source_text, tag):
+    """g++-compile `source_text` on top of cuda_emu.h into a shared object (cached)."""
+    key = hashlib.sha256(source_text.encode()).hexdigest()[:16]
+    if key not in _cache:
+        d = tempfile.mkdtemp(prefix="psb_emu_")
+        cpp = os.path.join(d, f"{tag}.cpp")
+        so = os.path.join(d, f"{tag}.so")
+        with open(cpp, "w") as fh:
+            fh.write(source_text)
+        subprocess.check_call(["g++", "-std=c++17", "-O1", "-pthread", "-shared", "-fPIC",
+                               "-Wno-unknown-pragmas", "-I" + EMU, "-I" + CSRC, cpp, "-o", so])
+        _cache[key] = C.CDLL(so)
+    return _cache[key]
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+# ---------------------------------------------------------------------------
+# psb_bin_power (csrc/diag_kernels.cuh)
+# ---------------------------------------------------------------------------
+
+def _spectrum_case(N, is_real, dtype, k_power, seed=1):
+    rng = np.random.default_rng(seed)
+    rd = np.float64 if dtype == "f64" else np.float32
+    cd = np.complex128 if dtype == "f64" else np.complex64
+    kx = np.fft.fftfreq(N[0], 1 / N[0]).astype(rd)
+    ky = np.fft.fftfreq(N[1], 1 / N[1]).astype(rd)
+    kz = (np.fft.rfftfreq(N[2], 1 / N[2]) if is_real
+          else np.fft.fftfreq(N[2], 1 / N[2])).astype(rd)
+    K = (len(kx), len(ky), len(kz))
+    fk = (rng.standard_normal(K) + 1j * rng.standard_normal(K)).astype(cd)
+    dk = np.array([0.3, 0.41, 0.37])
+    bw = dk.min()
+    kv = np.meshgrid(kx, ky, kz, indexing="ij")
+    kmag = np.sqrt(sum((d * k.astype(np.float64))**2 for d, k in zip(dk, kv)))
+    nb = int(kmag.max() / bw + .5) + 1
+    b = np.floor(kmag / bw + .5).astype(int)
+    mult = (np.where((kv[2] > 0) & (kv[2] < N[2] / 2), 2., 1.) if is_real
+            else np.ones_like(kmag))
+    w = mult * kmag**k_power * (fk.real.astype(np.float64)**2 + fk.imag.astype(np.float64)**2)
+    ref = np.bincount(b.ravel(), weights=w.ravel(), minlength=nb)[:nb]
+    return dict(kx=kx, ky=ky, kz=kz, K=K, fk=fk, dk=dk, bw=bw, nb=nb, ref=ref,
+                nyq=N[2] / 2)
+
+
+@pytest.mark.parametrize("N, is_real, dtype, k_power, copies, use_shared, blocks", [
+    ((16, 12, 20), 1, "f64", 3, 8, 1, 5),        # r2c, per-warp copies
+    ((16, 12, 20), 0, "f64", 3, 3, 1, 7),        # c2c (|k| not monotone along z), 3 copies
+    ((8, 20, 70), 1, "f32", 2.5, 1, 1, 3),       # complex64, pow(), Kz = 36 (one tail chunk)
+    ((8, 20, 140), 0, "f64", 0, 8, 0, 4),        # global atomics only, Kz > 64 + tail
+    ((4, 9, 66), 1, "f64", 1, 2, 1, 100),        # more CTAs than row groups, Ky % 8 != 0
+])
+def test_bin_power_kernel_on_host(N, is_real, dtype, k_power, copies, use_shared, blocks):
+    src = open(os.path.join(EMU, "emu_diag.cpp")).read()
+    lib = build_emu(src, "emu_diag")
+    c = _spectrum_case(N, is_real, dtype, k_power)
+    out = np.zeros(c["nb"])
+    lib.emu_bin_power(
+        C.c_int(dtype == "f64"), _ptr(c["fk"]), _ptr(c["kx"]), _ptr(c["ky"]), _ptr(c["kz"]),
+        C.c_longlong(c["K"][0]), C.c_longlong(c["K"][1]), C.c_longlong(c["K"][2]),
+        c["dk"].ctypes.data_as(C.POINTER(C.c_double)), C.c_double(c["bw"]),
+        C.c_double(k_power), C.c_double(c["nyq"]), C.c_int(c["nb"]), C.c_int(is_real),
+        C.c_int(copies), C.c_int(use_shared), C.c_int(blocks),
+        out.ctypes.data_as(C.POINTER(C.c_double)))
+    assert np.max(np.abs(out - c["ref"])) <= 1e-13 * np.max(np.abs(c["ref"]))
+
+
+# ---------------------------------------------------------------------------
+# generated Histogrammer kernels (codegen.generate_histogram_kernel)
+# ---------------------------------------------------------------------------
+
+def run_generated_histogram_on_host(ksrc, arrays, halos, scalars, shape, blocks):
+    driver = (
+        '#include "cuda_emu.h"\n' + ksrc.source +
+        'extern "C" void run(const psb_jit_args* a, int blocks) {\n'
+        f'  emu::launch(dim3(blocks), dim3(32, {codegen.HIST_WARPS}), '
+        f'[&] {{ {ksrc.name}(*a); }});\n}}\n')
+    lib = build_emu(driver, "emu_hist")
+    args = codegen.JitArgs()
+    for n, (name, sub, _) in enumerate(ksrc.slots):
+        view = arrays[name][sub] if sub else arrays[name]
+        assert view.flags["C_CONTIGUOUS"]
+        args.arrays[n] = view.ctypes.data
+        args.halos[n] = halos[name]
+    hist = np.zeros((ksrc.num_hists, ksrc.num_bins))
+    args.arrays[ksrc.hist_slot] = hist.ctypes.data
+    for n, s in enumerate(ksrc.scalars):
+        args.scalars[n] = scalars[s]
+    args.Nx, args.Ny, args.Nz = shape
+    lib.run(C.byref(args), C.c_int(blocks))
+    return hist
+
+
+@pytest.mark.parametrize("N, h, dtype, nb, blocks", [
+    ((6, 9, 40), 2, "float64", 12, 4),           # tails in y (9 % 8) and z (40 % 32)
+    ((3, 16, 150), 1, "float32", 40, 50),        # two unrolled z iterations, fp32 bins
+    ((5, 8, 32), 0, "float64", 3500, 3),         # 2 x 3500 bins > 48 KB: global atomics only
+])
+def test_generated_field_histograms_on_host(N, h, dtype, nb, blocks):
+    """The two histograms of FieldHistogrammer (pystella/histogram.py:210-290): linear and
+    logarithmic bins with clipping, in one generated kernel."""
+    rng = np.random.default_rng(5)
+    pad = tuple(n + 2 * h for n in N)
+    f_arr = (rng.standard_normal(pad) * 3).astype(dtype)
+    inner = f_arr[h:h + N[0], h:h + N[1], h:h + N[2]] if h else f_arr
+    f = Field("f", offset=h)
+    vmin, vmax, log, fabs = var("min"), var("max"), var("log"), var("fabs")
+
+    def clip(e):
+        return vmax(vmin(e, nb - 1), 0)
+
+    lin = (f - var("min_f")) / (var("max_f") - var("min_f"))
+    lg = (log(fabs(f)) - var("min_log_f")) / (var("max_log_f") - var("min_log_f"))
+    ctype = "double" if dtype == "float64" else "float"
+    ksrc = codegen.generate_histogram_kernel([(clip(lin * nb), 1), (clip(lg * nb), f * f)], nb,
+                                             ctype, halo_shape=h)
+    use_shared, copies = codegen.histogram_layout(2, nb)
+    assert use_shared == (2 * nb * 8 <= 48 * 1024)
+    T = np.dtype(dtype).type
+    sc = dict(min_f=float(inner.min()), max_f=float(inner.max()),
+              min_log_f=float(np.log(np.abs(inner)).min()),
+              max_log_f=float(np.log(np.abs(inner)).max()))
+    got = run_generated_histogram_on_host(ksrc, {"f": f_arr}, {"f": h}, sc, N, blocks)
+    # NumPy in the kernel's precision
+    x = inner.astype(dtype)
+    s = {k: T(v) for k, v in sc.items()}
+    b0 = np.floor(np.maximum(np.minimum((x - s["min_f"]) / (s["max_f"] - s["min_f"]) * T(nb),
+                                        T(nb - 1)), T(0))).astype(int)
+    b1 = np.floor(np.maximum(np.minimum(
+        (np.log(np.abs(x)) - s["min_log_f"]) / (s["max_log_f"] - s["min_log_f"]) * T(nb),
+        T(nb - 1)), T(0))).astype(int)
+    ref0 = np.bincount(b0.ravel(), minlength=nb).astype(float)
+    ref1 = np.bincount(b1.ravel(), weights=(x * x).astype(np.float64).ravel(), minlength=nb)
+    assert got[0].sum() == np.prod(N)
+    # a value within one ulp of a bin edge may land in the neighbouring bin (log/divide
+    # rounding of libm vs NumPy): compare cumulative counts with a tolerance of 2 sites
+    assert np.max(np.abs(np.cumsum(got[0]) - np.cumsum(ref0))) <= 2
+    assert np.allclose(np.cumsum(got[1]), np.cumsum(ref1), rtol=1e-12,
+                       atol=2 * float((x * x).max()))
+
+
+def test_generated_histogram_drops_out_of_range_bins_and_nan():
+    """Bins outside [0, num_bins) are dropped (the reference's kernel would write out of
+    bounds, histogram.py:118-126); NaN bins as well."""
+    N, nb = (2, 3, 37), 5
+    rng = np.random.default_rng(0)
+    x = rng.uniform(-3, 8, N)
+    x[0, 1, 5] = np.nan
+    f = Field("f", offset=0)
+    ksrc = codegen.generate_histogram_kernel([(f, 2)], nb, "double", halo_shape=0)
+    got = run_generated_histogram_on_host(ksrc, {"f": x}, {"f": 0}, {}, N, 2)
+    ok = np.isfinite(x) & (np.floor(x) >= 0) & (np.floor(x) < nb)
+    ref = np.bincount(np.floor(x[ok]).astype(int), minlength=nb) * 2.
+    assert np.array_equal(got[0], ref)
+
+
+def test_warp_aggregation_handles_repeated_runs():
+    """Equal bins that are NOT adjacent in a warp (a, b, a) must both be counted: the run
+    heads then collide on one shared-memory address and rely on the atomic."""
+    N, nb = (1, 1, 64), 4
+    x = np.tile(np.array([0., 1., 0., 0., 2., 2., 1., 3.]), 8).reshape(N)
+    f = Field("f", offset=0)
+    ksrc = codegen.generate_histogram_kernel([(f, f + 1)], nb, "double", halo_shape=0)
+    got = run_generated_histogram_on_host(ksrc, {"f": x}, {"f": 0}, {}, N, 1)
+    ref = np.bincount(x.astype(int).ravel(), weights=(x + 1).ravel(), minlength=nb)
+    assert np.array_equal(got[0], ref)
+
+
+@pytest.mark.parametrize("ctype, nb", [("double", 12), ("float", 432), ("double", 7000)])
+def test_generated_histogram_compiles_for_sm_100a(ctype, nb, monkeypatch):
+    """NVRTC accepts the generated histogram kernels (no GPU needed): shared-memory copies
+    for small bin counts, global atomics beyond 48 KB."""
+    monkeypatch.setenv("PSB_JIT_CACHE", "off")
+    f = Field("f", offset="h")
+    lin = (f - var("min_f")) / (var("max_f") - var("min_f")) * nb
+    ksrc = codegen.generate_histogram_kernel(
+        [(lin, 1), (var("log")(var("fabs")(f)), f * f)], nb, ctype, halo_shape=2)
+    handle = codegen.JitLibrary.compile(ksrc)
+    assert handle > 0 and codegen.JitLibrary.get().psb_jit_cubin_size(handle) > 0
+    assert ("__shared__ double temp" in ksrc.source) == (2 * nb * 8 <= 48 * 1024)

@@ -2,7 +2,8 @@
 GPU tests of the run-time generated kernels (custom stencils, classical RK stages, generated
 right-hand sides inside the fused pipeline, non-polynomial reducers), of the kernel variants
 (aligned thread mapping, finite-difference pipeline, vectorised reduction) and of the loop
-companions (example golden constraint, device transforms, histograms, CUDA-graph capture).
+companions (example golden constraint, CUDA-graph capture; the device transforms, spectra and
+histograms are in test_zz_gpu_diagnostics.py).
 Every case is a hard gate: validated on B200 in rounds 1 and 2.
 """
 import os
@@ -130,82 +131,6 @@ def test_example_golden_constraint_statistical_2e_2(golden, loop):
     out = example.main(argv)
     assert out["steps"] == 64 and out["initial_conditions"] == "rayleigh"
     assert abs(out["constraint"] / golden["example"]["constraint"] - 1) < 2e-2, out
-
-
-def test_fourier_on_device():
-    """cuFFT path of DFT / RayleighGenerator / PowerSpectra == the host backend."""
-    rng = np.random.default_rng(14)
-    grid, h = (16, 12, 20), 2
-    decomp = ps.DomainDecomposition((1, 1, 1), h, grid_shape=grid)
-    dev = ps.DFT(decomp, None, None, grid, "float64")
-    host = ps.DFT(decomp, None, None, grid, "float64", backend="fftw")
-    assert dev.fk.is_cuda and not host.fk.is_cuda
-    pad = tuple(n + 2 * h for n in grid)
-    fx = rng.random(pad)
-    fk_d = dev.dft(to_dev(fx)).cpu().numpy()
-    fk_h = host.dft(fx).numpy()
-    assert np.allclose(fk_d, fk_h, rtol=1e-12, atol=1e-10)
-    back = torch.zeros(pad, dtype=torch.float64, device="cuda")
-    dev.idft(to_dev(fk_h), back)
-    assert np.allclose(back.cpu().numpy()[h:-h, h:-h, h:-h],
-                       np.prod(grid) * fx[h:-h, h:-h, h:-h], rtol=1e-11)
-    assert float(back[0].abs().max()) == 0.
-
-    L = (5., 6., 7.)
-    dk = tuple(2 * np.pi / Li for Li in L)
-    rands = rng.random((4,) + host.shape(True))
-    kw = dict(norm=1.44e-12, omega_k=lambda k: np.sqrt(k**2 + 0.7), hubble=0.31)
-    out = []
-    for fft in (dev, host):
-        modes = ps.RayleighGenerator(None, fft, dk, float(np.prod(L)), seed=1)
-        modes._uniform = lambda shape, fft=fft: torch.from_numpy(rands.copy()).to(fft.device)
-        out.append([x.cpu().numpy() for x in modes.generate_WKB(None, **kw)])
-    assert np.allclose(out[0][0], out[1][0], rtol=1e-12, atol=1e-24)
-    assert np.allclose(out[0][1], out[1][1], rtol=1e-12, atol=1e-24)
-    s_d = ps.PowerSpectra(decomp, dev, dk, float(np.prod(L)))(to_dev(fx))
-    s_h = ps.PowerSpectra(decomp, host, dk, float(np.prod(L)))(fx)
-    ok = np.isfinite(s_h)
-    assert np.allclose(s_d[ok], s_h[ok], rtol=1e-11)
-
-
-def test_histograms_on_device():
-    """Histogrammer / FieldHistogrammer on CUDA tensors == numpy (test/test_histogram.py)."""
-    from pystella_b200.field import var
-    rng = np.random.default_rng(15)
-    grid, h, num_bins = (24, 16, 20), 1, 123
-    decomp = ps.DomainDecomposition((1, 1, 1), h, grid_shape=grid)
-    _fx = ps.Field("fx")
-    hist = ps.Histogrammer(decomp, {"count": (var("abs")(_fx) * num_bins, 1),
-                                    "squared": (var("abs")(_fx) * num_bins, _fx**2)},
-                           num_bins, "float64", rank_shape=grid)
-    fx = rng.random(grid)
-    out = hist(None, fx=to_dev(fx))
-    idx = np.floor(np.abs(fx) * num_bins).astype(int).reshape(-1)
-    assert np.array_equal(out["count"], np.bincount(idx, minlength=num_bins))
-    assert np.allclose(out["squared"],
-                       np.bincount(idx, weights=fx.reshape(-1)**2, minlength=num_bins),
-                       rtol=1e-12)
-    fh = ps.FieldHistogrammer(decomp, num_bins, "float64", rank_shape=grid, halo_shape=h)
-    pad = tuple(n + 2 * h for n in grid)
-    f = rng.random((2,) + pad) * 4.2 - 1.2
-    res = fh(to_dev(f))
-    for s in range(2):
-        fi = f[s][h:-h, h:-h, h:-h]
-        assert res["linear"][s].sum() == np.prod(grid)
-        np_res = np.histogram(fi, bins=res["linear_bins"][s])[0]
-        assert np.sum(np.abs(res["linear"][s] - np_res)) <= 4
-        assert res["log"][s].sum() == np.prod(grid)
-
-
-def test_distributed_fourier_nccl():
-    """Slab DFT over NCCL all-to-all == numpy on the gathered array (2 GPUs)."""
-    import os
-    import subprocess
-    import sys
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
-    from test_distributed import _run
-    _run("gpu_fourier", 2)
 
 
 @pytest.mark.parametrize("cls", ["Stencil", "StreamingStencil"])

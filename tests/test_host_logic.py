@@ -83,6 +83,49 @@ def test_reference_arm_prints_contract_line():
     assert line["config"] == bench.config_dict(cfg, bench.workload(cfg, 1, 0), 1)
 
 
+def test_bench_extras_are_bounded_and_never_fatal(monkeypatch):
+    """bench.run_extras: every extra record runs in its own subprocess; a timeout, a crash
+    or garbage output costs that entry only, and the time budget is respected."""
+    import json
+    import subprocess
+    import types
+    sys.path.insert(0, ROOT)
+    bench = importlib.import_module("bench")
+    calls = []
+
+    def fake_run(cmd, **kw):
+        calls.append((cmd, kw))
+        assert "--no-extras" in cmd and "--no-cpu" in cmd and kw["timeout"] <= 150
+        if "--diagnostics" in cmd:
+            return types.SimpleNamespace(returncode=0, stderr="", stdout=json.dumps(
+                {"bin_power": {"ok": True}}) + "\n")
+        name = cmd[cmd.index("--config") + 1]
+        if name == "c2":
+            line = {"value": 9.0e4, "unit": bench.UNIT, "steps": 40, "ms_per_step": 0.9,
+                    "dtype": "f64", "config": {"workload": "w"},
+                    "roofline": {"frac": 0.85, "kernel": "k"},
+                    "parity": {"ok": True, "max_rel": 5e-14, "tol": 1e-12}}
+            return types.SimpleNamespace(returncode=0, stderr="",
+                                         stdout="noise\n" + json.dumps(line) + "\n")
+        if name == "c5":
+            raise subprocess.TimeoutExpired(cmd, kw["timeout"])
+        return types.SimpleNamespace(returncode=-11, stderr="segfault", stdout="not json")
+
+    monkeypatch.setattr(subprocess, "run", fake_run)
+    args = types.SimpleNamespace(extras_budget=240.0)
+    out = bench.run_extras(args)
+    assert out["c2"]["value"] == 9.0e4 and out["c2"]["parity_ok"] is True
+    assert out["c2"]["roofline_frac"] == 0.85
+    assert out["c5"] == {"error": "timeout"}
+    assert out["c4"]["error"] == "rc=-11"
+    assert out["diagnostics"]["bin_power"]["ok"] is True
+    assert len(calls) == 4
+    # no budget left: nothing is launched
+    calls.clear()
+    out = bench.run_extras(types.SimpleNamespace(extras_budget=5.0))
+    assert not calls and all("skipped" in out[k] for k in ("c2", "c5", "c4", "diagnostics"))
+
+
 # ---------------------------------------------------------------------------------------
 # index arithmetic of the warp-specialised pipeline (csrc/fused_stage_ws.cuh, WsCfg and the
 # consumer's own_off / pw_off / k), restated and checked by enumeration: every interior
