@@ -25,7 +25,8 @@ from pystella_b200.field import (Call, Field, Power, Product, Quotient, Subscrip
                                  Variable, _field_shift, _const_index, is_constant)
 
 __all__ = ["expr_to_c", "KernelSource", "generate_kernel", "JitLibrary", "GenericMap",
-           "generate_histogram_kernel", "GeneratedHistogram"]
+           "generate_histogram_kernel", "GeneratedHistogram", "generate_stencil_kernel",
+           "TiledStencilMap"]
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 MAX_ARRAYS, MAX_SCALARS = 48, 32
@@ -184,14 +185,9 @@ class KernelSource:
         self.domain_slots = tuple(domain_slots)
 
 
-def generate_kernel(map_instructions, tmp_instructions=None, dtype="double",
-                    name="psb_generated_map", halo_shape=None):
-    """
-    ``map_instructions`` / ``tmp_instructions``: lists of ``(assignee, expr)`` (dicts
-    are accepted).  Temporaries (Variables) are evaluated first, in order; then every
-    map statement in order, later statements seeing earlier assignments
-    (``elementwise.py:173-203``).
-    """
+def _analyse_map(map_instructions, tmp_instructions, halo_shape):
+    """Operands and statement bodies of an element-wise map: -> ``(slots, refs, scalars,
+    body)`` (shared by the direct and the shared-memory-tile emitters)."""
     def as_list(x):
         if x is None:
             return []
@@ -269,6 +265,18 @@ def generate_kernel(map_instructions, tmp_instructions=None, dtype="double",
                 f"stencil read of '{info['ref'].name}', which the same kernel writes "
                 "(evaluate the stencil into a separate array first)")
 
+    return slots, refs, scalars, body
+
+
+def generate_kernel(map_instructions, tmp_instructions=None, dtype="double",
+                    name="psb_generated_map", halo_shape=None):
+    """
+    ``map_instructions`` / ``tmp_instructions``: lists of ``(assignee, expr)`` (dicts
+    are accepted).  Temporaries (Variables) are evaluated first, in order; then every
+    map statement in order, later statements seeing earlier assignments
+    (``elementwise.py:173-203``).
+    """
+    slots, refs, scalars, body = _analyse_map(map_instructions, tmp_instructions, halo_shape)
     lines = [
         "// generated by pystella_b200.codegen -- do not edit",
         f"typedef {dtype} T;",
@@ -307,6 +315,166 @@ def generate_kernel(map_instructions, tmp_instructions=None, dtype="double",
                      if info["written"] and info["ref"].absolute
                      and not any(info["ref"].shift)})
     return KernelSource("\n".join(lines) + "\n", name, slots, scalars, dtype, domain)
+
+
+# ---------------------------------------------------------------------------
+# stencil maps with a shared-memory tile (pystella/stencil.py:36-143)
+# ---------------------------------------------------------------------------
+
+TILE_TZ, TILE_TY, TILE_RY = 64, 4, 2     # block (64, 4); every thread owns 2 rows: tile 8 x 64
+TILE_SMEM_LIMIT = 200 * 1024
+
+
+def generate_stencil_kernel(map_instructions, tmp_instructions=None, dtype="double",
+                            name="psb_generated_stencil", halo_shape=None, prefetch_args=()):
+    """
+    The reference's ``Stencil`` / ``StreamingStencil`` stage ``prefetch_args`` in local
+    memory (``lp.add_prefetch(..., fetch_bounding_box=True)``, streaming along ``i`` for the
+    latter: stencil.py:66-84, 113-133).  Here both get the streaming form, which is the
+    one that reads every plane once: a CTA owns a (8 x 64) column of sites in (y, z) and
+    marches along x over a chunk of planes; for every array named in ``prefetch_args`` the
+    bounding box of its stencil offsets is kept in shared memory as a ring of
+    ``hi_x - lo_x + 1`` planes of ``(8 + hi_y - lo_y) x (64 + hi_z - lo_z)`` elements,
+    filled cooperatively (coalesced rows) one plane per step; the statements then read that
+    array from shared memory only.  Arrays not named are read directly.  Same statement
+    semantics as :func:`generate_kernel`.
+    """
+    slots, refs, scalars, body = _analyse_map(map_instructions, tmp_instructions, halo_shape)
+    prefetch = []
+    for pname in prefetch_args:
+        pname = str(pname)
+        group = [info for info in refs.values() if info["ref"].name == pname]
+        if not group:
+            raise ValueError(f"prefetch_args names '{pname}', which no statement reads")
+        if any(info["written"] for info in group):
+            continue                      # read at the centre only (see _analyse_map)
+        for slot in sorted({info["slot"] for info in group}):
+            g = [info for info in group if info["slot"] == slot]
+            lo = [min(info["ref"].shift[ax] for info in g) for ax in range(3)]
+            hi = [max(info["ref"].shift[ax] for info in g) for ax in range(3)]
+            prefetch.append(dict(name=pname, slot=slot, absolute=g[0]["ref"].absolute,
+                                 lo=lo, hi=hi, refs=g))
+    if not prefetch:
+        raise ValueError("no array to prefetch")
+    S = 8 if dtype == "double" else 4
+    TYT = TILE_TY * TILE_RY
+    off = 0
+    for p in prefetch:
+        p["ex"] = p["hi"][0] - p["lo"][0] + 1
+        p["ey"] = TYT + p["hi"][1] - p["lo"][1]
+        p["ez"] = TILE_TZ + p["hi"][2] - p["lo"][2]
+        p["off"] = off
+        off += p["ex"] * p["ey"] * p["ez"]
+        off = (off + 3) // 4 * 4                      # keep 16-byte alignment of the rings
+    smem_bytes = off * S
+    if smem_bytes > TILE_SMEM_LIMIT:
+        raise NotImplementedError(f"the prefetch tiles need {smem_bytes} bytes of shared "
+                                  "memory")
+    in_tile = {}
+    for n, p in enumerate(prefetch):
+        for info in p["refs"]:
+            in_tile[info["var"]] = (n, p)
+
+    lines = [
+        "// generated by pystella_b200.codegen -- do not edit",
+        f"typedef {dtype} T;",
+        "struct psb_jit_args {",
+        f"  void* arrays[{MAX_ARRAYS}]; int halos[{MAX_ARRAYS}];",
+        f"  double scalars[{MAX_SCALARS}]; long long Nx, Ny, Nz;",
+        "};",
+        "#define IDX(h, si, sj, sk) ((((long long)(i + (h) + (si))) * (Ny + 2 * (h)) + "
+        "(j + (h) + (sj))) * (Nz + 2 * (h)) + (k + (h) + (sk)))",
+        "#define IDXA(h, a, b, c) ((((long long)(i + (a))) * (Ny + 2 * (h)) + "
+        "(j + (b))) * (Nz + 2 * (h)) + (k + (c)))",
+        f"#define TZ {TILE_TZ}",
+        f"#define TY {TILE_TY}",
+        f"#define RY {TILE_RY}",
+        "#define TYT (TY * RY)",
+        f'extern "C" __global__ void __launch_bounds__({TILE_TZ * TILE_TY}) {name}'
+        "(const psb_jit_args args) {",
+        "  const long long Nx = args.Nx, Ny = args.Ny, Nz = args.Nz;",
+        "#ifdef PSB_CUDA_EMU",
+        "  T* const smem = (T*)emu::dynamic_smem();",
+        "#else",
+        "  extern __shared__ __align__(16) unsigned char psb_smem_raw[];",
+        "  T* const smem = (T*)psb_smem_raw;",
+        "#endif",
+        "  const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * TZ + tx;",
+        "  const long long z0 = (long long)blockIdx.x * TZ, j0 = (long long)blockIdx.y * TYT;",
+        "  const long long cx = (Nx + gridDim.z - 1) / gridDim.z;   // planes per x chunk",
+        "  const long long i0 = (long long)blockIdx.z * cx;",
+        "  const long long i1 = (i0 + cx < Nx) ? i0 + cx : Nx;",
+        "  if (i0 >= i1) return;                                   // uniform in the CTA",
+        "  const long long k = z0 + tx;",
+    ]
+    for n, sname in enumerate(scalars):
+        lines.append(f"  const T s_{sname} = (T)args.scalars[{n}];")
+    for n, p in enumerate(prefetch):
+        s_ = p["slot"]
+        if p["absolute"]:
+            ox, oy, oz = (str(v) for v in p["lo"])
+        else:
+            ox, oy, oz = (f"(args.halos[{s_}] + ({v}))" for v in p["lo"])
+        lines += [
+            f"  // ring of '{p['name']}': {p['ex']} planes of {p['ey']} x {p['ez']}",
+            f"  T* const ring{n} = smem + {p['off']};",
+            f"  const T* const src{n} = (const T*)args.arrays[{s_}];",
+            f"  const long long py{n} = Ny + 2 * args.halos[{s_}], "
+            f"pz{n} = Nz + 2 * args.halos[{s_}];",
+            f"  const long long ox{n} = {ox}, oy{n} = j0 + {oy}, oz{n} = z0 + {oz};",
+            f"#define LOAD_PLANE{n}(c) do {{ \\",
+            f"    T* const dst_ = ring{n} + ((c) % {p['ex']}) * {p['ey'] * p['ez']}; \\",
+            f"    const T* const row_ = src{n} + (i0 + (c) + ox{n}) * py{n} * pz{n}; \\",
+            f"    for (int e_ = tid; e_ < {p['ey'] * p['ez']}; e_ += TZ * TY) {{ \\",
+            f"      const int jj_ = e_ / {p['ez']}, kk_ = e_ - jj_ * {p['ez']}; \\",
+            f"      const long long pj_ = oy{n} + jj_, pk_ = oz{n} + kk_; \\",
+            f"      if (pj_ < py{n} && pk_ < pz{n}) dst_[e_] = row_[pj_ * pz{n} + pk_]; \\",
+            "    } } while (0)",
+            f"  for (int c = 0; c < {p['ex'] - 1}; ++c) LOAD_PLANE{n}(c);",
+        ]
+    lines += ["  // q: plane counter within the chunk (int: cheap ring arithmetic)",
+              "  for (int q = 0; q < (int)(i1 - i0); ++q) {",
+              "    const long long i = i0 + q;"]
+    for n, p in enumerate(prefetch):
+        lines.append(f"    LOAD_PLANE{n}(q + {p['ex'] - 1});")
+    lines += [
+        "    __syncthreads();",
+        "    #pragma unroll",
+        "    for (int r = 0; r < RY; ++r) {",
+        "      const int jl = ty + TY * r;",
+        "      const long long j = j0 + jl;",
+        "      if (j < Ny && k < Nz) {",
+    ]
+    for info in refs.values():
+        s_, (si, sj, sk) = info["slot"], info["ref"].shift
+        macro = "IDXA" if info["ref"].absolute else "IDX"
+        addr = f"((T*)args.arrays[{s_}])[{macro}(args.halos[{s_}], {si}, {sj}, {sk})]"
+        info["addr"] = addr
+        if info["var"] in in_tile:
+            n, p = in_tile[info["var"]]
+            dx, dy, dz = si - p["lo"][0], sj - p["lo"][1], sk - p["lo"][2]
+            lines.append(f"        T {info['var']} = ring{n}[((q + {dx}) % {p['ex']}) * "
+                         f"{p['ey'] * p['ez']} + (jl + {dy}) * {p['ez']} + (tx + {dz})];")
+        elif info["read"]:
+            lines.append(f"        T {info['var']} = {addr};")
+        else:
+            lines.append(f"        T {info['var']};")
+    lines += ["      " + ln for ln in body]
+    for info in refs.values():
+        if info["written"]:
+            lines.append(f"        {info['addr']} = {info['var']};")
+    lines += ["      }", "    }", "    __syncthreads();", "  }"]
+    for n in range(len(prefetch)):
+        lines.append(f"#undef LOAD_PLANE{n}")
+    lines.append("}")
+    domain = sorted({info["slot"] for info in refs.values()
+                     if info["written"] and info["ref"].absolute
+                     and not any(info["ref"].shift)})
+    ksrc = KernelSource("\n".join(lines) + "\n", name, slots, scalars, dtype, domain)
+    ksrc.smem_bytes = smem_bytes
+    ksrc.prefetch = [dict(name=p["name"], slot=p["slot"], absolute=p["absolute"],
+                          lo=tuple(p["lo"]), hi=tuple(p["hi"])) for p in prefetch]
+    return ksrc
 
 
 # ---------------------------------------------------------------------------
@@ -809,3 +977,68 @@ class GeneratedHistogram:
             raise _lib.PsbError("launch of a generated histogram kernel failed: "
                                 + lib.psb_jit_last_log().decode(errors="replace"))
         return hist
+
+
+class TiledStencilMap(GenericMap):
+    """
+    A compiled stencil map whose ``prefetch_args`` are staged in shared memory
+    (:func:`generate_stencil_kernel`): what ``pystella.Stencil`` / ``StreamingStencil``
+    ask loopy for (``stencil.py:66-84, 113-133``).  Same call contract as
+    :class:`GenericMap`.
+    """
+
+    PLANES_PER_CHUNK = 64
+
+    def __init__(self, map_instructions, tmp_instructions=None, dtype="float64",
+                 halo_shape=None, rank_shape=None, prefetch_args=()):
+        self.dtype = np.dtype(dtype)
+        ctype = {"float64": "double", "float32": "float"}[self.dtype.name]
+        self.ksrc = generate_stencil_kernel(map_instructions, tmp_instructions, ctype,
+                                            halo_shape=halo_shape,
+                                            prefetch_args=prefetch_args)
+        self.halo_shape = halo_shape
+        self.rank_shape = tuple(rank_shape) if rank_shape is not None else None
+        self._handle = None
+
+    @staticmethod
+    def check_reach(prefetch, halos):
+        """The stencil offsets of a staged array must stay inside its padding."""
+        for p in prefetch:
+            H = halos[p["slot"]]
+            lo, hi = ((0, 2 * H) if p["absolute"] else (-H, H))
+            if min(p["lo"]) < lo or max(p["hi"]) > hi:
+                raise ValueError(
+                    f"'{p['name']}' is read at offsets {p['lo']}..{p['hi']}, outside its "
+                    f"padding of {H}")
+
+    @classmethod
+    def launch_grid(cls, shape, sms):
+        """-> (gx, gy, gz): (8 x 64) columns in (y, z), x cut into chunks of ~64 planes
+        (more, shorter chunks while the grid would not fill the GPU twice over)."""
+        gx = (shape[2] + TILE_TZ - 1) // TILE_TZ
+        gy = (shape[1] + TILE_TY * TILE_RY - 1) // (TILE_TY * TILE_RY)
+        gz = max(1, (shape[0] + cls.PLANES_PER_CHUNK - 1) // cls.PLANES_PER_CHUNK)
+        while gx * gy * gz < 2 * sms and shape[0] // (2 * gz) >= 8:
+            gz *= 2
+        return gx, gy, min(gz, 65535)
+
+    def __call__(self, queue=None, filter_args=False, **kwargs):
+        import torch
+        from pystella_b200 import _lib
+        if self._handle is None:
+            self._handle = JitLibrary.compile(self.ksrc)
+        args = JitArgs()
+        shape, views = _bind_operands(self.ksrc, kwargs, self.dtype, self.rank_shape,
+                                      self._halo_of, args)
+        self.check_reach(self.ksrc.prefetch, [args.halos[n]
+                                              for n in range(len(self.ksrc.slots))])
+        sms = torch.cuda.get_device_properties(views[0].device).multi_processor_count
+        gx, gy, gz = self.launch_grid(shape, sms)
+        lib = JitLibrary.get()
+        params = (C.c_void_p * 1)(C.addressof(args))
+        rc = lib.psb_jit_launch_params(self._handle, params, gx, gy, gz, TILE_TZ, TILE_TY, 1,
+                                       self.ksrc.smem_bytes, _lib.stream_ptr(queue))
+        if rc != 0:
+            raise _lib.PsbError("launch of a generated stencil kernel failed: "
+                                + lib.psb_jit_last_log().decode(errors="replace"))
+        return None, {}

@@ -94,20 +94,34 @@ class Stencil(ElementWiseMap):
     """
     ``Stencil(map_instructions, halo_shape, prefetch_args=[...], **kwargs)``
     (``pystella/stencil.py:36-98``): an element-wise map whose statements read neighbouring
-    sites.  The reference stages ``prefetch_args`` in local memory; the generated kernel
-    reads neighbours through L1/L2 instead, so the argument only names the stencilled
-    arrays (the hand-written stencil kernels are :class:`FiniteDifferencer` and
-    :class:`FusedStencilStage`).  Served by the generated kernels (default; see
-    :func:`jit_enabled`).
+    sites.  The reference stages ``prefetch_args`` in local memory; so does the generated
+    kernel here (``codegen.generate_stencil_kernel``: a ring of x planes of the stencil's
+    bounding box in shared memory per named array, a CTA streaming along x), arrays not
+    named are read through L1/L2.  ``tile=False`` (or an empty ``prefetch_args``) selects the
+    direct kernel for every array.  The hand-written stencil kernels are
+    :class:`FiniteDifferencer` and :class:`FusedStencilStage`.
     As a ``MapKernel`` class it behaves like :class:`ElementWiseMap`.
     """
 
     def __init__(self, map_instructions=None, halo_shape=None, **kwargs):
         self.prefetch_args = kwargs.pop("prefetch_args", [])
         kwargs.pop("lsize", None)
+        tile = kwargs.pop("tile", True)
         if map_instructions is not None and halo_shape is None:
             raise TypeError("Stencil requires halo_shape")
+        tiled_kwargs = dict(kwargs)
         super().__init__(map_instructions, halo_shape=halo_shape, **kwargs)
+        if self._generic is not None and tile and self.prefetch_args:
+            from pystella_b200.codegen import TiledStencilMap
+            try:
+                self._generic = TiledStencilMap(
+                    map_instructions, tiled_kwargs.get("tmp_instructions"),
+                    dtype=tiled_kwargs.get("dtype") or "float64", halo_shape=halo_shape,
+                    rank_shape=tiled_kwargs.get("rank_shape"),
+                    prefetch_args=self.prefetch_args)
+            except (NotImplementedError, ValueError):
+                pass        # tiles larger than shared memory / nothing to stage: keep
+                #             the direct kernel
 
 
 class StreamingStencil(Stencil):

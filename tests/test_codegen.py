@@ -372,6 +372,12 @@ def test_stencil_map_with_raw_subscripts_on_host(h, cls):
     # the reference's call, no flag (test/test_stencil.py:37-90)
     stencil_map = getattr(ps, cls)(map_dict, h, prefetch_args=["x"])
     assert stencil_map.prefetch_args == ["x"]
+    # default: x staged in shared memory (executed in tests/test_cuda_emu.py); the direct
+    # kernel (tile=False) is the one this per-site host transformation can run
+    assert isinstance(stencil_map._generic, codegen.TiledStencilMap)
+    assert stencil_map._generic.ksrc.prefetch[0]["hi"] == (2 * h, 2 * h, 2 * h)
+    stencil_map = getattr(ps, cls)(map_dict, h, prefetch_args=["x"], tile=False)
+    assert type(stencil_map._generic) is codegen.GenericMap
     ksrc = stencil_map._generic.ksrc
     N = (6, 5, 7)
     x_h = rng.random(tuple(n + 2 * h for n in N))

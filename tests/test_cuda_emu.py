@@ -207,3 +207,127 @@ def test_generated_histogram_compiles_for_sm_100a(ctype, nb, monkeypatch):
     handle = codegen.JitLibrary.compile(ksrc)
     assert handle > 0 and codegen.JitLibrary.get().psb_jit_cubin_size(handle) > 0
     assert ("__shared__ double temp" in ksrc.source) == (2 * nb * 8 <= 48 * 1024)
+
+
+# ---------------------------------------------------------------------------
+# stencil maps with shared-memory tiles (codegen.generate_stencil_kernel)
+# ---------------------------------------------------------------------------
+
+def run_generated_stencil_on_host(ksrc, arrays, halos, scalars, shape, gz):
+    driver = (
+        '#include "cuda_emu.h"\n' + ksrc.source +
+        'extern "C" void run(const psb_jit_args* a, int gx, int gy, int gz, long long smem) {\n'
+        f'  emu::launch_smem(dim3(gx, gy, gz), dim3({codegen.TILE_TZ}, {codegen.TILE_TY}), '
+        f'(size_t)smem, [&] {{ {ksrc.name}(*a); }});\n}}\n')
+    lib = build_emu(driver, "emu_stencil")
+    args = codegen.JitArgs()
+    for n, (name, sub, _) in enumerate(ksrc.slots):
+        view = arrays[name][sub] if sub else arrays[name]
+        assert view.flags["C_CONTIGUOUS"]
+        args.arrays[n] = view.ctypes.data
+        args.halos[n] = halos[name]
+    for n, s in enumerate(ksrc.scalars):
+        args.scalars[n] = scalars[s]
+    args.Nx, args.Ny, args.Nz = shape
+    codegen.TiledStencilMap.check_reach(ksrc.prefetch, [halos[name] for name, _, _ in ksrc.slots])
+    gx = (shape[2] + codegen.TILE_TZ - 1) // codegen.TILE_TZ
+    tyt = codegen.TILE_TY * codegen.TILE_RY
+    gy = (shape[1] + tyt - 1) // tyt
+    lib.run(C.byref(args), C.c_int(gx), C.c_int(gy), C.c_int(gz),
+            C.c_longlong(ksrc.smem_bytes))
+
+
+@pytest.mark.parametrize("h, dtype, N, gz", [
+    (1, "float64", (6, 5, 7), 1),          # the reference's test: a single short tile
+    (2, "float64", (9, 11, 70), 2),        # tails in y (11 % 8) and z (70 % 64), 2 x chunks
+    (2, "float32", (7, 16, 64), 3),        # exact tiles, uneven x chunks (3 + 3 + 1)
+    (1, "float64", (3, 8, 130), 5),        # more x chunks than planes
+])
+def test_tiled_stencil_raw_subscripts_on_host(h, dtype, N, gz):
+    """test/test_stencil.py:36-90: the six-point sum, `x` staged in shared memory."""
+    rng = np.random.default_rng(9)
+    x, y = var("x"), var("y")
+    i, j, k = var("i"), var("j"), var("k")
+    map_dict = {y[i, j, k]: (x[i + h + h, j + h, k + h] + x[i + h, j + h + h, k + h]
+                             + x[i + h, j + h, k + h + h] + x[i - h + h, j + h, k + h]
+                             + x[i + h, j - h + h, k + h] + x[i + h, j + h, k - h + h])}
+    ctype = "double" if dtype == "float64" else "float"
+    ksrc = codegen.generate_stencil_kernel(map_dict, None, ctype, halo_shape=h,
+                                           prefetch_args=["x"])
+    assert ksrc.prefetch == [dict(name="x", slot=0, absolute=True, lo=(0, 0, 0),
+                                  hi=(2 * h, 2 * h, 2 * h))]
+    x_h = rng.random(tuple(n + 2 * h for n in N)).astype(dtype)
+    y_h = rng.random(N).astype(dtype)
+    run_generated_stencil_on_host(ksrc, {"x": x_h, "y": y_h}, {"x": h, "y": 0}, {}, N, gz)
+    y_true = (x_h[2*h:, h:-h, h:-h] + x_h[h:-h, 2*h:, h:-h] + x_h[h:-h, h:-h, 2*h:]
+              + x_h[:-2*h, h:-h, h:-h] + x_h[h:-h, :-2*h, h:-h] + x_h[h:-h, h:-h, :-2*h])
+    tol = 5e-14 if dtype == "float64" else 1e-5
+    assert np.max(np.abs(y_h - y_true)) <= tol * np.max(np.abs(y_true))
+
+
+def test_tiled_stencil_fields_temporaries_and_mixed_operands_on_host():
+    """Field operands with asymmetric offsets, two staged arrays with different padding, a
+    directly read array, a temporary and a scalar; a second statement that sees the first."""
+    from pystella_b200.field import shift_fields
+    rng = np.random.default_rng(3)
+    N, hf, hg = (5, 10, 66), 2, 1
+    f = Field("f", offset=hf)
+    g = Field("g", offset=hg)
+    u = Field("u", offset=0)
+    out1, out2 = Field("out1", offset=0), Field("out2", offset=1)
+
+    def sh(fld, s):
+        return shift_fields(fld, s)
+
+    tmp = {var("c"): var("alpha") * 2}
+    maps = [(out1, sh(f, (2, 0, 0)) - sh(f, (-1, 0, 0)) + sh(f, (0, -2, 1)) * var("c")
+             + sh(g, (0, 1, -1)) * u),
+            (out2, out1 + sh(g, (1, 0, 0)) + sh(f, (0, 0, 0)))]
+    ksrc = codegen.generate_stencil_kernel(maps, tmp, "double", halo_shape=2,
+                                           prefetch_args=["f", "g"])
+    byname = {p["name"]: p for p in ksrc.prefetch}
+    assert byname["f"]["lo"] == (-1, -2, 0) and byname["f"]["hi"] == (2, 0, 1)
+    assert byname["g"]["lo"] == (0, 0, -1) and byname["g"]["hi"] == (1, 1, 0)
+    arr = {"f": rng.random(tuple(n + 2 * hf for n in N)),
+           "g": rng.random(tuple(n + 2 * hg for n in N)),
+           "u": rng.random(N), "out1": np.zeros(N),
+           "out2": np.zeros(tuple(n + 2 for n in N))}
+    halos = {"f": hf, "g": hg, "u": 0, "out1": 0, "out2": 1}
+    alpha = 0.7
+    run_generated_stencil_on_host(ksrc, arr, halos, {"alpha": alpha}, N, 2)
+
+    def view(a, h, s):
+        return a[tuple(slice(h + si, h + si + n) for si, n in zip(s, N))]
+    fa, ga = arr["f"], arr["g"]
+    o1 = (view(fa, hf, (2, 0, 0)) - view(fa, hf, (-1, 0, 0))
+          + view(fa, hf, (0, -2, 1)) * (alpha * 2) + view(ga, hg, (0, 1, -1)) * arr["u"])
+    o2 = o1 + view(ga, hg, (1, 0, 0)) + view(fa, hf, (0, 0, 0))
+    assert np.max(np.abs(arr["out1"] - o1)) < 1e-14
+    assert np.max(np.abs(view(arr["out2"], 1, (0, 0, 0)) - o2)) < 1e-14
+    assert arr["out2"][0].max() == 0 and arr["out2"][:, :, 0].max() == 0   # halo untouched
+
+
+def test_tiled_stencil_rejects_offsets_outside_the_padding():
+    x, y = var("x"), var("y")
+    i, j, k = var("i"), var("j"), var("k")
+    ksrc = codegen.generate_stencil_kernel({y[i, j, k]: x[i + 4, j + 2, k + 2]}, None,
+                                           "double", halo_shape=2, prefetch_args=["x"])
+    with pytest.raises(ValueError, match="outside its padding"):
+        codegen.TiledStencilMap.check_reach(ksrc.prefetch, [1, 0])
+    codegen.TiledStencilMap.check_reach(ksrc.prefetch, [2, 0])
+
+
+@pytest.mark.parametrize("ctype", ["double", "float"])
+def test_tiled_stencil_compiles_for_sm_100a(ctype, monkeypatch):
+    monkeypatch.setenv("PSB_JIT_CACHE", "off")
+    h = 2
+    x, y = var("x"), var("y")
+    i, j, k = var("i"), var("j"), var("k")
+    map_dict = {y[i, j, k]: (x[i + h + h, j + h, k + h] + x[i + h, j + h + h, k + h]
+                             + x[i + h, j + h, k + h + h] + x[i - h + h, j + h, k + h]
+                             + x[i + h, j - h + h, k + h] + x[i + h, j + h, k - h + h])}
+    ksrc = codegen.generate_stencil_kernel(map_dict, None, ctype, halo_shape=h,
+                                           prefetch_args=["x"])
+    assert codegen.JitLibrary.compile(ksrc) > 0
+    assert codegen.TiledStencilMap.launch_grid((512, 512, 512), 148) == (8, 64, 8)
+    assert codegen.TiledStencilMap.launch_grid((16, 12, 40), 148) == (1, 2, 2)

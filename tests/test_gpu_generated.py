@@ -144,7 +144,9 @@ def test_stencil_map_raw_subscripts(cls):
     map_dict = {y[i, j, k]: (x[i + h + h, j + h, k + h] + x[i + h, j + h + h, k + h]
                              + x[i + h, j + h, k + h + h] + x[i - h + h, j + h, k + h]
                              + x[i + h, j - h + h, k + h] + x[i + h, j + h, k - h + h])}
-    stencil_map = getattr(ps, cls)(map_dict, h, prefetch_args=["x"], jit=True)
+    # the direct (L1/L2) kernel; the shared-memory-tile default is tested in
+    # test_zz_gpu_diagnostics.py
+    stencil_map = getattr(ps, cls)(map_dict, h, prefetch_args=["x"], jit=True, tile=False)
     x_h = rng.random(tuple(n + 2 * h for n in N))
     yd = torch.zeros(N, dtype=torch.float64, device="cuda")
     stencil_map(None, x=to_dev(x_h), y=yd)

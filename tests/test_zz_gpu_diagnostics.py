@@ -205,3 +205,54 @@ def test_field_histogram_bounds_and_counts_at_config_size():
     assert res["linear"][0].sum() == n**3 and res["log"][0].sum() == n**3
     ref = torch.histc(x, bins=nb, min=float(x.min()), max=float(x.max())).cpu().numpy()
     assert np.sum(np.abs(res["linear"][0] - ref)) <= 8
+
+
+# ---------------------------------------------------------------------------
+# Stencil / StreamingStencil with prefetch_args staged in shared memory (row a5)
+# ---------------------------------------------------------------------------
+
+def _six_point(h):
+    from pystella_b200.field import var
+    x, y = var("x"), var("y")
+    i, j, k = var("i"), var("j"), var("k")
+    return {y[i, j, k]: (x[i + h + h, j + h, k + h] + x[i + h, j + h + h, k + h]
+                         + x[i + h, j + h, k + h + h] + x[i - h + h, j + h, k + h]
+                         + x[i + h, j - h + h, k + h] + x[i + h, j + h, k - h + h])}
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+@pytest.mark.parametrize("cls", ["Stencil", "StreamingStencil"])
+@pytest.mark.parametrize("h, N", [(1, (16, 12, 40)), (2, (37, 19, 150))])
+def test_tiled_stencil_map(cls, dtype, h, N):
+    """test/test_stencil.py:36-90 with the reference's call and tolerances: `x` staged in
+    shared memory (tails in y and z, several x chunks)."""
+    from pystella_b200.codegen import TiledStencilMap
+    rng = np.random.default_rng(16)
+    stencil_map = getattr(ps, cls)(_six_point(h), h, prefetch_args=["x"], dtype=dtype)
+    assert isinstance(stencil_map._generic, TiledStencilMap)
+    x_h = rng.random(tuple(n + 2 * h for n in N)).astype(dtype)
+    yd = torch.zeros(N, dtype=getattr(torch, dtype), device="cuda")
+    stencil_map(None, x=to_dev(x_h), y=yd)
+    y_true = (x_h[2*h:, h:-h, h:-h] + x_h[h:-h, 2*h:, h:-h] + x_h[h:-h, h:-h, 2*h:]
+              + x_h[:-2*h, h:-h, h:-h] + x_h[h:-h, :-2*h, h:-h] + x_h[h:-h, h:-h, :-2*h])
+    tol = 5e-14 if dtype == "float64" else 1e-5
+    assert np.max(np.abs(yd.cpu().numpy() - y_true)) <= tol * np.max(np.abs(y_true))
+
+
+def test_tiled_stencil_equals_direct_kernel_at_config_size():
+    """256^3 fp64, h = 2: the shared-memory-tile kernel and the direct kernel agree bit for
+    bit (same expression, same operand order), and both equal shifted tensor sums."""
+    h, n = 2, 256
+    N = (n, n, n)
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.rand(tuple(m + 2 * h for m in N), dtype=torch.float64, device="cuda",
+                   generator=gen)
+    y_tile = torch.zeros(N, dtype=torch.float64, device="cuda")
+    y_direct = torch.zeros_like(y_tile)
+    ps.Stencil(_six_point(h), h, prefetch_args=["x"])(None, x=x, y=y_tile)
+    ps.Stencil(_six_point(h), h, prefetch_args=["x"], tile=False)(None, x=x, y=y_direct)
+    assert torch.equal(y_tile, y_direct)
+    c = slice(h, -h)
+    ref = ((((x[2*h:, c, c] + x[c, 2*h:, c]) + x[c, c, 2*h:]) + x[:-2*h, c, c])
+           + x[c, :-2*h, c]) + x[c, c, :-2*h]
+    assert torch.equal(y_tile, ref)
