@@ -771,8 +771,9 @@ def run_extras(args):
     return out
 
 
-def run_diagnostics(args):
-    """Times the diagnostics kernels of row f-4 at the headline lattice (512^3 fp64):
+def run_diagnostics(args, dev=None, timed=None, dft_backend=None):
+    """(`dev`, `timed`, `dft_backend`: test hooks -- tests/test_emulated_api.py runs this
+    function on host tensors against the CPU execution model.)  Times the diagnostics kernels of row f-4 at the headline lattice (512^3 fp64):
     FieldHistogrammer (bounds through psb_reduce + the generated two-histogram kernel) and
     PowerSpectra.bin_power (psb_bin_power), each against its algorithmic traffic (one read
     of the array) and against the tensor-operation formulation it replaces, which is also
@@ -780,15 +781,17 @@ def run_diagnostics(args):
     import torch
     import pystella_b200 as ps
     from pystella_b200 import _kernels
-    torch.cuda.set_device(0)
-    dev = torch.device("cuda", 0)
+    on_gpu = dev is None
+    if on_gpu:
+        torch.cuda.set_device(0)
+        dev = torch.device("cuda", 0)
     n = args.grid or 512
     h, nb = 2, 432
     grid = (n, n, n)
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     peak = json.load(open(peaks_path))["hbm_gbs"] if os.path.exists(peaks_path) else 6650.0
 
-    def timed(fn, reps=10, warm=3):
+    def cuda_timed(fn, reps=10, warm=3):
         for _ in range(warm):
             fn()
         torch.cuda.synchronize()
@@ -799,76 +802,114 @@ def run_diagnostics(args):
         b.record()
         torch.cuda.synchronize()
         return a.elapsed_time(b) / reps
+    timed = timed or cuda_timed
 
     rec = {"lattice": list(grid), "dtype": "f64", "peak_gbs": peak}
     decomp = ps.DomainDecomposition((1, 1, 1), h, grid_shape=grid)
     gen = torch.Generator(device=dev).manual_seed(11)
-    f = torch.randn((1,) + tuple(m + 2 * h for m in grid), dtype=torch.float64, device=dev,
-                    generator=gen)
     sites = float(n)**3
 
-    # ---- FieldHistogrammer: bounds + two histograms
-    fh = ps.FieldHistogrammer(decomp, nb, "float64", halo_shape=h)
-    bounds = fh._bounds(f[0])
-    ms_bounds = timed(lambda: fh._bounds(f[0]))
-    gen_hist = lambda: ps.Histogrammer._device_histograms(fh, None, dict(f=f[0], **bounds))  # noqa: E731
-    got = gen_hist()
-    ms_hist = timed(gen_hist)
-    eager = lambda: ps.Histogrammer._host_histograms(fh, dict(f=f[0], **bounds))  # noqa: E731
-    ref = eager()
-    ms_eager = timed(eager, reps=3, warm=1)
-    diff = float((got - ref).abs().sum())
-    rec["field_histogram"] = {
-        "num_bins": nb, "histograms": 2,
-        "bounds_ms": ms_bounds, "bounds_gbs": sites * 8 / ms_bounds / 1e6,
-        "bounds_what": "one psb_reduce launch pair (max f, min f, max |f|, min |f|) + the "
-                       "host read-back of 4 doubles",
-        "kernel_ms": ms_hist, "kernel_gbs": sites * 8 / ms_hist / 1e6,
-        "kernel_frac_of_peak": sites * 8 / ms_hist / 1e6 / peak,
-        "tensor_ops_ms": ms_eager, "speedup_vs_tensor_ops": ms_eager / ms_hist,
-        "sites_counted": [float(got[0].sum()), float(got[1].sum())],
-        "abs_count_difference_vs_tensor_ops": diff,
-        "ok": bool(got[0].sum() == sites and got[1].sum() == sites and diff <= 16),
-        "kernel": "generated (NVRTC) two-histogram kernel, csrc/hist_accum.cuh",
-    }
-    del f, got, ref
-    torch.cuda.empty_cache()
+    def field_histogram():
+        f = torch.randn((1,) + tuple(m + 2 * h for m in grid), dtype=torch.float64,
+                        device=dev, generator=gen)
+        fh = ps.FieldHistogrammer(decomp, nb, "float64", halo_shape=h)
+        bounds = fh._bounds(f[0])
+        ms_bounds = timed(lambda: fh._bounds(f[0]))
+        gen_hist = lambda: ps.Histogrammer._device_histograms(  # noqa: E731
+            fh, None, dict(f=f[0], **bounds))
+        got = gen_hist()
+        ms_hist = timed(gen_hist)
+        eager = lambda: ps.Histogrammer._host_histograms(fh, dict(f=f[0], **bounds))  # noqa: E731
+        ref = eager()
+        ms_eager = timed(eager, reps=3, warm=1)
+        diff = float((got - ref).abs().sum())
+        return {
+            "num_bins": nb, "histograms": 2,
+            "bounds_ms": ms_bounds, "bounds_gbs": sites * 8 / ms_bounds / 1e6,
+            "bounds_what": "one psb_reduce launch pair (max f, min f, max |f|, min |f|) + the "
+                           "host read-back of 4 doubles",
+            "kernel_ms": ms_hist, "kernel_gbs": sites * 8 / ms_hist / 1e6,
+            "kernel_frac_of_peak": sites * 8 / ms_hist / 1e6 / peak,
+            "tensor_ops_ms": ms_eager, "speedup_vs_tensor_ops": ms_eager / ms_hist,
+            "sites_counted": [float(got[0].sum()), float(got[1].sum())],
+            "abs_count_difference_vs_tensor_ops": diff,
+            "ok": bool(got[0].sum() == sites and got[1].sum() == sites and diff <= 16),
+            "kernel": "generated (NVRTC) two-histogram kernel, csrc/hist_accum.cuh",
+        }
 
-    # ---- PowerSpectra.bin_power
-    fft = ps.DFT(decomp, None, None, grid, "float64")
-    L = 5.0
-    dk = (2 * np.pi / L,) * 3
-    spectra = ps.PowerSpectra(decomp, fft, dk, L**3)
-    K = tuple(fft.shape(True))
-    fk = torch.view_as_complex(torch.randn(K + (2,), dtype=torch.float64, device=dev,
-                                           generator=gen))
-    momenta = [fft.sub_k[m] for m in ("momenta_x", "momenta_y", "momenta_z")]
-    run = lambda: _kernels.bin_power(fk, momenta, dk, spectra.bin_width, 3, n / 2,  # noqa: E731
-                                     spectra.num_bins, True)
-    got = run()
-    ms_bin = timed(run)
-    bins, mult, kmag = (t.to(dev) for t in spectra._host_tables())
+    def bin_power():
+        fft = (ps.DFT(decomp, None, None, grid, "float64") if dft_backend is None
+               else ps.DFT(decomp, None, None, grid, "float64", backend=dft_backend))
+        L = 5.0
+        dk = (2 * np.pi / L,) * 3
+        spectra = ps.PowerSpectra(decomp, fft, dk, L**3)
+        K = tuple(fft.shape(True))
+        fk = torch.view_as_complex(torch.randn(K + (2,), dtype=torch.float64, device=dev,
+                                               generator=gen))
+        momenta = [fft.sub_k[m] for m in ("momenta_x", "momenta_y", "momenta_z")]
+        run = lambda: _kernels.bin_power(fk, momenta, dk, spectra.bin_width, 3,  # noqa: E731
+                                         n / 2, spectra.num_bins, True)
+        got = run()
+        ms_bin = timed(run)
+        bins, mult, kmag = (t.to(dev) for t in spectra._host_tables())
 
-    def eager_spec():
-        k = fk.reshape(-1)
-        wgt = mult * kmag**3 * (k.real**2 + k.imag**2)
-        out = torch.zeros(spectra.num_bins, dtype=torch.float64, device=dev)
-        out.index_add_(0, bins, wgt)
-        return out
-    ref = eager_spec()
-    ms_eager = timed(eager_spec, reps=3, warm=1)
-    modes = float(np.prod(K))
-    err = float(((got - ref).abs().max() / ref.abs().max()))
-    rec["bin_power"] = {
-        "kshape": list(K), "num_bins": spectra.num_bins,
-        "kernel_ms": ms_bin, "kernel_gbs": modes * 16 / ms_bin / 1e6,
-        "kernel_frac_of_peak": modes * 16 / ms_bin / 1e6 / peak,
-        "tensor_ops_ms": ms_eager, "speedup_vs_tensor_ops": ms_eager / ms_bin,
-        "max_rel_difference_vs_tensor_ops": err, "ok": bool(err < 1e-12),
-        "kernel": "psb::bin_power_kernel<double, true> (csrc/diag.cu), algorithmic traffic "
-                  "16 B per mode",
-    }
+        def eager_spec():
+            k = fk.reshape(-1)
+            wgt = mult * kmag**3 * (k.real**2 + k.imag**2)
+            out = torch.zeros(spectra.num_bins, dtype=torch.float64, device=dev)
+            out.index_add_(0, bins, wgt)
+            return out
+        ref = eager_spec()
+        ms_eager = timed(eager_spec, reps=3, warm=1)
+        modes = float(np.prod(K))
+        err = float(((got - ref).abs().max() / ref.abs().max()))
+        return {
+            "kshape": list(K), "num_bins": spectra.num_bins,
+            "kernel_ms": ms_bin, "kernel_gbs": modes * 16 / ms_bin / 1e6,
+            "kernel_frac_of_peak": modes * 16 / ms_bin / 1e6 / peak,
+            "tensor_ops_ms": ms_eager, "speedup_vs_tensor_ops": ms_eager / ms_bin,
+            "max_rel_difference_vs_tensor_ops": err, "ok": bool(err < 1e-12),
+            "kernel": "psb::bin_power_kernel<double, true> (csrc/diag.cu), algorithmic "
+                      "traffic 16 B per mode",
+        }
+
+    def stencil_map():
+        # the reference's own stencil benchmark (test/test_stencil.py:36-90 with
+        # timing=True): bandwidth = (x.nbytes + y.nbytes) / time
+        from pystella_b200.field import var
+        xs, ys = var("x"), var("y")
+        ii, jj, kk = var("i"), var("j"), var("k")
+        md = {ys[ii, jj, kk]: (xs[ii + h + h, jj + h, kk + h] + xs[ii + h, jj + h + h, kk + h]
+                               + xs[ii + h, jj + h, kk + h + h] + xs[ii - h + h, jj + h, kk + h]
+                               + xs[ii + h, jj - h + h, kk + h] + xs[ii + h, jj + h, kk - h + h])}
+        x = torch.rand(tuple(m + 2 * h for m in grid), dtype=torch.float64, device=dev,
+                       generator=gen)
+        y_t = torch.zeros(grid, dtype=torch.float64, device=dev)
+        y_d = torch.zeros_like(y_t)
+        tiled = ps.Stencil(md, h, prefetch_args=["x"])
+        direct = ps.Stencil(md, h, prefetch_args=["x"], tile=False)
+        ms_t = timed(lambda: tiled(None, x=x, y=y_t))
+        ms_d = timed(lambda: direct(None, x=x, y=y_d))
+        nbytes = x.numel() * 8 + y_t.numel() * 8
+        return {
+            "what": "six-point sum of test/test_stencil.py, h = 2: x staged in shared memory "
+                    "(default) vs read through L1/L2 (tile=False); bytes = x + y once",
+            "tiled_ms": ms_t, "tiled_gbs": nbytes / ms_t / 1e6,
+            "tiled_frac_of_peak": nbytes / ms_t / 1e6 / peak,
+            "direct_ms": ms_d, "direct_gbs": nbytes / ms_d / 1e6,
+            "ok": bool(torch.equal(y_t, y_d)),
+        }
+
+    for name, section in (("field_histogram", field_histogram), ("bin_power", bin_power),
+                          ("stencil_map", stencil_map)):
+        try:
+            rec[name] = section()
+        except Exception as exc:  # noqa: BLE001
+            rec[name] = {"error": repr(exc)[:400]}
+        if on_gpu:
+            torch.cuda.empty_cache()
     print(json.dumps(rec), flush=True)
+    return rec
 
 
 # ---------------------------------------------------------------------------

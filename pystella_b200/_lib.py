@@ -276,10 +276,16 @@ def stream_ptr(queue=None):
     raise TypeError("queue must be a torch.cuda.Stream or None")
 
 
+def on_device(t):
+    """True for tensors the kernels can take (CUDA tensors).  One place, so that the CPU
+    test-suite can run the launch code against the execution model of tests/cuda_emu."""
+    return bool(t.is_cuda)
+
+
 def require_cuda_tensor(t, name):
     if not isinstance(t, torch.Tensor):
         raise TypeError(f"{name} must be a torch.Tensor on a CUDA device, got {type(t)}")
-    if not t.is_cuda:
+    if not on_device(t):
         raise PsbError(f"{name} lives on {t.device}: the hot path runs on the GPU only "
                        "(no CPU fallback)")
     if not t.is_contiguous():

@@ -8,40 +8,9 @@ namespace psb {
 
 template <typename R> static int launch_bin_power(const psb_bin_power_args* a, cudaStream_t stream) {
   BinPowerParams<R> p;
-  p.fk = static_cast<const typename Cplx<R>::type*>(a->fk);
-  p.kx = static_cast<const R*>(a->momenta_x);
-  p.ky = static_cast<const R*>(a->momenta_y);
-  p.kz = static_cast<const R*>(a->momenta_z);
-  p.Kx = a->Kx;
-  p.Ky = a->Ky;
-  p.Kz = a->Kz;
-  p.dkx = a->dk[0];
-  p.dky = a->dk[1];
-  p.dkz = a->dk[2];
-  p.inv_bin_width = 1.0 / a->bin_width;
-  p.k_power = a->k_power;
-  p.nyquist = a->nyquist;
-  p.ipow = -1;
-  if (a->k_power >= 0 && a->k_power <= 16 && a->k_power == double(int(a->k_power)))
-    p.ipow = int(a->k_power);
-  p.num_bins = a->num_bins;
-  p.is_real = a->is_real;
-  p.spectrum = a->spectrum;
-  // block-private copies of the spectrum in shared memory: one per warp while they fit
-  // in 48 KB, a single one up to 6144 bins, global atomics beyond that
-  const size_t bytes_one = size_t(a->num_bins) * sizeof(double);
-  const size_t budget = 48 * 1024;
-  p.use_shared = bytes_one <= budget ? 1 : 0;
-  p.copies = 1;
-  if (p.use_shared) {
-    p.copies = int(budget / bytes_one);
-    if (p.copies > kDiagWarps) p.copies = kDiagWarps;
-  }
-  const size_t smem = p.use_shared ? bytes_one * p.copies : 0;
-  const long long ngroups = a->Kx * ((a->Ky + kDiagWarps - 1) / kDiagWarps);
-  long long blocks = a->tune_blocks > 0 ? a->tune_blocks : 4LL * num_sms();
-  if (blocks > ngroups) blocks = ngroups;
-  if (blocks < 1) blocks = 1;
+  size_t smem = 0;
+  long long blocks = 1;
+  bin_power_setup<R>(a, num_sms(), p, smem, blocks);
   if (p.use_shared)
     bin_power_kernel<R, true><<<dim3((unsigned)blocks), dim3(32, kDiagWarps), smem, stream>>>(p);
   else

@@ -3,6 +3,7 @@
 // tests/cuda_emu/cuda_emu.h.
 #pragma once
 #include "hist_accum.cuh"
+#include "pystella_b200.h"
 
 namespace psb {
 
@@ -99,6 +100,47 @@ __global__ void __launch_bounds__(32 * kDiagWarps) bin_power_kernel(const BinPow
     __syncthreads();
     hist_flush(temp, p.copies, p.num_bins, p.spectrum, tid, nthreads);
   }
+}
+
+// Host side: kernel parameters and launch geometry for `a` (everything but the launch;
+// shared with the CPU execution model of the tests).  Block-private copies of the spectrum
+// in shared memory: one per warp while they fit in 48 KB, a single one up to 6144 bins,
+// global atomics beyond that.  4 CTAs per SM unless tune_blocks says otherwise.
+template <typename R>
+inline void bin_power_setup(const psb_bin_power_args* a, int num_sms, BinPowerParams<R>& p,
+                            size_t& smem_bytes, long long& blocks) {
+  p.fk = static_cast<const typename Cplx<R>::type*>(a->fk);
+  p.kx = static_cast<const R*>(a->momenta_x);
+  p.ky = static_cast<const R*>(a->momenta_y);
+  p.kz = static_cast<const R*>(a->momenta_z);
+  p.Kx = a->Kx;
+  p.Ky = a->Ky;
+  p.Kz = a->Kz;
+  p.dkx = a->dk[0];
+  p.dky = a->dk[1];
+  p.dkz = a->dk[2];
+  p.inv_bin_width = 1.0 / a->bin_width;
+  p.k_power = a->k_power;
+  p.nyquist = a->nyquist;
+  p.ipow = -1;
+  if (a->k_power >= 0 && a->k_power <= 16 && a->k_power == double(int(a->k_power)))
+    p.ipow = int(a->k_power);
+  p.num_bins = a->num_bins;
+  p.is_real = a->is_real;
+  p.spectrum = a->spectrum;
+  const size_t bytes_one = size_t(a->num_bins) * sizeof(double);
+  const size_t budget = 48 * 1024;
+  p.use_shared = bytes_one <= budget ? 1 : 0;
+  p.copies = 1;
+  if (p.use_shared) {
+    p.copies = int(budget / bytes_one);
+    if (p.copies > kDiagWarps) p.copies = kDiagWarps;
+  }
+  smem_bytes = p.use_shared ? bytes_one * p.copies : 0;
+  const long long ngroups = a->Kx * ((a->Ky + kDiagWarps - 1) / kDiagWarps);
+  blocks = a->tune_blocks > 0 ? a->tune_blocks : 4LL * num_sms;
+  if (blocks > ngroups) blocks = ngroups;
+  if (blocks < 1) blocks = 1;
 }
 
 }  // namespace psb

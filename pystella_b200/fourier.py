@@ -30,6 +30,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
+from pystella_b200 import _lib
 from pystella_b200._lib import PsbError
 
 __all__ = ["DFT", "RayleighGenerator", "PowerSpectra", "fftfreq", "make_hermitian"]
@@ -511,7 +512,7 @@ class PowerSpectra:
         """-> NumPy array: the unnormalised binned spectrum of ``fk`` divided by the bin
         multiplicities (spectra.py:132-163)."""
         k = self.fft._to_device(fk)
-        if k.is_cuda:
+        if _lib.on_device(k):
             # one pass over fk, |k| formed on the fly from the 1-D momenta (csrc/diag.cu)
             from pystella_b200 import _kernels
             k = k.contiguous().reshape(self.kshape)

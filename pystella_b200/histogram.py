@@ -23,6 +23,7 @@ from itertools import product
 import numpy as np
 import torch
 
+from pystella_b200 import _lib
 from pystella_b200._lib import PsbError
 from pystella_b200.field import (Call, Field, Power, Product, Quotient, Subscript, Sum,
                                  Variable, _const_index, _field_shift, is_constant)
@@ -176,7 +177,7 @@ class Histogrammer:
 
     def _check_device(self, kwargs):
         for name, v in kwargs.items():
-            if isinstance(v, torch.Tensor) and v.dim() >= 3 and not v.is_cuda \
+            if isinstance(v, torch.Tensor) and v.dim() >= 3 and not _lib.on_device(v) \
                     and getattr(self.decomp, "host_ops", None) is None:
                 raise PsbError(f"'{name}' lives on {v.device}: histograms run on the GPU "
                                "only (no CPU fallback)")
@@ -199,9 +200,9 @@ class Histogrammer:
     def __call__(self, queue=None, filter_args=False, **kwargs):
         kwargs.pop("allocator", None)
         self._check_device(kwargs)
-        on_host = any(isinstance(v, torch.Tensor) and v.dim() >= 3 and not v.is_cuda
-                      for v in kwargs.values())
-        if on_host or (getattr(self.decomp, "host_ops", None) is not None
+        tensors = [v for v in kwargs.values() if isinstance(v, torch.Tensor) and v.dim() >= 3]
+        on_host = any(not _lib.on_device(v) for v in tensors)
+        if on_host or (not tensors and getattr(self.decomp, "host_ops", None) is not None
                        and not torch.cuda.is_available()):
             hist = self._host_histograms(kwargs)
         else:
@@ -272,7 +273,7 @@ class FieldHistogrammer(Histogrammer):
         self._bound_names = ("max_f", "min_f", "max_log_f", "min_log_f")
 
     def _bounds(self, f, queue=None):
-        if f.is_cuda:
+        if _lib.on_device(f):
             # one pass: max f, min f, max |f|, min |f| (psb_reduce ops 1 = max, 2 = min,
             # flag 1 = absolute value); log is monotone, so the bounds of log|f| are the
             # logs of the bounds of |f|

@@ -25,7 +25,7 @@ CSRC = os.path.join(ROOT, "pystella_b200", "csrc")
 _cache = {}
 
 
-def build_emu(source_text, tag):
+def build_emu(source_text, tag, extra=()):
     """g++-compile `source_text` on top of cuda_emu.h into a shared object (cached)."""
     key = hashlib.sha256(source_text.encode()).hexdigest()[:16]
     if key not in _cache:
@@ -35,7 +35,9 @@ def build_emu(source_text, tag):
         with open(cpp, "w") as fh:
             fh.write(source_text)
         subprocess.check_call(["g++", "-std=c++17", "-O1", "-pthread", "-shared", "-fPIC",
-                               "-Wno-unknown-pragmas", "-I" + EMU, "-I" + CSRC, cpp, "-o", so])
+                               "-Wno-unknown-pragmas", "-I" + EMU, "-I" + CSRC,
+                               "-I" + os.path.join(ROOT, "include")] + list(extra)
+                              + [cpp, "-o", so])
         _cache[key] = C.CDLL(so)
     return _cache[key]
 
@@ -48,7 +50,7 @@ def _ptr(a):
 # psb_bin_power (csrc/diag_kernels.cuh)
 # ---------------------------------------------------------------------------
 
-def _spectrum_case(N, is_real, dtype, k_power, seed=1):
+def _spectrum_case(N, is_real, dtype, k_power, seed=1, bw_scale=1.0):
     rng = np.random.default_rng(seed)
     rd = np.float64 if dtype == "f64" else np.float32
     cd = np.complex128 if dtype == "f64" else np.complex64
@@ -59,7 +61,7 @@ def _spectrum_case(N, is_real, dtype, k_power, seed=1):
     K = (len(kx), len(ky), len(kz))
     fk = (rng.standard_normal(K) + 1j * rng.standard_normal(K)).astype(cd)
     dk = np.array([0.3, 0.41, 0.37])
-    bw = dk.min()
+    bw = dk.min() * bw_scale
     kv = np.meshgrid(kx, ky, kz, indexing="ij")
     kmag = np.sqrt(sum((d * k.astype(np.float64))**2 for d, k in zip(dk, kv)))
     nb = int(kmag.max() / bw + .5) + 1
@@ -72,25 +74,33 @@ def _spectrum_case(N, is_real, dtype, k_power, seed=1):
                 nyq=N[2] / 2)
 
 
-@pytest.mark.parametrize("N, is_real, dtype, k_power, copies, use_shared, blocks", [
-    ((16, 12, 20), 1, "f64", 3, 8, 1, 5),        # r2c, per-warp copies
-    ((16, 12, 20), 0, "f64", 3, 3, 1, 7),        # c2c (|k| not monotone along z), 3 copies
-    ((8, 20, 70), 1, "f32", 2.5, 1, 1, 3),       # complex64, pow(), Kz = 36 (one tail chunk)
-    ((8, 20, 140), 0, "f64", 0, 8, 0, 4),        # global atomics only, Kz > 64 + tail
-    ((4, 9, 66), 1, "f64", 1, 2, 1, 100),        # more CTAs than row groups, Ky % 8 != 0
+@pytest.mark.parametrize("N, is_real, dtype, k_power, bw_scale, blocks", [
+    ((16, 12, 20), 1, "f64", 3, 1.0, 5),         # r2c, per-warp copies
+    ((16, 12, 20), 0, "f64", 3, 1.0, 7),         # c2c (|k| not monotone along z)
+    ((8, 20, 70), 1, "f32", 2.5, 1.0, 3),        # complex64, pow(), Kz = 36 (one tail chunk)
+    ((8, 20, 140), 0, "f64", 0, 0.001, 4),       # ~10^4 bins: global atomics only, Kz > 64
+    ((4, 9, 66), 1, "f64", 1, 0.05, 100),        # 2 copies; more CTAs than row groups
+    ((4, 9, 66), 1, "f64", 1, 1.0, 0),           # automatic grid (4 CTAs per "SM")
 ])
-def test_bin_power_kernel_on_host(N, is_real, dtype, k_power, copies, use_shared, blocks):
+def test_bin_power_kernel_on_host(N, is_real, dtype, k_power, bw_scale, blocks):
+    """csrc/diag_kernels.cuh (kernel + launch set-up) behind the psb_bin_power struct."""
+    from pystella_b200 import _lib
     src = open(os.path.join(EMU, "emu_diag.cpp")).read()
     lib = build_emu(src, "emu_diag")
-    c = _spectrum_case(N, is_real, dtype, k_power)
+    c = _spectrum_case(N, is_real, dtype, k_power, bw_scale=bw_scale)
     out = np.zeros(c["nb"])
-    lib.emu_bin_power(
-        C.c_int(dtype == "f64"), _ptr(c["fk"]), _ptr(c["kx"]), _ptr(c["ky"]), _ptr(c["kz"]),
-        C.c_longlong(c["K"][0]), C.c_longlong(c["K"][1]), C.c_longlong(c["K"][2]),
-        c["dk"].ctypes.data_as(C.POINTER(C.c_double)), C.c_double(c["bw"]),
-        C.c_double(k_power), C.c_double(c["nyq"]), C.c_int(c["nb"]), C.c_int(is_real),
-        C.c_int(copies), C.c_int(use_shared), C.c_int(blocks),
-        out.ctypes.data_as(C.POINTER(C.c_double)))
+    a = _lib.BinPowerArgs()
+    a.dtype = _lib.PSB_F64 if dtype == "f64" else _lib.PSB_F32
+    a.is_real = is_real
+    a.Kx, a.Ky, a.Kz = c["K"]
+    a.fk, a.momenta_x, a.momenta_y, a.momenta_z = (x.ctypes.data for x in
+                                                   (c["fk"], c["kx"], c["ky"], c["kz"]))
+    for mu in range(3):
+        a.dk[mu] = c["dk"][mu]
+    a.bin_width, a.k_power, a.nyquist = c["bw"], k_power, c["nyq"]
+    a.num_bins, a.tune_blocks = c["nb"], blocks
+    a.spectrum = out.ctypes.data
+    assert lib.emu_psb_bin_power(C.byref(a), C.c_int(2)) == 0
     assert np.max(np.abs(out - c["ref"])) <= 1e-13 * np.max(np.abs(c["ref"]))
 
 

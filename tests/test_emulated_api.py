@@ -1,0 +1,149 @@
+"""
+The public API of the diagnostics and stencil maps driven END TO END on host tensors: the
+product's own launch code (marshalling, layout inference, grid sizes) with the CUDA libraries
+replaced by the CPU execution model of the same kernel sources (tests/emu_device.py).  What
+remains for the GPU box (tests/test_zz_gpu_diagnostics.py) is the hardware: NVRTC's code for
+sm_100a, real atomics, launch limits.
+"""
+import numpy as np
+import pytest
+import torch
+
+import pystella_b200 as ps
+from emu_device import NUM_SMS, emulated_device
+from pystella_b200.field import var
+
+
+def test_histogrammer_through_the_emulated_device(monkeypatch):
+    """test/test_histogram.py of the reference: two histograms sharing a bin expression."""
+    rng = np.random.default_rng(15)
+    grid, num_bins = (5, 9, 40), 23
+    decomp = ps.DomainDecomposition((1, 1, 1), 0, grid_shape=grid)
+    _fx = ps.Field("fx")
+    hist = ps.Histogrammer(decomp, {"count": (var("abs")(_fx) * num_bins, 1),
+                                    "squared": (var("abs")(_fx) * num_bins, _fx**2)},
+                           num_bins, "float64", rank_shape=grid)
+    fx = rng.random(grid)
+    with emulated_device(monkeypatch) as dev:
+        out = hist(None, fx=torch.from_numpy(fx))
+    assert len(dev.jit.launches) == 1          # both histograms: one kernel, one pass
+    name, g, b, smem = dev.jit.launches[0]
+    assert b == (32, 8, 1) and g == (min(4 * NUM_SMS, 5 * 2), 1, 1)
+    idx = np.floor(np.abs(fx) * num_bins).astype(int).reshape(-1)
+    assert np.array_equal(out["count"], np.bincount(idx, minlength=num_bins))
+    assert np.allclose(out["squared"],
+                       np.bincount(idx, weights=fx.reshape(-1)**2, minlength=num_bins),
+                       rtol=1e-13)
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+def test_field_histogrammer_through_the_emulated_device(monkeypatch, dtype):
+    rng = np.random.default_rng(16)
+    grid, h, num_bins = (4, 6, 37), 2, 11
+    decomp = ps.DomainDecomposition((1, 1, 1), h, grid_shape=grid)
+    fh = ps.FieldHistogrammer(decomp, num_bins, "float64", halo_shape=h)
+    pad = tuple(n + 2 * h for n in grid)
+    f = (rng.random((2,) + pad) * 4.2 - 1.2).astype(dtype)
+    with emulated_device(monkeypatch) as dev:
+        res = fh(torch.from_numpy(f))
+    assert len(dev.jit.launches) == 2          # one kernel per outer index
+    for s in range(2):
+        fi = f[s][h:-h, h:-h, h:-h]
+        assert res["linear_bins"][s][0] == fi.min() and res["linear_bins"][s][-1] == fi.max()
+        assert np.isclose(res["log_bins"][s][-1], np.abs(fi).max(), rtol=1e-14)
+        assert np.isclose(res["log_bins"][s][0], np.abs(fi).min(), rtol=1e-13)
+        assert res["linear"][s].sum() == np.prod(grid) == res["log"][s].sum()
+        np_res = np.histogram(fi, bins=res["linear_bins"][s])[0]
+        assert np.sum(np.abs(res["linear"][s] - np_res)) <= 4
+        np_log = np.histogram(np.abs(fi), bins=res["log_bins"][s])[0]
+        assert np.sum(np.abs(res["log"][s] - np_log)) <= 4
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+def test_power_spectra_through_the_emulated_device(monkeypatch, dtype):
+    """PowerSpectra.__call__ / bin_power: the kernel path == the per-mode tables of the host
+    path (pystella/fourier/spectra.py:132-215), r2c layout, anisotropic box."""
+    rng = np.random.default_rng(14)
+    grid, h = (8, 6, 20), 1
+    decomp = ps.DomainDecomposition((1, 1, 1), h, grid_shape=grid)
+    fft = ps.DFT(decomp, None, None, grid, dtype, backend="fftw")
+    L = (5., 6., 7.)
+    dk = tuple(2 * np.pi / Li for Li in L)
+    spectra = ps.PowerSpectra(decomp, fft, dk, float(np.prod(L)))
+    fx = rng.random(tuple(n + 2 * h for n in grid)).astype(dtype)
+    ref = spectra(fx, k_power=2)                          # host tables
+    fk = fft.dft(fx).clone()
+    with emulated_device(monkeypatch):
+        got = spectra(fx, k_power=2)
+        got_frac = spectra.bin_power(fk, k_power=1.5)
+    ok = np.isfinite(ref)
+    rtol = 1e-12 if dtype == "float64" else 2e-5
+    assert np.allclose(got[ok], ref[ok], rtol=rtol)
+    ref_frac = spectra.bin_power(fk, k_power=1.5)
+    assert np.allclose(got_frac[ok], ref_frac[ok], rtol=rtol)
+
+
+@pytest.mark.parametrize("cls", ["Stencil", "StreamingStencil"])
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+def test_stencil_call_through_the_emulated_device(monkeypatch, cls, dtype):
+    """test/test_stencil.py:36-90 with the reference's call; `x` staged in shared memory."""
+    rng = np.random.default_rng(9)
+    h, N = 2, (19, 11, 70)
+    x, y = var("x"), var("y")
+    i, j, k = var("i"), var("j"), var("k")
+    map_dict = {y[i, j, k]: (x[i + h + h, j + h, k + h] + x[i + h, j + h + h, k + h]
+                             + x[i + h, j + h, k + h + h] + x[i - h + h, j + h, k + h]
+                             + x[i + h, j - h + h, k + h] + x[i + h, j + h, k - h + h])}
+    stencil_map = getattr(ps, cls)(map_dict, h, prefetch_args=["x"], dtype=dtype)
+    x_h = rng.random(tuple(n + 2 * h for n in N)).astype(dtype)
+    y_t = torch.zeros(N, dtype=getattr(torch, dtype))
+    with emulated_device(monkeypatch) as dev:
+        stencil_map(None, x=torch.from_numpy(x_h), y=y_t)
+        name, g, b, smem = dev.jit.launches[-1]
+        assert b == (64, 4, 1) and g == (2, 2, 2) and smem == stencil_map._generic.ksrc.smem_bytes
+        with pytest.raises(ValueError, match="outside its padding"):
+            stencil_map(None, x=torch.from_numpy(np.ascontiguousarray(x_h[1:-1, 1:-1, 1:-1])),
+                        y=torch.zeros(tuple(n + 2 for n in N), dtype=getattr(torch, dtype)))
+    y_true = (x_h[2*h:, h:-h, h:-h] + x_h[h:-h, 2*h:, h:-h] + x_h[h:-h, h:-h, 2*h:]
+              + x_h[:-2*h, h:-h, h:-h] + x_h[h:-h, :-2*h, h:-h] + x_h[h:-h, h:-h, :-2*h])
+    tol = 5e-14 if dtype == "float64" else 1e-5
+    assert np.max(np.abs(y_t.numpy() - y_true)) <= tol * np.max(np.abs(y_true))
+
+
+def test_elementwise_map_call_through_the_emulated_device(monkeypatch):
+    """The generic ElementWiseMap launch path (GenericMap.__call__) on the same harness."""
+    rng = np.random.default_rng(2)
+    N, h = (3, 5, 70), 1
+    f = ps.Field("f", offset="h")
+    out = ps.Field("out", offset=0)
+    m = ps.ElementWiseMap({out: var("c") * f**2 + 1}, halo_shape=h)
+    f_h = rng.random(tuple(n + 2 * h for n in N))
+    o = torch.zeros(N, dtype=torch.float64)
+    with emulated_device(monkeypatch):
+        m(None, f=torch.from_numpy(f_h), out=o, c=2.5)
+    assert np.allclose(o.numpy(), 2.5 * f_h[h:-h, h:-h, h:-h]**2 + 1, rtol=1e-15)
+
+
+def test_bench_diagnostics_record_on_the_emulated_device(monkeypatch, capsys):
+    """bench.py --diagnostics (the extras record that times the new kernels on the GPU box)
+    executed on a 16^3 lattice of host tensors: every section reports ok."""
+    import importlib
+    import os
+    import sys
+    import types
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    bench = importlib.import_module("bench")
+
+    def timed(fn, reps=1, warm=0):
+        fn()
+        return 1.0
+
+    with emulated_device(monkeypatch):
+        rec = bench.run_diagnostics(types.SimpleNamespace(grid=16), dev=torch.device("cpu"),
+                                    timed=timed, dft_backend="fftw")
+    capsys.readouterr()
+    for name in ("field_histogram", "bin_power", "stencil_map"):
+        assert "error" not in rec[name], rec[name]
+        assert rec[name]["ok"] is True, rec[name]
+    assert rec["field_histogram"]["sites_counted"] == [16.**3, 16.**3]
+    assert rec["bin_power"]["kshape"] == [16, 16, 9]
