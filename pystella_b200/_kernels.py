@@ -282,21 +282,22 @@ def bin_power(fk, momenta, dk, bin_width, k_power, nyquist, num_bins, is_real,
     args.dtype, args.is_real = code, int(bool(is_real))
     args.Kx, args.Ky, args.Kz = fk.shape
     args.fk = fk.data_ptr()
+    stream_ctx = torch.cuda.stream(queue) if queue is not None else contextlib.nullcontext()
     keep = []
-    for name, m, n in zip(("momenta_x", "momenta_y", "momenta_z"), momenta, fk.shape):
-        _lib.require_cuda_tensor(m, name)
-        if m.dtype != rdtype:
-            m = m.to(rdtype)
-            keep.append(m)
-        if m.numel() != n:
-            raise ValueError(f"{name} has {m.numel()} entries, fk has extent {n}")
-        setattr(args, name, m.data_ptr())
+    with stream_ctx:       # temporaries are allocated on the stream the kernel runs on
+        for name, m, n in zip(("momenta_x", "momenta_y", "momenta_z"), momenta, fk.shape):
+            _lib.require_cuda_tensor(m, name)
+            if m.dtype != rdtype:
+                m = m.to(rdtype)
+                keep.append(m)
+            if m.numel() != n:
+                raise ValueError(f"{name} has {m.numel()} entries, fk has extent {n}")
+            setattr(args, name, m.data_ptr())
+        spectrum = torch.zeros(int(num_bins), dtype=torch.float64, device=fk.device)
     for mu in range(3):
         args.dk[mu] = float(dk[mu])
     args.bin_width, args.k_power, args.nyquist = float(bin_width), float(k_power), float(nyquist)
     args.num_bins, args.tune_blocks = int(num_bins), int(blocks)
-    with torch.cuda.stream(queue) if queue is not None else contextlib.nullcontext():
-        spectrum = torch.zeros(int(num_bins), dtype=torch.float64, device=fk.device)
     args.spectrum = spectrum.data_ptr()
     rc = lib.psb_bin_power(C.byref(args), _lib.stream_ptr(queue))
     _lib.check(lib, rc, "psb_bin_power")

@@ -363,8 +363,9 @@ def generate_stencil_kernel(map_instructions, tmp_instructions=None, dtype="doub
         p["ex"] = p["hi"][0] - p["lo"][0] + 1
         p["ey"] = TYT + p["hi"][1] - p["lo"][1]
         p["ez"] = TILE_TZ + p["hi"][2] - p["lo"][2]
+        p["ns"] = p["ex"] + 1             # ring slots: the planes in use + the one in flight
         p["off"] = off
-        off += p["ex"] * p["ey"] * p["ez"]
+        off += p["ns"] * p["ey"] * p["ez"]
         off = (off + 3) // 4 * 4                      # keep 16-byte alignment of the rings
     smem_bytes = off * S
     if smem_bytes > TILE_SMEM_LIMIT:
@@ -390,6 +391,20 @@ def generate_stencil_kernel(map_instructions, tmp_instructions=None, dtype="doub
         f"#define TY {TILE_TY}",
         f"#define RY {TILE_RY}",
         "#define TYT (TY * RY)",
+        "// asynchronous global -> shared copies (LDGSTS): the next plane is in flight while",
+        "// the current one is evaluated; plain copies under the CPU execution model",
+        "#ifdef PSB_CUDA_EMU",
+        "#define PSB_CP_ASYNC(dst, src) (*(dst) = *(src))",
+        "#define PSB_CP_WAIT() ((void)0)",
+        "#else",
+        "__device__ __forceinline__ void psb_cp_async(T* dst, const T* src) {",
+        "  const unsigned d = (unsigned)__cvta_generic_to_shared(dst);",
+        f'  asm volatile("cp.async.ca.shared.global [%0], [%1], {S};" ::"r"(d), "l"(src) '
+        ': "memory");',
+        "}",
+        "#define PSB_CP_ASYNC(dst, src) psb_cp_async((dst), (src))",
+        '#define PSB_CP_WAIT() asm volatile("cp.async.wait_all;" ::: "memory")',
+        "#endif",
         f'extern "C" __global__ void __launch_bounds__({TILE_TZ * TILE_TY}) {name}'
         "(const psb_jit_args args) {",
         "  const long long Nx = args.Nx, Ny = args.Ny, Nz = args.Nz;",
@@ -416,29 +431,36 @@ def generate_stencil_kernel(map_instructions, tmp_instructions=None, dtype="doub
         else:
             ox, oy, oz = (f"(args.halos[{s_}] + ({v}))" for v in p["lo"])
         lines += [
-            f"  // ring of '{p['name']}': {p['ex']} planes of {p['ey']} x {p['ez']}",
+            f"  // ring of '{p['name']}': {p['ns']} slots ({p['ex']} planes in use + 1 in "
+            f"flight) of {p['ey']} x {p['ez']}",
             f"  T* const ring{n} = smem + {p['off']};",
             f"  const T* const src{n} = (const T*)args.arrays[{s_}];",
             f"  const long long py{n} = Ny + 2 * args.halos[{s_}], "
             f"pz{n} = Nz + 2 * args.halos[{s_}];",
             f"  const long long ox{n} = {ox}, oy{n} = j0 + {oy}, oz{n} = z0 + {oz};",
             f"#define LOAD_PLANE{n}(c) do {{ \\",
-            f"    T* const dst_ = ring{n} + ((c) % {p['ex']}) * {p['ey'] * p['ez']}; \\",
+            f"    T* const dst_ = ring{n} + ((c) % {p['ns']}) * {p['ey'] * p['ez']}; \\",
             f"    const T* const row_ = src{n} + (i0 + (c) + ox{n}) * py{n} * pz{n}; \\",
             f"    for (int e_ = tid; e_ < {p['ey'] * p['ez']}; e_ += TZ * TY) {{ \\",
             f"      const int jj_ = e_ / {p['ez']}, kk_ = e_ - jj_ * {p['ez']}; \\",
             f"      const long long pj_ = oy{n} + jj_, pk_ = oz{n} + kk_; \\",
-            f"      if (pj_ < py{n} && pk_ < pz{n}) dst_[e_] = row_[pj_ * pz{n} + pk_]; \\",
+            f"      if (pj_ < py{n} && pk_ < pz{n}) "
+            f"PSB_CP_ASYNC(dst_ + e_, row_ + pj_ * pz{n} + pk_); \\",
             "    } } while (0)",
-            f"  for (int c = 0; c < {p['ex'] - 1}; ++c) LOAD_PLANE{n}(c);",
+            f"  for (int c = 0; c < {p['ex']}; ++c) LOAD_PLANE{n}(c);",
         ]
-    lines += ["  // q: plane counter within the chunk (int: cheap ring arithmetic)",
-              "  for (int q = 0; q < (int)(i1 - i0); ++q) {",
-              "    const long long i = i0 + q;"]
+    lines += ["  PSB_CP_WAIT();",
+              "  __syncthreads();",
+              "  // q: plane counter within the chunk (int: cheap ring arithmetic)",
+              "  const int nq = (int)(i1 - i0);",
+              "  for (int q = 0; q < nq; ++q) {",
+              "    const long long i = i0 + q;",
+              "    if (q + 1 < nq) {        // the plane step q + 1 adds, into the slot step "
+              "q - 1 released"]
     for n, p in enumerate(prefetch):
-        lines.append(f"    LOAD_PLANE{n}(q + {p['ex'] - 1});")
+        lines.append(f"      LOAD_PLANE{n}(q + {p['ex']});")
     lines += [
-        "    __syncthreads();",
+        "    }",
         "    #pragma unroll",
         "    for (int r = 0; r < RY; ++r) {",
         "      const int jl = ty + TY * r;",
@@ -453,7 +475,7 @@ def generate_stencil_kernel(map_instructions, tmp_instructions=None, dtype="doub
         if info["var"] in in_tile:
             n, p = in_tile[info["var"]]
             dx, dy, dz = si - p["lo"][0], sj - p["lo"][1], sk - p["lo"][2]
-            lines.append(f"        T {info['var']} = ring{n}[((q + {dx}) % {p['ex']}) * "
+            lines.append(f"        T {info['var']} = ring{n}[((q + {dx}) % {p['ns']}) * "
                          f"{p['ey'] * p['ez']} + (jl + {dy}) * {p['ez']} + (tx + {dz})];")
         elif info["read"]:
             lines.append(f"        T {info['var']} = {addr};")
@@ -463,7 +485,10 @@ def generate_stencil_kernel(map_instructions, tmp_instructions=None, dtype="doub
     for info in refs.values():
         if info["written"]:
             lines.append(f"        {info['addr']} = {info['var']};")
-    lines += ["      }", "    }", "    __syncthreads();", "  }"]
+    lines += ["      }", "    }",
+              "    PSB_CP_WAIT();           // the plane in flight has landed ...",
+              "    __syncthreads();         // ... for everybody, and step q's reads are done",
+              "  }"]
     for n in range(len(prefetch)):
         lines.append(f"#undef LOAD_PLANE{n}")
     lines.append("}")
@@ -472,6 +497,10 @@ def generate_stencil_kernel(map_instructions, tmp_instructions=None, dtype="doub
                      and not any(info["ref"].shift)})
     ksrc = KernelSource("\n".join(lines) + "\n", name, slots, scalars, dtype, domain)
     ksrc.smem_bytes = smem_bytes
+    written_slots = {info["slot"] for info in refs.values() if info["written"]}
+    #: running the map twice gives the same result (no array is both read and written)
+    ksrc.idempotent = not any(info["read"] and info["slot"] in written_slots
+                              for info in refs.values())
     ksrc.prefetch = [dict(name=p["name"], slot=p["slot"], absolute=p["absolute"],
                           lo=tuple(p["lo"]), hi=tuple(p["hi"])) for p in prefetch]
     return ksrc

@@ -96,9 +96,14 @@ class Stencil(ElementWiseMap):
     (``pystella/stencil.py:36-98``): an element-wise map whose statements read neighbouring
     sites.  The reference stages ``prefetch_args`` in local memory; so does the generated
     kernel here (``codegen.generate_stencil_kernel``: a ring of x planes of the stencil's
-    bounding box in shared memory per named array, a CTA streaming along x), arrays not
-    named are read through L1/L2.  ``tile=False`` (or an empty ``prefetch_args``) selects the
-    direct kernel for every array.  The hand-written stencil kernels are
+    bounding box in shared memory per named array, filled with asynchronous copies while the
+    CTA streams along x), arrays not named are read through L1/L2.  ``tile=False`` (or an
+    empty ``prefetch_args``) selects the direct kernel for every array.
+
+    Both kernels evaluate the same statements; when the map is idempotent (no array is both
+    read and written) the first call times each of them on the caller's arrays (3 launches
+    each, CUDA events on the launch stream) and keeps the faster one (``autotune=False``:
+    always the shared-memory kernel).  The hand-written stencil kernels are
     :class:`FiniteDifferencer` and :class:`FusedStencilStage`.
     As a ``MapKernel`` class it behaves like :class:`ElementWiseMap`.
     """
@@ -107,21 +112,59 @@ class Stencil(ElementWiseMap):
         self.prefetch_args = kwargs.pop("prefetch_args", [])
         kwargs.pop("lsize", None)
         tile = kwargs.pop("tile", True)
+        autotune = kwargs.pop("autotune", True)
         if map_instructions is not None and halo_shape is None:
             raise TypeError("Stencil requires halo_shape")
         tiled_kwargs = dict(kwargs)
         super().__init__(map_instructions, halo_shape=halo_shape, **kwargs)
+        self._candidates = None
+        self.tuning = None               # {"tiled": ms, "direct": ms, "chosen": name}
         if self._generic is not None and tile and self.prefetch_args:
             from pystella_b200.codegen import TiledStencilMap
             try:
-                self._generic = TiledStencilMap(
+                tiled = TiledStencilMap(
                     map_instructions, tiled_kwargs.get("tmp_instructions"),
                     dtype=tiled_kwargs.get("dtype") or "float64", halo_shape=halo_shape,
                     rank_shape=tiled_kwargs.get("rank_shape"),
                     prefetch_args=self.prefetch_args)
             except (NotImplementedError, ValueError):
-                pass        # tiles larger than shared memory / nothing to stage: keep
+                return      # tiles larger than shared memory / nothing to stage: keep
                 #             the direct kernel
+            if autotune and tiled.ksrc.idempotent:
+                self._candidates = {"tiled": tiled, "direct": self._generic}
+            self._generic = tiled
+
+    def _autotune(self, queue, kwargs):
+        """Time both kernels on the caller's arrays; -> the faster one."""
+        import torch
+        candidates, self._candidates = self._candidates, None
+        if not torch.cuda.is_available() or torch.cuda.is_current_stream_capturing():
+            return
+        stream = queue if queue is not None else torch.cuda.current_stream()
+        times = {}
+        try:
+            for name, kern in candidates.items():
+                kern(queue, **kwargs)                       # compile + first launch
+                a = torch.cuda.Event(enable_timing=True)
+                b = torch.cuda.Event(enable_timing=True)
+                a.record(stream)
+                for _ in range(3):
+                    kern(queue, **kwargs)
+                b.record(stream)
+                b.synchronize()
+                times[name] = a.elapsed_time(b) / 3
+        except (ValueError, TypeError):
+            raise                                           # the caller's arguments
+        except Exception:  # noqa: BLE001
+            return                                          # keep the shared-memory kernel
+        best = min(times, key=times.get)
+        self._generic = candidates[best]
+        self.tuning = dict(times, chosen=best)
+
+    def __call__(self, queue=None, filter_args=False, **kwargs):
+        if self._candidates is not None:
+            self._autotune(queue, kwargs)
+        return super().__call__(queue, filter_args=filter_args, **kwargs)
 
 
 class StreamingStencil(Stencil):

@@ -147,3 +147,52 @@ def test_bench_diagnostics_record_on_the_emulated_device(monkeypatch, capsys):
         assert rec[name]["ok"] is True, rec[name]
     assert rec["field_histogram"]["sites_counted"] == [16.**3, 16.**3]
     assert rec["bin_power"]["kshape"] == [16, 16, 9]
+
+
+def test_stencil_autotune_keeps_the_faster_kernel(monkeypatch):
+    """Stencil's first call times the shared-memory and the direct kernel (idempotent maps
+    only) and keeps the faster one; in-place maps are never run twice."""
+    import time
+    import types
+
+    class FakeEvent:
+        def __init__(self, enable_timing=False):
+            self.t = None
+
+        def record(self, stream=None):
+            self.t = time.perf_counter()
+
+        def synchronize(self):
+            pass
+
+        def elapsed_time(self, other):
+            return (other.t - self.t) * 1e3
+
+    rng = np.random.default_rng(4)
+    h, N = 1, (4, 8, 64)
+    x, y = var("x"), var("y")
+    i, j, k = var("i"), var("j"), var("k")
+    md = {y[i, j, k]: x[i + h + h, j + h, k + h] - x[i, j + h, k + h]}
+    st = ps.Stencil(md, h, prefetch_args=["x"])
+    assert set(st._candidates) == {"tiled", "direct"}
+    x_h = rng.random(tuple(n + 2 * h for n in N))
+    y_t = torch.zeros(N, dtype=torch.float64)
+    with emulated_device(monkeypatch) as dev:
+        monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+        monkeypatch.setattr(torch.cuda, "is_current_stream_capturing", lambda: False)
+        monkeypatch.setattr(torch.cuda, "current_stream", lambda: types.SimpleNamespace())
+        monkeypatch.setattr(torch.cuda, "Event", FakeEvent)
+        st(None, x=torch.from_numpy(x_h), y=y_t)
+        assert st._candidates is None and st.tuning["chosen"] in ("tiled", "direct")
+        assert len(dev.jit.launches) == 2 * 4 + 1      # (1 + 3) launches each, then the call
+        assert st._generic is {"tiled": st._generic, "direct": st._generic}[st.tuning["chosen"]]
+    assert np.allclose(y_t.numpy(), x_h[2*h:, h:-h, h:-h] - x_h[:-2*h, h:-h, h:-h], rtol=1e-15)
+
+    # an in-place map (y read and written) must not be autotuned
+    f = ps.Field("f", offset="h")
+    acc = ps.Field("acc", offset=0)
+    from pystella_b200.field import shift_fields
+    st2 = ps.Stencil({acc: acc + shift_fields(f, (1, 0, 0))}, h, prefetch_args=["f"])
+    assert st2._candidates is None
+    from pystella_b200.codegen import TiledStencilMap
+    assert isinstance(st2._generic, TiledStencilMap) and not st2._generic.ksrc.idempotent

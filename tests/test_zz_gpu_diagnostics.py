@@ -228,7 +228,8 @@ def test_tiled_stencil_map(cls, dtype, h, N):
     shared memory (tails in y and z, several x chunks)."""
     from pystella_b200.codegen import TiledStencilMap
     rng = np.random.default_rng(16)
-    stencil_map = getattr(ps, cls)(_six_point(h), h, prefetch_args=["x"], dtype=dtype)
+    stencil_map = getattr(ps, cls)(_six_point(h), h, prefetch_args=["x"], dtype=dtype,
+                                   autotune=False)
     assert isinstance(stencil_map._generic, TiledStencilMap)
     x_h = rng.random(tuple(n + 2 * h for n in N)).astype(dtype)
     yd = torch.zeros(N, dtype=getattr(torch, dtype), device="cuda")
@@ -249,9 +250,17 @@ def test_tiled_stencil_equals_direct_kernel_at_config_size():
                    generator=gen)
     y_tile = torch.zeros(N, dtype=torch.float64, device="cuda")
     y_direct = torch.zeros_like(y_tile)
-    ps.Stencil(_six_point(h), h, prefetch_args=["x"])(None, x=x, y=y_tile)
+    ps.Stencil(_six_point(h), h, prefetch_args=["x"], autotune=False)(None, x=x, y=y_tile)
     ps.Stencil(_six_point(h), h, prefetch_args=["x"], tile=False)(None, x=x, y=y_direct)
     assert torch.equal(y_tile, y_direct)
+    # the default: the first call times both kernels on these arrays and keeps the faster
+    tuned = ps.Stencil(_six_point(h), h, prefetch_args=["x"])
+    y_tuned = torch.zeros_like(y_tile)
+    tuned(None, x=x, y=y_tuned)
+    assert tuned.tuning["chosen"] in ("tiled", "direct") and tuned._candidates is None
+    assert tuned.tuning["tiled"] > 0 and tuned.tuning["direct"] > 0
+    tuned(None, x=x, y=y_tuned)
+    assert torch.equal(y_tuned, y_direct)
     c = slice(h, -h)
     ref = ((((x[2*h:, c, c] + x[c, 2*h:, c]) + x[c, c, 2*h:]) + x[:-2*h, c, c])
            + x[c, :-2*h, c]) + x[c, c, :-2*h]
