@@ -72,6 +72,18 @@ def init_rayleigh(p, decomp, f, dfdt, f0, potential, energy, expand, backend=Non
     return eff_mass
 
 
+def make_rho_diagnostics(decomp, scalar_sector, mpl, halo_shape, rank_shape, dtype):
+    """The reference example's energy-density diagnostics (lines 139-146): a
+    FieldHistogrammer with 1000 bins and the element-wise map
+    ``rho = T_00 / (3 mpl^2 hubble^2 / 8 pi)`` (conformal-time quantities)."""
+    hist = ps.FieldHistogrammer(decomp, 1000, dtype, rank_shape=rank_shape)
+    a_sq_rho = 3 * mpl**2 * ps.Field("hubble", indices=[])**2 / 8 / np.pi
+    rho_dict = {ps.Field("rho"): scalar_sector.stress_tensor(0, 0) / a_sq_rho}
+    compute_rho = ps.ElementWiseMap(rho_dict, halo_shape=halo_shape, rank_shape=rank_shape,
+                                    dtype=dtype)
+    return hist, compute_rho
+
+
 def make_potential(p):
     def potential(f):
         phi, chi = f[0], f[1]
@@ -174,8 +186,8 @@ def main(argv=None):
         if p.gravitational_waves:
             derivs(None, fx=hij, lap=lap_hij)
 
-    # output as in the reference example (lines 135-190), minus the rho histogram
-    out = spectra = projector = None
+    # output as in the reference example (lines 131-190)
+    out = spectra = projector = hist = compute_rho = None
     if p.output is not None:
         if decomp.rank == 0:
             out = ps.OutputFile(name=p.output, runfile=__file__, grid_shape=p.grid_shape,
@@ -186,6 +198,8 @@ def main(argv=None):
             fft_out = ps.DFT(decomp, None, None, p.grid_shape, p.dtype)
             spectra = ps.PowerSpectra(decomp, fft_out, dk, float(np.prod(p.box_dim)))
             projector = ps.Projector(fft_out, h, dk, p.dx)
+            hist, compute_rho = make_rho_diagnostics(decomp, scalar_sector, p.mpl, h,
+                                                     rank_shape, p.dtype)
     a_last_spec = [.1]
 
     def output(t, a, hubble, energy, constraint):
@@ -197,10 +211,19 @@ def main(argv=None):
             out.output("statistics/f", t=t, a=a, **f_stats)
         if spectra is not None and a / a_last_spec[0] >= 1.05:
             a_last_spec[0] = a
-            spec_out = {"scalar": spectra(f)}
+            # energy density in units of the critical density, its histogram and spectrum
+            # (reference lines 155-163, 171)
+            if not p.gravitational_waves:
+                derivs(None, fx=f, grd=dfdx)
+            rho = torch.empty(rank_shape, dtype=dtype, device=device)
+            compute_rho(None, a=np.array(a), hubble=np.array(hubble), rho=rho, f=f,
+                        dfdt=dfdt, dfdx=dfdx)
+            rho_hist = hist(rho)
+            spec_out = {"scalar": spectra(f), "rho": spectra(rho)}
             if p.gravitational_waves:
                 spec_out["gw"] = spectra.gw(dhijdt, projector, hubble)
             if out is not None:
+                out.output("rho_histogram", t=t, a=a, **rho_hist)
                 out.output("spectra", t=t, a=a, **spec_out)
 
     t, step_count = 0., 0

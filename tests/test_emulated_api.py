@@ -196,3 +196,45 @@ def test_stencil_autotune_keeps_the_faster_kernel(monkeypatch):
     assert st2._candidates is None
     from pystella_b200.codegen import TiledStencilMap
     assert isinstance(st2._generic, TiledStencilMap) and not st2._generic.ksrc.idempotent
+
+
+def test_example_rho_diagnostics_through_the_emulated_device(monkeypatch):
+    """examples/scalar_preheating.py (reference lines 139-163): rho = T_00 / (3 mpl^2 H^2 /
+    8 pi) through a generated ElementWiseMap, then its FieldHistogrammer -- the example's
+    own construction, executed on host tensors."""
+    import importlib.util
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                        "examples", "scalar_preheating.py")
+    spec = importlib.util.spec_from_file_location("example_scalar_preheating", path)
+    example = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(example)
+
+    rng = np.random.default_rng(8)
+    grid, h, ns = (4, 8, 40), 2, 2
+    p = example.parser.parse_args([])
+    decomp = ps.DomainDecomposition((1, 1, 1), h, grid_shape=grid)
+    sector = ps.ScalarSector(ns, potential=example.make_potential(p))
+    hist, compute_rho = example.make_rho_diagnostics(decomp, sector, p.mpl, h, grid, "float64")
+    pad = tuple(n + 2 * h for n in grid)
+    f = 0.2 + 0.05 * rng.standard_normal((ns,) + pad)
+    dfdt = -0.1 + 0.05 * rng.standard_normal((ns,) + pad)
+    dfdx = 0.05 * rng.standard_normal((ns, 3) + grid)
+    a, hubble = 1.3, 0.41
+    rho = torch.zeros(grid, dtype=torch.float64)
+    with emulated_device(monkeypatch):
+        compute_rho(None, a=np.array(a), hubble=np.array(hubble), rho=rho,
+                    f=torch.from_numpy(f), dfdt=torch.from_numpy(dfdt),
+                    dfdx=torch.from_numpy(dfdx))
+        res = hist(rho)
+    fi = f[:, h:-h, h:-h, h:-h]
+    di = dfdt[:, h:-h, h:-h, h:-h]
+    # T_00 = sum_n dfdt_n^2 + g_00 L,  L = -kinetic/2 - V,  g_00 = -a^2
+    kinetic = sum(-di[n]**2 / a**2 + (dfdx[n]**2).sum(axis=0) / a**2 for n in range(ns))
+    V = example.make_potential(p)([fi[0], fi[1]])
+    T00 = (di**2).sum(axis=0) - a**2 * (-kinetic / 2 - V)
+    ref = T00 / (3 * p.mpl**2 * hubble**2 / 8 / np.pi)
+    assert np.allclose(rho.numpy(), ref, rtol=1e-13)
+    assert res["linear"].sum() == np.prod(grid) == res["log"].sum()
+    assert res["linear"].shape == (1000,) and res["linear_bins"].shape == (1001,)
+    assert np.sum(np.abs(res["linear"] - np.histogram(ref, bins=res["linear_bins"])[0])) <= 4
