@@ -341,3 +341,86 @@ def test_tiled_stencil_compiles_for_sm_100a(ctype, monkeypatch):
     assert codegen.JitLibrary.compile(ksrc) > 0
     assert codegen.TiledStencilMap.launch_grid((512, 512, 512), 148) == (8, 64, 8)
     assert codegen.TiledStencilMap.launch_grid((16, 12, 40), 148) == (1, 2, 2)
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_tiled_stencil_random_cases_on_host(seed):
+    """Randomised sweep: 1-3 input arrays with their own paddings, 2-5 random offsets each
+    (anywhere inside the padding, asymmetric bounding boxes), a random subset staged in shared
+    memory, random lattice extents (tails in y and z, short x), random number of x chunks;
+    two outputs, the second reading the first."""
+    from pystella_b200.field import shift_fields
+    rng = np.random.default_rng(1000 + seed)
+    dtype = "float64" if seed % 3 else "float32"
+    ctype = "double" if dtype == "float64" else "float"
+    N = (int(rng.integers(1, 9)), int(rng.integers(1, 20)), int(rng.integers(1, 140)))
+    narr = int(rng.integers(1, 4))
+    names = ["p", "q", "r"][:narr]
+    halos, fields, arrays, shifts = {}, {}, {}, {}
+    for nm in names:
+        H = int(rng.integers(1, 4))
+        halos[nm] = H
+        fields[nm] = Field(nm, offset=H)
+        arrays[nm] = rng.random(tuple(n + 2 * H for n in N)).astype(dtype)
+        shifts[nm] = [tuple(int(v) for v in rng.integers(-H, H + 1, 3))
+                      for _ in range(int(rng.integers(2, 6)))]
+    coef = {nm: [float(c) for c in rng.integers(1, 5, len(shifts[nm]))] for nm in names}
+    out1, out2 = Field("out1", offset=0), Field("out2", offset=0)
+    expr = 0
+    for nm in names:
+        for c, s in zip(coef[nm], shifts[nm]):
+            expr = expr + c * shift_fields(fields[nm], s)
+    maps = [(out1, expr * var("scale")), (out2, out1 - fields[names[0]])]
+    staged = [nm for nm in names if rng.random() < 0.7] or [names[0]]
+    ksrc = codegen.generate_stencil_kernel(maps, None, ctype, halo_shape=max(halos.values()),
+                                           prefetch_args=staged)
+    arrays.update(out1=np.zeros(N, dtype), out2=np.zeros(N, dtype))
+    halos.update(out1=0, out2=0)
+    scale = 0.5
+    gz = int(rng.integers(1, 4))
+    run_generated_stencil_on_host(ksrc, arrays, halos, {"scale": scale}, N, gz)
+
+    def view(a, H, s):
+        return a[tuple(slice(H + si, H + si + n) for si, n in zip(s, N))].astype(np.float64)
+    ref1 = sum(c * view(arrays[nm], halos[nm], s)
+               for nm in names for c, s in zip(coef[nm], shifts[nm])) * scale
+    ref2 = ref1 - view(arrays[names[0]], halos[names[0]], (0, 0, 0))
+    tol = 1e-13 if dtype == "float64" else 2e-5
+    scale1 = max(1.0, np.max(np.abs(ref1)))
+    assert np.max(np.abs(arrays["out1"] - ref1)) <= tol * scale1, (N, staged, shifts, gz)
+    assert np.max(np.abs(arrays["out2"] - ref2)) <= tol * scale1, (N, staged, shifts, gz)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_generated_histogram_random_cases_on_host(seed):
+    """Randomised sweep: 1-3 histograms over 1-2 arrays with different paddings, random
+    lattice extents, bin counts on both sides of the shared-memory limit, weights that are
+    constants or expressions; bins partly out of range."""
+    rng = np.random.default_rng(2000 + seed)
+    dtype = "float64" if seed % 2 else "float32"
+    ctype = "double" if dtype == "float64" else "float"
+    T = np.dtype(dtype).type
+    N = (int(rng.integers(1, 7)), int(rng.integers(1, 20)), int(rng.integers(1, 150)))
+    nb = int(rng.choice([3, 17, 100, 2500]))
+    Hf, Hg = int(rng.integers(0, 3)), int(rng.integers(0, 3))
+    f, g = Field("f", offset=Hf), Field("g", offset=Hg)
+    fa = rng.random(tuple(n + 2 * Hf for n in N)).astype(dtype)
+    ga = rng.random(tuple(n + 2 * Hg for n in N)).astype(dtype)
+    nh = int(rng.integers(1, 4))
+    s = T(nb * 1.3)
+    hists = [(f * var("s") - 2, 1), (g * var("s"), f + g), (f * g * var("s"), 2.5)][:nh]
+    ksrc = codegen.generate_histogram_kernel(hists, nb, ctype, halo_shape=None)
+    arrays = {"f": fa, "g": ga}
+    halos = {"f": Hf, "g": Hg}
+    got = run_generated_histogram_on_host(ksrc, arrays, halos, {"s": float(s)}, N,
+                                          int(rng.integers(1, 6)))
+
+    def inner(a, H):
+        return a[tuple(slice(H, H + n) for n in N)]
+    fi, gi = inner(fa, Hf), inner(ga, Hg)
+    bins = [np.floor(fi * s - T(2)), np.floor(gi * s), np.floor(fi * gi * s)][:nh]
+    weights = [np.ones(N), (fi + gi).astype(np.float64), np.full(N, 2.5)][:nh]
+    for j in range(nh):
+        ok = (bins[j] >= 0) & (bins[j] < nb)
+        ref = np.bincount(bins[j][ok].astype(int), weights=weights[j][ok], minlength=nb)
+        assert np.allclose(got[j], ref, rtol=1e-12, atol=1e-12), (N, nb, j)
