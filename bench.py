@@ -656,7 +656,10 @@ def run_b200_arm(args):
             and not (args.grid or args.nx or args.dtype or args.scaling)):
         del job
         torch.cuda.empty_cache()
-        extras = run_extras(args)
+        try:
+            extras = run_extras(args)
+        except BaseException as exc:  # noqa: BLE001 -- never at the expense of the line
+            extras = {"error": repr(exc)[:400]}
 
     if rank == 0:
         config = config_dict(cfg, w, world)
