@@ -656,6 +656,13 @@ def run_b200_arm(args):
             and not (args.grid or args.nx or args.dtype or args.scaling)):
         del job
         torch.cuda.empty_cache()
+        # insurance: should the run be cut short while the extras are being collected, the
+        # headline numbers are at least in the stderr log
+        print("[bench] headline (before extras): " + json.dumps({
+            "value": value, "ms_per_step": ms_per_step, "steps": steps,
+            "roofline_frac": roofline["frac"], "parity": parity,
+            "e2e_value": (e2e or {}).get("value"),
+            "cpu_baseline": (cpu or {}).get("value")}), file=sys.stderr, flush=True)
         try:
             extras = run_extras(args)
         except BaseException as exc:  # noqa: BLE001 -- never at the expense of the line
