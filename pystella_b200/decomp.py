@@ -23,7 +23,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-from pystella_b200 import _kernels
+from pystella_b200 import _kernels, _lib
 from pystella_b200._lib import PsbError
 
 logger = logging.getLogger(__name__)
@@ -155,7 +155,7 @@ class DomainDecomposition:
 
     # -- local kernels (device) or injected host ops (tests) -------------------
     def _wrap(self, fx, mask, queue):
-        if fx.is_cuda:
+        if _lib.on_device(fx):
             _kernels.halo_wrap(fx, self.halo_shape, mask, queue)
         elif self.host_ops is not None:
             self.host_ops.wrap(fx, self.halo_shape, mask)
@@ -164,7 +164,7 @@ class DomainDecomposition:
                            "on the GPU only (no CPU fallback)")
 
     def _pack(self, fx, buf, axis, queue, unpack=False):
-        if fx.is_cuda:
+        if _lib.on_device(fx):
             _kernels.halo_pack(fx, buf, self.halo_shape, axis, queue, unpack=unpack)
         elif self.host_ops is not None:
             self.host_ops.pack(fx, buf, self.halo_shape, axis, unpack)
@@ -355,7 +355,7 @@ class DomainDecomposition:
 
 
 def _is_dev(x):
-    return isinstance(x, torch.Tensor) and x.is_cuda
+    return isinstance(x, torch.Tensor) and _lib.on_device(x)
 
 
 def _np_dtype(x):

@@ -20,7 +20,7 @@ from itertools import product
 import numpy as np
 import torch
 
-from pystella_b200 import _kernels
+from pystella_b200 import _kernels, _lib
 from pystella_b200._lib import PsbError
 from pystella_b200.field import (Call, Field, Variable, _walk, evaluate, is_constant,
                                  substitute, to_polynomial)
@@ -173,7 +173,7 @@ class Reduction:
             t = kwargs[ref.name]
             if not isinstance(t, torch.Tensor):
                 raise TypeError(f"'{ref.name}' must be a torch.Tensor on the GPU")
-            if not t.is_cuda:
+            if not _lib.on_device(t):
                 raise PsbError(f"'{ref.name}' lives on {t.device}: reductions run on "
                                "the GPU only (no CPU fallback)")
             if any(ref.shift):

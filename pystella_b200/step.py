@@ -411,7 +411,7 @@ def _scalar_value(x):
 
 
 def _is_device(x):
-    return isinstance(x, torch.Tensor) and x.is_cuda
+    return isinstance(x, torch.Tensor) and _lib.on_device(x)
 
 
 class Stepper:
@@ -561,7 +561,7 @@ class Stepper:
             return False
         if all(isinstance(x, torch.Tensor) for x in arrays):
             for n in self.dof_names:
-                if not kwargs[n].is_cuda:
+                if not _lib.on_device(kwargs[n]):
                     raise PsbError(
                         f"'{n}' lives on {kwargs[n].device}: the stepper kernels run on "
                         "the GPU only (no CPU fallback)")

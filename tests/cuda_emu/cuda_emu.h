@@ -19,7 +19,9 @@
 #include <cstdint>
 #include <cstring>
 #include <functional>
+#include <memory>
 #include <mutex>
+#include <pthread.h>
 #include <thread>
 #include <vector>
 
@@ -32,6 +34,8 @@
 #define __launch_bounds__(...)
 #define __shared__ static
 #define __align__(n) alignas(n)
+#define __grid_constant__
+#define __noinline__
 
 struct dim3 {
   unsigned x, y, z;
@@ -46,33 +50,82 @@ static inline float2 make_float2(float a, float b) { return {a, b}; }
 
 namespace emu {
 
-class Barrier {      // reusable counting barrier (sense-reversing)
- public:
-  void reset(int n) { n_ = n; count_ = 0; gen_ = 0; }
-  void wait() {
-    std::unique_lock<std::mutex> lk(m_);
-    const unsigned long g = gen_;
-    if (++count_ == n_) { count_ = 0; ++gen_; cv_.notify_all(); return; }
-    cv_.wait(lk, [&] { return gen_ != g; });
+class Barrier {      // reusable barrier (futex-based pthread barrier: far cheaper than a
+ public:            // mutex + condition-variable broadcast for teams of 256-512 threads)
+  Barrier() = default;
+  Barrier(const Barrier&) = delete;
+  ~Barrier() { if (live_) pthread_barrier_destroy(&b_); }
+  void reset(int n) {
+    if (live_) pthread_barrier_destroy(&b_);
+    pthread_barrier_init(&b_, nullptr, (unsigned)n);
+    live_ = true;
   }
+  void wait() { pthread_barrier_wait(&b_); }
  private:
-  std::mutex m_;
-  std::condition_variable cv_;
-  int n_ = 1, count_ = 0;
-  unsigned long gen_ = 0;
+  pthread_barrier_t b_;
+  bool live_ = false;
 };
 
 struct Team {
   Barrier block;
-  std::vector<Barrier> warps;
+  std::unique_ptr<Barrier[]> warps;
   std::vector<std::vector<unsigned long long>> warp_buf;   // 32 slots of 8 bytes per warp
 };
 
 inline Team*& team() { static Team* t = nullptr; return t; }
-inline thread_local uint3_emu t_threadIdx, t_blockIdx;
 inline thread_local int t_linear = 0;
-inline dim3& g_blockDim() { static dim3 d; return d; }
-inline dim3& g_gridDim() { static dim3 d; return d; }
+
+}  // namespace emu
+
+// the CUDA built-in index variables: real objects (not macros), so that members of the same
+// name elsewhere (cudaLaunchConfig_t::gridDim) are left alone
+inline thread_local uint3_emu threadIdx, blockIdx;
+inline dim3 blockDim, gridDim;
+
+namespace emu {
+
+// Worker threads are kept between launches (creating 256-512 threads per launch costs more
+// than most of the small kernels of the tests); the pool is leaked on purpose.
+struct Pool {
+  std::mutex m;
+  std::condition_variable cv;
+  std::vector<std::thread> ths;
+  unsigned long gen = 0;
+  int nt = 0;
+  std::function<void(int)> job;
+  Barrier done;
+
+  void worker(int t) {
+    unsigned long seen = 0;
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> lk(m);
+        cv.wait(lk, [&] { return gen != seen; });
+        seen = gen;
+        if (t >= nt) continue;
+      }
+      job(t);
+      done.wait();
+    }
+  }
+  void run(int n, std::function<void(int)> f) {
+    {
+      std::unique_lock<std::mutex> lk(m);
+      while ((int)ths.size() < n) {
+        const int t = (int)ths.size();
+        ths.emplace_back([this, t] { worker(t); });
+        ths.back().detach();
+      }
+      job = std::move(f);
+      nt = n;
+      done.reset(n + 1);
+      ++gen;
+    }
+    cv.notify_all();
+    done.wait();
+  }
+};
+inline Pool& pool() { static Pool* p = new Pool; return *p; }
 
 template <class F>
 void launch(dim3 grid, dim3 block, F&& body) {
@@ -80,28 +133,24 @@ void launch(dim3 grid, dim3 block, F&& body) {
   Team tm;
   tm.block.reset(nt);
   const int nw = (nt + 31) / 32;
-  tm.warps = std::vector<Barrier>(nw);
+  tm.warps.reset(new Barrier[nw]);
   tm.warp_buf.assign(nw, std::vector<unsigned long long>(32, 0));
   for (int w = 0; w < nw; ++w) tm.warps[w].reset(std::min(32, nt - 32 * w));
   team() = &tm;
-  g_blockDim() = block;
-  g_gridDim() = grid;
-  std::vector<std::thread> ths;
-  for (int t = 0; t < nt; ++t) {
-    ths.emplace_back([&, t] {
-      t_linear = t;
-      t_threadIdx = {unsigned(t % block.x), unsigned((t / block.x) % block.y),
-                     unsigned(t / (block.x * block.y))};
-      for (unsigned bz = 0; bz < grid.z; ++bz)
-        for (unsigned by = 0; by < grid.y; ++by)
-          for (unsigned bx = 0; bx < grid.x; ++bx) {
-            t_blockIdx = {bx, by, bz};
-            body();
-            tm.block.wait();          // the next block reuses the statics ("shared memory")
-          }
-    });
-  }
-  for (auto& th : ths) th.join();
+  blockDim = block;
+  gridDim = grid;
+  pool().run(nt, [&](int t) {
+    t_linear = t;
+    threadIdx = {unsigned(t % block.x), unsigned((t / block.x) % block.y),
+                 unsigned(t / (block.x * block.y))};
+    for (unsigned bz = 0; bz < grid.z; ++bz)
+      for (unsigned by = 0; by < grid.y; ++by)
+        for (unsigned bx = 0; bx < grid.x; ++bx) {
+          blockIdx = {bx, by, bz};
+          body();
+          tm.block.wait();          // the next block reuses the statics ("shared memory")
+        }
+  });
   team() = nullptr;
 }
 
@@ -162,14 +211,14 @@ T atomic_add(T* p, T v) {
 
 }  // namespace emu
 
-#define threadIdx (emu::t_threadIdx)
-#define blockIdx (emu::t_blockIdx)
-#define blockDim (emu::g_blockDim())
-#define gridDim (emu::g_gridDim())
-
 static inline void __syncthreads() { emu::team()->block.wait(); }
 static inline void __syncwarp(unsigned = 0xffffffffu) { emu::team()->warps[emu::t_linear / 32].wait(); }
 static inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+static inline void __threadfence_system() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+static inline void __nanosleep(unsigned) { std::this_thread::yield(); }
+static inline size_t __cvta_generic_to_shared(const void* p) { return (size_t)p; }
+static inline double __longlong_as_double(long long v) { double d; std::memcpy(&d, &v, 8); return d; }
+static inline long long __double_as_longlong(double d) { long long v; std::memcpy(&v, &d, 8); return v; }
 
 static inline double atomicAdd(double* p, double v) { return emu::atomic_add(p, v); }
 static inline float atomicAdd(float* p, float v) { return emu::atomic_add(p, v); }
@@ -193,6 +242,16 @@ static inline int __ffs(unsigned x) { return __builtin_ffs(int(x)); }
 template <class T> static inline T __shfl_xor_sync(unsigned, T v, int m) {
   return emu::shfl(v, (emu::t_linear % 32) ^ m);
 }
+
+// CUDA's global integer min / max
+static inline int min(int a, int b) { return a < b ? a : b; }
+static inline int max(int a, int b) { return a > b ? a : b; }
+static inline long long min(long long a, long long b) { return a < b ? a : b; }
+static inline long long max(long long a, long long b) { return a > b ? a : b; }
+static inline long min(long a, long b) { return a < b ? a : b; }
+static inline long max(long a, long b) { return a > b ? a : b; }
+static inline unsigned min(unsigned a, unsigned b) { return a < b ? a : b; }
+static inline unsigned max(unsigned a, unsigned b) { return a > b ? a : b; }
 
 static inline double __ldg(const double* p) { return *p; }
 static inline float __ldg(const float* p) { return *p; }

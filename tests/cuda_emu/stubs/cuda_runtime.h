@@ -1,0 +1,23 @@
+// Test infrastructure: the few host-side CUDA runtime names the stand-alone translation units
+// of pystella_b200/csrc use, so that they compile with g++ on top of cuda_emu.h.
+#pragma once
+#include <stdint.h>
+#include <stdio.h>
+typedef struct CUstream_st* cudaStream_t;
+typedef int cudaError_t;
+#define cudaSuccess 0
+static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+static inline const char* cudaGetErrorString(cudaError_t) { return "emulated"; }
+static inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
+enum cudaDeviceAttr { cudaDevAttrMultiProcessorCount = 16 };
+static inline cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr, int) { *v = 3; return cudaSuccess; }
+// programmatic-launch plumbing of common.cuh (template, never instantiated under emulation)
+enum cudaLaunchAttributeID { cudaLaunchAttributeProgrammaticStreamSerialization = 1 };
+struct cudaLaunchAttributeValue { int programmaticStreamSerializationAllowed; };
+struct cudaLaunchAttribute { cudaLaunchAttributeID id; cudaLaunchAttributeValue val; };
+struct cudaLaunchConfig_t {
+  dim3 gridDim, blockDim; size_t dynamicSmemBytes; cudaStream_t stream;
+  cudaLaunchAttribute* attrs; unsigned numAttrs;
+};
+template <typename... A, typename... B>
+static inline cudaError_t cudaLaunchKernelEx(const cudaLaunchConfig_t*, void (*)(A...), B...) { return 1; }

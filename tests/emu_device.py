@@ -6,9 +6,10 @@ kernel source on the CPU execution model of tests/cuda_emu/cuda_emu.h:
 
 * generated kernels (`libpystella_b200_jit.so`: psb_jit_launch / psb_jit_launch_params)
   -> the generated source compiled with g++ and run block by block;
-* `psb_bin_power` -> csrc/diag_kernels.cuh through tests/cuda_emu/emu_diag.cpp;
-* `psb_reduce` (validated on the GPU in tests/test_gpu_*.py) -> a NumPy restatement of its
-  contract, enough for the callers' argument tables to be checked.
+* `libpystella_b200.so` -> a HOST build of its stand-alone translation units (halo, element-
+  wise stages, finite differences (generic tile kernel), reductions, background,
+  diagnostics) with the same C ABI (tests/emu_library.py).  The TMA pipelines (fused
+  stages) are hardware-specific and have no emulated counterpart.
 
 Nothing here is reachable from the product.
 """
@@ -20,7 +21,7 @@ import types
 import numpy as np
 import torch
 
-from test_cuda_emu import EMU, build_emu
+from test_cuda_emu import build_emu
 
 NUM_SMS = 3      # small, so that the persistent kernels loop over several row groups per CTA
 
@@ -55,50 +56,26 @@ class EmuJitLibrary:
         return b""
 
 
-class EmuMainLibrary:
-    """Stands in for libpystella_b200.so (the entry points the diagnostics use)."""
-
-    def __init__(self):
-        src = open(os.path.join(EMU, "emu_diag.cpp")).read()
-        self._diag = build_emu(src, "emu_diag", extra=["-I" + os.path.join(
-            os.path.dirname(EMU), "..", "include")])
-
-    def psb_bin_power(self, args_ref, stream):
-        return self._diag.emu_psb_bin_power(args_ref, C.c_int(NUM_SMS))
-
-    def psb_last_error(self):
-        return b""
-
-
-def numpy_reduce_poly(arrays, halos, terms, ops, flags, shape, queue=None, strict=False,
-                      variant=0):
-    """Contract of psb_reduce (include/pystella_b200.h): out[r] = op_r over sites of
-    sum_t coef_t prod_j arr_j^power_tj, |.| first if flags bit 0."""
-    views = [a.numpy()[tuple(slice(h, h + n) for n in shape)] if h else a.numpy()
-             for a, h in zip(arrays, halos)]
-    out = []
-    for r, (op, fl) in enumerate(zip(ops, flags)):
-        val = np.zeros(shape)
-        for (o, coef, powers) in terms:
-            if o == r:
-                t = np.full(shape, float(coef))
-                for v, p in zip(views, powers):
-                    t = t * v.astype(np.float64)**int(p)
-                val = val + t
-        if fl & 1:
-            val = np.abs(val)
-        out.append({0: val.sum(), 1: val.max(), 2: val.min()}[op])
-    return torch.tensor(out, dtype=torch.float64)
+def emulated_main_library():
+    """Stands in for libpystella_b200.so: the HOST build of its stand-alone translation
+    units (tests/emu_library.py), with the ctypes prototypes of pystella_b200._lib."""
+    import emu_library
+    from pystella_b200 import _lib
+    lib = emu_library.build()
+    for name, (restype, argtypes) in _lib.SYMBOLS.items():
+        fn = getattr(lib, name, None)
+        if fn is not None:
+            fn.restype, fn.argtypes = restype, argtypes
+    return lib
 
 
 @contextlib.contextmanager
 def emulated_device(monkeypatch):
     from pystella_b200 import _kernels, _lib, codegen
-    jit, main = EmuJitLibrary(), EmuMainLibrary()
+    jit, main = EmuJitLibrary(), emulated_main_library()
     monkeypatch.setattr(_lib, "on_device", lambda t: True)
     monkeypatch.setattr(_lib, "stream_ptr", lambda queue=None: None)
     monkeypatch.setattr(_lib, "load", lambda strict=False: main)
-    monkeypatch.setattr(_kernels, "reduce_poly", numpy_reduce_poly)
     monkeypatch.setattr(codegen.JitLibrary, "compile", classmethod(lambda cls, ksrc: ksrc))
     monkeypatch.setattr(codegen.JitLibrary, "get", classmethod(lambda cls: jit))
     monkeypatch.setattr(torch.cuda, "get_device_properties",
