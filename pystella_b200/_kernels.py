@@ -40,7 +40,8 @@ def scalar_stage(*, fused, f_in, f_out, dfdt, kf, kdfdt, lap_f=None, h, dx=(1., 
                  dV_terms=None, wrap=(True, True, True), x_range=None,
                  queue=None, strict=False, xchunk=0, variant=0,
                  energy_partials=None, energy_slot_offset=0, V_terms=None,
-                 count_slots_only=False, peer=None, generated=None, tail=None,
+                 count_slots_only=False, probe_plan=False, peer=None, generated=None,
+                 tail=None,
                  prefetch=0, pws_sched=None, launch_flags=0):
     """
     One scalar-sector LSRK stage on padded arrays of shape ``(n, Nx+2h, Ny+2h, Nz+2h)``
@@ -123,6 +124,13 @@ def scalar_stage(*, fused, f_in, f_out, dfdt, kf, kdfdt, lap_f=None, h, dx=(1., 
                 if pw < 0 or pw > 127:
                     raise ValueError("monomial powers must be in 0..127")
                 args.vpower[t][m] = pw
+    if probe_plan:
+        # can the TMA pipeline (and hence its run-time generated instances) serve this
+        # layout?  Dry run of psb_scalar_stage_fused_plan: geometry only, no driver call
+        raw = C.create_string_buffer(C.sizeof(_lib.FusedPlan) + 64)
+        plan = _lib.FusedPlan.from_address((C.addressof(raw) + 63) // 64 * 64)
+        plan.reserved = 1
+        return lib.psb_scalar_stage_fused_plan(C.byref(args), C.byref(plan)) == 0
     if count_slots_only:
         n = lib.psb_scalar_stage_energy_slots(C.byref(args))
         if n < 0:

@@ -521,7 +521,11 @@ class Stepper:
                             and not tune.get("tables", False)
                             and tune.get("variant", 0) == 0):   # explicit variants: tables
                         try:
+                            tables = system
                             system = general(s.rhs_dict, s.potential(s.f), None)
+                            # layouts the TMA pipeline cannot describe (odd radii, odd
+                            # rows, unaligned views) are served by the table-driven kernel
+                            system.tables = tables
                         except NotImplementedError:
                             pass
                     systems.append(system)
@@ -814,7 +818,8 @@ class LowStorageRKStepper(Stepper):
             if isinstance(expr, Field) and expr.name in kwargs \
                     and isinstance(kwargs[expr.name], torch.Tensor):
                 dev = kwargs[expr.name]
-                if not (dev.is_cuda and dev.dtype == torch.float64 and dev.numel() == 1):
+                if not (_lib.on_device(dev) and dev.dtype == torch.float64
+                        and dev.numel() == 1):
                     raise ValueError(f"device scalar '{expr.name}' must be one float64")
                 out[which] = (1.0, dev)
                 continue
@@ -837,6 +842,21 @@ class LowStorageRKStepper(Stepper):
                               for c, p in system.V]
         return out, dV
 
+    def _generated_instance_applies(self, system, f, dfdt, kf, kd, h):
+        """The generated instance of a polynomial system is the TMA pipeline compiled with
+        the potential inlined: it exists for the layouts that pipeline serves.  Asked of the
+        library itself (dry-run launch plan), once per layout."""
+        key = (system.f_name, tuple(f.shape), f.dtype, h,
+               tuple(t.data_ptr() % 16 for t in (f, dfdt, kf, kd)))
+        cache = self.__dict__.setdefault("_generated_ok", {})
+        if key not in cache:
+            tune = self.tune or {}
+            cache[key] = bool(_kernels.scalar_stage(
+                fused=True, probe_plan=True, f_in=f, f_out=kf, dfdt=dfdt, kf=kf, kdfdt=kd,
+                h=h, dx=self.dx, dt=0.0, A=0.0, B=0.0, dV_terms=None,
+                strict=self.strict_fp, xchunk=tune.get("xchunk", 0)))
+        return cache[key]
+
     def _scalar_stage(self, system, stage, queue, kwargs, dt, A, B):
         try:
             f = kwargs[system.f_name]
@@ -848,6 +868,10 @@ class LowStorageRKStepper(Stepper):
         h = self.halo_shape
         if h is None:
             raise ValueError("pass halo_shape= when constructing a device stepper")
+        if (self.fused and getattr(system, "generated", None) is not None
+                and getattr(system, "tables", None) is not None
+                and not self._generated_instance_applies(system, f, dfdt, kf, kd, h)):
+            system = system.tables
         scal, dV = self._scalars(system, kwargs)
         common = dict(dfdt=dfdt, kf=kf, kdfdt=kd, h=h, dt=dt, A=A, B=B,
                       a=scal["a"][0], hubble=scal["hubble"][0],

@@ -17,6 +17,8 @@
 #include <cmath>
 #include <condition_variable>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <memory>
@@ -127,6 +129,11 @@ struct Pool {
 };
 inline Pool& pool() { static Pool* p = new Pool; return *p; }
 
+// Block order: CUDA promises none.  Forward by default; `reverse` runs the highest linear
+// block index first, which a kernel whose block 0 WAITS for the others needs on a model that
+// runs blocks one after the other (the watcher CTA of csrc/stage_tail.cuh).
+inline bool& reverse_blocks() { static bool r = false; return r; }
+
 template <class F>
 void launch(dim3 grid, dim3 block, F&& body) {
   const int nt = int(block.x * block.y * block.z);
@@ -143,13 +150,14 @@ void launch(dim3 grid, dim3 block, F&& body) {
     t_linear = t;
     threadIdx = {unsigned(t % block.x), unsigned((t / block.x) % block.y),
                  unsigned(t / (block.x * block.y))};
-    for (unsigned bz = 0; bz < grid.z; ++bz)
-      for (unsigned by = 0; by < grid.y; ++by)
-        for (unsigned bx = 0; bx < grid.x; ++bx) {
-          blockIdx = {bx, by, bz};
-          body();
-          tm.block.wait();          // the next block reuses the statics ("shared memory")
-        }
+    const unsigned long nb = (unsigned long)grid.x * grid.y * grid.z;
+    for (unsigned long n = 0; n < nb; ++n) {
+      const unsigned long b = reverse_blocks() ? nb - 1 - n : n;
+      blockIdx = {unsigned(b % grid.x), unsigned((b / grid.x) % grid.y),
+                  unsigned(b / ((unsigned long)grid.x * grid.y))};
+      body();
+      tm.block.wait();          // the next block reuses the statics ("shared memory")
+    }
   });
   team() = nullptr;
 }
@@ -192,6 +200,17 @@ inline unsigned ballot(bool pred) {
   return bits;
 }
 
+// PTX of the hardware pipelines (mbarrier, TMA, ...) has no meaning here: reaching it is a bug
+inline void unsupported_ptx() {
+  fprintf(stderr, "cuda_emu: PTX of a hardware-only path was reached\n");
+  abort();
+}
+// bar.sync id, count: only the whole-block form is modelled
+inline void named_barrier(int id, int count) {
+  if (id != 0 || count != int(blockDim.x * blockDim.y * blockDim.z)) unsupported_ptx();
+  team()->block.wait();
+}
+
 template <class T>
 T atomic_add(T* p, T v) {
   // CAS loop on the bit pattern: works for float / double / integers
@@ -228,6 +247,14 @@ static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long 
   return emu::atomic_add(p, v);
 }
 
+template <class T> static inline T atomicExch(T* p, T v) {
+  return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST);
+}
+template <class T> static inline T atomicCAS(T* p, T cmp, T v) {
+  __atomic_compare_exchange_n(p, &cmp, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST);
+  return cmp;
+}
+
 template <class T> static inline T __shfl_sync(unsigned, T v, int lane) { return emu::shfl(v, lane); }
 template <class T> static inline T __shfl_down_sync(unsigned, T v, unsigned d) {
   const int lane = emu::t_linear % 32;
@@ -242,6 +269,11 @@ static inline int __ffs(unsigned x) { return __builtin_ffs(int(x)); }
 template <class T> static inline T __shfl_xor_sync(unsigned, T v, int m) {
   return emu::shfl(v, (emu::t_linear % 32) ^ m);
 }
+
+// streaming (evict-first) loads / stores: plain accesses here
+template <class T> static inline T __ldcs(const T* p) { return *p; }
+template <class T> static inline void __stcs(T* p, T v) { *p = v; }
+template <class T> static inline T __ldcg(const T* p) { return *p; }
 
 // CUDA's global integer min / max
 static inline int min(int a, int b) { return a < b ? a : b; }

@@ -20,4 +20,23 @@ struct cudaLaunchConfig_t {
   cudaLaunchAttribute* attrs; unsigned numAttrs;
 };
 template <typename... A, typename... B>
-static inline cudaError_t cudaLaunchKernelEx(const cudaLaunchConfig_t*, void (*)(A...), B...) { return 1; }
+static inline cudaError_t cudaLaunchKernelEx(const cudaLaunchConfig_t* cfg, void (*kern)(A...),
+                                             B... args) {
+  emu::launch_smem(cfg->gridDim, cfg->blockDim, cfg->dynamicSmemBytes,
+                   [&] { kern(static_cast<A>(args)...); });
+  return cudaSuccess;
+}
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+template <typename F>
+static inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
+
+// driver entry points: none on the emulated device
+enum cudaDriverEntryPointQueryResult { cudaDriverEntryPointSuccess = 0,
+                                       cudaDriverEntryPointSymbolNotFound = 1 };
+#define cudaEnableDefault 0
+static inline cudaError_t cudaGetDriverEntryPoint(const char*, void** fn, unsigned long long,
+                                                  cudaDriverEntryPointQueryResult* q) {
+  *fn = nullptr;
+  *q = cudaDriverEntryPointSymbolNotFound;
+  return 1;
+}

@@ -20,8 +20,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "pystella_b200", "csrc")
 EMU = os.path.join(ROOT, "tests", "cuda_emu")
 
-SOURCES = ["halo.cu", "rk_stage.cu", "stage_unfused.cu", "tensor_stage.cu", "reduce.cu",
-           "expansion.cu", "diag.cu", "fd.cu"]
+SOURCES = ["common.cu", "halo.cu", "rk_stage.cu", "stage_unfused.cu", "tensor_stage.cu",
+           "reduce.cu", "expansion.cu", "diag.cu", "fd.cu",
+           "fused_stage.cu", "fused_stage_f64.cu", "fused_stage_f32.cu"]
+#: the fused-stage units instantiate every kernel variant (incl. the TMA pipelines, which
+#: cannot run here: their PTX traps): compiled without optimisation to keep the build short
+UNOPTIMISED = {"fused_stage_f64.cu", "fused_stage_f32.cu"}
 
 #: headers replaced as a whole: the TMA pipeline of the finite-difference kernels reports
 #: "layout not eligible", so that psb_finite_difference takes its generic tile kernel (the
@@ -101,44 +105,57 @@ def transform_launches(src):
     return out + src[pos:]
 
 
-_ASM = [
-    # programmatic dependent launch: no-ops without the launch attribute
-    (re.compile(r'asm volatile\("griddepcontrol\.(?:launch_dependents|wait);"\s*:::\s*"memory"\);'),
-     ";"),
-    # system-scope release store / acquire load of the inter-GPU flags
-    (re.compile(r'asm volatile\("st\.release\.sys\.global\.u64 \[%0\], %1;"\s*::\s*"l"\((\w+)\),'
-                r'\s*"l"\((\w+)\)\s*:\s*"memory"\);'),
-     r"__atomic_store_n(\1, \2, __ATOMIC_RELEASE);"),
-    (re.compile(r'asm volatile\("ld\.acquire\.sys\.global\.u64 %0, \[%1\];"\s*:\s*"=l"\((\w+)\)'
-                r'\s*:\s*"l"\((\w+)\)\s*:\s*"memory"\);'),
-     r"\1 = __atomic_load_n(\2, __ATOMIC_ACQUIRE);"),
-]
+_OPERAND = re.compile(r'"[=+]?[a-z]"\s*\(((?:[^()]|\([^()]*\))*)\)')
+
+
+def _asm_replacement(stmt):
+    """C++ meaning of one `asm volatile(...)` statement on the emulated paths; PTX that only
+    the hardware pipelines execute (mbarrier, TMA, prefetch) aborts if it is ever reached."""
+    ops = [m.group(1).strip() for m in _OPERAND.finditer(stmt)]
+    if "griddepcontrol" in stmt:
+        return ";"                               # no-ops without the launch attribute
+    if "st.release.sys.global.u64" in stmt:
+        return f"__atomic_store_n({ops[0]}, {ops[1]}, __ATOMIC_RELEASE);"
+    if "ld.acquire.sys.global.u64" in stmt:
+        return f"{ops[0]} = __atomic_load_n({ops[1]}, __ATOMIC_ACQUIRE);"
+    if "st.volatile.global.f64" in stmt:
+        return f"*(volatile double*)({ops[0]}) = ({ops[1]});"
+    if "ld.volatile.global.b64" in stmt:
+        return f"{ops[0]} = *(volatile unsigned long long*)({ops[1]});"
+    if "bar.sync %0, %1" in stmt:
+        return f"emu::named_barrier({ops[0]}, {ops[1]});"
+    return "emu::unsupported_ptx();"
+
+
+_DYN_SMEM = re.compile(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?([\w ]+?)\s+(\w+)\[\];")
 
 
 def transform_asm(src):
-    """The handful of PTX statements on the emulated paths -> their C++ meaning."""
-    for rx, repl in _ASM:
-        src = rx.sub(repl, src)
-    return src
+    # dynamic shared memory: `extern __shared__ T name[];` -> the model's buffer
+    src = _DYN_SMEM.sub(r"\1* \2 = reinterpret_cast<\1*>(emu::dynamic_smem());", src)
+    out, pos = "", 0
+    while True:
+        at = src.find("asm volatile", pos)
+        if at < 0:
+            break
+        i = src.index("(", at)
+        depth, j, in_str = 1, i + 1, False
+        while depth:
+            ch = src[j]
+            if ch == '"' and src[j - 1] != "\\":
+                in_str = not in_str
+            elif not in_str:
+                depth += {"(": 1, ")": -1}.get(ch, 0)
+            j += 1
+        end = src.index(";", j) + 1
+        out += src[pos:at] + _asm_replacement(src[at:end])
+        pos = end
+    return out + src[pos:]
 
 
-_COMMON = r'''
-// stands in for common.cu under emulation: error channel and ABI constants
-#include <stdarg.h>
-#include "common.cuh"
-namespace psb {
-static thread_local char g_error[1024] = "";
-void set_error(const char* fmt, ...) {
-  va_list ap; va_start(ap, fmt); vsnprintf(g_error, sizeof(g_error), fmt, ap); va_end(ap);
-}
-int encode_field_tensor_map(CUtensorMap*, int, const void*, int64_t, int64_t, int64_t, int64_t,
-                            int64_t, int, int, int) { return 1; }   // no TMA here
-}
-extern "C" {
-const char* psb_last_error(void) { return psb::g_error; }
-int psb_abi_version(void) { return PSB_ABI_VERSION; }
-int psb_strict_fp(void) { return 1; }
-}
+_CONTROL = '''
+// knobs of the execution model, exported next to the C ABI
+extern "C" void emu_set_reverse_blocks(int v) { emu::reverse_blocks() = v != 0; }
 '''
 
 _lib = None
@@ -153,12 +170,13 @@ def build(verbose=False):
     for name in SOURCES:
         with open(os.path.join(CSRC, name)) as fh:
             texts[name] = transform_asm(transform_launches(fh.read()))
-    texts["emu_common.cu"] = _COMMON
+    texts["emu_control.cu"] = _CONTROL
     headers = {}
     for hdr in sorted(os.listdir(CSRC)):
         if hdr.endswith(".cuh"):
             with open(os.path.join(CSRC, hdr)) as fh:
-                headers[hdr] = SHADOWED.get(hdr) or transform_asm(fh.read())
+                headers[hdr] = SHADOWED.get(hdr) or transform_asm(
+                    transform_launches(fh.read()))
     h = hashlib.sha256()
     for name in sorted(texts):
         h.update(texts[name].encode())
@@ -173,13 +191,14 @@ def build(verbose=False):
         for hdr, text in headers.items():       # transformed copies shadow csrc/*.cuh
             with open(os.path.join(d, hdr), "w") as fh:
                 fh.write(text)
-        objs = []
-        for name, text in texts.items():
+        def compile_one(item):
+            name, text = item
             cpp = os.path.join(d, name[:-3] + ".cpp")
             with open(cpp, "w") as fh:
                 fh.write(text)
             obj = cpp[:-4] + ".o"
-            cmd = ["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-pthread", "-fPIC", "-c",
+            cmd = ["g++", "-std=c++17", "-O0" if name in UNOPTIMISED else "-O1",
+                   "-ffp-contract=off", "-pthread", "-fPIC", "-c",
                    "-Wno-unknown-pragmas", "-Wno-attributes", "-DPSB_STRICT_FP=1",
                    "-include", os.path.join(EMU, "cuda_emu.h"),
                    "-I" + d, "-I" + os.path.join(EMU, "stubs"), "-I" + EMU, "-I" + CSRC,
@@ -187,7 +206,11 @@ def build(verbose=False):
             res = subprocess.run(cmd, capture_output=True, text=True)
             if res.returncode != 0:
                 raise RuntimeError(f"emulated build of {name} failed:\n" + res.stderr[-4000:])
-            objs.append(obj)
+            return obj
+
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+            objs = list(ex.map(compile_one, texts.items()))
         tmp = so + f".{os.getpid()}.tmp"
         subprocess.check_call(["g++", "-shared", "-pthread", "-o", tmp] + objs)
         os.replace(tmp, so)

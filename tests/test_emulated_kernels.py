@@ -14,6 +14,7 @@ import torch
 
 import test_gpu_api as API
 import test_gpu_kernels as KER
+import test_zz_gpu_diagnostics as ZZ
 from emu_device import emulated_device
 
 
@@ -28,14 +29,29 @@ def device(monkeypatch):
             return fn(*a, **k)
         return wrapped
 
-    for mod in (API, KER):
+    for mod in (API, KER, ZZ):
         monkeypatch.setattr(mod, "to_dev", host)
     for name in ("zeros", "empty", "rand", "randn", "ones", "tensor", "full"):
         monkeypatch.setattr(torch, name, strip(getattr(torch, name)))
     monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
     monkeypatch.setattr(torch.cuda, "current_device", lambda: 0)
+
+    # the TMA instances of the fused stage exist on the hardware only: automatic kernel
+    # selection (tune_variant 0) is pinned to the cooperative-loader instance here
+    from pystella_b200 import _kernels
+    real_stage = _kernels.scalar_stage
+
+    def scalar_stage(**kw):
+        if kw.get("fused") and kw.get("variant", 0) == 0:
+            kw["variant"] = 2
+        return real_stage(**kw)
+    monkeypatch.setattr(_kernels, "scalar_stage", scalar_stage)
     with emulated_device(monkeypatch) as dev:
+        # the watcher CTA of the fused stage (csrc/stage_tail.cuh) waits for the rows of all
+        # other CTAs: on a model that runs blocks one after the other it has to come last
+        dev.main.emu_set_reverse_blocks(1)
         yield dev
+        dev.main.emu_set_reverse_blocks(0)
 
 
 # ---- kernels through the thin wrappers of pystella_b200._kernels ------------------------
@@ -114,3 +130,32 @@ def test_two_scalars_plus_gw_sector_unfused(device):
 @pytest.mark.parametrize("name", ["RungeKutta3SSP"])
 def test_classical_rk_wave_equation(device, name):
     API.test_classical_rk_wave_equation_device(name)
+
+
+# ---- the fused stage: its generic instance (cooperative loader instead of TMA) -----------
+# Same stencil / right-hand side / low-storage update / energy sums / write-through halos /
+# in-kernel stage tail as the TMA pipelines, which exist on the hardware only.
+
+FUSED_CASES = [c for c in KER.CASES
+               if c[4] in (2, 3) or c[1] % 2 == 1 or c[0][2] % 2 == 1]
+
+
+@pytest.mark.parametrize("stage", [0, 2])
+@pytest.mark.parametrize("N,h,n,pot,variant", FUSED_CASES)
+def test_fused_stage_generic_kernel_bit_exact(device, N, h, n, pot, variant, stage):
+    KER.test_fused_stage_fp64(N, h, n, pot, variant, True, stage)
+
+
+def test_fused_wave_equation_example(device):
+    API.test_wave_equation_example((32, 32, 32), 1, True)
+
+
+def test_device_resident_preheating_loop(device):
+    """Fused stage + in-kernel energy sums + watcher-CTA tail (fold, FLRW background) +
+    DeviceExpansion, against the oracle's loop."""
+    API.test_device_resident_preheating_loop(1)
+
+
+@pytest.mark.parametrize("h, N", [(1, (12, 10, 16)), (2, (12, 10, 17)), (3, (8, 12, 14))])
+def test_fused_two_fields_on_non_tma_layouts(device, h, N):
+    ZZ.test_fused_two_fields_on_non_tma_layouts(h, N)

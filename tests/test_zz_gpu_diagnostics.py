@@ -265,3 +265,46 @@ def test_tiled_stencil_equals_direct_kernel_at_config_size():
     ref = ((((x[2*h:, c, c] + x[c, 2*h:, c]) + x[c, c, 2*h:]) + x[:-2*h, c, c])
            + x[c, :-2*h, c]) + x[c, c, :-2*h]
     assert torch.equal(y_tile, ref)
+
+
+# ---------------------------------------------------------------------------
+# fused stepper: non-quadratic polynomial potentials on layouts without a TMA description
+# ---------------------------------------------------------------------------
+
+@pytest.mark.parametrize("h, N", [(1, (12, 10, 16)), (2, (12, 10, 17)), (3, (8, 12, 14))])
+def test_fused_two_fields_on_non_tma_layouts(h, N):
+    """ScalarSector(2) with the preheating potential under FusedStencilStage prefers the
+    run-time generated instance of the TMA pipeline; for odd radii / odd rows that pipeline
+    does not exist and the table-driven stage kernel must serve the system (found by running
+    the stage on the CPU execution model: the stepper used to raise "served by the
+    cooperative loader").  Five stages against the oracle, in-kernel halos included."""
+    import oracle as O
+    from test_gpu_api import _example_potential
+    from helpers import scale_err
+    rng = np.random.default_rng(49279)
+    pad = tuple(n + 2 * h for n in N)
+    dx = tuple(5 / n for n in N)
+    dt = 0.1 * min(dx)
+    potential, terms = _example_potential()
+    f0 = (np.array([.193, 0.])[:, None, None, None] + 1e-3 * rng.standard_normal((2,) + pad))
+    d0 = (np.array([-.142231, 0.])[:, None, None, None]
+          + 1e-3 * rng.standard_normal((2,) + pad))
+    a, hubble = 1.07, 0.45
+    fr, dr = f0.copy(), d0.copy()
+    kfr, kdr = np.zeros_like(fr), np.zeros_like(fr)
+    lap = np.zeros((2,) + N)
+    for s in range(5):
+        O.reference_schedule_stage(s, fr, dr, kfr, kdr, lap, h, dx, dt, a=a, hubble=hubble,
+                                   potential_terms=terms)
+    sector = ps.ScalarSector(2, potential=potential)
+    decomp = ps.DomainDecomposition((1, 1, 1), h, N)
+    stepper = ps.LowStorageRK54([sector], halo_shape=h, rank_shape=N, dt=dt,
+                                MapKernel=ps.FusedStencilStage, dx=dx, decomp=decomp)
+    assert getattr(stepper.systems[0], "tables", None) is not None   # generated preferred
+    f, dfdt = to_dev(f0), to_dev(d0)
+    for s in range(5):
+        stepper(s, f=f, dfdt=dfdt, a=np.array(a), hubble=np.array([hubble]))
+    for got, ref in ((f, fr), (dfdt, dr)):
+        for i in range(2):
+            assert scale_err(O.interior(got[i].cpu().numpy(), h),
+                             O.interior(ref[i], h)) < 1e-12
