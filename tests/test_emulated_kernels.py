@@ -20,8 +20,8 @@ from emu_device import emulated_device
 
 @pytest.fixture
 def device(monkeypatch):
-    def host(a):
-        return torch.from_numpy(np.ascontiguousarray(a))
+    def host(a):          # like .cuda(): a copy, never a view of the NumPy original
+        return torch.from_numpy(np.array(a, copy=True, order="C"))
 
     def strip(fn):
         def wrapped(*a, **k):
@@ -146,14 +146,33 @@ def test_fused_stage_generic_kernel_bit_exact(device, N, h, n, pot, variant, sta
     KER.test_fused_stage_fp64(N, h, n, pot, variant, True, stage)
 
 
+def test_fused_x_range_split_equals_whole(device):
+    KER.test_fused_x_range_split_equals_whole()
+
+
+@pytest.mark.parametrize("N,h,n,pot", [((32, 32, 32), 2, 1, KER.POT1), ((17, 9, 33), 1, 1, None)])
+def test_fused_stage_fp32(device, N, h, n, pot):
+    KER.test_fused_stage_fp32(N, h, n, pot)
+
+
+def test_fused_scalars_with_unfused_tensor_sector(device, monkeypatch):
+    API.test_unfused_gw_sector_with_fused_scalars(np.float64, 1e-12, monkeypatch)
+
+
+def test_fused_two_fields_and_generic_dict(device):
+    API.test_scalar_sector_two_fields(True, np.float64, 1e-12)
+    API.test_generic_dict_with_friction_matches_sector()
+
+
 def test_fused_wave_equation_example(device):
     API.test_wave_equation_example((32, 32, 32), 1, True)
 
 
-def test_device_resident_preheating_loop(device):
+@pytest.mark.parametrize("nscalars", [1, 2])
+def test_device_resident_preheating_loop(device, nscalars):
     """Fused stage + in-kernel energy sums + watcher-CTA tail (fold, FLRW background) +
     DeviceExpansion, against the oracle's loop."""
-    API.test_device_resident_preheating_loop(1)
+    API.test_device_resident_preheating_loop(nscalars)
 
 
 @pytest.mark.parametrize("h, N", [(1, (12, 10, 16)), (2, (12, 10, 17)), (3, (8, 12, 14))])
