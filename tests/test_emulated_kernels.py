@@ -13,6 +13,7 @@ import pytest
 import torch
 
 import test_gpu_api as API
+import test_gpu_generated as GEN
 import test_gpu_kernels as KER
 import test_zz_gpu_diagnostics as ZZ
 from emu_device import emulated_device
@@ -29,7 +30,7 @@ def device(monkeypatch):
             return fn(*a, **k)
         return wrapped
 
-    for mod in (API, KER, ZZ):
+    for mod in (API, GEN, KER, ZZ):
         monkeypatch.setattr(mod, "to_dev", host)
     for name in ("zeros", "empty", "rand", "randn", "ones", "tensor", "full"):
         monkeypatch.setattr(torch, name, strip(getattr(torch, name)))
@@ -178,3 +179,14 @@ def test_device_resident_preheating_loop(device, nscalars):
 @pytest.mark.parametrize("h, N", [(1, (12, 10, 16)), (2, (12, 10, 17)), (3, (8, 12, 14))])
 def test_fused_two_fields_on_non_tma_layouts(device, h, N):
     ZZ.test_fused_two_fields_on_non_tma_layouts(h, N)
+
+
+# ---- run-time generated kernels next to the hand-written ones ------------------------------
+
+def test_generated_kernels_of_the_python_layer(device):
+    """Custom-stencil FiniteDifferencer, a classical RK stage for an arbitrary rhs_dict and
+    non-polynomial reducers: generated sources on the model, hand-written kernels around
+    them from the host build."""
+    GEN.test_custom_stencil_differencer()
+    GEN.test_classical_rk_generated_stage("RungeKutta2Heun")
+    GEN.test_reduction_with_generated_reducers()
