@@ -854,7 +854,8 @@ class LowStorageRKStepper(Stepper):
             cache[key] = bool(_kernels.scalar_stage(
                 fused=True, probe_plan=True, f_in=f, f_out=kf, dfdt=dfdt, kf=kf, kdfdt=kd,
                 h=h, dx=self.dx, dt=0.0, A=0.0, B=0.0, dV_terms=None,
-                strict=self.strict_fp, xchunk=tune.get("xchunk", 0)))
+                strict=self.strict_fp, xchunk=tune.get("xchunk", 0),
+                variant=tune.get("variant", 0)))
         return cache[key]
 
     def _scalar_stage(self, system, stage, queue, kwargs, dt, A, B):
@@ -869,8 +870,13 @@ class LowStorageRKStepper(Stepper):
         if h is None:
             raise ValueError("pass halo_shape= when constructing a device stepper")
         if (self.fused and getattr(system, "generated", None) is not None
-                and getattr(system, "tables", None) is not None
                 and not self._generated_instance_applies(system, f, dfdt, kf, kd, h)):
+            if getattr(system, "tables", None) is None:
+                raise NotImplementedError(
+                    "the fused stage of a system with a run-time generated right-hand side "
+                    "is an instance of the TMA pipeline: it needs an even halo_shape, an even "
+                    "number of z sites and 16-byte aligned rows and arrays.  For this layout "
+                    "use the element-wise stepper (default MapKernel) with FiniteDifferencer")
             system = system.tables
         scal, dV = self._scalars(system, kwargs)
         common = dict(dfdt=dfdt, kf=kf, kdfdt=kd, h=h, dt=dt, A=A, B=B,
