@@ -21,6 +21,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <map>
+#include <unordered_map>
 #include <memory>
 #include <mutex>
 #include <pthread.h>
@@ -70,6 +72,8 @@ class Barrier {      // reusable barrier (futex-based pthread barrier: far cheap
 
 struct Team {
   Barrier block;
+  std::mutex named_mutex;
+  std::map<int, std::unique_ptr<Barrier>> named;
   std::unique_ptr<Barrier[]> warps;
   std::vector<std::vector<unsigned long long>> warp_buf;   // 32 slots of 8 bytes per warp
 };
@@ -200,15 +204,107 @@ inline unsigned ballot(bool pred) {
   return bits;
 }
 
-// PTX of the hardware pipelines (mbarrier, TMA, ...) has no meaning here: reaching it is a bug
+// whether tensor maps can be encoded (off: the library behaves as without the driver entry
+// point and every kernel takes its non-TMA instance)
+inline bool& tma_enabled() { static bool e = true; return e; }
+
+// ---- mbarrier + TMA (cp.async.bulk.tensor) model -------------------------------------------
+// State is kept beside the 64-bit words (keyed by address); one lock and one condition
+// variable for all barriers: the lattices of the tests are tiny.
+struct Mbar { int expected = 0, pending = 0; long tx = 0; unsigned phase = 0; };
+inline std::mutex& mbar_mutex() { static std::mutex m; return m; }
+inline std::condition_variable& mbar_cv() { static std::condition_variable c; return c; }
+inline std::unordered_map<const void*, Mbar>& mbars() {
+  static std::unordered_map<const void*, Mbar> t; return t;
+}
+inline void mbar_settle(Mbar& b) {           // a phase completes: all arrivals and all bytes
+  if (b.pending == 0 && b.tx == 0) { b.phase ^= 1u; b.pending = b.expected; }
+}
+inline void mbar_init(const void* p, unsigned count) {
+  std::lock_guard<std::mutex> lk(mbar_mutex());
+  Mbar b; b.expected = b.pending = int(count); mbars()[p] = b;
+}
+inline void mbar_arrive(const void* p) {
+  { std::lock_guard<std::mutex> lk(mbar_mutex()); Mbar& b = mbars()[p]; --b.pending; mbar_settle(b); }
+  mbar_cv().notify_all();
+}
+inline void mbar_expect_tx(const void* p, unsigned bytes) {
+  { std::lock_guard<std::mutex> lk(mbar_mutex()); Mbar& b = mbars()[p]; b.tx += bytes; --b.pending;
+    mbar_settle(b); }
+  mbar_cv().notify_all();
+}
+inline void mbar_complete_tx(const void* p, unsigned bytes) {
+  { std::lock_guard<std::mutex> lk(mbar_mutex()); Mbar& b = mbars()[p]; b.tx -= bytes; mbar_settle(b); }
+  mbar_cv().notify_all();
+}
+inline void mbar_wait(const void* p, unsigned parity) {   // until the phase of that parity is over
+  std::unique_lock<std::mutex> lk(mbar_mutex());
+  mbar_cv().wait(lk, [&] { return mbars()[p].phase != (parity & 1u); });
+}
+
+// software tensor map: what cuTensorMapEncodeTiled is given, stored in the 128 opaque bytes
+struct TensorMap {
+  char* base; int es; unsigned rank; unsigned long long dim[4]; unsigned long long stride[3];
+  unsigned box[4];
+};
+inline int encode_tiled(void* map, int dtype, unsigned rank, void* base,
+                        const unsigned long long* gdim, const unsigned long long* gstride,
+                        const unsigned* box, const unsigned*, int, int, int, int) {
+  if (!tma_enabled()) return 1;           // as if the driver refused: callers fall back
+  TensorMap t;
+  std::memset(&t, 0, sizeof(t));
+  t.base = static_cast<char*>(base);
+  t.es = dtype == 8 ? 8 : 4;              // CU_TENSOR_MAP_DATA_TYPE_FLOAT64 = 8 in the stub
+  t.rank = rank;
+  for (unsigned k = 0; k < 4; ++k) { t.dim[k] = k < rank ? gdim[k] : 1; t.box[k] = k < rank ? box[k] : 1; }
+  for (unsigned k = 0; k + 1 < rank; ++k) t.stride[k] = gstride[k];
+  static_assert(sizeof(TensorMap) <= 128, "tensor map model");
+  std::memcpy(map, &t, sizeof(t));
+  return 0;
+}
+// tile load: box elements innermost coordinate first, zeros outside the tensor, then the
+// byte count of the WHOLE box is credited to the mbarrier (as the hardware does)
+inline void tma_load_4d(void* dst, unsigned long long map, const void* bar, int c0, int c1, int c2,
+                        int c3) {
+  TensorMap t;
+  std::memcpy(&t, reinterpret_cast<const void*>(map), sizeof(t));
+  char* out = static_cast<char*>(dst);
+  const long long c[4] = {c0, c1, c2, c3};
+  for (unsigned i3 = 0; i3 < t.box[3]; ++i3)
+    for (unsigned i2 = 0; i2 < t.box[2]; ++i2)
+      for (unsigned i1 = 0; i1 < t.box[1]; ++i1)
+        for (unsigned i0 = 0; i0 < t.box[0]; ++i0) {
+          const long long g[4] = {c[0] + i0, c[1] + i1, c[2] + i2, c[3] + i3};
+          bool in = true;
+          for (int k = 0; k < 4; ++k) in = in && g[k] >= 0 && (unsigned long long)g[k] < t.dim[k];
+          if (in)
+            std::memcpy(out, t.base + g[0] * t.es + g[1] * (long long)t.stride[0] +
+                                 g[2] * (long long)t.stride[1] + g[3] * (long long)t.stride[2], t.es);
+          else
+            std::memset(out, 0, t.es);
+          out += t.es;
+        }
+  mbar_complete_tx(bar, t.box[0] * t.box[1] * t.box[2] * t.box[3] * t.es);
+}
+
+// PTX of hardware-only paths without a model here: reaching it is a bug
 inline void unsupported_ptx() {
   fprintf(stderr, "cuda_emu: PTX of a hardware-only path was reached\n");
   abort();
 }
-// bar.sync id, count: only the whole-block form is modelled
+// bar.sync id, count: the whole block, or a named barrier among `count` threads (the consumer
+// warps of the warp-specialised kernels)
 inline void named_barrier(int id, int count) {
-  if (id != 0 || count != int(blockDim.x * blockDim.y * blockDim.z)) unsupported_ptx();
-  team()->block.wait();
+  Team& tm = *team();
+  if (id == 0 && count == int(blockDim.x * blockDim.y * blockDim.z)) { tm.block.wait(); return; }
+  Barrier* b;
+  {
+    std::lock_guard<std::mutex> lk(tm.named_mutex);
+    auto& slot = tm.named[id];
+    if (!slot) { slot.reset(new Barrier); slot->reset(count); }
+    b = slot.get();
+  }
+  b->wait();
 }
 
 template <class T>

@@ -30,12 +30,17 @@ enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 template <typename F>
 static inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
 
-// driver entry points: none on the emulated device
+// driver entry points: the one the library asks for, served by the tensor-map model
 enum cudaDriverEntryPointQueryResult { cudaDriverEntryPointSuccess = 0,
                                        cudaDriverEntryPointSymbolNotFound = 1 };
 #define cudaEnableDefault 0
-static inline cudaError_t cudaGetDriverEntryPoint(const char*, void** fn, unsigned long long,
+static inline cudaError_t cudaGetDriverEntryPoint(const char* name, void** fn, unsigned long long,
                                                   cudaDriverEntryPointQueryResult* q) {
+  if (std::strcmp(name, "cuTensorMapEncodeTiled") == 0) {
+    *fn = reinterpret_cast<void*>(&emu::encode_tiled);
+    *q = cudaDriverEntryPointSuccess;
+    return cudaSuccess;
+  }
   *fn = nullptr;
   *q = cudaDriverEntryPointSymbolNotFound;
   return 1;

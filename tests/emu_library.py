@@ -22,22 +22,14 @@ EMU = os.path.join(ROOT, "tests", "cuda_emu")
 
 SOURCES = ["common.cu", "halo.cu", "rk_stage.cu", "stage_unfused.cu", "tensor_stage.cu",
            "reduce.cu", "expansion.cu", "diag.cu", "fd.cu",
-           "fused_stage.cu", "fused_stage_f64.cu", "fused_stage_f32.cu"]
+           "fused_stage.cu", "fused_stage_f64.cu", "fused_stage_f32.cu",
+           "tensor_stage_fused.cu"]
 #: the fused-stage units instantiate every kernel variant (incl. the TMA pipelines, which
 #: cannot run here: their PTX traps): compiled without optimisation to keep the build short
-UNOPTIMISED = {"fused_stage_f64.cu", "fused_stage_f32.cu"}
+UNOPTIMISED = {"fused_stage_f64.cu", "fused_stage_f32.cu", "tensor_stage_fused.cu"}
 
-#: headers replaced as a whole: the TMA pipeline of the finite-difference kernels reports
-#: "layout not eligible", so that psb_finite_difference takes its generic tile kernel (the
-#: path odd radii and unaligned layouts take on the GPU)
-SHADOWED = {
-    "fd_ws.cuh": """#pragma once
-namespace psb {
-template <typename T, int H, int MODE>
-static int launch_fd_ws(const FDParams<T>&, cudaStream_t) { return -1; }
-}  // namespace psb
-""",
-}
+SHADOWED = {}
+
 
 def _split_top_level(text):
     parts, depth, cur = [], 0, ""
@@ -109,9 +101,9 @@ _OPERAND = re.compile(r'"[=+]?[a-z]"\s*\(((?:[^()]|\([^()]*\))*)\)')
 
 
 def _asm_replacement(stmt):
-    """C++ meaning of one `asm volatile(...)` statement on the emulated paths; PTX that only
-    the hardware pipelines execute (mbarrier, TMA, prefetch) aborts if it is ever reached."""
-    ops = [m.group(1).strip() for m in _OPERAND.finditer(stmt)]
+    """C++ meaning of one `asm volatile(...)` statement under the execution model."""
+    ops = [re.sub(r"^smem_u32\((.*)\)$", r"\1", m.group(1).strip())
+           for m in _OPERAND.finditer(stmt)]
     if "griddepcontrol" in stmt:
         return ";"                               # no-ops without the launch attribute
     if "st.release.sys.global.u64" in stmt:
@@ -122,8 +114,25 @@ def _asm_replacement(stmt):
         return f"*(volatile double*)({ops[0]}) = ({ops[1]});"
     if "ld.volatile.global.b64" in stmt:
         return f"{ops[0]} = *(volatile unsigned long long*)({ops[1]});"
-    if "bar.sync %0, %1" in stmt:
-        return f"emu::named_barrier({ops[0]}, {ops[1]});"
+    m = re.search(r"bar\.sync (\w+|%0), (%\d)", stmt)
+    if m:
+        ident = ops[0] if m.group(1) == "%0" else m.group(1)
+        count = ops[1] if m.group(1) == "%0" else ops[0]
+        return f"emu::named_barrier({ident}, {count});"
+    # mbarrier / TMA (tests/cuda_emu/cuda_emu.h: the model)
+    if "mbarrier.init" in stmt:
+        return f"emu::mbar_init({ops[0]}, {ops[1]});"
+    if "mbarrier.arrive.expect_tx" in stmt:
+        return f"emu::mbar_expect_tx({ops[0]}, {ops[1]});"
+    if "mbarrier.arrive" in stmt:
+        return f"emu::mbar_arrive({ops[0]});"
+    if "mbarrier.try_wait.parity" in stmt:
+        return f"emu::mbar_wait({ops[0]}, {ops[1]});"
+    if "cp.async.bulk.tensor.4d.shared" in stmt:
+        return ("emu::tma_load_4d(" + ", ".join(ops[:7]) + ");")
+    if ("fence.mbarrier_init" in stmt or "fence.proxy.async" in stmt
+            or "cp.async.bulk.prefetch" in stmt or "prefetch.tensormap" in stmt):
+        return ";"                               # ordering / cache hints
     return "emu::unsupported_ptx();"
 
 
@@ -156,6 +165,7 @@ def transform_asm(src):
 _CONTROL = '''
 // knobs of the execution model, exported next to the C ABI
 extern "C" void emu_set_reverse_blocks(int v) { emu::reverse_blocks() = v != 0; }
+extern "C" void emu_set_tma(int v) { emu::tma_enabled() = v != 0; }
 '''
 
 _lib = None

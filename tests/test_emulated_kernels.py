@@ -1,12 +1,18 @@
 """
-The GPU parity tests of the stand-alone kernels, EXECUTED in the CPU suite: the bodies of
-tests/test_gpu_kernels.py and tests/test_gpu_api.py run unchanged against a HOST build of the
-same CUDA sources (tests/emu_library.py: halo, element-wise LSRK / classical RK / tensor stages,
-finite differences (generic tile kernel), reductions, background; launch syntax transformed,
-everything else compiled as it is with -ffp-contract=off, i.e. the strict build's arithmetic).
-On the GPU box the same functions are the hard gates; here they check the kernels' logic,
-the C ABI and the Python layer above it against the oracle without a device.  The TMA pipelines
-(fused stages) exist on the hardware only and are not covered here.
+The GPU parity tests, EXECUTED in the CPU suite: the bodies of tests/test_gpu_kernels.py and
+tests/test_gpu_api.py run unchanged against a HOST build of the same CUDA sources
+(tests/emu_library.py) on the execution model of tests/cuda_emu/cuda_emu.h, which includes
+mbarriers, TMA tile loads (cp.async.bulk.tensor with a software tensor map), named barriers
+and warp shuffles.  Covered: halos, element-wise LSRK / classical RK / tensor stages, finite
+differences (TMA pipeline and generic tile kernel), reductions, background -- and the hot
+kernels themselves: the warp-specialised TMA pipeline of the fused scalar stage
+(fused_stage_ws.cuh), its persistent variant (fused_stage_pws.cuh), the fused tensor stage
+(tensor_stage_fused.cu) and the generic instance, bit-exact against the oracle
+(-ffp-contract=off = the strict build's arithmetic), with the in-kernel stage tail.
+On the GPU box the same functions are the hard gates; here they check the kernels' logic
+(ring protocol, parities, x chunks, halo write-through, energy rows), the C ABI and the Python
+layer above it without a device.  Not modelled: the memory model, asynchrony, performance;
+the NVRTC-generated instances of the pipeline are exercised on the GPU only.
 """
 import numpy as np
 import pytest
@@ -37,16 +43,9 @@ def device(monkeypatch):
     monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
     monkeypatch.setattr(torch.cuda, "current_device", lambda: 0)
 
-    # the TMA instances of the fused stage exist on the hardware only: automatic kernel
-    # selection (tune_variant 0) is pinned to the cooperative-loader instance here
-    from pystella_b200 import _kernels
-    real_stage = _kernels.scalar_stage
-
-    def scalar_stage(**kw):
-        if kw.get("fused") and kw.get("variant", 0) == 0:
-            kw["variant"] = 2
-        return real_stage(**kw)
-    monkeypatch.setattr(_kernels, "scalar_stage", scalar_stage)
+    # polynomial potentials through the coefficient tables (the NVRTC-generated instances of
+    # the pipeline are a GPU-only path)
+    monkeypatch.setenv("PSB_JIT", "0")
     with emulated_device(monkeypatch) as dev:
         # the watcher CTA of the fused stage (csrc/stage_tail.cuh) waits for the rows of all
         # other CTAs: on a model that runs blocks one after the other it has to come last
@@ -92,10 +91,6 @@ def test_plane_wave_eigenvalues(device, h):
 
 # ---- the reference-facing Python API ----------------------------------------------------
 
-def test_wave_equation_example_unfused(device):
-    API.test_wave_equation_example((24, 20, 36), 2, False)
-
-
 @pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-12), (np.float32, 2e-5)])
 def test_scalar_sector_two_fields_unfused(device, dtype, tol):
     API.test_scalar_sector_two_fields(False, dtype, tol)
@@ -133,18 +128,34 @@ def test_classical_rk_wave_equation(device, name):
     API.test_classical_rk_wave_equation_device(name)
 
 
-# ---- the fused stage: its generic instance (cooperative loader instead of TMA) -----------
-# Same stencil / right-hand side / low-storage update / energy sums / write-through halos /
-# in-kernel stage tail as the TMA pipelines, which exist on the hardware only.
-
-FUSED_CASES = [c for c in KER.CASES
-               if c[4] in (2, 3) or c[1] % 2 == 1 or c[0][2] % 2 == 1]
-
+# ---- the fused stages ---------------------------------------------------------------------
 
 @pytest.mark.parametrize("stage", [0, 2])
-@pytest.mark.parametrize("N,h,n,pot,variant", FUSED_CASES)
-def test_fused_stage_generic_kernel_bit_exact(device, N, h, n, pot, variant, stage):
+@pytest.mark.parametrize("N,h,n,pot,variant", KER.CASES)
+def test_fused_stage_bit_exact(device, N, h, n, pot, variant, stage):
+    """Every case of the GPU test: the TMA pipeline for even radii and aligned rows, the
+    generic instance (cooperative loader / scalar) for the others."""
     KER.test_fused_stage_fp64(N, h, n, pot, variant, True, stage)
+
+
+@pytest.mark.parametrize("N,n,pot", [((32, 32, 32), 1, KER.POT1), ((24, 20, 64), 2, KER.POT2)])
+def test_persistent_fused_stage_bit_exact(device, N, n, pot):
+    """tune_variant 30: persistent CTAs, continuous pipeline, atomically claimed chunks."""
+    KER.test_fused_stage_fp64(N, 2, n, pot, 30, True, 2)
+
+
+def test_tma_path_is_the_one_that_ran(device):
+    """With tensor-map encoding switched off the automatic variant has nothing to launch on a
+    TMA-eligible layout (-1), while the cooperative-loader variant still runs: the cases above
+    did go through the pipeline."""
+    from pystella_b200._lib import PsbError
+    device.main.emu_set_tma(0)
+    try:
+        with pytest.raises(PsbError, match="code -1"):
+            KER.test_fused_stage_fp64((20, 24, 36), 2, 1, KER.POT1, 0, True, 2)
+        KER.test_fused_stage_fp64((20, 24, 36), 2, 1, KER.POT1, 2, True, 2)
+    finally:
+        device.main.emu_set_tma(1)
 
 
 def test_fused_x_range_split_equals_whole(device):
@@ -156,8 +167,11 @@ def test_fused_stage_fp32(device, N, h, n, pot):
     KER.test_fused_stage_fp32(N, h, n, pot)
 
 
-def test_fused_scalars_with_unfused_tensor_sector(device, monkeypatch):
-    API.test_unfused_gw_sector_with_fused_scalars(np.float64, 1e-12, monkeypatch)
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-12)])
+def test_two_scalars_plus_fused_tensor_sector(device, dtype, tol):
+    """Config 4's stage: two coupled scalars (TMA pipeline) + the fused tensor stage
+    (tensor_stage_fused.cu: six Laplacians and the source gradients in-kernel)."""
+    API.test_two_scalars_plus_gw_sector(True, dtype, tol)
 
 
 def test_fused_two_fields_and_generic_dict(device):
@@ -165,8 +179,9 @@ def test_fused_two_fields_and_generic_dict(device):
     API.test_generic_dict_with_friction_matches_sector()
 
 
-def test_fused_wave_equation_example(device):
-    API.test_wave_equation_example((32, 32, 32), 1, True)
+@pytest.mark.parametrize("N,h", [((24, 20, 36), 2)])
+def test_fused_wave_equation_example(device, N, h):
+    API.test_wave_equation_example(N, h, True)
 
 
 @pytest.mark.parametrize("nscalars", [1, 2])
@@ -177,13 +192,15 @@ def test_device_resident_preheating_loop(device, nscalars):
 
 
 @pytest.mark.parametrize("h, N", [(1, (12, 10, 16)), (2, (12, 10, 17)), (3, (8, 12, 14))])
-def test_fused_two_fields_on_non_tma_layouts(device, h, N):
-    ZZ.test_fused_two_fields_on_non_tma_layouts(h, N)
+def test_fused_two_fields_on_non_tma_layouts(device, h, N, monkeypatch):
+    monkeypatch.setenv("PSB_JIT", "1")      # the generated instance is preferred ...
+    ZZ.test_fused_two_fields_on_non_tma_layouts(h, N)   # ... and the tables serve the layout
 
 
 # ---- run-time generated kernels next to the hand-written ones ------------------------------
 
-def test_generated_kernels_of_the_python_layer(device):
+def test_generated_kernels_of_the_python_layer(device, monkeypatch):
+    monkeypatch.setenv("PSB_JIT", "1")
     """Custom-stencil FiniteDifferencer, a classical RK stage for an arbitrary rhs_dict and
     non-polynomial reducers: generated sources on the model, hand-written kernels around
     them from the host build."""
