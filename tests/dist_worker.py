@@ -329,6 +329,67 @@ def _single_rank_spectrum(full, grid, dk, volume):
         return num_bins, bin_counts, norm * hist / bin_counts
 
 
+def _emulate_cuda():
+    """Case `emu_fused`: the multi-rank fused stepper on gloo ranks WITHOUT a GPU -- host
+    tensors, the CUDA kernels executed on the CPU model (tests/emu_device.py), streams and
+    events reduced to program order.  -> the object that keeps the patches alive."""
+    import contextlib
+    import types
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from emu_device import emulated_device
+
+    class Patches:
+        def __init__(self):
+            self.undo = []
+
+        def setattr(self, obj, name, val):
+            self.undo.append((obj, name, getattr(obj, name)))
+            setattr(obj, name, val)
+
+    mp_ = Patches()
+    stack = contextlib.ExitStack()
+    dev = stack.enter_context(emulated_device(mp_))
+    dev.main.emu_set_reverse_blocks(1)
+    os.environ["PSB_JIT"] = "0"          # coefficient tables (generated instances: GPU only)
+
+    class Stream:
+        def __init__(self, *a, **k):
+            pass
+
+        def wait_event(self, ev):
+            pass
+
+        def wait_stream(self, st):
+            pass
+
+    class Event:
+        def __init__(self, *a, **k):
+            pass
+
+        def record(self, stream=None):
+            pass
+
+        def synchronize(self):
+            pass
+
+    def strip(fn):
+        def wrapped(*a, **k):
+            k.pop("device", None)
+            return fn(*a, **k)
+        return wrapped
+
+    mp_.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self.clone())   # a copy, like H2D
+    for name in ("zeros", "empty", "ones", "tensor", "full"):
+        mp_.setattr(torch, name, strip(getattr(torch, name)))
+    mp_.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    mp_.setattr(torch.cuda, "current_device", lambda: 0)
+    mp_.setattr(torch.cuda, "Stream", Stream)
+    mp_.setattr(torch.cuda, "Event", Event)
+    mp_.setattr(torch.cuda, "current_stream", lambda *a, **k: Stream())
+    mp_.setattr(torch.cuda, "stream", lambda s: contextlib.nullcontext())
+    return types.SimpleNamespace(stack=stack, patches=mp_, dev=dev)
+
+
 def _worker(rank, world, port, case, args):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank),
                       WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
@@ -355,6 +416,9 @@ def _worker(rank, world, port, case, args):
         elif case == "gpu_fused":
             _fused_case(rank, world, backend, int(args[0]), args[1] == "1",
                         args[2] if len(args) > 2 else "peer")
+        elif case == "emu_fused":
+            keep = _emulate_cuda()      # noqa: F841 -- patches live as long as the worker
+            _fused_case(rank, world, backend, int(args[0]), args[1] == "1", "nccl")
         else:
             raise ValueError(case)
         dist.barrier()

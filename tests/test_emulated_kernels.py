@@ -197,6 +197,21 @@ def test_fused_two_fields_on_non_tma_layouts(device, h, N, monkeypatch):
     ZZ.test_fused_two_fields_on_non_tma_layouts(h, N)   # ... and the tables serve the layout
 
 
+# ---- several ranks: boundary / interior launches, face exchange, energy all-reduce ----------
+
+@pytest.mark.parametrize("world, nscalars", [(2, 1), (3, 2)])
+def test_fused_stepper_on_gloo_ranks(world, nscalars):
+    """tests/dist_worker.py::_fused_case (the 2-GPU test of the send/recv halo mode) on gloo
+    ranks without a GPU: every rank runs the stage kernels on the execution model (boundary
+    slabs in one two-range launch, interior launch), exchanges the x faces of the new state
+    with torch.distributed, all-reduces the energy sums and advances the background; fields
+    against the global oracle to 1e-12, energies bit-identical on all ranks."""
+    import emu_library
+    from test_distributed import _run
+    emu_library.build()                 # once, before the ranks start
+    _run("emu_fused", world, str(nscalars), "1", timeout=600)
+
+
 # ---- run-time generated kernels next to the hand-written ones ------------------------------
 
 def test_generated_kernels_of_the_python_layer(device, monkeypatch):
