@@ -26,8 +26,17 @@ from test_cuda_emu import build_emu
 NUM_SMS = 3      # small, so that the persistent kernels loop over several row groups per CTA
 
 
+class EmuFusedHandle:
+    """A generated instance of the fused pipeline (pystella_b200/fused_jit.py): the functor
+    source that NVRTC would get, and the kernel instance to call."""
+
+    def __init__(self, source, name_expr):
+        self.source, self.name_expr = source, name_expr
+
+
 class EmuJitLibrary:
-    """Stands in for libpystella_b200_jit.so: handles are KernelSource objects."""
+    """Stands in for libpystella_b200_jit.so: handles are KernelSource objects (generated
+    maps / histograms / stencils) or EmuFusedHandle objects (generated fused stages)."""
 
     def __init__(self):
         self.launches = []
@@ -51,6 +60,36 @@ class EmuJitLibrary:
         from pystella_b200.codegen import JitArgs
         args = C.cast(params[0], C.POINTER(JitArgs))
         return self._run(handle, args, (gx, gy, gz), (bx, by, bz), smem)
+
+    def psb_jit_launch_params_v(self, handle, params, gx, gy, gz, bx, by, bz, smem, flags,
+                                stream):
+        """The generated instance of the warp-specialised pipeline: same parameter list as on
+        the GPU (FusedParams, four tensor maps, user scalars)."""
+        import re
+        import emu_library
+        m = re.match(r"psb::fused_stage_ws_kernel<(\w+), (\d+), (\d+),", handle.name_expr)
+        T, NF = m.group(1), m.group(3)
+        driver = (
+            "#define __CUDACC_RTC__ 1\n" + handle.source +
+            'extern "C" void run(void** params, int gx, int gy, int gz, int threads, '
+            "long long smem) {\n"
+            f"  const psb::FusedParams<{T}, {NF}>& p = "
+            f"*static_cast<const psb::FusedParams<{T}, {NF}>*>(params[0]);\n"
+            "  const CUtensorMap* m[4];\n"
+            "  for (int i = 0; i < 4; ++i) m[i] = static_cast<const CUtensorMap*>(params[1 + i]);\n"
+            "  const psb::PsbJitScalars& js = *static_cast<const psb::PsbJitScalars*>(params[5]);\n"
+            "  emu::launch_smem(dim3(gx, gy, gz), dim3(threads, 1, 1), (size_t)smem, [&] {\n"
+            f"    {handle.name_expr}(p, *m[0], *m[1], *m[2], *m[3], js); }});\n}}\n")
+        here = os.path.dirname(os.path.abspath(__file__))
+        lib = build_emu(driver, "emu_fused_jit",
+                        first=["-include", os.path.join(here, "cuda_emu", "cuda_emu.h"),
+                               "-I" + emu_library.rtc_include_dir(),
+                               "-I" + os.path.join(here, "cuda_emu", "stubs"),
+                               "-ffp-contract=off"])
+        self.launches.append((handle.name_expr, (gx, gy, gz), (bx, by, bz), smem))
+        lib.run(params, C.c_int(int(gx)), C.c_int(int(gy)), C.c_int(int(gz)), C.c_int(int(bx)),
+                C.c_longlong(int(smem)))
+        return 0
 
     def psb_jit_last_log(self):
         return b""
@@ -76,6 +115,10 @@ def emulated_device(monkeypatch):
     monkeypatch.setattr(_lib, "on_device", lambda t: True)
     monkeypatch.setattr(_lib, "stream_ptr", lambda queue=None: None)
     monkeypatch.setattr(_lib, "load", lambda strict=False: main)
+    from pystella_b200 import fused_jit
+    monkeypatch.setattr(fused_jit.GeneratedFusedStage, "compile",
+                        lambda self, plan, strict=False: EmuFusedHandle(
+                            self.source, self.name_expression(plan)))
     monkeypatch.setattr(codegen.JitLibrary, "compile", classmethod(lambda cls, ksrc: ksrc))
     monkeypatch.setattr(codegen.JitLibrary, "get", classmethod(lambda cls: jit))
     monkeypatch.setattr(torch.cuda, "get_device_properties",

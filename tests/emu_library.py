@@ -169,11 +169,12 @@ extern "C" void emu_set_tma(int v) { emu::tma_enabled() = v != 0; }
 '''
 
 _lib = None
+_dir = None
 
 
 def build(verbose=False):
     """-> ctypes library with the emulated entry points (built once per source state)."""
-    global _lib
+    global _lib, _dir
     if _lib is not None:
         return _lib
     texts = {}
@@ -224,5 +225,31 @@ def build(verbose=False):
         tmp = so + f".{os.getpid()}.tmp"
         subprocess.check_call(["g++", "-shared", "-pthread", "-o", tmp] + objs)
         os.replace(tmp, so)
+    # second copy of the headers for sources written for NVRTC (the generated instances of
+    # the pipeline): they are compiled with __CUDACC_RTC__ defined, which drops the host code;
+    # only the first guard of common.cuh (its own stand-ins for the system headers) must go
+    rtc = os.path.join(d, "rtc")
+    if not os.path.isdir(rtc):
+        os.makedirs(rtc + ".tmp", exist_ok=True)
+        for hdr, text in headers.items():
+            if hdr == "common.cuh":
+                text = text.replace("#ifndef __CUDACC_RTC__", "#if 1  /* emulated */", 1)
+            if hdr == "fused_stage_impl.cuh":
+                # the persistent variant has no generated instances, and g++ (unlike NVRTC)
+                # looks names of its templates up before fused_stage_ws.cuh has defined them
+                text = text.replace('#include "fused_stage_pws.cuh"', "")
+            with open(os.path.join(rtc + ".tmp", hdr), "w") as fh:
+                fh.write(text)
+        try:
+            os.replace(rtc + ".tmp", rtc)
+        except OSError:
+            pass                      # another process was faster
+    _dir = d
     _lib = C.CDLL(so)
     return _lib
+
+
+def rtc_include_dir():
+    """Directory with the transformed headers for NVRTC-style sources (after build())."""
+    build()
+    return os.path.join(_dir, "rtc")

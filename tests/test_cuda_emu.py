@@ -25,7 +25,7 @@ CSRC = os.path.join(ROOT, "pystella_b200", "csrc")
 _cache = {}
 
 
-def build_emu(source_text, tag, extra=()):
+def build_emu(source_text, tag, extra=(), first=()):
     """g++-compile `source_text` on top of cuda_emu.h into a shared object (cached)."""
     key = hashlib.sha256(source_text.encode()).hexdigest()[:16]
     if key not in _cache:
@@ -35,7 +35,8 @@ def build_emu(source_text, tag, extra=()):
         with open(cpp, "w") as fh:
             fh.write(source_text)
         subprocess.check_call(["g++", "-std=c++17", "-O1", "-pthread", "-shared", "-fPIC",
-                               "-Wno-unknown-pragmas", "-I" + EMU, "-I" + CSRC,
+                               "-Wno-unknown-pragmas", "-Wno-attributes"] + list(first)
+                              + ["-I" + EMU, "-I" + CSRC,
                                "-I" + os.path.join(ROOT, "include")] + list(extra)
                               + [cpp, "-o", so])
         _cache[key] = C.CDLL(so)

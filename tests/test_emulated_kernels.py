@@ -11,8 +11,8 @@ kernels themselves: the warp-specialised TMA pipeline of the fused scalar stage
 (-ffp-contract=off = the strict build's arithmetic), with the in-kernel stage tail.
 On the GPU box the same functions are the hard gates; here they check the kernels' logic
 (ring protocol, parities, x chunks, halo write-through, energy rows), the C ABI and the Python
-layer above it without a device.  Not modelled: the memory model, asynchrony, performance;
-the NVRTC-generated instances of the pipeline are exercised on the GPU only.
+layer above it without a device.  Not modelled: the memory model, asynchrony, performance.  The NVRTC-generated instances of the pipeline run
+here as well: their functor source is compiled for the model instead of with NVRTC.
 """
 import numpy as np
 import pytest
@@ -195,6 +195,29 @@ def test_device_resident_preheating_loop(device, nscalars):
 def test_fused_two_fields_on_non_tma_layouts(device, h, N, monkeypatch):
     monkeypatch.setenv("PSB_JIT", "1")      # the generated instance is preferred ...
     ZZ.test_fused_two_fields_on_non_tma_layouts(h, N)   # ... and the tables serve the layout
+
+
+# ---- NVRTC-generated instances of the pipeline (non-quadratic potentials by default) --------
+
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-12), (np.float32, 2e-5)])
+def test_generated_instance_two_coupled_fields(device, monkeypatch, dtype, tol):
+    """Config 4's scalar stage: the warp-specialised pipeline compiled with the potential
+    m^2 phi^2 / 2 + g^2 phi^2 chi^2 / 2 inlined (pystella_b200/fused_jit.py).  The functor
+    source NVRTC would get is compiled for the model and launched with the library's launch
+    plan (FusedParams, four tensor maps, user scalars) -- five stages against the oracle."""
+    monkeypatch.setenv("PSB_JIT", "1")
+    API.test_scalar_sector_two_fields(True, dtype, tol)
+    assert device.jit.launches[-1][0].startswith("psb::fused_stage_ws_kernel<")
+
+
+def test_generated_instance_cosine_potential_and_device_loop(device, monkeypatch):
+    """A non-polynomial right-hand side (tests/test_gpu_generated.py) in the fused pipeline,
+    and the device-resident loop (energy sums of the generated potential + in-kernel tail)."""
+    monkeypatch.setenv("PSB_JIT", "1")
+    GEN._case_generated_rhs("float64", 1e-12)
+    GEN._case_generated_loop()
+    API.test_device_resident_preheating_loop(2)
+    assert device.jit.launches[-1][0].startswith("psb::fused_stage_ws_kernel<double, 2, 2,")
 
 
 # ---- several ranks: boundary / interior launches, face exchange, energy all-reduce ----------
