@@ -222,7 +222,7 @@ def test_generated_instance_cosine_potential_and_device_loop(device, monkeypatch
 
 # ---- several ranks: boundary / interior launches, face exchange, energy all-reduce ----------
 
-@pytest.mark.parametrize("world, nscalars", [(2, 1), (3, 2)])
+@pytest.mark.parametrize("world, nscalars", [(3, 2)])
 def test_fused_stepper_on_gloo_ranks(world, nscalars):
     """tests/dist_worker.py::_fused_case (the 2-GPU test of the send/recv halo mode) on gloo
     ranks without a GPU: every rank runs the stage kernels on the execution model (boundary
