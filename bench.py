@@ -70,7 +70,7 @@ def parse():
     p.add_argument("--no-extras", action="store_true",
                    help="skip the extra records of the default N=1 run (other configurations "
                         "and the diagnostics kernels, each in its own bounded subprocess)")
-    p.add_argument("--extras-budget", type=float, default=240.0,
+    p.add_argument("--extras-budget", type=float, default=200.0,
                    help="wall-clock budget (s) of all extra records together")
     p.add_argument("--diagnostics", action="store_true",
                    help="time the diagnostics kernels only (histograms, spectrum binning) "
@@ -746,7 +746,7 @@ def run_extras(args):
                "--no-e2e", "--no-cpu", "--no-extras"] + extra
         t0 = time.perf_counter()
         try:
-            res = subprocess.run(cmd, capture_output=True, text=True, timeout=min(left, 150.0),
+            res = subprocess.run(cmd, capture_output=True, text=True, timeout=min(left, 120.0),
                                  cwd=ROOT)
             rec = _last_json_line(res.stdout)
             if rec is None:

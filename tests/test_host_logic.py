@@ -95,7 +95,7 @@ def test_bench_extras_are_bounded_and_never_fatal(monkeypatch):
 
     def fake_run(cmd, **kw):
         calls.append((cmd, kw))
-        assert "--no-extras" in cmd and "--no-cpu" in cmd and kw["timeout"] <= 150
+        assert "--no-extras" in cmd and "--no-cpu" in cmd and kw["timeout"] <= 120
         if "--diagnostics" in cmd:
             return types.SimpleNamespace(returncode=0, stderr="", stdout=json.dumps(
                 {"bin_power": {"ok": True}}) + "\n")
