@@ -24,6 +24,9 @@ EMU = os.path.join(ROOT, "tests", "cuda_emu")
 CSRC = os.path.join(ROOT, "pystella_b200", "csrc")
 _cache = {}
 
+# a kernel that hangs on the execution model (a protocol bug) must fail the run, not stall it
+pytestmark = pytest.mark.timeout(600, method="thread")
+
 
 def build_emu(source_text, tag, extra=(), first=()):
     """g++-compile `source_text` on top of cuda_emu.h into a shared object (cached)."""

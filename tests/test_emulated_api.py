@@ -13,6 +13,9 @@ import pystella_b200 as ps
 from emu_device import NUM_SMS, emulated_device
 from pystella_b200.field import var
 
+# a kernel that hangs on the execution model (a protocol bug) must fail the run, not stall it
+pytestmark = pytest.mark.timeout(600, method="thread")
+
 
 def test_histogrammer_through_the_emulated_device(monkeypatch):
     """test/test_histogram.py of the reference: two histograms sharing a bin expression."""

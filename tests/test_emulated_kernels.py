@@ -24,6 +24,9 @@ import test_gpu_kernels as KER
 import test_zz_gpu_diagnostics as ZZ
 from emu_device import emulated_device
 
+# a kernel that hangs on the execution model (a protocol bug) must fail the run, not stall it
+pytestmark = pytest.mark.timeout(600, method="thread")
+
 
 @pytest.fixture
 def device(monkeypatch):
