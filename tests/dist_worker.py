@@ -329,6 +329,73 @@ def _single_rank_spectrum(full, grid, dk, volume):
         return num_bins, bin_counts, norm * hist / bin_counts
 
 
+def _install_shared_memory_peers(mp_):
+    """Peer memory between the ranks of one node, for the emulated device: POSIX shared
+    memory takes the place of NVLink-mapped allocations.  `torch.distributed.
+    _symmetric_memory` (which pystella_b200/peer.py uses for allocation and address exchange
+    only) is replaced by a module with the same three calls: `empty` allocates a named
+    segment, `rendezvous` exchanges the names over the process group and maps the peers'
+    segments, `get_buffer(q, ...)` is this process's view of rank q's segment.  The kernels
+    of the ranks run concurrently in their own processes, so the flag barriers of
+    psb_expansion_stage_peer / the in-kernel tail really wait on one another."""
+    import atexit
+    import types
+    from multiprocessing import shared_memory
+
+    owned, mapped = {}, []
+
+    def empty(*size, dtype=torch.float64, device=None):
+        numel = int(np.prod(size)) if size else 1
+        nbytes = max(1, numel * torch.empty(0, dtype=dtype).element_size())
+        shm = shared_memory.SharedMemory(create=True, size=nbytes)
+        t = torch.frombuffer(shm.buf, dtype=dtype, count=numel)
+        t.zero_()
+        owned[t.data_ptr()] = (shm, numel, dtype)
+        return t
+
+    class Handle:
+        def __init__(self, views):
+            self.views = views
+
+        def barrier(self, *a, **k):
+            dist.barrier()
+
+        def get_buffer(self, q, shape, dtype, *a, **k):
+            n = int(np.prod(shape))
+            return self.views[q].view(dtype)[:n].view(tuple(shape))
+
+    def rendezvous(buf, group_name=None):
+        shm, numel, dtype = owned[buf.data_ptr()]
+        names = [None] * dist.get_world_size()
+        dist.all_gather_object(names, (shm.name, numel))
+        views = []
+        for q, (name, n) in enumerate(names):
+            if q == dist.get_rank():
+                views.append(buf)
+                continue
+            peer = shared_memory.SharedMemory(name=name)
+            mapped.append(peer)
+            views.append(torch.frombuffer(peer.buf, dtype=dtype, count=n))
+        dist.barrier()
+        return Handle(views)
+
+    def cleanup():
+        for shm, _, _ in owned.values():
+            try:
+                shm.unlink()
+            except Exception:  # noqa: BLE001
+                pass
+    atexit.register(cleanup)
+
+    fake = types.ModuleType("torch.distributed._symmetric_memory")
+    fake.empty, fake.rendezvous = empty, rendezvous
+    sys.modules["torch.distributed._symmetric_memory"] = fake
+    torch.distributed._symmetric_memory = fake
+    from pystella_b200 import peer
+    mp_.setattr(peer, "peer_memory_available",
+                lambda decomp: decomp is not None and decomp.nranks > 1)
+
+
 def _emulate_cuda():
     """Case `emu_fused`: the multi-rank fused stepper on gloo ranks WITHOUT a GPU -- host
     tensors, the CUDA kernels executed on the CPU model (tests/emu_device.py), streams and
@@ -379,6 +446,7 @@ def _emulate_cuda():
         return wrapped
 
     mp_.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self.clone())   # a copy, like H2D
+    _install_shared_memory_peers(mp_)
     for name in ("zeros", "empty", "ones", "tensor", "full"):
         mp_.setattr(torch, name, strip(getattr(torch, name)))
     mp_.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
@@ -416,9 +484,13 @@ def _worker(rank, world, port, case, args):
         elif case == "gpu_fused":
             _fused_case(rank, world, backend, int(args[0]), args[1] == "1",
                         args[2] if len(args) > 2 else "peer")
+        elif case == "emu_fused_gw":
+            keep = _emulate_cuda()      # noqa: F841
+            _fused_gw_case(rank, world, backend, args[0], len(args) > 1 and args[1] == "1")
         elif case == "emu_fused":
             keep = _emulate_cuda()      # noqa: F841 -- patches live as long as the worker
-            _fused_case(rank, world, backend, int(args[0]), args[1] == "1", "nccl")
+            _fused_case(rank, world, backend, int(args[0]), args[1] == "1",
+                        args[2] if len(args) > 2 else "nccl")
         else:
             raise ValueError(case)
         dist.barrier()

@@ -223,19 +223,40 @@ def test_generated_instance_cosine_potential_and_device_loop(device, monkeypatch
     assert device.jit.launches[-1][0].startswith("psb::fused_stage_ws_kernel<double, 2, 2,")
 
 
-# ---- several ranks: boundary / interior launches, face exchange, energy all-reduce ----------
+# ---- several ranks -------------------------------------------------------------------------
+# The bodies of the multi-GPU tests (tests/dist_worker.py) on gloo ranks without a GPU.  Every
+# rank is a process that runs the stage kernels on the execution model; the ranks really run
+# concurrently, so flag barriers wait on one another.
 
-@pytest.mark.parametrize("world, nscalars", [(3, 2)])
-def test_fused_stepper_on_gloo_ranks(world, nscalars):
-    """tests/dist_worker.py::_fused_case (the 2-GPU test of the send/recv halo mode) on gloo
-    ranks without a GPU: every rank runs the stage kernels on the execution model (boundary
-    slabs in one two-range launch, interior launch), exchanges the x faces of the new state
-    with torch.distributed, all-reduces the energy sums and advances the background; fields
-    against the global oracle to 1e-12, energies bit-identical on all ranks."""
+def _run_ranks(case, world, *args):
     import emu_library
     from test_distributed import _run
     emu_library.build()                 # once, before the ranks start
-    _run("emu_fused", world, str(nscalars), "1", timeout=600)
+    _run(case, world, *args, timeout=900)
+
+
+def test_fused_stepper_send_recv_halos_on_three_ranks():
+    """Send/recv halo mode: boundary slabs in one two-range launch, interior launch, x faces
+    of the new state exchanged with torch.distributed, energy sums all-reduced, background
+    advanced; two coupled fields against the global oracle, energies bit-identical on all
+    ranks."""
+    _run_ranks("emu_fused", 3, "2", "1", "nccl")
+
+
+def test_fused_stepper_peer_memory_halos_on_two_ranks():
+    """The default multi-GPU schedule: the stage kernels store their boundary planes straight
+    into the neighbour's halos (POSIX shared memory stands in for NVLink peer mappings, see
+    dist_worker._install_shared_memory_peers), psb_expansion_stage_peer all-gathers the
+    energy sums over peer memory, is the inter-rank barrier and advances the background;
+    uneven slabs; fields against the global oracle, energies bit-identical on both ranks."""
+    _run_ranks("emu_fused", 2, "1", "1", "peer")
+
+
+def test_config4_structure_over_peer_memory_with_in_kernel_tail():
+    """Two coupled scalars + fused tensor stage on two ranks, fp32: both kernels store into
+    the neighbour's halos, the tensor kernel's watcher CTA runs the inter-rank exchange and
+    the background stage (tune peer_tail); == the C oracle on the global lattice."""
+    _run_ranks("emu_fused_gw", 2, "f32", "1")
 
 
 # ---- run-time generated kernels next to the hand-written ones ------------------------------
