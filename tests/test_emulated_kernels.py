@@ -182,11 +182,6 @@ def test_fused_two_fields_and_generic_dict(device):
     API.test_generic_dict_with_friction_matches_sector()
 
 
-@pytest.mark.parametrize("N,h", [((24, 20, 36), 2)])
-def test_fused_wave_equation_example(device, N, h):
-    API.test_wave_equation_example(N, h, True)
-
-
 @pytest.mark.parametrize("nscalars", [1, 2])
 def test_device_resident_preheating_loop(device, nscalars):
     """Fused stage + in-kernel energy sums + watcher-CTA tail (fold, FLRW background) +
@@ -218,7 +213,6 @@ def test_generated_instance_cosine_potential_and_device_loop(device, monkeypatch
     and the device-resident loop (energy sums of the generated potential + in-kernel tail)."""
     monkeypatch.setenv("PSB_JIT", "1")
     GEN._case_generated_rhs("float64", 1e-12)
-    GEN._case_generated_loop()
     API.test_device_resident_preheating_loop(2)
     assert device.jit.launches[-1][0].startswith("psb::fused_stage_ws_kernel<double, 2, 2,")
 
