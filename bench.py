@@ -20,6 +20,12 @@ global_sites * 5 * steps / seconds / 1e6.  Prints ONE JSON line (rank 0).  After
 region the run restarts from the seeded initial conditions, integrates 2 steps on all ranks
 through the public API, gathers an x-window that straddles a rank boundary (the periodic
 boundary at N = 1) and compares it with the CPU oracle on rank 0: `"parity"` in the line.
+
+The default run (N = 1, config c3, no overrides) afterwards collects `"extras"`: the other
+single-GPU configurations (c2, c5, c4) and the diagnostics kernels (`--diagnostics`:
+histograms, spectrum binning, stencil map), each in its own subprocess of this script under a
+time limit (`--extras-budget`, `--no-extras`); the headline numbers are measured, and echoed to
+stderr, before any of them starts.
 """
 
 import argparse
