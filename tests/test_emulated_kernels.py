@@ -253,6 +253,28 @@ def test_config4_structure_over_peer_memory_with_in_kernel_tail():
     _run_ranks("emu_fused_gw", 2, "f32", "1")
 
 
+# ---- the GPU gates of the diagnostics kernels (tests/test_zz_gpu_diagnostics.py) -------------
+
+@pytest.mark.parametrize("grid, is_real, dtype, k_power, bw_scale", [
+    ((32, 24, 40), True, "f64", 3, 1.0), ((16, 20, 70), True, "f32", 2.5, 1.0),
+    ((16, 20, 140), False, "f64", 0, 1.0), ((24, 24, 24), True, "f64", 1, 0.002)])
+def test_bin_power_gpu_gate(device, grid, is_real, dtype, k_power, bw_scale):
+    ZZ.test_bin_power_kernel(grid, is_real, dtype, k_power, bw_scale)
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+def test_histogram_gpu_gates(device, monkeypatch, dtype):
+    monkeypatch.setenv("PSB_JIT", "1")
+    ZZ.test_generated_histograms_match_numpy(dtype)
+    ZZ.test_histograms_on_device()
+
+
+@pytest.mark.parametrize("cls", ["Stencil", "StreamingStencil"])
+def test_tiled_stencil_gpu_gate(device, monkeypatch, cls):
+    monkeypatch.setenv("PSB_JIT", "1")
+    ZZ.test_tiled_stencil_map(cls, "float64", 2, (37, 19, 150))
+
+
 # ---- run-time generated kernels next to the hand-written ones ------------------------------
 
 def test_generated_kernels_of_the_python_layer(device, monkeypatch):
