@@ -42,8 +42,18 @@ class TensorSystem:
             return False
         h = stepper.halo_shape
         hij = kwargs.get(self.h_name)
-        return (h in (2, 4) and hij is not None and hij.shape[-1] % 2 == 0
-                and self.nscalars in (1, 2))
+        if not (h in (2, 4) and hij is not None and hij.shape[-1] % 2 == 0
+                and self.nscalars in (1, 2)):
+            return False
+        # what cuTensorMapEncodeTiled needs (csrc/common.cu, encode_field_tensor_map): rows,
+        # planes and components that are multiples of 16 bytes (fp32: Nz + 2h a multiple
+        # of 4) and 16-byte aligned arrays; other layouts take the element-wise stage
+        es = hij.element_size()
+        Px, Py, Pz = hij.shape[-3:]
+        arrays = [hij, kwargs.get(self.dot_name)]
+        return ((Pz * es) % 16 == 0 and (Py * Pz * es) % 16 == 0
+                and (Px * Py * Pz * es) % 16 == 0
+                and all(t is not None and t.data_ptr() % 16 == 0 for t in arrays))
 
     def _run_fused(self, stepper, queue, kwargs, dt, A, B):
         from pystella_b200 import _kernels, fused

@@ -181,3 +181,68 @@ def example_run_oracle(p, ic, end_time):
     a, adot = state[0], state[1]
     constraint = abs(np.sqrt(8 * np.pi * a**2 / 3 / p["mpl"]**2 * total) * a / adot - 1)
     return nsteps, a, constraint, total
+
+
+def gw_stage_case(N, h, dtype, nstages, rng, to_device):
+    """Two coupled scalars + tensor sector under FusedStencilStage (config 4's stage) on the
+    lattice N: `nstages` LSRK54 stages through the public API against the oracle's scalar_rhs
+    + gw_rhs + lsrk_stage.  `to_device` uploads a NumPy array (a copy)."""
+    import pystella_b200 as ps
+    from test_gpu_api import _example_potential
+    tol = 1e-12 if dtype == np.float64 else 3e-5
+    pad = tuple(n + 2 * h for n in N)
+    dx = tuple(5 / n for n in N)
+    dt = 0.1 * min(dx)
+    potential, terms = _example_potential(mphi=1.0, gsq=0.3)
+    f0 = (0.2 * rng.standard_normal((2,) + pad)).astype(dtype)
+    d0 = (0.2 * rng.standard_normal((2,) + pad)).astype(dtype)
+    h0 = (1e-2 * rng.standard_normal((6,) + pad)).astype(dtype)
+    dh0 = (1e-2 * rng.standard_normal((6,) + pad)).astype(dtype)
+    a, hubble = 1.1, 0.3
+    F, D, Hh, DH = (x.astype(np.float64) for x in (f0, d0, h0, dh0))
+    kF, kD, kH, kDH = (np.zeros_like(x) for x in (F, D, Hh, DH))
+    A_, B_, _ = O.LSRK_TABLES["LowStorageRK54"]
+    for s_ in range(nstages):
+        lapf, grd, laph = [], [], []
+        for n in range(2):
+            O.share_halos(F[n], h)
+            lapf.append(O.laplacian(F[n], h, dx))
+            grd.append(O.gradient(F[n], h, dx))
+        for c in range(6):
+            O.share_halos(Hh[c], h)
+            laph.append(O.laplacian(Hh[c], h, dx))
+        Fi = [O.interior(F[n], h) for n in range(2)]
+        Di = [O.interior(D[n], h) for n in range(2)]
+        Hi = [O.interior(Hh[c], h) for c in range(6)]
+        DHi = [O.interior(DH[c], h) for c in range(6)]
+        rhs = [np.array(r) for r in O.scalar_rhs(Fi, Di, lapf, a, hubble, terms)]
+        rhs += [np.array(r) for r in O.gw_rhs(DHi, laph, np.stack(grd), hubble)]
+        unk, tmp = [], []
+        for n in range(2):
+            unk += [Fi[n], Di[n]]
+            tmp += [O.interior(kF[n], h), O.interior(kD[n], h)]
+        for c in range(6):
+            unk += [Hi[c], DHi[c]]
+            tmp += [O.interior(kH[c], h), O.interior(kDH[c], h)]
+        O.lsrk_stage(A_[s_], B_[s_], dt, unk, tmp, rhs)
+
+    decomp = ps.DomainDecomposition((1, 1, 1), h, N)
+    scalar_sector = ps.ScalarSector(2, potential=potential)
+    gw_sector = ps.TensorPerturbationSector([scalar_sector])
+    stepper = ps.LowStorageRK54([scalar_sector, gw_sector], halo_shape=h, rank_shape=N, dt=dt,
+                                MapKernel=ps.FusedStencilStage, dx=dx, decomp=decomp)
+    derivs = ps.FiniteDifferencer(decomp, h, dx, rank_shape=N)
+    f, dfdt, hij, dhijdt = (to_device(x) for x in (f0, d0, h0, dh0))
+    lap_f = torch.zeros((2,) + N, dtype=f.dtype, device=f.device)
+    dfdx = torch.zeros((2, 3) + N, dtype=f.dtype, device=f.device)
+    lap_hij = torch.zeros((6,) + N, dtype=f.dtype, device=f.device)
+    for s_ in range(nstages):
+        derivs(None, fx=f, lap=lap_f, grd=dfdx)
+        derivs(None, fx=hij, lap=lap_hij)
+        stepper(s_, queue=None, a=np.array(a), hubble=np.array(hubble), f=f, dfdt=dfdt,
+                dfdx=dfdx, lap_f=lap_f, hij=hij, dhijdt=dhijdt, lap_hij=lap_hij,
+                filter_args=True)
+    for got, ref in ((f, F), (dfdt, D), (hij, Hh), (dhijdt, DH)):
+        for c in range(ref.shape[0]):
+            assert scale_err(O.interior(got[c].cpu().numpy(), h), O.interior(ref[c], h)) < tol, \
+                (N, h, dtype, nstages, c)

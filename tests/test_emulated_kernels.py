@@ -229,6 +229,33 @@ def test_two_scalars_plus_fused_tensor_sector(device, dtype, tol):
     API.test_two_scalars_plus_gw_sector(True, dtype, tol)
 
 
+@pytest.mark.parametrize("seed", range(8))
+def test_fused_tensor_stage_random_sweep(device, seed):
+    """Config 4's stage (two coupled scalars + tensor sector under FusedStencilStage) on
+    random lattices: radius 2 or 4, fp64 / fp32, even and odd row lengths, rows that are and
+    are not multiples of 16 bytes (the latter take the element-wise tensor stage fed by
+    FiniteDifferencer), two or three RK stages -- against the oracle's scalar_rhs + gw_rhs +
+    lsrk_stage (tests/helpers.py::gw_stage_case, as tests/test_gpu_api.py does for one
+    lattice).  This sweep found that fp32 lattices with Nz + 2h not a multiple of 4 raised
+    instead of taking the element-wise stage (gw._fused_ok; fixed)."""
+    from helpers import gw_stage_case
+    rng = np.random.default_rng(7000 + seed)
+    h = int(rng.choice([2, 2, 4]))
+    N = (int(rng.integers(h, 14)), int(rng.integers(h, 14)), int(rng.integers(max(h, 4), 40)))
+    if rng.random() < 0.75:
+        N = (N[0], N[1], N[2] + N[2] % 2)
+    dtype = np.float64 if seed % 2 == 0 else np.float32
+    gw_stage_case(N, h, dtype, int(rng.integers(2, 4)), rng,
+                  lambda a: torch.from_numpy(np.array(a, copy=True, order="C")))
+
+
+@pytest.mark.parametrize("N, h, dtype", [((10, 12, 18), 2, np.float32),
+                                         ((10, 12, 16), 2, np.float32),
+                                         ((8, 9, 14), 4, np.float64)])
+def test_config4_stage_gpu_gate_on_rows_without_tma_description(device, N, h, dtype):
+    ZZ.test_config4_stage_on_rows_without_tma_description(N, h, dtype)
+
+
 def test_fused_two_fields_and_generic_dict(device):
     API.test_scalar_sector_two_fields(True, np.float64, 1e-12)
     API.test_generic_dict_with_friction_matches_sector()

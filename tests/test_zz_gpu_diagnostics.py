@@ -308,3 +308,17 @@ def test_fused_two_fields_on_non_tma_layouts(h, N):
         for i in range(2):
             assert scale_err(O.interior(got[i].cpu().numpy(), h),
                              O.interior(ref[i], h)) < 1e-12
+
+
+@pytest.mark.parametrize("N, h, dtype", [
+    ((10, 12, 18), 2, np.float32),     # Nz + 2h = 22: rows of 88 B, no tensor map possible
+    ((10, 12, 16), 2, np.float32),     # Nz + 2h = 20: 80 B rows, tensor map possible
+    ((8, 9, 14), 4, np.float64),       # odd Ny, radius 4
+])
+def test_config4_stage_on_rows_without_tma_description(N, h, dtype):
+    """Two scalars + tensor sector under FusedStencilStage on lattices whose rows are not
+    multiples of 16 bytes in fp32: the fused tensor stage cannot be described to TMA and the
+    element-wise tensor stage must serve them (found by the randomised sweep on the CPU
+    execution model: the stepper used to raise "layout not describable by TMA")."""
+    from helpers import gw_stage_case
+    gw_stage_case(N, h, dtype, 3, np.random.default_rng(77), to_dev)
