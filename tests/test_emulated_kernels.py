@@ -388,6 +388,70 @@ def test_config4_stage_gpu_gate_on_rows_without_tma_description(device, N, h, dt
     ZZ.test_config4_stage_on_rows_without_tma_description(N, h, dtype)
 
 
+@pytest.mark.parametrize("seed", range(8))
+def test_fused_stepper_api_random_sweep(device, monkeypatch, seed):
+    """The fused stepper through the public API on random systems: radius 1..4, one to three
+    fields, quadratic / quartic / coupled potentials, generated instances on or off, random
+    extents, fp64 / fp32, one or two steps; between steps the field is left alone, replaced by
+    a clone (a new tensor: halos must be refilled), rescaled in place (halos stale) or is a
+    view into a larger tensor.  Against the oracle's schedule.  (110 cases of the same generator
+    were run once while this was written: no failure.)"""
+    import oracle as O
+    import pystella_b200 as ps
+    rng = np.random.default_rng(9000 + seed)
+    pots = {1: [([(0.5, (2,))], lambda f: f[0]**2 / 2),
+                ([(0.5, (2,)), (0.25, (4,))], lambda f: f[0]**2 / 2 + f[0]**4 / 4)],
+            2: [([(0.5, (2, 0)), (0.5, (0, 2)), (0.5, (2, 2))],
+                 lambda f: f[0]**2 / 2 + f[1]**2 / 2 + f[0]**2 * f[1]**2 / 2),
+                ([(0.5, (2, 0)), (0.3, (0, 2))], lambda f: f[0]**2 / 2 + 0.3 * f[1]**2)],
+            3: [([(0.5, (2, 0, 0)), (0.5, (0, 2, 0)), (0.1, (1, 1, 1))],
+                 lambda f: f[0]**2 / 2 + f[1]**2 / 2 + 0.1 * f[0] * f[1] * f[2])]}
+    h = int(rng.choice([1, 2, 2, 2, 3, 4]))
+    n = int(rng.choice([1, 1, 2, 3]))
+    N = (int(rng.integers(h, 20)), int(rng.integers(h, 16)), int(rng.integers(max(h, 2), 50)))
+    if rng.random() < 0.7:
+        N = (N[0], N[1], N[2] + N[2] % 2)
+    dtype = np.float64 if rng.random() < 0.7 else np.float32
+    monkeypatch.setenv("PSB_JIT", "1" if rng.random() < 0.5 else "0")
+    terms, pot = pots[n][int(rng.integers(len(pots[n])))]
+    nsteps = int(rng.integers(1, 3))
+    edit = str(rng.choice(["none", "clone", "scale", "view"]))
+    pad = tuple(m + 2 * h for m in N)
+    dx = tuple(5 / m for m in N)
+    dt = 0.1 * min(dx)
+    f0 = (0.2 + 1e-2 * rng.standard_normal((n,) + pad)).astype(dtype)
+    d0 = (-0.1 + 1e-2 * rng.standard_normal((n,) + pad)).astype(dtype)
+    fr, dr = f0.astype(np.float64), d0.astype(np.float64)
+    kf, kd, lap = np.zeros_like(fr), np.zeros_like(fr), np.zeros((n,) + N)
+    stepper = ps.LowStorageRK54(ps.ScalarSector(n, potential=pot), halo_shape=h, dt=dt, dx=dx,
+                                decomp=ps.DomainDecomposition((1, 1, 1), h, N),
+                                MapKernel=ps.FusedStencilStage)
+    if edit == "view":
+        big = torch.zeros((n + 1,) + pad, dtype=torch.from_numpy(f0).dtype)
+        big[1:] = torch.from_numpy(f0)
+        f = big[1:]
+    else:
+        f = torch.from_numpy(f0.copy())
+    d = torch.from_numpy(d0.copy())
+    for step in range(nsteps):
+        for s_ in range(5):
+            O.reference_schedule_stage(s_, fr, dr, kf, kd, lap, h, dx, dt, a=1.05, hubble=0.2,
+                                       potential_terms=terms)
+            stepper(s_, f=f, dfdt=d, a=1.05, hubble=0.2)
+        if step + 1 < nsteps:
+            if edit == "clone":
+                f = f.clone()
+            elif edit == "scale":
+                f *= 1.5
+                fr *= 1.5
+    tol = 1e-12 if dtype == np.float64 else 3e-5
+    for i in range(n):
+        for got, ref in ((f, fr), (d, dr)):
+            g = O.interior(got[i].numpy().astype(np.float64), h)
+            r = O.interior(ref[i], h)
+            assert np.max(np.abs(g - r)) / np.max(np.abs(r)) < tol, (N, h, n, dtype, edit, i)
+
+
 def test_fused_two_fields_and_generic_dict(device):
     API.test_scalar_sector_two_fields(True, np.float64, 1e-12)
     API.test_generic_dict_with_friction_matches_sector()
