@@ -349,6 +349,26 @@ def test_fused_stage_fp32(device, N, h, n, pot):
     KER.test_fused_stage_fp32(N, h, n, pot)
 
 
+@pytest.mark.parametrize("seed", [0, 1, 3, 6])
+def test_fused_tensor_stage_random_sweep(device, seed):
+    """Config 4's stage (two coupled scalars + tensor sector under FusedStencilStage) on
+    random lattices: radius 2 or 4, fp64 / fp32, even and odd row lengths, rows that are and
+    are not multiples of 16 bytes (the latter take the element-wise tensor stage fed by
+    FiniteDifferencer), two or three RK stages -- against the oracle's scalar_rhs + gw_rhs +
+    lsrk_stage (tests/helpers.py::gw_stage_case, as tests/test_gpu_api.py does for one
+    lattice).  This sweep found that fp32 lattices with Nz + 2h not a multiple of 4 raised
+    instead of taking the element-wise stage (gw._fused_ok; fixed)."""
+    from helpers import gw_stage_case
+    rng = np.random.default_rng(7000 + seed)
+    h = int(rng.choice([2, 2, 4]))
+    N = (int(rng.integers(h, 14)), int(rng.integers(h, 14)), int(rng.integers(max(h, 4), 40)))
+    if rng.random() < 0.75:
+        N = (N[0], N[1], N[2] + N[2] % 2)
+    dtype = np.float64 if seed % 2 == 0 else np.float32
+    gw_stage_case(N, h, dtype, int(rng.integers(2, 4)), rng,
+                  lambda a: torch.from_numpy(np.array(a, copy=True, order="C")))
+
+
 @pytest.mark.parametrize("N, h, dtype", [((10, 12, 18), 2, np.float32)])
 def test_config4_stage_gpu_gate_on_rows_without_tma_description(device, N, h, dtype):
     ZZ.test_config4_stage_on_rows_without_tma_description(N, h, dtype)
